@@ -1,0 +1,207 @@
+/*
+ * libqie — C ABI of the B200-native MMDiT denoise step (Qwen-Image-Edit-2509).
+ *
+ * This is the drop-in boundary for the ONE hot path of shi3z/Qwen-Image-Edit-StreamDiffusion:
+ * the `pipeline.transformer(...)` call (the attribute the reference itself swaps at
+ * benchmark_lightning_compile.py:89-93, test_compiled.py:39-43, benchmark_compile.py:102-106)
+ * plus the per-step true-CFG combine / FlowMatch-Euler update the diffusers pipeline runs
+ * around it (reached from server.py:137-153, qwen_realtime.py:247-255, webui_realtime.py:77-85).
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a CUDA device pointer unless the name says `host`.
+ *   - every entry point returns 0 (QIE_OK) or a negative qie_status; the text of the last error
+ *     of the calling thread is available from qie_last_error().  No exception crosses the ABI.
+ *   - all work is enqueued on the caller's stream (`stream` is a cudaStream_t passed as void*);
+ *     no entry point synchronises the device in the steady state, none allocates inside
+ *     qie_forward (CUDA-graph capturable).
+ *   - the library never frees caller memory; caller keeps weights/workspace alive.
+ *   - sm_100a only: on any other device qie_create returns QIE_EARCH.  There is no CPU path.
+ *
+ * Joint sequence layout used by all per-token entry points ("qie_seq"):
+ *   each batch element owns rows_per_batch = img_pad + txt_pad rows; rows [0,img_rows) are image
+ *   tokens (noise latents then reference-image latents, the order of `hidden_states`), rows
+ *   [img_pad, img_pad+txt_rows) are text tokens; img_pad/txt_pad are img_rows/txt_rows rounded up
+ *   to 128.  Attention is permutation invariant over keys, so [img; txt] is equivalent to the
+ *   reference's cat([txt, img]) once each token carries its own RoPE row.
+ */
+#ifndef QIE_H_
+#define QIE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QIE_ABI_VERSION 1
+
+typedef enum qie_status {
+    QIE_OK = 0,
+    QIE_EINVAL = -1, /* bad argument */
+    QIE_ESHAPE = -2, /* unsupported shape */
+    QIE_ECUDA = -3,  /* CUDA runtime / driver error */
+    QIE_ENOMEM = -4, /* workspace too small */
+    QIE_EARCH = -5,  /* device is not sm_100 */
+    QIE_ESTATE = -6  /* weights not set etc. */
+} qie_status;
+
+typedef struct qie_handle qie_handle;
+
+/* replaces: QwenImageTransformer2DModel.config (diffusers transformer/config.json) */
+typedef struct qie_model_cfg {
+    int num_layers;  /* 60 */
+    int num_heads;   /* 24 */
+    int head_dim;    /* 128 (the only supported value) */
+    int in_channels; /* 64 */
+    int out_dim;     /* patch_size^2 * out_channels = 64 */
+    int joint_dim;   /* 3584 */
+    int rope_axes[3]; /* 16,56,56 ; sums to head_dim */
+} qie_model_cfg;
+
+typedef struct qie_seq {
+    int batch;
+    int img_rows; /* valid image tokens per batch element */
+    int txt_rows; /* valid text tokens per batch element */
+    int img_pad;  /* img_rows rounded up to 128 */
+    int txt_pad;  /* txt_rows rounded up to 128 */
+} qie_seq;
+
+/* weights of one QwenImageTransformerBlock; index [0] = image stream, [1] = text stream.
+ * All matrices are nn.Linear layout [out, in] row-major bf16 (or e4m3 when the *_w8 pointers are
+ * set); biases, norm weights and dequant scales are fp32.  state_dict keys: SURVEY App. A.10. */
+typedef struct qie_block_weights {
+    const void* qkv_w[2];          /* [3D, D]  to_q|to_k|to_v  /  add_q_proj|add_k_proj|add_v_proj */
+    const float* qkv_b[2];         /* [3D] */
+    const float* q_norm_w[2];      /* [128] norm_q / norm_added_q */
+    const float* k_norm_w[2];      /* [128] norm_k / norm_added_k */
+    const void* out_w[2];          /* [D, D]   to_out.0 / to_add_out */
+    const float* out_b[2];
+    const void* ff1_w[2];          /* [4D, D]  {img,txt}_mlp.net.0.proj */
+    const float* ff1_b[2];
+    const void* ff2_w[2];          /* [D, 4D]  {img,txt}_mlp.net.2 */
+    const float* ff2_b[2];
+    /* optional FP8 (e4m3) copies with per-output-channel fp32 scales; NULL = bf16 path */
+    const void* qkv_w8[2];  const float* qkv_ws[2];
+    const void* out_w8[2];  const float* out_ws[2];
+    const void* ff1_w8[2];  const float* ff1_ws[2];
+    const void* ff2_w8[2];  const float* ff2_ws[2];
+} qie_block_weights;
+
+typedef struct qie_weights {
+    const void* img_in_w;  const float* img_in_b;      /* [D, in_channels] */
+    const float* txt_norm_w;                           /* [joint_dim] */
+    const void* txt_in_w;  const float* txt_in_b;      /* [D, joint_dim] */
+    const void* t1_w;      const float* t1_b;          /* time_text_embed.timestep_embedder.linear_1 [D,256] */
+    const void* t2_w;      const float* t2_b;          /* ...linear_2 [D,D] */
+    const void* mod_w;     const float* mod_b;         /* all img_mod.1/txt_mod.1 stacked: [L][2][6D, D] bf16, [L][2][6D] */
+    const void* norm_out_w; const float* norm_out_b;   /* norm_out.linear [2D, D] */
+    const void* proj_out_w; const float* proj_out_b;   /* [out_dim, D] */
+    const qie_block_weights* blocks;                   /* HOST array of num_layers entries (copied) */
+} qie_weights;
+
+/* ---- library ---- */
+int qie_version(void);
+const char* qie_last_error(void);
+int qie_device_sm_count(void);
+
+/* ---- model handle: replaces constructing/holding `pipeline.transformer` (server.py:66-69) ---- */
+int qie_create(const qie_model_cfg* cfg, int device, qie_handle** out);
+int qie_destroy(qie_handle* h);
+int qie_set_weights(qie_handle* h, const qie_weights* w);
+/* 0 = bf16 GEMMs, 1 = FP8 e4m3 W8A8 GEMMs (needs the *_w8 pointers); replaces int8_linear.py /
+ * cublaslt_int8.py / triton_int8_gemm.py named at README.md:136-141 */
+int qie_set_precision(qie_handle* h, int mode);
+/* tuning/debug knobs outside the reference surface: key 0 = fuse QK-norm+RoPE into the QKV GEMM epilogue (default 1),
+ * key 1 = attention kernel variant */
+int qie_set_option(qie_handle* h, int key, int value);
+/* host helper: pad a (img_rows, txt_rows) pair into the joint layout */
+int qie_make_seq(int batch, int img_rows, int txt_rows, qie_seq* out);
+size_t qie_workspace_bytes(const qie_handle* h, const qie_seq* seq);
+
+/* replaces: QwenImageTransformer2DModel.forward(hidden_states, encoder_hidden_states, timestep,
+ *           img_shapes, txt_seq_lens), called by the pipeline loop.
+ *   hidden   bf16 [B, img_rows, in_channels]        enc  bf16 [B, txt_rows, joint_dim]
+ *   timestep fp32 [B] device (sigma in [0,1], i.e. already /1000 as the pipeline passes it)
+ *   img_shapes_host  int[n_img*3] (f,h,w) of ONE batch element (QwenEmbedRope uses element 0)
+ *   out      bf16 [B, img_rows, out_dim]
+ *   n_blocks < 0 runs all layers (a positive value truncates the stack — baseline/bench aid). */
+int qie_forward(qie_handle* h, const void* hidden, const void* enc, const float* timestep,
+                const int* img_shapes_host, int n_img, const qie_seq* seq, void* out,
+                void* workspace, size_t workspace_bytes, int n_blocks, void* stream);
+
+/* replaces: the true-CFG combine + norm rescale of QwenImageEditPlusPipeline.__call__ and
+ * FlowMatchEulerDiscreteScheduler.step, fused; v_uncond may be NULL (cond-only).
+ *   v_* bf16 rows of `v_row_stride` elements, first `channels` used; latents bf16 [rows, channels] in/out. */
+int qie_cfg_euler_step(const void* v_cond, const void* v_uncond, void* latents, float true_cfg_scale,
+                       float sigma, float sigma_next, int batch, int tokens, int channels,
+                       int v_tokens_stride, void* stream);
+
+/* host-only: FlowMatchEulerDiscreteScheduler.set_timesteps (dynamic exponential shift + terminal stretch);
+ * writes num_steps+1 sigmas.  replaces scheduler.set_timesteps(sigmas, mu) */
+int qie_flowmatch_sigmas(int num_steps, int image_seq_len, float* sigmas_host);
+/* host-only: QwenEmbedRope table in the joint layout: out_host float[rows_per_batch*64*2] (cos,sin) */
+int qie_rope_table_host(const qie_model_cfg* cfg, const int* img_shapes_host, int n_img, const qie_seq* seq,
+                        float* out_host);
+
+/* ---- per-kernel entry points (unit tests, profiling) ---- */
+enum qie_epilogue {
+    QIE_EPI_BF16 = 0,          /* out_bf16 = acc + bias                                  */
+    QIE_EPI_GELU_BF16 = 1,     /* out_bf16 = gelu_tanh(acc + bias)                       */
+    QIE_EPI_F32 = 2,           /* out_f32  = acc + bias                                  */
+    QIE_EPI_GATE_RESID_F32 = 3,/* out_f32 += gate[b, stream, n] * (acc + bias)           */
+    QIE_EPI_QKV_NORM_ROPE = 4  /* bf16 qkv with per-head RMSNorm + RoPE on q,k columns   */
+};
+typedef struct qie_gemm_args {
+    const void* a;            /* bf16 (or e4m3) [rows, K] */
+    int a_compact;            /* 0: A rows are joint-layout rows; 1: A is [B*seg_pad, K] of the single enabled stream */
+    const void* w[2];         /* per-stream weights [N, K] */
+    const float* bias[2];     /* per-stream bias [N] (may be NULL) */
+    void* out;                /* [rows, ldo] */
+    int out_compact;          /* same meaning as a_compact for the output rows */
+    int ldo;                  /* output leading dimension (elements) */
+    int N, K;
+    int streams;              /* bit0: image rows, bit1: text rows */
+    int epilogue;             /* enum qie_epilogue */
+    const float* gate;        /* GATE_RESID: gate vectors, element (b, stream, n) at gate[b*gate_bstride + stream*gate_sstride + n] */
+    long long gate_bstride, gate_sstride;
+    const float* rope;        /* QKV_NORM_ROPE: [rows_per_batch, 64, 2] */
+    const float* qk_norm_w[2][2]; /* QKV_NORM_ROPE: [stream][q/k] -> [128] */
+    int fp8;                  /* 1: a / w are e4m3, a_scale [rows] and w_scale[stream][N] dequantise in the epilogue */
+    const float* a_scale;
+    const float* w_scale[2];
+    int block_n;              /* 0 = auto */
+} qie_gemm_args;
+int qie_gemm(const qie_gemm_args* args, const qie_seq* seq, void* stream);
+
+/* joint attention over all valid rows of each batch element; qkv bf16 [rows, 3*H*128] (q|k|v), q and k already
+ * normed + roped; out bf16 [rows, H*128].  replaces F.scaled_dot_product_attention in
+ * QwenDoubleStreamAttnProcessor2_0. variant: 0 default. */
+int qie_attn_fwd(const void* qkv, void* out, const qie_seq* seq, int num_heads, int variant, void* stream);
+
+/* LayerNorm(no affine, eps) + x*(1+scale)+shift; x fp32 [rows, D] -> out bf16 [rows, D].
+ * shift/scale for (b, stream) at mod[b*mod_bstride + stream*mod_sstride + {shift_off,scale_off} + c].
+ * if out8/out_scale non-NULL also emits e4m3 rows with per-row scale (for the FP8 GEMMs). */
+int qie_ln_modulate(const float* x, const float* mod, long long mod_bstride, long long mod_sstride, int shift_off,
+                    int scale_off, void* out, void* out8, float* out_scale, int D, float eps, const qie_seq* seq,
+                    void* stream);
+/* y[b, n] = bias[n] + sum_k act(x[b,k]) * W[n,k]; act: 0 none, 1 SiLU. W bf16 [N,K], x/y fp32. batch<=8 */
+int qie_gemv(const float* x, const void* w, const float* bias, float* y, int batch, long long N, int K, int act,
+             void* stream);
+/* sinusoidal timestep projection (Timesteps(256, flip_sin_to_cos, scale=1000)): t fp32 [B] -> out fp32 [B,256] */
+int qie_timestep_proj(const float* t, float* out, int batch, int round_bf16, void* stream);
+/* per-head RMSNorm(weight) + interleaved-pair RoPE, in place on the q and k column blocks of qkv */
+int qie_qk_norm_rope(void* qkv, const float* rope, const float* const* norm_w /* [2 streams][2 q,k] */,
+                     int num_heads, float eps, const qie_seq* seq, void* stream);
+/* RMSNorm(weight) over rows: x bf16 [B, n, D] -> out bf16 [B, n_pad, D] (pad rows zero) */
+int qie_rmsnorm_pack(const void* x, const float* w, void* out, int batch, int n, int n_pad, int D, float eps,
+                     void* stream);
+/* copy [B, n, C] bf16 -> [B, n_pad, C] with zero pad rows */
+int qie_pack_rows(const void* x, void* out, int batch, int n, int n_pad, int C, void* stream);
+/* per-row dynamic e4m3 quantisation: x bf16 [rows, K] -> q e4m3 [rows,K], scale fp32 [rows] */
+int qie_quant_rows_e4m3(const void* x, void* q, float* scale, long long rows, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QIE_H_ */

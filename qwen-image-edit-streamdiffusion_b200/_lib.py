@@ -1,0 +1,144 @@
+"""ctypes binding of libqie.so (the C ABI declared in include/qie.h).
+
+The product path has NO fallback: if the shared library is missing, or a call fails, we raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("QIE_LIB", _HERE / "libqie.so"))
+
+
+class QieError(RuntimeError):
+    pass
+
+
+class ModelCfg(C.Structure):
+    _fields_ = [("num_layers", C.c_int), ("num_heads", C.c_int), ("head_dim", C.c_int),
+                ("in_channels", C.c_int), ("out_dim", C.c_int), ("joint_dim", C.c_int),
+                ("rope_axes", C.c_int * 3)]
+
+
+class Seq(C.Structure):
+    _fields_ = [("batch", C.c_int), ("img_rows", C.c_int), ("txt_rows", C.c_int),
+                ("img_pad", C.c_int), ("txt_pad", C.c_int)]
+
+    @property
+    def rows_per_batch(self) -> int:
+        return self.img_pad + self.txt_pad
+
+
+_P2 = C.c_void_p * 2
+
+
+class BlockWeights(C.Structure):
+    _fields_ = [("qkv_w", _P2), ("qkv_b", _P2), ("q_norm_w", _P2), ("k_norm_w", _P2),
+                ("out_w", _P2), ("out_b", _P2), ("ff1_w", _P2), ("ff1_b", _P2),
+                ("ff2_w", _P2), ("ff2_b", _P2),
+                ("qkv_w8", _P2), ("qkv_ws", _P2), ("out_w8", _P2), ("out_ws", _P2),
+                ("ff1_w8", _P2), ("ff1_ws", _P2), ("ff2_w8", _P2), ("ff2_ws", _P2)]
+
+
+class Weights(C.Structure):
+    _fields_ = [("img_in_w", C.c_void_p), ("img_in_b", C.c_void_p), ("txt_norm_w", C.c_void_p),
+                ("txt_in_w", C.c_void_p), ("txt_in_b", C.c_void_p),
+                ("t1_w", C.c_void_p), ("t1_b", C.c_void_p), ("t2_w", C.c_void_p), ("t2_b", C.c_void_p),
+                ("mod_w", C.c_void_p), ("mod_b", C.c_void_p),
+                ("norm_out_w", C.c_void_p), ("norm_out_b", C.c_void_p),
+                ("proj_out_w", C.c_void_p), ("proj_out_b", C.c_void_p),
+                ("blocks", C.POINTER(BlockWeights))]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("a_compact", C.c_int), ("w", _P2), ("bias", _P2),
+                ("out", C.c_void_p), ("out_compact", C.c_int), ("ldo", C.c_int),
+                ("N", C.c_int), ("K", C.c_int), ("streams", C.c_int), ("epilogue", C.c_int),
+                ("gate", C.c_void_p), ("gate_bstride", C.c_longlong), ("gate_sstride", C.c_longlong),
+                ("rope", C.c_void_p), ("qk_norm_w", (C.c_void_p * 2) * 2),
+                ("fp8", C.c_int), ("a_scale", C.c_void_p), ("w_scale", _P2), ("block_n", C.c_int)]
+
+
+EPI_BF16, EPI_GELU_BF16, EPI_F32, EPI_GATE_RESID_F32, EPI_QKV_NORM_ROPE = range(5)
+
+# every symbol include/qie.h declares: name -> (restype, argtypes)
+_vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+SYMBOLS = {
+    "qie_version": (_i, []),
+    "qie_last_error": (C.c_char_p, []),
+    "qie_device_sm_count": (_i, []),
+    "qie_create": (_i, [C.POINTER(ModelCfg), _i, C.POINTER(_vp)]),
+    "qie_destroy": (_i, [_vp]),
+    "qie_set_weights": (_i, [_vp, C.POINTER(Weights)]),
+    "qie_set_precision": (_i, [_vp, _i]),
+    "qie_set_option": (_i, [_vp, _i, _i]),
+    "qie_make_seq": (_i, [_i, _i, _i, C.POINTER(Seq)]),
+    "qie_workspace_bytes": (C.c_size_t, [_vp, C.POINTER(Seq)]),
+    "qie_forward": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_i), _i, C.POINTER(Seq), _vp, _vp, C.c_size_t, _i, _vp]),
+    "qie_cfg_euler_step": (_i, [_vp, _vp, _vp, _f, _f, _f, _i, _i, _i, _i, _vp]),
+    "qie_flowmatch_sigmas": (_i, [_i, _i, C.POINTER(_f)]),
+    "qie_rope_table_host": (_i, [C.POINTER(ModelCfg), C.POINTER(_i), _i, C.POINTER(Seq), C.POINTER(_f)]),
+    "qie_gemm": (_i, [C.POINTER(GemmArgs), C.POINTER(Seq), _vp]),
+    "qie_attn_fwd": (_i, [_vp, _vp, C.POINTER(Seq), _i, _i, _vp]),
+    "qie_ln_modulate": (_i, [_vp, _vp, _ll, _ll, _i, _i, _vp, _vp, _vp, _i, _f, C.POINTER(Seq), _vp]),
+    "qie_gemv": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp]),
+    "qie_timestep_proj": (_i, [_vp, _vp, _i, _i, _vp]),
+    "qie_qk_norm_rope": (_i, [_vp, _vp, C.POINTER(_vp), _i, _f, C.POINTER(Seq), _vp]),
+    "qie_rmsnorm_pack": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "qie_pack_rows": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "qie_quant_rows_e4m3": (_i, [_vp, _vp, _vp, _ll, _i, _vp]),
+}
+
+_lib = None
+
+
+def build_library(verbose: bool = False) -> Path:
+    """Compile csrc/*.cu for sm_100a into libqie.so (nvcc cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-C", str(_HERE / "csrc"), "-j4"], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout[-4000:], res.stderr[-4000:])
+    if res.returncode != 0:
+        raise QieError("building libqie.so failed")
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """Load libqie.so; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise QieError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU / PyTorch fallback for the hot path)")
+        l = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(l, name)   # AttributeError if the ABI lost a symbol
+            fn.restype, fn.argtypes = res, args
+        if l.qie_version() != 1:
+            raise QieError("libqie ABI version mismatch")
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().qie_last_error().decode(errors="replace")
+        raise QieError(f"{what or 'libqie'} failed with status {rc}: {msg}")
+
+
+def make_seq(batch: int, img_rows: int, txt_rows: int) -> Seq:
+    s = Seq()
+    check(lib().qie_make_seq(batch, img_rows, txt_rows, C.byref(s)), "qie_make_seq")
+    return s
+
+
+def ptr(t) -> C.c_void_p:
+    """device/host pointer of a torch tensor (None -> NULL)."""
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def cur_stream() -> C.c_void_p:
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

