@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""Headline benchmark: edited 1024x1024 images / s, 2-step Lightning schedule (BASELINE.json configs[1]).
+
+One "step" = one edited image = the hot path of the reference over one synthetic input:
+2 x QwenImageTransformer2DModel forward (60 blocks, 8192 image + 256 text tokens) + 2 x fused CFG/Euler update.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (libqie.so)
+  python bench.py --impl reference ...                      # the reference's CPU path (the fp32 oracle restatement of
+                                                            # the diffusers transformer; diffusers itself is not installable)
+Launch with torchrun for N > 1 (one rank per GPU).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "edited_1024x1024_images_per_s_2step_lightning"
+UNIT = "img/s"
+IMG_SHAPES = [[(1, 64, 64), (1, 64, 64)]]     # noise latents + one 1024^2 reference image
+N_NOISE, N_IMG_TOK, T_TXT = 4096, 8192, 256
+STEPS_PER_IMAGE = 2
+
+
+def flops_per_forward(cfg_layers=60, D=3072, H=24, S_i=N_IMG_TOK, T=T_TXT, B=1):
+    """per block 2*D*(3D + D + 2*FF)*S linear + 4*S^2*d_h*H attention (+ tiny top)."""
+    S = S_i + T
+    lin = 2.0 * D * (3 * D + D + 8 * D) * S
+    att = 4.0 * S * S * 128 * H
+    return B * cfg_layers * (lin + att)
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get("bf16_tflops_sustained", 1404.4), d.get("bf16_tflops", 1638.8), d.get("hbm_gbs", 6556.2), "measured"
+    return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in self.rows if len(r) >= 7)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the fp32 oracle (restated diffusers transformer) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step_factory(max_seconds_per_sample: float = 8.0):
+    """Returns (run_sample, scale, description): run_sample() executes ONE full-width transformer block of the oracle in
+    fp32 on `tokens` joint tokens; `scale` converts its time into seconds per edited image by FLOP proportion."""
+    from oracle import qwen_mmdit_ref as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = R.FULL_CONFIG
+    D = cfg.inner_dim
+    blk = R.QwenImageTransformerBlock(D, cfg.num_attention_heads, cfg.attention_head_dim).eval()
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.normal_(0, 0.02)
+    rope = R.QwenEmbedRope(10000, list(cfg.axes_dims_rope), scale_rope=True)
+
+    def make(n_side, t_txt):
+        shapes = [(1, n_side, n_side), (1, n_side, n_side)]
+        fr = rope(shapes, [t_txt])
+        s_i = 2 * n_side * n_side
+        g = torch.Generator().manual_seed(0)
+        return (torch.randn(1, s_i, D, generator=g), torch.randn(1, t_txt, D, generator=g),
+                torch.randn(1, D, generator=g), fr, s_i)
+
+    def block_flops(s_i, t):
+        S = s_i + t
+        return 2.0 * D * 12 * D * S + 4.0 * S * S * 128 * cfg.num_attention_heads
+
+    # calibrate on a quarter-size sequence, then pick the largest sample that fits the per-step budget
+    h, e, temb, fr, s_i = make(32, 64)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        blk(h, e, temb, fr)
+        t_cal = time.perf_counter() - t0
+    rate = block_flops(s_i, 64) / t_cal
+    side, t_txt = 64, T_TXT
+    while side > 16 and block_flops(2 * side * side, t_txt) / rate > max_seconds_per_sample:
+        side //= 2
+        t_txt = max(32, t_txt // 2)
+    h, e, temb, fr, s_i = make(side, t_txt)
+    image_flops = STEPS_PER_IMAGE * flops_per_forward()
+    scale = image_flops / block_flops(s_i, t_txt)
+
+    def run_sample():
+        with torch.no_grad():
+            blk(h, e, temb, fr)
+
+    desc = (f"1 of 60 full-width (D=3072, 24 heads) fp32 oracle blocks on {s_i}+{t_txt} tokens per step; seconds per image "
+            f"extrapolated by algorithmic-FLOP ratio x{scale:.1f} (2 forwards x 60 blocks at 8192+256 tokens)")
+    return run_sample, scale, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    run_sample, scale, desc = cpu_reference_step_factory()
+    for _ in range(args.warmup):
+        run_sample()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run_sample()
+    dt = (time.perf_counter() - t0) / args.steps
+    sec_per_image = dt * scale
+    v = 1.0 / sec_per_image
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec_per_image * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n):
+    return {"workload": "Qwen-Image-Edit-2509 MMDiT denoise (60 blocks, D=3072, 24 heads, random-init), 1024x1024 single-image "
+                        "edit, 2-step Lightning schedule, " + ("true-CFG 4.0 (cond+uncond)" if args.cfg else "cond-only"),
+            "img_tokens": N_IMG_TOK, "txt_tokens": T_TXT, "forwards_per_image": STEPS_PER_IMAGE * (2 if args.cfg else 1),
+            "layers": args.layers, "precision": args.precision,
+            "parallelism": f"dp{n}: one independent frame stream per GPU, weights replicated, no data-path collective",
+            "l2": "inputs larger than L2: 40.9 GB of weights + 0.6 GB of activations stream through the 126 MB L2 every forward"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import qie_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = qie_b200.QwenImageDiTConfig(num_layers=args.layers)
+    model = qie_b200.B200QwenImageTransformer2DModel.from_random(cfg, seed=0, device=dev)
+    if args.precision == "fp8":
+        model.set_precision("fp8")
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    lat = torch.randn(1, N_NOISE, 64, generator=g, device=dev).bfloat16()
+    img_lat = torch.randn(1, N_IMG_TOK - N_NOISE, 64, generator=g, device=dev).bfloat16()
+    cond = (torch.randn(1, T_TXT, cfg.joint_attention_dim, generator=g, device=dev) * 3).bfloat16()
+    unc = (torch.randn(1, T_TXT, cfg.joint_attention_dim, generator=g, device=dev) * 3).bfloat16() if args.cfg else None
+    host = {k: v.cpu().pin_memory() for k, v in (("lat", lat), ("img", img_lat), ("cond", cond))}
+    if unc is not None:
+        host["unc"] = unc.cpu().pin_memory()
+    out_host = torch.empty(lat.shape, dtype=torch.bfloat16).pin_memory()
+
+    def step_resident():
+        return qie_b200.run_denoise(model, lat, img_lat, cond, IMG_SHAPES, STEPS_PER_IMAGE, unc, 4.0)
+
+    def step_e2e():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        res = qie_b200.run_denoise(model, d["lat"], d["img"], d["cond"], IMG_SHAPES, STEPS_PER_IMAGE, d.get("unc"), 4.0)
+        out_host.copy_(res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller reads the edited latents
+        return res
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    L = qie_b200.lib()
+    with ClockSampler(local) as clk:
+        n0 = L.qie_launch_count()
+        ms_total = timed(step_resident, args.steps)
+        launches = L.qie_launch_count() - n0
+    clocks = clk.summary()
+    ms_step = ms_total / args.steps
+    value = world * 1e3 / ms_step
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = out_host.numel() * out_host.element_size()
+
+    # live per-kernel-class CUDA-event timing of the same step (events on the launching stream, inside qie_forward)
+    model.profile(True)
+    step_resident()
+    torch.cuda.synchronize()
+    model.read_profile()
+    for _ in range(args.steps):
+        step_resident()
+    torch.cuda.synchronize()
+    prof = model.read_profile()
+    model.profile(False)
+    sus, burst, hbm, which = peaks()
+    gm, at = prof["gemm"], prof["attention"]
+    gemm_tf = gm["work"] / (gm["ms"] * 1e-3) / 1e12 if gm["ms"] else 0.0
+    attn_tf = at["work"] / (at["ms"] * 1e-3) / 1e12 if at["ms"] else 0.0
+    tot_ms = sum(v["ms"] for v in prof.values())
+    roofline = {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 bf16, all linears of the step)",
+                "achieved": gemm_tf, "peak": sus, "unit": "TFLOP/s", "frac": gemm_tf / sus, "traffic": None,
+                "peak_source": f"{which} bf16_tflops_sustained (kernel timed inside a long step); burst {burst}",
+                "launches_per_step": gm["launches"] / args.steps, "avg_launch_ms": gm["ms"] / max(gm["launches"], 1),
+                "share_of_step": gm["ms"] / tot_ms if tot_ms else None,
+                "attention": {"achieved": attn_tf, "frac": attn_tf / sus, "share_of_step": at["ms"] / tot_ms if tot_ms else None,
+                              "avg_launch_ms": at["ms"] / max(at["launches"], 1)},
+                "adaln": {"achieved_gbs": prof["adaln"]["work"] / (prof["adaln"]["ms"] * 1e-3) / 1e9 if prof["adaln"]["ms"] else 0,
+                          "peak_gbs": hbm, "share_of_step": prof["adaln"]["ms"] / tot_ms if tot_ms else None},
+                "mod_gemv": {"achieved_gbs": prof["mod_gemv"]["work"] / (prof["mod_gemv"]["ms"] * 1e-3) / 1e9 if prof["mod_gemv"]["ms"] else 0,
+                             "peak_gbs": hbm, "share_of_step": prof["mod_gemv"]["ms"] / tot_ms if tot_ms else None},
+                "step_tflops": STEPS_PER_IMAGE * (2 if args.cfg else 1) * flops_per_forward(args.layers) / (ms_step * 1e-3) / 1e12}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        run_sample, scale, desc = cpu_reference_step_factory()
+        run_sample()
+        t0 = time.perf_counter()
+        n = 2
+        for _ in range(n):
+            run_sample()
+        sec_img = (time.perf_counter() - t0) / n * scale
+        cpu = {"value": 1.0 / sec_img, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": desc}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.precision == "bf16" else "fp8_e4m3(w8a8)+bf16", "data": "synthetic",
+                "config": workload_config(args, world), "clocks": clocks,
+                "e2e": {"value": world * 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "dit_forward_ms": ms_step / (STEPS_PER_IMAGE * (2 if args.cfg else 1))}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cfg", action="store_true", help="true-CFG (cond + uncond forwards per step)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp8"])
+    ap.add_argument("--layers", type=int, default=60)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

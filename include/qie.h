@@ -113,8 +113,12 @@ int qie_set_weights(qie_handle* h, const qie_weights* w);
  * cublaslt_int8.py / triton_int8_gemm.py named at README.md:136-141 */
 int qie_set_precision(qie_handle* h, int mode);
 /* tuning/debug knobs outside the reference surface: key 0 = fuse QK-norm+RoPE into the QKV GEMM epilogue (default 1),
- * key 1 = attention kernel variant */
+ * key 1 = attention kernel variant, key 2 = record CUDA events around every kernel class inside qie_forward */
 int qie_set_option(qie_handle* h, int key, int value);
+/* measurement aids: kernels launched by the library so far; event-timed ms / algorithmic work / launches per kernel
+ * class since the last read (class 0 GEMM [FLOP], 1 attention [FLOP], 2 adaLN [bytes], 3 modulation GEMV [bytes], 4 other) */
+unsigned long long qie_launch_count(void);
+int qie_profile_read(qie_handle* h, double* ms5, double* work5, int* launches5);
 /* host helper: pad a (img_rows, txt_rows) pair into the joint layout */
 int qie_make_seq(int batch, int img_rows, int txt_rows, qie_seq* out);
 size_t qie_workspace_bytes(const qie_handle* h, const qie_seq* seq);

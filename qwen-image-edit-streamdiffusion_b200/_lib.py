@@ -75,6 +75,8 @@ SYMBOLS = {
     "qie_set_weights": (_i, [_vp, C.POINTER(Weights)]),
     "qie_set_precision": (_i, [_vp, _i]),
     "qie_set_option": (_i, [_vp, _i, _i]),
+    "qie_launch_count": (C.c_ulonglong, []),
+    "qie_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i)]),
     "qie_make_seq": (_i, [_i, _i, _i, C.POINTER(Seq)]),
     "qie_workspace_bytes": (C.c_size_t, [_vp, C.POINTER(Seq)]),
     "qie_forward": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_i), _i, C.POINTER(Seq), _vp, _vp, C.c_size_t, _i, _vp]),

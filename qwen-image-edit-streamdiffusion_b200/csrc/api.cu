@@ -13,6 +13,7 @@
 namespace qie {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -94,6 +95,15 @@ struct qie_handle {
     std::vector<int> rope_key;
     float* d_small;         // tproj [8,256] | t1 [8,D] | temb [8,D] | mod [L,2? ...] see offsets
     size_t small_bytes;
+    // optional per-kernel-class CUDA-event timing (bench.py roofline): class 0 gemm, 1 attention, 2 adaLN, 3 gemv, 4 other
+    int profile;
+    struct Prof { int cls; cudaEvent_t a, b; double work; };
+    std::vector<Prof> prof;
+    std::vector<cudaEvent_t> ev_pool;
+    cudaEvent_t get_event() {
+        if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
 };
 
 using namespace qie;
@@ -203,6 +213,7 @@ extern "C" int qie_create(const qie_model_cfg* cfg, int device, qie_handle** out
     h->attn_variant = 0;
     h->d_rope = nullptr;
     h->rope_rows = 0;
+    h->profile = 0;
     // tproj [8,256] + t1 [8,D] + temb [8,D] + mod [8][L*2*6D] + final [8][2D]
     const size_t D = h->D, L = cfg->num_layers;
     h->small_bytes = sizeof(float) * 8 * (256 + 2 * D + L * 12 * D + 2 * D);
@@ -263,6 +274,7 @@ extern "C" int qie_set_option(qie_handle* h, int key, int value) {
     QIE_REQUIRE(h, QIE_EINVAL, "qie_set_option: null handle");
     if (key == 0) h->fuse_qk = value;
     else if (key == 1) h->attn_variant = value;
+    else if (key == 2) h->profile = value;
     else QIE_REQUIRE(false, QIE_EINVAL, "qie_set_option: unknown key %d", key);
     return QIE_OK;
 }
@@ -292,6 +304,33 @@ Ws carve(const qie_handle* h, const qie_seq* s) {
     w.total = o;
     return w;
 }
+}  // namespace
+
+extern "C" unsigned long long qie_launch_count(void) { return g_launches; }
+
+// sums the event-timed durations recorded since the last read; arrays of 5 classes (see qie_handle::profile)
+extern "C" int qie_profile_read(qie_handle* h, double* ms, double* work, int* launches) {
+    QIE_REQUIRE(h && ms && work && launches, QIE_EINVAL, "qie_profile_read: null pointer");
+    for (int i = 0; i < 5; ++i) { ms[i] = 0; work[i] = 0; launches[i] = 0; }
+    for (auto& p : h->prof) {
+        QIE_CUDA_OK(cudaEventSynchronize(p.b));
+        float t = 0.f;
+        QIE_CUDA_OK(cudaEventElapsedTime(&t, p.a, p.b));
+        ms[p.cls] += t; work[p.cls] += p.work; launches[p.cls] += 1;
+        h->ev_pool.push_back(p.a); h->ev_pool.push_back(p.b);
+    }
+    h->prof.clear();
+    return QIE_OK;
+}
+
+namespace {
+struct ProfScope {
+    qie_handle* h; cudaStream_t st; bool on; qie_handle::Prof p;
+    ProfScope(qie_handle* h_, cudaStream_t st_, int cls, double work) : h(h_), st(st_), on(h_->profile != 0) {
+        if (on) { p.cls = cls; p.work = work; p.a = h->get_event(); p.b = h->get_event(); cudaEventRecord(p.a, st); }
+    }
+    ~ProfScope() { if (on) { cudaEventRecord(p.b, st); h->prof.push_back(p); } }
+};
 }  // namespace
 
 extern "C" size_t qie_workspace_bytes(const qie_handle* h, const qie_seq* seq) {
@@ -335,6 +374,23 @@ extern "C" int qie_forward(qie_handle* h, const void* hidden, const void* enc, c
     const size_t rows = (size_t)B * rpb;
     const bool fp8 = h->precision == 1;
 
+    const double valid_rows = (double)B * (seq->img_rows + seq->txt_rows);
+    auto run_gemm = [&](qie_gemm_args& g) -> int {
+        const double mv = (double)B * (((g.streams & 1) ? seq->img_rows : 0) + ((g.streams & 2) ? seq->txt_rows : 0));
+        ProfScope ps(h, st, 0, 2.0 * mv * g.N * g.K);
+        return qie_gemm(&g, seq, st);
+    };
+    auto run_attn = [&]() -> int {
+        const double S = seq->img_rows + seq->txt_rows;
+        ProfScope ps(h, st, 1, 4.0 * S * S * 128.0 * h->cfg.num_heads * B);
+        return qie_attn_fwd(qkv, attn, seq, h->cfg.num_heads, h->attn_variant, st);
+    };
+    auto run_ln = [&](const float* mv, long long bs, long long ss, int sh, int sc, bool q8) -> int {
+        ProfScope ps(h, st, 2, valid_rows * D * 6.0);
+        return qie_ln_modulate(resid, mv, bs, ss, sh, sc, xm, q8 ? xm8 : nullptr, q8 ? xscale : nullptr, D, 1e-6f, seq,
+                               st);
+    };
+
     // ---- RoPE table (cached per shape key; host build + one H2D copy only when the shapes change) ----
     {
         std::vector<int> key(img_shapes_host, img_shapes_host + 3 * n_img);
@@ -366,7 +422,10 @@ extern "C" int qie_forward(qie_handle* h, const void* hidden, const void* enc, c
     if ((rc = qie_timestep_proj(timestep, tproj, B, 0, st))) return rc;
     if ((rc = qie_gemv(tproj, h->w.t1_w, h->w.t1_b, t1, B, D, 256, 0, st))) return rc;
     if ((rc = qie_gemv(t1, h->w.t2_w, h->w.t2_b, temb, B, D, D, 1, st))) return rc;
-    if (nb > 0 && (rc = qie_gemv(temb, h->w.mod_w, h->w.mod_b, mod, B, modN, D, 1, st))) return rc;
+    if (nb > 0) {
+        ProfScope ps(h, st, 3, (double)modN * D * 2);
+        if ((rc = qie_gemv(temb, h->w.mod_w, h->w.mod_b, mod, B, modN, D, 1, st))) return rc;
+    }
     if ((rc = qie_gemv(temb, h->w.norm_out_w, h->w.norm_out_b, fin, B, 2 * D, D, 1, st))) return rc;
     // mod row for (b, layer l, stream s): mod + b*modN + (l*2+s)*6D, chunks [shift1|scale1|gate1|shift2|scale2|gate2]
 
@@ -378,11 +437,11 @@ extern "C" int qie_forward(qie_handle* h, const void* hidden, const void* enc, c
         qie_gemm_args g{};
         g.a = xin; g.a_compact = 1; g.w[0] = h->w.img_in_w; g.bias[0] = h->w.img_in_b;
         g.out = resid; g.ldo = D; g.N = D; g.K = h->cfg.in_channels; g.streams = 1; g.epilogue = QIE_EPI_F32;
-        if ((rc = qie_gemm(&g, seq, st))) return rc;
+        if ((rc = run_gemm(g))) return rc;
         qie_gemm_args t{};
         t.a = xtxt; t.a_compact = 1; t.w[1] = h->w.txt_in_w; t.bias[1] = h->w.txt_in_b;
         t.out = resid; t.ldo = D; t.N = D; t.K = h->cfg.joint_dim; t.streams = 2; t.epilogue = QIE_EPI_F32;
-        if ((rc = qie_gemm(&t, seq, st))) return rc;
+        if ((rc = run_gemm(t))) return rc;
     }
 
     // ---- transformer blocks ----
@@ -390,8 +449,7 @@ extern "C" int qie_forward(qie_handle* h, const void* hidden, const void* enc, c
         const qie_block_weights& bw = h->blocks[l];
         const float* m = mod + (size_t)l * 12 * D;   // + b*modN + s*6D
         // adaLN 1 -> xm
-        if ((rc = qie_ln_modulate(resid, m, modN, 6LL * D, 0, D, xm, fp8 ? xm8 : nullptr, fp8 ? xscale : nullptr, D,
-                                  1e-6f, seq, st)))
+        if ((rc = run_ln(m, modN, 6LL * D, 0, D, fp8)))
             return rc;
         {   // QKV (+ QK-RMSNorm + RoPE)
             qie_gemm_args g{};
@@ -406,13 +464,13 @@ extern "C" int qie_forward(qie_handle* h, const void* hidden, const void* enc, c
                 g.w_scale[s] = bw.qkv_ws[s];
             }
             g.a = fp8 ? xm8 : xm; g.fp8 = fp8; g.a_scale = xscale;
-            if ((rc = qie_gemm(&g, seq, st))) return rc;
+            if ((rc = run_gemm(g))) return rc;
             if (!h->fuse_qk) {
                 const float* nw[4] = {bw.q_norm_w[0], bw.k_norm_w[0], bw.q_norm_w[1], bw.k_norm_w[1]};
                 if ((rc = qie_qk_norm_rope(qkv, h->d_rope, nw, h->cfg.num_heads, 1e-6f, seq, st))) return rc;
             }
         }
-        if ((rc = qie_attn_fwd(qkv, attn, seq, h->cfg.num_heads, h->attn_variant, st))) return rc;
+        if ((rc = run_attn())) return rc;
         {   // out-proj + gate1 * y + residual
             qie_gemm_args g{};
             g.N = D; g.K = D; g.streams = 3; g.out = resid; g.ldo = D; g.epilogue = QIE_EPI_GATE_RESID_F32;
@@ -427,11 +485,10 @@ extern "C" int qie_forward(qie_handle* h, const void* hidden, const void* enc, c
                 if ((rc = qie_quant_rows_e4m3(attn, attn8, xscale + rows, (long long)rows, D, st))) return rc;
                 g.a = attn8; g.fp8 = 1; g.a_scale = xscale + rows;
             }
-            if ((rc = qie_gemm(&g, seq, st))) return rc;
+            if ((rc = run_gemm(g))) return rc;
         }
         // adaLN 2 -> xm
-        if ((rc = qie_ln_modulate(resid, m, modN, 6LL * D, 3 * D, 4 * D, xm, fp8 ? xm8 : nullptr,
-                                  fp8 ? xscale : nullptr, D, 1e-6f, seq, st)))
+        if ((rc = run_ln(m, modN, 6LL * D, 3 * D, 4 * D, fp8)))
             return rc;
         {   // FF up + GELU(tanh)
             qie_gemm_args g{};
@@ -442,7 +499,7 @@ extern "C" int qie_forward(qie_handle* h, const void* hidden, const void* enc, c
                 g.w_scale[s] = bw.ff1_ws[s];
             }
             g.a = fp8 ? xm8 : xm; g.fp8 = fp8; g.a_scale = xscale;
-            if ((rc = qie_gemm(&g, seq, st))) return rc;
+            if ((rc = run_gemm(g))) return rc;
         }
         {   // FF down + gate2 * y + residual
             qie_gemm_args g{};
@@ -458,18 +515,18 @@ extern "C" int qie_forward(qie_handle* h, const void* hidden, const void* enc, c
                 if ((rc = qie_quant_rows_e4m3(ffh, ffh8, xscale + 2 * rows, (long long)rows, 4 * D, st))) return rc;
                 g.a = ffh8; g.fp8 = 1; g.a_scale = xscale + 2 * rows;
             }
-            if ((rc = qie_gemm(&g, seq, st))) return rc;
+            if ((rc = run_gemm(g))) return rc;
         }
     }
 
     // ---- norm_out (AdaLayerNormContinuous: scale first, then shift) + proj_out on the image stream ----
-    if ((rc = qie_ln_modulate(resid, fin, 2LL * D, 0, D, 0, xm, nullptr, nullptr, D, 1e-6f, seq, st))) return rc;
+    if ((rc = run_ln(fin, 2LL * D, 0, D, 0, false))) return rc;
     {
         qie_gemm_args g{};
         g.a = xm; g.w[0] = h->w.proj_out_w; g.bias[0] = h->w.proj_out_b;
         g.out = outp; g.out_compact = 1; g.ldo = h->cfg.out_dim; g.N = h->cfg.out_dim; g.K = D; g.streams = 1;
         g.epilogue = QIE_EPI_BF16;
-        if ((rc = qie_gemm(&g, seq, st))) return rc;
+        if ((rc = run_gemm(g))) return rc;
     }
     if (seq->img_pad == seq->img_rows) {
         QIE_CUDA_OK(cudaMemcpyAsync(out, outp, (size_t)B * seq->img_rows * h->cfg.out_dim * 2, cudaMemcpyDeviceToDevice,

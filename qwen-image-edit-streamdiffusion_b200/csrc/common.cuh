@@ -23,10 +23,12 @@ int cuda_fail(cudaError_t e, const char* what);
         if (_e != cudaSuccess) return ::qie::cuda_fail(_e, #expr); \
     } while (0)
 
+extern unsigned long long g_launches;   // kernels launched by this library (bench.py "gpu_launches")
 #define QIE_LAUNCH_OK(name)                                        \
     do {                                                           \
         cudaError_t _e = cudaGetLastError();                       \
         if (_e != cudaSuccess) return ::qie::cuda_fail(_e, name);  \
+        ++::qie::g_launches;                                       \
     } while (0)
 
 #define QIE_REQUIRE(cond, code, ...)          \

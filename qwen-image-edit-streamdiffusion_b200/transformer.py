@@ -252,6 +252,18 @@ class B200QwenImageTransformer2DModel(nn.Module):
         L.check(L.lib().qie_set_option(self._handle, key, value), "qie_set_option")
         return self
 
+    # ------------------------------------------------------------------ measurement aids
+    PROFILE_CLASSES = ("gemm", "attention", "adaln", "mod_gemv", "other")
+
+    def profile(self, on: bool):
+        """record CUDA events around every kernel class inside qie_forward (read with read_profile)."""
+        return self.set_option(2, 1 if on else 0)
+
+    def read_profile(self) -> Dict[str, Dict[str, float]]:
+        ms, work, n = (C.c_double * 5)(), (C.c_double * 5)(), (C.c_int * 5)()
+        L.check(L.lib().qie_profile_read(self._handle, ms, work, n), "qie_profile_read")
+        return {k: {"ms": ms[i], "work": work[i], "launches": n[i]} for i, k in enumerate(self.PROFILE_CLASSES)}
+
     # ------------------------------------------------------------------ forward
     def _workspace(self, seq: L.Seq) -> torch.Tensor:
         need = L.lib().qie_workspace_bytes(self._handle, C.byref(seq))
