@@ -175,6 +175,7 @@ typedef struct qie_gemm_args {
     const float* a_scale;
     const float* w_scale[2];
     int block_n;              /* 0 = auto */
+    int cta_group;            /* 0 = auto, 1 = one CTA per 128-row tile, 2 = CTA pair per 256-row tile (tcgen05 cta_group::2) */
 } qie_gemm_args;
 int qie_gemm(const qie_gemm_args* args, const qie_seq* seq, void* stream);
 

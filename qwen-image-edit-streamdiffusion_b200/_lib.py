@@ -59,7 +59,7 @@ class GemmArgs(C.Structure):
                 ("N", C.c_int), ("K", C.c_int), ("streams", C.c_int), ("epilogue", C.c_int),
                 ("gate", C.c_void_p), ("gate_bstride", C.c_longlong), ("gate_sstride", C.c_longlong),
                 ("rope", C.c_void_p), ("qk_norm_w", (C.c_void_p * 2) * 2),
-                ("fp8", C.c_int), ("a_scale", C.c_void_p), ("w_scale", _P2), ("block_n", C.c_int)]
+                ("fp8", C.c_int), ("a_scale", C.c_void_p), ("w_scale", _P2), ("block_n", C.c_int), ("cta_group", C.c_int)]
 
 
 EPI_BF16, EPI_GELU_BF16, EPI_F32, EPI_GATE_RESID_F32, EPI_QKV_NORM_ROPE = range(5)

@@ -292,6 +292,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p) {
         }
     }
 
+    __syncwarp();
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {

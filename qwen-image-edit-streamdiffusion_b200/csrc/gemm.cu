@@ -8,12 +8,18 @@
 // to 3D), to_out.0/to_add_out (+ gate*y + residual epilogue), img_mlp/txt_mlp net.0.proj (+GELU-tanh)
 // and net.2 (+ gate*y + residual), plus img_in/txt_in/proj_out.
 //
-// Structure (192 threads, 1 CTA / SM, grid = min(tiles, #SM), static round-robin tile schedule):
-//   warp 0 / lane 0 : TMA producer  — A tile [128 x 64] and W tile [BN x 64] (128B-swizzled rows) per stage
-//   warp 1 / lane 0 : MMA issuer    — tcgen05.mma.cta_group::1.kind::f16 128 x BN x 16, fp32 accum in TMEM
-//   warps 2..5      : epilogue      — tcgen05.ld 32x32b -> registers -> fused math -> global
+// Structure (192 threads, 1 CTA / SM, persistent, static round-robin tile schedule):
+//   warp 0 / lane 0 : TMA producer  — A tile [128 x 128 B] and W tile (128B-swizzled rows) per stage
+//   warp 1 / lane 0 : MMA issuer    — tcgen05.mma kind::f16 / kind::f8f6f4, fp32 accumulators in TMEM
+//   warps 2..5      : epilogue      — tcgen05.ld 32x32b -> registers -> per-warp smem transpose -> coalesced global
 // Three pipelines: smem full/empty ring (TMA <-> MMA), 2 TMEM accumulator stages (MMA <-> epilogue, so the
 // epilogue of tile i overlaps the main loop of tile i+1), and the tile loop.
+//
+// CG = 1: one CTA computes a 128 x BN tile (cta_group::1).
+// CG = 2: a cluster of two CTAs on one TPC computes a 256 x BN tile with ONE tcgen05.mma.cta_group::2 issued by the
+//         leader CTA: each CTA loads its own 128 A rows (any two 128-row blocks of the same stream) and HALF of the W
+//         tile (BN/2 rows), so L2->SM operand traffic per FLOP drops by a third and W smem reads are halved.  The peer's
+//         TMA credits the leader's full barrier; the leader's tcgen05.commit multicasts to both CTAs' barriers.
 // Roofline: tensor pipe; algorithmic FLOPs = 2*M*N*K.
 #include "common.cuh"
 
@@ -41,83 +47,64 @@ struct GemmDev {
     int model_dim;           // D (QKV epilogue: column block -> q/k/v)
 };
 
-template <int BN>
+template <int BN, int CG>
 struct GemmSmem {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK_BYTES;
-    static constexpr int B_BYTES = BN * GEMM_BK_BYTES;
+    static constexpr int B_BYTES = (BN / CG) * GEMM_BK_BYTES;               // each CTA of a pair holds half of the W tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = (196 * 1024) / STAGE_BYTES > 8 ? 8 : (196 * 1024) / STAGE_BYTES;
     static constexpr int BAR_BYTES = 256;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024: manual 1 KB alignment
+    static constexpr int EPI_ROW_BYTES = 144;                               // 32 fp32 + 16 B pad: conflict-free both ways
+    static constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_BYTES;               // per-warp transpose staging
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 4 * EPI_WARP_BYTES + 1024;   // +1024: manual alignment
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;             // two accumulator stages
 };
 
-// decode the m-block index into (batch, stream, tile-in-stream)
-struct MBlock {
-    int b, s, ti;
+// Work decomposition.  An "m-unit" is what one CTA (CG=1) or one CTA pair (CG=2) covers along M:
+// CG consecutive 128-row blocks of ONE stream of ONE batch element (the last unit of a stream may be half empty).
+struct MUnit {
+    int b, s, ti;      // batch, stream, first 128-row block inside the stream
 };
-__device__ __forceinline__ MBlock decode_mblock(const GemmDev& p, int mb) {
-    const int t0 = (p.streams & 1) ? p.seq.img_pad / GEMM_BM : 0;
-    const int t1 = (p.streams & 2) ? p.seq.txt_pad / GEMM_BM : 0;
-    MBlock r;
-    r.b = mb / (t0 + t1);
-    const int rem = mb % (t0 + t1);
-    r.s = rem >= t0 ? 1 : 0;
-    r.ti = r.s ? rem - t0 : rem;
+template <int CG>
+__device__ __forceinline__ int units_in_stream(int pad_rows) {
+    return (pad_rows / GEMM_BM + CG - 1) / CG;
+}
+template <int CG>
+__device__ __forceinline__ MUnit decode_munit(const GemmDev& p, int mu) {
+    const int u0 = (p.streams & 1) ? units_in_stream<CG>(p.seq.img_pad) : 0;
+    const int u1 = (p.streams & 2) ? units_in_stream<CG>(p.seq.txt_pad) : 0;
+    MUnit r;
+    r.b = mu / (u0 + u1);
+    const int rem = mu % (u0 + u1);
+    r.s = rem >= u0 ? 1 : 0;
+    r.ti = (r.s ? rem - u0 : rem) * CG;
     return r;
 }
 
-template <int EPI>
-__device__ __forceinline__ void store_chunk(const GemmDev& p, float (&v)[32], long long orow, int n0, bool valid) {
-    if constexpr (EPI == QIE_EPI_BF16 || EPI == QIE_EPI_GELU_BF16 || EPI == QIE_EPI_QKV_NORM_ROPE) {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + n0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            uint4 u;
-            if (valid) {
-                u.x = pack_bf16(v[i * 8 + 0], v[i * 8 + 1]);
-                u.y = pack_bf16(v[i * 8 + 2], v[i * 8 + 3]);
-                u.z = pack_bf16(v[i * 8 + 4], v[i * 8 + 5]);
-                u.w = pack_bf16(v[i * 8 + 6], v[i * 8 + 7]);
-            } else {
-                u = make_uint4(0, 0, 0, 0);
-            }
-            *reinterpret_cast<uint4*>(o + i * 8) = u;
-        }
-    } else {
-        float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + n0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float4 f = valid ? make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3])
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(o + i * 4) = f;
-        }
-    }
-}
-
-template <int BN, int EPI, bool FP8>
+template <int BN, int EPI, bool FP8, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
             const __grid_constant__ CUtensorMap tmB1, const GemmDev p) {
-    using S = GemmSmem<BN>;
+    using S = GemmSmem<BN, CG>;
     constexpr int STAGES = S::STAGES;
     constexpr int BK = FP8 ? 128 : 64;           // elements per k-block
-    constexpr uint32_t IDESC = FP8 ? umma_idesc_e4m3(GEMM_BM, BN) : umma_idesc_bf16(GEMM_BM, BN);
+    constexpr uint32_t IDESC = FP8 ? umma_idesc_e4m3(GEMM_BM * CG, BN) : umma_idesc_bf16(GEMM_BM * CG, BN);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
-    uint64_t* full_bar = bars;                   // [STAGES]
+    uint64_t* full_bar = bars;                   // [STAGES]   (CG=2: only the leader's copy is used)
     uint64_t* empty_bar = bars + STAGES;         // [STAGES]
     uint64_t* tfull_bar = bars + 2 * STAGES;     // [2]
-    uint64_t* tempty_bar = bars + 2 * STAGES + 2;// [2]
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;// [2]        (CG=2: only the leader's copy is used)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = lane_id();
-    const int t0 = (p.streams & 1) ? p.seq.img_pad / GEMM_BM : 0;
-    const int t1 = (p.streams & 2) ? p.seq.txt_pad / GEMM_BM : 0;
-    const int m_blocks = p.seq.batch * (t0 + t1);
-    const int num_tiles = m_blocks * p.n_blocks;
+    const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
+    const int u0 = (p.streams & 1) ? units_in_stream<CG>(p.seq.img_pad) : 0;
+    const int u1 = (p.streams & 2) ? units_in_stream<CG>(p.seq.txt_pad) : 0;
+    const int num_tiles = p.seq.batch * (u0 + u1) * p.n_blocks;      // tiles of one CTA (CG=1) / one pair (CG=2)
+    const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
     const int k_blocks = (p.K + BK - 1) / BK;
     const int rpb = p.seq.img_pad + p.seq.txt_pad;
 
@@ -131,35 +118,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);
+            mbar_init(&tempty_bar[i], 4 * CG);
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<S::TMEM_COLS>(tmem_slot);
+    if (warp == 1) {
+        if constexpr (CG == 2) tmem_alloc_cg2<S::TMEM_COLS>(tmem_slot);
+        else tmem_alloc<S::TMEM_COLS>(tmem_slot);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {
-            // ================= TMA producer =================
+            // ================= TMA producer (every CTA loads its own A rows and its share of W) =================
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int mb = tile / p.n_blocks, nb = tile % p.n_blocks;
-                const MBlock m = decode_mblock(p, mb);
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+                const int mu = tile / p.n_blocks, nb = tile % p.n_blocks;
+                const MUnit m = decode_munit<CG>(p, mu);
                 const int seg_pad = m.s ? p.seq.txt_pad : p.seq.img_pad;
-                const int a_row = p.a_compact ? m.b * seg_pad + m.ti * GEMM_BM
-                                              : m.b * rpb + (m.s ? p.seq.img_pad : 0) + m.ti * GEMM_BM;
+                int ti = m.ti + cta_rank;
+                if (ti * GEMM_BM >= seg_pad) ti = m.ti;          // odd block count: the peer re-reads the leader's rows
+                const int a_row = p.a_compact ? m.b * seg_pad + ti * GEMM_BM
+                                              : m.b * rpb + (m.s ? p.seq.img_pad : 0) + ti * GEMM_BM;
                 const CUtensorMap* tmB = m.s ? &tmB1 : &tmB0;
+                const int b_row = nb * BN + cta_rank * (BN / CG);
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * S::STAGE_BYTES;
                     uint8_t* sb = sa + S::A_BYTES;
-                    mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-                    tma_load_2d(sa, &tmA, kb * BK, a_row, &full_bar[stage]);
-                    tma_load_2d(sb, tmB, kb * BK, nb * BN, &full_bar[stage]);
+                    if constexpr (CG == 2) {
+                        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+                        const uint32_t bar = leader_smem_u32(&full_bar[stage]);
+                        tma_load_2d_cg2(sa, &tmA, kb * BK, a_row, bar);
+                        tma_load_2d_cg2(sb, tmB, kb * BK, b_row, bar);
+                    } else {
+                        mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+                        tma_load_2d(sa, &tmA, kb * BK, a_row, &full_bar[stage]);
+                        tma_load_2d(sb, tmB, kb * BK, b_row, &full_bar[stage]);
+                    }
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -168,13 +169,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ================= MMA issuer =================
+        if (lane == 0 && cta_rank == 0) {
+            // ================= MMA issuer (leader CTA only) =================
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -186,18 +187,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     const uint64_t db = umma_desc_kmajor_sw128(sa + S::A_BYTES);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {   // 4 x 32 B along the swizzled 128 B row
-                        if constexpr (FP8)
-                            umma_ss_f8(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) ? 1u : 0u);
-                        else
-                            umma_ss_f16(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) ? 1u : 0u);
+                        const uint32_t accum = (kb | k) ? 1u : 0u;
+                        if constexpr (CG == 2) {
+                            if constexpr (FP8) umma_ss_f8_cg2(d_tmem, da + 2 * k, db + 2 * k, IDESC, accum);
+                            else umma_ss_f16_cg2(d_tmem, da + 2 * k, db + 2 * k, IDESC, accum);
+                        } else {
+                            if constexpr (FP8) umma_ss_f8(d_tmem, da + 2 * k, db + 2 * k, IDESC, accum);
+                            else umma_ss_f16(d_tmem, da + 2 * k, db + 2 * k, IDESC, accum);
+                        }
                     }
-                    umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+                    // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+                    if constexpr (CG == 2) umma_commit_cg2(&empty_bar[stage], 3);
+                    else umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit(&tfull_bar[acc]);         // accumulator complete -> epilogue
+                // accumulator complete -> epilogue warps (of both CTAs)
+                if constexpr (CG == 2) umma_commit_cg2(&tfull_bar[acc], 3);
+                else umma_commit(&tfull_bar[acc]);
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1;
@@ -206,127 +215,180 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
     } else {
         // ================= epilogue (warps 2..5) =================
+        // Each warp owns the 32 accumulator rows of its TMEM lane quadrant.  Per 32-column chunk:
+        //   phase 1 (lane == row)   : tcgen05.ld -> registers -> padded per-warp smem tile
+        //   phase 2 (lanes == cols) : 8 lanes x float4 cover one 128 B row segment, 4 rows per instruction, so every
+        //                             global load/store of bias, gate, residual, rope and output is a coalesced line.
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
+        uint8_t* stg = smem + STAGES * S::STAGE_BYTES + S::BAR_BYTES + (warp - 2) * S::EPI_WARP_BYTES;
+        const int sub = lane >> 3, c4 = (lane & 7) * 4;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int mb = tile / p.n_blocks, nb = tile % p.n_blocks;
-            const MBlock m = decode_mblock(p, mb);
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+            const int mu = tile / p.n_blocks, nb = tile % p.n_blocks;
+            const MUnit m = decode_munit<CG>(p, mu);
             const int seg_pad = m.s ? p.seq.txt_pad : p.seq.img_pad;
             const int seg_rows = m.s ? p.seq.txt_rows : p.seq.img_rows;
-            const int local = m.ti * GEMM_BM + quad * 32 + lane;
-            const bool valid = local < seg_rows;
-            const int jrow_in_batch = (m.s ? p.seq.img_pad : 0) + local;     // row inside the joint layout
-            const long long jrow = (long long)m.b * rpb + jrow_in_batch;
-            const long long orow = p.out_compact ? (long long)m.b * seg_pad + local : jrow;
-            const long long arow = p.a_compact ? (long long)m.b * seg_pad + local : jrow;
+            const int ti = m.ti + cta_rank;
+            const bool dummy = ti * GEMM_BM >= seg_pad;                       // peer half of an odd last unit: nothing to store
+            const int local0 = ti * GEMM_BM + quad * 32;                      // first row of this warp inside the stream
+            const int jrow0_in_batch = (m.s ? p.seq.img_pad : 0) + local0;   // ... inside the joint layout
+            const long long jrow0 = (long long)m.b * rpb + jrow0_in_batch;
+            const long long orow0 = p.out_compact ? (long long)m.b * seg_pad + local0 : jrow0;
+            const long long arow0 = p.a_compact ? (long long)m.b * seg_pad + local0 : jrow0;
             const float* bias = p.bias[m.s];
-            float a_sc = 1.f;
-            if constexpr (FP8) a_sc = p.a_scale[arow];
 
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
 
-            auto load_chunk = [&](int c, float (&v)[32]) {
+            [[maybe_unused]] float as_row = 1.f;
+            if constexpr (FP8) as_row = dummy ? 0.f : p.a_scale[arow0 + lane];
+            // phase 1: chunk c of the accumulator -> staging, optionally (bias + per-row scale) applied in row layout
+            auto stage_chunk = [&](int c, float row_scale, bool add_bias_first) {
                 uint32_t r[32];
                 tmem_ld32(t_addr + c * 32, r);
                 tmem_ld_wait();
-                const int n0 = nb * BN + c * 32;
+                float* srow = reinterpret_cast<float*>(stg + lane * S::EPI_ROW_BYTES);
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                    float4 bv = bias ? *reinterpret_cast<const float4*>(bias + n0 + i) : make_float4(0, 0, 0, 0);
-                    if constexpr (FP8) {
-                        const float4 ws = *reinterpret_cast<const float4*>(p.w_scale[m.s] + n0 + i);
-                        v[i + 0] = __uint_as_float(r[i + 0]) * (a_sc * ws.x) + bv.x;
-                        v[i + 1] = __uint_as_float(r[i + 1]) * (a_sc * ws.y) + bv.y;
-                        v[i + 2] = __uint_as_float(r[i + 2]) * (a_sc * ws.z) + bv.z;
-                        v[i + 3] = __uint_as_float(r[i + 3]) * (a_sc * ws.w) + bv.w;
-                    } else {
-                        v[i + 0] = __uint_as_float(r[i + 0]) + bv.x;
-                        v[i + 1] = __uint_as_float(r[i + 1]) + bv.y;
-                        v[i + 2] = __uint_as_float(r[i + 2]) + bv.z;
-                        v[i + 3] = __uint_as_float(r[i + 3]) + bv.w;
+                    float4 f = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
+                                           __uint_as_float(r[i + 3]));
+                    if (add_bias_first) {
+                        const float4 bv = *reinterpret_cast<const float4*>(bias + nb * BN + c * 32 + i);
+                        if constexpr (FP8) {
+                            const float4 ws = *reinterpret_cast<const float4*>(p.w_scale[m.s] + nb * BN + c * 32 + i);
+                            f.x *= as_row * ws.x; f.y *= as_row * ws.y; f.z *= as_row * ws.z; f.w *= as_row * ws.w;
+                        }
+                        f.x = (f.x + bv.x) * row_scale; f.y = (f.y + bv.y) * row_scale;
+                        f.z = (f.z + bv.z) * row_scale; f.w = (f.w + bv.w) * row_scale;
                     }
+                    *reinterpret_cast<float4*>(srow + i) = f;
                 }
+                __syncwarp();
             };
 
-            if constexpr (EPI == QIE_EPI_QKV_NORM_ROPE) {
-                // a BN-wide tile holds BN/128 whole heads of exactly one of q / k / v (D % BN == 0)
-                const int which = (nb * BN) / p.model_dim;    // 0 q, 1 k, 2 v
-#pragma unroll 1
-                for (int hh = 0; hh < BN / 128; ++hh) {
-                    float v[32];
-                    if (which == 2) {
-#pragma unroll 1
-                        for (int c = 0; c < 4; ++c) {
-                            load_chunk(hh * 4 + c, v);
-                            store_chunk<EPI>(p, v, orow, nb * BN + hh * 128 + c * 32, valid);
-                        }
-                    } else {
-                        float ss = 0.f;
-#pragma unroll 1
-                        for (int c = 0; c < 4; ++c) {
-                            load_chunk(hh * 4 + c, v);
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) ss += v[i] * v[i];
-                        }
-                        const float rinv = rsqrtf(ss * (1.0f / 128.0f) + 1e-6f);
-                        const float* nw = p.qk_norm_w[m.s][which];
-                        const float* rp = p.rope + (long long)jrow_in_batch * 128;
-#pragma unroll 1
-                        for (int c = 0; c < 4; ++c) {
-                            load_chunk(hh * 4 + c, v);
-#pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                const float4 w = *reinterpret_cast<const float4*>(nw + c * 32 + i);
-                                const float4 cs = valid ? *reinterpret_cast<const float4*>(rp + c * 32 + i)
-                                                        : make_float4(1.f, 0.f, 1.f, 0.f);
-                                const float x0 = v[i] * rinv * w.x, x1 = v[i + 1] * rinv * w.y;
-                                const float x2 = v[i + 2] * rinv * w.z, x3 = v[i + 3] * rinv * w.w;
-                                v[i] = x0 * cs.x - x1 * cs.y;
-                                v[i + 1] = x0 * cs.y + x1 * cs.x;
-                                v[i + 2] = x2 * cs.z - x3 * cs.w;
-                                v[i + 3] = x2 * cs.w + x3 * cs.z;
-                            }
-                            store_chunk<EPI>(p, v, orow, nb * BN + hh * 128 + c * 32, valid);
-                        }
-                    }
-                }
-            } else {
+            [[maybe_unused]] float rinv_head = 1.f;
+            if (!dummy) {
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c) {
-                    float v[32];
-                    load_chunk(c, v);
                     const int n0 = nb * BN + c * 32;
-                    if constexpr (EPI == QIE_EPI_GELU_BF16) {
+                    int which = 2;
+                    if constexpr (EPI == QIE_EPI_QKV_NORM_ROPE) {
+                        which = (nb * BN) / p.model_dim;                      // 0 q, 1 k, 2 v (D % BN == 0)
+                        if (which != 2 && (c & 3) == 0) {                     // first chunk of a head: row RMS over 128 cols
+                            float ss = 0.f;
+#pragma unroll 1
+                            for (int cc = c; cc < c + 4; ++cc) {
+                                uint32_t r[32];
+                                tmem_ld32(t_addr + cc * 32, r);
+                                tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
-                        store_chunk<EPI>(p, v, orow, n0, valid);
-                    } else if constexpr (EPI == QIE_EPI_GATE_RESID_F32) {
-                        if (valid) {
-                            float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + n0;
-                            const float* g = p.gate + m.b * p.gate_bstride + m.s * p.gate_sstride + n0;
+                                for (int i = 0; i < 32; i += 4) {
+                                    const float4 bv = *reinterpret_cast<const float4*>(bias + nb * BN + cc * 32 + i);
+                                    float4 ws = make_float4(1.f, 1.f, 1.f, 1.f);
+                                    if constexpr (FP8) {
+                                        ws = *reinterpret_cast<const float4*>(p.w_scale[m.s] + nb * BN + cc * 32 + i);
+                                        ws.x *= as_row; ws.y *= as_row; ws.z *= as_row; ws.w *= as_row;
+                                    }
+                                    const float a0 = __uint_as_float(r[i]) * ws.x + bv.x;
+                                    const float a1 = __uint_as_float(r[i + 1]) * ws.y + bv.y;
+                                    const float a2 = __uint_as_float(r[i + 2]) * ws.z + bv.z;
+                                    const float a3 = __uint_as_float(r[i + 3]) * ws.w + bv.w;
+                                    ss += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+                                }
+                            }
+                            rinv_head = rsqrtf(ss * (1.0f / 128.0f) + 1e-6f);
+                        }
+                        stage_chunk(c, which != 2 ? rinv_head : 1.f, which != 2);
+                    } else {
+                        stage_chunk(c, 1.f, false);
+                    }
+                    const bool normed = EPI == QIE_EPI_QKV_NORM_ROPE && which != 2;
+
+                    // phase 2: issue every global load of this chunk first, then do the math and the stores
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (bias && !normed) bv = *reinterpret_cast<const float4*>(bias + n0 + c4);
+                    [[maybe_unused]] float4 wsc = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if constexpr (FP8) wsc = *reinterpret_cast<const float4*>(p.w_scale[m.s] + n0 + c4);
+                    [[maybe_unused]] float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if constexpr (EPI == QIE_EPI_GATE_RESID_F32)
+                        g4 = *reinterpret_cast<const float4*>(p.gate + m.b * p.gate_bstride + m.s * p.gate_sstride + n0 + c4);
+                    [[maybe_unused]] float4 nw4 = make_float4(1.f, 1.f, 1.f, 1.f);
+                    [[maybe_unused]] float4 aux[8];      // residual rows (GATE_RESID) or rope rows (QKV)
+                    if constexpr (EPI == QIE_EPI_QKV_NORM_ROPE) {
+                        if (normed) {
+                            nw4 = *reinterpret_cast<const float4*>(p.qk_norm_w[m.s][which] + (c & 3) * 32 + c4);
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                float4 r4 = *reinterpret_cast<float4*>(o + i);
-                                const float4 g4 = *reinterpret_cast<const float4*>(g + i);
-                                r4.x += g4.x * v[i];
-                                r4.y += g4.y * v[i + 1];
-                                r4.z += g4.z * v[i + 2];
-                                r4.w += g4.w * v[i + 3];
-                                *reinterpret_cast<float4*>(o + i) = r4;
+                            for (int it = 0; it < 8; ++it) {
+                                const int rr = it * 4 + sub;
+                                aux[it] = local0 + rr < seg_rows
+                                              ? __ldg(reinterpret_cast<const float4*>(
+                                                    p.rope + (long long)(jrow0_in_batch + rr) * 128 + (c & 3) * 32 + c4))
+                                              : make_float4(1.f, 0.f, 1.f, 0.f);
                             }
                         }
-                    } else {
-                        store_chunk<EPI>(p, v, orow, n0, valid);
                     }
+                    if constexpr (EPI == QIE_EPI_GATE_RESID_F32) {
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int rr = it * 4 + sub;
+                            aux[it] = local0 + rr < seg_rows
+                                          ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) +
+                                                                             (orow0 + rr) * p.ldo + n0 + c4)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                    [[maybe_unused]] float asc[8];
+                    if constexpr (FP8) {
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) asc[it] = normed ? 1.f : p.a_scale[arow0 + it * 4 + sub];
+                    }
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int rr = it * 4 + sub;
+                        const bool valid = local0 + rr < seg_rows;
+                        float4 v = *reinterpret_cast<const float4*>(stg + rr * S::EPI_ROW_BYTES + c4 * 4);
+                        if constexpr (FP8) {
+                            if (!normed) {
+                                v.x *= asc[it] * wsc.x; v.y *= asc[it] * wsc.y; v.z *= asc[it] * wsc.z; v.w *= asc[it] * wsc.w;
+                            }
+                        }
+                        if (normed) {
+                            const float4 cs = aux[it];
+                            const float x0 = v.x * nw4.x, x1 = v.y * nw4.y, x2 = v.z * nw4.z, x3 = v.w * nw4.w;
+                            v.x = x0 * cs.x - x1 * cs.y; v.y = x0 * cs.y + x1 * cs.x;
+                            v.z = x2 * cs.z - x3 * cs.w; v.w = x2 * cs.w + x3 * cs.z;
+                        } else {
+                            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                        }
+                        if constexpr (EPI == QIE_EPI_GELU_BF16) {
+                            v.x = gelu_tanh(v.x); v.y = gelu_tanh(v.y); v.z = gelu_tanh(v.z); v.w = gelu_tanh(v.w);
+                        }
+                        if constexpr (EPI == QIE_EPI_GATE_RESID_F32) {
+                            if (valid) {
+                                float4 r4 = aux[it];
+                                r4.x += g4.x * v.x; r4.y += g4.y * v.y; r4.z += g4.z * v.z; r4.w += g4.w * v.w;
+                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (orow0 + rr) * p.ldo + n0 + c4) = r4;
+                            }
+                        } else if constexpr (EPI == QIE_EPI_F32) {
+                            if (!valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (orow0 + rr) * p.ldo + n0 + c4) = v;
+                        } else {
+                            const uint2 u = valid ? make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w)) : make_uint2(0u, 0u);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (orow0 + rr) * p.ldo + n0 + c4) = u;
+                        }
+                    }
+                    __syncwarp();   // staging tile is reused by the next chunk
                 }
             }
-            // release this accumulator stage back to the MMA warp
+            // release this accumulator stage back to the MMA warp (of the leader CTA)
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                if constexpr (CG == 2) mbar_arrive_cluster(leader_smem_u32(&tempty_bar[acc]));
+                else mbar_arrive(&tempty_bar[acc]);
+            }
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;
@@ -334,41 +396,56 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
     }
 
+    __syncwarp();        // reconverge the single-lane producer / MMA roles before the aligned barriers below
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();   // the peer's barriers / smem must outlive the leader's last commit
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<S::TMEM_COLS>(tmem_base);
+        if constexpr (CG == 2) tmem_dealloc_cg2<S::TMEM_COLS>(tmem_base);
+        else tmem_dealloc<S::TMEM_COLS>(tmem_base);
     }
 }
 
-template <int BN, int EPI, bool FP8>
+template <int BN, int EPI, bool FP8, int CG>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB0, const CUtensorMap& tmB1, const GemmDev& p,
                        int num_tiles, cudaStream_t st) {
-    using S = GemmSmem<BN>;
+    using S = GemmSmem<BN, CG>;
     static bool configured = false;
     if (!configured) {
-        QIE_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, EPI, FP8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        QIE_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, EPI, FP8, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          S::TOTAL));
         configured = true;
     }
-    int grid = sm_count();
-    if (grid > num_tiles) grid = num_tiles;
-    gemm_kernel<BN, EPI, FP8><<<grid, GEMM_THREADS, S::TOTAL, st>>>(tmA, tmB0, tmB1, p);
+    int units = sm_count() / CG;                 // CTAs (CG=1) or CTA pairs (CG=2) resident at once
+    if (units > num_tiles) units = num_tiles;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(units * CG);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, FP8, CG>, tmA, tmB0, tmB1, p));
     QIE_LAUNCH_OK("gemm_kernel");
     return QIE_OK;
 }
 
-template <int BN, bool FP8>
+template <int BN, bool FP8, int CG>
 static int dispatch_epi(int epi, const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap& b1, const GemmDev& p,
                         int tiles, cudaStream_t st) {
     switch (epi) {
-        case QIE_EPI_BF16: return launch_gemm<BN, QIE_EPI_BF16, FP8>(a, b0, b1, p, tiles, st);
-        case QIE_EPI_GELU_BF16: return launch_gemm<BN, QIE_EPI_GELU_BF16, FP8>(a, b0, b1, p, tiles, st);
-        case QIE_EPI_F32: return launch_gemm<BN, QIE_EPI_F32, FP8>(a, b0, b1, p, tiles, st);
-        case QIE_EPI_GATE_RESID_F32: return launch_gemm<BN, QIE_EPI_GATE_RESID_F32, FP8>(a, b0, b1, p, tiles, st);
+        case QIE_EPI_BF16: return launch_gemm<BN, QIE_EPI_BF16, FP8, CG>(a, b0, b1, p, tiles, st);
+        case QIE_EPI_GELU_BF16: return launch_gemm<BN, QIE_EPI_GELU_BF16, FP8, CG>(a, b0, b1, p, tiles, st);
+        case QIE_EPI_F32: return launch_gemm<BN, QIE_EPI_F32, FP8, CG>(a, b0, b1, p, tiles, st);
+        case QIE_EPI_GATE_RESID_F32: return launch_gemm<BN, QIE_EPI_GATE_RESID_F32, FP8, CG>(a, b0, b1, p, tiles, st);
         case QIE_EPI_QKV_NORM_ROPE:
-            if constexpr (BN >= 128) return launch_gemm<BN, QIE_EPI_QKV_NORM_ROPE, FP8>(a, b0, b1, p, tiles, st);
+            if constexpr (BN >= 128) return launch_gemm<BN, QIE_EPI_QKV_NORM_ROPE, FP8, CG>(a, b0, b1, p, tiles, st);
     }
     set_error("qie_gemm: unsupported epilogue %d for block_n %d", epi, BN);
     return QIE_EINVAL;
@@ -427,9 +504,18 @@ extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream
         QIE_REQUIRE(g->N % 3 == 0 && p.model_dim % bn == 0 && bn >= 128 && g->rope, QIE_ESHAPE,
                     "qie_gemm: QKV epilogue needs N=3D, D %% block_n == 0, block_n>=128, rope table");
         for (int s = 0; s < 2; ++s)
-            if (g->streams & (1 << s))
+            if (g->streams & (1 << s)) {
                 QIE_REQUIRE(p.qk_norm_w[s][0] && p.qk_norm_w[s][1], QIE_EINVAL, "qie_gemm: qk norm weights null");
+                QIE_REQUIRE(p.bias[s], QIE_EINVAL, "qie_gemm: QKV epilogue needs a bias");
+            }
     }
+
+    // CTA pairs pay off once there are enough 256-row tiles to fill all 74 TPCs
+    const int t0 = (g->streams & 1) ? seq->img_pad / 128 : 0, t1 = (g->streams & 2) ? seq->txt_pad / 128 : 0;
+    const int pair_tiles = seq->batch * ((t0 + 1) / 2 + (t1 + 1) / 2) * p.n_blocks;
+    int cg = g->cta_group;
+    if (cg == 0) cg = (bn >= 128 && pair_tiles >= sm_count() / 2) ? 2 : 1;
+    QIE_REQUIRE(cg == 1 || (cg == 2 && bn >= 128), QIE_EINVAL, "qie_gemm: cta_group must be 1 or 2 (2 needs block_n >= 128)");
 
     const int rpb = seq->img_pad + seq->txt_pad;
     const int only = g->streams == 2 ? 1 : 0;
@@ -440,22 +526,25 @@ extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream
     if (rc) return rc;
     for (int s = 0; s < 2; ++s) {
         const void* w = g->w[s] ? g->w[s] : g->w[1 - s];
-        rc = make_tmap_2d(&tmB[s], w, (uint64_t)g->N, (uint64_t)g->K, (uint64_t)g->K * eb, bn, bk, eb);
+        rc = make_tmap_2d(&tmB[s], w, (uint64_t)g->N, (uint64_t)g->K, (uint64_t)g->K * eb, bn / cg, bk, eb);
         if (rc) return rc;
     }
-    const int t0 = (g->streams & 1) ? seq->img_pad / 128 : 0, t1 = (g->streams & 2) ? seq->txt_pad / 128 : 0;
-    const int tiles = seq->batch * (t0 + t1) * p.n_blocks;
+    const int tiles = cg == 2 ? pair_tiles : seq->batch * (t0 + t1) * p.n_blocks;
     cudaStream_t st = (cudaStream_t)stream;
+#define QIE_GEMM_DISPATCH(F8, CGV)                                                                         \
+    switch (bn) {                                                                                          \
+        case 64:                                                                                           \
+            if constexpr (CGV == 1) return dispatch_epi<64, F8, 1>(g->epilogue, tmA, tmB[0], tmB[1], p, tiles, st); \
+            break;                                                                                         \
+        case 128: return dispatch_epi<128, F8, CGV>(g->epilogue, tmA, tmB[0], tmB[1], p, tiles, st);      \
+        default: return dispatch_epi<256, F8, CGV>(g->epilogue, tmA, tmB[0], tmB[1], p, tiles, st);       \
+    }
     if (g->fp8) {
-        switch (bn) {
-            case 64: return dispatch_epi<64, true>(g->epilogue, tmA, tmB[0], tmB[1], p, tiles, st);
-            case 128: return dispatch_epi<128, true>(g->epilogue, tmA, tmB[0], tmB[1], p, tiles, st);
-            default: return dispatch_epi<256, true>(g->epilogue, tmA, tmB[0], tmB[1], p, tiles, st);
-        }
+        if (cg == 2) { QIE_GEMM_DISPATCH(true, 2) } else { QIE_GEMM_DISPATCH(true, 1) }
+    } else {
+        if (cg == 2) { QIE_GEMM_DISPATCH(false, 2) } else { QIE_GEMM_DISPATCH(false, 1) }
     }
-    switch (bn) {
-        case 64: return dispatch_epi<64, false>(g->epilogue, tmA, tmB[0], tmB[1], p, tiles, st);
-        case 128: return dispatch_epi<128, false>(g->epilogue, tmA, tmB[0], tmB[1], p, tiles, st);
-        default: return dispatch_epi<256, false>(g->epilogue, tmA, tmB[0], tmB[1], p, tiles, st);
-    }
+#undef QIE_GEMM_DISPATCH
+    set_error("qie_gemm: no kernel for block_n=%d cta_group=%d", bn, cg);
+    return QIE_EINVAL;
 }

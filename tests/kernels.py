@@ -30,7 +30,7 @@ def from_joint(s, x):
 
 
 def gemm(s, a, w, bias, out, epilogue, streams=3, a_compact=0, out_compact=0, gate=None, gate_bstride=0,
-         gate_sstride=0, rope=None, qk_norm_w=None, block_n=0, fp8=False, a_scale=None, w_scale=None):
+         gate_sstride=0, rope=None, qk_norm_w=None, block_n=0, fp8=False, a_scale=None, w_scale=None, cta_group=0):
     g = L.GemmArgs()
     g.a = a.data_ptr(); g.a_compact = a_compact
     for i in range(2):
@@ -54,6 +54,7 @@ def gemm(s, a, w, bias, out, epilogue, streams=3, a_compact=0, out_compact=0, ga
     if a_scale is not None:
         g.a_scale = a_scale.data_ptr()
     g.block_n = block_n
+    g.cta_group = cta_group
     L.check(L.lib().qie_gemm(C.byref(g), C.byref(s), L.cur_stream()), "qie_gemm")
     return out
 

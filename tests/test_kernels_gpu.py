@@ -128,14 +128,14 @@ def _gemm_ref(s, a, w, b):
     return ai @ w[0].float().t() + b[0], at @ w[1].float().t() + b[1]
 
 
-@pytest.mark.parametrize("block_n", [64, 128, 256])
-@pytest.mark.parametrize("B,img,txt", [(1, 256, 128), (2, 200, 19)])
-def test_gemm_bf16_epilogue(block_n, B, img, txt):
+@pytest.mark.parametrize("block_n,cta_group", [(64, 1), (128, 1), (256, 1), (128, 2), (256, 2)])
+@pytest.mark.parametrize("B,img,txt", [(1, 256, 128), (2, 200, 19), (1, 384, 300)])
+def test_gemm_bf16_epilogue(block_n, cta_group, B, img, txt):
     s = K.seq(B, img, txt)
     N, Kd = 512, 320            # K not a multiple of 64*stages: exercises the ring wrap + TMA K tail
     a, w, b = _gemm_case(s, N, Kd)
     out = torch.full((K.rows(s), N), 7.0, dtype=torch.bfloat16, device=DEV)
-    K.gemm(s, a, w, b, out, K.L.EPI_BF16, block_n=block_n)
+    K.gemm(s, a, w, b, out, K.L.EPI_BF16, block_n=block_n, cta_group=cta_group)
     ri, rt = _gemm_ref(s, a, w, b)
     gi, gt = K.from_joint(s, out)
     # fp32 accumulation, one bf16 rounding at the store
@@ -144,33 +144,36 @@ def test_gemm_bf16_epilogue(block_n, B, img, txt):
     assert pad.numel() == 0 or pad.abs().max() == 0
 
 
-def test_gemm_large_k_many_tiles():
-    s = K.seq(1, 2048, 256)
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_gemm_large_k_many_tiles(cta_group):
+    s = K.seq(1, 2048 + 128, 256)
     N, Kd = 3072, 3072
     a, w, b = _gemm_case(s, N, Kd, seed=30)
     out = torch.empty(K.rows(s), N, dtype=torch.bfloat16, device=DEV)
-    K.gemm(s, a, w, b, out, K.L.EPI_BF16)
+    K.gemm(s, a, w, b, out, K.L.EPI_BF16, cta_group=cta_group)
     ri, rt = _gemm_ref(s, a, w, b)
     gi, gt = K.from_joint(s, out)
     assert K.rel_err(gi, ri) <= 2 ** -7 and K.rel_err(gt, rt) <= 2 ** -7
 
 
-def test_gemm_gelu_and_f32():
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_gemm_gelu_and_f32(cta_group):
     s = K.seq(1, 384, 100)
     a, w, b = _gemm_case(s, 256, 256, seed=40)
     ri, rt = _gemm_ref(s, a, w, b)
     out = torch.empty(K.rows(s), 256, dtype=torch.bfloat16, device=DEV)
-    K.gemm(s, a, w, b, out, K.L.EPI_GELU_BF16)
+    K.gemm(s, a, w, b, out, K.L.EPI_GELU_BF16, cta_group=cta_group)
     gi, gt = K.from_joint(s, out)
     assert K.rel_err(gi, F.gelu(ri, approximate="tanh")) <= 2 ** -7
     assert K.rel_err(gt, F.gelu(rt, approximate="tanh")) <= 2 ** -7
     out32 = torch.empty(K.rows(s), 256, dtype=torch.float32, device=DEV)
-    K.gemm(s, a, w, b, out32, K.L.EPI_F32)
+    K.gemm(s, a, w, b, out32, K.L.EPI_F32, cta_group=cta_group)
     gi, gt = K.from_joint(s, out32)
     assert K.rel_err(gi, ri) <= 1e-5 and K.rel_err(gt, rt) <= 1e-5
 
 
-def test_gemm_gate_residual():
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_gemm_gate_residual(cta_group):
     s = K.seq(2, 256, 60)
     N = 256
     a, w, b = _gemm_case(s, N, 512, seed=50)
@@ -178,7 +181,7 @@ def test_gemm_gate_residual():
     gate = randn(2, 2, 6 * N, seed=52)
     resid = resid0.clone()
     K.gemm(s, a, w, b, resid, K.L.EPI_GATE_RESID_F32, gate=gate[:, :, 2 * N:], gate_bstride=2 * 6 * N,
-           gate_sstride=6 * N)
+           gate_sstride=6 * N, cta_group=cta_group)
     ri, rt = _gemm_ref(s, a, w, b)
     r0i, r0t = K.from_joint(s, resid0)
     gi, gt = K.from_joint(s, resid)
@@ -208,8 +211,8 @@ def test_gemm_compact_single_stream():
     assert K.rel_err(outc.reshape(2, s.txt_pad, N)[:, :s.txt_rows], at @ w.float().t() + bias) <= 2 ** -7
 
 
-@pytest.mark.parametrize("block_n", [128, 256])
-def test_gemm_qkv_norm_rope(block_n):
+@pytest.mark.parametrize("block_n,cta_group", [(128, 1), (256, 1), (128, 2), (256, 2)])
+def test_gemm_qkv_norm_rope(block_n, cta_group):
     H = 2
     D = H * 128
     s = K.seq(1, 200, 19)
@@ -218,7 +221,7 @@ def test_gemm_qkv_norm_rope(block_n):
     rope = torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).contiguous()
     nw = [[1 + randn(128, seed=72 + 2 * st + k, scale=0.1) for k in range(2)] for st in range(2)]
     out = torch.empty(K.rows(s), 3 * D, dtype=torch.bfloat16, device=DEV)
-    K.gemm(s, a, w, b, out, K.L.EPI_QKV_NORM_ROPE, rope=rope, qk_norm_w=nw, block_n=block_n)
+    K.gemm(s, a, w, b, out, K.L.EPI_QKV_NORM_ROPE, rope=rope, qk_norm_w=nw, block_n=block_n, cta_group=cta_group)
     refs = _gemm_ref(s, a, w, b)
     ropes = K.from_joint(s, rope.reshape(K.rows(s), 128))
     gots = K.from_joint(s, out)
@@ -232,7 +235,8 @@ def test_gemm_qkv_norm_rope(block_n):
         assert K.rel_err(gots[st][0].reshape(-1, 3, H, 128), r) <= 2 ** -7
 
 
-def test_gemm_fp8():
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_gemm_fp8(cta_group):
     s = K.seq(1, 256, 100)
     N, Kd = 512, 512
     a, w, b = _gemm_case(s, N, Kd, seed=80)
@@ -243,7 +247,7 @@ def test_gemm_fp8():
         w8.append((wi.float() / sc[:, None]).to(torch.float8_e4m3fn).view(torch.uint8))
         w_sc.append(sc.contiguous())
     out = torch.empty(K.rows(s), N, dtype=torch.bfloat16, device=DEV)
-    K.gemm(s, a8, w8, b, out, K.L.EPI_BF16, fp8=True, a_scale=a_sc, w_scale=w_sc)
+    K.gemm(s, a8, w8, b, out, K.L.EPI_BF16, fp8=True, a_scale=a_sc, w_scale=w_sc, cta_group=cta_group)
     # exact reference of the same quantised operands (products of e4m3 values are exact in fp32)
     adq = a8.view(torch.float8_e4m3fn).float() * a_sc[:, None]
     ai, at = K.from_joint(s, adq)
