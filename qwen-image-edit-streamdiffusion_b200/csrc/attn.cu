@@ -3,13 +3,15 @@
 // QwenDoubleStreamAttnProcessor2_0; q,k arrive RMS-normed + roped (QKV GEMM epilogue).
 //
 // One CTA = one (batch, head) x 256 query rows = two 128-row Q tiles that ping-pong on the tensor pipe:
-//   warp 0 / lane 0 : TMA producer (Q tiles once; K_j, V_j tiles through a 3-slot ring, 128 rows x 128 dims each)
-//   warp 1 / lane 0 : MMA issuer   S_t = Q_t K_j^T (SS, K-major x K-major)  -> TMEM S_t   (128 x 128 fp32)
-//                                  O_t += P_t V_j  (SS, P from smem, V MN-major) -> TMEM O_t (128 x 128 fp32)
+//   warp 0 / lane 0 : TMA producer (Q tiles once; K_j, V_j tiles through a ring, 128 rows x 128 dims each)
+//   warp 1 / lane 0 : MMA issuer   S_t = Q_t K_j^T (SS, K-major x K-major)          -> TMEM S_t (128 x 128 fp32)
+//                                  O_t += P_t V_j  (P_t from TMEM [TS] or smem [SS], V MN-major) -> TMEM O_t
 //   warps 4..7      : softmax warpgroup of tile 0 (thread r owns query row r == TMEM lane r)
 //   warps 8..11     : softmax warpgroup of tile 1
-// TMEM: S0 | S1 | O0 | O1 = 4 x 128 columns.  Online softmax with lazy rescaling: the running reference max
-// only moves when the row max grows by > 8 (log2 domain), so the O read-modify-write in TMEM is rare.
+// TMEM: S0 | S1 | O0 | O1 = 4 x 128 columns; the bf16 P_t tile aliases the first 64 columns of S_t (the MMA pipe runs
+// PV_t(j) before S_t(j+1) in issue order, so the alias is safe).  Online softmax with lazy rescaling: the reference max
+// only moves when the row max grows by > 8 (log2 domain), so the O read-modify-write in TMEM is rare.  The softmax
+// inner loop uses packed fp32x2 FFMA2/FADD2 and 3-input FMNMX3; exp2 runs on the MUFU.
 // KV rows in the padding of either stream are masked to -inf (each 128-row KV tile belongs to one stream).
 // Roofline: tensor pipe (co-limited by MUFU ex2); algorithmic FLOPs = 4 * S^2 * 128 per (batch, head).
 #include "common.cuh"
@@ -20,8 +22,13 @@ constexpr int ATT_THREADS = 384;
 constexpr int ATT_TILE = 128;                       // q rows per tile, kv rows per tile, head dim
 constexpr int ATT_HALF_BYTES = ATT_TILE * 128;      // 128 rows x 64 bf16 (one swizzled half tile) = 16 KB
 constexpr int ATT_TILE_BYTES = 2 * ATT_HALF_BYTES;  // 32 KB
-constexpr int ATT_KV_STAGES = 3;
-constexpr int ATT_SMEM = (2 + 2 + ATT_KV_STAGES) * ATT_TILE_BYTES + 256 + 1024;
+
+template <bool P_TMEM>
+struct AttCfg {
+    static constexpr int KV_STAGES = P_TMEM ? 5 : 3;                  // P in smem costs two 32 KB tiles
+    static constexpr int P_TILES = P_TMEM ? 0 : 2;
+    static constexpr int SMEM = (2 + P_TILES + KV_STAGES) * ATT_TILE_BYTES + 256 + 1024;
+};
 
 struct AttnDev {
     qie_seq seq;
@@ -38,21 +45,124 @@ __device__ __forceinline__ int kv_valid_rows(const qie_seq& s, int j) {
     return min(ATT_TILE, s.txt_rows - (r0 - s.img_pad));
 }
 
+// packed fp32x2 helpers (Blackwell FFMA2 / FADD2)
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// row max over the 128 scores of this thread's row; FULL = every kv column valid (no per-element predicate)
+template <bool FULL>
+__device__ __forceinline__ float row_max(uint32_t tS, int nv) {
+    uint32_t sa[32], sb[32];
+    float m0 = -INFINITY, m1 = -INFINITY;
+    tmem_ld32(tS, sa);
+    tmem_ld_wait();
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+        uint32_t(&cur)[32] = (ch & 1) ? sb : sa;
+        uint32_t(&nxt)[32] = (ch & 1) ? sa : sb;
+        if (ch < 3) tmem_ld32(tS + (ch + 1) * 32, nxt);
+        if constexpr (FULL) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                m0 = max3(m0, __uint_as_float(cur[i]), __uint_as_float(cur[i + 1]));
+                m1 = max3(m1, __uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3]));
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (ch * 32 + i < nv) m0 = fmaxf(m0, __uint_as_float(cur[i]));
+        }
+        if (ch < 3) tmem_ld_wait();
+    }
+    return fmaxf(m0, m1);
+}
+
+// p = exp2(s*c - m), accumulate the row sum (packed fp32x2), emit bf16 P either as packed words (TMEM) or into the
+// 128B-swizzled smem tile (row r: 16-byte chunk index XOR (r & 7))
+template <bool FULL, bool P_TMEM>
+__device__ __forceinline__ void softmax_pass2(uint32_t tS, int nv, uint64_t c2, uint64_t nm2, uint64_t& l2,
+                                              uint32_t (&pw)[64], uint8_t* prow, int r) {
+    uint32_t sa[32], sb[32];
+    tmem_ld32(tS, sa);
+    tmem_ld_wait();
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+        uint32_t(&cur)[32] = (ch & 1) ? sb : sa;
+        uint32_t(&nxt)[32] = (ch & 1) ? sa : sb;
+        if (ch < 3) tmem_ld32(tS + (ch + 1) * 32, nxt);
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            float x0, x1;
+            upk2(fma2(pk2u(cur[i], cur[i + 1]), c2, nm2), x0, x1);
+            if constexpr (!FULL) {
+                if (ch * 32 + i >= nv) x0 = -INFINITY;
+                if (ch * 32 + i + 1 >= nv) x1 = -INFINITY;
+            }
+            const float e0 = fast_exp2(x0), e1 = fast_exp2(x1);
+            l2 = add2(l2, pk2(e0, e1));
+            w[i >> 1] = pack_bf16(e0, e1);
+        }
+        if constexpr (P_TMEM) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pw[ch * 16 + i] = w[i];
+        } else {
+            uint8_t* hrow = prow + (ch >> 1) * ATT_HALF_BYTES;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const int chunk = ((ch & 1) * 4 + q4) ^ (r & 7);
+                *reinterpret_cast<uint4*>(hrow + chunk * 16) =
+                    make_uint4(w[q4 * 4], w[q4 * 4 + 1], w[q4 * 4 + 2], w[q4 * 4 + 3]);
+            }
+        }
+        if (ch < 3) tmem_ld_wait();
+    }
+}
+
+template <bool P_TMEM>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p) {
+    using C = AttCfg<P_TMEM>;
+    constexpr int KV_STAGES = C::KV_STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                                   // [2 tiles][2 halves][128 x 128 B]
-    uint8_t* sP = smem + 2 * ATT_TILE_BYTES;              // [2 tiles][2 halves]
-    uint8_t* sKV = smem + 4 * ATT_TILE_BYTES;             // [stages][2 halves]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (4 + ATT_KV_STAGES) * ATT_TILE_BYTES);
-    uint64_t* q_full = bars;            // [1]
-    uint64_t* kv_full = bars + 1;       // [3]
-    uint64_t* kv_empty = bars + 4;      // [3]
-    uint64_t* s_full = bars + 7;        // [2]  MMA -> softmax: S_t ready
-    uint64_t* p_full = bars + 9;        // [2]  softmax -> MMA: P_t in smem, S_t consumed, O_t rescaled
-    uint64_t* pv_done = bars + 11;      // [2]  MMA -> softmax: O_t += P_t V_j retired
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    uint8_t* sQ = smem;                                           // [2 tiles][2 halves][128 x 128 B]
+    uint8_t* sP = smem + 2 * ATT_TILE_BYTES;                      // [2 tiles][2 halves]   (SS variant only)
+    uint8_t* sKV = smem + (2 + C::P_TILES) * ATT_TILE_BYTES;      // [stages][2 halves]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 + C::P_TILES + KV_STAGES) * ATT_TILE_BYTES);
+    uint64_t* q_full = bars;                        // [1]
+    uint64_t* kv_full = bars + 1;                   // [KV_STAGES]
+    uint64_t* kv_empty = bars + 1 + KV_STAGES;      // [KV_STAGES]
+    uint64_t* s_full = bars + 1 + 2 * KV_STAGES;    // [2]  MMA -> softmax: S_t ready (implies PV_t of the previous tile retired)
+    uint64_t* p_full = s_full + 2;                  // [2]  softmax -> MMA: P_t written, S_t consumed, O_t rescaled
+    uint64_t* pv_done = s_full + 4;                 // [2]  MMA -> softmax: O_t += P_t V_j retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
 
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int rpb = p.seq.img_pad + p.seq.txt_pad;
@@ -67,7 +177,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p) {
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmQKV);
         mbar_init(q_full, 1);
-        for (int i = 0; i < ATT_KV_STAGES; ++i) {
+        for (int i = 0; i < KV_STAGES; ++i) {
             mbar_init(&kv_full[i], 1);
             mbar_init(&kv_empty[i], 1);
         }
@@ -103,7 +213,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p) {
                     for (int hf = 0; hf < 2; ++hf)
                         tma_load_2d(sKV + stage * ATT_TILE_BYTES + hf * ATT_HALF_BYTES, &tmQKV, col + hf * 64,
                                     row_base + j * ATT_TILE, &kv_full[stage]);
-                    if (++stage == ATT_KV_STAGES) {
+                    if (++stage == KV_STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -119,7 +229,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p) {
             int stage = 0;
             uint32_t phase = 0;
             auto advance = [&]() {
-                if (++stage == ATT_KV_STAGES) {
+                if (++stage == KV_STAGES) {
                     stage = 0;
                     phase ^= 1;
                 }
@@ -135,13 +245,19 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p) {
                 umma_commit(&s_full[t]);
             };
             auto issue_PV = [&](int t, int vstage, bool first) {   // O_t (+)= P_t V
-                const uint32_t pp = smem_u32(sP + t * ATT_TILE_BYTES), v = smem_u32(sKV + vstage * ATT_TILE_BYTES);
+                const uint32_t v = smem_u32(sKV + vstage * ATT_TILE_BYTES);
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {         // 8 x 16 kv rows
-                    const uint32_t aoff = (s >> 2) * ATT_HALF_BYTES + (s & 3) * 32;
-                    umma_ss_f16(tmem_base + 256 + t * 128, umma_desc_kmajor_sw128(pp + aoff),
-                                umma_desc_mnmajor_sw128(v + s * p.v_kstep, p.v_lbo, p.v_sbo), IDESC_O,
-                                (first && s == 0) ? 0u : 1u);
+                    const uint64_t vdesc = umma_desc_mnmajor_sw128(v + s * p.v_kstep, p.v_lbo, p.v_sbo);
+                    const uint32_t accum = (first && s == 0) ? 0u : 1u;
+                    if constexpr (P_TMEM) {
+                        // A = P_t from TMEM: 16 bf16 of K per step = 8 packed 32-bit columns
+                        umma_ts_f16(tmem_base + 256 + t * 128, tmem_base + t * 128 + s * 8, vdesc, IDESC_O, accum);
+                    } else {
+                        const uint32_t pp = smem_u32(sP + t * ATT_TILE_BYTES);
+                        const uint32_t aoff = (s >> 2) * ATT_HALF_BYTES + (s & 3) * 32;
+                        umma_ss_f16(tmem_base + 256 + t * 128, umma_desc_kmajor_sw128(pp + aoff), vdesc, IDESC_O, accum);
+                    }
                 }
                 umma_commit(&pv_done[t]);
             };
@@ -173,7 +289,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p) {
                             mbar_wait(&kv_full[kstage], kphase);
                             tc_fence_after();
                         }
-                        issue_S(t, kstage);
+                        issue_S(t, kstage);                // in-order after PV_t(j): may overwrite the aliased P_t
                         if (t == nt - 1) umma_commit(&kv_empty[kstage]);
                     }
                 }
@@ -189,82 +305,56 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p) {
             const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
             const uint32_t tS = tmem_base + lane_addr + t * 128;
             const uint32_t tO = tmem_base + lane_addr + 256 + t * 128;
-            uint8_t* prow = sP + t * ATT_TILE_BYTES + r * 128;   // row r of each 64-column half
+            [[maybe_unused]] uint8_t* prow = sP + t * ATT_TILE_BYTES + r * 128;   // row r of each 64-column half
             const float c = p.scale_log2;
-            float m_ref = -INFINITY, l = 0.f;
+            const uint64_t c2 = pk2(c, c);
+            float m_ref = -INFINITY;
+            uint64_t l2 = pk2(0.f, 0.f);
             for (int j = 0; j < n_kv; ++j) {
                 const int nv = kv_valid_rows(p.seq, j);
+                const bool full = nv == ATT_TILE;
                 mbar_wait(&s_full[t], j & 1);
                 tc_fence_after();
-                // ---- pass 1: row max ----
-                float mx = -INFINITY;
-#pragma unroll 1
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t s[32];
-                    tmem_ld32(tS + ch * 32, s);
-                    tmem_ld_wait();
-                    if (ch * 32 + 32 <= nv) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (ch * 32 + i < nv) mx = fmaxf(mx, __uint_as_float(s[i]));
-                    }
-                }
+                // ---- pass 1: row max (TMEM loads software-pipelined: chunk ch+1 is in flight while ch is reduced) ----
+                float mx = full ? row_max<true>(tS, nv) : row_max<false>(tS, nv);
                 mx *= c;
                 float alpha = 1.f;
                 const bool grow = mx > m_ref + 8.0f;   // also true on the first tile (m_ref = -inf)
                 if (grow) {
-                    alpha = exp2f(m_ref - mx);         // 0 on the first tile
+                    alpha = fast_exp2(m_ref - mx);     // 0 on the first tile
                     m_ref = mx;
-                    l *= alpha;
+                    l2 = fma2(l2, pk2(alpha, alpha), pk2(0.f, 0.f));
                 }
-                if (j > 0) {
-                    // O_t and the P_t buffer are owned by the tensor pipe until PV(j-1) retires
-                    mbar_wait(&pv_done[t], (j - 1) & 1);
-                    tc_fence_after();
-                    if (__any_sync(0xffffffffu, grow)) {
+                if (j > 0 && __any_sync(0xffffffffu, grow)) {
+                    // s_full(j) was committed after PV_t(j-1) in issue order, so O_t is quiescent here
 #pragma unroll 1
-                        for (int ch = 0; ch < 4; ++ch) {
-                            uint32_t o[32];
-                            tmem_ld32(tO + ch * 32, o);
-                            tmem_ld_wait();
+                    for (int ch = 0; ch < 4; ++ch) {
+                        uint32_t o[32];
+                        tmem_ld32(tO + ch * 32, o);
+                        tmem_ld_wait();
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                            tmem_st32(tO + ch * 32, o);
-                        }
-                        tmem_st_wait();
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(tO + ch * 32, o);
                     }
+                    tmem_st_wait();
                 }
-                // ---- pass 2: p = exp2(s*c - m_ref), row sum, bf16 P into swizzled smem ----
-#pragma unroll 1
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t s[32];
-                    tmem_ld32(tS + ch * 32, s);
-                    tmem_ld_wait();
-                    float e[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float x = fast_exp2(fmaf(__uint_as_float(s[i]), c, -m_ref));
-                        e[i] = (ch * 32 + i < nv) ? x : 0.f;
+                // ---- pass 2: p = exp2(s*c - m_ref), row sum, bf16 P ----
+                const uint64_t nm2 = pk2(-m_ref, -m_ref);
+                [[maybe_unused]] uint32_t pw[64];      // P row as 64 packed bf16x2 words (TMEM variant)
+                if (full) softmax_pass2<true, P_TMEM>(tS, nv, c2, nm2, l2, pw, prow, r);
+                else softmax_pass2<false, P_TMEM>(tS, nv, c2, nm2, l2, pw, prow, r);
+                if constexpr (P_TMEM) {
+                    // all S columns of this row are consumed: overwrite S_t[0,64) with the packed P row
+                    uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&pw[0]);
+                    uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&pw[32]);
+                    tmem_st32(tS, lo);
+                    tmem_st32(tS + 32, hi);
+                    tmem_st_wait();
+                } else {
+                    if (j > 0) {   // the P_t smem tile is read by PV_t(j-1); s_full(j) implies it retired, nothing to wait
                     }
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) l += e[i];
-                    // columns ch*32..+31 -> half (ch>>1), 16-byte chunks ((ch&1)*4 .. +3), XOR-swizzled by row&7
-                    uint8_t* hrow = prow + (ch >> 1) * ATT_HALF_BYTES;
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        uint4 u;
-                        u.x = pack_bf16(e[q4 * 8 + 0], e[q4 * 8 + 1]);
-                        u.y = pack_bf16(e[q4 * 8 + 2], e[q4 * 8 + 3]);
-                        u.z = pack_bf16(e[q4 * 8 + 4], e[q4 * 8 + 5]);
-                        u.w = pack_bf16(e[q4 * 8 + 6], e[q4 * 8 + 7]);
-                        const int chunk = ((ch & 1) * 4 + q4) ^ (r & 7);
-                        *reinterpret_cast<uint4*>(hrow + chunk * 16) = u;
-                    }
+                    fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor (async) proxy
                 }
-                fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor (async) proxy
                 tc_fence_before();          // orders this thread's TMEM loads/stores before the arrive
                 mbar_arrive(&p_full[t]);
             }
@@ -272,7 +362,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p) {
             mbar_wait(&pv_done[t], (n_kv - 1) & 1);
             tc_fence_after();
             const int qrow = q_row0 + t * ATT_TILE + r;
-            const float inv = 1.f / l;
+            float l_lo, l_hi;
+            upk2(l2, l_lo, l_hi);
+            const float inv = 1.f / (l_lo + l_hi);
             __nv_bfloat16* orow = p.out + (long long)(row_base + qrow) * D + head * ATT_TILE;
 #pragma unroll 1
             for (int ch = 0; ch < 4; ++ch) {
@@ -301,16 +393,31 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p) {
     }
 }
 
+template <bool P_TMEM>
+static int launch_attn(const CUtensorMap& tm, const AttnDev& p, dim3 grid, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        QIE_CUDA_OK(cudaFuncSetAttribute(attn_kernel<P_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         AttCfg<P_TMEM>::SMEM));
+        configured = true;
+    }
+    attn_kernel<P_TMEM><<<grid, ATT_THREADS, AttCfg<P_TMEM>::SMEM, st>>>(tm, p);
+    QIE_LAUNCH_OK("attn_kernel");
+    return QIE_OK;
+}
+
 }  // namespace qie
 
 using namespace qie;
 
+// variant 0: P through TMEM (TS MMA, default); variant 1: P through shared memory (SS MMA)
 extern "C" int qie_attn_fwd(const void* qkv, void* out, const qie_seq* seq, int num_heads, int variant, void* stream) {
     QIE_REQUIRE(qkv && out && seq, QIE_EINVAL, "qie_attn_fwd: null pointer");
     QIE_REQUIRE(seq->img_pad % 128 == 0 && seq->txt_pad % 128 == 0 && seq->batch > 0 && num_heads > 0 &&
                     seq->img_rows > 0 && seq->txt_rows > 0 && seq->img_rows > seq->img_pad - 128 &&
                     seq->txt_rows > seq->txt_pad - 128,
                 QIE_ESHAPE, "qie_attn_fwd: bad sequence layout (every 128-row KV tile needs >= 1 valid row)");
+    QIE_REQUIRE(variant == 0 || variant == 1, QIE_EINVAL, "qie_attn_fwd: variant must be 0 or 1");
     const int rpb = seq->img_pad + seq->txt_pad;
     const int D = num_heads * 128;
     CUtensorMap tm;
@@ -326,17 +433,7 @@ extern "C" int qie_attn_fwd(const void* qkv, void* out, const qie_seq* seq, int 
     p.v_lbo = ATT_HALF_BYTES;
     p.v_sbo = 1024;
     p.v_kstep = 2048;
-    if (variant == 1) {   // probe: swapped LBO/SBO roles
-        p.v_lbo = 1024;
-        p.v_sbo = ATT_HALF_BYTES;
-    }
-    static bool configured = false;
-    if (!configured) {
-        QIE_CUDA_OK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        configured = true;
-    }
     dim3 grid((rpb + 255) / 256, num_heads, seq->batch);
-    attn_kernel<<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tm, p);
-    QIE_LAUNCH_OK("attn_kernel");
-    return QIE_OK;
+    return variant == 0 ? launch_attn<true>(tm, p, grid, (cudaStream_t)stream)
+                        : launch_attn<false>(tm, p, grid, (cudaStream_t)stream);
 }

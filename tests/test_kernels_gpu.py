@@ -261,7 +261,7 @@ def test_gemm_fp8(cta_group):
 
 # ------------------------------------------------------------------ attention
 @pytest.mark.parametrize("B,img,txt,H", [(1, 256, 128, 2), (1, 384, 128, 1), (2, 200, 19, 2), (1, 1024, 219, 3)])
-@pytest.mark.parametrize("variant", [0])
+@pytest.mark.parametrize("variant", [0, 1])
 def test_attention(B, img, txt, H, variant):
     s = K.seq(B, img, txt)
     D = H * 128

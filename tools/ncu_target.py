@@ -1,0 +1,29 @@
+"""Minimal launch sequence for ncu captures: python tools/ncu_target.py attn|gemm"""
+import sys
+from pathlib import Path
+import math, torch
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent)); sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tests"))
+import kernels as K
+dev = "cuda:0"
+what = sys.argv[1]
+s = K.seq(1, 8192, 256)
+if what == "attn":
+    H = 24
+    qkv = torch.randn(K.rows(s), 3 * H * 128, device=dev).bfloat16()
+    for v in (1, 0, 1, 0):
+        K.attn(s, qkv, H, v)
+else:
+    D = 3072
+    M = K.rows(s)
+    for name, N, Kd, epi in [("qkv", 3 * D, D, K.L.EPI_QKV_NORM_ROPE), ("ff2", D, 4 * D, K.L.EPI_GATE_RESID_F32)]:
+        a = torch.randn(M, Kd, device=dev).bfloat16()
+        w = [(torch.randn(N, Kd, device=dev) / math.sqrt(Kd)).bfloat16() for _ in range(2)]
+        b = [torch.randn(N, device=dev) * 0.1 for _ in range(2)]
+        f32 = epi == K.L.EPI_GATE_RESID_F32
+        out = torch.zeros(M, N, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
+        gate = torch.randn(1, 2, 6 * D, device=dev)
+        rope = torch.randn(M, 64, 2, device=dev)
+        nw = [[torch.ones(128, device=dev) for _ in range(2)] for _ in range(2)]
+        for _ in range(2):
+            K.gemm(s, a, w, b, out, epi, gate=gate, gate_bstride=12 * D, gate_sstride=6 * D, rope=rope, qk_norm_w=nw)
+torch.cuda.synchronize()
