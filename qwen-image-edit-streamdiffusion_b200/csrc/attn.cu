@@ -19,6 +19,7 @@
 namespace qie {
 
 constexpr int ATT_THREADS = 384;
+#define QIE_ATTN_DEFAULT_VARIANT 0x20     /* P in TMEM, 2 of 8 score pairs on the FMA-pipe polynomial (best measured) */
 constexpr int ATT_TILE = 128;                       // q rows per tile, kv rows per tile, head dim
 constexpr int ATT_HALF_BYTES = ATT_TILE * 128;      // 128 rows x 64 bf16 (one swizzled half tile) = 16 KB
 constexpr int ATT_TILE_BYTES = 2 * ATT_HALF_BYTES;  // 32 KB
@@ -105,7 +106,7 @@ __device__ __forceinline__ float row_max(uint32_t tS, int nv) {
 
 // p = exp2(s*c - m), accumulate the row sum (packed fp32x2), emit bf16 P either as packed words (TMEM) or into the
 // 128B-swizzled smem tile (row r: 16-byte chunk index XOR (r & 7))
-template <bool FULL, bool P_TMEM>
+template <bool FULL, bool P_TMEM, int POLY>
 __device__ __forceinline__ void softmax_pass2(uint32_t tS, int nv, uint64_t c2, uint64_t nm2, uint64_t& l2,
                                               uint32_t (&pw)[64], uint8_t* prow, int r) {
     uint32_t sa[32], sb[32];
@@ -119,13 +120,35 @@ __device__ __forceinline__ void softmax_pass2(uint32_t tS, int nv, uint64_t c2, 
         uint32_t w[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-            float x0, x1;
-            upk2(fma2(pk2u(cur[i], cur[i + 1]), c2, nm2), x0, x1);
-            if constexpr (!FULL) {
-                if (ch * 32 + i >= nv) x0 = -INFINITY;
-                if (ch * 32 + i + 1 >= nv) x1 = -INFINITY;
+            const uint64_t X = fma2(pk2u(cur[i], cur[i + 1]), c2, nm2);
+            float e0, e1;
+            if (FULL && ((i >> 1) & 7) < POLY) {
+                // FMA-pipe exp2 (the MUFU is the co-bottleneck of this kernel): x = n + f, n = round(x), |f| <= 1/2,
+                // 2^f by a degree-3 minimax polynomial (rel err 7.5e-5 << bf16 rounding of P), 2^n via the exponent bits
+                float x0, x1;
+                upk2(X, x0, x1);
+                const uint64_t Xc = pk2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+                const uint64_t T = add2(Xc, pk2(12582912.f, 12582912.f));          // 1.5 * 2^23: low mantissa bits = n
+                const uint64_t N = add2(T, pk2(-12582912.f, -12582912.f));
+                const uint64_t Fr = fma2(N, pk2(-1.f, -1.f), Xc);
+                uint64_t P = fma2(Fr, pk2(0.0551716574f, 0.0551716574f), pk2(0.2426111400f, 0.2426111400f));
+                P = fma2(P, Fr, pk2(0.6932609677f, 0.6932609677f));
+                P = fma2(P, Fr, pk2(0.9999280572f, 0.9999280572f));
+                float t0, t1, p0, p1;
+                upk2(T, t0, t1);
+                upk2(P, p0, p1);
+                e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+                e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+            } else {
+                float x0, x1;
+                upk2(X, x0, x1);
+                if constexpr (!FULL) {
+                    if (ch * 32 + i >= nv) x0 = -INFINITY;
+                    if (ch * 32 + i + 1 >= nv) x1 = -INFINITY;
+                }
+                e0 = fast_exp2(x0);
+                e1 = fast_exp2(x1);
             }
-            const float e0 = fast_exp2(x0), e1 = fast_exp2(x1);
             l2 = add2(l2, pk2(e0, e1));
             w[i >> 1] = pack_bf16(e0, e1);
         }
@@ -145,7 +168,7 @@ __device__ __forceinline__ void softmax_pass2(uint32_t tS, int nv, uint64_t c2, 
     }
 }
 
-template <bool P_TMEM>
+template <bool P_TMEM, int POLY>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p) {
     using C = AttCfg<P_TMEM>;
@@ -341,8 +364,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p) {
                 // ---- pass 2: p = exp2(s*c - m_ref), row sum, bf16 P ----
                 const uint64_t nm2 = pk2(-m_ref, -m_ref);
                 [[maybe_unused]] uint32_t pw[64];      // P row as 64 packed bf16x2 words (TMEM variant)
-                if (full) softmax_pass2<true, P_TMEM>(tS, nv, c2, nm2, l2, pw, prow, r);
-                else softmax_pass2<false, P_TMEM>(tS, nv, c2, nm2, l2, pw, prow, r);
+                if (full) softmax_pass2<true, P_TMEM, POLY>(tS, nv, c2, nm2, l2, pw, prow, r);
+                else softmax_pass2<false, P_TMEM, POLY>(tS, nv, c2, nm2, l2, pw, prow, r);
                 if constexpr (P_TMEM) {
                     // all S columns of this row are consumed: overwrite S_t[0,64) with the packed P row
                     uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&pw[0]);
@@ -393,15 +416,15 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p) {
     }
 }
 
-template <bool P_TMEM>
+template <bool P_TMEM, int POLY>
 static int launch_attn(const CUtensorMap& tm, const AttnDev& p, dim3 grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        QIE_CUDA_OK(cudaFuncSetAttribute(attn_kernel<P_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        QIE_CUDA_OK(cudaFuncSetAttribute(attn_kernel<P_TMEM, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          AttCfg<P_TMEM>::SMEM));
         configured = true;
     }
-    attn_kernel<P_TMEM><<<grid, ATT_THREADS, AttCfg<P_TMEM>::SMEM, st>>>(tm, p);
+    attn_kernel<P_TMEM, POLY><<<grid, ATT_THREADS, AttCfg<P_TMEM>::SMEM, st>>>(tm, p);
     QIE_LAUNCH_OK("attn_kernel");
     return QIE_OK;
 }
@@ -410,14 +433,19 @@ static int launch_attn(const CUtensorMap& tm, const AttnDev& p, dim3 grid, cudaS
 
 using namespace qie;
 
-// variant 0: P through TMEM (TS MMA, default); variant 1: P through shared memory (SS MMA)
+// variant bit 0: 0 = P through TMEM (TS MMA), 1 = P through shared memory (SS MMA);
+// variant bits 4..7: how many of every 8 score pairs take the FMA-pipe polynomial exp2 instead of MUFU.EX2 (0, 2, 3, 4);
+// variant 0 selects the tuned default.
 extern "C" int qie_attn_fwd(const void* qkv, void* out, const qie_seq* seq, int num_heads, int variant, void* stream) {
     QIE_REQUIRE(qkv && out && seq, QIE_EINVAL, "qie_attn_fwd: null pointer");
     QIE_REQUIRE(seq->img_pad % 128 == 0 && seq->txt_pad % 128 == 0 && seq->batch > 0 && num_heads > 0 &&
                     seq->img_rows > 0 && seq->txt_rows > 0 && seq->img_rows > seq->img_pad - 128 &&
                     seq->txt_rows > seq->txt_pad - 128,
                 QIE_ESHAPE, "qie_attn_fwd: bad sequence layout (every 128-row KV tile needs >= 1 valid row)");
-    QIE_REQUIRE(variant == 0 || variant == 1, QIE_EINVAL, "qie_attn_fwd: variant must be 0 or 1");
+    if (variant == 0) variant = QIE_ATTN_DEFAULT_VARIANT;     // bit 8 (0x100) marks an explicit choice, e.g. 0x100 = TMEM P, all-MUFU
+    const int poly = (variant >> 4) & 15, psmem = variant & 1;
+    QIE_REQUIRE((variant & ~0x1F1) == 0 && (poly == 0 || poly == 2 || poly == 3 || poly == 4), QIE_EINVAL,
+                "qie_attn_fwd: bad variant 0x%x", variant);
     const int rpb = seq->img_pad + seq->txt_pad;
     const int D = num_heads * 128;
     CUtensorMap tm;
@@ -434,6 +462,16 @@ extern "C" int qie_attn_fwd(const void* qkv, void* out, const qie_seq* seq, int 
     p.v_sbo = 1024;
     p.v_kstep = 2048;
     dim3 grid((rpb + 255) / 256, num_heads, seq->batch);
-    return variant == 0 ? launch_attn<true>(tm, p, grid, (cudaStream_t)stream)
-                        : launch_attn<false>(tm, p, grid, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+#define QIE_ATTN_CASE(P)                                               \
+    case P:                                                            \
+        return psmem ? launch_attn<false, P>(tm, p, grid, st) : launch_attn<true, P>(tm, p, grid, st);
+    switch (poly) {
+        QIE_ATTN_CASE(0)
+        QIE_ATTN_CASE(2)
+        QIE_ATTN_CASE(3)
+        QIE_ATTN_CASE(4)
+    }
+#undef QIE_ATTN_CASE
+    return QIE_EINVAL;
 }

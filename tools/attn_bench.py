@@ -20,9 +20,9 @@ for img, txt in ((8192, 256), (8192, 219), (2048, 256)):
     qkv = torch.randn(K.rows(s), 3 * H * 128, device=dev).bfloat16()
     S = img + txt
     flops = 4.0 * S * S * 128 * H
-    for v in (0, 1):
+    for v in (0x100, 0x01, 0x20, 0x21, 0x30, 0x31, 0x40, 0x41):
         ms = bench(lambda: K.attn(s, qkv, H, v))
-        print(f"attn img={img} txt={txt} variant={v}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s", flush=True)
+        print(f"attn img={img} txt={txt} variant={v:#x}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s", flush=True)
     x = qkv[: S].reshape(1, S, 3, H, 128)
     q, k, v_ = (x[:, :, i].transpose(1, 2).contiguous() for i in range(3))
     ms = bench(lambda: F.scaled_dot_product_attention(q, k, v_))
