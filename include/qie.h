@@ -134,6 +134,31 @@ int qie_forward(qie_handle* h, const void* hidden, const void* enc, const float*
                 const int* img_shapes_host, int n_img, const qie_seq* seq, void* out,
                 void* workspace, size_t workspace_bytes, int n_blocks, void* stream);
 
+/* ---- phase-wise forward for sequence-parallel (Ulysses) callers: the caller runs NCCL all-to-alls between the QKV
+ * and ATTN phases and between ATTN and POST (replaces nothing in the reference — it has no multi-GPU attention; it is the
+ * partition north_star asks for).  `seq` then describes the LOCAL token shard of this rank and `sp` places it inside the
+ * whole sequence so the RoPE rows match.  qie_forward == qie_forward_phase(QIE_PHASE_ALL, layer -1, sp NULL). */
+#define QIE_PHASE_BEGIN 1
+#define QIE_PHASE_QKV 2
+#define QIE_PHASE_ATTN 4
+#define QIE_PHASE_POST 8
+#define QIE_PHASE_END 16
+#define QIE_PHASE_ALL 31
+typedef struct qie_sp {
+    int rank, size;
+    int img_total, txt_total;   /* tokens of the whole (unsharded) sequence */
+    int img_offset, txt_offset; /* first image / text token owned by this rank */
+} qie_sp;
+int qie_forward_phase(qie_handle* h, int phases, int layer /* -1 = all layers */, const void* hidden, const void* enc,
+                      const float* timestep, const int* img_shapes_host, int n_img, const qie_seq* seq, const qie_sp* sp,
+                      void* out, void* workspace, size_t workspace_bytes, int n_blocks, void* stream);
+/* byte offset inside the workspace of: 0 = qkv [rows, 3D] bf16, 1 = attention output [rows, D] bf16 */
+long long qie_workspace_offset(const qie_handle* h, const qie_seq* seq, int which);
+/* joint attention over an explicit list of 128-row KV tiles: qkv bf16 [n_tiles*128, 3*heads*128], tile_valid (device
+ * int[n_tiles]) = valid rows of each tile (>= 1); every row is also a query row. */
+int qie_attn_fwd_tiles(const void* qkv, void* out, int n_tiles, const int* tile_valid_dev, int num_heads, int variant,
+                       void* stream);
+
 /* replaces: the true-CFG combine + norm rescale of QwenImageEditPlusPipeline.__call__ and
  * FlowMatchEulerDiscreteScheduler.step, fused; v_uncond may be NULL (cond-only).
  *   v_* bf16 rows of `v_row_stride` elements, first `channels` used; latents bf16 [rows, channels] in/out. */

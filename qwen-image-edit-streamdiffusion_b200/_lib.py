@@ -32,6 +32,11 @@ class Seq(C.Structure):
         return self.img_pad + self.txt_pad
 
 
+class Sp(C.Structure):
+    _fields_ = [("rank", C.c_int), ("size", C.c_int), ("img_total", C.c_int), ("txt_total", C.c_int),
+                ("img_offset", C.c_int), ("txt_offset", C.c_int)]
+
+
 _P2 = C.c_void_p * 2
 
 
@@ -80,6 +85,10 @@ SYMBOLS = {
     "qie_make_seq": (_i, [_i, _i, _i, C.POINTER(Seq)]),
     "qie_workspace_bytes": (C.c_size_t, [_vp, C.POINTER(Seq)]),
     "qie_forward": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_i), _i, C.POINTER(Seq), _vp, _vp, C.c_size_t, _i, _vp]),
+    "qie_forward_phase": (_i, [_vp, _i, _i, _vp, _vp, _vp, C.POINTER(_i), _i, C.POINTER(Seq), C.POINTER(Sp), _vp, _vp,
+                               C.c_size_t, _i, _vp]),
+    "qie_workspace_offset": (_ll, [_vp, C.POINTER(Seq), _i]),
+    "qie_attn_fwd_tiles": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp]),
     "qie_cfg_euler_step": (_i, [_vp, _vp, _vp, _f, _f, _f, _i, _i, _i, _i, _vp]),
     "qie_flowmatch_sigmas": (_i, [_i, _i, C.POINTER(_f)]),
     "qie_rope_table_host": (_i, [C.POINTER(ModelCfg), C.POINTER(_i), _i, C.POINTER(Seq), C.POINTER(_f)]),

@@ -338,11 +338,17 @@ extern "C" size_t qie_workspace_bytes(const qie_handle* h, const qie_seq* seq) {
     return carve(h, seq).total;
 }
 
-extern "C" int qie_forward(qie_handle* h, const void* hidden, const void* enc, const float* timestep,
-                           const int* img_shapes_host, int n_img, const qie_seq* seq, void* out, void* workspace,
-                           size_t workspace_bytes, int n_blocks, void* stream) {
-    QIE_REQUIRE(h && hidden && enc && timestep && img_shapes_host && seq && out && workspace, QIE_EINVAL,
-                "qie_forward: null pointer");
+// One implementation for the whole step and for its phases (sequence-parallel callers interleave NCCL all-to-alls):
+//   BEGIN: RoPE table, temb + modulation vectors, stream embeddings        QKV : adaLN1 + QKV GEMM (+QK-norm+RoPE) of `layer`
+//   ATTN : joint attention of `layer`                                      POST: out-proj, adaLN2, FF of `layer`
+//   END  : norm_out + proj_out
+static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden, const void* enc, const float* timestep,
+                        const int* img_shapes_host, int n_img, const qie_seq* seq, const qie_sp* sp, void* out,
+                        void* workspace, size_t workspace_bytes, int n_blocks, void* stream) {
+    QIE_REQUIRE(h && seq && workspace, QIE_EINVAL, "qie_forward: null pointer");
+    if (phases & QIE_PHASE_BEGIN)
+        QIE_REQUIRE(hidden && enc && timestep && img_shapes_host, QIE_EINVAL, "qie_forward: null input pointer");
+    if (phases & QIE_PHASE_END) QIE_REQUIRE(out, QIE_EINVAL, "qie_forward: null output pointer");
     QIE_REQUIRE(h->has_weights, QIE_ESTATE, "qie_forward: weights not set");
     QIE_REQUIRE(seq->batch >= 1 && seq->batch <= 8, QIE_ESHAPE, "qie_forward: batch must be 1..8");
     qie_seq chk;
@@ -392,14 +398,33 @@ extern "C" int qie_forward(qie_handle* h, const void* hidden, const void* enc, c
     };
 
     // ---- RoPE table (cached per shape key; host build + one H2D copy only when the shapes change) ----
-    {
+    if (phases & QIE_PHASE_BEGIN) {
         std::vector<int> key(img_shapes_host, img_shapes_host + 3 * n_img);
         key.push_back(seq->img_rows);
         key.push_back(seq->txt_rows);
+        if (sp) {
+            const int extra[6] = {sp->rank, sp->size, sp->img_total, sp->txt_total, sp->img_offset, sp->txt_offset};
+            key.insert(key.end(), extra, extra + 6);
+        }
         if (key != h->rope_key || !h->d_rope) {
             std::vector<float> tab((size_t)rpb * 128);
-            rc = qie_rope_table_host(&h->cfg, img_shapes_host, n_img, seq, tab.data());
-            if (rc) return rc;
+            if (!sp) {
+                rc = qie_rope_table_host(&h->cfg, img_shapes_host, n_img, seq, tab.data());
+                if (rc) return rc;
+            } else {
+                // sequence-parallel shard: build the table of the WHOLE sequence, keep the rows this rank owns
+                QIE_REQUIRE(seq->batch == 1 && sp->img_offset + seq->img_rows <= sp->img_total &&
+                                sp->txt_offset + seq->txt_rows <= sp->txt_total,
+                            QIE_ESHAPE, "qie_forward: bad sequence-parallel shard");
+                qie_seq full;
+                if ((rc = qie_make_seq(1, sp->img_total, sp->txt_total, &full))) return rc;
+                std::vector<float> all((size_t)(full.img_pad + full.txt_pad) * 128);
+                if ((rc = qie_rope_table_host(&h->cfg, img_shapes_host, n_img, &full, all.data()))) return rc;
+                for (size_t i = 0; i < tab.size(); i += 2) { tab[i] = 1.f; tab[i + 1] = 0.f; }
+                memcpy(tab.data(), all.data() + (size_t)sp->img_offset * 128, (size_t)seq->img_rows * 128 * sizeof(float));
+                memcpy(tab.data() + (size_t)seq->img_pad * 128, all.data() + (size_t)(full.img_pad + sp->txt_offset) * 128,
+                       (size_t)seq->txt_rows * 128 * sizeof(float));
+            }
             if (h->rope_rows < rpb) {
                 cudaFree(h->d_rope);
                 h->d_rope = nullptr;
@@ -419,6 +444,7 @@ extern "C" int qie_forward(qie_handle* h, const void* hidden, const void* enc, c
     float* mod = temb + 8 * (size_t)D;                       // [B][L*2*6D]
     const long long modN = (long long)nb * 12 * D;   // batch stride of the modulation table
     float* fin = mod + 8 * (size_t)L * 12 * D;                     // [B][2D]
+    if (phases & QIE_PHASE_BEGIN) {
     if ((rc = qie_timestep_proj(timestep, tproj, B, 0, st))) return rc;
     if ((rc = qie_gemv(tproj, h->w.t1_w, h->w.t1_b, t1, B, D, 256, 0, st))) return rc;
     if ((rc = qie_gemv(t1, h->w.t2_w, h->w.t2_b, temb, B, D, D, 1, st))) return rc;
@@ -443,11 +469,14 @@ extern "C" int qie_forward(qie_handle* h, const void* hidden, const void* enc, c
         t.out = resid; t.ldo = D; t.N = D; t.K = h->cfg.joint_dim; t.streams = 2; t.epilogue = QIE_EPI_F32;
         if ((rc = run_gemm(t))) return rc;
     }
+    }   // QIE_PHASE_BEGIN
 
     // ---- transformer blocks ----
-    for (int l = 0; l < nb; ++l) {
+    const int l_begin = layer < 0 ? 0 : layer, l_end = layer < 0 ? nb : (layer < nb ? layer + 1 : nb);
+    for (int l = l_begin; l < l_end; ++l) {
         const qie_block_weights& bw = h->blocks[l];
         const float* m = mod + (size_t)l * 12 * D;   // + b*modN + s*6D
+        if (phases & QIE_PHASE_QKV) {
         // adaLN 1 -> xm
         if ((rc = run_ln(m, modN, 6LL * D, 0, D, fp8)))
             return rc;
@@ -470,7 +499,9 @@ extern "C" int qie_forward(qie_handle* h, const void* hidden, const void* enc, c
                 if ((rc = qie_qk_norm_rope(qkv, h->d_rope, nw, h->cfg.num_heads, 1e-6f, seq, st))) return rc;
             }
         }
-        if ((rc = run_attn())) return rc;
+        }   // QIE_PHASE_QKV
+        if ((phases & QIE_PHASE_ATTN) && (rc = run_attn())) return rc;
+        if (phases & QIE_PHASE_POST) {
         {   // out-proj + gate1 * y + residual
             qie_gemm_args g{};
             g.N = D; g.K = D; g.streams = 3; g.out = resid; g.ldo = D; g.epilogue = QIE_EPI_GATE_RESID_F32;
@@ -517,9 +548,11 @@ extern "C" int qie_forward(qie_handle* h, const void* hidden, const void* enc, c
             }
             if ((rc = run_gemm(g))) return rc;
         }
+        }   // QIE_PHASE_POST
     }
 
     // ---- norm_out (AdaLayerNormContinuous: scale first, then shift) + proj_out on the image stream ----
+    if (!(phases & QIE_PHASE_END)) return QIE_OK;
     if ((rc = run_ln(fin, 2LL * D, 0, D, 0, false))) return rc;
     {
         qie_gemm_args g{};
@@ -535,4 +568,27 @@ extern "C" int qie_forward(qie_handle* h, const void* hidden, const void* enc, c
         if ((rc = unpack_rows(outp, out, B, seq->img_rows, seq->img_pad, h->cfg.out_dim, st))) return rc;
     }
     return QIE_OK;
+}
+
+extern "C" int qie_forward(qie_handle* h, const void* hidden, const void* enc, const float* timestep,
+                           const int* img_shapes_host, int n_img, const qie_seq* seq, void* out, void* workspace,
+                           size_t workspace_bytes, int n_blocks, void* stream) {
+    return forward_impl(h, QIE_PHASE_ALL, -1, hidden, enc, timestep, img_shapes_host, n_img, seq, nullptr, out, workspace,
+                        workspace_bytes, n_blocks, stream);
+}
+
+extern "C" int qie_forward_phase(qie_handle* h, int phases, int layer, const void* hidden, const void* enc,
+                                 const float* timestep, const int* img_shapes_host, int n_img, const qie_seq* seq,
+                                 const qie_sp* sp, void* out, void* workspace, size_t workspace_bytes, int n_blocks,
+                                 void* stream) {
+    QIE_REQUIRE(phases > 0 && (phases & ~QIE_PHASE_ALL) == 0, QIE_EINVAL, "qie_forward_phase: bad phase mask %d", phases);
+    return forward_impl(h, phases, layer, hidden, enc, timestep, img_shapes_host, n_img, seq, sp, out, workspace,
+                        workspace_bytes, n_blocks, stream);
+}
+
+// byte offset of an activation buffer inside the workspace: 0 = qkv [rows, 3D] bf16, 1 = attention output [rows, D] bf16
+extern "C" long long qie_workspace_offset(const qie_handle* h, const qie_seq* seq, int which) {
+    if (!h || !seq) return -1;
+    const Ws ws = carve(h, seq);
+    return which == 0 ? (long long)ws.qkv : which == 1 ? (long long)ws.attn : -1;
 }

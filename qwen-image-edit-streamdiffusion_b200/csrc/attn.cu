@@ -38,6 +38,7 @@ struct AttnDev {
     float scale_log2;        // softmax scale * log2(e)
     uint32_t v_lbo, v_sbo;   // V (MN-major) descriptor strides, bytes
     uint32_t v_kstep;        // byte advance of the V descriptor per 16 kv rows
+    const int* tile_valid;   // optional: valid rows per 128-row KV tile (sequence-parallel layout); NULL = from seq
 };
 
 __device__ __forceinline__ int kv_valid_rows(const qie_seq& s, int j) {
@@ -334,7 +335,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p) {
             float m_ref = -INFINITY;
             uint64_t l2 = pk2(0.f, 0.f);
             for (int j = 0; j < n_kv; ++j) {
-                const int nv = kv_valid_rows(p.seq, j);
+                const int nv = p.tile_valid ? __ldg(p.tile_valid + j) : kv_valid_rows(p.seq, j);
                 const bool full = nv == ATT_TILE;
                 mbar_wait(&s_full[t], j & 1);
                 tc_fence_after();
@@ -433,6 +434,18 @@ static int launch_attn(const CUtensorMap& tm, const AttnDev& p, dim3 grid, cudaS
 
 using namespace qie;
 
+static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int* tile_valid, int num_heads, int variant,
+                       void* stream);
+
+extern "C" int qie_attn_fwd_tiles(const void* qkv, void* out, int n_tiles, const int* tile_valid_dev, int num_heads,
+                                  int variant, void* stream) {
+    QIE_REQUIRE(qkv && out && tile_valid_dev && n_tiles > 0 && num_heads > 0, QIE_EINVAL, "qie_attn_fwd_tiles: bad argument");
+    qie_seq s{};
+    s.batch = 1;
+    s.img_rows = s.img_pad = n_tiles * 128;
+    return attn_launch(qkv, out, &s, tile_valid_dev, num_heads, variant, stream);
+}
+
 // variant bit 0: 0 = P through TMEM (TS MMA), 1 = P through shared memory (SS MMA);
 // variant bits 4..7: how many of every 8 score pairs take the FMA-pipe polynomial exp2 instead of MUFU.EX2 (0, 2, 3, 4);
 // variant 0 selects the tuned default.
@@ -442,6 +455,11 @@ extern "C" int qie_attn_fwd(const void* qkv, void* out, const qie_seq* seq, int 
                     seq->img_rows > 0 && seq->txt_rows > 0 && seq->img_rows > seq->img_pad - 128 &&
                     seq->txt_rows > seq->txt_pad - 128,
                 QIE_ESHAPE, "qie_attn_fwd: bad sequence layout (every 128-row KV tile needs >= 1 valid row)");
+    return attn_launch(qkv, out, seq, nullptr, num_heads, variant, stream);
+}
+
+static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int* tile_valid, int num_heads, int variant,
+                       void* stream) {
     if (variant == 0) variant = QIE_ATTN_DEFAULT_VARIANT;     // bit 8 (0x100) marks an explicit choice, e.g. 0x100 = TMEM P, all-MUFU
     const int poly = (variant >> 4) & 15, psmem = variant & 1;
     QIE_REQUIRE((variant & ~0x1F1) == 0 && (poly == 0 || poly == 2 || poly == 3 || poly == 4), QIE_EINVAL,
@@ -454,6 +472,7 @@ extern "C" int qie_attn_fwd(const void* qkv, void* out, const qie_seq* seq, int 
     AttnDev p{};
     p.seq = *seq;
     p.H = num_heads;
+    p.tile_valid = tile_valid;
     p.out = (__nv_bfloat16*)out;
     p.scale_log2 = 0.08838834764831845f * 1.4426950408889634f;   // 1/sqrt(128) * log2(e)
     // V tile in smem: two halves (64 dims each, 16 KB apart) of 128 kv rows x 128 B, 128B-swizzled by TMA.
