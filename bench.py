@@ -169,7 +169,8 @@ def workload_config(args, n):
                         "edit, 2-step Lightning schedule, " + ("true-CFG 4.0 (cond+uncond)" if args.cfg else "cond-only"),
             "img_tokens": N_IMG_TOK, "txt_tokens": T_TXT, "forwards_per_image": STEPS_PER_IMAGE * (2 if args.cfg else 1),
             "layers": args.layers, "precision": args.precision,
-            "parallelism": f"dp{n}: one independent frame stream per GPU, weights replicated, no data-path collective",
+            "parallelism": (f"dp{n}: one independent frame stream per GPU, weights replicated, no data-path collective"
+                            if args.mode == "dp" else f"{args.mode} over {n} GPUs: ONE frame, weights replicated"),
             "l2": "inputs larger than L2: 40.9 GB of weights + 0.6 GB of activations stream through the 126 MB L2 every forward"}
 
 
@@ -204,12 +205,38 @@ def run_ours(args):
         host["unc"] = unc.cpu().pin_memory()
     out_host = torch.empty(lat.shape, dtype=torch.bfloat16).pin_memory()
 
+    # --mode dp (default): every rank edits its own frame.  Other modes spread ONE frame over the ranks (strong scaling):
+    #   cfgpair: cond / uncond branches on 2 GPU groups;  ulysses: sequence-parallel forward;  cfg+ulysses: both.
+    runner, layout = model, None
+    if args.mode != "dp":
+        if world < 2:
+            raise SystemExit("--mode cfgpair/ulysses needs torchrun with >= 2 ranks")
+        branches = 2 if "cfg" in args.mode else 1
+        if branches == 2 and not args.cfg:
+            raise SystemExit("--mode cfgpair needs --cfg")
+        layout = qie_b200.make_layout(world, rank, branches)
+        if layout.sp_size > 1:
+            runner = qie_b200.UlyssesTransformer(model, layout.sp_group)
+        g = torch.Generator(device=dev).manual_seed(1)      # one frame: identical inputs on every rank
+        lat = torch.randn(1, N_NOISE, 64, generator=g, device=dev).bfloat16()
+        img_lat = torch.randn(1, N_IMG_TOK - N_NOISE, 64, generator=g, device=dev).bfloat16()
+        cond = (torch.randn(1, T_TXT, cfg.joint_attention_dim, generator=g, device=dev) * 3).bfloat16()
+        unc = (torch.randn(1, T_TXT, cfg.joint_attention_dim, generator=g, device=dev) * 3).bfloat16() if args.cfg else None
+        host = {k: v.cpu().pin_memory() for k, v in (("lat", lat), ("img", img_lat), ("cond", cond))}
+        if unc is not None:
+            host["unc"] = unc.cpu().pin_memory()
+
+    def denoise(l, i, c, u):
+        if layout is not None and layout.cfg_branches == 2:
+            return qie_b200.run_denoise_parallel(runner, layout, l, i, c, u, IMG_SHAPES, STEPS_PER_IMAGE, 4.0)
+        return qie_b200.run_denoise(runner, l, i, c, IMG_SHAPES, STEPS_PER_IMAGE, u, 4.0)
+
     def step_resident():
-        return qie_b200.run_denoise(model, lat, img_lat, cond, IMG_SHAPES, STEPS_PER_IMAGE, unc, 4.0)
+        return denoise(lat, img_lat, cond, unc)
 
     def step_e2e():
         d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        res = qie_b200.run_denoise(model, d["lat"], d["img"], d["cond"], IMG_SHAPES, STEPS_PER_IMAGE, d.get("unc"), 4.0)
+        res = denoise(d["lat"], d["img"], d["cond"], d.get("unc"))
         out_host.copy_(res, non_blocking=True)
         torch.cuda.current_stream().synchronize()      # the caller reads the edited latents
         return res
@@ -242,7 +269,8 @@ def run_ours(args):
         launches = L.qie_launch_count() - n0
     clocks = clk.summary()
     ms_step = ms_total / args.steps
-    value = world * 1e3 / ms_step
+    frames = world if args.mode == "dp" else 1     # frames finished per step by the whole job
+    value = frames * 1e3 / ms_step
 
     for _ in range(2):
         step_e2e()
@@ -251,7 +279,7 @@ def run_ours(args):
     d2h = out_host.numel() * out_host.element_size()
 
     # live per-kernel-class CUDA-event timing of the same step (events on the launching stream, inside qie_forward)
-    model.profile(True)
+    model.profile(args.mode == "dp")
     step_resident()
     torch.cuda.synchronize()
     model.read_profile()
@@ -291,10 +319,10 @@ def run_ours(args):
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if args.mode == "dp" else "strong", "vs_baseline": None,
                 "dtype": "bf16" if args.precision == "bf16" else "fp8_e4m3(w8a8)+bf16", "data": "synthetic",
                 "config": workload_config(args, world), "clocks": clocks,
-                "e2e": {"value": world * 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "e2e": {"value": frames * 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "dit_forward_ms": ms_step / (STEPS_PER_IMAGE * (2 if args.cfg else 1))}
@@ -312,6 +340,7 @@ def main():
     ap.add_argument("--cfg", action="store_true", help="true-CFG (cond + uncond forwards per step)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp8"])
     ap.add_argument("--layers", type=int, default=60)
+    ap.add_argument("--mode", default="dp", choices=["dp", "cfgpair", "ulysses", "cfg+ulysses"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
