@@ -310,7 +310,7 @@ class QwenImageTransformer2DModelRef(nn.Module):
                 attention_kwargs=None, controlnet_block_samples=None, return_dict=True,
                 num_blocks: Optional[int] = None):
         h = self.img_in(hidden_states)
-        ts = timestep.to(h.dtype)
+        ts = timestep.to(device=h.device, dtype=h.dtype)
         e = self.txt_in(self.txt_norm(encoder_hidden_states))
         temb = self.time_text_embed(ts, h)
         img_freqs, txt_freqs = self.pos_embed(img_shapes, txt_seq_lens)
