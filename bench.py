@@ -195,6 +195,8 @@ def run_ours(args):
     model = qie_b200.B200QwenImageTransformer2DModel.from_random(cfg, seed=0, device=dev)
     if args.precision == "fp8":
         model.set_precision("fp8")
+    if args.attn_variant:
+        model.set_option(1, args.attn_variant)
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     lat = torch.randn(1, N_NOISE, 64, generator=g, device=dev).bfloat16()
     img_lat = torch.randn(1, N_IMG_TOK - N_NOISE, 64, generator=g, device=dev).bfloat16()
@@ -340,6 +342,7 @@ def main():
     ap.add_argument("--cfg", action="store_true", help="true-CFG (cond + uncond forwards per step)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp8"])
     ap.add_argument("--layers", type=int, default=60)
+    ap.add_argument("--attn-variant", type=lambda x: int(x, 0), default=0, help="attention kernel variant (0 = library default)")
     ap.add_argument("--mode", default="dp", choices=["dp", "cfgpair", "ulysses", "cfg+ulysses"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -19,7 +19,7 @@
 namespace qie {
 
 constexpr int ATT_THREADS = 384;
-#define QIE_ATTN_DEFAULT_VARIANT 0x20     /* P in TMEM, 2 of 8 score pairs on the FMA-pipe polynomial (best measured) */
+#define QIE_ATTN_DEFAULT_VARIANT 0x102    /* CTA-pair kernel, all exp2 on the MUFU (best measured in-step) */
 constexpr int ATT_TILE = 128;                       // q rows per tile, kv rows per tile, head dim
 constexpr int ATT_HALF_BYTES = ATT_TILE * 128;      // 128 rows x 64 bf16 (one swizzled half tile) = 16 KB
 constexpr int ATT_TILE_BYTES = 2 * ATT_HALF_BYTES;  // 32 KB
@@ -430,6 +430,333 @@ static int launch_attn(const CUtensorMap& tm, const AttnDev& p, dim3 grid, cudaS
     return QIE_OK;
 }
 
+// Single-pass softmax tile for a FULL 128-column tile when a finite reference m is already known: p = exp2(s*c - m) is
+// computed straight away while the maximum of x = s*c - m is tracked; the caller redoes the tile (rare) only when some
+// row's x exceeded the lazy-rescale threshold.  Saves the separate row-max pass (4 TMEM loads + waits) of every tile.
+template <int POLY>
+__device__ __forceinline__ float softmax_fast(uint32_t tS, uint64_t c2, uint64_t nm2, uint64_t& l2, uint32_t (&pw)[64]) {
+    uint32_t sa[32], sb[32];
+    float m0 = -INFINITY, m1 = -INFINITY;
+    tmem_ld32(tS, sa);
+    tmem_ld_wait();
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+        uint32_t(&cur)[32] = (ch & 1) ? sb : sa;
+        uint32_t(&nxt)[32] = (ch & 1) ? sa : sb;
+        if (ch < 3) tmem_ld32(tS + (ch + 1) * 32, nxt);
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            const uint64_t X = fma2(pk2u(cur[i], cur[i + 1]), c2, nm2);
+            float x0, x1, e0, e1;
+            upk2(X, x0, x1);
+            if ((i >> 1) & 1) m1 = max3(m1, x0, x1);
+            else m0 = max3(m0, x0, x1);
+            if (((i >> 1) & 7) < POLY) {
+                const uint64_t Xc = pk2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+                const uint64_t T = add2(Xc, pk2(12582912.f, 12582912.f));
+                const uint64_t N = add2(T, pk2(-12582912.f, -12582912.f));
+                const uint64_t Fr = fma2(N, pk2(-1.f, -1.f), Xc);
+                uint64_t P = fma2(Fr, pk2(0.0551716574f, 0.0551716574f), pk2(0.2426111400f, 0.2426111400f));
+                P = fma2(P, Fr, pk2(0.6932609677f, 0.6932609677f));
+                P = fma2(P, Fr, pk2(0.9999280572f, 0.9999280572f));
+                float t0, t1, p0, p1;
+                upk2(T, t0, t1);
+                upk2(P, p0, p1);
+                e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+                e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+            } else {
+                e0 = fast_exp2(x0);
+                e1 = fast_exp2(x1);
+            }
+            l2 = add2(l2, pk2(e0, e1));
+            pw[ch * 16 + (i >> 1)] = pack_bf16(e0, e1);
+        }
+        if (ch < 3) tmem_ld_wait();
+    }
+    return fmaxf(m0, m1);
+}
+
+// =====================================================================================================================
+// CTA-pair attention (cta_group::2).  A cluster of two CTAs owns 256 query rows of one (batch, head): CTA r holds Q rows
+// [128 r, 128 r + 128).  Every MMA is ONE 256-row tcgen05.mma.cta_group::2 issued by the leader:
+//     S  = Q K_j^T : each CTA stages HALF of K_j (64 kv rows)   -> K smem reads and L2->SM bytes halved vs the 1-CTA tile
+//     O += P V_j   : P from each CTA's TMEM (TS), each CTA stages HALF of V_j (64 of the 128 head dims, MN-major)
+// One Q tile per SM leaves TMEM room for TWO independent softmax streams: warpgroup b owns the KV tiles j = b (mod 2),
+// with its own S buffer, its own running (max, sum) and its own O accumulator (S0 | S1 | O0 | O1 = 512 columns) — a
+// split-KV decomposition inside the CTA, merged once in the epilogue (O = sum_b 2^(m_b-m) O_b / sum_b 2^(m_b-m) l_b).
+// There is no per-tile synchronisation between the warpgroups, so while one is on the MUFU (exp2) the other reads TMEM /
+// reduces maxima, and the tensor pipe always has the other stream's S / PV to run: S_b(j+2) is issued right after PV_b(j).
+// Work unit = 256 query rows on one TPC -> 792 units on 74 TPCs for config 2 (10.7 rounds, 97 % balance; 89 % before).
+// =====================================================================================================================
+constexpr int AT2_THREADS = 384;
+constexpr int AT2_SLOT_BYTES = 16 * 1024;      // half of a K or V tile
+constexpr int AT2_STAGES = 10;
+constexpr int AT2_SMEM = ATT_TILE_BYTES + AT2_STAGES * AT2_SLOT_BYTES + 2048 + 512 + 1024;
+
+template <int POLY>
+__global__ void __launch_bounds__(AT2_THREADS, 1)
+attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm64, const AttnDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                                       // [2 d-halves][128 rows x 128 B]
+    uint8_t* sKV = smem + ATT_TILE_BYTES;                     // [stages][16 KB]
+    float2* xchg = reinterpret_cast<float2*>(sKV + AT2_STAGES * AT2_SLOT_BYTES);   // [2 WGs][128 rows] (m_ref, l)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xchg) + 2048);
+    uint64_t* q_full = bars;                       // leader
+    uint64_t* kv_full = bars + 1;                  // [stages] leader
+    uint64_t* kv_empty = kv_full + AT2_STAGES;     // [stages] both (multicast commit)
+    uint64_t* s_full = kv_empty + AT2_STAGES;      // [2] both
+    uint64_t* p_full = s_full + 2;                 // [2] leader, 8 warp arrivals (4 softmax warps x 2 CTAs)
+    uint64_t* pv_done = p_full + 2;                // [2] both
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int cta_rank = (int)cluster_ctarank();
+    const int rpb = p.seq.img_pad + p.seq.txt_pad;
+    const int n_kv = rpb / ATT_TILE;               // >= 2 (both streams are non-empty)
+    const int head = blockIdx.y, b = blockIdx.z;
+    const int q_row0 = (blockIdx.x >> 1) * 2 * ATT_TILE + cta_rank * ATT_TILE;   // my Q tile, row inside the batch element
+    const bool q_valid = q_row0 < rpb;
+    const int D = p.H * ATT_TILE;
+    const int colQ = head * ATT_TILE, colK = D + head * ATT_TILE, colV = 2 * D + head * ATT_TILE;
+    const int row_base = b * rpb;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm128);
+        tma_prefetch_desc(&tm64);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < AT2_STAGES; ++i) {
+            mbar_init(&kv_full[i], 1);
+            mbar_init(&kv_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_full[i], 8);
+            mbar_init(&pv_done[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_cg2<512>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= TMA producer (each CTA: own Q tile, its half of every K / V tile) =================
+            if (cta_rank == 0) mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+            const int qr = q_valid ? q_row0 : 0;     // an out-of-range peer tile still feeds the pair MMA (never stored)
+            for (int hf = 0; hf < 2; ++hf)
+                tma_load_2d_cg2(sQ + hf * ATT_HALF_BYTES, &tm128, colQ + hf * 64, row_base + qr, leader_smem_u32(q_full));
+            int stage = 0;
+            uint32_t phase = 0;
+            auto load = [&](bool is_v, int j) {
+                mbar_wait(&kv_empty[stage], phase ^ 1);
+                if (cta_rank == 0) mbar_expect_tx(&kv_full[stage], 2 * AT2_SLOT_BYTES);
+                const uint32_t bar = leader_smem_u32(&kv_full[stage]);
+                uint8_t* dst = sKV + stage * AT2_SLOT_BYTES;
+                if (is_v) {      // 128 kv rows x my 64 head dims
+                    tma_load_2d_cg2(dst, &tm128, colV + cta_rank * 64, row_base + j * ATT_TILE, bar);
+                } else {         // my 64 kv rows x 128 head dims, as two 64-dim halves of 8 KB
+                    for (int hf = 0; hf < 2; ++hf)
+                        tma_load_2d_cg2(dst + hf * 8192, &tm64, colK + hf * 64, row_base + j * ATT_TILE + cta_rank * 64, bar);
+                }
+                if (++stage == AT2_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            };
+            load(false, 0);
+            load(false, 1);
+            for (int j = 0; j < n_kv; ++j) {
+                load(true, j);
+                if (j + 2 < n_kv) load(false, j + 2);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && cta_rank == 0) {
+            // ================= MMA issuer (leader) =================
+            constexpr uint32_t IDESC_S = umma_idesc_bf16(256, 128, false);
+            constexpr uint32_t IDESC_O = umma_idesc_bf16(256, 128, true);   // B = V is MN-major
+            int stage = 0;
+            uint32_t phase = 0;
+            auto next_slot = [&]() -> uint32_t {      // waits for the next ring slot, returns its smem address
+                mbar_wait(&kv_full[stage], phase);
+                tc_fence_after();
+                return smem_u32(sKV + stage * AT2_SLOT_BYTES);
+            };
+            auto release_slot = [&]() {
+                umma_commit_cg2(&kv_empty[stage], 3);
+                if (++stage == AT2_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            };
+            auto issue_S = [&](int buf) {
+                const uint32_t k = next_slot(), q = smem_u32(sQ);
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {   // 8 x 16 head dims
+                    umma_ss_f16_cg2(tmem_base + buf * 128,
+                                    umma_desc_kmajor_sw128(q + (s >> 2) * ATT_HALF_BYTES + (s & 3) * 32),
+                                    umma_desc_kmajor_sw128(k + (s >> 2) * 8192 + (s & 3) * 32), IDESC_S, s ? 1u : 0u);
+                }
+                umma_commit_cg2(&s_full[buf], 3);
+                release_slot();
+            };
+            mbar_wait(q_full, 0);
+            tc_fence_after();
+            issue_S(0);
+            issue_S(1);
+            for (int j = 0; j < n_kv; ++j) {
+                const int buf = j & 1;
+                const uint32_t v = next_slot();
+                mbar_wait(&p_full[buf], (j >> 1) & 1);     // both CTAs: P(j) in TMEM over S_buf, O_buf rescaled
+                tc_fence_after();
+#pragma unroll
+                for (int s = 0; s < 8; ++s)     // 8 x 16 kv rows; A = P (8 packed columns per step)
+                    umma_ts_f16_cg2(tmem_base + 256 + buf * 128, tmem_base + buf * 128 + s * 8,
+                                    umma_desc_mnmajor_sw128(v + s * 2048, ATT_HALF_BYTES, 1024), IDESC_O,
+                                    (j < 2 && s == 0) ? 0u : 1u);
+                umma_commit_cg2(&pv_done[buf], 3);
+                release_slot();
+                if (j + 2 < n_kv) issue_S(buf);            // in order after PV(j): may overwrite the aliased P(j)
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= softmax: warpgroup wg (warps 4-7 / 8-11) owns KV tiles j = wg, wg+2, ... =================
+        const int wg = (warp - 4) >> 2;
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;                    // row inside my Q tile == TMEM lane
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        const uint32_t tS = tmem_base + lane_addr + wg * 128;
+        const uint32_t tO = tmem_base + lane_addr + 256 + wg * 128;
+        const float c = p.scale_log2;
+        const uint64_t c2 = pk2(c, c);
+        float m_ref = -INFINITY;
+        uint64_t l2 = pk2(0.f, 0.f);
+        int it = 0;
+        for (int j = wg; j < n_kv; j += 2, ++it) {
+            const int nv = p.tile_valid ? __ldg(p.tile_valid + j) : kv_valid_rows(p.seq, j);
+            const bool full = nv == ATT_TILE;
+            mbar_wait(&s_full[wg], it & 1);
+            tc_fence_after();
+            uint32_t pw[64];
+            bool done = false;
+            if (full && it > 0) {
+                // fast path: one pass against the current reference; redo only if a row max grew by more than the threshold
+                const uint64_t l2_before = l2;
+                const float xmax = softmax_fast<POLY>(tS, c2, pk2(-m_ref, -m_ref), l2, pw);
+                done = !__any_sync(0xffffffffu, xmax > 8.0f);
+                if (!done) l2 = l2_before;
+            }
+            if (!done) {
+                float mx = (full ? row_max<true>(tS, nv) : row_max<false>(tS, nv)) * c;
+                float alpha = 1.f;
+                const bool grow = mx > m_ref + 8.0f;
+                if (grow) {
+                    alpha = fast_exp2(m_ref - mx);
+                    m_ref = mx;
+                    l2 = fma2(l2, pk2(alpha, alpha), pk2(0.f, 0.f));
+                }
+                if (it > 0 && __any_sync(0xffffffffu, grow)) {
+                    // s_full of this tile was committed after PV of my previous tile in issue order: O_wg is quiescent
+#pragma unroll 1
+                    for (int ch = 0; ch < 4; ++ch) {
+                        uint32_t o[32];
+                        tmem_ld32(tO + ch * 32, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(tO + ch * 32, o);
+                    }
+                    tmem_st_wait();
+                }
+                const uint64_t nm2 = pk2(-m_ref, -m_ref);
+                if (full) softmax_pass2<true, true, POLY>(tS, nv, c2, nm2, l2, pw, nullptr, r);
+                else softmax_pass2<false, true, POLY>(tS, nv, c2, nm2, l2, pw, nullptr, r);
+            }
+            {
+                uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&pw[0]);
+                uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&pw[32]);
+                tmem_st32(tS, lo);
+                tmem_st32(tS + 32, hi);
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(leader_smem_u32(&p_full[wg]));
+        }
+        // ---- epilogue: merge the two softmax streams of this row, O / l -> bf16 -> global ----
+        float l_lo, l_hi;
+        upk2(l2, l_lo, l_hi);
+        xchg[wg * 128 + r] = make_float2(m_ref, l_lo + l_hi);
+        mbar_wait(&pv_done[wg], (it - 1) & 1);             // my last PV retired (it >= 1)
+        tc_fence_after();
+        tc_fence_before();
+        named_bar_sync(1, 256);                            // both streams of every row are final
+        tc_fence_after();
+        const float2 mine = xchg[wg * 128 + r], other = xchg[(wg ^ 1) * 128 + r];
+        const float m = fmaxf(mine.x, other.x);
+        const float a_me = fast_exp2(mine.x - m), a_ot = fast_exp2(other.x - m);
+        const float inv = 1.f / (mine.y * a_me + other.y * a_ot);
+        const float f0 = (wg == 0 ? a_me : a_ot) * inv, f1 = (wg == 0 ? a_ot : a_me) * inv;   // factors of O0, O1
+        if (q_valid) {
+            // warpgroup wg writes head dims [64 wg, 64 wg + 64) of its rows
+            const uint32_t tO0 = tmem_base + lane_addr + 256 + wg * 64, tO1 = tO0 + 128;
+            __nv_bfloat16* orow = p.out + (long long)(row_base + q_row0 + r) * D + head * ATT_TILE + wg * 64;
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ++ch) {
+                uint32_t o0[32], o1[32];
+                tmem_ld32(tO0 + ch * 32, o0);
+                tmem_ld32(tO1 + ch * 32, o1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        v[i] = __uint_as_float(o0[q4 * 8 + i]) * f0 + __uint_as_float(o1[q4 * 8 + i]) * f1;
+                    *reinterpret_cast<uint4*>(orow + ch * 32 + q4 * 8) =
+                        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                }
+            }
+        }
+    }
+
+    __syncwarp();
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_cg2<512>(tmem_base);
+    }
+}
+
+template <int POLY>
+static int launch_attn_pair(const CUtensorMap& tm128, const CUtensorMap& tm64, const AttnDev& p, dim3 grid, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        QIE_CUDA_OK(cudaFuncSetAttribute(attn_pair_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(AT2_THREADS);
+    cfg.dynamicSmemBytes = AT2_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_pair_kernel<POLY>, tm128, tm64, p));
+    QIE_LAUNCH_OK("attn_pair_kernel");
+    return QIE_OK;
+}
+
 }  // namespace qie
 
 using namespace qie;
@@ -461,8 +788,8 @@ extern "C" int qie_attn_fwd(const void* qkv, void* out, const qie_seq* seq, int 
 static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int* tile_valid, int num_heads, int variant,
                        void* stream) {
     if (variant == 0) variant = QIE_ATTN_DEFAULT_VARIANT;     // bit 8 (0x100) marks an explicit choice, e.g. 0x100 = TMEM P, all-MUFU
-    const int poly = (variant >> 4) & 15, psmem = variant & 1;
-    QIE_REQUIRE((variant & ~0x1F1) == 0 && (poly == 0 || poly == 2 || poly == 3 || poly == 4), QIE_EINVAL,
+    const int poly = (variant >> 4) & 15, psmem = variant & 1, pair = (variant >> 1) & 1;
+    QIE_REQUIRE((variant & ~0x1F3) == 0 && (poly == 0 || poly == 2 || poly == 3 || poly == 4) && !(pair && psmem), QIE_EINVAL,
                 "qie_attn_fwd: bad variant 0x%x", variant);
     const int rpb = seq->img_pad + seq->txt_pad;
     const int D = num_heads * 128;
@@ -482,6 +809,18 @@ static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int
     p.v_kstep = 2048;
     dim3 grid((rpb + 255) / 256, num_heads, seq->batch);
     cudaStream_t st = (cudaStream_t)stream;
+    if (pair) {   // CTA-pair kernel: two CTAs per 256 query rows, K tiles staged as 64-row halves
+        CUtensorMap tm64;
+        rc = make_tmap_2d(&tm64, qkv, (uint64_t)seq->batch * rpb, (uint64_t)3 * D, (uint64_t)3 * D * 2, 64, 64, 2);
+        if (rc) return rc;
+        grid.x *= 2;
+        switch (poly) {
+            case 0: return launch_attn_pair<0>(tm, tm64, p, grid, st);
+            case 2: return launch_attn_pair<2>(tm, tm64, p, grid, st);
+            case 3: return launch_attn_pair<3>(tm, tm64, p, grid, st);
+            case 4: return launch_attn_pair<4>(tm, tm64, p, grid, st);
+        }
+    }
 #define QIE_ATTN_CASE(P)                                               \
     case P:                                                            \
         return psmem ? launch_attn<false, P>(tm, p, grid, st) : launch_attn<true, P>(tm, p, grid, st);

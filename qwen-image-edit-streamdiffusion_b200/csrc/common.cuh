@@ -189,7 +189,9 @@ __device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMa
         : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+    // default semantics (release at CTA scope): the .release.cluster form costs a MEMBAR.ALL.GPU + ERRBAR per arrive;
+    // the data handed over here lives in TMEM and is ordered by tcgen05.wait::st + tcgen05.fence::before_thread_sync
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_dst) {   // one warp in EACH CTA of the pair
@@ -223,6 +225,20 @@ __device__ __forceinline__ void umma_ss_f8_cg2(uint32_t d_tmem, uint64_t a_desc,
         "}" ::"r"(d_tmem),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+__device__ __forceinline__ void umma_ts_f16_cg2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 // commit of the pair's MMAs, arriving on the mbarrier at this smem offset in every CTA of `cta_mask`
 __device__ __forceinline__ void umma_commit_cg2(uint64_t* bar, uint16_t cta_mask) {

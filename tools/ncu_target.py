@@ -10,7 +10,7 @@ s = K.seq(1, 8192, 256)
 if what == "attn":
     H = 24
     qkv = torch.randn(K.rows(s), 3 * H * 128, device=dev).bfloat16()
-    for v in (1, 0, 1, 0):
+    for v in ([int(x, 0) for x in sys.argv[2:]] or [1, 0, 1, 0]):
         K.attn(s, qkv, H, v)
 else:
     D = 3072
