@@ -193,8 +193,8 @@ def run_ours(args):
 
     cfg = qie_b200.QwenImageDiTConfig(num_layers=args.layers)
     model = qie_b200.B200QwenImageTransformer2DModel.from_random(cfg, seed=0, device=dev)
-    if args.precision == "fp8":
-        model.set_precision("fp8")
+    if args.precision != "bf16":
+        model.set_precision(args.precision)
     if args.attn_variant:
         model.set_option(1, args.attn_variant)
     g = torch.Generator(device=dev).manual_seed(1 + rank)
@@ -295,7 +295,7 @@ def run_ours(args):
     gemm_tf = gm["work"] / (gm["ms"] * 1e-3) / 1e12 if gm["ms"] else 0.0
     attn_tf = at["work"] / (at["ms"] * 1e-3) / 1e12 if at["ms"] else 0.0
     tot_ms = sum(v["ms"] for v in prof.values())
-    roofline = {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 bf16, all linears of the step)",
+    roofline = {"bound": "tensor", "kernel": f"gemm_kernel (tcgen05 {args.precision}, all linears of the step)",
                 "achieved": gemm_tf, "peak": sus, "unit": "TFLOP/s", "frac": gemm_tf / sus, "traffic": None,
                 "peak_source": f"{which} bf16_tflops_sustained (kernel timed inside a long step); burst {burst}",
                 "launches_per_step": gm["launches"] / args.steps, "avg_launch_ms": gm["ms"] / max(gm["launches"], 1),
@@ -322,7 +322,7 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if args.mode == "dp" else "strong", "vs_baseline": None,
-                "dtype": "bf16" if args.precision == "bf16" else "fp8_e4m3(w8a8)+bf16", "data": "synthetic",
+                "dtype": {"bf16": "bf16", "fp8": "fp8_e4m3(w8a8)+bf16", "int8": "int8(w8a8)+bf16"}[args.precision], "data": "synthetic",
                 "config": workload_config(args, world), "clocks": clocks,
                 "e2e": {"value": frames * 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e},
@@ -340,7 +340,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cfg", action="store_true", help="true-CFG (cond + uncond forwards per step)")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp8"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp8", "int8"])
     ap.add_argument("--layers", type=int, default=60)
     ap.add_argument("--attn-variant", type=lambda x: int(x, 0), default=0, help="attention kernel variant (0 = library default)")
     ap.add_argument("--mode", default="dp", choices=["dp", "cfgpair", "ulysses", "cfg+ulysses"])

@@ -109,7 +109,7 @@ int qie_device_sm_count(void);
 int qie_create(const qie_model_cfg* cfg, int device, qie_handle** out);
 int qie_destroy(qie_handle* h);
 int qie_set_weights(qie_handle* h, const qie_weights* w);
-/* 0 = bf16 GEMMs, 1 = FP8 e4m3 W8A8 GEMMs (needs the *_w8 pointers); replaces int8_linear.py /
+/* 0 = bf16 GEMMs, 1 = FP8 e4m3 W8A8, 2 = INT8 W8A8 (both need the *_w8 / *_ws pointers); replaces int8_linear.py /
  * cublaslt_int8.py / triton_int8_gemm.py named at README.md:136-141 */
 int qie_set_precision(qie_handle* h, int mode);
 /* tuning/debug knobs outside the reference surface: key 0 = fuse QK-norm+RoPE into the QKV GEMM epilogue (default 1),
@@ -118,6 +118,7 @@ int qie_set_option(qie_handle* h, int key, int value);
 /* measurement aids: kernels launched by the library so far; event-timed ms / algorithmic work / launches per kernel
  * class since the last read (class 0 GEMM [FLOP], 1 attention [FLOP], 2 adaLN [bytes], 3 modulation GEMV [bytes], 4 other) */
 unsigned long long qie_launch_count(void);
+int qie_tune(int key, int value);   /* kernel launch-shape experiments: 0 adaLN threads/block, 1 adaLN smem reservation */
 int qie_profile_read(qie_handle* h, double* ms5, double* work5, int* launches5);
 /* host helper: pad a (img_rows, txt_rows) pair into the joint layout */
 int qie_make_seq(int batch, int img_rows, int txt_rows, qie_seq* out);
@@ -196,7 +197,7 @@ typedef struct qie_gemm_args {
     long long gate_bstride, gate_sstride;
     const float* rope;        /* QKV_NORM_ROPE: [rows_per_batch, 64, 2] */
     const float* qk_norm_w[2][2]; /* QKV_NORM_ROPE: [stream][q/k] -> [128] */
-    int fp8;                  /* 1: a / w are e4m3, a_scale [rows] and w_scale[stream][N] dequantise in the epilogue */
+    int fp8;                  /* operand type: 0 bf16; 1 e4m3, 2 int8: a_scale [rows] and w_scale[stream][N] dequantise in the epilogue */
     const float* a_scale;
     const float* w_scale[2];
     int block_n;              /* 0 = auto */
@@ -213,8 +214,8 @@ int qie_attn_fwd(const void* qkv, void* out, const qie_seq* seq, int num_heads, 
  * shift/scale for (b, stream) at mod[b*mod_bstride + stream*mod_sstride + {shift_off,scale_off} + c].
  * if out8/out_scale non-NULL also emits e4m3 rows with per-row scale (for the FP8 GEMMs). */
 int qie_ln_modulate(const float* x, const float* mod, long long mod_bstride, long long mod_sstride, int shift_off,
-                    int scale_off, void* out, void* out8, float* out_scale, int D, float eps, const qie_seq* seq,
-                    void* stream);
+                    int scale_off, void* out, void* out8, float* out_scale, int qmode /* 1 e4m3, 2 int8 */, int D, float eps,
+                    const qie_seq* seq, void* stream);
 /* y[b, n] = bias[n] + sum_k act(x[b,k]) * W[n,k]; act: 0 none, 1 SiLU. W bf16 [N,K], x/y fp32. batch<=8 */
 int qie_gemv(const float* x, const void* w, const float* bias, float* y, int batch, long long N, int K, int act,
              void* stream);
@@ -228,8 +229,9 @@ int qie_rmsnorm_pack(const void* x, const float* w, void* out, int batch, int n,
                      void* stream);
 /* copy [B, n, C] bf16 -> [B, n_pad, C] with zero pad rows */
 int qie_pack_rows(const void* x, void* out, int batch, int n, int n_pad, int C, void* stream);
-/* per-row dynamic e4m3 quantisation: x bf16 [rows, K] -> q e4m3 [rows,K], scale fp32 [rows] */
-int qie_quant_rows_e4m3(const void* x, void* q, float* scale, long long rows, int K, void* stream);
+/* per-row dynamic symmetric quantisation: x bf16 [rows, K] -> q [rows,K] (qmode 1: e4m3, scale amax/448; 2: int8, scale
+ * amax/127, round-to-nearest-even), scale fp32 [rows] */
+int qie_quant_rows(const void* x, void* q, float* scale, long long rows, int K, int qmode, void* stream);
 
 #ifdef __cplusplus
 }

@@ -81,6 +81,7 @@ SYMBOLS = {
     "qie_set_precision": (_i, [_vp, _i]),
     "qie_set_option": (_i, [_vp, _i, _i]),
     "qie_launch_count": (C.c_ulonglong, []),
+    "qie_tune": (_i, [_i, _i]),
     "qie_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i)]),
     "qie_make_seq": (_i, [_i, _i, _i, C.POINTER(Seq)]),
     "qie_workspace_bytes": (C.c_size_t, [_vp, C.POINTER(Seq)]),
@@ -94,13 +95,13 @@ SYMBOLS = {
     "qie_rope_table_host": (_i, [C.POINTER(ModelCfg), C.POINTER(_i), _i, C.POINTER(Seq), C.POINTER(_f)]),
     "qie_gemm": (_i, [C.POINTER(GemmArgs), C.POINTER(Seq), _vp]),
     "qie_attn_fwd": (_i, [_vp, _vp, C.POINTER(Seq), _i, _i, _vp]),
-    "qie_ln_modulate": (_i, [_vp, _vp, _ll, _ll, _i, _i, _vp, _vp, _vp, _i, _f, C.POINTER(Seq), _vp]),
+    "qie_ln_modulate": (_i, [_vp, _vp, _ll, _ll, _i, _i, _vp, _vp, _vp, _i, _i, _f, C.POINTER(Seq), _vp]),
     "qie_gemv": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp]),
     "qie_timestep_proj": (_i, [_vp, _vp, _i, _i, _vp]),
     "qie_qk_norm_rope": (_i, [_vp, _vp, C.POINTER(_vp), _i, _f, C.POINTER(Seq), _vp]),
     "qie_rmsnorm_pack": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "qie_pack_rows": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
-    "qie_quant_rows_e4m3": (_i, [_vp, _vp, _vp, _ll, _i, _vp]),
+    "qie_quant_rows": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp]),
 }
 
 _lib = None

@@ -256,8 +256,8 @@ extern "C" int qie_set_weights(qie_handle* h, const qie_weights* w) {
 
 extern "C" int qie_set_precision(qie_handle* h, int mode) {
     QIE_REQUIRE(h, QIE_EINVAL, "qie_set_precision: null handle");
-    QIE_REQUIRE(mode >= 0 && mode <= 1, QIE_EINVAL, "qie_set_precision: mode must be 0 (bf16) or 1 (fp8)");
-    if (mode == 1) {
+    QIE_REQUIRE(mode >= 0 && mode <= 2, QIE_EINVAL, "qie_set_precision: mode must be 0 (bf16), 1 (fp8 e4m3) or 2 (int8)");
+    if (mode >= 1) {
         QIE_REQUIRE(h->has_weights, QIE_ESTATE, "qie_set_precision: set weights first");
         for (auto& b : h->blocks)
             for (int s = 0; s < 2; ++s)
@@ -378,7 +378,7 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
     void* ffh8 = W + ws.ffh8;
     float* xscale = (float*)(W + ws.xscale);   // [3][rows]: xm, attn, ffh scales
     const size_t rows = (size_t)B * rpb;
-    const bool fp8 = h->precision == 1;
+    const int fp8 = h->precision;   // 0 bf16, 1 e4m3 W8A8, 2 int8 W8A8
 
     const double valid_rows = (double)B * (seq->img_rows + seq->txt_rows);
     auto run_gemm = [&](qie_gemm_args& g) -> int {
@@ -393,8 +393,8 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
     };
     auto run_ln = [&](const float* mv, long long bs, long long ss, int sh, int sc, bool q8) -> int {
         ProfScope ps(h, st, 2, valid_rows * D * 6.0);
-        return qie_ln_modulate(resid, mv, bs, ss, sh, sc, xm, q8 ? xm8 : nullptr, q8 ? xscale : nullptr, D, 1e-6f, seq,
-                               st);
+        return qie_ln_modulate(resid, mv, bs, ss, sh, sc, xm, q8 ? xm8 : nullptr, q8 ? xscale : nullptr, h->precision, D,
+                               1e-6f, seq, st);
     };
 
     // ---- RoPE table (cached per shape key; host build + one H2D copy only when the shapes change) ----
@@ -513,8 +513,8 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
             }
             g.a = attn;
             if (fp8) {
-                if ((rc = qie_quant_rows_e4m3(attn, attn8, xscale + rows, (long long)rows, D, st))) return rc;
-                g.a = attn8; g.fp8 = 1; g.a_scale = xscale + rows;
+                if ((rc = qie_quant_rows(attn, attn8, xscale + rows, (long long)rows, D, h->precision, st))) return rc;
+                g.a = attn8; g.fp8 = fp8; g.a_scale = xscale + rows;
             }
             if ((rc = run_gemm(g))) return rc;
         }
@@ -543,8 +543,8 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
             }
             g.a = ffh;
             if (fp8) {
-                if ((rc = qie_quant_rows_e4m3(ffh, ffh8, xscale + 2 * rows, (long long)rows, 4 * D, st))) return rc;
-                g.a = ffh8; g.fp8 = 1; g.a_scale = xscale + 2 * rows;
+                if ((rc = qie_quant_rows(ffh, ffh8, xscale + 2 * rows, (long long)rows, 4 * D, h->precision, st))) return rc;
+                g.a = ffh8; g.fp8 = fp8; g.a_scale = xscale + 2 * rows;
             }
             if ((rc = run_gemm(g))) return rc;
         }

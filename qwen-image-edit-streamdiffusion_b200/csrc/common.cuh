@@ -299,6 +299,35 @@ __host__ __device__ constexpr uint32_t umma_idesc_e4m3(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::i8 with signed int8 x signed int8 -> int32 (c_format S32 = 2, a_format = b_format = 1)
+__host__ __device__ constexpr uint32_t umma_idesc_s8(int M, int N) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// one tcgen05.mma with both operands from smem; QT 0 = bf16 (kind::f16), 1 = e4m3 (kind::f8f6f4), 2 = int8 (kind::i8)
+template <int QT, int CG>
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+#define QIE_UMMA(KIND, GROUP)                                                              \
+    asm volatile(                                                                          \
+        "{\n\t"                                                                            \
+        ".reg .pred p;\n\t"                                                                \
+        "setp.ne.b32 p, %4, 0;\n\t"                                                        \
+        "tcgen05.mma.cta_group::" GROUP ".kind::" KIND " [%0], %1, %2, %3, p;\n\t"         \
+        "}" ::"r"(d_tmem),                                                                 \
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)                              \
+        : "memory")
+    if constexpr (CG == 2) {
+        if constexpr (QT == 2) QIE_UMMA("i8", "2");
+        else if constexpr (QT == 1) QIE_UMMA("f8f6f4", "2");
+        else QIE_UMMA("f16", "2");
+    } else {
+        if constexpr (QT == 2) QIE_UMMA("i8", "1");
+        else if constexpr (QT == 1) QIE_UMMA("f8f6f4", "1");
+        else QIE_UMMA("f16", "1");
+    }
+#undef QIE_UMMA
+}
+
 // ---- small math ----
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -322,6 +351,11 @@ __device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float
     const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
     const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
     return lo | (hi << 16);
+}
+__device__ __forceinline__ uint32_t pack_s8x4(float a, float b, float c, float d) {   // round-to-nearest-even, clamp +-127
+    const int ia = max(-127, min(127, __float2int_rn(a))), ib = max(-127, min(127, __float2int_rn(b)));
+    const int ic = max(-127, min(127, __float2int_rn(c))), id = max(-127, min(127, __float2int_rn(d)));
+    return (uint32_t)(ia & 0xFF) | ((uint32_t)(ib & 0xFF) << 8) | ((uint32_t)(ic & 0xFF) << 16) | ((uint32_t)(id & 0xFF) << 24);
 }
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;

@@ -81,14 +81,17 @@ __device__ __forceinline__ MUnit decode_munit(const GemmDev& p, int mu) {
     return r;
 }
 
-template <int BN, int EPI, bool FP8, int CG>
+template <int BN, int EPI, int QT, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
             const __grid_constant__ CUtensorMap tmB1, const GemmDev p) {
     using S = GemmSmem<BN, CG>;
     constexpr int STAGES = S::STAGES;
+    constexpr bool FP8 = QT != 0;                // 8-bit operands (e4m3 or int8): 128-element k-blocks, dequant epilogue
     constexpr int BK = FP8 ? 128 : 64;           // elements per k-block
-    constexpr uint32_t IDESC = FP8 ? umma_idesc_e4m3(GEMM_BM * CG, BN) : umma_idesc_bf16(GEMM_BM * CG, BN);
+    constexpr uint32_t IDESC = QT == 2 ? umma_idesc_s8(GEMM_BM * CG, BN)
+                               : QT == 1 ? umma_idesc_e4m3(GEMM_BM * CG, BN) : umma_idesc_bf16(GEMM_BM * CG, BN);
+    auto accf = [](uint32_t r) -> float { return QT == 2 ? (float)(int)r : __uint_as_float(r); };   // int32 accumulators for kind::i8
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -188,13 +191,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {   // 4 x 32 B along the swizzled 128 B row
                         const uint32_t accum = (kb | k) ? 1u : 0u;
-                        if constexpr (CG == 2) {
-                            if constexpr (FP8) umma_ss_f8_cg2(d_tmem, da + 2 * k, db + 2 * k, IDESC, accum);
-                            else umma_ss_f16_cg2(d_tmem, da + 2 * k, db + 2 * k, IDESC, accum);
-                        } else {
-                            if constexpr (FP8) umma_ss_f8(d_tmem, da + 2 * k, db + 2 * k, IDESC, accum);
-                            else umma_ss_f16(d_tmem, da + 2 * k, db + 2 * k, IDESC, accum);
-                        }
+                        umma_ss<QT, CG>(d_tmem, da + 2 * k, db + 2 * k, IDESC, accum);
                     }
                     // frees the smem slot (in both CTAs of a pair) when these MMAs retire
                     if constexpr (CG == 2) umma_commit_cg2(&empty_bar[stage], 3);
@@ -252,8 +249,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 float* srow = reinterpret_cast<float*>(stg + lane * S::EPI_ROW_BYTES);
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                    float4 f = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
-                                           __uint_as_float(r[i + 3]));
+                    float4 f = make_float4(accf(r[i]), accf(r[i + 1]), accf(r[i + 2]), accf(r[i + 3]));
                     if (add_bias_first) {
                         const float4 bv = *reinterpret_cast<const float4*>(bias + nb * BN + c * 32 + i);
                         if constexpr (FP8) {
@@ -291,10 +287,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                         ws = *reinterpret_cast<const float4*>(p.w_scale[m.s] + nb * BN + cc * 32 + i);
                                         ws.x *= as_row; ws.y *= as_row; ws.z *= as_row; ws.w *= as_row;
                                     }
-                                    const float a0 = __uint_as_float(r[i]) * ws.x + bv.x;
-                                    const float a1 = __uint_as_float(r[i + 1]) * ws.y + bv.y;
-                                    const float a2 = __uint_as_float(r[i + 2]) * ws.z + bv.z;
-                                    const float a3 = __uint_as_float(r[i + 3]) * ws.w + bv.w;
+                                    const float a0 = accf(r[i]) * ws.x + bv.x;
+                                    const float a1 = accf(r[i + 1]) * ws.y + bv.y;
+                                    const float a2 = accf(r[i + 2]) * ws.z + bv.z;
+                                    const float a3 = accf(r[i + 3]) * ws.w + bv.w;
                                     ss += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
                                 }
                             }
@@ -407,13 +403,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
 }
 
-template <int BN, int EPI, bool FP8, int CG>
+template <int BN, int EPI, int QT, int CG>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB0, const CUtensorMap& tmB1, const GemmDev& p,
                        int num_tiles, cudaStream_t st) {
     using S = GemmSmem<BN, CG>;
     static bool configured = false;
     if (!configured) {
-        QIE_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, EPI, FP8, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        QIE_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, EPI, QT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          S::TOTAL));
         configured = true;
     }
@@ -431,21 +427,21 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB0, const CU
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, FP8, CG>, tmA, tmB0, tmB1, p));
+    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, QT, CG>, tmA, tmB0, tmB1, p));
     QIE_LAUNCH_OK("gemm_kernel");
     return QIE_OK;
 }
 
-template <int BN, bool FP8, int CG>
+template <int BN, int QT, int CG>
 static int dispatch_epi(int epi, const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap& b1, const GemmDev& p,
                         int tiles, cudaStream_t st) {
     switch (epi) {
-        case QIE_EPI_BF16: return launch_gemm<BN, QIE_EPI_BF16, FP8, CG>(a, b0, b1, p, tiles, st);
-        case QIE_EPI_GELU_BF16: return launch_gemm<BN, QIE_EPI_GELU_BF16, FP8, CG>(a, b0, b1, p, tiles, st);
-        case QIE_EPI_F32: return launch_gemm<BN, QIE_EPI_F32, FP8, CG>(a, b0, b1, p, tiles, st);
-        case QIE_EPI_GATE_RESID_F32: return launch_gemm<BN, QIE_EPI_GATE_RESID_F32, FP8, CG>(a, b0, b1, p, tiles, st);
+        case QIE_EPI_BF16: return launch_gemm<BN, QIE_EPI_BF16, QT, CG>(a, b0, b1, p, tiles, st);
+        case QIE_EPI_GELU_BF16: return launch_gemm<BN, QIE_EPI_GELU_BF16, QT, CG>(a, b0, b1, p, tiles, st);
+        case QIE_EPI_F32: return launch_gemm<BN, QIE_EPI_F32, QT, CG>(a, b0, b1, p, tiles, st);
+        case QIE_EPI_GATE_RESID_F32: return launch_gemm<BN, QIE_EPI_GATE_RESID_F32, QT, CG>(a, b0, b1, p, tiles, st);
         case QIE_EPI_QKV_NORM_ROPE:
-            if constexpr (BN >= 128) return launch_gemm<BN, QIE_EPI_QKV_NORM_ROPE, FP8, CG>(a, b0, b1, p, tiles, st);
+            if constexpr (BN >= 128) return launch_gemm<BN, QIE_EPI_QKV_NORM_ROPE, QT, CG>(a, b0, b1, p, tiles, st);
     }
     set_error("qie_gemm: unsupported epilogue %d for block_n %d", epi, BN);
     return QIE_EINVAL;
@@ -458,6 +454,7 @@ using namespace qie;
 extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream) {
     QIE_REQUIRE(g && seq && g->a && g->out, QIE_EINVAL, "qie_gemm: null pointer");
     QIE_REQUIRE(g->streams >= 1 && g->streams <= 3, QIE_EINVAL, "qie_gemm: streams mask must be 1..3");
+    QIE_REQUIRE(g->fp8 >= 0 && g->fp8 <= 2, QIE_EINVAL, "qie_gemm: fp8 (operand type) must be 0 bf16, 1 e4m3, 2 int8");
     QIE_REQUIRE(seq->img_pad % 128 == 0 && seq->txt_pad % 128 == 0 && seq->img_pad >= seq->img_rows &&
                     seq->txt_pad >= seq->txt_rows && seq->batch > 0,
                 QIE_ESHAPE, "qie_gemm: bad sequence layout");
@@ -539,10 +536,12 @@ extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream
         case 128: return dispatch_epi<128, F8, CGV>(g->epilogue, tmA, tmB[0], tmB[1], p, tiles, st);      \
         default: return dispatch_epi<256, F8, CGV>(g->epilogue, tmA, tmB[0], tmB[1], p, tiles, st);       \
     }
-    if (g->fp8) {
-        if (cg == 2) { QIE_GEMM_DISPATCH(true, 2) } else { QIE_GEMM_DISPATCH(true, 1) }
+    if (g->fp8 == 1) {
+        if (cg == 2) { QIE_GEMM_DISPATCH(1, 2) } else { QIE_GEMM_DISPATCH(1, 1) }
+    } else if (g->fp8 == 2) {
+        if (cg == 2) { QIE_GEMM_DISPATCH(2, 2) } else { QIE_GEMM_DISPATCH(2, 1) }
     } else {
-        if (cg == 2) { QIE_GEMM_DISPATCH(false, 2) } else { QIE_GEMM_DISPATCH(false, 1) }
+        if (cg == 2) { QIE_GEMM_DISPATCH(0, 2) } else { QIE_GEMM_DISPATCH(0, 1) }
     }
 #undef QIE_GEMM_DISPATCH
     set_error("qie_gemm: no kernel for block_n=%d cta_group=%d", bn, cg);

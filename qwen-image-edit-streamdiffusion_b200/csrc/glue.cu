@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ x
                                                      long long mod_bstride, long long mod_sstride, int shift_off,
                                                      int scale_off, __nv_bfloat16* __restrict__ out,
                                                      uint8_t* __restrict__ out8, float* __restrict__ out_scale,
-                                                     float eps, qie_seq seq) {
+                                                     int qmode, float eps, qie_seq seq) {
     constexpr int D = NV * 128;
     const int rpb = seq.img_pad + seq.txt_pad;
     const long long rows = (long long)seq.batch * rpb;
@@ -120,14 +120,18 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ x
         *reinterpret_cast<uint2*>(orow + (i * 32 + lane) * 4) =
             make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
     }
-    if (out8) {   // per-token dynamic e4m3 quantisation for the FP8 GEMM path
+    if (out8) {   // per-token dynamic quantisation for the W8A8 GEMM paths (quantises the bf16-rounded values)
         amax = warp_max(amax);
-        const float scale = amax > 0.f ? amax / 448.f : 1.f;
-        const float inv = 1.f / scale;
+        amax = __bfloat162float(__float2bfloat16(amax));
+        const float qmax = qmode == 2 ? 127.f : 448.f;
+        const float scale = amax > 0.f ? amax / qmax : 1.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
+            const float4 b = make_float4(__bfloat162float(__float2bfloat16(v[i].x)), __bfloat162float(__float2bfloat16(v[i].y)),
+                                         __bfloat162float(__float2bfloat16(v[i].z)), __bfloat162float(__float2bfloat16(v[i].w)));
             *reinterpret_cast<uint32_t*>(out8 + row * D + (i * 32 + lane) * 4) =
-                pack_e4m3x4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+                qmode == 2 ? pack_s8x4(b.x / scale, b.y / scale, b.z / scale, b.w / scale)
+                           : pack_e4m3x4(b.x / scale, b.y / scale, b.z / scale, b.w / scale);
         }
         if (lane == 0) out_scale[row] = scale;
     }
@@ -295,9 +299,9 @@ __global__ void unpack_rows_kernel(const uint4* __restrict__ x, uint4* __restric
 }
 
 // per-row dynamic e4m3 quantisation (activation side of the W8A8 path; README.md:140 "quantize + matmul + dequantize")
-__global__ void __launch_bounds__(256) quant_rows_e4m3_kernel(const __nv_bfloat16* __restrict__ x,
-                                                              uint8_t* __restrict__ q, float* __restrict__ scale,
-                                                              long long rows, int K) {
+__global__ void __launch_bounds__(256) quant_rows_kernel(const __nv_bfloat16* __restrict__ x,
+                                                         uint8_t* __restrict__ q, float* __restrict__ scale,
+                                                         long long rows, int K, int qmode) {
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = lane_id();
@@ -310,13 +314,18 @@ __global__ void __launch_bounds__(256) quant_rows_e4m3_kernel(const __nv_bfloat1
                                  fmaxf(fmaxf(fabsf(cc.x), fabsf(cc.y)), fmaxf(fabsf(d.x), fabsf(d.y)))));
     }
     amax = warp_max(amax);
-    const float s = amax > 0.f ? amax / 448.f : 1.f, inv = 1.f / s;
+    const float s = amax > 0.f ? amax / (qmode == 2 ? 127.f : 448.f) : 1.f;   // true divisions: bit-equal to torch.round(x / s) of the restated W8A8 reference
     for (int c = lane * 8; c < K; c += 256) {
         uint4 u = *reinterpret_cast<const uint4*>(xr + c);
         float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
         uint2 o;
-        o.x = pack_e4m3x4(a.x * inv, a.y * inv, b.x * inv, b.y * inv);
-        o.y = pack_e4m3x4(cc.x * inv, cc.y * inv, d.x * inv, d.y * inv);
+        if (qmode == 2) {
+            o.x = pack_s8x4(a.x / s, a.y / s, b.x / s, b.y / s);
+            o.y = pack_s8x4(cc.x / s, cc.y / s, d.x / s, d.y / s);
+        } else {
+            o.x = pack_e4m3x4(a.x / s, a.y / s, b.x / s, b.y / s);
+            o.y = pack_e4m3x4(cc.x / s, cc.y / s, d.x / s, d.y / s);
+        }
         *reinterpret_cast<uint2*>(q + row * K + c) = o;
     }
     if (lane == 0) scale[row] = s;
@@ -344,18 +353,35 @@ extern "C" int qie_cfg_euler_step(const void* v_cond, const void* v_uncond, void
     return QIE_OK;
 }
 
+namespace qie {
+int g_ln_threads = 128, g_ln_smem = 0;   // 128 threads (4 rows) per block measured best: 4350 GB/s vs 3700 at 256
+}
+// experiment knobs (not part of the reference surface): 0 = adaLN threads per block, 1 = adaLN dynamic smem reservation
+extern "C" int qie_tune(int key, int value) {
+    if (key == 0 && (value == 64 || value == 128 || value == 256 || value == 512)) { qie::g_ln_threads = value; return QIE_OK; }
+    if (key == 1 && value >= 0 && value <= 200 * 1024) { qie::g_ln_smem = value; return QIE_OK; }
+    ::qie::set_error("qie_tune: bad key/value %d/%d", key, value);
+    return QIE_EINVAL;
+}
+
 extern "C" int qie_ln_modulate(const float* x, const float* mod, long long mod_bstride, long long mod_sstride,
-                               int shift_off, int scale_off, void* out, void* out8, float* out_scale, int D, float eps,
-                               const qie_seq* seq, void* stream) {
+                               int shift_off, int scale_off, void* out, void* out8, float* out_scale, int qmode, int D,
+                               float eps, const qie_seq* seq, void* stream) {
     QIE_REQUIRE(x && mod && out && seq, QIE_EINVAL, "qie_ln_modulate: null pointer");
     QIE_REQUIRE((out8 == nullptr) == (out_scale == nullptr), QIE_EINVAL, "qie_ln_modulate: out8/out_scale mismatch");
     const long long rows = (long long)seq->batch * (seq->img_pad + seq->txt_pad);
-    const int blocks = (int)((rows + 7) / 8);
+    // Several short waves instead of one: a dynamic-smem reservation caps the resident blocks per SM so that the stores of
+    // one wave overlap the loads of the next (one warp per row, the whole row in registers).
+    const int threads = g_ln_threads, wpb = threads / 32;
+    const int blocks = (int)((rows + wpb - 1) / wpb);
+    const size_t dsm = (size_t)g_ln_smem;
     cudaStream_t st = (cudaStream_t)stream;
 #define QIE_LN_CASE(NV)                                                                                       \
     case NV:                                                                                                  \
-        ln_mod_kernel<NV><<<blocks, 256, 0, st>>>(x, mod, mod_bstride, mod_sstride, shift_off, scale_off,     \
-                                                  (__nv_bfloat16*)out, (uint8_t*)out8, out_scale, eps, *seq); \
+        if (dsm > 48 * 1024)                                                                                  \
+            QIE_CUDA_OK(cudaFuncSetAttribute(ln_mod_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm)); \
+        ln_mod_kernel<NV><<<blocks, threads, dsm, st>>>(x, mod, mod_bstride, mod_sstride, shift_off, scale_off, \
+                                                  (__nv_bfloat16*)out, (uint8_t*)out8, out_scale, qmode, eps, *seq); \
         break;
     QIE_REQUIRE(D % 128 == 0, QIE_ESHAPE, "qie_ln_modulate: D=%d not a multiple of 128", D);
     switch (D / 128) {
@@ -462,11 +488,11 @@ int unpack_rows(const void* x, void* out, int batch, int n, int n_pad, int C, cu
 }
 }  // namespace qie
 
-extern "C" int qie_quant_rows_e4m3(const void* x, void* q, float* scale, long long rows, int K, void* stream) {
-    QIE_REQUIRE(x && q && scale, QIE_EINVAL, "qie_quant_rows_e4m3: null pointer");
-    QIE_REQUIRE(K % 8 == 0, QIE_ESHAPE, "qie_quant_rows_e4m3: K %% 8 != 0");
-    quant_rows_e4m3_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, (uint8_t*)q, scale, rows, K);
-    QIE_LAUNCH_OK("quant_rows_e4m3_kernel");
+extern "C" int qie_quant_rows(const void* x, void* q, float* scale, long long rows, int K, int qmode, void* stream) {
+    QIE_REQUIRE(x && q && scale, QIE_EINVAL, "qie_quant_rows: null pointer");
+    QIE_REQUIRE(K % 8 == 0 && (qmode == 1 || qmode == 2), QIE_ESHAPE, "qie_quant_rows: K %% 8 != 0 or bad mode");
+    quant_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (uint8_t*)q, scale, rows, K, qmode);
+    QIE_LAUNCH_OK("quant_rows_kernel");
     return QIE_OK;
 }

@@ -239,13 +239,31 @@ class B200QwenImageTransformer2DModel(nn.Module):
                 ws[l].copy_(s)
                 w8[l].copy_((wf / s.unsqueeze(-1)).to(torch.float8_e4m3fn))
         self._fp8_ready = True
+        self._q8_kind = "fp8"
+        self._register()
+        return self
+
+    def quantize_int8(self):
+        """Offline per-output-channel symmetric int8 weights (s_w = max|W_n|/127, round-to-nearest-even) — the W side of the
+        README's Int8Linear / triton_int8_gemm ("quantize + matmul + dequantize", README.md:136-141)."""
+        for name in ("qkv", "out", "ff1", "ff2"):
+            w = self._t[name + "_w"]
+            w8 = self._alloc(name + "_w8", w.shape, torch.int8)
+            ws = self._alloc(name + "_ws", w.shape[:-1], torch.float32)
+            for l in range(w.shape[0]):
+                wf = w[l].float()
+                s = wf.abs().amax(dim=-1).clamp_min(1e-12) / 127.0
+                ws[l].copy_(s)
+                w8[l].copy_(torch.round(wf / s.unsqueeze(-1)).clamp_(-127, 127).to(torch.int8))
+        self._fp8_ready = True
+        self._q8_kind = "int8"
         self._register()
         return self
 
     def set_precision(self, mode: str):
-        if mode == "fp8" and not self._fp8_ready:
-            self.quantize_fp8()
-        L.check(L.lib().qie_set_precision(self._handle, {"bf16": 0, "fp8": 1}[mode]), "qie_set_precision")
+        if mode in ("fp8", "int8") and getattr(self, "_q8_kind", None) != mode:
+            self.quantize_fp8() if mode == "fp8" else self.quantize_int8()
+        L.check(L.lib().qie_set_precision(self._handle, {"bf16": 0, "fp8": 1, "int8": 2}[mode]), "qie_set_precision")
         return self
 
     def set_option(self, key: int, value: int):

@@ -50,7 +50,7 @@ def gemm(s, a, w, bias, out, epilogue, streams=3, a_compact=0, out_compact=0, ga
         for st in range(2):
             for k in range(2):
                 g.qk_norm_w[st][k] = qk_norm_w[st][k].data_ptr()
-    g.fp8 = 1 if fp8 else 0
+    g.fp8 = int(fp8)
     if a_scale is not None:
         g.a_scale = a_scale.data_ptr()
     g.block_n = block_n
@@ -65,12 +65,12 @@ def attn(s, qkv, heads, variant=0):
     return out
 
 
-def ln_modulate(s, x, mod, bstride, sstride, shift_off, scale_off, D, fp8=False):
+def ln_modulate(s, x, mod, bstride, sstride, shift_off, scale_off, D, fp8=False, qmode=1):
     out = torch.empty(x.shape[0], D, dtype=torch.bfloat16, device=x.device)
     out8 = torch.empty(x.shape[0], D, dtype=torch.uint8, device=x.device) if fp8 else None
     sc = torch.empty(x.shape[0], dtype=torch.float32, device=x.device) if fp8 else None
     L.check(L.lib().qie_ln_modulate(L.ptr(x), L.ptr(mod), bstride, sstride, shift_off, scale_off, L.ptr(out),
-                                    L.ptr(out8), L.ptr(sc), D, 1e-6, C.byref(s), L.cur_stream()), "qie_ln_modulate")
+                                    L.ptr(out8), L.ptr(sc), qmode, D, 1e-6, C.byref(s), L.cur_stream()), "qie_ln_modulate")
     return (out, out8, sc) if fp8 else out
 
 
@@ -103,11 +103,11 @@ def rmsnorm_pack(x, w, n_pad):
     return out
 
 
-def quant_rows(x):
+def quant_rows(x, qmode=1):
     q = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
     sc = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
-    L.check(L.lib().qie_quant_rows_e4m3(L.ptr(x), L.ptr(q), L.ptr(sc), x.shape[0], x.shape[1], L.cur_stream()),
-            "qie_quant_rows_e4m3")
+    L.check(L.lib().qie_quant_rows(L.ptr(x), L.ptr(q), L.ptr(sc), x.shape[0], x.shape[1], qmode, L.cur_stream()),
+            "qie_quant_rows")
     return q, sc
 
 

@@ -128,10 +128,14 @@ def test_fp8_path_not_worse_than_int8_oracle():
     bf = ours(hidden.to(DEV), enc.to(DEV), None, ts.to(DEV), shapes, [19], return_dict=False)[0]
     ours.set_precision("fp8")
     f8 = ours(hidden.to(DEV), enc.to(DEV), None, ts.to(DEV), shapes, [19], return_dict=False)[0]
+    ours.set_precision("int8")
+    i8 = ours(hidden.to(DEV), enc.to(DEV), None, ts.to(DEV), shapes, [19], return_dict=False)[0]
     ours.set_precision("bf16")
-    e_bf, e_f8 = K.rel_err(bf.cpu(), ref), K.rel_err(f8.cpu(), ref)
+    e_bf, e_f8, e_i8 = K.rel_err(bf.cpu(), ref), K.rel_err(f8.cpu(), ref), K.rel_err(i8.cpu(), ref)
+    print(f"whole-step max-rel-err vs fp32 oracle: bf16 {e_bf:.3e}  fp8 {e_f8:.3e}  int8 {e_i8:.3e}")
     assert e_bf <= VEL_TOL
     assert e_f8 <= 0.1, e_f8            # 3-bit mantissa operands through 2 blocks
+    assert e_i8 <= 0.05, e_i8           # 7-bit operands with per-token / per-channel scales
     # single linear: e4m3 vs int8 oracle on the same activations
     x = torch.randn(256, 256) * 2
     x[:, 3] *= 30                        # an outlier channel

@@ -290,3 +290,33 @@ def test_attention_large_scores_lazy_rescale():
     q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
     ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(-1, D)
     assert K.rel_err(got, ref) <= 2 ** -6
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_gemm_int8_bit_exact_against_int8_oracle(cta_group):
+    """INT8 W8A8 (tcgen05 kind::i8, int32 accumulate): the activation quantiser reproduces the restated Int8Linear oracle's
+    integers exactly, the integer accumulation is exact, and the dequantised output equals the oracle's up to the final
+    bf16 rounding (README.md:136-141 "quantize + matmul + dequantize")."""
+    from oracle import qwen_mmdit_ref as R
+    s = K.seq(1, 256, 100)
+    N, Kd = 512, 512
+    a, w, b = _gemm_case(s, N, Kd, seed=85)
+    a[:, 7] *= 20                                             # an outlier channel
+    a8, a_sc = K.quant_rows(a, qmode=2)
+    xf = a.float()
+    s_x = xf.abs().amax(dim=1, keepdim=True) / 127.0
+    assert torch.equal(a8.view(torch.int8).float(), torch.round(xf / s_x).clamp(-127, 127))    # bit-exact integers
+    w8, w_sc = [], []
+    for wi in w:      # offline weight quantisation exactly as the oracle does it (on the host: torch-CUDA divides by a
+        wc = wi.float().cpu()   # constant via a reciprocal multiply, which can flip a rounding)
+        sc = wc.abs().amax(dim=1) / 127.0
+        w8.append(torch.round(wc / sc[:, None]).clamp(-127, 127).to(torch.int8).view(torch.uint8).to(DEV))
+        w_sc.append(sc.contiguous().to(DEV))
+    out = torch.empty(K.rows(s), N, dtype=torch.float32, device=DEV)
+    K.gemm(s, a8, w8, b, out, K.L.EPI_F32, fp8=2, a_scale=a_sc, w_scale=w_sc, cta_group=cta_group)
+    ai, at = K.from_joint(s, xf)
+    gi, gt = K.from_joint(s, out)
+    ri = R.ref_int8_linear(ai[0].cpu(), w[0].float().cpu(), b[0].cpu()).to(DEV)
+    rt = R.ref_int8_linear(at[0].cpu(), w[1].float().cpu(), b[1].cpu()).to(DEV)
+    # same integers, same int32 sums; only the order of the two fp32 scale multiplies may differ by 1 ulp
+    assert K.rel_err(gi[0], ri) <= 1e-6 and K.rel_err(gt[0], rt) <= 1e-6
