@@ -291,12 +291,18 @@ def run_ours(args):
     prof = model.read_profile()
     model.profile(False)
     sus, burst, hbm, which = peaks()
+    traffic = None      # dram__bytes_read.sum + dram__bytes_write.sum per gemm_kernel launch, from the committed ncu capture
+    tp = ROOT / "profiles" / "r01_gemm_traffic.json"
+    if tp.exists() and args.precision == "bf16":
+        traffic = json.loads(tp.read_text()).get("gemm_kernel_avg_dram_bytes_per_launch")
     gm, at = prof["gemm"], prof["attention"]
     gemm_tf = gm["work"] / (gm["ms"] * 1e-3) / 1e12 if gm["ms"] else 0.0
     attn_tf = at["work"] / (at["ms"] * 1e-3) / 1e12 if at["ms"] else 0.0
     tot_ms = sum(v["ms"] for v in prof.values())
     roofline = {"bound": "tensor", "kernel": f"gemm_kernel (tcgen05 {args.precision}, all linears of the step)",
-                "achieved": gemm_tf, "peak": sus, "unit": "TFLOP/s", "frac": gemm_tf / sus, "traffic": None,
+                "achieved": gemm_tf, "peak": sus, "unit": "TFLOP/s", "frac": gemm_tf / sus, "traffic": traffic,
+                "traffic_note": "bytes per launch averaged over the 4 per-block GEMM shapes, ncu --set full (profiles/r01_gemm_traffic.json); "
+                                "algorithmic operand+output bytes average 420 MB per launch",
                 "peak_source": f"{which} bf16_tflops_sustained (kernel timed inside a long step); burst {burst}",
                 "launches_per_step": gm["launches"] / args.steps, "avg_launch_ms": gm["ms"] / max(gm["launches"], 1),
                 "share_of_step": gm["ms"] / tot_ms if tot_ms else None,

@@ -81,6 +81,19 @@ __device__ __forceinline__ MUnit decode_munit(const GemmDev& p, int mu) {
     return r;
 }
 
+// Tile rasterisation: m-units are walked in bands of GEMM_GROUP_M; inside a band m varies fastest, so the ~74 tiles that
+// are resident at once cover ~8 m-units x ~9 n-blocks (A and W panels of a few MB each, L2-resident) instead of one m-unit
+// x all n-blocks (which streams the whole W matrix through L2 for every 256 rows: measured 5x the algorithmic DRAM reads).
+constexpr int GEMM_GROUP_M = 8;
+__device__ __forceinline__ void tile_to_mn(int tile, int m_units, int n_blocks, int& mu, int& nb) {
+    const int band = tile / (GEMM_GROUP_M * n_blocks);
+    const int first = band * GEMM_GROUP_M;
+    const int gm = min(GEMM_GROUP_M, m_units - first);
+    const int local = tile - band * GEMM_GROUP_M * n_blocks;
+    mu = first + local % gm;
+    nb = local / gm;
+}
+
 template <int BN, int EPI, int QT, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
@@ -106,7 +119,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
     const int u0 = (p.streams & 1) ? units_in_stream<CG>(p.seq.img_pad) : 0;
     const int u1 = (p.streams & 2) ? units_in_stream<CG>(p.seq.txt_pad) : 0;
-    const int num_tiles = p.seq.batch * (u0 + u1) * p.n_blocks;      // tiles of one CTA (CG=1) / one pair (CG=2)
+    const int m_units = p.seq.batch * (u0 + u1);
+    const int num_tiles = m_units * p.n_blocks;                     // tiles of one CTA (CG=1) / one pair (CG=2)
     const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
     const int k_blocks = (p.K + BK - 1) / BK;
     const int rpb = p.seq.img_pad + p.seq.txt_pad;
@@ -141,7 +155,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-                const int mu = tile / p.n_blocks, nb = tile % p.n_blocks;
+                int mu, nb;
+                tile_to_mn(tile, m_units, p.n_blocks, mu, nb);
                 const MUnit m = decode_munit<CG>(p, mu);
                 const int seg_pad = m.s ? p.seq.txt_pad : p.seq.img_pad;
                 int ti = m.ti + cta_rank;
@@ -222,7 +237,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-            const int mu = tile / p.n_blocks, nb = tile % p.n_blocks;
+            int mu, nb;
+            tile_to_mn(tile, m_units, p.n_blocks, mu, nb);
             const MUnit m = decode_munit<CG>(p, mu);
             const int seg_pad = m.s ? p.seq.txt_pad : p.seq.img_pad;
             const int seg_rows = m.s ? p.seq.txt_rows : p.seq.img_rows;

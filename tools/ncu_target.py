@@ -15,7 +15,8 @@ if what == "attn":
 else:
     D = 3072
     M = K.rows(s)
-    for name, N, Kd, epi in [("qkv", 3 * D, D, K.L.EPI_QKV_NORM_ROPE), ("ff2", D, 4 * D, K.L.EPI_GATE_RESID_F32)]:
+    for name, N, Kd, epi in [("qkv", 3 * D, D, K.L.EPI_QKV_NORM_ROPE), ("out", D, D, K.L.EPI_GATE_RESID_F32),
+                             ("ff1", 4 * D, D, K.L.EPI_GELU_BF16), ("ff2", D, 4 * D, K.L.EPI_GATE_RESID_F32)]:
         a = torch.randn(M, Kd, device=dev).bfloat16()
         w = [(torch.randn(N, Kd, device=dev) / math.sqrt(Kd)).bfloat16() for _ in range(2)]
         b = [torch.randn(N, device=dev) * 0.1 for _ in range(2)]
