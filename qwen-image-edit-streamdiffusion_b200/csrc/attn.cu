@@ -19,7 +19,7 @@
 namespace qie {
 
 constexpr int ATT_THREADS = 384;
-#define QIE_ATTN_DEFAULT_VARIANT 0x102    /* CTA-pair kernel, all exp2 on the MUFU (best measured in-step) */
+#define QIE_ATTN_DEFAULT_VARIANT 0x24     /* decoupled CTA-pair kernel (pair2), 2 of 8 score pairs on the FMA-pipe polynomial: best measured in-step */
 constexpr int ATT_TILE = 128;                       // q rows per tile, kv rows per tile, head dim
 constexpr int ATT_HALF_BYTES = ATT_TILE * 128;      // 128 rows x 64 bf16 (one swizzled half tile) = 16 KB
 constexpr int ATT_TILE_BYTES = 2 * ATT_HALF_BYTES;  // 32 KB
@@ -733,6 +733,676 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constan
     }
 }
 
+// =====================================================================================================================
+// CTA-pair attention, decoupled variant ("pair2").  Same work split as attn_pair_kernel (cluster of 2 CTAs = 256 query
+// rows, one Q tile per CTA, cta_group::2 MMAs, two split-KV softmax streams with their own O accumulators), but the
+// softmax -> tensor-pipe chain of a stream is cut in two places:
+//   * the whole S row (128 fp32) is pulled into registers first and the S buffer is handed back at once (s_free), so
+//     S(j+2) of the stream is computed WHILE the exponentials of tile j are still running;
+//   * P goes to a swizzled shared-memory tile (SS PV MMA) instead of aliasing S in TMEM.
+// K and V travel through separate rings (consumption orders S(0),S(1),.. and PV(0),PV(1),.. are both ascending).
+// Issue order of the leader: S(0) S(1) | S(2) S(3) PV(0) PV(1) | S(4) S(5) PV(2) PV(3) | ...
+// =====================================================================================================================
+constexpr int AT3_KSTAGES = 4, AT3_VSTAGES = 3;   // 96 KB (Q + 2 P tiles) + 7 x 16 KB slots fit the 227 KB limit
+constexpr int AT3_SMEM = ATT_TILE_BYTES * 3 + (AT3_KSTAGES + AT3_VSTAGES) * AT2_SLOT_BYTES + 2048 + 512 + 1024;
+
+template <int POLY, int DBG>
+__global__ void __launch_bounds__(AT2_THREADS, 1)
+attn_pair2_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm64, const AttnDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                                       // [2 d-halves][128 rows x 128 B]
+    uint8_t* sP = smem + ATT_TILE_BYTES;                      // [2 streams][2 kv-halves][128 rows x 128 B]
+    uint8_t* sK = smem + 3 * ATT_TILE_BYTES;                  // [K stages][16 KB]
+    uint8_t* sV = sK + AT3_KSTAGES * AT2_SLOT_BYTES;          // [V stages][16 KB]
+    float2* xchg = reinterpret_cast<float2*>(sV + AT3_VSTAGES * AT2_SLOT_BYTES);   // [2 WGs][128 rows] (m_ref, l)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xchg) + 2048);
+    uint64_t* q_full = bars;                       // leader
+    uint64_t* k_full = bars + 1;                   // [K stages] leader
+    uint64_t* k_empty = k_full + AT3_KSTAGES;      // both
+    uint64_t* v_full = k_empty + AT3_KSTAGES;      // [V stages] leader
+    uint64_t* v_empty = v_full + AT3_VSTAGES;      // both
+    uint64_t* s_full = v_empty + AT3_VSTAGES;      // [2] both
+    uint64_t* s_free = s_full + 2;                 // [2] leader, 8 warp arrivals: S_b is in registers everywhere
+    uint64_t* p_full = s_free + 2;                 // [2] leader, 8 warp arrivals: P_b is in shared memory
+    uint64_t* pv_done = p_full + 2;                // [2] both
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int cta_rank = (int)cluster_ctarank();
+    const int rpb = p.seq.img_pad + p.seq.txt_pad;
+    const int n_kv = rpb / ATT_TILE;               // >= 2
+    const int head = blockIdx.y, b = blockIdx.z;
+    const int q_row0 = (blockIdx.x >> 1) * 2 * ATT_TILE + cta_rank * ATT_TILE;
+    const bool q_valid = q_row0 < rpb;
+    const int D = p.H * ATT_TILE;
+    const int colQ = head * ATT_TILE, colK = D + head * ATT_TILE, colV = 2 * D + head * ATT_TILE;
+    const int row_base = b * rpb;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm128);
+        tma_prefetch_desc(&tm64);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < AT3_KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+        for (int i = 0; i < AT3_VSTAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_free[i], 8);
+            mbar_init(&p_full[i], 8);
+            mbar_init(&pv_done[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_cg2<512>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= TMA producer =================
+            if (cta_rank == 0) mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+            const int qr = q_valid ? q_row0 : 0;
+            for (int hf = 0; hf < 2; ++hf)
+                tma_load_2d_cg2(sQ + hf * ATT_HALF_BYTES, &tm128, colQ + hf * 64, row_base + qr, leader_smem_u32(q_full));
+            int ks = 0, vs = 0;
+            uint32_t kph = 0, vph = 0;
+            auto load_k = [&](int j) {       // my 64 kv rows x 128 head dims, as two 64-dim halves of 8 KB
+                mbar_wait(&k_empty[ks], kph ^ 1);
+                if (DBG == 3 && j >= 4) {     // timing experiment: no K/V traffic after the first tiles (stale smem, wrong results)
+                    if (cta_rank == 0) mbar_arrive(&k_full[ks]);
+                    if (++ks == AT3_KSTAGES) { ks = 0; kph ^= 1; }
+                    return;
+                }
+                if (cta_rank == 0) mbar_expect_tx(&k_full[ks], 2 * AT2_SLOT_BYTES);
+                const uint32_t bar = leader_smem_u32(&k_full[ks]);
+                for (int hf = 0; hf < 2; ++hf)
+                    tma_load_2d_cg2(sK + ks * AT2_SLOT_BYTES + hf * 8192, &tm64, colK + hf * 64,
+                                    row_base + j * ATT_TILE + cta_rank * 64, bar);
+                if (++ks == AT3_KSTAGES) { ks = 0; kph ^= 1; }
+            };
+            auto load_v = [&](int j) {       // 128 kv rows x my 64 head dims
+                mbar_wait(&v_empty[vs], vph ^ 1);
+                if (DBG == 3 && j >= 4) {
+                    if (cta_rank == 0) mbar_arrive(&v_full[vs]);
+                    if (++vs == AT3_VSTAGES) { vs = 0; vph ^= 1; }
+                    return;
+                }
+                if (cta_rank == 0) mbar_expect_tx(&v_full[vs], 2 * AT2_SLOT_BYTES);
+                tma_load_2d_cg2(sV + vs * AT2_SLOT_BYTES, &tm128, colV + cta_rank * 64, row_base + j * ATT_TILE,
+                                leader_smem_u32(&v_full[vs]));
+                if (++vs == AT3_VSTAGES) { vs = 0; vph ^= 1; }
+            };
+            load_k(0);
+            load_k(1);
+            for (int j0 = 0; j0 < n_kv; j0 += 2) {
+                for (int t = 0; t < 2; ++t)
+                    if (j0 + t + 2 < n_kv) load_k(j0 + t + 2);
+                for (int t = 0; t < 2; ++t)
+                    if (j0 + t < n_kv) load_v(j0 + t);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && cta_rank == 0) {
+            // ================= MMA issuer (leader) =================
+            constexpr uint32_t IDESC_S = umma_idesc_bf16(256, 128, false);
+            constexpr uint32_t IDESC_O = umma_idesc_bf16(256, 128, true);   // B = V is MN-major
+            int ks = 0, vs = 0;
+            uint32_t kph = 0, vph = 0;
+            auto issue_S = [&](int buf) {
+                mbar_wait(&k_full[ks], kph);
+                tc_fence_after();
+                const uint32_t k = smem_u32(sK + ks * AT2_SLOT_BYTES), q = smem_u32(sQ);
+#pragma unroll
+                for (int s = 0; s < 8; ++s)
+                    umma_ss_f16_cg2(tmem_base + buf * 128,
+                                    umma_desc_kmajor_sw128(q + (s >> 2) * ATT_HALF_BYTES + (s & 3) * 32),
+                                    umma_desc_kmajor_sw128(k + (s >> 2) * 8192 + (s & 3) * 32), IDESC_S, s ? 1u : 0u);
+                umma_commit_cg2(&s_full[buf], 3);
+                umma_commit_cg2(&k_empty[ks], 3);
+                if (++ks == AT3_KSTAGES) { ks = 0; kph ^= 1; }
+            };
+            auto issue_PV = [&](int buf, bool first) {
+                mbar_wait(&v_full[vs], vph);
+                tc_fence_after();
+                const uint32_t v = smem_u32(sV + vs * AT2_SLOT_BYTES), pp = smem_u32(sP + buf * ATT_TILE_BYTES);
+#pragma unroll
+                for (int s = 0; s < 8; ++s)     // 8 x 16 kv rows
+                    umma_ss_f16_cg2(tmem_base + 256 + buf * 128,
+                                    umma_desc_kmajor_sw128(pp + (s >> 2) * ATT_HALF_BYTES + (s & 3) * 32),
+                                    umma_desc_mnmajor_sw128(v + s * 2048, ATT_HALF_BYTES, 1024), IDESC_O,
+                                    (first && s == 0) ? 0u : 1u);
+                umma_commit_cg2(&pv_done[buf], 3);
+                umma_commit_cg2(&v_empty[vs], 3);
+                if (++vs == AT3_VSTAGES) { vs = 0; vph ^= 1; }
+            };
+            // Two issuer threads so that neither kind of MMA queues behind the other's dependency:
+            //   warp 1: S(j)  as soon as the stream's S buffer is free (s_free) and K_j has landed
+            //   warp 2: PV(j) as soon as P(j) is in shared memory (p_full) and V_j has landed
+            mbar_wait(q_full, 0);
+            tc_fence_after();
+            issue_S(0);
+            issue_S(1);
+            for (int j = 2; j < n_kv; ++j) {
+                mbar_wait(&s_free[j & 1], ((j - 2) >> 1) & 1);   // S(j-2) of this stream is in registers in both CTAs
+                tc_fence_after();
+                issue_S(j & 1);
+            }
+            (void)issue_PV;
+        }
+    } else if (warp == 2) {
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t IDESC_O = umma_idesc_bf16(256, 128, true);   // B = V is MN-major
+            int vs = 0;
+            uint32_t vph = 0;
+            for (int j = 0; j < n_kv; ++j) {
+                const int buf = j & 1;
+                mbar_wait(&v_full[vs], vph);
+                mbar_wait(&p_full[buf], (j >> 1) & 1);           // P(j) is in shared memory in both CTAs, O_buf rescaled
+                tc_fence_after();
+                const uint32_t v = smem_u32(sV + vs * AT2_SLOT_BYTES), pp = smem_u32(sP + buf * ATT_TILE_BYTES);
+#pragma unroll
+                for (int s = 0; s < 8; ++s)     // 8 x 16 kv rows
+                    umma_ss_f16_cg2(tmem_base + 256 + buf * 128,
+                                    umma_desc_kmajor_sw128(pp + (s >> 2) * ATT_HALF_BYTES + (s & 3) * 32),
+                                    umma_desc_mnmajor_sw128(v + s * 2048, ATT_HALF_BYTES, 1024), IDESC_O,
+                                    (j < 2 && s == 0) ? 0u : 1u);
+                umma_commit_cg2(&pv_done[buf], 3);
+                umma_commit_cg2(&v_empty[vs], 3);
+                if (++vs == AT3_VSTAGES) { vs = 0; vph ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= softmax streams =================
+        const int wg = (warp - 4) >> 2;
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        const uint32_t tS = tmem_base + lane_addr + wg * 128;
+        const uint32_t tO = tmem_base + lane_addr + 256 + wg * 128;
+        uint8_t* prow = sP + wg * ATT_TILE_BYTES + r * 128;
+        const float c = p.scale_log2;
+        const uint64_t c2 = pk2(c, c);
+        float m_ref = -INFINITY;
+        uint64_t l2 = pk2(0.f, 0.f);
+        int it = 0;
+        for (int j = wg; j < n_kv; j += 2, ++it) {
+            const int nv = p.tile_valid ? __ldg(p.tile_valid + j) : kv_valid_rows(p.seq, j);
+            mbar_wait(&s_full[wg], it & 1);
+            tc_fence_after();
+            uint32_t s[128];
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t(&dst)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[ch * 32]);
+                tmem_ld32(tS + ch * 32, dst);
+            }
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(leader_smem_u32(&s_free[wg]));   // the tensor pipe may refill S_wg now
+            // ---- row max from registers ----
+            float m0 = -INFINITY, m1 = -INFINITY;
+            if (DBG & 2) {
+                m0 = 0.f;             // timing experiment: no max pass
+            } else if (nv == ATT_TILE) {
+#pragma unroll
+                for (int i = 0; i < 128; i += 4) {
+                    m0 = max3(m0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+                    m1 = max3(m1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 128; ++i)
+                    if (i < nv) m0 = fmaxf(m0, __uint_as_float(s[i]));
+            }
+            const float mx = fmaxf(m0, m1) * c;
+            float alpha = 1.f;
+            const bool grow = mx > m_ref + 8.0f;
+            if (grow) {
+                alpha = fast_exp2(m_ref - mx);
+                m_ref = mx;
+                l2 = fma2(l2, pk2(alpha, alpha), pk2(0.f, 0.f));
+            }
+            const uint64_t nm2 = pk2(-m_ref, -m_ref);
+            // ---- exponentials in place: s[i/2] <- bf16x2(p_i, p_i+1) ----
+            if (nv == ATT_TILE) {
+#pragma unroll
+                for (int i = 0; i < 128; i += 2) {
+                    const uint64_t X = fma2(pk2u(s[i], s[i + 1]), c2, nm2);
+                    float x0, x1, e0, e1;
+                    upk2(X, x0, x1);
+                    if (((i >> 1) & 7) < POLY) {
+                        const uint64_t Xc = pk2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+                        const uint64_t T = add2(Xc, pk2(12582912.f, 12582912.f));
+                        const uint64_t N = add2(T, pk2(-12582912.f, -12582912.f));
+                        const uint64_t Fr = fma2(N, pk2(-1.f, -1.f), Xc);
+                        uint64_t P = fma2(Fr, pk2(0.0551716574f, 0.0551716574f), pk2(0.2426111400f, 0.2426111400f));
+                        P = fma2(P, Fr, pk2(0.6932609677f, 0.6932609677f));
+                        P = fma2(P, Fr, pk2(0.9999280572f, 0.9999280572f));
+                        float t0, t1, p0, p1;
+                        upk2(T, t0, t1);
+                        upk2(P, p0, p1);
+                        e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+                        e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+                    } else if (DBG & 1) {     // timing experiment: no MUFU (results are wrong)
+                        e0 = x0 * 0.5f;
+                        e1 = x1 * 0.5f;
+                    } else {
+                        e0 = fast_exp2(x0);
+                        e1 = fast_exp2(x1);
+                    }
+                    l2 = add2(l2, pk2(e0, e1));
+                    s[i >> 1] = pack_bf16(e0, e1);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 128; i += 2) {
+                    float x0, x1;
+                    upk2(fma2(pk2u(s[i], s[i + 1]), c2, nm2), x0, x1);
+                    const float e0 = i < nv ? fast_exp2(x0) : 0.f, e1 = i + 1 < nv ? fast_exp2(x1) : 0.f;
+                    l2 = add2(l2, pk2(e0, e1));
+                    s[i >> 1] = pack_bf16(e0, e1);
+                }
+            }
+            if (it > 0) {
+                // my previous PV (it reads the P tile and owns O_wg) must have retired before P / O are touched
+                mbar_wait(&pv_done[wg], (it - 1) & 1);
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll 1
+                    for (int ch = 0; ch < 4; ++ch) {
+                        uint32_t o[32];
+                        tmem_ld32(tO + ch * 32, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(tO + ch * 32, o);
+                    }
+                    tmem_st_wait();
+                }
+            }
+            // P row -> 128B-swizzled K-major tile: kv columns 0-63 in half 0, 64-127 in half 1; 16 B chunk index ^ (row & 7)
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int chunk = (q & 7) ^ (r & 7);
+                *reinterpret_cast<uint4*>(prow + (q >> 3) * ATT_HALF_BYTES + chunk * 16) =
+                    make_uint4(s[q * 4], s[q * 4 + 1], s[q * 4 + 2], s[q * 4 + 3]);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(leader_smem_u32(&p_full[wg]));
+        }
+        // ---- epilogue: merge the two streams of this row ----
+        float l_lo, l_hi;
+        upk2(l2, l_lo, l_hi);
+        xchg[wg * 128 + r] = make_float2(m_ref, l_lo + l_hi);
+        mbar_wait(&pv_done[wg], (it - 1) & 1);
+        tc_fence_after();
+        tc_fence_before();
+        named_bar_sync(1, 256);
+        tc_fence_after();
+        const float2 mine = xchg[wg * 128 + r], other = xchg[(wg ^ 1) * 128 + r];
+        const float m = fmaxf(mine.x, other.x);
+        const float a_me = fast_exp2(mine.x - m), a_ot = fast_exp2(other.x - m);
+        const float inv = 1.f / (mine.y * a_me + other.y * a_ot);
+        const float f0 = (wg == 0 ? a_me : a_ot) * inv, f1 = (wg == 0 ? a_ot : a_me) * inv;
+        if (q_valid) {
+            const uint32_t tO0 = tmem_base + lane_addr + 256 + wg * 64, tO1 = tO0 + 128;
+            __nv_bfloat16* orow = p.out + (long long)(row_base + q_row0 + r) * D + head * ATT_TILE + wg * 64;
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ++ch) {
+                uint32_t o0[32], o1[32];
+                tmem_ld32(tO0 + ch * 32, o0);
+                tmem_ld32(tO1 + ch * 32, o1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        v[i] = __uint_as_float(o0[q4 * 8 + i]) * f0 + __uint_as_float(o1[q4 * 8 + i]) * f1;
+                    *reinterpret_cast<uint4*>(orow + ch * 32 + q4 * 8) =
+                        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                }
+            }
+        }
+    }
+
+    __syncwarp();
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_cg2<512>(tmem_base);
+    }
+}
+
+template <int POLY, int DBG>
+static int launch_attn_pair2(const CUtensorMap& tm128, const CUtensorMap& tm64, const AttnDev& p, dim3 grid, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        QIE_CUDA_OK(cudaFuncSetAttribute(attn_pair2_kernel<POLY, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_SMEM));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(AT2_THREADS);
+    cfg.dynamicSmemBytes = AT3_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_pair2_kernel<POLY, DBG>, tm128, tm64, p));
+    QIE_LAUNCH_OK("attn_pair2_kernel");
+    return QIE_OK;
+}
+
+// =====================================================================================================================
+// Decoupled single-CTA kernel ("dq"): two 128-row Q tiles per CTA (as attn_kernel), all barriers CTA-local, and the
+// softmax <-> tensor-pipe chain cut as in pair2: the S row goes to registers at once and the S buffer is released
+// (s_free) so S_t(j+1) runs while the exponentials of tile j are computed; P goes through a swizzled smem tile (SS PV).
+// Issue order: S0(0) S1(0) | S0(j+1) S1(j+1) PV0(j) PV1(j) | ...   Ring order: K0, K1, V0, K2, V1, ...
+// =====================================================================================================================
+constexpr int AT4_STAGES = 3;
+constexpr int AT4_SMEM = (4 + AT4_STAGES) * ATT_TILE_BYTES + 512 + 1024;
+
+template <int POLY>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                                   // [2 tiles][2 halves][128 x 128 B]
+    uint8_t* sP = smem + 2 * ATT_TILE_BYTES;              // [2 tiles][2 halves]
+    uint8_t* sKV = smem + 4 * ATT_TILE_BYTES;             // [stages][2 halves]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (4 + AT4_STAGES) * ATT_TILE_BYTES);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;
+    uint64_t* kv_empty = kv_full + AT4_STAGES;
+    uint64_t* s_full = kv_empty + AT4_STAGES;      // [2]
+    uint64_t* s_free = s_full + 2;                 // [2] 4 warp arrivals
+    uint64_t* p_full = s_free + 2;                 // [2] 4 warp arrivals
+    uint64_t* pv_done = p_full + 2;                // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int rpb = p.seq.img_pad + p.seq.txt_pad;
+    const int n_kv = rpb / ATT_TILE;
+    const int head = blockIdx.y, b = blockIdx.z;
+    const int q_row0 = blockIdx.x * 2 * ATT_TILE;
+    const bool tile1_on = q_row0 + ATT_TILE < rpb;
+    const int nt = tile1_on ? 2 : 1;
+    const int D = p.H * ATT_TILE;
+    const int colQ = head * ATT_TILE, colK = D + head * ATT_TILE, colV = 2 * D + head * ATT_TILE;
+    const int row_base = b * rpb;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmQKV);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < AT4_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(&s_full[t], 1);
+            mbar_init(&s_free[t], 4);
+            mbar_init(&p_full[t], 4);
+            mbar_init(&pv_done[t], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= TMA producer: Q tiles, then K0, K1, V0, K2, V1, ... =================
+            mbar_expect_tx(q_full, nt * ATT_TILE_BYTES);
+            for (int t = 0; t < nt; ++t)
+                for (int hf = 0; hf < 2; ++hf)
+                    tma_load_2d(sQ + t * ATT_TILE_BYTES + hf * ATT_HALF_BYTES, &tmQKV, colQ + hf * 64,
+                                row_base + q_row0 + t * ATT_TILE, q_full);
+            int stage = 0;
+            uint32_t phase = 0;
+            auto load = [&](int col, int j) {
+                mbar_wait(&kv_empty[stage], phase ^ 1);
+                mbar_expect_tx(&kv_full[stage], ATT_TILE_BYTES);
+                for (int hf = 0; hf < 2; ++hf)
+                    tma_load_2d(sKV + stage * ATT_TILE_BYTES + hf * ATT_HALF_BYTES, &tmQKV, col + hf * 64,
+                                row_base + j * ATT_TILE, &kv_full[stage]);
+                if (++stage == AT4_STAGES) { stage = 0; phase ^= 1; }
+            };
+            load(colK, 0);
+            for (int j = 0; j < n_kv; ++j) {
+                if (j + 1 < n_kv) load(colK, j + 1);
+                load(colV, j);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ================= MMA issuer =================
+            constexpr uint32_t IDESC_S = umma_idesc_bf16(128, 128, false);
+            constexpr uint32_t IDESC_O = umma_idesc_bf16(128, 128, true);
+            int stage = 0;
+            uint32_t phase = 0;
+            auto wait_slot = [&]() -> uint32_t {
+                mbar_wait(&kv_full[stage], phase);
+                tc_fence_after();
+                return smem_u32(sKV + stage * ATT_TILE_BYTES);
+            };
+            auto release_slot = [&]() {
+                umma_commit(&kv_empty[stage]);
+                if (++stage == AT4_STAGES) { stage = 0; phase ^= 1; }
+            };
+            auto issue_S = [&](int t, uint32_t k) {
+                const uint32_t q = smem_u32(sQ + t * ATT_TILE_BYTES);
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const uint32_t off = (s >> 2) * ATT_HALF_BYTES + (s & 3) * 32;
+                    umma_ss_f16(tmem_base + t * 128, umma_desc_kmajor_sw128(q + off), umma_desc_kmajor_sw128(k + off),
+                                IDESC_S, s ? 1u : 0u);
+                }
+                umma_commit(&s_full[t]);
+            };
+            auto issue_PV = [&](int t, uint32_t v, bool first) {
+                const uint32_t pp = smem_u32(sP + t * ATT_TILE_BYTES);
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const uint32_t aoff = (s >> 2) * ATT_HALF_BYTES + (s & 3) * 32;
+                    umma_ss_f16(tmem_base + 256 + t * 128, umma_desc_kmajor_sw128(pp + aoff),
+                                umma_desc_mnmajor_sw128(v + s * 2048, ATT_HALF_BYTES, 1024), IDESC_O,
+                                (first && s == 0) ? 0u : 1u);
+                }
+                umma_commit(&pv_done[t]);
+            };
+            mbar_wait(q_full, 0);
+            tc_fence_after();
+            {
+                const uint32_t k = wait_slot();
+                for (int t = 0; t < nt; ++t) issue_S(t, k);
+                release_slot();
+            }
+            for (int j = 0; j < n_kv; ++j) {
+                if (j + 1 < n_kv) {
+                    const uint32_t k = wait_slot();
+                    for (int t = 0; t < nt; ++t) {
+                        mbar_wait(&s_free[t], j & 1);          // S_t(j) is in registers
+                        tc_fence_after();
+                        issue_S(t, k);
+                    }
+                    release_slot();
+                }
+                const uint32_t v = wait_slot();
+                for (int t = 0; t < nt; ++t) {
+                    mbar_wait(&p_full[t], j & 1);              // P_t(j) in smem, O_t rescaled
+                    tc_fence_after();
+                    issue_PV(t, v, j == 0);
+                }
+                release_slot();
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= softmax warpgroups (one per Q tile) =================
+        const int t = (warp - 4) >> 2;
+        if (t == 0 || tile1_on) {
+            const int quad = warp & 3;
+            const int r = quad * 32 + lane;
+            const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+            const uint32_t tS = tmem_base + lane_addr + t * 128;
+            const uint32_t tO = tmem_base + lane_addr + 256 + t * 128;
+            uint8_t* prow = sP + t * ATT_TILE_BYTES + r * 128;
+            const float c = p.scale_log2;
+            const uint64_t c2 = pk2(c, c);
+            float m_ref = -INFINITY;
+            uint64_t l2 = pk2(0.f, 0.f);
+            for (int j = 0; j < n_kv; ++j) {
+                const int nv = p.tile_valid ? __ldg(p.tile_valid + j) : kv_valid_rows(p.seq, j);
+                mbar_wait(&s_full[t], j & 1);
+                tc_fence_after();
+                uint32_t s[128];
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t(&dst)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[ch * 32]);
+                    tmem_ld32(tS + ch * 32, dst);
+                }
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_free[t]);        // the tensor pipe may refill S_t now
+                float m0 = -INFINITY, m1 = -INFINITY;
+                if (nv == ATT_TILE) {
+#pragma unroll
+                    for (int i = 0; i < 128; i += 4) {
+                        m0 = max3(m0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+                        m1 = max3(m1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 128; ++i)
+                        if (i < nv) m0 = fmaxf(m0, __uint_as_float(s[i]));
+                }
+                const float mx = fmaxf(m0, m1) * c;
+                float alpha = 1.f;
+                const bool grow = mx > m_ref + 8.0f;
+                if (grow) {
+                    alpha = fast_exp2(m_ref - mx);
+                    m_ref = mx;
+                    l2 = fma2(l2, pk2(alpha, alpha), pk2(0.f, 0.f));
+                }
+                const uint64_t nm2 = pk2(-m_ref, -m_ref);
+                if (nv == ATT_TILE) {
+#pragma unroll
+                    for (int i = 0; i < 128; i += 2) {
+                        const uint64_t X = fma2(pk2u(s[i], s[i + 1]), c2, nm2);
+                        float x0, x1, e0, e1;
+                        upk2(X, x0, x1);
+                        if (((i >> 1) & 7) < POLY) {
+                            const uint64_t Xc = pk2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+                            const uint64_t T = add2(Xc, pk2(12582912.f, 12582912.f));
+                            const uint64_t N = add2(T, pk2(-12582912.f, -12582912.f));
+                            const uint64_t Fr = fma2(N, pk2(-1.f, -1.f), Xc);
+                            uint64_t P = fma2(Fr, pk2(0.0551716574f, 0.0551716574f), pk2(0.2426111400f, 0.2426111400f));
+                            P = fma2(P, Fr, pk2(0.6932609677f, 0.6932609677f));
+                            P = fma2(P, Fr, pk2(0.9999280572f, 0.9999280572f));
+                            float t0, t1, p0, p1;
+                            upk2(T, t0, t1);
+                            upk2(P, p0, p1);
+                            e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+                            e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+                        } else {
+                            e0 = fast_exp2(x0);
+                            e1 = fast_exp2(x1);
+                        }
+                        l2 = add2(l2, pk2(e0, e1));
+                        s[i >> 1] = pack_bf16(e0, e1);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 128; i += 2) {
+                        float x0, x1;
+                        upk2(fma2(pk2u(s[i], s[i + 1]), c2, nm2), x0, x1);
+                        const float e0 = i < nv ? fast_exp2(x0) : 0.f, e1 = i + 1 < nv ? fast_exp2(x1) : 0.f;
+                        l2 = add2(l2, pk2(e0, e1));
+                        s[i >> 1] = pack_bf16(e0, e1);
+                    }
+                }
+                if (j > 0) {
+                    mbar_wait(&pv_done[t], (j - 1) & 1);       // PV_t(j-1) has released the P tile and O_t
+                    tc_fence_after();
+                    if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll 1
+                        for (int ch = 0; ch < 4; ++ch) {
+                            uint32_t o[32];
+                            tmem_ld32(tO + ch * 32, o);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st32(tO + ch * 32, o);
+                        }
+                        tmem_st_wait();
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int chunk = (q & 7) ^ (r & 7);
+                    *reinterpret_cast<uint4*>(prow + (q >> 3) * ATT_HALF_BYTES + chunk * 16) =
+                        make_uint4(s[q * 4], s[q * 4 + 1], s[q * 4 + 2], s[q * 4 + 3]);
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[t]);
+            }
+            mbar_wait(&pv_done[t], (n_kv - 1) & 1);
+            tc_fence_after();
+            float l_lo, l_hi;
+            upk2(l2, l_lo, l_hi);
+            const float inv = 1.f / (l_lo + l_hi);
+            __nv_bfloat16* orow = p.out + (long long)(row_base + q_row0 + t * ATT_TILE + r) * D + head * ATT_TILE;
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t o[32];
+                tmem_ld32(tO + ch * 32, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    uint4 u;
+                    u.x = pack_bf16(__uint_as_float(o[q4 * 8 + 0]) * inv, __uint_as_float(o[q4 * 8 + 1]) * inv);
+                    u.y = pack_bf16(__uint_as_float(o[q4 * 8 + 2]) * inv, __uint_as_float(o[q4 * 8 + 3]) * inv);
+                    u.z = pack_bf16(__uint_as_float(o[q4 * 8 + 4]) * inv, __uint_as_float(o[q4 * 8 + 5]) * inv);
+                    u.w = pack_bf16(__uint_as_float(o[q4 * 8 + 6]) * inv, __uint_as_float(o[q4 * 8 + 7]) * inv);
+                    *reinterpret_cast<uint4*>(orow + ch * 32 + q4 * 8) = u;
+                }
+            }
+        }
+    }
+
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+template <int POLY>
+static int launch_attn_dq(const CUtensorMap& tm, const AttnDev& p, dim3 grid, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        QIE_CUDA_OK(cudaFuncSetAttribute(attn_dq_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT4_SMEM));
+        configured = true;
+    }
+    attn_dq_kernel<POLY><<<grid, ATT_THREADS, AT4_SMEM, st>>>(tm, p);
+    QIE_LAUNCH_OK("attn_dq_kernel");
+    return QIE_OK;
+}
+
 template <int POLY>
 static int launch_attn_pair(const CUtensorMap& tm128, const CUtensorMap& tm64, const AttnDev& p, dim3 grid, cudaStream_t st) {
     static bool configured = false;
@@ -788,8 +1458,9 @@ extern "C" int qie_attn_fwd(const void* qkv, void* out, const qie_seq* seq, int 
 static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int* tile_valid, int num_heads, int variant,
                        void* stream) {
     if (variant == 0) variant = QIE_ATTN_DEFAULT_VARIANT;     // bit 8 (0x100) marks an explicit choice, e.g. 0x100 = TMEM P, all-MUFU
-    const int poly = (variant >> 4) & 15, psmem = variant & 1, pair = (variant >> 1) & 1;
-    QIE_REQUIRE((variant & ~0x1F3) == 0 && (poly == 0 || poly == 2 || poly == 3 || poly == 4) && !(pair && psmem), QIE_EINVAL,
+    const int poly = (variant >> 4) & 15, psmem = variant & 1, pair = (variant >> 1) & 1, pair2 = (variant >> 2) & 1;
+    const int dq = (variant >> 3) & 1;
+    QIE_REQUIRE((variant & ~0x7FF) == 0 && !(dq && (pair || pair2 || psmem)) && !(pair2 && (pair || psmem)) && (poly == 0 || poly == 2 || poly == 3 || poly == 4) && !(pair && psmem), QIE_EINVAL,
                 "qie_attn_fwd: bad variant 0x%x", variant);
     const int rpb = seq->img_pad + seq->txt_pad;
     const int D = num_heads * 128;
@@ -809,11 +1480,31 @@ static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int
     p.v_kstep = 2048;
     dim3 grid((rpb + 255) / 256, num_heads, seq->batch);
     cudaStream_t st = (cudaStream_t)stream;
-    if (pair) {   // CTA-pair kernel: two CTAs per 256 query rows, K tiles staged as 64-row halves
+    if (dq) {     // decoupled single-CTA kernel
+        switch (poly) {
+            case 0: return launch_attn_dq<0>(tm, p, grid, st);
+            case 2: return launch_attn_dq<2>(tm, p, grid, st);
+            case 3: return launch_attn_dq<3>(tm, p, grid, st);
+            case 4: return launch_attn_dq<4>(tm, p, grid, st);
+        }
+    }
+    if (pair || pair2) {   // CTA-pair kernels: two CTAs per 256 query rows, K tiles staged as 64-row halves
         CUtensorMap tm64;
         rc = make_tmap_2d(&tm64, qkv, (uint64_t)seq->batch * rpb, (uint64_t)3 * D, (uint64_t)3 * D * 2, 64, 64, 2);
         if (rc) return rc;
         grid.x *= 2;
+        if (pair2) {
+            const int dbg = (variant >> 9) & 3;      // timing experiments (0x200: no MUFU, 0x400: no max pass)
+            if (dbg == 1) return launch_attn_pair2<0, 1>(tm, tm64, p, grid, st);
+            if (dbg == 2) return launch_attn_pair2<0, 2>(tm, tm64, p, grid, st);
+            if (dbg == 3) return launch_attn_pair2<0, 3>(tm, tm64, p, grid, st);
+            switch (poly) {
+                case 0: return launch_attn_pair2<0, 0>(tm, tm64, p, grid, st);
+                case 2: return launch_attn_pair2<2, 0>(tm, tm64, p, grid, st);
+                case 3: return launch_attn_pair2<3, 0>(tm, tm64, p, grid, st);
+                case 4: return launch_attn_pair2<4, 0>(tm, tm64, p, grid, st);
+            }
+        }
         switch (poly) {
             case 0: return launch_attn_pair<0>(tm, tm64, p, grid, st);
             case 2: return launch_attn_pair<2>(tm, tm64, p, grid, st);

@@ -261,7 +261,7 @@ def test_gemm_fp8(cta_group):
 
 # ------------------------------------------------------------------ attention
 @pytest.mark.parametrize("B,img,txt,H", [(1, 256, 128, 2), (1, 384, 128, 1), (2, 200, 19, 2), (1, 1024, 219, 3)])
-@pytest.mark.parametrize("variant", [0, 0x100, 0x01, 0x20, 0x31, 0x40, 0x41, 0x102, 0x22, 0x42])
+@pytest.mark.parametrize("variant", [0, 0x100, 0x01, 0x20, 0x31, 0x41, 0x102, 0x22, 0x42, 0x104, 0x24, 0x34, 0x108, 0x28])
 def test_attention(B, img, txt, H, variant):
     s = K.seq(B, img, txt)
     D = H * 128
