@@ -312,6 +312,7 @@ def run_ours(args):
                           "peak_gbs": hbm, "share_of_step": prof["adaln"]["ms"] / tot_ms if tot_ms else None},
                 "mod_gemv": {"achieved_gbs": prof["mod_gemv"]["work"] / (prof["mod_gemv"]["ms"] * 1e-3) / 1e9 if prof["mod_gemv"]["ms"] else 0,
                              "peak_gbs": hbm, "share_of_step": prof["mod_gemv"]["ms"] / tot_ms if tot_ms else None},
+                "event_sum_ms_per_step": tot_ms / args.steps,      # sum of the per-kernel event intervals; the rest of ms_per_step is inter-kernel gaps
                 "step_tflops": STEPS_PER_IMAGE * (2 if args.cfg else 1) * flops_per_forward(args.layers) / (ms_step * 1e-3) / 1e12}
 
     cpu = None

@@ -177,3 +177,57 @@ def test_full_size_model_two_step_denoise_parity():
     assert cos >= COS_TOL, cos
     del oracle
     torch.cuda.empty_cache()
+
+
+def test_config5_shapes_batch8_three_images_ragged_text():
+    """BASELINE.json configs[4] shapes at FULL width, 4 of the 60 blocks: streaming batch of 8 frames at 512x512 with two
+    reference images -> img_shapes [(1,32,32)]*3 per frame (3072 image tokens), ragged T = 427; fp32 oracle on the GPU."""
+    ref_cfg = R.RefConfig(num_layers=4)
+    cfg = qie_b200.QwenImageDiTConfig(num_layers=4)
+    ours = qie_b200.B200QwenImageTransformer2DModel.from_random(cfg, seed=3, device=DEV)
+    with torch.device(DEV):
+        oracle = R.QwenImageTransformer2DModelRef(ref_cfg)
+    oracle.load_state_dict(ours.export_state_dict(), strict=True)
+    oracle.eval()
+    B, T = 8, 427
+    shapes = [[(1, 32, 32), (1, 32, 32), (1, 32, 32)]] * B
+    g = torch.Generator(device=DEV).manual_seed(11)
+    hidden = torch.randn(B, 3072, 64, generator=g, device=DEV).bfloat16()
+    enc = (torch.randn(B, T, 3584, generator=g, device=DEV) * 3).bfloat16()
+    ts = torch.tensor([1.0, 0.77, 0.46, 0.02, 1.0, 0.77, 0.46, 0.02], device=DEV).bfloat16()   # per-frame timesteps
+    with torch.no_grad():
+        ref = oracle(hidden.float(), enc.float(), None, ts.float(), shapes, [T] * B)[0]
+    got = ours(hidden, enc, None, ts, shapes, [T] * B, return_dict=False)[0]
+    for b in range(B):
+        assert K.rel_err(got[b], ref[b]) <= VEL_TOL, (b, K.rel_err(got[b], ref[b]))
+
+
+def test_error_convention_on_device():
+    """Status codes + messages through the C ABI on a real device (no exception crosses the boundary)."""
+    import ctypes as C
+    from qie_b200 import _lib as L
+    lib = L.lib()
+    bad = L.ModelCfg(2, 2, 64, 64, 64, 128, (C.c_int * 3)(8, 28, 28))             # head_dim 64 is not supported
+    h = C.c_void_p()
+    assert lib.qie_create(C.byref(bad), 0, C.byref(h)) == -2 and b"head_dim" in lib.qie_last_error()
+    ref_cfg, our_cfg = small_cfg(layers=1)
+    _, ours = build_pair(ref_cfg, our_cfg)
+    shapes = [[(1, 8, 16)]]
+    hidden, enc = R.make_inputs(ref_cfg, shapes, 7)
+    # a workspace that is too small -> QIE_ENOMEM (-4), reported as QieError by the wrapper
+    seq = qie_b200.make_seq(1, 128, 7)
+    need = lib.qie_workspace_bytes(ours._handle, C.byref(seq))
+    ws = torch.zeros(2048, dtype=torch.uint8, device=DEV)
+    out = torch.empty(1, 128, 64, dtype=torch.bfloat16, device=DEV)
+    flat = (C.c_int * 3)(1, 8, 16)
+    ts = torch.ones(1, device=DEV)
+    rc = lib.qie_forward(ours._handle, L.ptr(hidden.to(DEV).bfloat16()), L.ptr(enc.to(DEV).bfloat16()), L.ptr(ts), flat, 1,
+                         C.byref(seq), L.ptr(out), C.c_void_p((ws.data_ptr() + 1023) // 1024 * 1024), 1024, -1, L.cur_stream())
+    assert rc == -4 and need > 1024 and b"workspace" in lib.qie_last_error()
+    # img_shapes that do not cover the tokens -> QIE_ESHAPE through the python wrapper
+    with pytest.raises(qie_b200.QieError, match="img_shapes"):
+        ours(hidden.to(DEV), enc.to(DEV), None, ts, [[(1, 8, 8)]], [7])
+    # weights not set
+    bare = qie_b200.B200QwenImageTransformer2DModel(our_cfg, DEV)
+    with pytest.raises(qie_b200.QieError, match="weights not set"):
+        bare(hidden.to(DEV), enc.to(DEV), None, ts, shapes, [7])
