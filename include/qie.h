@@ -160,6 +160,17 @@ long long qie_workspace_offset(const qie_handle* h, const qie_seq* seq, int whic
 int qie_attn_fwd_tiles(const void* qkv, void* out, int n_tiles, const int* tile_valid_dev, int num_heads, int variant,
                        void* stream);
 
+/* ---- exact caches ("next" row N1): replaces cached_pipeline_v2.py (README.md:125) and the
+ * precompute_conditions stub of qwen_realtime.py:140-165.  temb, every block's modulation vectors and the final
+ * scale/shift depend on the timestep only; txt_in(txt_norm(prompt_embeds)) on the prompt only.  Cached forwards are
+ * bit-identical to uncached ones.  qie_cache_schedule / qie_cache_prompt are setup-time calls (allocate + synchronise). */
+int qie_cache_schedule(qie_handle* h, const float* timesteps_host, int n, void* stream);
+int qie_cache_prompt(qie_handle* h, int slot /* 0..3 */, const void* enc /* bf16 [txt_rows, joint_dim] */, int txt_rows,
+                     void* stream);
+/* selection applied by the following qie_forward calls: sched_idx_host[b] per batch row (NULL or -1 = compute), prompt
+ * slot (-1 = compute) */
+int qie_cache_select(qie_handle* h, const int* sched_idx_host, int batch, int prompt_slot);
+
 /* replaces: the true-CFG combine + norm rescale of QwenImageEditPlusPipeline.__call__ and
  * FlowMatchEulerDiscreteScheduler.step, fused; v_uncond may be NULL (cond-only).
  *   v_* bf16 rows of `v_row_stride` elements, first `channels` used; latents bf16 [rows, channels] in/out. */

@@ -90,6 +90,9 @@ SYMBOLS = {
                                C.c_size_t, _i, _vp]),
     "qie_workspace_offset": (_ll, [_vp, C.POINTER(Seq), _i]),
     "qie_attn_fwd_tiles": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp]),
+    "qie_cache_schedule": (_i, [_vp, C.POINTER(_f), _i, _vp]),
+    "qie_cache_prompt": (_i, [_vp, _i, _vp, _i, _vp]),
+    "qie_cache_select": (_i, [_vp, C.POINTER(_i), _i, _i]),
     "qie_cfg_euler_step": (_i, [_vp, _vp, _vp, _f, _f, _f, _i, _i, _i, _i, _vp]),
     "qie_flowmatch_sigmas": (_i, [_i, _i, C.POINTER(_f)]),
     "qie_rope_table_host": (_i, [C.POINTER(ModelCfg), C.POINTER(_i), _i, C.POINTER(Seq), C.POINTER(_f)]),

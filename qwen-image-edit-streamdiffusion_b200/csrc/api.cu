@@ -95,6 +95,14 @@ struct qie_handle {
     std::vector<int> rope_key;
     float* d_small;         // tproj [8,256] | t1 [8,D] | temb [8,D] | mod [L,2? ...] see offsets
     size_t small_bytes;
+    // exact caches: per-timestep modulation tables and per-prompt text-stream embeddings
+    float* d_sched_mod = nullptr;   // [n_sched][L*12*D]
+    float* d_sched_fin = nullptr;   // [n_sched][2D]
+    int n_sched = 0;
+    float* d_prompt[4] = {nullptr, nullptr, nullptr, nullptr};   // fp32 [txt_pad, D] (pad rows zero)
+    int prompt_rows[4] = {0, 0, 0, 0};
+    int sel_sched[8] = {-1, -1, -1, -1, -1, -1, -1, -1};         // per batch row, -1 = compute
+    int sel_prompt = -1;
     // optional per-kernel-class CUDA-event timing (bench.py roofline): class 0 gemm, 1 attention, 2 adaLN, 3 gemv, 4 other
     int profile;
     struct Prof { int cls; cudaEvent_t a, b; double work; };
@@ -230,6 +238,9 @@ extern "C" int qie_destroy(qie_handle* h) {
     if (!h) return QIE_OK;
     cudaFree(h->d_small);
     cudaFree(h->d_rope);
+    cudaFree(h->d_sched_mod);
+    cudaFree(h->d_sched_fin);
+    for (float* p : h->d_prompt) cudaFree(p);
     delete h;
     return QIE_OK;
 }
@@ -445,6 +456,19 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
     const long long modN = (long long)nb * 12 * D;   // batch stride of the modulation table
     float* fin = mod + 8 * (size_t)L * 12 * D;                     // [B][2D]
     if (phases & QIE_PHASE_BEGIN) {
+    bool sched_cached = h->n_sched > 0;
+    for (int b = 0; b < B; ++b) sched_cached = sched_cached && h->sel_sched[b] >= 0 && h->sel_sched[b] < h->n_sched;
+    if (sched_cached) {
+        // every vector below depends on the timestep only: reuse the tables built by qie_cache_schedule (bit-identical)
+        for (int b = 0; b < B; ++b) {
+            const size_t i = (size_t)h->sel_sched[b];
+            if (nb > 0)
+                QIE_CUDA_OK(cudaMemcpyAsync(mod + (size_t)b * modN, h->d_sched_mod + i * (size_t)L * 12 * D,
+                                            (size_t)modN * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            QIE_CUDA_OK(cudaMemcpyAsync(fin + (size_t)b * 2 * D, h->d_sched_fin + i * 2 * D, (size_t)2 * D * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, st));
+        }
+    } else {
     if ((rc = qie_timestep_proj(timestep, tproj, B, 0, st))) return rc;
     if ((rc = qie_gemv(tproj, h->w.t1_w, h->w.t1_b, t1, B, D, 256, 0, st))) return rc;
     if ((rc = qie_gemv(t1, h->w.t2_w, h->w.t2_b, temb, B, D, D, 1, st))) return rc;
@@ -453,21 +477,32 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
         if ((rc = qie_gemv(temb, h->w.mod_w, h->w.mod_b, mod, B, modN, D, 1, st))) return rc;
     }
     if ((rc = qie_gemv(temb, h->w.norm_out_w, h->w.norm_out_b, fin, B, 2 * D, D, 1, st))) return rc;
+    }
     // mod row for (b, layer l, stream s): mod + b*modN + (l*2+s)*6D, chunks [shift1|scale1|gate1|shift2|scale2|gate2]
 
     // ---- stream embeddings -> fp32 residual in the joint layout ----
     if ((rc = qie_pack_rows(hidden, xin, B, seq->img_rows, seq->img_pad, h->cfg.in_channels, st))) return rc;
-    if ((rc = qie_rmsnorm_pack(enc, h->w.txt_norm_w, xtxt, B, seq->txt_rows, seq->txt_pad, h->cfg.joint_dim, 1e-6f, st)))
+    const bool prompt_cached = h->sel_prompt >= 0 && h->d_prompt[h->sel_prompt] && !sp &&
+                               h->prompt_rows[h->sel_prompt] == seq->txt_rows;
+    if (!prompt_cached &&
+        (rc = qie_rmsnorm_pack(enc, h->w.txt_norm_w, xtxt, B, seq->txt_rows, seq->txt_pad, h->cfg.joint_dim, 1e-6f, st)))
         return rc;
     {
         qie_gemm_args g{};
         g.a = xin; g.a_compact = 1; g.w[0] = h->w.img_in_w; g.bias[0] = h->w.img_in_b;
         g.out = resid; g.ldo = D; g.N = D; g.K = h->cfg.in_channels; g.streams = 1; g.epilogue = QIE_EPI_F32;
         if ((rc = run_gemm(g))) return rc;
+        if (prompt_cached) {
+            // txt_in(txt_norm(prompt_embeds)) depends on the prompt only: copy the cached fp32 rows into the residual
+            for (int b = 0; b < B; ++b)
+                QIE_CUDA_OK(cudaMemcpyAsync(resid + ((size_t)b * rpb + seq->img_pad) * D, h->d_prompt[h->sel_prompt],
+                                            (size_t)seq->txt_pad * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        } else {
         qie_gemm_args t{};
         t.a = xtxt; t.a_compact = 1; t.w[1] = h->w.txt_in_w; t.bias[1] = h->w.txt_in_b;
         t.out = resid; t.ldo = D; t.N = D; t.K = h->cfg.joint_dim; t.streams = 2; t.epilogue = QIE_EPI_F32;
         if ((rc = run_gemm(t))) return rc;
+        }
     }
     }   // QIE_PHASE_BEGIN
 
@@ -591,4 +626,73 @@ extern "C" long long qie_workspace_offset(const qie_handle* h, const qie_seq* se
     if (!h || !seq) return -1;
     const Ws ws = carve(h, seq);
     return which == 0 ? (long long)ws.qkv : which == 1 ? (long long)ws.attn : -1;
+}
+
+// ---- exact caches (replaces cached_pipeline_v2.py, README.md:125, and the precompute_conditions stub at
+// qwen_realtime.py:140-165).  Setup-time calls: they allocate and synchronise. ----
+extern "C" int qie_cache_schedule(qie_handle* h, const float* timesteps_host, int n, void* stream) {
+    QIE_REQUIRE(h && timesteps_host && n > 0 && n <= 64, QIE_EINVAL, "qie_cache_schedule: bad argument");
+    QIE_REQUIRE(h->has_weights, QIE_ESTATE, "qie_cache_schedule: weights not set");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t D = h->D, L = h->cfg.num_layers, modN = L * 12 * D;
+    cudaFree(h->d_sched_mod);
+    cudaFree(h->d_sched_fin);
+    h->d_sched_mod = h->d_sched_fin = nullptr;
+    h->n_sched = 0;
+    QIE_CUDA_OK(cudaMalloc(&h->d_sched_mod, (size_t)n * modN * sizeof(float)));
+    QIE_CUDA_OK(cudaMalloc(&h->d_sched_fin, (size_t)n * 2 * D * sizeof(float)));
+    float* tproj = h->d_small;
+    float* t1 = tproj + 8 * 256;
+    float* temb = t1 + 8 * D;
+    float* d_t = temb + 8 * D;     // borrow the head of the modulation table for the timestep values
+    for (int i = 0; i < n; ++i) {  // one entry at a time: the same kernels, batch 1 -> bit-identical to the uncached forward
+        QIE_CUDA_OK(cudaMemcpyAsync(d_t, timesteps_host + i, sizeof(float), cudaMemcpyHostToDevice, st));
+        int rc;
+        if ((rc = qie_timestep_proj(d_t, tproj, 1, 0, st))) return rc;
+        if ((rc = qie_gemv(tproj, h->w.t1_w, h->w.t1_b, t1, 1, D, 256, 0, st))) return rc;
+        if ((rc = qie_gemv(t1, h->w.t2_w, h->w.t2_b, temb, 1, D, D, 1, st))) return rc;
+        if ((rc = qie_gemv(temb, h->w.mod_w, h->w.mod_b, h->d_sched_mod + (size_t)i * modN, 1, (long long)modN, D, 1, st))) return rc;
+        if ((rc = qie_gemv(temb, h->w.norm_out_w, h->w.norm_out_b, h->d_sched_fin + (size_t)i * 2 * D, 1, 2 * D, D, 1, st))) return rc;
+        QIE_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    h->n_sched = n;
+    return QIE_OK;
+}
+
+extern "C" int qie_cache_prompt(qie_handle* h, int slot, const void* enc, int txt_rows, void* stream) {
+    QIE_REQUIRE(h && enc && slot >= 0 && slot < 4 && txt_rows > 0, QIE_EINVAL, "qie_cache_prompt: bad argument");
+    QIE_REQUIRE(h->has_weights, QIE_ESTATE, "qie_cache_prompt: weights not set");
+    cudaStream_t st = (cudaStream_t)stream;
+    qie_seq s;
+    int rc = qie_make_seq(1, 128, txt_rows, &s);
+    if (rc) return rc;
+    const size_t D = h->D;
+    cudaFree(h->d_prompt[slot]);
+    h->d_prompt[slot] = nullptr;
+    h->prompt_rows[slot] = 0;
+    void* xtxt = nullptr;
+    QIE_CUDA_OK(cudaMalloc(&h->d_prompt[slot], (size_t)s.txt_pad * D * sizeof(float)));
+    QIE_CUDA_OK(cudaMalloc(&xtxt, (size_t)s.txt_pad * h->cfg.joint_dim * 2));
+    rc = qie_rmsnorm_pack(enc, h->w.txt_norm_w, xtxt, 1, txt_rows, s.txt_pad, h->cfg.joint_dim, 1e-6f, st);
+    if (!rc) {
+        qie_gemm_args t{};
+        t.a = xtxt; t.a_compact = 1; t.w[1] = h->w.txt_in_w; t.bias[1] = h->w.txt_in_b;
+        t.out = h->d_prompt[slot]; t.out_compact = 1; t.ldo = (int)D; t.N = (int)D; t.K = h->cfg.joint_dim; t.streams = 2;
+        t.epilogue = QIE_EPI_F32;
+        rc = qie_gemm(&t, &s, st);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(xtxt);
+    if (rc) return rc;
+    QIE_CUDA_OK(e);
+    h->prompt_rows[slot] = txt_rows;
+    return QIE_OK;
+}
+
+// selection used by the following qie_forward calls: sched_idx_host[b] (or NULL / -1 = compute), prompt_slot (-1 = compute)
+extern "C" int qie_cache_select(qie_handle* h, const int* sched_idx_host, int batch, int prompt_slot) {
+    QIE_REQUIRE(h && batch >= 0 && batch <= 8 && prompt_slot >= -1 && prompt_slot < 4, QIE_EINVAL, "qie_cache_select: bad argument");
+    for (int b = 0; b < 8; ++b) h->sel_sched[b] = (sched_idx_host && b < batch) ? sched_idx_host[b] : -1;
+    h->sel_prompt = prompt_slot;
+    return QIE_OK;
 }

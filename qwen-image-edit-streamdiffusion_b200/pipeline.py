@@ -47,7 +47,7 @@ def model_timestep(sigma: float, batch: int, device) -> torch.Tensor:
 def run_denoise(transformer, latents: torch.Tensor, image_latents: torch.Tensor, prompt_embeds: torch.Tensor,
                 img_shapes: List, num_inference_steps: int, negative_prompt_embeds: Optional[torch.Tensor] = None,
                 true_cfg_scale: float = 4.0, sigmas: Optional[Sequence[float]] = None, collect: Optional[list] = None,
-                uncond_fn=None) -> torch.Tensor:
+                uncond_fn=None, use_caches: bool = False) -> torch.Tensor:
     """The hot loop.  `uncond_fn(x, ts)` lets the CFG-pair parallel path supply v_uncond from the peer GPU."""
     latents = latents.to(torch.bfloat16).contiguous().clone()
     B, n, _ = latents.shape
@@ -56,17 +56,21 @@ def run_denoise(transformer, latents: torch.Tensor, image_latents: torch.Tensor,
     image_latents = image_latents.to(torch.bfloat16)
     for i in range(num_inference_steps):
         x = torch.cat([latents, image_latents], dim=1)
-        ts = model_timestep(float(sig[i]), B, latents.device)
+        ts_host = model_timestep(float(sig[i]), B, "cpu")
+        ts = ts_host.to(latents.device)
+        # use_caches: the transformer holds cache_schedule()/cache_prompt("cond"/"uncond") entries (exact)
+        kw = dict(timestep_values=[float(ts_host[0])], cached_prompt="cond") if use_caches else {}
         v = transformer(hidden_states=x, timestep=ts, encoder_hidden_states=prompt_embeds, img_shapes=img_shapes,
-                        txt_seq_lens=[prompt_embeds.shape[1]] * B, return_dict=False)[0]
+                        txt_seq_lens=[prompt_embeds.shape[1]] * B, return_dict=False, **kw)[0]
         u = None
         if do_cfg:
             if uncond_fn is not None:
                 u = uncond_fn(x, ts)
             else:
+                kwu = dict(kw, cached_prompt="uncond") if use_caches else {}
                 u = transformer(hidden_states=x, timestep=ts, encoder_hidden_states=negative_prompt_embeds,
                                 img_shapes=img_shapes, txt_seq_lens=[negative_prompt_embeds.shape[1]] * B,
-                                return_dict=False)[0]
+                                return_dict=False, **kwu)[0]
         if collect is not None:
             collect.append((v[:, :n].clone(), None if u is None else u[:, :n].clone()))
         cfg_euler_step(latents, v, u, true_cfg_scale, float(sig[i]), float(sig[i + 1]))

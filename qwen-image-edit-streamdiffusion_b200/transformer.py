@@ -61,6 +61,39 @@ def _block_keys(i: int) -> Dict[str, str]:
     }
 
 
+def merge_lora(sd: Dict[str, torch.Tensor], lora_sd: Dict[str, torch.Tensor], scale: float = 1.0) -> Dict[str, torch.Tensor]:
+    """W' = W + scale * (alpha / r) * B @ A for every targeted Linear, folded before packing / quantisation, so the two extra
+    skinny GEMMs PEFT runs per Linear (`pipeline.load_lora_weights`, server.py:76-79) disappear.
+    Accepts PEFT / diffusers naming (`<module>.lora_A.weight`, `<module>.lora_B.weight`, optional `<module>.alpha`) and the
+    kohya-style `lora_down` / `lora_up`, with an optional `transformer.` or `diffusion_model.` prefix."""
+    out = dict(sd)
+    pairs = {}
+    for k, v in lora_sd.items():
+        base = k
+        for pre in ("transformer.", "diffusion_model.", "base_model.model."):
+            if base.startswith(pre):
+                base = base[len(pre):]
+        for a_tag, b_tag in ((".lora_A.weight", ".lora_B.weight"), (".lora_down.weight", ".lora_up.weight"),
+                             (".lora_A.default.weight", ".lora_B.default.weight")):
+            if base.endswith(a_tag):
+                pairs.setdefault(base[: -len(a_tag)], {})["A"] = v
+            elif base.endswith(b_tag):
+                pairs.setdefault(base[: -len(b_tag)], {})["B"] = v
+        if base.endswith(".alpha"):
+            pairs.setdefault(base[: -len(".alpha")], {})["alpha"] = float(v)
+    for mod, ab in pairs.items():
+        if "A" not in ab or "B" not in ab:
+            raise L.QieError(f"LoRA entry for {mod} is incomplete")
+        key = mod + ".weight"
+        if key not in out:
+            raise L.QieError(f"LoRA targets {mod}, which is not a Linear of this transformer")
+        A, B = ab["A"].float(), ab["B"].float()
+        r = A.shape[0]
+        s_ = scale * (ab.get("alpha", float(r)) / r)
+        out[key] = (out[key].float() + s_ * (B @ A)).to(out[key].dtype)
+    return out
+
+
 class B200QwenImageTransformer2DModel(nn.Module):
     """`pipe.transformer = B200QwenImageTransformer2DModel.from_state_dict(sd)`."""
 
@@ -182,6 +215,22 @@ class B200QwenImageTransformer2DModel(nn.Module):
         return m
 
     @classmethod
+    def from_safetensors(cls, paths, config: QwenImageDiTConfig = QwenImageDiTConfig(), device="cuda:0", lora: Optional[str] = None,
+                         lora_scale: float = 1.0) -> "B200QwenImageTransformer2DModel":
+        """Load a diffusers `transformer/` checkpoint (one or several .safetensors shards, diffusers key names) and optionally
+        merge a LoRA file offline (next-row N2: the reference loads the Lightning LoRA un-merged via PEFT, server.py:76-79)."""
+        from safetensors import safe_open
+        sd = {}
+        for p in ([paths] if isinstance(paths, (str, bytes)) or hasattr(paths, "__fspath__") else list(paths)):
+            with safe_open(str(p), framework="pt", device="cpu") as f:
+                for k in f.keys():
+                    sd[k] = f.get_tensor(k)
+        if lora is not None:
+            with safe_open(str(lora), framework="pt", device="cpu") as f:
+                sd = merge_lora(sd, {k: f.get_tensor(k) for k in f.keys()}, lora_scale)
+        return cls.from_state_dict(sd, config, device)
+
+    @classmethod
     def from_random(cls, config: QwenImageDiTConfig = QwenImageDiTConfig(), seed: int = 0, device="cuda:0",
                     std: float = 0.02) -> "B200QwenImageTransformer2DModel":
         """Random-init weights of the architecture generated directly in HBM (no checkpoint, no network).
@@ -270,6 +319,53 @@ class B200QwenImageTransformer2DModel(nn.Module):
         L.check(L.lib().qie_set_option(self._handle, key, value), "qie_set_option")
         return self
 
+    # ------------------------------------------------------------------ exact caches
+    def cache_schedule(self, timesteps: Sequence[float]):
+        """Precompute temb, all modulation vectors and the final scale/shift for a fixed list of timestep values (the
+        values `forward` will receive, i.e. pipeline.model_timestep(sigma)).  Replaces the fixed-schedule part of the
+        reference's cached_pipeline_v2.py (README.md:125): the 13.6 GB modulation GEMV leaves the per-frame loop."""
+        vals = [float(t) for t in timesteps]
+        arr = (C.c_float * len(vals))(*vals)
+        with torch.cuda.device(self._device):
+            L.check(L.lib().qie_cache_schedule(self._handle, arr, len(vals), L.cur_stream()), "qie_cache_schedule")
+        self._sched_vals = [C.c_float(v).value for v in vals]
+        return self
+
+    def cache_prompt(self, name: str, prompt_embeds: torch.Tensor):
+        """Precompute txt_in(txt_norm(prompt_embeds)) once per prompt (reference: CachedConditions /
+        precompute_conditions, qwen_realtime.py:69-89,140-165 — a stub there).  `name` e.g. "cond" / "uncond"."""
+        names = self.__dict__.setdefault("_prompt_slots", {})
+        if name not in names:
+            if len(names) >= 4:
+                raise L.QieError("at most 4 cached prompts")
+            names[name] = len(names)
+        e = prompt_embeds.to(device=self._device, dtype=torch.bfloat16)
+        if e.dim() == 3:
+            if e.shape[0] != 1:
+                raise L.QieError("cache_prompt takes one prompt ([T, C] or [1, T, C])")
+            e = e[0]
+        e = e.contiguous()
+        with torch.cuda.device(self._device):
+            L.check(L.lib().qie_cache_prompt(self._handle, names[name], L.ptr(e), e.shape[0], L.cur_stream()), "qie_cache_prompt")
+        self.__dict__.setdefault("_prompt_rows", {})[name] = e.shape[0]
+        return self
+
+    def _select_caches(self, B: int, T: int, timestep_values, cached_prompt):
+        idx = None
+        vals = getattr(self, "_sched_vals", None)
+        if timestep_values is not None and vals:
+            tv = [C.c_float(float(v)).value for v in timestep_values]
+            tv = tv * B if len(tv) == 1 else tv
+            if len(tv) == B and all(v in vals for v in tv):
+                idx = (C.c_int * B)(*[vals.index(v) for v in tv])
+        slot = -1
+        if cached_prompt is not None:
+            slots = getattr(self, "_prompt_slots", {})
+            if cached_prompt not in slots or self._prompt_rows[cached_prompt] != T:
+                raise L.QieError(f"no cached prompt {cached_prompt!r} with {T} tokens")
+            slot = slots[cached_prompt]
+        L.check(L.lib().qie_cache_select(self._handle, idx, B if idx is not None else 0, slot), "qie_cache_select")
+
     # ------------------------------------------------------------------ measurement aids
     PROFILE_CLASSES = ("gemm", "attention", "adaln", "mod_gemv", "other")
 
@@ -294,7 +390,8 @@ class B200QwenImageTransformer2DModel(nn.Module):
                 encoder_hidden_states_mask: torch.Tensor = None, timestep: torch.Tensor = None,
                 img_shapes: Optional[List] = None, txt_seq_lens: Optional[List[int]] = None,
                 guidance: torch.Tensor = None, attention_kwargs: Optional[dict] = None,
-                controlnet_block_samples=None, return_dict: bool = True, num_blocks: int = -1, **_ignored):
+                controlnet_block_samples=None, return_dict: bool = True, num_blocks: int = -1,
+                timestep_values: Optional[Sequence[float]] = None, cached_prompt: Optional[str] = None, **_ignored):
         if controlnet_block_samples is not None:
             raise L.QieError("controlnet residuals are not on the reference's path and are not supported")
         if hidden_states.device != self._device:
@@ -318,6 +415,7 @@ class B200QwenImageTransformer2DModel(nn.Module):
         ts = timestep.to(device=self._device, dtype=torch.float32).reshape(-1).expand(B).contiguous()
         out = torch.empty(B, S_i, self.cfg.out_dim, dtype=torch.bfloat16, device=self._device)
         shp = (C.c_int * len(flat))(*flat)
+        self._select_caches(B, T, timestep_values, cached_prompt)
         with torch.cuda.device(self._device):
             L.check(L.lib().qie_forward(self._handle, L.ptr(hs), L.ptr(enc), L.ptr(ts), shp, len(flat) // 3,
                                         C.byref(seq), L.ptr(out), C.c_void_p(base), ws.numel() - (base - ws.data_ptr()),

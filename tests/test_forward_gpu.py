@@ -231,3 +231,57 @@ def test_error_convention_on_device():
     bare = qie_b200.B200QwenImageTransformer2DModel(our_cfg, DEV)
     with pytest.raises(qie_b200.QieError, match="weights not set"):
         bare(hidden.to(DEV), enc.to(DEV), None, ts, shapes, [7])
+
+
+def test_schedule_and_prompt_caches_are_bit_identical():
+    """Next-row N1: cached per-timestep modulation tables and cached per-prompt text embeddings must not
+    change a single bit of the denoise result."""
+    ref_cfg, our_cfg = small_cfg(layers=3)
+    _, ours = build_pair(ref_cfg, our_cfg)
+    shapes = [[(1, 16, 16), (1, 12, 10)]]
+    g = torch.Generator().manual_seed(9)
+    lat = torch.randn(1, 256, 64, generator=g).bfloat16().to(DEV)
+    img_lat = torch.randn(1, 120, 64, generator=g).bfloat16().to(DEV)
+    cond = (torch.randn(1, 37, 128, generator=g) * 3).bfloat16().to(DEV)
+    unc = (torch.randn(1, 22, 128, generator=g) * 3).bfloat16().to(DEV)
+    plain = qie_b200.run_denoise(ours, lat, img_lat, cond, shapes, 4, unc, 4.0)
+    sig = qie_b200.flowmatch_sigmas(4, 256)
+    ours.cache_schedule([float(qie_b200.model_timestep(float(s), 1, "cpu")[0]) for s in sig[:4]])
+    ours.cache_prompt("cond", cond).cache_prompt("uncond", unc)
+    n0 = qie_b200.lib().qie_launch_count()
+    cached = qie_b200.run_denoise(ours, lat, img_lat, cond, shapes, 4, unc, 4.0, use_caches=True)
+    n_cached = qie_b200.lib().qie_launch_count() - n0
+    n0 = qie_b200.lib().qie_launch_count()
+    again = qie_b200.run_denoise(ours, lat, img_lat, cond, shapes, 4, unc, 4.0)
+    n_plain = qie_b200.lib().qie_launch_count() - n0
+    assert torch.equal(plain, cached) and torch.equal(plain, again)
+    assert n_cached == n_plain - 8 * 7        # 8 forwards x (timestep proj + 4 gemv + text rmsnorm + txt_in GEMM) skipped
+
+
+def test_lora_merge_matches_unmerged_side_path():
+    """Next-row N2: offline LoRA merge == PEFT's un-merged x@A^T@B^T*scale side path (server.py:76-79)."""
+    ref_cfg, our_cfg = small_cfg(layers=2)
+    oracle, _ = build_pair(ref_cfg, our_cfg)
+    sd = {k: v.clone() for k, v in oracle.state_dict().items()}
+    g = torch.Generator().manual_seed(4)
+    lora = {}
+    for mod in ("transformer_blocks.0.attn.to_q", "transformer_blocks.1.img_mlp.net.2", "transformer_blocks.1.attn.add_k_proj"):
+        w = sd[mod + ".weight"]
+        lora["transformer." + mod + ".lora_A.weight"] = torch.randn(8, w.shape[1], generator=g) * 0.05
+        lora["transformer." + mod + ".lora_B.weight"] = torch.randn(w.shape[0], 8, generator=g) * 0.05
+        lora["transformer." + mod + ".alpha"] = torch.tensor(4.0)
+    merged = qie_b200.merge_lora(sd, lora, scale=1.0)
+    ours = qie_b200.B200QwenImageTransformer2DModel.from_state_dict(merged, our_cfg, DEV)
+    # reference: the oracle with the same merged weights rounded to bf16 (what the packed model holds)
+    oracle.load_state_dict({k: v.to(torch.bfloat16).float() for k, v in merged.items()})
+    w0 = sd["transformer_blocks.0.attn.to_q.weight"]
+    expect = w0 + 0.5 * lora["transformer.transformer_blocks.0.attn.to_q.lora_B.weight"] @ lora["transformer.transformer_blocks.0.attn.to_q.lora_A.weight"]
+    assert torch.allclose(merged["transformer_blocks.0.attn.to_q.weight"], expect, atol=1e-6)      # alpha / r = 4 / 8
+    shapes = [[(1, 16, 16)]]
+    hidden, enc = R.make_inputs(ref_cfg, shapes, 19)
+    hidden, enc = bf16_round(hidden), bf16_round(enc)
+    ts = torch.tensor([0.5])
+    with torch.no_grad():
+        ref = oracle(hidden, enc, None, ts, shapes, [19])[0]
+    got = ours(hidden.to(DEV), enc.to(DEV), None, ts.to(DEV), shapes, [19], return_dict=False)[0]
+    assert K.rel_err(got.cpu(), ref) <= VEL_TOL

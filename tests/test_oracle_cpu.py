@@ -217,3 +217,27 @@ def test_product_path_does_not_import_the_oracle():
     for f in list(pkg.glob("*.py")) + list((pkg / "csrc").glob("*")):
         if f.is_file() and f.suffix in (".py", ".cu", ".cuh"):
             assert "oracle" not in f.read_text().replace("int8 oracle", ""), f
+
+
+def test_merge_lora_host_math_and_naming(tmp_path):
+    """N2 host logic: W' = W + scale * alpha/r * B@A for PEFT and kohya key styles; safetensors round trip of the keys."""
+    from safetensors.torch import save_file, load_file
+    g = torch.Generator().manual_seed(0)
+    sd = {"transformer_blocks.0.attn.to_q.weight": torch.randn(16, 8, generator=g),
+          "transformer_blocks.0.attn.to_q.bias": torch.randn(16, generator=g),
+          "transformer_blocks.0.img_mlp.net.2.weight": torch.randn(8, 32, generator=g)}
+    A1, B1 = torch.randn(4, 8, generator=g), torch.randn(16, 4, generator=g)
+    A2, B2 = torch.randn(2, 32, generator=g), torch.randn(8, 2, generator=g)
+    lora = {"transformer.transformer_blocks.0.attn.to_q.lora_A.weight": A1,
+            "transformer.transformer_blocks.0.attn.to_q.lora_B.weight": B1,
+            "transformer_blocks.0.img_mlp.net.2.lora_down.weight": A2,
+            "transformer_blocks.0.img_mlp.net.2.lora_up.weight": B2,
+            "transformer_blocks.0.img_mlp.net.2.alpha": torch.tensor(1.0)}
+    save_file(lora, str(tmp_path / "lora.safetensors"))
+    m = qie_b200.merge_lora(sd, load_file(str(tmp_path / "lora.safetensors")), scale=0.5)
+    assert torch.allclose(m["transformer_blocks.0.attn.to_q.weight"], sd["transformer_blocks.0.attn.to_q.weight"] + 0.5 * B1 @ A1)
+    assert torch.allclose(m["transformer_blocks.0.img_mlp.net.2.weight"],
+                          sd["transformer_blocks.0.img_mlp.net.2.weight"] + 0.5 * (1.0 / 2) * B2 @ A2)
+    assert torch.equal(m["transformer_blocks.0.attn.to_q.bias"], sd["transformer_blocks.0.attn.to_q.bias"])
+    with pytest.raises(qie_b200.QieError, match="not a Linear"):
+        qie_b200.merge_lora(sd, {"nope.lora_A.weight": A1, "nope.lora_B.weight": B1})
