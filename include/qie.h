@@ -220,6 +220,9 @@ int qie_gemm(const qie_gemm_args* args, const qie_seq* seq, void* stream);
  * normed + roped; out bf16 [rows, H*128].  replaces F.scaled_dot_product_attention in
  * QwenDoubleStreamAttnProcessor2_0. variant: 0 default. */
 int qie_attn_fwd(const void* qkv, void* out, const qie_seq* seq, int num_heads, int variant, void* stream);
+/* Timing experiment (not part of the reference surface): device buffer of 2*5*32*8 uint64 that the trace build of the
+ * attention kernel (variant 0x804) fills with per-role clock64 stamps of one CTA pair; NULL disables. */
+int qie_attn_set_trace(void* dev_buf);
 
 /* LayerNorm(no affine, eps) + x*(1+scale)+shift; x fp32 [rows, D] -> out bf16 [rows, D].
  * shift/scale for (b, stream) at mod[b*mod_bstride + stream*mod_sstride + {shift_off,scale_off} + c].

@@ -98,6 +98,7 @@ SYMBOLS = {
     "qie_rope_table_host": (_i, [C.POINTER(ModelCfg), C.POINTER(_i), _i, C.POINTER(Seq), C.POINTER(_f)]),
     "qie_gemm": (_i, [C.POINTER(GemmArgs), C.POINTER(Seq), _vp]),
     "qie_attn_fwd": (_i, [_vp, _vp, C.POINTER(Seq), _i, _i, _vp]),
+    "qie_attn_set_trace": (_i, [_vp]),
     "qie_ln_modulate": (_i, [_vp, _vp, _ll, _ll, _i, _i, _vp, _vp, _vp, _i, _i, _f, C.POINTER(Seq), _vp]),
     "qie_gemv": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp]),
     "qie_timestep_proj": (_i, [_vp, _vp, _i, _i, _vp]),

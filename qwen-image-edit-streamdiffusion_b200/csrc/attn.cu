@@ -39,7 +39,21 @@ struct AttnDev {
     uint32_t v_lbo, v_sbo;   // V (MN-major) descriptor strides, bytes
     uint32_t v_kstep;        // byte advance of the V descriptor per 16 kv rows
     const int* tile_valid;   // optional: valid rows per 128-row KV tile (sequence-parallel layout); NULL = from seq
+    unsigned long long* trace;   // timing experiment (pair2 DBG 4): clock64 stamps of one cluster, see tools/attn_trace.py
 };
+
+// trace layout: [cta_rank 2][role 11][tile 32][event 8]; roles: 0 S issuer, 1 PV issuer, 2 + wg*4 + quad softmax warps, 10 TMA producer
+constexpr int TR_NJ = 32, TR_NEV = 8, TR_ROLES = 11;
+__device__ __forceinline__ unsigned long long clk64() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+    return t;
+}
+#define TRC(role, j, ev)                                                                                   \
+    do {                                                                                                   \
+        if (DBG == 4 && traced && (j) < TR_NJ)                                                             \
+            p.trace[((cta_rank * TR_ROLES + (role)) * TR_NJ + (j)) * TR_NEV + (ev)] = clk64();             \
+    } while (0)
 
 __device__ __forceinline__ int kv_valid_rows(const qie_seq& s, int j) {
     const int r0 = j * ATT_TILE;
@@ -778,6 +792,7 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_consta
     const int D = p.H * ATT_TILE;
     const int colQ = head * ATT_TILE, colK = D + head * ATT_TILE, colV = 2 * D + head * ATT_TILE;
     const int row_base = b * rpb;
+    [[maybe_unused]] const bool traced = DBG == 4 && p.trace && (blockIdx.x >> 1) == 3 && blockIdx.y == 9 && blockIdx.z == 0;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm128);
@@ -810,6 +825,7 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_consta
             uint32_t kph = 0, vph = 0;
             auto load_k = [&](int j) {       // my 64 kv rows x 128 head dims, as two 64-dim halves of 8 KB
                 mbar_wait(&k_empty[ks], kph ^ 1);
+                TRC(10, j, 0);
                 if (DBG == 3 && j >= 4) {     // timing experiment: no K/V traffic after the first tiles (stale smem, wrong results)
                     if (cta_rank == 0) mbar_arrive(&k_full[ks]);
                     if (++ks == AT3_KSTAGES) { ks = 0; kph ^= 1; }
@@ -824,6 +840,7 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_consta
             };
             auto load_v = [&](int j) {       // 128 kv rows x my 64 head dims
                 mbar_wait(&v_empty[vs], vph ^ 1);
+                TRC(10, j, 1);
                 if (DBG == 3 && j >= 4) {
                     if (cta_rank == 0) mbar_arrive(&v_full[vs]);
                     if (++vs == AT3_VSTAGES) { vs = 0; vph ^= 1; }
@@ -850,8 +867,9 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_consta
             constexpr uint32_t IDESC_O = umma_idesc_bf16(256, 128, true);   // B = V is MN-major
             int ks = 0, vs = 0;
             uint32_t kph = 0, vph = 0;
-            auto issue_S = [&](int buf) {
+            auto issue_S = [&](int buf, int jt) {
                 mbar_wait(&k_full[ks], kph);
+                TRC(0, jt, 1);
                 tc_fence_after();
                 const uint32_t k = smem_u32(sK + ks * AT2_SLOT_BYTES), q = smem_u32(sQ);
 #pragma unroll
@@ -861,6 +879,7 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_consta
                                     umma_desc_kmajor_sw128(k + (s >> 2) * 8192 + (s & 3) * 32), IDESC_S, s ? 1u : 0u);
                 umma_commit_cg2(&s_full[buf], 3);
                 umma_commit_cg2(&k_empty[ks], 3);
+                TRC(0, jt, 2);
                 if (++ks == AT3_KSTAGES) { ks = 0; kph ^= 1; }
             };
             auto issue_PV = [&](int buf, bool first) {
@@ -882,12 +901,13 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_consta
             //   warp 2: PV(j) as soon as P(j) is in shared memory (p_full) and V_j has landed
             mbar_wait(q_full, 0);
             tc_fence_after();
-            issue_S(0);
-            issue_S(1);
+            issue_S(0, 0);
+            issue_S(1, 1);
             for (int j = 2; j < n_kv; ++j) {
                 mbar_wait(&s_free[j & 1], ((j - 2) >> 1) & 1);   // S(j-2) of this stream is in registers in both CTAs
+                TRC(0, j, 0);
                 tc_fence_after();
-                issue_S(j & 1);
+                issue_S(j & 1, j);
             }
             (void)issue_PV;
         }
@@ -899,7 +919,9 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_consta
             for (int j = 0; j < n_kv; ++j) {
                 const int buf = j & 1;
                 mbar_wait(&v_full[vs], vph);
+                TRC(1, j, 0);
                 mbar_wait(&p_full[buf], (j >> 1) & 1);           // P(j) is in shared memory in both CTAs, O_buf rescaled
+                TRC(1, j, 1);
                 tc_fence_after();
                 const uint32_t v = smem_u32(sV + vs * AT2_SLOT_BYTES), pp = smem_u32(sP + buf * ATT_TILE_BYTES);
 #pragma unroll
@@ -910,6 +932,7 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_consta
                                     (j < 2 && s == 0) ? 0u : 1u);
                 umma_commit_cg2(&pv_done[buf], 3);
                 umma_commit_cg2(&v_empty[vs], 3);
+                TRC(1, j, 2);
                 if (++vs == AT3_VSTAGES) { vs = 0; vph ^= 1; }
             }
         }
@@ -927,9 +950,12 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_consta
         float m_ref = -INFINITY;
         uint64_t l2 = pk2(0.f, 0.f);
         int it = 0;
+        [[maybe_unused]] const bool traced_all = traced;
         for (int j = wg; j < n_kv; j += 2, ++it) {
+            [[maybe_unused]] const bool traced = traced_all && lane == 0;
             const int nv = p.tile_valid ? __ldg(p.tile_valid + j) : kv_valid_rows(p.seq, j);
             mbar_wait(&s_full[wg], it & 1);
+            TRC(2 + wg * 4 + quad, j, 0);
             tc_fence_after();
             uint32_t s[128];
 #pragma unroll
@@ -938,6 +964,7 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_consta
                 tmem_ld32(tS + ch * 32, dst);
             }
             tmem_ld_wait();
+            TRC(2 + wg * 4 + quad, j, 1);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(leader_smem_u32(&s_free[wg]));   // the tensor pipe may refill S_wg now
@@ -957,6 +984,8 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_consta
                     if (i < nv) m0 = fmaxf(m0, __uint_as_float(s[i]));
             }
             const float mx = fmaxf(m0, m1) * c;
+            if (DBG == 4 && mx == 12345.678f) m_ref = 0.f;   // (keeps the stamp below after the max pass)
+            TRC(2 + wg * 4 + quad, j, 2);
             float alpha = 1.f;
             const bool grow = mx > m_ref + 8.0f;
             if (grow) {
@@ -1005,9 +1034,11 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_consta
                     s[i >> 1] = pack_bf16(e0, e1);
                 }
             }
+            TRC(2 + wg * 4 + quad, j, 3);
             if (it > 0) {
                 // my previous PV (it reads the P tile and owns O_wg) must have retired before P / O are touched
                 mbar_wait(&pv_done[wg], (it - 1) & 1);
+                TRC(2 + wg * 4 + quad, j, 4);
                 tc_fence_after();
                 if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll 1
@@ -1029,10 +1060,12 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_consta
                 *reinterpret_cast<uint4*>(prow + (q >> 3) * ATT_HALF_BYTES + chunk * 16) =
                     make_uint4(s[q * 4], s[q * 4 + 1], s[q * 4 + 2], s[q * 4 + 3]);
             }
+            TRC(2 + wg * 4 + quad, j, 5);
             fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(leader_smem_u32(&p_full[wg]));
+            TRC(2 + wg * 4 + quad, j, 6);
         }
         // ---- epilogue: merge the two streams of this row ----
         float l_lo, l_hi;
@@ -1100,6 +1133,379 @@ static int launch_attn_pair2(const CUtensorMap& tm128, const CUtensorMap& tm64, 
     cfg.numAttrs = 1;
     QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_pair2_kernel<POLY, DBG>, tm128, tm64, p));
     QIE_LAUNCH_OK("attn_pair2_kernel");
+    return QIE_OK;
+}
+
+// =====================================================================================================================
+// CTA-pair attention with 256-wide KV tiles ("pair3").  The trace of pair2 (tools/attn_trace.py, profiles/) showed the
+// tensor pipe itself to be the limiter: a 256 x 128 x 16 SS MMA needs 4 KB of A and 4 KB of B per SM every 64 cycles =
+// 128 B/clk of operand ingest, and runs at ~2/3 of the nominal rate (the GEMM shows the same for block_n 128 vs 256).
+// This kernel raises the arithmetic intensity of both MMAs:
+//   S = Q K_j^T   : one 256 x 256 x 128 SS MMA group per 256 KV rows (96 B/clk of operands, the GEMM main-loop shape)
+//   O += P_j V_j  : P (bf16) lives in TMEM and is the A operand (TS MMA), so only V comes from shared memory (64 B/clk)
+// TMEM: O [0,128) | S [128,384) fp32 | P [384,512) bf16x2.  One softmax stream: both warpgroups work on the SAME KV tile,
+// warpgroup w on score columns [128 w, 128 w + 128); they agree on the row max through shared memory once per tile (so
+// both halves of P use one reference) and keep separate partial row sums.  S is pulled into registers at once and handed
+// back (s_free), so S(j+1) runs under the exponentials of tile j; PV(j) runs under the softmax of tile j+1.
+// Issue order of the leader: S(0) | S(1) PV(0) | S(2) PV(1) | ...
+// =====================================================================================================================
+constexpr int AT5_KSTAGES = 3, AT5_VSTAGES = 2;
+constexpr int AT5_THREADS = 384;              // warps 0-7 softmax (two warpgroups), warp 8 TMA, warp 9 MMA issuer, 10-11 idle
+constexpr int AT5_STAGE_BYTES = 32 * 1024;     // K: my 128 kv rows x 128 dims; V: 256 kv rows x my 64 dims
+constexpr int AT5_SMEM = ATT_TILE_BYTES + (AT5_KSTAGES + AT5_VSTAGES) * AT5_STAGE_BYTES + 2048 + 1024 + 512 + 1024;
+
+template <int POLY, int DBG>
+__global__ void __launch_bounds__(AT5_THREADS, 1)
+attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                                       // [2 d-halves][128 rows x 128 B]
+    uint8_t* sK = smem + ATT_TILE_BYTES;                      // [K stages][2 d-halves][128 kv rows x 128 B]
+    uint8_t* sV = sK + AT5_KSTAGES * AT5_STAGE_BYTES;         // [V stages][256 kv rows x 128 B (my 64 dims)]
+    float* xm = reinterpret_cast<float*>(sV + AT5_VSTAGES * AT5_STAGE_BYTES);   // [2 parities][2 WGs][128 rows] tile max
+    float* xl = xm + 512;                                                        // [2 WGs][128 rows] partial row sums
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xl) + 1024);
+    uint64_t* q_full = bars;                       // leader
+    uint64_t* k_full = bars + 1;                   // [K stages] leader
+    uint64_t* k_empty = k_full + AT5_KSTAGES;      // both
+    uint64_t* v_full = k_empty + AT5_KSTAGES;      // [V stages] leader
+    uint64_t* v_empty = v_full + AT5_VSTAGES;      // both
+    uint64_t* s_full = v_empty + AT5_VSTAGES;      // both
+    uint64_t* s_free = s_full + 1;                 // leader, 16 warp arrivals: S is in registers everywhere
+    uint64_t* p_full = s_free + 1;                 // leader, 16 warp arrivals: P is in TMEM, O rescaled
+    uint64_t* pv_done = p_full + 1;                // both
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int cta_rank = (int)cluster_ctarank();
+    const int rpb = p.seq.img_pad + p.seq.txt_pad;
+    const int n128 = rpb / ATT_TILE;
+    const int n_kv = (n128 + 1) / 2;               // 256-row KV tiles (the last one may be half empty)
+    const int head = blockIdx.y, b = blockIdx.z;
+    const int q_row0 = (blockIdx.x >> 1) * 2 * ATT_TILE + cta_rank * ATT_TILE;
+    const bool q_valid = q_row0 < rpb;
+    const int D = p.H * ATT_TILE;
+    const int colQ = head * ATT_TILE, colK = D + head * ATT_TILE, colV = 2 * D + head * ATT_TILE;
+    const int row_base = b * rpb;
+    [[maybe_unused]] const bool traced = DBG == 4 && p.trace && (blockIdx.x >> 1) == 3 && blockIdx.y == 9 && blockIdx.z == 0;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm128);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < AT5_KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+        for (int i = 0; i < AT5_VSTAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+        mbar_init(s_full, 1);
+        mbar_init(s_free, 16);
+        mbar_init(p_full, 16);
+        mbar_init(pv_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 9) tmem_alloc_cg2<512>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t COL_S = 128, COL_P = 384;
+    // Register redistribution (the kernel is compiled for 384 threads x 168 registers): the control warpgroup (warps 8-11)
+    // hands registers to the two softmax warpgroups, whose threads hold a whole 128-value score row.
+
+    if (warp >= 8) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+      if (warp == 8) {
+        if (lane == 0) {
+            // ================= TMA producer =================
+            if (cta_rank == 0) mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+            const int qr = q_valid ? q_row0 : 0;
+            for (int hf = 0; hf < 2; ++hf)
+                tma_load_2d_cg2(sQ + hf * ATT_HALF_BYTES, &tm128, colQ + hf * 64, row_base + qr, leader_smem_u32(q_full));
+            int ks = 0, vs = 0;
+            uint32_t kph = 0, vph = 0;
+            auto load_k = [&](int j) {       // my 128 kv rows (half of the 256-row tile) x 128 head dims, two 64-dim halves
+                mbar_wait(&k_empty[ks], kph ^ 1);
+                TRC(10, j, 0);
+                if (cta_rank == 0) mbar_expect_tx(&k_full[ks], 2 * AT5_STAGE_BYTES);
+                const uint32_t bar = leader_smem_u32(&k_full[ks]);
+                for (int hf = 0; hf < 2; ++hf)
+                    tma_load_2d_cg2(sK + ks * AT5_STAGE_BYTES + hf * ATT_HALF_BYTES, &tm128, colK + hf * 64,
+                                    row_base + j * 256 + cta_rank * ATT_TILE, bar);
+                if (++ks == AT5_KSTAGES) { ks = 0; kph ^= 1; }
+            };
+            auto load_v = [&](int j) {       // 256 kv rows x my 64 head dims
+                mbar_wait(&v_empty[vs], vph ^ 1);
+                TRC(10, j, 1);
+                if (cta_rank == 0) mbar_expect_tx(&v_full[vs], 2 * AT5_STAGE_BYTES);
+                const uint32_t bar = leader_smem_u32(&v_full[vs]);
+                for (int hf = 0; hf < 2; ++hf)
+                    tma_load_2d_cg2(sV + vs * AT5_STAGE_BYTES + hf * ATT_HALF_BYTES, &tm128, colV + cta_rank * 64,
+                                    row_base + j * 256 + hf * ATT_TILE, bar);
+                if (++vs == AT5_VSTAGES) { vs = 0; vph ^= 1; }
+            };
+            load_k(0);
+            for (int j = 0; j < n_kv; ++j) {
+                if (j + 1 < n_kv) load_k(j + 1);
+                load_v(j);
+            }
+        }
+      } else if (warp == 9) {
+        // The issuer has the highest warp id of its scheduler: the arbiter serves it first, so an MMA is issued as soon
+        // as its operands are ready even while two softmax warps keep that scheduler busy.
+        if (lane == 0 && cta_rank == 0) {
+            // ================= MMA issuer (leader) =================
+            constexpr uint32_t IDESC_S = umma_idesc_bf16(256, 256, false);
+            constexpr uint32_t IDESC_O = umma_idesc_bf16(256, 128, true);   // B = V is MN-major
+            int ks = 0, vs = 0;
+            uint32_t kph = 0, vph = 0;
+            const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(sQ));
+            auto issue_S = [&](int jt) {
+                mbar_wait(&k_full[ks], kph);
+                TRC(0, jt, 1);
+                tc_fence_after();
+                const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(sK + ks * AT5_STAGE_BYTES));
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {   // 8 x 16 head dims: + 32 B inside a swizzled row, + 16 KB for the second d-half
+                    const uint64_t off = (uint64_t)(((s >> 2) * ATT_HALF_BYTES + (s & 3) * 32) >> 4);
+                    umma_ss_f16_cg2(tmem_base + COL_S, dq + off, dk + off, IDESC_S, s ? 1u : 0u);
+                }
+                umma_commit_cg2(s_full, 3);
+                umma_commit_cg2(&k_empty[ks], 3);
+                TRC(0, jt, 2);
+                if (++ks == AT5_KSTAGES) { ks = 0; kph ^= 1; }
+            };
+            mbar_wait(q_full, 0);
+            tc_fence_after();
+            issue_S(0);
+            for (int j = 0; j < n_kv; ++j) {
+                if (j + 1 < n_kv) {
+                    mbar_wait(s_free, j & 1);                // S(j) is in registers in both CTAs
+                    TRC(0, j + 1, 0);
+                    tc_fence_after();
+                    issue_S(j + 1);
+                }
+                mbar_wait(&v_full[vs], vph);
+                TRC(1, j, 0);
+                mbar_wait(p_full, j & 1);                    // P(j) is in TMEM in both CTAs, O rescaled
+                TRC(1, j, 1);
+                tc_fence_after();
+                const uint64_t dv = umma_desc_mnmajor_sw128(smem_u32(sV + vs * AT5_STAGE_BYTES), ATT_HALF_BYTES, 1024);
+#pragma unroll
+                for (int s = 0; s < 16; ++s)    // 16 x 16 kv rows (2 KB of V each); A = P (8 packed columns per step)
+                    umma_ts_f16_cg2(tmem_base, tmem_base + COL_P + s * 8, dv + (uint64_t)(s * 128), IDESC_O,
+                                    (j == 0 && s == 0) ? 0u : 1u);
+                umma_commit_cg2(pv_done, 3);
+                umma_commit_cg2(&v_empty[vs], 3);
+                TRC(1, j, 2);
+                if (++vs == AT5_VSTAGES) { vs = 0; vph ^= 1; }
+            }
+        }
+      } else if (warp == 10 && DBG == 4) {
+        // trace build only: an observer that stamps when the S / PV MMA groups really complete
+        if (lane == 0)
+            for (int j = 0; j < n_kv; ++j) {
+                mbar_wait(s_full, j & 1);
+                TRC(1, j, 3);
+            }
+      } else if (warp == 11 && DBG == 4) {
+        if (lane == 0)
+            for (int j = 0; j < n_kv; ++j) {
+                mbar_wait(pv_done, j & 1);
+                TRC(1, j, 4);
+            }
+      }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+        // ================= softmax (warps 0-7): warpgroup wg owns score columns [128 wg, 128 wg + 128) of every KV tile =================
+        const int wg = warp >> 2;
+        const int quad = warp & 3;                   // TMEM lane quadrant a warp may touch = warp id % 4
+        const int r = quad * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        const uint32_t tS = tmem_base + lane_addr + COL_S + wg * 128;
+        const uint32_t tP = tmem_base + lane_addr + COL_P + wg * 64;
+        const uint32_t tO = tmem_base + lane_addr + wg * 64;          // the half of O this warpgroup rescales / stores
+        const float c = p.scale_log2;
+        const uint64_t c2 = pk2(c, c);
+        float m_ref = -INFINITY;
+        uint64_t l2 = pk2(0.f, 0.f);
+        [[maybe_unused]] const bool traced_all = traced;
+        auto valid_rows = [&](int t128) -> int {     // valid kv rows of my half of a 256-row tile
+            return t128 < n128 ? (p.tile_valid ? __ldg(p.tile_valid + t128) : kv_valid_rows(p.seq, t128)) : 0;
+        };
+        int nv_next = valid_rows(wg);
+        for (int j = 0; j < n_kv; ++j) {
+            [[maybe_unused]] const bool traced = traced_all && lane == 0;
+            const int nv = nv_next;
+            mbar_wait(s_full, j & 1);
+            TRC(2 + wg * 4 + quad, j, 0);
+            tc_fence_after();
+            uint32_t s[128];
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t(&dst)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[ch * 32]);
+                tmem_ld32(tS + ch * 32, dst);
+            }
+            nv_next = valid_rows(2 * (j + 1) + wg);          // its constant-bank / global latency hides under the TMEM load
+            tmem_ld_wait();
+            TRC(2 + wg * 4 + quad, j, 1);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(leader_smem_u32(s_free));   // the tensor pipe may refill S now
+            // ---- row max of my 128 columns, then the row max of the whole 256-wide tile through shared memory ----
+            float m0 = -INFINITY, m1 = -INFINITY;
+            if (nv == ATT_TILE) {
+                float m2 = -INFINITY, m3 = -INFINITY;     // four chains of 16 instead of two of 32
+#pragma unroll
+                for (int i = 0; i < 128; i += 8) {
+                    m0 = max3(m0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+                    m1 = max3(m1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+                    m2 = max3(m2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+                    m3 = max3(m3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+                }
+                m0 = fmaxf(m0, m2);
+                m1 = fmaxf(m1, m3);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 128; ++i)
+                    if (i < nv) m0 = fmaxf(m0, __uint_as_float(s[i]));
+            }
+            float* xmj = xm + (j & 1) * 256;
+            xmj[wg * 128 + r] = fmaxf(m0, m1);
+            named_bar_sync(1 + quad, 64);                     // only my partner warp (same rows, other warpgroup)
+            const float mx = fmaxf(fmaxf(m0, m1), xmj[(wg ^ 1) * 128 + r]) * c;
+            if (DBG == 4 && mx == 12345.678f) m_ref = 0.f;
+            TRC(2 + wg * 4 + quad, j, 2);
+            float alpha = 1.f;
+            const bool grow = mx > m_ref + 8.0f;      // identical decision in both warpgroups (same row, same inputs)
+            if (grow) {
+                alpha = fast_exp2(m_ref - mx);
+                m_ref = mx;
+                l2 = fma2(l2, pk2(alpha, alpha), pk2(0.f, 0.f));
+            }
+            const uint64_t nm2 = pk2(-m_ref, -m_ref);
+            // ---- exponentials in place: s[i/2] <- bf16x2(p_i, p_i+1) ----
+            if (nv == ATT_TILE) {
+#pragma unroll
+                for (int i = 0; i < 128; i += 2) {
+                    const uint64_t X = fma2(pk2u(s[i], s[i + 1]), c2, nm2);
+                    float x0, x1, e0, e1;
+                    upk2(X, x0, x1);
+                    if (((i >> 1) & 7) < POLY) {
+                        const uint64_t Xc = pk2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+                        const uint64_t T = add2(Xc, pk2(12582912.f, 12582912.f));
+                        const uint64_t N = add2(T, pk2(-12582912.f, -12582912.f));
+                        const uint64_t Fr = fma2(N, pk2(-1.f, -1.f), Xc);
+                        uint64_t P = fma2(Fr, pk2(0.0551716574f, 0.0551716574f), pk2(0.2426111400f, 0.2426111400f));
+                        P = fma2(P, Fr, pk2(0.6932609677f, 0.6932609677f));
+                        P = fma2(P, Fr, pk2(0.9999280572f, 0.9999280572f));
+                        float t0, t1, p0, p1;
+                        upk2(T, t0, t1);
+                        upk2(P, p0, p1);
+                        e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+                        e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+                    } else {
+                        e0 = fast_exp2(x0);
+                        e1 = fast_exp2(x1);
+                    }
+                    l2 = add2(l2, pk2(e0, e1));
+                    s[i >> 1] = pack_bf16(e0, e1);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 128; i += 2) {
+                    float x0, x1;
+                    upk2(fma2(pk2u(s[i], s[i + 1]), c2, nm2), x0, x1);
+                    const float e0 = i < nv ? fast_exp2(x0) : 0.f, e1 = i + 1 < nv ? fast_exp2(x1) : 0.f;
+                    l2 = add2(l2, pk2(e0, e1));
+                    s[i >> 1] = pack_bf16(e0, e1);
+                }
+            }
+            TRC(2 + wg * 4 + quad, j, 3);
+            if (j > 0) {
+                // PV(j-1) reads the P buffer and owns O: it must have retired before either is touched
+                mbar_wait(pv_done, (j - 1) & 1);
+                TRC(2 + wg * 4 + quad, j, 4);
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll 1
+                    for (int ch = 0; ch < 2; ++ch) {
+                        uint32_t o[32];
+                        tmem_ld32(tO + ch * 32, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(tO + ch * 32, o);
+                    }
+                }
+            }
+            {
+                uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+                uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+                tmem_st32(tP, lo);
+                tmem_st32(tP + 32, hi);
+                tmem_st_wait();
+            }
+            TRC(2 + wg * 4 + quad, j, 5);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(leader_smem_u32(p_full));
+            TRC(2 + wg * 4 + quad, j, 6);
+            TRC(2 + wg * 4 + quad, j, 7);
+        }
+        // ---- epilogue: O / (l_wg0 + l_wg1) -> bf16 -> global; warpgroup wg stores head dims [64 wg, 64 wg + 64) ----
+        float l_lo, l_hi;
+        upk2(l2, l_lo, l_hi);
+        xl[wg * 128 + r] = l_lo + l_hi;
+        mbar_wait(pv_done, (n_kv - 1) & 1);
+        tc_fence_after();
+        named_bar_sync(1 + quad, 64);
+        const float inv = 1.f / (xl[r] + xl[128 + r]);
+        if (q_valid) {
+            __nv_bfloat16* orow = p.out + (long long)(row_base + q_row0 + r) * D + head * ATT_TILE + wg * 64;
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ++ch) {
+                uint32_t o[32];
+                tmem_ld32(tO + ch * 32, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(o[q4 * 8 + i]) * inv;
+                    *reinterpret_cast<uint4*>(orow + ch * 32 + q4 * 8) =
+                        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                }
+            }
+        }
+    }
+
+    __syncwarp();
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 9) {
+        tc_fence_after();
+        tmem_dealloc_cg2<512>(tmem_base);
+    }
+}
+
+template <int POLY, int DBG>
+static int launch_attn_pair3(const CUtensorMap& tm128, const AttnDev& p, dim3 grid, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        QIE_CUDA_OK(cudaFuncSetAttribute(attn_pair3_kernel<POLY, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT5_SMEM));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(AT5_THREADS);
+    cfg.dynamicSmemBytes = AT5_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_pair3_kernel<POLY, DBG>, tm128, p));
+    QIE_LAUNCH_OK("attn_pair3_kernel");
     return QIE_OK;
 }
 
@@ -1433,6 +1839,12 @@ using namespace qie;
 
 static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int* tile_valid, int num_heads, int variant,
                        void* stream);
+static unsigned long long* g_attn_trace = nullptr;
+// timing experiment: device buffer of 2*5*32*8 u64 that variant 0x804 (pair2 trace build) fills with clock64 stamps
+extern "C" int qie_attn_set_trace(void* dev_buf) {
+    g_attn_trace = (unsigned long long*)dev_buf;
+    return QIE_OK;
+}
 
 extern "C" int qie_attn_fwd_tiles(const void* qkv, void* out, int n_tiles, const int* tile_valid_dev, int num_heads,
                                   int variant, void* stream) {
@@ -1460,7 +1872,13 @@ static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int
     if (variant == 0) variant = QIE_ATTN_DEFAULT_VARIANT;     // bit 8 (0x100) marks an explicit choice, e.g. 0x100 = TMEM P, all-MUFU
     const int poly = (variant >> 4) & 15, psmem = variant & 1, pair = (variant >> 1) & 1, pair2 = (variant >> 2) & 1;
     const int dq = (variant >> 3) & 1;
-    QIE_REQUIRE((variant & ~0x7FF) == 0 && !(dq && (pair || pair2 || psmem)) && !(pair2 && (pair || psmem)) && (poly == 0 || poly == 2 || poly == 3 || poly == 4) && !(pair && psmem), QIE_EINVAL,
+    const int pair3 = (variant >> 12) & 1;
+    if (pair3) {
+        QIE_REQUIRE((variant & 0x60F) == 0 && (poly == 0 || poly == 2 || poly == 3 || poly == 4), QIE_EINVAL,
+                    "qie_attn_fwd: bad variant 0x%x", variant);
+        variant &= ~0x1000;
+    }
+    QIE_REQUIRE((variant & ~0xFFF) == 0 && !(dq && (pair || pair2 || psmem)) && !(pair2 && (pair || psmem)) && (poly == 0 || poly == 2 || poly == 3 || poly == 4) && !(pair && psmem), QIE_EINVAL,
                 "qie_attn_fwd: bad variant 0x%x", variant);
     const int rpb = seq->img_pad + seq->txt_pad;
     const int D = num_heads * 128;
@@ -1480,6 +1898,16 @@ static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int
     p.v_kstep = 2048;
     dim3 grid((rpb + 255) / 256, num_heads, seq->batch);
     cudaStream_t st = (cudaStream_t)stream;
+    if (pair3) {  // CTA pair, 256-wide KV tiles, P in TMEM
+        grid.x *= 2;
+        if (variant & 0x800) { p.trace = g_attn_trace; return launch_attn_pair3<2, 4>(tm, p, grid, st); }   // trace build
+        switch (poly) {
+            case 0: return launch_attn_pair3<0, 0>(tm, p, grid, st);
+            case 2: return launch_attn_pair3<2, 0>(tm, p, grid, st);
+            case 3: return launch_attn_pair3<3, 0>(tm, p, grid, st);
+            case 4: return launch_attn_pair3<4, 0>(tm, p, grid, st);
+        }
+    }
     if (dq) {     // decoupled single-CTA kernel
         switch (poly) {
             case 0: return launch_attn_dq<0>(tm, p, grid, st);
@@ -1494,7 +1922,8 @@ static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int
         if (rc) return rc;
         grid.x *= 2;
         if (pair2) {
-            const int dbg = (variant >> 9) & 3;      // timing experiments (0x200: no MUFU, 0x400: no max pass)
+            const int dbg = (variant >> 9) & 7;      // timing experiments (0x200: no MUFU, 0x400: no max pass, 0x800: trace)
+            if (dbg == 4) { p.trace = g_attn_trace; return launch_attn_pair2<2, 4>(tm, tm64, p, grid, st); }
             if (dbg == 1) return launch_attn_pair2<0, 1>(tm, tm64, p, grid, st);
             if (dbg == 2) return launch_attn_pair2<0, 2>(tm, tm64, p, grid, st);
             if (dbg == 3) return launch_attn_pair2<0, 3>(tm, tm64, p, grid, st);
