@@ -160,6 +160,37 @@ long long qie_workspace_offset(const qie_handle* h, const qie_seq* seq, int whic
 int qie_attn_fwd_tiles(const void* qkv, void* out, int n_tiles, const int* tile_valid_dev, int num_heads, int variant,
                        void* stream);
 
+/* ---- fused Ulysses exchange over NVLink peer memory (SURVEY §8e "fusion target"): instead of pack kernel + NCCL
+ * all-to-all + unpack kernel around the attention of every block, the producing kernels store straight into the
+ * consumer rank's buffers through peer-mapped pointers:
+ *   - the QKV GEMM epilogue (RMSNorm + RoPE applied) writes head group g of q|k|v into rank g's gathered buffer
+ *     qkv_gather[g] [size*rows_pad, 3*(H/size)*128] at row (my_rank*rows_pad + local row);
+ *   - the attention epilogue of rank g writes its heads' output for the tokens of rank s into attn_out[s] [rows_pad, H*128].
+ * The only synchronisation left is qie_peer_barrier between the phases (one flag store per peer + one spin per peer).
+ * Buffers must be peer-accessible: allocate them with qie_peer_alloc and exchange the 64-byte handles between the
+ * ranks (torch.distributed all_gather of bytes), map with qie_peer_open.  Single-GPU emulation (tests): point the
+ * tables at local buffers of the emulated ranks and run the ranks' phases one after the other, without the barrier. */
+typedef struct qie_peers {
+    int rank, size;          /* my rank in the sequence-parallel group, group size (2..8, divides num_heads) */
+    int rows_pad;            /* img_pad + txt_pad of a token shard (identical on every rank) */
+    void* qkv_gather[8];     /* rank g's gathered q|k|v buffer (peer-mapped device pointers; [rank] is my own) */
+    void* attn_out[8];       /* rank s's attention-output buffer = its workspace + qie_workspace_offset(..., 1) */
+    const int* tile_valid;   /* device int[size*rows_pad/128]: valid rows of every 128-row tile of the gathered sequence */
+} qie_peers;
+/* installs (or with NULL removes) the peer tables used by the QKV and ATTN phases of qie_forward_phase on `stream` */
+int qie_set_peers(qie_handle* h, const qie_peers* peers, void* stream);
+/* cudaMalloc'ed, zero-filled, IPC-exportable device buffer; handle_out receives the 64-byte cudaIpcMemHandle_t */
+int qie_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle_out64);
+int qie_peer_free(void* dev_ptr);
+/* maps a buffer exported by another process of this node (enables peer access to its device on first use) */
+int qie_peer_open(const unsigned char* handle64, void** dev_ptr);
+int qie_peer_close(void* dev_ptr);
+/* all-ranks barrier on `stream` with system-scope release/acquire: flags[r] is rank r's array of 8 uint32 (peer-mapped,
+ * zero-initialised); every call must use epoch = previous epoch + 1 (starting at 1) on every rank.  The kernel gives up
+ * (sets a sticky error, see qie_peer_barrier_timeouts) after ~2 s instead of hanging the GPU. */
+int qie_peer_barrier(void* const* flags_host /* [size] */, int rank, int size, unsigned epoch, void* stream);
+int qie_peer_barrier_timeouts(void);
+
 /* ---- exact caches ("next" row N1): replaces cached_pipeline_v2.py (README.md:125) and the
  * precompute_conditions stub of qwen_realtime.py:140-165.  temb, every block's modulation vectors and the final
  * scale/shift depend on the timestep only; txt_in(txt_norm(prompt_embeds)) on the prompt only.  Cached forwards are
@@ -213,6 +244,10 @@ typedef struct qie_gemm_args {
     const float* w_scale[2];
     int block_n;              /* 0 = auto */
     int cta_group;            /* 0 = auto, 1 = one CTA per 128-row tile, 2 = CTA pair per 256-row tile (tcgen05 cta_group::2) */
+    /* QKV_NORM_ROPE only, batch 1: scatter the output over the sequence-parallel group instead of writing `out`
+     * (see qie_peers): peer_out = DEVICE array of sp_size pointers to the ranks' gathered buffers */
+    void* const* peer_out;
+    int sp_rank, sp_size, sp_rows;
 } qie_gemm_args;
 int qie_gemm(const qie_gemm_args* args, const qie_seq* seq, void* stream);
 

@@ -64,7 +64,13 @@ class GemmArgs(C.Structure):
                 ("N", C.c_int), ("K", C.c_int), ("streams", C.c_int), ("epilogue", C.c_int),
                 ("gate", C.c_void_p), ("gate_bstride", C.c_longlong), ("gate_sstride", C.c_longlong),
                 ("rope", C.c_void_p), ("qk_norm_w", (C.c_void_p * 2) * 2),
-                ("fp8", C.c_int), ("a_scale", C.c_void_p), ("w_scale", _P2), ("block_n", C.c_int), ("cta_group", C.c_int)]
+                ("fp8", C.c_int), ("a_scale", C.c_void_p), ("w_scale", _P2), ("block_n", C.c_int), ("cta_group", C.c_int),
+                ("peer_out", C.c_void_p), ("sp_rank", C.c_int), ("sp_size", C.c_int), ("sp_rows", C.c_int)]
+
+
+class Peers(C.Structure):
+    _fields_ = [("rank", C.c_int), ("size", C.c_int), ("rows_pad", C.c_int), ("qkv_gather", C.c_void_p * 8),
+                ("attn_out", C.c_void_p * 8), ("tile_valid", C.c_void_p)]
 
 
 EPI_BF16, EPI_GELU_BF16, EPI_F32, EPI_GATE_RESID_F32, EPI_QKV_NORM_ROPE = range(5)
@@ -90,6 +96,13 @@ SYMBOLS = {
                                C.c_size_t, _i, _vp]),
     "qie_workspace_offset": (_ll, [_vp, C.POINTER(Seq), _i]),
     "qie_attn_fwd_tiles": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp]),
+    "qie_set_peers": (_i, [_vp, C.POINTER(Peers), _vp]),
+    "qie_peer_alloc": (_i, [C.c_size_t, C.POINTER(_vp), C.c_char_p]),
+    "qie_peer_free": (_i, [_vp]),
+    "qie_peer_open": (_i, [C.c_char_p, C.POINTER(_vp)]),
+    "qie_peer_close": (_i, [_vp]),
+    "qie_peer_barrier": (_i, [C.POINTER(_vp), _i, _i, C.c_uint, _vp]),
+    "qie_peer_barrier_timeouts": (_i, []),
     "qie_cache_schedule": (_i, [_vp, C.POINTER(_f), _i, _vp]),
     "qie_cache_prompt": (_i, [_vp, _i, _vp, _i, _vp]),
     "qie_cache_select": (_i, [_vp, C.POINTER(_i), _i, _i]),

@@ -73,6 +73,8 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 }
 
 int unpack_rows(const void* x, void* out, int batch, int n, int n_pad, int C, cudaStream_t st);
+int attn_fwd_peers(const void* qkv_gathered, void* const* peer_out_dev, int n_tiles, const int* tile_valid_dev, int heads_local,
+                   int sp_rows, int out_ld, int head_off, void* stream);
 
 // -------------------------------------------------------------------------------------------
 // model handle
@@ -90,9 +92,9 @@ struct qie_handle {
     qie_weights w;
     std::vector<qie_block_weights> blocks;
     // library-owned small device buffers
-    float* d_rope;          // [rope_rows, 64, 2]
-    int rope_rows;
-    std::vector<int> rope_key;
+    float* d_rope;          // [rope_rows, 64, 2]: the table selected by the last BEGIN / QKV phase (owned by rope_cache)
+    struct RopeEntry { std::vector<int> key; float* d; };
+    std::vector<RopeEntry> rope_cache;   // one table per (img_shapes, rows, sequence-parallel shard); small, oldest evicted
     float* d_small;         // tproj [8,256] | t1 [8,D] | temb [8,D] | mod [L,2? ...] see offsets
     size_t small_bytes;
     // exact caches: per-timestep modulation tables and per-prompt text-stream embeddings
@@ -103,6 +105,10 @@ struct qie_handle {
     int prompt_rows[4] = {0, 0, 0, 0};
     int sel_sched[8] = {-1, -1, -1, -1, -1, -1, -1, -1};         // per batch row, -1 = compute
     int sel_prompt = -1;
+    // fused Ulysses exchange (qie_set_peers): host copy + device table [0..7] qkv_gather, [8..15] attn_out
+    bool has_peers = false;
+    qie_peers peers{};
+    void** d_peer_tab = nullptr;
     // optional per-kernel-class CUDA-event timing (bench.py roofline): class 0 gemm, 1 attention, 2 adaLN, 3 gemv, 4 other
     int profile;
     struct Prof { int cls; cudaEvent_t a, b; double work; };
@@ -220,7 +226,6 @@ extern "C" int qie_create(const qie_model_cfg* cfg, int device, qie_handle** out
     h->fuse_qk = 1;
     h->attn_variant = 0;
     h->d_rope = nullptr;
-    h->rope_rows = 0;
     h->profile = 0;
     // tproj [8,256] + t1 [8,D] + temb [8,D] + mod [8][L*2*6D] + final [8][2D]
     const size_t D = h->D, L = cfg->num_layers;
@@ -237,9 +242,10 @@ extern "C" int qie_create(const qie_model_cfg* cfg, int device, qie_handle** out
 extern "C" int qie_destroy(qie_handle* h) {
     if (!h) return QIE_OK;
     cudaFree(h->d_small);
-    cudaFree(h->d_rope);
+    for (auto& e : h->rope_cache) cudaFree(e.d);
     cudaFree(h->d_sched_mod);
     cudaFree(h->d_sched_fin);
+    cudaFree(h->d_peer_tab);
     for (float* p : h->d_prompt) cudaFree(p);
     delete h;
     return QIE_OK;
@@ -398,18 +404,34 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
         return qie_gemm(&g, seq, st);
     };
     auto run_attn = [&]() -> int {
+        if (h->has_peers) {
+            // my head group over the gathered sequence of every rank; the epilogue stores each token's output into the
+            // attention buffer of the rank that owns the token
+            const qie_peers& pr = h->peers;
+            const int hl = h->cfg.num_heads / pr.size, n_tiles = pr.size * pr.rows_pad / 128;
+            const double S = (double)n_tiles * 128;
+            ProfScope ps(h, st, 1, 4.0 * S * S * 128.0 * hl);
+            return attn_fwd_peers(pr.qkv_gather[pr.rank], h->d_peer_tab + 8, n_tiles, pr.tile_valid, hl, pr.rows_pad, D,
+                                  pr.rank * hl, st);
+        }
         const double S = seq->img_rows + seq->txt_rows;
         ProfScope ps(h, st, 1, 4.0 * S * S * 128.0 * h->cfg.num_heads * B);
         return qie_attn_fwd(qkv, attn, seq, h->cfg.num_heads, h->attn_variant, st);
     };
+    if (h->has_peers && (phases & (QIE_PHASE_QKV | QIE_PHASE_ATTN)))
+        QIE_REQUIRE(B == 1 && h->peers.rows_pad == rpb && h->fuse_qk && sp && sp->size == h->peers.size &&
+                        sp->rank == h->peers.rank,
+                    QIE_ESTATE, "qie_forward_phase: installed peers do not match this call (batch 1, same shard padding, same rank)");
     auto run_ln = [&](const float* mv, long long bs, long long ss, int sh, int sc, bool q8) -> int {
         ProfScope ps(h, st, 2, valid_rows * D * 6.0);
         return qie_ln_modulate(resid, mv, bs, ss, sh, sc, xm, q8 ? xm8 : nullptr, q8 ? xscale : nullptr, h->precision, D,
                                1e-6f, seq, st);
     };
 
-    // ---- RoPE table (cached per shape key; host build + one H2D copy only when the shapes change) ----
-    if (phases & QIE_PHASE_BEGIN) {
+    // ---- RoPE table (cached per shape key; host build + one H2D copy only when a new shape / shard appears).  Selected in
+    // the BEGIN phase and again in every QKV phase, so one handle can serve several shards in turn (single-GPU emulation of
+    // a sequence-parallel group) ----
+    if ((phases & (QIE_PHASE_BEGIN | QIE_PHASE_QKV)) && img_shapes_host) {
         std::vector<int> key(img_shapes_host, img_shapes_host + 3 * n_img);
         key.push_back(seq->img_rows);
         key.push_back(seq->txt_rows);
@@ -417,7 +439,10 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
             const int extra[6] = {sp->rank, sp->size, sp->img_total, sp->txt_total, sp->img_offset, sp->txt_offset};
             key.insert(key.end(), extra, extra + 6);
         }
-        if (key != h->rope_key || !h->d_rope) {
+        float* found = nullptr;
+        for (auto& e : h->rope_cache)
+            if (e.key == key) found = e.d;
+        if (!found) {
             std::vector<float> tab((size_t)rpb * 128);
             if (!sp) {
                 rc = qie_rope_table_host(&h->cfg, img_shapes_host, n_img, seq, tab.data());
@@ -436,17 +461,18 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
                 memcpy(tab.data() + (size_t)seq->img_pad * 128, all.data() + (size_t)(full.img_pad + sp->txt_offset) * 128,
                        (size_t)seq->txt_rows * 128 * sizeof(float));
             }
-            if (h->rope_rows < rpb) {
-                cudaFree(h->d_rope);
-                h->d_rope = nullptr;
-                QIE_CUDA_OK(cudaMalloc(&h->d_rope, (size_t)rpb * 128 * sizeof(float)));
-                h->rope_rows = rpb;
+            if (h->rope_cache.size() >= 16) {      // cudaFree synchronises the device: no kernel still reads the evicted table
+                cudaFree(h->rope_cache.front().d);
+                h->rope_cache.erase(h->rope_cache.begin());
             }
-            QIE_CUDA_OK(cudaMemcpyAsync(h->d_rope, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-            QIE_CUDA_OK(cudaStreamSynchronize(st));   // tab is a stack-owned host buffer; only on shape change
-            h->rope_key = key;
+            QIE_CUDA_OK(cudaMalloc(&found, tab.size() * sizeof(float)));
+            QIE_CUDA_OK(cudaMemcpyAsync(found, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+            QIE_CUDA_OK(cudaStreamSynchronize(st));   // tab is a stack-owned host buffer; only when a new shape appears
+            h->rope_cache.push_back({key, found});
         }
+        h->d_rope = found;
     }
+    QIE_REQUIRE(!(phases & QIE_PHASE_QKV) || h->d_rope, QIE_ESTATE, "qie_forward_phase: QKV phase before any BEGIN phase");
 
     // ---- small per-timestep vectors: temb, every block's modulation, final scale/shift ----
     float* tproj = h->d_small;
@@ -528,6 +554,9 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
                 g.w_scale[s] = bw.qkv_ws[s];
             }
             g.a = fp8 ? xm8 : xm; g.fp8 = fp8; g.a_scale = xscale;
+            if (h->has_peers) {   // epilogue scatters q|k|v of head group g into rank g's gathered buffer (peer stores)
+                g.peer_out = h->d_peer_tab; g.sp_rank = h->peers.rank; g.sp_size = h->peers.size; g.sp_rows = h->peers.rows_pad;
+            }
             if ((rc = run_gemm(g))) return rc;
             if (!h->fuse_qk) {
                 const float* nw[4] = {bw.q_norm_w[0], bw.k_norm_w[0], bw.q_norm_w[1], bw.k_norm_w[1]};
@@ -619,6 +648,30 @@ extern "C" int qie_forward_phase(qie_handle* h, int phases, int layer, const voi
     QIE_REQUIRE(phases > 0 && (phases & ~QIE_PHASE_ALL) == 0, QIE_EINVAL, "qie_forward_phase: bad phase mask %d", phases);
     return forward_impl(h, phases, layer, hidden, enc, timestep, img_shapes_host, n_img, seq, sp, out, workspace,
                         workspace_bytes, n_blocks, stream);
+}
+
+extern "C" int qie_set_peers(qie_handle* h, const qie_peers* peers, void* stream) {
+    QIE_REQUIRE(h, QIE_EINVAL, "qie_set_peers: null handle");
+    if (!peers) {
+        h->has_peers = false;
+        return QIE_OK;
+    }
+    QIE_REQUIRE(peers->size >= 2 && peers->size <= 8 && peers->rank >= 0 && peers->rank < peers->size &&
+                    h->cfg.num_heads % peers->size == 0 && peers->rows_pad > 0 && peers->rows_pad % 128 == 0 && peers->tile_valid,
+                QIE_EINVAL, "qie_set_peers: bad group (size %d rank %d rows_pad %d)", peers->size, peers->rank, peers->rows_pad);
+    for (int i = 0; i < peers->size; ++i)
+        QIE_REQUIRE(peers->qkv_gather[i] && peers->attn_out[i], QIE_EINVAL, "qie_set_peers: buffer of rank %d is null", i);
+    if (!h->d_peer_tab) QIE_CUDA_OK(cudaMalloc(&h->d_peer_tab, 16 * sizeof(void*)));
+    void* tab[16] = {};
+    for (int i = 0; i < peers->size; ++i) {
+        tab[i] = peers->qkv_gather[i];
+        tab[8 + i] = peers->attn_out[i];
+    }
+    // pageable source: the runtime stages it before returning, so `tab` may live on this stack; ordered on `stream`
+    QIE_CUDA_OK(cudaMemcpyAsync(h->d_peer_tab, tab, sizeof(tab), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    h->peers = *peers;
+    h->has_peers = true;
+    return QIE_OK;
 }
 
 // byte offset of an activation buffer inside the workspace: 0 = qkv [rows, 3D] bf16, 1 = attention output [rows, D] bf16

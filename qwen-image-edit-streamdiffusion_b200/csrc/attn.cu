@@ -19,7 +19,7 @@
 namespace qie {
 
 constexpr int ATT_THREADS = 384;
-#define QIE_ATTN_DEFAULT_VARIANT 0x24     /* decoupled CTA-pair kernel (pair2), 2 of 8 score pairs on the FMA-pipe polynomial: best measured in-step */
+#define QIE_ATTN_DEFAULT_VARIANT 0x1020   /* CTA pair, 256-wide KV tiles, P in TMEM (pair3), 2 of 8 score pairs on the FMA-pipe polynomial: best measured */
 constexpr int ATT_TILE = 128;                       // q rows per tile, kv rows per tile, head dim
 constexpr int ATT_HALF_BYTES = ATT_TILE * 128;      // 128 rows x 64 bf16 (one swizzled half tile) = 16 KB
 constexpr int ATT_TILE_BYTES = 2 * ATT_HALF_BYTES;  // 32 KB
@@ -40,6 +40,10 @@ struct AttnDev {
     uint32_t v_kstep;        // byte advance of the V descriptor per 16 kv rows
     const int* tile_valid;   // optional: valid rows per 128-row KV tile (sequence-parallel layout); NULL = from seq
     unsigned long long* trace;   // timing experiment (pair2 DBG 4): clock64 stamps of one cluster, see tools/attn_trace.py
+    // sequence-parallel scatter of the output (pair3 only; qie_peers): query tile rows [s*sp_rows, (s+1)*sp_rows) belong to the
+    // tokens of rank s and go to peer_out[s] [sp_rows, out_ld] at head column (head_off + head) * 128
+    void* const* peer_out;
+    int sp_rows, out_ld, head_off;
 };
 
 // trace layout: [cta_rank 2][role 11][tile 32][event 8]; roles: 0 S issuer, 1 PV issuer, 2 + wg*4 + quad softmax warps, 10 TMA producer
@@ -1154,7 +1158,7 @@ constexpr int AT5_THREADS = 384;              // warps 0-7 softmax (two warpgrou
 constexpr int AT5_STAGE_BYTES = 32 * 1024;     // K: my 128 kv rows x 128 dims; V: 256 kv rows x my 64 dims
 constexpr int AT5_SMEM = ATT_TILE_BYTES + (AT5_KSTAGES + AT5_VSTAGES) * AT5_STAGE_BYTES + 2048 + 1024 + 512 + 1024;
 
-template <int POLY, int DBG>
+template <int POLY, int DBG, int PREMAX>
 __global__ void __launch_bounds__(AT5_THREADS, 1)
 attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
     extern __shared__ uint8_t smem_raw[];
@@ -1330,6 +1334,11 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
             return t128 < n128 ? (p.tile_valid ? __ldg(p.tile_valid + t128) : kv_valid_rows(p.seq, t128)) : 0;
         };
         int nv_next = valid_rows(wg);
+        // Software pipelining of the max pass: while the exponentials of tile j keep the MUFU busy, the row max of tile j+1
+        // (whose S is already complete in TMEM) is reduced on the ALU pipe from 32-column chunks; tile j+1 then starts
+        // its exponentials right after the TMEM load.
+        bool have_pre = false;
+        float pre_max = -INFINITY;
         for (int j = 0; j < n_kv; ++j) {
             [[maybe_unused]] const bool traced = traced_all && lane == 0;
             const int nv = nv_next;
@@ -1350,7 +1359,9 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
             if (lane == 0) mbar_arrive_cluster(leader_smem_u32(s_free));   // the tensor pipe may refill S now
             // ---- row max of my 128 columns, then the row max of the whole 256-wide tile through shared memory ----
             float m0 = -INFINITY, m1 = -INFINITY;
-            if (nv == ATT_TILE) {
+            if (have_pre) {
+                m0 = pre_max;
+            } else if (nv == ATT_TILE) {
                 float m2 = -INFINITY, m3 = -INFINITY;     // four chains of 16 instead of two of 32
 #pragma unroll
                 for (int i = 0; i < 128; i += 8) {
@@ -1381,9 +1392,37 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
             }
             const uint64_t nm2 = pk2(-m_ref, -m_ref);
             // ---- exponentials in place: s[i/2] <- bf16x2(p_i, p_i+1) ----
+            have_pre = false;
             if (nv == ATT_TILE) {
+                const bool can_pre = PREMAX && j + 1 < n_kv && nv_next == ATT_TILE;
+                bool pre_on = false;
+                int pre_done = 0;
+                float q0 = -INFINITY, q1 = -INFINITY, q2 = -INFINITY, q3 = -INFINITY;
+                auto premax_to = [&](int target) {
+                    if (can_pre && !pre_on) {
+                        pre_on = __all_sync(0xffffffffu, mbar_test_wait(s_full, (j + 1) & 1));   // S(j+1) complete? (non-blocking)
+                        if (pre_on) tc_fence_after();
+                    }
+                    if (pre_on) {
+#pragma unroll 1
+                        for (; pre_done < target; ++pre_done) {
+                            uint32_t t[32];
+                            tmem_ld32(tS + pre_done * 32, t);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; i += 8) {
+                                q0 = max3(q0, __uint_as_float(t[i]), __uint_as_float(t[i + 1]));
+                                q1 = max3(q1, __uint_as_float(t[i + 2]), __uint_as_float(t[i + 3]));
+                                q2 = max3(q2, __uint_as_float(t[i + 4]), __uint_as_float(t[i + 5]));
+                                q3 = max3(q3, __uint_as_float(t[i + 6]), __uint_as_float(t[i + 7]));
+                            }
+                        }
+                    }
+                };
 #pragma unroll
                 for (int i = 0; i < 128; i += 2) {
+                    if (i == 64) premax_to(2);
+                    if (i == 96) premax_to(3);
                     const uint64_t X = fma2(pk2u(s[i], s[i + 1]), c2, nm2);
                     float x0, x1, e0, e1;
                     upk2(X, x0, x1);
@@ -1406,6 +1445,11 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
                     }
                     l2 = add2(l2, pk2(e0, e1));
                     s[i >> 1] = pack_bf16(e0, e1);
+                }
+                premax_to(4);
+                if (pre_on) {
+                    have_pre = true;
+                    pre_max = fmaxf(fmaxf(q0, q1), fmaxf(q2, q3));
                 }
             } else {
 #pragma unroll
@@ -1459,6 +1503,11 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
         const float inv = 1.f / (xl[r] + xl[128 + r]);
         if (q_valid) {
             __nv_bfloat16* orow = p.out + (long long)(row_base + q_row0 + r) * D + head * ATT_TILE + wg * 64;
+            if (p.peer_out) {      // a 128-row query tile never straddles two ranks' shards (sp_rows % 128 == 0)
+                const int srank = q_row0 / p.sp_rows;
+                orow = reinterpret_cast<__nv_bfloat16*>(__ldg(reinterpret_cast<const unsigned long long*>(p.peer_out) + srank)) +
+                       (long long)(q_row0 - srank * p.sp_rows + r) * p.out_ld + (p.head_off + head) * ATT_TILE + wg * 64;
+            }
 #pragma unroll 1
             for (int ch = 0; ch < 2; ++ch) {
                 uint32_t o[32];
@@ -1485,11 +1534,11 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
     }
 }
 
-template <int POLY, int DBG>
+template <int POLY, int DBG, int PREMAX>
 static int launch_attn_pair3(const CUtensorMap& tm128, const AttnDev& p, dim3 grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        QIE_CUDA_OK(cudaFuncSetAttribute(attn_pair3_kernel<POLY, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT5_SMEM));
+        QIE_CUDA_OK(cudaFuncSetAttribute(attn_pair3_kernel<POLY, DBG, PREMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT5_SMEM));
         configured = true;
     }
     cudaLaunchConfig_t cfg{};
@@ -1504,7 +1553,7 @@ static int launch_attn_pair3(const CUtensorMap& tm128, const AttnDev& p, dim3 gr
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_pair3_kernel<POLY, DBG>, tm128, p));
+    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_pair3_kernel<POLY, DBG, PREMAX>, tm128, p));
     QIE_LAUNCH_OK("attn_pair3_kernel");
     return QIE_OK;
 }
@@ -1837,8 +1886,9 @@ static int launch_attn_pair(const CUtensorMap& tm128, const CUtensorMap& tm64, c
 
 using namespace qie;
 
+struct AttnScatter { void* const* peer_out; int sp_rows, out_ld, head_off; };
 static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int* tile_valid, int num_heads, int variant,
-                       void* stream);
+                       void* stream, const AttnScatter* sc = nullptr);
 static unsigned long long* g_attn_trace = nullptr;
 // timing experiment: device buffer of 2*5*32*8 u64 that variant 0x804 (pair2 trace build) fills with clock64 stamps
 extern "C" int qie_attn_set_trace(void* dev_buf) {
@@ -1867,14 +1917,29 @@ extern "C" int qie_attn_fwd(const void* qkv, void* out, const qie_seq* seq, int 
     return attn_launch(qkv, out, seq, nullptr, num_heads, variant, stream);
 }
 
+// attention of one rank of a sequence-parallel group over its gathered q|k|v, output scattered to the token owners
+// (called by the ATTN phase of qie_forward_phase when peers are installed)
+namespace qie {
+int attn_fwd_peers(const void* qkv_gathered, void* const* peer_out_dev, int n_tiles, const int* tile_valid_dev, int heads_local,
+                   int sp_rows, int out_ld, int head_off, void* stream) {
+    QIE_REQUIRE(qkv_gathered && peer_out_dev && tile_valid_dev && n_tiles > 0 && heads_local > 0 && sp_rows % 128 == 0,
+                QIE_EINVAL, "attn_fwd_peers: bad argument");
+    qie_seq s{};
+    s.batch = 1;
+    s.img_rows = s.img_pad = n_tiles * 128;
+    AttnScatter sc{peer_out_dev, sp_rows, out_ld, head_off};
+    return attn_launch(qkv_gathered, const_cast<void*>(qkv_gathered) /* unused */, &s, tile_valid_dev, heads_local, 0x1020, stream, &sc);
+}
+}  // namespace qie
+
 static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int* tile_valid, int num_heads, int variant,
-                       void* stream) {
+                       void* stream, const AttnScatter* sc) {
     if (variant == 0) variant = QIE_ATTN_DEFAULT_VARIANT;     // bit 8 (0x100) marks an explicit choice, e.g. 0x100 = TMEM P, all-MUFU
     const int poly = (variant >> 4) & 15, psmem = variant & 1, pair = (variant >> 1) & 1, pair2 = (variant >> 2) & 1;
     const int dq = (variant >> 3) & 1;
     const int pair3 = (variant >> 12) & 1;
     if (pair3) {
-        QIE_REQUIRE((variant & 0x60F) == 0 && (poly == 0 || poly == 2 || poly == 3 || poly == 4), QIE_EINVAL,
+        QIE_REQUIRE((variant & 0x60E) == 0 && (poly == 0 || poly == 2 || poly == 3 || poly == 4), QIE_EINVAL,
                     "qie_attn_fwd: bad variant 0x%x", variant);
         variant &= ~0x1000;
     }
@@ -1890,6 +1955,13 @@ static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int
     p.H = num_heads;
     p.tile_valid = tile_valid;
     p.out = (__nv_bfloat16*)out;
+    if (sc) {
+        QIE_REQUIRE(pair3 && seq->batch == 1, QIE_EINVAL, "attention output scatter needs the pair3 kernel and batch 1");
+        p.peer_out = sc->peer_out;
+        p.sp_rows = sc->sp_rows;
+        p.out_ld = sc->out_ld;
+        p.head_off = sc->head_off;
+    }
     p.scale_log2 = 0.08838834764831845f * 1.4426950408889634f;   // 1/sqrt(128) * log2(e)
     // V tile in smem: two halves (64 dims each, 16 KB apart) of 128 kv rows x 128 B, 128B-swizzled by TMA.
     // MN-major canonical layout: 8 kv rows x 128 B = one 1024 B atom (SBO), next 64 dims LBO away.
@@ -1900,12 +1972,14 @@ static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int
     cudaStream_t st = (cudaStream_t)stream;
     if (pair3) {  // CTA pair, 256-wide KV tiles, P in TMEM
         grid.x *= 2;
-        if (variant & 0x800) { p.trace = g_attn_trace; return launch_attn_pair3<2, 4>(tm, p, grid, st); }   // trace build
+        const int premax = (variant & 0x1) ? 1 : 0;          // bit 0: pipelined max pass (measured slower: S(j+1) completes too late to prefetch)
+        if (variant & 0x800) { p.trace = g_attn_trace; return premax ? launch_attn_pair3<2, 4, 1>(tm, p, grid, st) : launch_attn_pair3<2, 4, 0>(tm, p, grid, st); }
+        if (premax) return launch_attn_pair3<2, 0, 1>(tm, p, grid, st);
         switch (poly) {
-            case 0: return launch_attn_pair3<0, 0>(tm, p, grid, st);
-            case 2: return launch_attn_pair3<2, 0>(tm, p, grid, st);
-            case 3: return launch_attn_pair3<3, 0>(tm, p, grid, st);
-            case 4: return launch_attn_pair3<4, 0>(tm, p, grid, st);
+            case 0: return launch_attn_pair3<0, 0, 0>(tm, p, grid, st);
+            case 2: return launch_attn_pair3<2, 0, 0>(tm, p, grid, st);
+            case 3: return launch_attn_pair3<3, 0, 0>(tm, p, grid, st);
+            case 4: return launch_attn_pair3<4, 0, 0>(tm, p, grid, st);
         }
     }
     if (dq) {     // decoupled single-CTA kernel

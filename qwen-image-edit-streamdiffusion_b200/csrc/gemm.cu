@@ -45,6 +45,8 @@ struct GemmDev {
     const float* a_scale;
     const float* w_scale[2];
     int model_dim;           // D (QKV epilogue: column block -> q/k/v)
+    void* const* peer_out;   // QKV epilogue, sequence parallel: device table of the ranks' gathered q|k|v buffers (or NULL)
+    int sp_rank, sp_hl, sp_rows;   // my rank, heads per rank, rows of one rank's shard in the gathered layout
 };
 
 template <int BN, int CG>
@@ -317,6 +319,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         stage_chunk(c, 1.f, false);
                     }
                     const bool normed = EPI == QIE_EPI_QKV_NORM_ROPE && which != 2;
+                    // sequence-parallel scatter: this 32-column chunk belongs to one head, i.e. to one destination rank;
+                    // its rows go to row (my_rank * shard_rows + local row) of that rank's gathered [q|k|v] buffer
+                    [[maybe_unused]] __nv_bfloat16* scat = nullptr;
+                    [[maybe_unused]] long long scat_ld = 0;
+                    if constexpr (EPI == QIE_EPI_QKV_NORM_ROPE) {
+                        if (p.peer_out) {
+                            const int head = (n0 - which * p.model_dim) >> 7, g = head / p.sp_hl;
+                            scat_ld = 3LL * p.sp_hl * 128;
+                            scat = reinterpret_cast<__nv_bfloat16*>(__ldg(reinterpret_cast<const unsigned long long*>(p.peer_out) + g)) +
+                                   ((long long)p.sp_rank * p.sp_rows + jrow0_in_batch) * scat_ld +
+                                   (which * p.sp_hl + (head - g * p.sp_hl)) * 128 + (n0 & 127) + c4;
+                        }
+                    }
 
                     // phase 2: issue every global load of this chunk first, then do the math and the stores
                     float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -388,7 +403,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (orow0 + rr) * p.ldo + n0 + c4) = v;
                         } else {
                             const uint2 u = valid ? make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w)) : make_uint2(0u, 0u);
-                            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (orow0 + rr) * p.ldo + n0 + c4) = u;
+                            if (EPI == QIE_EPI_QKV_NORM_ROPE && scat)
+                                *reinterpret_cast<uint2*>(scat + rr * scat_ld) = u;     // NVLink peer store (or local when g == my rank)
+                            else
+                                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (orow0 + rr) * p.ldo + n0 + c4) = u;
                         }
                     }
                     __syncwarp();   // staging tile is reused by the next chunk
@@ -513,6 +531,16 @@ extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream
         for (int k = 0; k < 2; ++k) p.qk_norm_w[s][k] = g->qk_norm_w[s][k];
     }
     p.model_dim = g->N / 3;
+    if (g->peer_out) {
+        QIE_REQUIRE(g->epilogue == QIE_EPI_QKV_NORM_ROPE && seq->batch == 1 && g->sp_size >= 1 && g->sp_size <= 8 &&
+                        g->sp_rank >= 0 && g->sp_rank < g->sp_size && (g->N / 3 / 128) % g->sp_size == 0 &&
+                        g->sp_rows == seq->img_pad + seq->txt_pad && g->streams == 3,
+                    QIE_EINVAL, "qie_gemm: peer scatter needs the QKV epilogue, batch 1, both streams, heads %% sp_size == 0");
+        p.peer_out = g->peer_out;
+        p.sp_rank = g->sp_rank;
+        p.sp_hl = g->N / 3 / 128 / g->sp_size;
+        p.sp_rows = g->sp_rows;
+    }
     if (g->epilogue == QIE_EPI_QKV_NORM_ROPE) {
         QIE_REQUIRE(g->N % 3 == 0 && p.model_dim % bn == 0 && bn >= 128 && g->rope, QIE_ESHAPE,
                     "qie_gemm: QKV epilogue needs N=3D, D %% block_n == 0, block_n>=128, rope table");

@@ -87,12 +87,53 @@ def unpack_heads(o_recv: torch.Tensor, size: int) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------
+# peer-memory buffers of the fused exchange (qie_peers in include/qie.h)
+# ------------------------------------------------------------------------------------------------
+class PeerRankBuffers:
+    """What ONE rank of a sequence-parallel group owns: its workspace (the attention-output buffer lives inside), the
+    gathered q|k|v buffer of its head group and its barrier flags, all cudaMalloc'ed by libqie so that they can be
+    exported over CUDA IPC and written by the other ranks' kernels through NVLink."""
+
+    def __init__(self, ws_bytes: int, gather_bytes: int):
+        lib = L.lib()
+        self.ptrs, self.handles = [], []
+        for n in (ws_bytes, gather_bytes, 256):
+            p, h = C.c_void_p(), C.create_string_buffer(64)
+            L.check(lib.qie_peer_alloc(n, C.byref(p), h), "qie_peer_alloc")
+            if n == ws_bytes and p.value % 1024:      # qie_forward wants a 1 KB aligned workspace; large cudaMallocs are
+                raise L.QieError("cudaMalloc returned a workspace that is not 1 KB aligned")
+            self.ptrs.append(p.value)
+            self.handles.append(h.raw)
+        self.ws, self.gather, self.flags = self.ptrs
+        self.ws_bytes = ws_bytes
+
+    def free(self):
+        for p in self.ptrs:
+            L.lib().qie_peer_free(C.c_void_p(p))
+        self.ptrs = []
+
+
+def make_peers(rank: int, size: int, rows_pad: int, gathers: Sequence[int], attn_outs: Sequence[int], tile_valid: torch.Tensor):
+    pr = L.Peers()
+    pr.rank, pr.size, pr.rows_pad = rank, size, rows_pad
+    for i in range(size):
+        pr.qkv_gather[i] = gathers[i]
+        pr.attn_out[i] = attn_outs[i]
+    pr.tile_valid = tile_valid.data_ptr()
+    return pr
+
+
+# ------------------------------------------------------------------------------------------------
 # Ulysses sequence-parallel transformer
 # ------------------------------------------------------------------------------------------------
 class UlyssesTransformer:
-    """Wraps a B200QwenImageTransformer2DModel; same call surface, the work of ONE forward is spread over `group`."""
+    """Wraps a B200QwenImageTransformer2DModel; same call surface, the work of ONE forward is spread over `group`.
 
-    def __init__(self, transformer, group=None):
+    fused=False: NCCL all-to-alls between the phases (baseline form).
+    fused=True : the QKV-GEMM and attention epilogues store straight into the peers' buffers over NVLink (CUDA IPC mapped
+                 memory) and the phases are separated by qie_peer_barrier only — no pack / all-to-all / unpack kernels."""
+
+    def __init__(self, transformer, group=None, fused: bool = False):
         self.t = transformer
         self.group = group
         self.size = dist.get_world_size(group)
@@ -101,6 +142,59 @@ class UlyssesTransformer:
             raise L.QieError(f"{transformer.cfg.num_attention_heads} heads do not split over {self.size} ranks")
         self.config = transformer.config
         self._tile_cache = {}
+        self.fused = fused
+        self._peer_state = None      # (key, PeerRankBuffers, opened pointers, Peers struct, flag table)
+        self._epoch = 0
+
+    # ---- fused path -------------------------------------------------------------------------------------------------
+    def _peer_setup(self, plan: "ShardPlan", seq, tiles: torch.Tensor):
+        t, lib, P = self.t, L.lib(), self.size
+        hl = t.cfg.num_attention_heads // P
+        key = (plan.img_pad, plan.txt_pad, P)
+        if self._peer_state is not None and self._peer_state[0] == key:
+            return self._peer_state
+        if self._peer_state is not None:
+            raise L.QieError("the fused Ulysses path keeps one shard geometry per wrapper; build a new UlyssesTransformer")
+        ws_bytes = lib.qie_workspace_bytes(t._handle, C.byref(seq))
+        mine = PeerRankBuffers(ws_bytes, P * plan.rows_pad * 3 * hl * 128 * 2)
+        dev = t.device
+        blob = torch.frombuffer(bytearray(b"".join(mine.handles)), dtype=torch.uint8).to(dev)
+        allb = torch.empty(P * blob.numel(), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allb, blob, group=self.group)
+        allb = allb.cpu().view(P, 3, 64)
+        ws_p, gather_p, flag_p, opened = [], [], [], []
+        for r in range(P):
+            if r == self.rank:
+                ptrs = (mine.ws, mine.gather, mine.flags)
+            else:
+                ptrs = []
+                for i in range(3):
+                    q = C.c_void_p()
+                    L.check(lib.qie_peer_open(bytes(allb[r, i].tolist()), C.byref(q)), "qie_peer_open")
+                    ptrs.append(q.value)
+                    opened.append(q.value)
+            ws_p.append(ptrs[0]); gather_p.append(ptrs[1]); flag_p.append(ptrs[2])
+        off = lib.qie_workspace_offset(t._handle, C.byref(seq), 1)
+        peers = make_peers(self.rank, P, plan.rows_pad, gather_p, [w + off for w in ws_p], tiles)
+        L.check(lib.qie_set_peers(t._handle, C.byref(peers), L.cur_stream()), "qie_set_peers")
+        flags = (C.c_void_p * P)(*flag_p)
+        self._peer_state = (key, mine, opened, peers, flags)
+        return self._peer_state
+
+    def _barrier(self, flags):
+        self._epoch += 1
+        L.check(L.lib().qie_peer_barrier(flags, self.rank, self.size, self._epoch, L.cur_stream()), "qie_peer_barrier")
+
+    def close(self):
+        if self._peer_state is not None:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            L.lib().qie_set_peers(self.t._handle, None, None)
+            for q in self._peer_state[2]:
+                L.lib().qie_peer_close(C.c_void_p(q))
+            dist.barrier(group=self.group)
+            self._peer_state[1].free()
+            self._peer_state = None
 
     def cache_context(self, name):
         return self.t.cache_context(name)
@@ -116,11 +210,17 @@ class UlyssesTransformer:
         dev = t.device
         seq = L.Seq(1, plan.img_rows, plan.txt_rows, plan.img_pad, plan.txt_pad)
         sp = L.Sp(plan.rank, plan.size, plan.img_total, plan.txt_total, plan.img_offset, plan.txt_offset)
+        D, H, P = t.cfg.inner_dim, t.cfg.num_attention_heads, self.size
+        rows = plan.rows_pad
+        key = plan.tile_valid
+        if key not in self._tile_cache:
+            self._tile_cache[key] = torch.tensor(plan.tile_valid, dtype=torch.int32, device=dev)
+        tiles = self._tile_cache[key]
+        if self.fused:
+            return self._call_fused(hidden_states, encoder_hidden_states, timestep, img_shapes, plan, seq, sp, tiles, return_dict)
         ws = t._workspace(seq)
         base = (ws.data_ptr() + 1023) // 1024 * 1024
         ws_bytes = ws.numel() - (base - ws.data_ptr())
-        D, H, P = t.cfg.inner_dim, t.cfg.num_attention_heads, self.size
-        rows = plan.rows_pad
 
         def view(which, width):
             off = lib.qie_workspace_offset(t._handle, C.byref(seq), which) + (base - ws.data_ptr())
@@ -134,10 +234,6 @@ class UlyssesTransformer:
         flat = [int(v) for fhw in shapes for v in fhw]
         shp = (C.c_int * len(flat))(*flat)
         out_local = torch.empty(1, plan.img_rows, t.cfg.out_dim, dtype=torch.bfloat16, device=dev)
-        key = plan.tile_valid
-        if key not in self._tile_cache:
-            self._tile_cache[key] = torch.tensor(plan.tile_valid, dtype=torch.int32, device=dev)
-        tiles = self._tile_cache[key]
         hl = H // P
         q_recv = torch.empty(P, rows, 3 * hl * 128, dtype=torch.bfloat16, device=dev)
         o_full = torch.empty(P, rows, hl * 128, dtype=torch.bfloat16, device=dev)
@@ -159,18 +255,102 @@ class UlyssesTransformer:
                 attn_local.copy_(unpack_heads(o_recv, P))
                 phase(8, l)                                                          # out-proj, adaLN2, FF on local tokens
             phase(16, -1)
-            # every rank needs the whole velocity for the (replicated) Euler update
-            sizes = split_sizes(S_i, P)
-            if len(set(sizes)) == 1:
-                full = torch.empty(P * plan.img_rows, t.cfg.out_dim, dtype=torch.bfloat16, device=dev)
-                dist.all_gather_into_tensor(full, out_local[0], group=self.group)
-                out = full.view(1, S_i, t.cfg.out_dim)
-            else:
-                parts = [torch.empty(n, t.cfg.out_dim, dtype=torch.bfloat16, device=dev) for n in sizes]
-                dist.all_gather(parts, out_local[0].contiguous(), group=self.group)
-                out = torch.cat(parts, 0).unsqueeze(0)
+            out = self._gather_velocity(out_local, S_i)
         out = out.to(hidden_states.dtype) if hidden_states.dtype != torch.bfloat16 else out
         return (out,) if not return_dict else type("Out", (), {"sample": out})()
+
+    def _gather_velocity(self, out_local, S_i):
+        """every rank needs the whole velocity for the (replicated) Euler update"""
+        t, P, dev = self.t, self.size, self.t.device
+        sizes = split_sizes(S_i, P)
+        if len(set(sizes)) == 1:
+            full = torch.empty(P * sizes[0], t.cfg.out_dim, dtype=torch.bfloat16, device=dev)
+            dist.all_gather_into_tensor(full, out_local[0], group=self.group)
+            return full.view(1, S_i, t.cfg.out_dim)
+        parts = [torch.empty(n, t.cfg.out_dim, dtype=torch.bfloat16, device=dev) for n in sizes]
+        dist.all_gather(parts, out_local[0].contiguous(), group=self.group)
+        return torch.cat(parts, 0).unsqueeze(0)
+
+    def _call_fused(self, hidden_states, encoder_hidden_states, timestep, img_shapes, plan, seq, sp, tiles, return_dict):
+        t, lib, dev = self.t, L.lib(), self.t.device
+        _, mine, _, _, flags = self._peer_setup(plan, seq, tiles)
+        S_i = hidden_states.shape[1]
+        hs = hidden_states[:, plan.img_offset: plan.img_offset + plan.img_rows].to(torch.bfloat16).contiguous()
+        enc = encoder_hidden_states[:, plan.txt_offset: plan.txt_offset + plan.txt_rows].to(dev, torch.bfloat16).contiguous()
+        ts = timestep.to(device=dev, dtype=torch.float32).reshape(-1).expand(1).contiguous()
+        shapes = img_shapes[0] if isinstance(img_shapes[0][0], (list, tuple)) else img_shapes
+        flat = [int(v) for fhw in shapes for v in fhw]
+        shp = (C.c_int * len(flat))(*flat)
+        out_local = torch.empty(1, plan.img_rows, t.cfg.out_dim, dtype=torch.bfloat16, device=dev)
+
+        def phase(mask, layer):
+            L.check(lib.qie_forward_phase(t._handle, mask, layer, L.ptr(hs), L.ptr(enc), L.ptr(ts), shp, len(flat) // 3,
+                                          C.byref(seq), C.byref(sp), L.ptr(out_local), C.c_void_p(mine.ws), mine.ws_bytes, -1,
+                                          L.cur_stream()), "qie_forward_phase")
+
+        with torch.cuda.device(dev):
+            phase(1, -1)
+            for l in range(t.cfg.num_layers):
+                phase(2, l)              # adaLN1 + QKV GEMM: the epilogue stores q|k|v of head group g into rank g's gather buffer
+                self._barrier(flags)     # everybody's q|k|v has landed in my gather buffer
+                phase(4, l)              # attention of my heads over all tokens: the epilogue stores into the token owners' buffers
+                self._barrier(flags)     # everybody's heads have landed in my attention buffer (and my gather buffer is free again)
+                phase(8, l)              # out-proj, adaLN2, FF on my tokens
+            phase(16, -1)
+            out = self._gather_velocity(out_local, S_i)
+        out = out.to(hidden_states.dtype) if hidden_states.dtype != torch.bfloat16 else out
+        return (out,) if not return_dict else type("Out", (), {"sample": out})()
+
+
+def emulate_fused_ulysses(transformer, size: int, hidden_states, encoder_hidden_states, timestep, img_shapes):
+    """Single-GPU emulation of the fused peer-memory path (tests): the `size` ranks live in ONE process on one device, the
+    peer tables point at each emulated rank's local buffers, and the ranks' phases run one after the other on one stream
+    (stream order replaces qie_peer_barrier; kernels that wait on one another must not share a GPU).  Everything else —
+    shard plan, scatter addressing in the QKV-GEMM and attention epilogues, tile list — is the code the real path runs."""
+    t, lib, dev = transformer, L.lib(), transformer.device
+    S_i, T = hidden_states.shape[1], encoder_hidden_states.shape[1]
+    H = t.cfg.num_attention_heads
+    hl = H // size
+    plans = [make_shard_plan(S_i, T, size, r) for r in range(size)]
+    rows = plans[0].rows_pad
+    tiles = torch.tensor(plans[0].tile_valid, dtype=torch.int32, device=dev)
+    seqs = [L.Seq(1, p.img_rows, p.txt_rows, p.img_pad, p.txt_pad) for p in plans]
+    sps = [L.Sp(p.rank, p.size, p.img_total, p.txt_total, p.img_offset, p.txt_offset) for p in plans]
+    ws_bytes = max(lib.qie_workspace_bytes(t._handle, C.byref(s)) for s in seqs)
+    bufs = [PeerRankBuffers(ws_bytes, size * rows * 3 * hl * 128 * 2) for _ in range(size)]
+    off = lib.qie_workspace_offset(t._handle, C.byref(seqs[0]), 1)
+    peers = [make_peers(r, size, rows, [b.gather for b in bufs], [b.ws + off for b in bufs], tiles) for r in range(size)]
+    ts = timestep.to(device=dev, dtype=torch.float32).reshape(-1).expand(1).contiguous()
+    shapes = img_shapes[0] if isinstance(img_shapes[0][0], (list, tuple)) else img_shapes
+    flat = [int(v) for fhw in shapes for v in fhw]
+    shp = (C.c_int * len(flat))(*flat)
+    hs = [hidden_states[:, p.img_offset: p.img_offset + p.img_rows].to(torch.bfloat16).contiguous() for p in plans]
+    enc = [encoder_hidden_states[:, p.txt_offset: p.txt_offset + p.txt_rows].to(dev, torch.bfloat16).contiguous() for p in plans]
+    outs = [torch.empty(1, p.img_rows, t.cfg.out_dim, dtype=torch.bfloat16, device=dev) for p in plans]
+
+    def phase(r, mask, layer):
+        L.check(lib.qie_set_peers(t._handle, C.byref(peers[r]), L.cur_stream()), "qie_set_peers")
+        L.check(lib.qie_forward_phase(t._handle, mask, layer, L.ptr(hs[r]), L.ptr(enc[r]), L.ptr(ts), shp, len(flat) // 3,
+                                      C.byref(seqs[r]), C.byref(sps[r]), L.ptr(outs[r]), C.c_void_p(bufs[r].ws), ws_bytes, -1,
+                                      L.cur_stream()), "qie_forward_phase")
+
+    try:
+        with torch.cuda.device(dev):
+            for r in range(size):
+                phase(r, 1, -1)
+            for l in range(t.cfg.num_layers):
+                for m in (2, 4, 8):
+                    for r in range(size):
+                        phase(r, m, l)
+            for r in range(size):
+                phase(r, 16, -1)
+            torch.cuda.synchronize()
+    finally:
+        lib.qie_set_peers(t._handle, None, None)
+        torch.cuda.synchronize()
+        for b in bufs:
+            b.free()
+    return torch.cat([o[0] for o in outs], 0).unsqueeze(0)
 
 
 # ------------------------------------------------------------------------------------------------

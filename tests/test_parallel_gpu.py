@@ -33,6 +33,36 @@ def test_attention_over_explicit_tile_list():
     assert K.rel_err(out[valid], ref[valid]) <= 2 ** -6
 
 
+def _tiny_model(dev, layers=3, heads=4):
+    from oracle import qwen_mmdit_ref as R
+    ref_cfg = R.RefConfig(num_layers=layers, attention_head_dim=128, num_attention_heads=heads, joint_attention_dim=128)
+    cfg = qie_b200.QwenImageDiTConfig(num_layers=layers, num_attention_heads=heads, joint_attention_dim=128)
+    oracle = R.init_weights_(R.QwenImageTransformer2DModelRef(ref_cfg), seed=0)
+    return qie_b200.B200QwenImageTransformer2DModel.from_state_dict(oracle.state_dict(), cfg, dev)
+
+
+@pytest.mark.parametrize("size,img,txt", [(2, (16, 16, 12, 10), 37), (4, (32, 32, 32, 32), 300), (2, (16, 16, 16, 16), 256)])
+def test_fused_peer_exchange_emulated_on_one_gpu(size, img, txt):
+    """The fused Ulysses exchange (QKV-GEMM epilogue and attention epilogue storing straight into the consumer ranks'
+    buffers, include/qie.h qie_peers) with the ranks emulated one after the other on ONE device: same addressing code as
+    the multi-GPU path, stream order instead of qie_peer_barrier.  Must equal the single-GPU forward."""
+    dev = torch.device("cuda", 0)
+    model = _tiny_model(dev)
+    shapes = [[(1, img[0], img[1]), (1, img[2], img[3])]]
+    n0, n1 = img[0] * img[1], img[2] * img[3]
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, n0 + n1, 64, generator=g).bfloat16().to(dev)
+    cond = (torch.randn(1, txt, 128, generator=g) * 3).bfloat16().to(dev)
+    ts = torch.tensor([0.5], device=dev)
+    single = model(x, cond, None, ts, shapes, [txt], return_dict=False)[0]
+    multi = qie_b200.emulate_fused_ulysses(model, size, x, cond, ts, shapes)
+    err = ((multi.float() - single.float()).abs().max() / single.float().abs().max()).item()
+    assert err <= 1e-2, err
+    # and the handle is back to the plain path afterwards
+    again = model(x, cond, None, ts, shapes, [txt], return_dict=False)[0]
+    assert torch.equal(again, single)
+
+
 def _worker(rank, world, q):
     import sys
     from pathlib import Path
@@ -61,6 +91,14 @@ def _worker(rank, world, q):
         sp = qie_b200.UlyssesTransformer(model, None)
         multi = sp(x, cond, None, ts, shapes, [37], return_dict=False)[0]
         e_sp = ((multi.float() - single.float()).abs().max() / single.float().abs().max()).item()
+        # --- the same with the fused peer-memory exchange (CUDA IPC mapped buffers, epilogue stores over NVLink)
+        fsp = qie_b200.UlyssesTransformer(model, None, fused=True)
+        fused = fsp(x, cond, None, ts, shapes, [37], return_dict=False)[0]
+        fused2 = fsp(x, cond, None, ts, shapes, [37], return_dict=False)[0]       # buffers / epochs are reused
+        fsp.close()
+        e_f = max(((f.float() - single.float()).abs().max() / single.float().abs().max()).item() for f in (fused, fused2))
+        e_sp = max(e_sp, e_f)
+        assert qie_b200.lib().qie_peer_barrier_timeouts() == 0
         # --- CFG pair vs one GPU
         layout = qie_b200.make_layout(world, rank, 2)
         one = qie_b200.run_denoise(model, lat, img_lat, cond, shapes, 3, unc, 4.0)
