@@ -170,7 +170,7 @@ def workload_config(args, n):
             "img_tokens": N_IMG_TOK, "txt_tokens": T_TXT, "forwards_per_image": STEPS_PER_IMAGE * (2 if args.cfg else 1),
             "layers": args.layers, "precision": args.precision, "caches": bool(getattr(args, "cache", False)),
             "parallelism": (f"dp{n}: one independent frame stream per GPU, weights replicated, no data-path collective"
-                            if args.mode == "dp" else f"{args.mode} over {n} GPUs: ONE frame, weights replicated"),
+                            if args.mode == "dp" else f"{args.mode}{' (fused peer-memory exchange)' if args.fused else ' (NCCL all-to-all)' if 'ulysses' in args.mode else ''} over {n} GPUs: ONE frame, weights replicated"),
             "l2": "inputs larger than L2: 40.9 GB of weights + 0.6 GB of activations stream through the 126 MB L2 every forward"}
 
 
@@ -218,7 +218,7 @@ def run_ours(args):
             raise SystemExit("--mode cfgpair needs --cfg")
         layout = qie_b200.make_layout(world, rank, branches)
         if layout.sp_size > 1:
-            runner = qie_b200.UlyssesTransformer(model, layout.sp_group)
+            runner = qie_b200.UlyssesTransformer(model, layout.sp_group, fused=args.fused)
         g = torch.Generator(device=dev).manual_seed(1)      # one frame: identical inputs on every rank
         lat = torch.randn(1, N_NOISE, 64, generator=g, device=dev).bfloat16()
         img_lat = torch.randn(1, N_IMG_TOK - N_NOISE, 64, generator=g, device=dev).bfloat16()
@@ -362,6 +362,8 @@ def main():
     ap.add_argument("--cache", action="store_true", help="use the exact schedule/prompt caches (N1); reported separately, "
                     "never the default: the headline recomputes every timestep-dependent vector inside the timed region")
     ap.add_argument("--mode", default="dp", choices=["dp", "cfgpair", "ulysses", "cfg+ulysses"])
+    ap.add_argument("--fused", action="store_true", help="ulysses modes: exchange q|k|v and the attention output through "
+                    "epilogue stores into peer memory (NVLink) instead of NCCL all-to-alls")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

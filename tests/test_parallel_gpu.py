@@ -41,13 +41,14 @@ def _tiny_model(dev, layers=3, heads=4):
     return qie_b200.B200QwenImageTransformer2DModel.from_state_dict(oracle.state_dict(), cfg, dev)
 
 
-@pytest.mark.parametrize("size,img,txt", [(2, (16, 16, 12, 10), 37), (4, (32, 32, 32, 32), 300), (2, (16, 16, 16, 16), 256)])
-def test_fused_peer_exchange_emulated_on_one_gpu(size, img, txt):
+@pytest.mark.parametrize("size,heads,img,txt", [(2, 4, (16, 16, 12, 10), 37), (4, 4, (32, 32, 32, 32), 300),
+                                                (2, 4, (16, 16, 16, 16), 256), (2, 6, (16, 16, 12, 10), 37)])
+def test_fused_peer_exchange_emulated_on_one_gpu(size, heads, img, txt):
     """The fused Ulysses exchange (QKV-GEMM epilogue and attention epilogue storing straight into the consumer ranks'
     buffers, include/qie.h qie_peers) with the ranks emulated one after the other on ONE device: same addressing code as
     the multi-GPU path, stream order instead of qie_peer_barrier.  Must equal the single-GPU forward."""
     dev = torch.device("cuda", 0)
-    model = _tiny_model(dev)
+    model = _tiny_model(dev, heads=heads)      # heads 6 over 2 ranks: a 256-column GEMM tile (2 heads) straddles two ranks
     shapes = [[(1, img[0], img[1]), (1, img[2], img[3])]]
     n0, n1 = img[0] * img[1], img[2] * img[3]
     g = torch.Generator().manual_seed(11)
