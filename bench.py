@@ -290,7 +290,7 @@ def run_ours(args):
     d2h = out_host.numel() * out_host.element_size()
 
     # live per-kernel-class CUDA-event timing of the same step (events on the launching stream, inside qie_forward)
-    model.profile(args.mode == "dp")
+    model.profile(True)      # sequence-parallel modes: rank 0's shard (per-rank work / per-rank time)
     step_resident()
     torch.cuda.synchronize()
     model.read_profile()
