@@ -9,9 +9,11 @@
 // and net.2 (+ gate*y + residual), plus img_in/txt_in/proj_out.
 //
 // Structure (192 threads, 1 CTA / SM, persistent, static round-robin tile schedule):
-//   warp 0 / lane 0 : TMA producer  — A tile [128 x 128 B] and W tile (128B-swizzled rows) per stage
-//   warp 1 / lane 0 : MMA issuer    — tcgen05.mma kind::f16 / kind::f8f6f4, fp32 accumulators in TMEM
-//   warps 2..5      : epilogue      — tcgen05.ld 32x32b -> registers -> per-warp smem transpose -> coalesced global
+//   warps 0..3      : epilogue      — tcgen05.ld 32x32b -> registers -> per-warp smem transpose -> coalesced global
+//   warp 4 / lane 0 : TMA producer  — A tile [128 x 128 B] and W tile (128B-swizzled rows) per stage
+//   warp 5 / lane 0 : MMA issuer    — tcgen05.mma kind::f16 / kind::f8f6f4, fp32 accumulators in TMEM.  Highest warp id of
+//                                     its scheduler on purpose: the arbiter serves the highest id first, so the issuer is
+//                                     never queued behind the epilogue warp it shares the scheduler with.
 // Three pipelines: smem full/empty ring (TMA <-> MMA), 2 TMEM accumulator stages (MMA <-> epilogue, so the
 // epilogue of tile i overlaps the main loop of tile i+1), and the tile loop.
 //
@@ -141,7 +143,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         fence_barrier_init();
     }
-    if (warp == 1) {
+    if (warp == 5) {
         if constexpr (CG == 2) tmem_alloc_cg2<S::TMEM_COLS>(tmem_slot);
         else tmem_alloc<S::TMEM_COLS>(tmem_slot);
     }
@@ -151,7 +153,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == 4) {
         if (lane == 0) {
             // ================= TMA producer (every CTA loads its own A rows and its share of W) =================
             int stage = 0;
@@ -188,7 +190,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 5) {
         if (lane == 0 && cta_rank == 0) {
             // ================= MMA issuer (leader CTA only) =================
             int stage = 0;
@@ -228,13 +230,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         }
     } else {
-        // ================= epilogue (warps 2..5) =================
+        // ================= epilogue (warps 0..3) =================
         // Each warp owns the 32 accumulator rows of its TMEM lane quadrant.  Per 32-column chunk:
         //   phase 1 (lane == row)   : tcgen05.ld -> registers -> padded per-warp smem tile
         //   phase 2 (lanes == cols) : 8 lanes x float4 cover one 128 B row segment, 4 rows per instruction, so every
         //                             global load/store of bias, gate, residual, rope and output is a coalesced line.
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
-        uint8_t* stg = smem + STAGES * S::STAGE_BYTES + S::BAR_BYTES + (warp - 2) * S::EPI_WARP_BYTES;
+        uint8_t* stg = smem + STAGES * S::STAGE_BYTES + S::BAR_BYTES + warp * S::EPI_WARP_BYTES;
         const int sub = lane >> 3, c4 = (lane & 7) * 4;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -430,7 +432,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tc_fence_before();
     if constexpr (CG == 2) cluster_sync_all();   // the peer's barriers / smem must outlive the leader's last commit
     else __syncthreads();
-    if (warp == 1) {
+    if (warp == 5) {
         tc_fence_after();
         if constexpr (CG == 2) tmem_dealloc_cg2<S::TMEM_COLS>(tmem_base);
         else tmem_dealloc<S::TMEM_COLS>(tmem_base);
