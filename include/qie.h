@@ -209,6 +209,17 @@ int qie_cfg_euler_step(const void* v_cond, const void* v_uncond, void* latents, 
                        float sigma, float sigma_next, int batch, int tokens, int channels,
                        int v_tokens_stride, void* stream);
 
+/* ---- "next" row N3: the layout step either side of the denoise loop, fused with the VAE-latent
+ * (de)normalisation.  replaces QwenImageEditPlusPipeline._pack_latents / _unpack_latents and the
+ * `(z - latents_mean) / latents_std` (encode side) / `z * latents_std + latents_mean` (decode side) tensor ops.
+ *   z       bf16 [B, C, h, w]   (C = in_channels / 4 = 16 latent channels, h and w even)
+ *   tokens  bf16 [B, (h/2)*(w/2), 4*C]; channel index of a token = c*4 + dy*2 + dx
+ *   mean/std fp32 [C] device, both NULL = pure re-layout (noise latents) */
+int qie_pack_latents(const void* z, const float* mean, const float* std, void* tokens, int batch, int channels, int h,
+                     int w, void* stream);
+int qie_unpack_latents(const void* tokens, const float* mean, const float* std, void* z, int batch, int channels, int h,
+                       int w, void* stream);
+
 /* host-only: FlowMatchEulerDiscreteScheduler.set_timesteps (dynamic exponential shift + terminal stretch);
  * writes num_steps+1 sigmas.  replaces scheduler.set_timesteps(sigmas, mu) */
 int qie_flowmatch_sigmas(int num_steps, int image_seq_len, float* sigmas_host);

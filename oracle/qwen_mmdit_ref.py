@@ -396,13 +396,39 @@ def ref_timestep_for_model(sigma: float, dtype: torch.dtype) -> torch.Tensor:
     return t / 1000
 
 
+def ref_pack_latents(z: torch.Tensor, mean=None, std=None) -> torch.Tensor:
+    """QwenImageEditPlusPipeline._pack_latents (SURVEY A.7): [B,C,h,w] -> [B,(h/2)(w/2),4C], channel = c*4 + dy*2 + dx;
+    image latents are normalised first: (z - latents_mean) / latents_std (per latent channel)."""
+    B, C, h, w = z.shape
+    if mean is not None:
+        z = (z - mean.view(1, C, 1, 1)) / std.view(1, C, 1, 1)
+    return z.view(B, C, h // 2, 2, w // 2, 2).permute(0, 2, 4, 1, 3, 5).reshape(B, (h // 2) * (w // 2), C * 4)
+
+
+def ref_unpack_latents(tokens: torch.Tensor, h: int, w: int, mean=None, std=None) -> torch.Tensor:
+    """_unpack_latents, then the decode-side de-normalisation z * latents_std + latents_mean (A.7) -> [B,C,1,h,w]."""
+    B, n, c4 = tokens.shape
+    C = c4 // 4
+    z = tokens.view(B, h // 2, w // 2, C, 2, 2).permute(0, 3, 1, 4, 2, 5).reshape(B, C, h, w)
+    if mean is not None:
+        z = z * std.view(1, C, 1, 1) + mean.view(1, C, 1, 1)
+    return z.unsqueeze(2)
+
+
+def ref_stream_prepare_latent(prev_latent, noise, frame_count: int, keyframe_interval: int = 20, noise_strength: float = 0.05):
+    """RealtimeConfig / QwenRealtimePipeline.prepare_latent of the reference (qwen_realtime.py:52-53, 201-224):
+    key frame (every keyframe_interval frames, or no previous latent) -> pure noise; else prev_latent + noise_strength*noise."""
+    is_key = (frame_count % keyframe_interval == 0) or (prev_latent is None)
+    return (noise if is_key else prev_latent + noise_strength * noise), is_key
+
+
 def ref_run_denoise(model, latents, image_latents, cond_embeds, img_shapes, num_steps: int,
-                    uncond_embeds=None, true_cfg_scale: float = 4.0, collect=None):
-    """The upstream pipeline denoise loop (A.6) on cached embeddings."""
+                    uncond_embeds=None, true_cfg_scale: float = 4.0, collect=None, begin_index: int = 0):
+    """The upstream pipeline denoise loop (A.6) on cached embeddings; begin_index = scheduler.set_begin_index."""
     sig = ref_flowmatch_sigmas(num_steps, latents.shape[1])
     n = latents.shape[1]
     B = latents.shape[0]
-    for i in range(num_steps):
+    for i in range(begin_index, num_steps):
         x = torch.cat([latents, image_latents], dim=1)
         ts = ref_timestep_for_model(float(sig[i]), latents.dtype).expand(B)
         v = model(hidden_states=x, timestep=ts, encoder_hidden_states=cond_embeds, img_shapes=img_shapes,

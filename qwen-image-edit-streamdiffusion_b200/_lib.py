@@ -107,6 +107,8 @@ SYMBOLS = {
     "qie_cache_prompt": (_i, [_vp, _i, _vp, _i, _vp]),
     "qie_cache_select": (_i, [_vp, C.POINTER(_i), _i, _i]),
     "qie_cfg_euler_step": (_i, [_vp, _vp, _vp, _f, _f, _f, _i, _i, _i, _i, _vp]),
+    "qie_pack_latents": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "qie_unpack_latents": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "qie_flowmatch_sigmas": (_i, [_i, _i, C.POINTER(_f)]),
     "qie_rope_table_host": (_i, [C.POINTER(ModelCfg), C.POINTER(_i), _i, C.POINTER(Seq), C.POINTER(_f)]),
     "qie_gemm": (_i, [C.POINTER(GemmArgs), C.POINTER(Seq), _vp]),

@@ -488,6 +488,64 @@ int unpack_rows(const void* x, void* out, int batch, int n, int n_pad, int C, cu
 }
 }  // namespace qie
 
+// _pack_latents / _unpack_latents fused with the VAE-latent normalisation.  One thread per (token, latent
+// channel): the four bf16 of a 2x2 patch are one 8-byte store (pack) / load (unpack) on the token side, two 4-byte
+// accesses on the [B, C, h, w] side.  0.5 MB at 1024^2: launch-latency bound, HBM traffic = read once + write once.
+template <bool PACK>
+__global__ void latent_layout_kernel(__nv_bfloat16* __restrict__ z, __nv_bfloat16* __restrict__ tok,
+                                     const float* __restrict__ mean, const float* __restrict__ stdv, int batch, int C,
+                                     int h, int w) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int h2 = h / 2, w2 = w / 2;
+    if (i >= (long long)batch * h2 * w2 * C) return;
+    const int c = (int)(i % C);
+    const long long t = i / C;                                   // token index over the batch
+    const int x2 = (int)(t % w2), y2 = (int)((t / w2) % h2), b = (int)(t / ((long long)w2 * h2));
+    __nv_bfloat16* zp = z + (((long long)b * C + c) * h + 2 * y2) * w + 2 * x2;
+    __nv_bfloat16* tp = tok + t * (4 * C) + c * 4;
+    const float m = mean ? mean[c] : 0.f, sd = stdv ? stdv[c] : 1.f;
+    if (PACK) {
+        const float2 r0 = unpack_bf16(*reinterpret_cast<const uint32_t*>(zp));
+        const float2 r1 = unpack_bf16(*reinterpret_cast<const uint32_t*>(zp + w));
+        *reinterpret_cast<uint2*>(tp) = make_uint2(pack_bf16(__fdiv_rn(r0.x - m, sd), __fdiv_rn(r0.y - m, sd)),
+                                                   pack_bf16(__fdiv_rn(r1.x - m, sd), __fdiv_rn(r1.y - m, sd)));
+    } else {
+        const uint2 u = *reinterpret_cast<const uint2*>(tp);
+        const float2 r0 = unpack_bf16(u.x), r1 = unpack_bf16(u.y);
+        // separate multiply and add (no FMA contraction): bit-equal to the tensor ops `z * std + mean` it replaces
+        *reinterpret_cast<uint32_t*>(zp) = pack_bf16(__fadd_rn(__fmul_rn(r0.x, sd), m), __fadd_rn(__fmul_rn(r0.y, sd), m));
+        *reinterpret_cast<uint32_t*>(zp + w) = pack_bf16(__fadd_rn(__fmul_rn(r1.x, sd), m), __fadd_rn(__fmul_rn(r1.y, sd), m));
+    }
+}
+
+static int latent_layout(bool pack, const void* z, const float* mean, const float* stdv, const void* tokens, int batch,
+                         int channels, int h, int w, void* stream) {
+    QIE_REQUIRE(z && tokens, QIE_EINVAL, "qie_%spack_latents: null pointer", pack ? "" : "un");
+    QIE_REQUIRE(batch > 0 && channels > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, QIE_ESHAPE,
+                "qie_%spack_latents: latent height and width must be even (got %d x %d)", pack ? "" : "un", h, w);
+    QIE_REQUIRE((mean == nullptr) == (stdv == nullptr), QIE_EINVAL, "qie_%spack_latents: give both mean and std or neither",
+                pack ? "" : "un");
+    const long long total = (long long)batch * (h / 2) * (w / 2) * channels;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (pack)
+        latent_layout_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)z, (__nv_bfloat16*)tokens, mean,
+                                                                             stdv, batch, channels, h, w);
+    else
+        latent_layout_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)z, (__nv_bfloat16*)tokens, mean,
+                                                                              stdv, batch, channels, h, w);
+    QIE_LAUNCH_OK("latent_layout_kernel");
+    return QIE_OK;
+}
+
+extern "C" int qie_pack_latents(const void* z, const float* mean, const float* stdv, void* tokens, int batch, int channels,
+                                int h, int w, void* stream) {
+    return latent_layout(true, z, mean, stdv, tokens, batch, channels, h, w, stream);
+}
+extern "C" int qie_unpack_latents(const void* tokens, const float* mean, const float* stdv, void* z, int batch, int channels,
+                                  int h, int w, void* stream) {
+    return latent_layout(false, z, mean, stdv, tokens, batch, channels, h, w, stream);
+}
+
 extern "C" int qie_quant_rows(const void* x, void* q, float* scale, long long rows, int K, int qmode, void* stream) {
     QIE_REQUIRE(x && q && scale, QIE_EINVAL, "qie_quant_rows: null pointer");
     QIE_REQUIRE(K % 8 == 0 && (qmode == 1 || qmode == 2), QIE_ESHAPE, "qie_quant_rows: K %% 8 != 0 or bad mode");

@@ -43,18 +43,53 @@ def model_timestep(sigma: float, batch: int, device) -> torch.Tensor:
     return (t / 1000).expand(batch).to(device)
 
 
+def pack_latents(z: torch.Tensor, mean: Optional[torch.Tensor] = None, std: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`_pack_latents` of the upstream pipeline (SURVEY A.7): [B, C, h, w] (or [B, C, 1, h, w]) bf16 -> [B, (h/2)(w/2), 4C];
+    with the VAE `latents_mean` / `latents_std` given, the `(z - mean) / std` of the image-latent path is fused in."""
+    if z.dim() == 5:
+        z = z[:, :, 0]
+    assert z.dtype == torch.bfloat16 and z.is_cuda
+    z = z.contiguous()
+    B, Cc, h, w = z.shape
+    out = torch.empty(B, (h // 2) * (w // 2), 4 * Cc, dtype=torch.bfloat16, device=z.device)
+    m = None if mean is None else mean.to(z.device, torch.float32).contiguous()
+    sd = None if std is None else std.to(z.device, torch.float32).contiguous()
+    with torch.cuda.device(z.device):
+        L.check(L.lib().qie_pack_latents(L.ptr(z), L.ptr(m), L.ptr(sd), L.ptr(out), B, Cc, h, w, L.cur_stream()), "qie_pack_latents")
+    return out
+
+
+def unpack_latents(tokens: torch.Tensor, h: int, w: int, mean: Optional[torch.Tensor] = None,
+                   std: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`_unpack_latents` + `z * latents_std + latents_mean` (decode side): [B, (h/2)(w/2), 4C] -> [B, C, 1, h, w]."""
+    assert tokens.dtype == torch.bfloat16 and tokens.is_cuda
+    tokens = tokens.contiguous()
+    B, n, c4 = tokens.shape
+    if n != (h // 2) * (w // 2) or c4 % 4:
+        raise L.QieError(f"unpack_latents: {n} tokens x {c4} channels do not form a {h}x{w} latent")
+    z = torch.empty(B, c4 // 4, h, w, dtype=torch.bfloat16, device=tokens.device)
+    m = None if mean is None else mean.to(tokens.device, torch.float32).contiguous()
+    sd = None if std is None else std.to(tokens.device, torch.float32).contiguous()
+    with torch.cuda.device(tokens.device):
+        L.check(L.lib().qie_unpack_latents(L.ptr(tokens), L.ptr(m), L.ptr(sd), L.ptr(z), B, c4 // 4, h, w, L.cur_stream()),
+                "qie_unpack_latents")
+    return z.unsqueeze(2)
+
+
 @torch.no_grad()
 def run_denoise(transformer, latents: torch.Tensor, image_latents: torch.Tensor, prompt_embeds: torch.Tensor,
                 img_shapes: List, num_inference_steps: int, negative_prompt_embeds: Optional[torch.Tensor] = None,
                 true_cfg_scale: float = 4.0, sigmas: Optional[Sequence[float]] = None, collect: Optional[list] = None,
-                uncond_fn=None, use_caches: bool = False) -> torch.Tensor:
-    """The hot loop.  `uncond_fn(x, ts)` lets the CFG-pair parallel path supply v_uncond from the peer GPU."""
+                uncond_fn=None, use_caches: bool = False, begin_index: int = 0) -> torch.Tensor:
+    """The hot loop.  `uncond_fn(x, ts)` lets the CFG-pair parallel path supply v_uncond from the peer GPU.
+    `begin_index` > 0 enters the schedule part-way (scheduler.set_begin_index upstream): the streaming path starts from the
+    previous frame's re-noised latent instead of pure noise."""
     latents = latents.to(torch.bfloat16).contiguous().clone()
     B, n, _ = latents.shape
     sig = np.asarray(sigmas, dtype=np.float32) if sigmas is not None else flowmatch_sigmas(num_inference_steps, n)
     do_cfg = true_cfg_scale > 1 and (negative_prompt_embeds is not None or uncond_fn is not None)
     image_latents = image_latents.to(torch.bfloat16)
-    for i in range(num_inference_steps):
+    for i in range(begin_index, num_inference_steps):
         x = torch.cat([latents, image_latents], dim=1)
         ts_host = model_timestep(float(sig[i]), B, "cpu")
         ts = ts_host.to(latents.device)
@@ -75,3 +110,52 @@ def run_denoise(transformer, latents: torch.Tensor, image_latents: torch.Tensor,
             collect.append((v[:, :n].clone(), None if u is None else u[:, :n].clone()))
         cfg_euler_step(latents, v, u, true_cfg_scale, float(sig[i]), float(sig[i + 1]))
     return latents
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# "next" row N4: stateful streaming (the StreamDiffusion-style loop qwen_realtime.py:201-224 sketches but never wires:
+# `prepare_latent` is dead code there and process_frame always denoises from pure noise, qwen_realtime.py:226-268)
+# ------------------------------------------------------------------------------------------------------------------
+class StreamingDenoiser:
+    """Per-frame state of a realtime edit stream.
+
+    Key frames (every `keyframe_interval` frames, and the first) denoise from pure noise over the whole schedule; the frames
+    in between start from `prev_latent + noise_strength * noise` (qwen_realtime.py:216-222, `noise_strength` 0.05,
+    `keyframe_interval` 20 in RealtimeConfig) and only run the last `stream_steps` steps of the schedule, i.e. they enter
+    FlowMatchEulerDiscreteScheduler at `begin_index = num_inference_steps - stream_steps`."""
+
+    def __init__(self, transformer, img_shapes, prompt_embeds, negative_prompt_embeds=None, num_inference_steps: int = 4,
+                 true_cfg_scale: float = 1.0, noise_strength: float = 0.05, keyframe_interval: int = 20,
+                 stream_steps: int = 2, denoise_fn=None):
+        if not (1 <= stream_steps <= num_inference_steps):
+            raise ValueError("stream_steps must be in [1, num_inference_steps]")
+        if keyframe_interval < 1:
+            raise ValueError("keyframe_interval must be >= 1")
+        self.t, self.img_shapes = transformer, img_shapes
+        self.cond, self.uncond = prompt_embeds, negative_prompt_embeds
+        self.steps, self.cfg_scale = num_inference_steps, true_cfg_scale
+        self.noise_strength, self.keyframe_interval, self.stream_steps = noise_strength, keyframe_interval, stream_steps
+        self.prev_latent: Optional[torch.Tensor] = None
+        self.frame_count = 0
+        self.is_keyframe = True
+        self._denoise = denoise_fn or run_denoise
+
+    def prepare_latent(self, noise: torch.Tensor):
+        """qwen_realtime.py:201-224 — returns (start latent, begin_index)."""
+        self.is_keyframe = (self.frame_count % self.keyframe_interval == 0) or (self.prev_latent is None)
+        if self.is_keyframe:
+            return noise, 0
+        return self.prev_latent + self.noise_strength * noise.to(self.prev_latent.dtype), self.steps - self.stream_steps
+
+    def process_frame(self, image_latents: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
+        """One frame: `image_latents` = packed VAE latents of the camera frame (condition), `noise` = N(0,1) of the latent shape."""
+        start, begin = self.prepare_latent(noise)
+        out = self._denoise(self.t, start, image_latents, self.cond, self.img_shapes, self.steps, self.uncond, self.cfg_scale,
+                            begin_index=begin)
+        self.prev_latent = out
+        self.frame_count += 1
+        return out
+
+    def forwards_per_frame(self) -> int:
+        per_step = 2 if (self.uncond is not None and self.cfg_scale > 1) else 1
+        return per_step * (self.steps if self.is_keyframe else self.stream_steps)

@@ -285,3 +285,52 @@ def test_lora_merge_matches_unmerged_side_path():
         ref = oracle(hidden, enc, None, ts, shapes, [19])[0]
     got = ours(hidden.to(DEV), enc.to(DEV), None, ts.to(DEV), shapes, [19], return_dict=False)[0]
     assert K.rel_err(got.cpu(), ref) <= VEL_TOL
+
+
+# ------------------------------------------------------------------ next rows N3 / N4
+@pytest.mark.parametrize("B,h,w", [(1, 128, 128), (2, 6, 10), (1, 64, 96)])
+def test_pack_unpack_latents_bit_exact(B, h, w):
+    """qie_pack_latents / qie_unpack_latents against the restated _pack_latents / _unpack_latents (+ VAE normalisation)."""
+    g = torch.Generator().manual_seed(21)
+    C_ = 16
+    z = torch.randn(B, C_, h, w, generator=g).bfloat16()
+    mean, std = torch.randn(C_, generator=g), torch.rand(C_, generator=g) + 0.5
+    # pure re-layout: bit exact
+    tok = qie_b200.pack_latents(z.to(DEV))
+    assert torch.equal(tok.cpu(), R.ref_pack_latents(z))
+    assert torch.equal(qie_b200.unpack_latents(tok, h, w).cpu(), z.unsqueeze(2))
+    # fused normalisation: fp32 arithmetic on the bf16 inputs, one rounding -> equal to the fp32 oracle rounded once
+    tokn = qie_b200.pack_latents(z.to(DEV), mean, std)
+    assert torch.equal(tokn.cpu(), R.ref_pack_latents(z.float(), mean, std).bfloat16())
+    zn = qie_b200.unpack_latents(tokn, h, w, mean, std)
+    assert torch.equal(zn.cpu(), R.ref_unpack_latents(tokn.cpu().float(), h, w, mean, std).bfloat16())
+    with pytest.raises(qie_b200.QieError):
+        qie_b200.unpack_latents(tok, h + 2, w)
+
+
+def test_streaming_frames_match_oracle():
+    """N4: key frame, streamed frame (enters the schedule at begin_index with prev_latent + 0.05*noise), key frame — the CUDA
+    path against the fp32 oracle running the same state machine."""
+    ref_cfg = R.RefConfig(num_layers=2, attention_head_dim=128, num_attention_heads=2, joint_attention_dim=128)
+    cfg = qie_b200.QwenImageDiTConfig(num_layers=2, num_attention_heads=2, joint_attention_dim=128)
+    oracle = R.init_weights_(R.QwenImageTransformer2DModelRef(ref_cfg), seed=0).eval()
+    with torch.no_grad():
+        for p_ in oracle.parameters():
+            p_.copy_(p_.to(torch.bfloat16).float())
+    model = qie_b200.B200QwenImageTransformer2DModel.from_state_dict(oracle.state_dict(), cfg, DEV)
+    shapes = [[(1, 16, 16), (1, 16, 16)]]
+    g = torch.Generator().manual_seed(33)
+    rnd = lambda *s_: torch.randn(*s_, generator=g).to(torch.bfloat16).float()
+    cond = rnd(1, 19, 128) * 3
+    sd = qie_b200.StreamingDenoiser(model, shapes, cond.to(DEV), num_inference_steps=4, keyframe_interval=2, stream_steps=2)
+    prev = None
+    for f in range(3):
+        img_lat, noise = rnd(1, 256, 64), rnd(1, 256, 64)
+        start, key = R.ref_stream_prepare_latent(prev, noise, f, 2, 0.05)
+        with torch.no_grad():
+            want = R.ref_run_denoise(oracle, start, img_lat, cond, shapes, 4, begin_index=0 if key else 2)
+        got = sd.process_frame(img_lat.to(DEV), noise.to(DEV).bfloat16())
+        assert sd.is_keyframe == key
+        cos = torch.nn.functional.cosine_similarity(got.float().cpu().flatten(), want.flatten(), dim=0).item()
+        assert cos >= 0.999, (f, cos)
+        prev = want

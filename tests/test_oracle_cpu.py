@@ -241,3 +241,56 @@ def test_merge_lora_host_math_and_naming(tmp_path):
     assert torch.equal(m["transformer_blocks.0.attn.to_q.bias"], sd["transformer_blocks.0.attn.to_q.bias"])
     with pytest.raises(qie_b200.QieError, match="not a Linear"):
         qie_b200.merge_lora(sd, {"nope.lora_A.weight": A1, "nope.lora_B.weight": B1})
+
+
+# ------------------------------------------------------------------ next rows N3 / N4
+def test_pack_latents_index_formula_and_round_trip():
+    """_pack_latents: channel index of a packed token = c*4 + dy*2 + dx; unpack is its inverse; the VAE
+    normalisation round-trips."""
+    g = torch.Generator().manual_seed(5)
+    B, C, h, w = 2, 16, 6, 8
+    z = torch.randn(B, C, h, w, generator=g)
+    tok = R.ref_pack_latents(z)
+    assert tok.shape == (B, (h // 2) * (w // 2), 4 * C)
+    for (b, c, y, x) in [(0, 0, 0, 0), (1, 3, 5, 7), (0, 15, 2, 5), (1, 7, 3, 0)]:
+        assert tok[b, (y // 2) * (w // 2) + x // 2, c * 4 + (y % 2) * 2 + (x % 2)] == z[b, c, y, x]
+    assert torch.equal(R.ref_unpack_latents(tok, h, w)[:, :, 0], z)
+    mean, std = torch.randn(C, generator=g), torch.rand(C, generator=g) + 0.5
+    back = R.ref_unpack_latents(R.ref_pack_latents(z, mean, std), h, w, mean, std)[:, :, 0]
+    assert torch.allclose(back, z, atol=1e-5)
+
+
+def test_stream_prepare_latent_follows_the_reference_sketch():
+    """qwen_realtime.py:201-224: key frame every keyframe_interval frames (and when there is no previous latent)."""
+    noise, prev = torch.ones(1, 4, 8), torch.full((1, 4, 8), 2.0)
+    lat, key = R.ref_stream_prepare_latent(None, noise, 3)
+    assert key and torch.equal(lat, noise)
+    lat, key = R.ref_stream_prepare_latent(prev, noise, 20)
+    assert key and torch.equal(lat, noise)
+    lat, key = R.ref_stream_prepare_latent(prev, noise, 21)
+    assert not key and torch.allclose(lat, prev + 0.05 * noise)
+
+
+def test_streaming_denoiser_host_logic_matches_oracle_schedule():
+    """StreamingDenoiser (host side of N4) on CPU with an injected denoise function: which frames are key frames, where the
+    schedule is entered, and that the previous latent feeds the next frame — against ref_stream_prepare_latent."""
+    import qie_b200
+    calls = []
+
+    def fake_denoise(t, start, img_lat, cond, shapes, steps, unc, scale, begin_index=0):
+        calls.append((start.clone(), begin_index))
+        return start * 0.5 + 1.0
+
+    sd = qie_b200.StreamingDenoiser(None, None, None, num_inference_steps=4, keyframe_interval=3, stream_steps=1,
+                                    noise_strength=0.05, denoise_fn=fake_denoise)
+    g = torch.Generator().manual_seed(0)
+    prev = None
+    for f in range(7):
+        noise = torch.randn(1, 4, 8, generator=g)
+        want, key = R.ref_stream_prepare_latent(prev, noise, f, 3, 0.05)
+        out = sd.process_frame(None, noise)
+        start, begin = calls[-1]
+        assert torch.allclose(start, want) and begin == (0 if key else 3) and sd.is_keyframe == key
+        assert sd.forwards_per_frame() == (4 if key else 1)
+        prev = out
+    assert sd.frame_count == 7
