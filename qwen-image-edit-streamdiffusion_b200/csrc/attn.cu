@@ -44,6 +44,10 @@ struct AttnDev {
     // tokens of rank s and go to peer_out[s] [sp_rows, out_ld] at head column (head_off + head) * 128
     void* const* peer_out;
     int sp_rows, out_ld, head_off;
+    // speculative-reference build of pair3: `overflow` is raised when a score exceeded the running reference by more than 2^100
+    // (its P tile is then unusable); the exact build launched right behind it only runs when `run_if` points at a raised flag
+    int* overflow;
+    const int* run_if;
 };
 
 // trace layout: [cta_rank 2][role 11][tile 32][event 8]; roles: 0 S issuer, 1 PV issuer, 2 + wg*4 + quad softmax warps, 10 TMA producer
@@ -1156,7 +1160,7 @@ static int launch_attn_pair2(const CUtensorMap& tm128, const CUtensorMap& tm64, 
 constexpr int AT5_KSTAGES = 3, AT5_VSTAGES = 2;
 constexpr int AT5_THREADS = 384;              // warps 0-7 softmax (two warpgroups), warp 8 TMA, warp 9 MMA issuer, 10-11 idle
 constexpr int AT5_STAGE_BYTES = 32 * 1024;     // K: my 128 kv rows x 128 dims; V: 256 kv rows x my 64 dims
-constexpr int AT5_SMEM = ATT_TILE_BYTES + (AT5_KSTAGES + AT5_VSTAGES) * AT5_STAGE_BYTES + 2048 + 1024 + 512 + 1024;
+constexpr int AT5_SMEM = ATT_TILE_BYTES + (AT5_KSTAGES + AT5_VSTAGES) * AT5_STAGE_BYTES + 2048 + 1024 + 2048 + 512 + 1024;
 
 template <int POLY, int DBG, int PREMAX>
 __global__ void __launch_bounds__(AT5_THREADS, 1)
@@ -1168,7 +1172,8 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
     uint8_t* sV = sK + AT5_KSTAGES * AT5_STAGE_BYTES;         // [V stages][256 kv rows x 128 B (my 64 dims)]
     float* xm = reinterpret_cast<float*>(sV + AT5_VSTAGES * AT5_STAGE_BYTES);   // [2 parities][2 WGs][128 rows] tile max
     float* xl = xm + 512;                                                        // [2 WGs][128 rows] partial row sums
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xl) + 1024);
+    float* xr = xl + 256;                                                        // [2 parities][2 WGs][128 rows] running max (scaled)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xr) + 2048);
     uint64_t* q_full = bars;                       // leader
     uint64_t* k_full = bars + 1;                   // [K stages] leader
     uint64_t* k_empty = k_full + AT5_KSTAGES;      // both
@@ -1191,6 +1196,7 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
     const int D = p.H * ATT_TILE;
     const int colQ = head * ATT_TILE, colK = D + head * ATT_TILE, colV = 2 * D + head * ATT_TILE;
     const int row_base = b * rpb;
+    if (p.run_if && *p.run_if == 0) return;        // exact rerun behind a speculative launch: nothing overflowed, nothing to do
     [[maybe_unused]] const bool traced = DBG == 4 && p.trace && (blockIdx.x >> 1) == 3 && blockIdx.y == 9 && blockIdx.z == 0;
 
     if (threadIdx.x == 0) {
@@ -1214,7 +1220,7 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
     // hands registers to the two softmax warpgroups, whose threads hold a whole 128-value score row.
 
     if (warp >= 8) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
       if (warp == 8) {
         if (lane == 0) {
             // ================= TMA producer =================
@@ -1316,7 +1322,7 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
             }
       }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         // ================= softmax (warps 0-7): warpgroup wg owns score columns [128 wg, 128 wg + 128) of every KV tile =================
         const int wg = warp >> 2;
         const int quad = warp & 3;                   // TMEM lane quadrant a warp may touch = warp id % 4
@@ -1339,6 +1345,12 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
         // its exponentials right after the TMEM load.
         bool have_pre = false;
         float pre_max = -INFINITY;
+        // PREMAX == 2, speculative reference: from the second tile on there is no max pass in front of the exponentials.  The
+        // reference is the largest score both warpgroups have seen in EARLIER tiles (exchanged through shared memory one tile
+        // late); the current tile's maximum is tracked inside the exponential loop on the otherwise idle ALU pipe.  Scores above
+        // the reference just give P > 1 (fp32 / bf16 have the range; O and l share the reference, so the result is exact); only a
+        // jump of more than 2^100 within one tile would overflow, which raises p.overflow and reruns the exact kernel.
+        float m_run = -INFINITY;
         for (int j = 0; j < n_kv; ++j) {
             [[maybe_unused]] const bool traced = traced_all && lane == 0;
             const int nv = nv_next;
@@ -1358,8 +1370,10 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(leader_smem_u32(s_free));   // the tensor pipe may refill S now
             // ---- row max of my 128 columns, then the row max of the whole 256-wide tile through shared memory ----
+            const bool spec = PREMAX == 2 && j > 0;
             float m0 = -INFINITY, m1 = -INFINITY;
-            if (have_pre) {
+            if (spec) {
+            } else if (have_pre) {
                 m0 = pre_max;
             } else if (nv == ATT_TILE) {
                 float m2 = -INFINITY, m3 = -INFINITY;     // four chains of 16 instead of two of 32
@@ -1377,10 +1391,20 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
                 for (int i = 0; i < 128; ++i)
                     if (i < nv) m0 = fmaxf(m0, __uint_as_float(s[i]));
             }
-            float* xmj = xm + (j & 1) * 256;
-            xmj[wg * 128 + r] = fmaxf(m0, m1);
-            named_bar_sync(1 + quad, 64);                     // only my partner warp (same rows, other warpgroup)
-            const float mx = fmaxf(fmaxf(m0, m1), xmj[(wg ^ 1) * 128 + r]) * c;
+            float mx;
+            if (spec) {
+                named_bar_sync(1 + quad, 64);                 // my partner has published its running max of tile j-1
+                mx = fmaxf(m_run, xr[((j - 1) & 1) * 256 + (wg ^ 1) * 128 + r]);
+            } else {
+                float* xmj = xm + (j & 1) * 256;
+                xmj[wg * 128 + r] = fmaxf(m0, m1);
+                named_bar_sync(1 + quad, 64);                 // only my partner warp (same rows, other warpgroup)
+                mx = fmaxf(fmaxf(m0, m1), xmj[(wg ^ 1) * 128 + r]) * c;
+                if (PREMAX == 2) {
+                    m_run = mx;
+                    xr[(j & 1) * 256 + wg * 128 + r] = mx;
+                }
+            }
             if (DBG == 4 && mx == 12345.678f) m_ref = 0.f;
             TRC(2 + wg * 4 + quad, j, 2);
             float alpha = 1.f;
@@ -1393,8 +1417,9 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
             const uint64_t nm2 = pk2(-m_ref, -m_ref);
             // ---- exponentials in place: s[i/2] <- bf16x2(p_i, p_i+1) ----
             have_pre = false;
+            [[maybe_unused]] float xt0 = -INFINITY, xt1 = -INFINITY;      // max of (score - reference) over my columns of this tile
             if (nv == ATT_TILE) {
-                const bool can_pre = PREMAX && j + 1 < n_kv && nv_next == ATT_TILE;
+                const bool can_pre = PREMAX == 1 && j + 1 < n_kv && nv_next == ATT_TILE;
                 bool pre_on = false;
                 int pre_done = 0;
                 float q0 = -INFINITY, q1 = -INFINITY, q2 = -INFINITY, q3 = -INFINITY;
@@ -1426,6 +1451,10 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
                     const uint64_t X = fma2(pk2u(s[i], s[i + 1]), c2, nm2);
                     float x0, x1, e0, e1;
                     upk2(X, x0, x1);
+                    if (PREMAX == 2) {
+                        if (i & 2) xt1 = max3(xt1, x0, x1);
+                        else xt0 = max3(xt0, x0, x1);
+                    }
                     if (((i >> 1) & 7) < POLY) {
                         const uint64_t Xc = pk2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
                         const uint64_t T = add2(Xc, pk2(12582912.f, 12582912.f));
@@ -1457,9 +1486,19 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
                     float x0, x1;
                     upk2(fma2(pk2u(s[i], s[i + 1]), c2, nm2), x0, x1);
                     const float e0 = i < nv ? fast_exp2(x0) : 0.f, e1 = i + 1 < nv ? fast_exp2(x1) : 0.f;
+                    if (PREMAX == 2) {
+                        if (i < nv) xt0 = fmaxf(xt0, x0);
+                        if (i + 1 < nv) xt1 = fmaxf(xt1, x1);
+                    }
                     l2 = add2(l2, pk2(e0, e1));
                     s[i >> 1] = pack_bf16(e0, e1);
                 }
+            }
+            if (spec) {
+                const float xmax = fmaxf(xt0, xt1);
+                m_run = fmaxf(m_run, xmax + m_ref);
+                xr[(j & 1) * 256 + wg * 128 + r] = m_run;
+                if (__any_sync(0xffffffffu, xmax > 100.f) && lane == 0) atomicOr(p.overflow, 1);
             }
             TRC(2 + wg * 4 + quad, j, 3);
             if (j > 0) {
@@ -1939,7 +1978,7 @@ static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int
     const int dq = (variant >> 3) & 1;
     const int pair3 = (variant >> 12) & 1;
     if (pair3) {
-        QIE_REQUIRE((variant & 0x60E) == 0 && (poly == 0 || poly == 2 || poly == 3 || poly == 4), QIE_EINVAL,
+        QIE_REQUIRE((variant & 0x60C) == 0 && (poly == 0 || poly == 2 || poly == 3 || poly == 4), QIE_EINVAL,
                     "qie_attn_fwd: bad variant 0x%x", variant);
         variant &= ~0x1000;
     }
@@ -1973,8 +2012,25 @@ static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int
     if (pair3) {  // CTA pair, 256-wide KV tiles, P in TMEM
         grid.x *= 2;
         const int premax = (variant & 0x1) ? 1 : 0;          // bit 0: pipelined max pass (measured slower: S(j+1) completes too late to prefetch)
+        const int spec = (variant & 0x2) ? 1 : 0;            // bit 1: speculative reference (no max pass in front of the exponentials;
+                                                             // measured slower: 0.77 vs 0.69 ms, the in-loop max tracking raises register pressure)
         if (variant & 0x800) { p.trace = g_attn_trace; return premax ? launch_attn_pair3<2, 4, 1>(tm, p, grid, st) : launch_attn_pair3<2, 4, 0>(tm, p, grid, st); }
         if (premax) return launch_attn_pair3<2, 0, 1>(tm, p, grid, st);
+        if (spec) {
+            // fast launch with a speculative softmax reference, then the exact kernel, which returns at once unless the fast
+            // one raised its overflow flag (a score 2^100 above every earlier score of its row: never on real activations)
+            static int* flags = nullptr;
+            static unsigned next = 0;
+            if (!flags) QIE_CUDA_OK(cudaMalloc(&flags, 64 * sizeof(int)));
+            int* flag = flags + (next++ & 63);
+            QIE_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+            p.overflow = flag;
+            int rc2 = poly == 3 ? launch_attn_pair3<3, 0, 2>(tm, p, grid, st) : launch_attn_pair3<2, 0, 2>(tm, p, grid, st);
+            if (rc2) return rc2;
+            p.overflow = nullptr;
+            p.run_if = flag;
+            return launch_attn_pair3<2, 0, 0>(tm, p, grid, st);
+        }
         switch (poly) {
             case 0: return launch_attn_pair3<0, 0, 0>(tm, p, grid, st);
             case 2: return launch_attn_pair3<2, 0, 0>(tm, p, grid, st);

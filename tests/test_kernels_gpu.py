@@ -263,7 +263,7 @@ def test_gemm_fp8(cta_group):
 @pytest.mark.parametrize("B,img,txt,H", [(1, 256, 128, 2), (1, 384, 128, 1), (2, 200, 19, 2), (1, 1024, 219, 3),
                                          (2, 520, 130, 2)])
 @pytest.mark.parametrize("variant", [0, 0x100, 0x01, 0x20, 0x31, 0x41, 0x102, 0x22, 0x42, 0x104, 0x24, 0x34, 0x108, 0x28,
-                                     0x1000, 0x1020, 0x1030, 0x1040, 0x1021])
+                                     0x1000, 0x1020, 0x1030, 0x1040, 0x1021, 0x1022, 0x1032])
 def test_attention(B, img, txt, H, variant):
     s = K.seq(B, img, txt)
     D = H * 128
@@ -291,6 +291,26 @@ def test_attention_large_scores_lazy_rescale():
     x = qkv.float().reshape(1, -1, 3, H, 128)
     q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
     ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(-1, D)
+    assert K.rel_err(got, ref) <= 2 ** -6
+
+
+@pytest.mark.parametrize("variant", [0, 0x1020, 0x1022])
+@pytest.mark.parametrize("jump", [3.0, 40.0])
+def test_attention_score_jumps_between_tiles(variant, jump):
+    """Keys whose scale jumps from one KV tile to the next: the lazy rescale path (moderate jump) and, for the speculative-
+    reference build 0x1022, the overflow flag + exact rerun (a jump far beyond 2^100 in the exponent)."""
+    s = K.seq(1, 768, 128)
+    H, D = 1, 128
+    qkv = randn(K.rows(s), 3 * D, seed=92, dtype=torch.bfloat16)
+    kscale = torch.ones(K.rows(s), 1, device=DEV)
+    kscale[512:768] = jump                                   # the third 256-row KV tile carries much larger keys
+    qkv[:, D:2 * D] = (qkv[:, D:2 * D].float() * kscale).to(torch.bfloat16)
+    qkv[:, :D] = (qkv[:, :D].float() * 4).to(torch.bfloat16)
+    got = K.attn(s, qkv, H, variant)
+    x = qkv.float().reshape(1, -1, 3, H, 128)
+    q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(-1, D)
+    assert torch.isfinite(got.float()).all()
     assert K.rel_err(got, ref) <= 2 ** -6
 
 
