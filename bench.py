@@ -33,9 +33,9 @@ N_NOISE, N_IMG_TOK, T_TXT = 4096, 8192, 256
 STEPS_PER_IMAGE = 2
 
 
-def flops_per_forward(cfg_layers=60, D=3072, H=24, S_i=N_IMG_TOK, T=T_TXT, B=1):
+def flops_per_forward(cfg_layers=60, D=3072, H=24, S_i=None, T=None, B=1):
     """per block 2*D*(3D + D + 2*FF)*S linear + 4*S^2*d_h*H attention (+ tiny top)."""
-    S = S_i + T
+    S = (N_IMG_TOK if S_i is None else S_i) + (T_TXT if T is None else T)
     lin = 2.0 * D * (3 * D + D + 8 * D) * S
     att = 4.0 * S * S * 128 * H
     return B * cfg_layers * (lin + att)
@@ -165,8 +165,10 @@ def run_reference(args):
 
 
 def workload_config(args, n):
-    return {"workload": "Qwen-Image-Edit-2509 MMDiT denoise (60 blocks, D=3072, 24 heads, random-init), 1024x1024 single-image "
-                        "edit, 2-step Lightning schedule, " + ("true-CFG 4.0 (cond+uncond)" if args.cfg else "cond-only"),
+    what = ("1024x1024 single-image edit, 2-step Lightning schedule, " if getattr(args, "workload", "1024x1ref") == "1024x1ref"
+            else "512x512 frame with two reference images (one frame of BASELINE configs[4]), 4-step schedule, ")
+    return {"workload": "Qwen-Image-Edit-2509 MMDiT denoise (60 blocks, D=3072, 24 heads, random-init), " + what +
+                        ("true-CFG 4.0 (cond+uncond)" if args.cfg else "cond-only"),
             "img_tokens": N_IMG_TOK, "txt_tokens": T_TXT, "forwards_per_image": STEPS_PER_IMAGE * (2 if args.cfg else 1),
             "layers": args.layers, "precision": args.precision, "caches": bool(getattr(args, "cache", False)),
             "parallelism": (f"dp{n}: one independent frame stream per GPU, weights replicated, no data-path collective"
@@ -365,7 +367,15 @@ def main():
     ap.add_argument("--fused", action="store_true", help="ulysses modes: exchange q|k|v and the attention output through "
                     "epilogue stores into peer memory (NVLink) instead of NCCL all-to-alls")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="1024x1ref", choices=["1024x1ref", "512x2ref"],
+                    help="1024x1ref = the headline (BASELINE configs[1]); 512x2ref = one frame of configs[4]: 512x512, two "
+                         "reference images (3072 image tokens), 448 text tokens, 4 steps (use with --cfg)")
     args = ap.parse_args()
+    if args.workload == "512x2ref":
+        global METRIC, IMG_SHAPES, N_NOISE, N_IMG_TOK, T_TXT, STEPS_PER_IMAGE
+        METRIC = "edited_512x512_two_image_frames_per_s_4step"
+        IMG_SHAPES = [[(1, 32, 32), (1, 32, 32), (1, 32, 32)]]
+        N_NOISE, N_IMG_TOK, T_TXT, STEPS_PER_IMAGE = 1024, 3072, 448, 4
     if args.impl == "reference":
         run_reference(args)
     else:
