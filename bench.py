@@ -199,6 +199,8 @@ def run_ours(args):
         model.set_precision(args.precision)
     if args.attn_variant:
         model.set_option(1, args.attn_variant)
+    if os.environ.get("QIE_L2_HINTS"):      # A/B switch for the GEMM TMA L2 eviction hints (qie_tune key 2)
+        qie_b200.lib().qie_tune(2, int(os.environ["QIE_L2_HINTS"]))
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     lat = torch.randn(1, N_NOISE, 64, generator=g, device=dev).bfloat16()
     img_lat = torch.randn(1, N_IMG_TOK - N_NOISE, 64, generator=g, device=dev).bfloat16()

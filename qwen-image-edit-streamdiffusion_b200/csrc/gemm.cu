@@ -47,6 +47,7 @@ struct GemmDev {
     const float* a_scale;
     const float* w_scale[2];
     int model_dim;           // D (QKV epilogue: column block -> q/k/v)
+    int l2_hints;            // bit 0: weights evict-last, bit 1: activations evict-first (CTA-pair kernels)
     void* const* peer_out;   // QKV epilogue, sequence parallel: device table of the ranks' gathered q|k|v buffers (or NULL)
     int sp_rank, sp_hl, sp_rows;   // my rank, heads per rank, rows of one rank's shard in the gathered layout
 };
@@ -158,6 +159,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // ================= TMA producer (every CTA loads its own A rows and its share of W) =================
             int stage = 0;
             uint32_t phase = 0;
+            // L2 residency: the weight matrix is re-read by every m-unit (33 times at config 2) and fits the 126 MB L2, the
+            // activation panel of a band is needed by the ~n_blocks tiles that run together: weights evict last, activations
+            // first, so the weights are fetched from HBM once per launch instead of once per band (p.l2_hints, qie_tune key 2)
+            const uint64_t pol_w = l2_policy_evict_last(), pol_a = l2_policy_evict_first();
+            const int hints = p.l2_hints;
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 int mu, nb;
                 tile_to_mn(tile, m_units, p.n_blocks, mu, nb);
@@ -176,8 +182,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     if constexpr (CG == 2) {
                         if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
                         const uint32_t bar = leader_smem_u32(&full_bar[stage]);
-                        tma_load_2d_cg2(sa, &tmA, kb * BK, a_row, bar);
-                        tma_load_2d_cg2(sb, tmB, kb * BK, b_row, bar);
+                        if (hints & 2) tma_load_2d_cg2_hint(sa, &tmA, kb * BK, a_row, bar, pol_a);
+                        else tma_load_2d_cg2(sa, &tmA, kb * BK, a_row, bar);
+                        if (hints & 1) tma_load_2d_cg2_hint(sb, tmB, kb * BK, b_row, bar, pol_w);
+                        else tma_load_2d_cg2(sb, tmB, kb * BK, b_row, bar);
                     } else {
                         mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
                         tma_load_2d(sa, &tmA, kb * BK, a_row, &full_bar[stage]);
@@ -487,6 +495,8 @@ static int dispatch_epi(int epi, const CUtensorMap& a, const CUtensorMap& b0, co
 
 using namespace qie;
 
+int g_gemm_l2_hints = 0;    // set through qie_tune(2, v)
+
 extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream) {
     QIE_REQUIRE(g && seq && g->a && g->out, QIE_EINVAL, "qie_gemm: null pointer");
     QIE_REQUIRE(g->streams >= 1 && g->streams <= 3, QIE_EINVAL, "qie_gemm: streams mask must be 1..3");
@@ -533,6 +543,7 @@ extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream
         for (int k = 0; k < 2; ++k) p.qk_norm_w[s][k] = g->qk_norm_w[s][k];
     }
     p.model_dim = g->N / 3;
+    p.l2_hints = g_gemm_l2_hints;
     if (g->peer_out) {
         QIE_REQUIRE(g->epilogue == QIE_EPI_QKV_NORM_ROPE && seq->batch == 1 && g->sp_size >= 1 && g->sp_size <= 8 &&
                         g->sp_rank >= 0 && g->sp_rank < g->sp_size && (g->N / 3 / 128) % g->sp_size == 0 &&

@@ -1,6 +1,8 @@
 // Memory-bound glue kernels of the MMDiT step (HBM roofline): fused CFG+Euler, adaLN modulate,
 // batched modulation GEMV, timestep projection, QK RMSNorm+RoPE, text RMSNorm, row packing.
 // All are vectorised (16 B / lane), one warp per row, fp32 statistics.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace qie {
@@ -134,6 +136,135 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ x
                            : pack_e4m3x4(b.x / scale, b.y / scale, b.z / scale, b.w / scale);
         }
         if (lane == 0) out_scale[row] = scale;
+    }
+}
+
+// K-lnmod, streaming form (default): persistent, one CTA per SM, 8 warps.  Every warp owns a two-row landing ring in shared
+// memory that 1-D bulk copies (cp.async.bulk -> UBLKCP, completion on a warp-private mbarrier) keep filled one row ahead, so
+// HBM reads stay in flight while the warp normalises and stores the previous row; rows are handed out by an atomic counter
+// (8448 rows over 1184 warps would otherwise quantise to 8 vs 7 rows per warp).  Same arithmetic as ln_mod_kernel.
+template <int NV>
+__global__ void __launch_bounds__(256, 1) ln_mod_stream_kernel(const float* __restrict__ x, const float* __restrict__ mod,
+                                                               long long mod_bstride, long long mod_sstride, int shift_off,
+                                                               int scale_off, __nv_bfloat16* __restrict__ out,
+                                                               uint8_t* __restrict__ out8, float* __restrict__ out_scale,
+                                                               int qmode, float eps, qie_seq seq, int* __restrict__ counters) {
+    constexpr int D = NV * 128, ROW_BYTES = D * 4;
+    extern __shared__ uint8_t ln_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ln_smem_raw) + 127) & ~uintptr_t(127));
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    float* buf = reinterpret_cast<float*>(smem + (size_t)warp * 2 * ROW_BYTES);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)8 * 2 * ROW_BYTES) + warp * 2;
+    const int rpb = seq.img_pad + seq.txt_pad;
+    const int rows = seq.batch * rpb;
+    if (lane == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    const int total_warps = gridDim.x * 8, gwarp = blockIdx.x * 8 + warp;
+    auto fetch = [&]() -> int {               // rows beyond the static prefix (two per warp) come from the counter
+        int r = 0;
+        if (lane == 0) r = 2 * total_warps + atomicAdd(&counters[0], 1);
+        return __shfl_sync(0xffffffffu, r, 0);
+    };
+    auto is_valid = [&](int row) -> bool {
+        const int r = row % rpb, stream = r >= seq.img_pad ? 1 : 0;
+        return (stream ? r - seq.img_pad : r) < (stream ? seq.txt_rows : seq.img_rows);
+    };
+    auto issue = [&](int st, int row) {       // bulk copy of one fp32 row into my landing buffer `st`
+        if (row < rows && is_valid(row) && lane == 0) {
+            mbar_expect_tx(&bar[st], ROW_BYTES);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(buf + (size_t)st * D)),
+                         "l"(x + (size_t)row * D), "r"(ROW_BYTES), "r"(smem_u32(&bar[st]))
+                         : "memory");
+        }
+    };
+    int cur = gwarp, nxt = total_warps + gwarp;   // no atomics in the start-up phase
+    issue(0, cur);
+    int st = 0;
+    uint32_t ph[2] = {0, 0};
+    while (cur < rows) {
+        issue(st ^ 1, nxt);
+        const int nxt2 = fetch();             // its latency hides under the row below
+        const int row = cur;
+        const int b = row / rpb, r = row % rpb;
+        const int stream = r >= seq.img_pad ? 1 : 0;
+        __nv_bfloat16* orow = out + (size_t)row * D;
+        if (!is_valid(row)) {   // keep pad rows exactly zero so downstream GEMM rows stay finite
+#pragma unroll
+            for (int i = 0; i < NV; ++i) *reinterpret_cast<uint2*>(orow + (i * 32 + lane) * 4) = make_uint2(0u, 0u);
+            if (out8) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) *reinterpret_cast<uint32_t*>(out8 + (size_t)row * D + (i * 32 + lane) * 4) = 0u;
+                if (lane == 0) out_scale[row] = 0.f;
+            }
+        } else {
+            mbar_wait(&bar[st], ph[st]);
+            ph[st] ^= 1;
+            const float4* xr = reinterpret_cast<const float4*>(buf + (size_t)st * D);
+            float4 v[NV];
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                v[i] = xr[i * 32 + lane];
+                s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            }
+            const float mean = warp_sum(s) * (1.0f / D);
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+                q += (a * a + bb * bb) + (c * c + d * d);
+            }
+            const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+            const float* mrow = mod + b * mod_bstride + stream * mod_sstride;
+            const float4* sh = reinterpret_cast<const float4*>(mrow + shift_off);
+            const float4* sc = reinterpret_cast<const float4*>(mrow + scale_off);
+            float amax = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                float4 h = sh[i * 32 + lane], c = sc[i * 32 + lane];
+                v[i].x = (v[i].x - mean) * rstd * (1.f + c.x) + h.x;
+                v[i].y = (v[i].y - mean) * rstd * (1.f + c.y) + h.y;
+                v[i].z = (v[i].z - mean) * rstd * (1.f + c.z) + h.z;
+                v[i].w = (v[i].w - mean) * rstd * (1.f + c.w) + h.w;
+                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
+                *reinterpret_cast<uint2*>(orow + (i * 32 + lane) * 4) =
+                    make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+            }
+            if (out8) {
+                amax = warp_max(amax);
+                amax = __bfloat162float(__float2bfloat16(amax));
+                const float qmax = qmode == 2 ? 127.f : 448.f;
+                const float scale = amax > 0.f ? amax / qmax : 1.f;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    const float4 bq = make_float4(__bfloat162float(__float2bfloat16(v[i].x)), __bfloat162float(__float2bfloat16(v[i].y)),
+                                                  __bfloat162float(__float2bfloat16(v[i].z)), __bfloat162float(__float2bfloat16(v[i].w)));
+                    *reinterpret_cast<uint32_t*>(out8 + (size_t)row * D + (i * 32 + lane) * 4) =
+                        qmode == 2 ? pack_s8x4(bq.x / scale, bq.y / scale, bq.z / scale, bq.w / scale)
+                                   : pack_e4m3x4(bq.x / scale, bq.y / scale, bq.z / scale, bq.w / scale);
+                }
+                if (lane == 0) out_scale[row] = scale;
+            }
+            fence_proxy_async_smem();         // my reads of this landing buffer are ordered before the bulk copy that refills it
+        }
+        __syncwarp();
+        cur = nxt;
+        nxt = nxt2;
+        st ^= 1;
+    }
+    // the last warp to leave re-arms the row counter for the next launch (launches are serialised on one stream)
+    if (lane == 0) {
+        __threadfence();
+        if (atomicAdd(&counters[1], 1) == (int)(gridDim.x * 8) - 1) {
+            counters[0] = 0;
+            counters[1] = 0;
+            __threadfence();
+        }
     }
 }
 
@@ -355,11 +486,15 @@ extern "C" int qie_cfg_euler_step(const void* v_cond, const void* v_uncond, void
 
 namespace qie {
 int g_ln_threads = 128, g_ln_smem = 0;   // 128 threads (4 rows) per block measured best: 4350 GB/s vs 3700 at 256
+int g_ln_variant = 1;                    // 1 = streaming persistent kernel (default), 0 = one warp per row, grid over rows
 }
 // experiment knobs (not part of the reference surface): 0 = adaLN threads per block, 1 = adaLN dynamic smem reservation
+extern int g_gemm_l2_hints;   // gemm.cu
 extern "C" int qie_tune(int key, int value) {
     if (key == 0 && (value == 64 || value == 128 || value == 256 || value == 512)) { qie::g_ln_threads = value; return QIE_OK; }
     if (key == 1 && value >= 0 && value <= 200 * 1024) { qie::g_ln_smem = value; return QIE_OK; }
+    if (key == 2 && value >= 0 && value <= 3) { g_gemm_l2_hints = value; return QIE_OK; }
+    if (key == 3 && (value == 0 || value == 1)) { qie::g_ln_variant = value; return QIE_OK; }
     ::qie::set_error("qie_tune: bad key/value %d/%d", key, value);
     return QIE_EINVAL;
 }
@@ -372,6 +507,44 @@ extern "C" int qie_ln_modulate(const float* x, const float* mod, long long mod_b
     const long long rows = (long long)seq->batch * (seq->img_pad + seq->txt_pad);
     // Several short waves instead of one: a dynamic-smem reservation caps the resident blocks per SM so that the stores of
     // one wave overlap the loads of the next (one warp per row, the whole row in registers).
+    if (g_ln_variant == 1 && D % 128 == 0 && (size_t)D * 4 * 16 + 256 <= 200 * 1024) {
+        // streaming form: persistent CTAs, bulk-copy landing ring per warp, dynamic row hand-out
+        static int* counters = nullptr;
+        if (!counters) {
+            QIE_CUDA_OK(cudaMalloc(&counters, 2 * sizeof(int)));
+            QIE_CUDA_OK(cudaMemset(counters, 0, 2 * sizeof(int)));
+        }
+        const int sblocks = (int)std::min<long long>(sm_count(), (rows + 7) / 8);
+        const size_t ssm = (size_t)D * 4 * 16 + 256;
+        cudaStream_t sst = (cudaStream_t)stream;
+#define QIE_LNS_CASE(NV)                                                                                             \
+    case NV: {                                                                                                       \
+        static bool cfgd = false;                                                                                    \
+        if (!cfgd) {                                                                                                 \
+            QIE_CUDA_OK(cudaFuncSetAttribute(ln_mod_stream_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+            cfgd = true;                                                                                             \
+        }                                                                                                            \
+        ln_mod_stream_kernel<NV><<<sblocks, 256, ssm, sst>>>(x, mod, mod_bstride, mod_sstride, shift_off, scale_off, \
+                                                            (__nv_bfloat16*)out, (uint8_t*)out8, out_scale, qmode, eps, *seq, counters); \
+        break;                                                                                                       \
+    }
+        switch (D / 128) {
+            QIE_LNS_CASE(1)
+            QIE_LNS_CASE(2)
+            QIE_LNS_CASE(3)
+            QIE_LNS_CASE(4)
+            QIE_LNS_CASE(6)
+            QIE_LNS_CASE(8)
+            QIE_LNS_CASE(12)
+            QIE_LNS_CASE(16)
+            QIE_LNS_CASE(24)
+            default:
+                QIE_REQUIRE(false, QIE_ESHAPE, "qie_ln_modulate: unsupported D=%d", D);
+        }
+#undef QIE_LNS_CASE
+        QIE_LAUNCH_OK("ln_mod_stream_kernel");
+        return QIE_OK;
+    }
     const int threads = g_ln_threads, wpb = threads / 32;
     const int blocks = (int)((rows + wpb - 1) / wpb);
     const size_t dsm = (size_t)g_ln_smem;

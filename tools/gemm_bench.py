@@ -15,6 +15,8 @@ def bench(fn, n=10):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 
+import os
+K.L.check(K.L.lib().qie_tune(2, int(os.environ.get("QIE_L2_HINTS", "0"))))
 s = K.seq(1, 8192, 256)
 M = K.rows(s)
 D = 3072
@@ -31,7 +33,7 @@ for name, N, Kd, epi in [("qkv", 3 * D, D, K.L.EPI_QKV_NORM_ROPE), ("qkv_plain",
     rope = torch.randn(M, 64, 2, device=dev)
     nw = [[torch.ones(128, device=dev) for _ in range(2)] for _ in range(2)]
     flops = 2.0 * M * N * Kd
-    for bn, cg in ((256, 1), (128, 2), (256, 2)):
+    for bn, cg in ((256, 2),):
         fn = lambda: K.gemm(s, a, w, b, out, epi, gate=gate, gate_bstride=12 * D, gate_sstride=6 * D, rope=rope, qk_norm_w=nw, block_n=bn, cta_group=cg)
         ms = bench(fn)
         res.append((name, bn, ms, flops / ms / 1e9))

@@ -20,8 +20,12 @@ def run():
     i[0] = (i[0] + 1) % 4
     K.ln_modulate(s, xs[i[0]], mod, 12 * D, 6 * D, 0, D, D)
 byts = K.rows(s) * D * 6
-for thr in (256, 128, 64):
-    for smem in (0, 24, 32, 44, 56, 72, 100):
+K.L.check(K.L.lib().qie_tune(3, 1))
+ms = bench(run)
+print(f"streaming kernel: {ms*1e3:.1f} us {byts/ms/1e6:.0f} GB/s", flush=True)
+K.L.check(K.L.lib().qie_tune(3, 0))
+for thr in (128,):
+    for smem in (0,):
         K.L.check(K.L.lib().qie_tune(0, thr)); K.L.check(K.L.lib().qie_tune(1, smem * 1024))
         ms = bench(run)
         print(f"threads {thr} smem {smem}KB: {ms*1e3:.1f} us {byts/ms/1e6:.0f} GB/s", flush=True)
