@@ -48,6 +48,11 @@ struct GemmDev {
     const float* w_scale[2];
     int model_dim;           // D (QKV epilogue: column block -> q/k/v)
     int l2_hints;            // bit 0: weights evict-last, bit 1: activations evict-first (CTA-pair kernels)
+    // split-K tail: the last `tail_tiles` tiles (the partial wave of the persistent schedule) are cut into `tail_split` K
+    // ranges, one work item each, so the tail wave costs 1/tail_split of a tile; partial accumulators meet in `scratch`
+    int tail_tiles, tail_split, tail_dbg;
+    float* scratch;          // [tail_tiles][tail_split][CG*128 rows][BN] fp32
+    int* tickets;            // [tail_tiles][8 row slices]
     void* const* peer_out;   // QKV epilogue, sequence parallel: device table of the ranks' gathered q|k|v buffers (or NULL)
     int sp_rank, sp_hl, sp_rows;   // my rank, heads per rank, rows of one rank's shard in the gathered layout
 };
@@ -99,6 +104,29 @@ __device__ __forceinline__ void tile_to_mn(int tile, int m_units, int n_blocks, 
     nb = local / gm;
 }
 
+// Work items of the persistent schedule: the first (num_tiles - tail_tiles) items are whole tiles; every remaining tile
+// is `tail_split` items, each covering one K range.
+struct WorkItem {
+    int tile, part, kb0, kb1;
+    bool split;
+};
+__device__ __forceinline__ WorkItem decode_item(int item, int num_tiles, int tail_tiles, int tail_split, int k_blocks) {
+    WorkItem w;
+    const int whole = num_tiles - tail_tiles;
+    if (item < whole) {
+        w.tile = item; w.part = 0; w.kb0 = 0; w.kb1 = k_blocks; w.split = false;
+    } else {
+        const int i = item - whole;
+        w.tile = whole + i / tail_split;
+        w.part = i % tail_split;
+        const int per = (k_blocks + tail_split - 1) / tail_split;
+        w.kb0 = w.part * per;
+        w.kb1 = min(k_blocks, w.kb0 + per);
+        w.split = true;
+    }
+    return w;
+}
+
 template <int BN, int EPI, int QT, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
@@ -128,6 +156,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int num_tiles = m_units * p.n_blocks;                     // tiles of one CTA (CG=1) / one pair (CG=2)
     const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
     const int k_blocks = (p.K + BK - 1) / BK;
+    const int num_items = num_tiles - p.tail_tiles + p.tail_tiles * p.tail_split;
     const int rpb = p.seq.img_pad + p.seq.txt_pad;
 
     if (threadIdx.x == 0) {
@@ -164,9 +193,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // first, so the weights are fetched from HBM once per launch instead of once per band (p.l2_hints, qie_tune key 2)
             const uint64_t pol_w = l2_policy_evict_last(), pol_a = l2_policy_evict_first();
             const int hints = p.l2_hints;
-            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+            for (int item = tile0; item < num_items; item += tile_step) {
+                const WorkItem wi = decode_item(item, num_tiles, p.tail_tiles, p.tail_split, k_blocks);
                 int mu, nb;
-                tile_to_mn(tile, m_units, p.n_blocks, mu, nb);
+                tile_to_mn(wi.tile, m_units, p.n_blocks, mu, nb);
                 const MUnit m = decode_munit<CG>(p, mu);
                 const int seg_pad = m.s ? p.seq.txt_pad : p.seq.img_pad;
                 int ti = m.ti + cta_rank;
@@ -175,7 +205,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                               : m.b * rpb + (m.s ? p.seq.img_pad : 0) + ti * GEMM_BM;
                 const CUtensorMap* tmB = m.s ? &tmB1 : &tmB0;
                 const int b_row = nb * BN + cta_rank * (BN / CG);
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * S::STAGE_BYTES;
                     uint8_t* sb = sa + S::A_BYTES;
@@ -205,11 +235,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+            for (int item = tile0; item < num_items; item += tile_step) {
+                const WorkItem wi = decode_item(item, num_tiles, p.tail_tiles, p.tail_split, k_blocks);
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
@@ -217,7 +248,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     const uint64_t db = umma_desc_kmajor_sw128(sa + S::A_BYTES);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {   // 4 x 32 B along the swizzled 128 B row
-                        const uint32_t accum = (kb | k) ? 1u : 0u;
+                        const uint32_t accum = ((kb - wi.kb0) | k) ? 1u : 0u;
                         umma_ss<QT, CG>(d_tmem, da + 2 * k, db + 2 * k, IDESC, accum);
                     }
                     // frees the smem slot (in both CTAs of a pair) when these MMAs retire
@@ -248,9 +279,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int sub = lane >> 3, c4 = (lane & 7) * 4;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        for (int item = tile0; item < num_items; item += tile_step) {
+            const WorkItem wi = decode_item(item, num_tiles, p.tail_tiles, p.tail_split, k_blocks);
             int mu, nb;
-            tile_to_mn(tile, m_units, p.n_blocks, mu, nb);
+            tile_to_mn(wi.tile, m_units, p.n_blocks, mu, nb);
             const MUnit m = decode_munit<CG>(p, mu);
             const int seg_pad = m.s ? p.seq.txt_pad : p.seq.img_pad;
             const int seg_rows = m.s ? p.seq.txt_rows : p.seq.img_rows;
@@ -292,6 +324,78 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 __syncwarp();
             };
 
+            // ---- split-K tail item: park my raw partial accumulators in scratch; the warp whose slice arrives last sums the
+            // partials of all K ranges in part order (deterministic) and runs the normal epilogue on the sums
+            bool from_scratch = false, released = false;
+            [[maybe_unused]] const float* part0 = nullptr;
+            if constexpr (EPI != QIE_EPI_QKV_NORM_ROPE) {
+                if (wi.split) {
+                    const int tail_idx = wi.tile - (num_tiles - p.tail_tiles);
+                    const size_t part_elems = (size_t)CG * GEMM_BM * BN;
+                    float* mine = p.scratch + ((size_t)tail_idx * p.tail_split + wi.part) * part_elems +
+                                  (size_t)(cta_rank * GEMM_BM + quad * 32) * BN;
+                    if (!dummy && !(p.tail_dbg & 1)) {
+#pragma unroll 1
+                        for (int c = 0; c < BN / 32; ++c) {
+                            stage_chunk(c, 1.f, false);
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) {
+                                const int rr = it * 4 + sub;
+                                *reinterpret_cast<float4*>(mine + (size_t)rr * BN + c * 32 + c4) =
+                                    *reinterpret_cast<const float4*>(stg + rr * S::EPI_ROW_BYTES + c4 * 4);
+                            }
+                            __syncwarp();
+                        }
+                    }
+                    // the accumulator stage is free again as soon as it has been copied out
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (CG == 2) mbar_arrive_cluster(leader_smem_u32(&tempty_bar[acc]));
+                        else mbar_arrive(&tempty_bar[acc]);
+                    }
+                    released = true;
+                    bool last = false;
+                    if (!dummy && !(p.tail_dbg & 2)) {
+                        __threadfence();
+                        __syncwarp();
+                        int t = 0;
+                        int* ticket = p.tickets + tail_idx * 8 + cta_rank * 4 + quad;
+                        if (lane == 0) t = atomicAdd(ticket, 1);
+                        t = __shfl_sync(0xffffffffu, t, 0);
+                        last = t == p.tail_split - 1;
+                        if (last) {
+                            if (lane == 0) *ticket = 0;          // re-armed for the next launch
+                            __threadfence();
+                            from_scratch = true;
+                            part0 = p.scratch + (size_t)tail_idx * p.tail_split * part_elems +
+                                    (size_t)(cta_rank * GEMM_BM + quad * 32) * BN;
+                        }
+                    }
+                    if (!last) {
+                        if (++acc == 2) {
+                            acc = 0;
+                            acc_phase ^= 1;
+                        }
+                        continue;
+                    }
+                }
+            }
+            auto stage_from_scratch = [&](int c) {          // sum of the K-range partials, in part order -> staging tile
+                const size_t part_elems = (size_t)CG * GEMM_BM * BN;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + sub;
+                    float4 a = __ldcg(reinterpret_cast<const float4*>(part0 + (size_t)rr * BN + c * 32 + c4));
+                    for (int pp = 1; pp < p.tail_split; ++pp) {
+                        const float4 b4 = __ldcg(reinterpret_cast<const float4*>(part0 + pp * part_elems + (size_t)rr * BN + c * 32 + c4));
+                        a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+                    }
+                    *reinterpret_cast<float4*>(stg + rr * S::EPI_ROW_BYTES + c4 * 4) = a;
+                }
+                __syncwarp();
+            };
+
             [[maybe_unused]] float rinv_head = 1.f;
             if (!dummy) {
 #pragma unroll 1
@@ -326,7 +430,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         }
                         stage_chunk(c, which != 2 ? rinv_head : 1.f, which != 2);
                     } else {
-                        stage_chunk(c, 1.f, false);
+                        if (from_scratch) stage_from_scratch(c);
+                        else stage_chunk(c, 1.f, false);
                     }
                     const bool normed = EPI == QIE_EPI_QKV_NORM_ROPE && which != 2;
                     // sequence-parallel scatter: this 32-column chunk belongs to one head, i.e. to one destination rank;
@@ -425,7 +530,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // release this accumulator stage back to the MMA warp (of the leader CTA)
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && !released) {
                 if constexpr (CG == 2) mbar_arrive_cluster(leader_smem_u32(&tempty_bar[acc]));
                 else mbar_arrive(&tempty_bar[acc]);
             }
@@ -496,6 +601,9 @@ static int dispatch_epi(int epi, const CUtensorMap& a, const CUtensorMap& b0, co
 using namespace qie;
 
 int g_gemm_l2_hints = 0;    // set through qie_tune(2, v)
+int g_gemm_split_tail = 0;  // qie_tune(4, v).  Off by default: the shorter tail wave gains 5-10 % per GEMM (measured with the
+                            // reduction disabled), but the finishing warp's serial L2 round trips over the partials cost as
+                            // much again (profiles/r01_ncu_summary.md); a bulk-copy landing zone in the idle ring is the fix.
 
 extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream) {
     QIE_REQUIRE(g && seq && g->a && g->out, QIE_EINVAL, "qie_gemm: null pointer");
@@ -585,6 +693,36 @@ extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream
     }
     const int tiles = cg == 2 ? pair_tiles : seq->batch * (t0 + t1) * p.n_blocks;
     cudaStream_t st = (cudaStream_t)stream;
+    // split-K tail (qie_tune key 4; default off, see g_gemm_split_tail): only when the persistent schedule ends in a partial wave that a K split can
+    // shorten, never for the QKV epilogue (row statistics over whole heads) or int8 (int32 partials would not survive fp32)
+    p.tail_tiles = 0;
+    p.tail_split = 1;
+    {
+        const int units = sm_count() / cg;
+        const int tail = tiles % units, kblocks = (g->K + bk - 1) / bk;
+        if (g_gemm_split_tail && cg == 2 && bn == 256 && tiles > units && tail > 0 && g->epilogue != QIE_EPI_QKV_NORM_ROPE &&
+            g->fp8 != 2) {
+            int split = units / tail;
+            if (split > 8) split = 8;
+            while (split > 1 && kblocks / split < 6) --split;
+            if (split > 1) {
+                static float* scratch = nullptr;
+                static int* tickets = nullptr;
+                if (!scratch) {
+                    QIE_CUDA_OK(cudaMalloc(&scratch, (size_t)96 * 2 * GEMM_BM * 256 * sizeof(float)));
+                    QIE_CUDA_OK(cudaMalloc(&tickets, 96 * 8 * sizeof(int)));
+                    QIE_CUDA_OK(cudaMemset(tickets, 0, 96 * 8 * sizeof(int)));
+                }
+                if (tail * split <= 96) {
+                    p.tail_tiles = tail;
+                    p.tail_split = split;
+                    p.tail_dbg = g_gemm_split_tail >> 1;
+                    p.scratch = scratch;
+                    p.tickets = tickets;
+                }
+            }
+        }
+    }
 #define QIE_GEMM_DISPATCH(F8, CGV)                                                                         \
     switch (bn) {                                                                                          \
         case 64:                                                                                           \

@@ -489,12 +489,13 @@ int g_ln_threads = 128, g_ln_smem = 0;   // 128 threads (4 rows) per block measu
 int g_ln_variant = 1;                    // 1 = streaming persistent kernel (default), 0 = one warp per row, grid over rows
 }
 // experiment knobs (not part of the reference surface): 0 = adaLN threads per block, 1 = adaLN dynamic smem reservation
-extern int g_gemm_l2_hints;   // gemm.cu
+extern int g_gemm_l2_hints, g_gemm_split_tail;   // gemm.cu
 extern "C" int qie_tune(int key, int value) {
     if (key == 0 && (value == 64 || value == 128 || value == 256 || value == 512)) { qie::g_ln_threads = value; return QIE_OK; }
     if (key == 1 && value >= 0 && value <= 200 * 1024) { qie::g_ln_smem = value; return QIE_OK; }
     if (key == 2 && value >= 0 && value <= 3) { g_gemm_l2_hints = value; return QIE_OK; }
     if (key == 3 && (value == 0 || value == 1)) { qie::g_ln_variant = value; return QIE_OK; }
+    if (key == 4 && value >= 0 && value <= 7) { g_gemm_split_tail = value; return QIE_OK; }   // bit 0 on/off; bits 1-2: timing experiments
     ::qie::set_error("qie_tune: bad key/value %d/%d", key, value);
     return QIE_EINVAL;
 }

@@ -192,6 +192,50 @@ def test_gemm_gate_residual(cta_group):
     assert torch.equal(resid.reshape(2, -1, N)[:, s.img_pad + s.txt_rows:], resid0.reshape(2, -1, N)[:, s.img_pad + s.txt_rows:])
 
 
+@pytest.mark.parametrize("epi", ["gate_resid", "gelu", "bf16"])
+@pytest.mark.parametrize("img,txt,N,Kd", [(8192, 256, 3072, 1024), (4096 + 200, 219, 3072, 768), (8192, 256, 1792, 3072)])
+def test_gemm_split_k_tail(epi, img, txt, N, Kd):
+    """Shapes whose persistent schedule ends in a partial wave: the tail tiles are cut into K ranges whose fp32 partials meet
+    in scratch and are summed in part order (csrc/gemm.cu, WorkItem).  Checked against the fp32 reference, against the
+    un-split schedule of the same kernel, and for run-to-run determinism (no atomics on the data path)."""
+    s = K.seq(1, img, txt)
+    a, w, b = _gemm_case(s, N, Kd, seed=70)
+    rows = K.rows(s)
+    gate = randn(1, 2, N, seed=75)
+    res0 = randn(rows, N, seed=76)
+
+    def run(split):
+        K.L.check(K.L.lib().qie_tune(4, split))
+        try:
+            if epi == "gate_resid":
+                out = res0.clone()
+                K.gemm(s, a, w, b, out, K.L.EPI_GATE_RESID_F32, gate=gate, gate_bstride=2 * N, gate_sstride=N, cta_group=2)
+            elif epi == "gelu":
+                out = torch.empty(rows, N, dtype=torch.bfloat16, device=DEV)
+                K.gemm(s, a, w, b, out, K.L.EPI_GELU_BF16, cta_group=2)
+            else:
+                out = torch.empty(rows, N, dtype=torch.bfloat16, device=DEV)
+                K.gemm(s, a, w, b, out, K.L.EPI_BF16, cta_group=2)
+            return out
+        finally:
+            K.L.check(K.L.lib().qie_tune(4, 0))
+
+    split, again, whole = run(1), run(1), run(0)
+    assert torch.equal(split, again)                                   # deterministic
+    ri, rt = _gemm_ref(s, a, w, b)
+    gi, gt = K.from_joint(s, split.float())
+    wi_, wt_ = K.from_joint(s, whole.float())
+    if epi == "gate_resid":
+        r0i, r0t = K.from_joint(s, res0)
+        ri, rt = r0i + gate[:, 0, None, :] * ri, r0t + gate[:, 1, None, :] * rt
+    elif epi == "gelu":
+        ri, rt = F.gelu(ri, approximate="tanh"), F.gelu(rt, approximate="tanh")
+    tol = 1e-5 if epi == "gate_resid" else 2 ** -7
+    assert K.rel_err(gi, ri) <= max(tol, 2e-6 * Kd ** 0.5) and K.rel_err(gt, rt) <= max(tol, 2e-6 * Kd ** 0.5)
+    # same numbers as the un-split schedule up to the fp32 association of the K ranges
+    assert K.rel_err(gi, wi_) <= (5e-6 if epi == "gate_resid" else 2 ** -7) and K.rel_err(gt, wt_) <= (5e-6 if epi == "gate_resid" else 2 ** -7)
+
+
 def test_gemm_compact_single_stream():
     s = K.seq(2, 200, 19)
     N, Kd = 256, 64
