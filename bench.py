@@ -199,8 +199,9 @@ def run_ours(args):
         model.set_precision(args.precision)
     if args.attn_variant:
         model.set_option(1, args.attn_variant)
-    if os.environ.get("QIE_L2_HINTS"):      # A/B switch for the GEMM TMA L2 eviction hints (qie_tune key 2)
-        qie_b200.lib().qie_tune(2, int(os.environ["QIE_L2_HINTS"]))
+    for env, key in (("QIE_L2_HINTS", 2), ("QIE_LN_VARIANT", 3), ("QIE_SPLIT_TAIL", 4)):   # A/B switches (qie_tune keys)
+        if os.environ.get(env):
+            qie_b200.lib().qie_tune(key, int(os.environ[env]))
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     lat = torch.randn(1, N_NOISE, 64, generator=g, device=dev).bfloat16()
     img_lat = torch.randn(1, N_IMG_TOK - N_NOISE, 64, generator=g, device=dev).bfloat16()

@@ -383,16 +383,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             auto stage_from_scratch = [&](int c) {          // sum of the K-range partials, in part order -> staging tile
                 const size_t part_elems = (size_t)CG * GEMM_BM * BN;
+                // all loads of a range are issued before the first add, and range 1 before range 0 is consumed: one L2 round trip
+                // per chunk for the common two-range split instead of one per (row group, range)
+                float4 a[8], b4[8];
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int rr = it * 4 + sub;
-                    float4 a = __ldcg(reinterpret_cast<const float4*>(part0 + (size_t)rr * BN + c * 32 + c4));
-                    for (int pp = 1; pp < p.tail_split; ++pp) {
-                        const float4 b4 = __ldcg(reinterpret_cast<const float4*>(part0 + pp * part_elems + (size_t)rr * BN + c * 32 + c4));
-                        a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+                for (int it = 0; it < 8; ++it)
+                    a[it] = __ldcg(reinterpret_cast<const float4*>(part0 + (size_t)(it * 4 + sub) * BN + c * 32 + c4));
+                for (int pp = 1; pp < p.tail_split; ++pp) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it)
+                        b4[it] = __ldcg(reinterpret_cast<const float4*>(part0 + pp * part_elems + (size_t)(it * 4 + sub) * BN + c * 32 + c4));
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        a[it].x += b4[it].x; a[it].y += b4[it].y; a[it].z += b4[it].z; a[it].w += b4[it].w;
                     }
-                    *reinterpret_cast<float4*>(stg + rr * S::EPI_ROW_BYTES + c4 * 4) = a;
                 }
+#pragma unroll
+                for (int it = 0; it < 8; ++it)
+                    *reinterpret_cast<float4*>(stg + (it * 4 + sub) * S::EPI_ROW_BYTES + c4 * 4) = a[it];
                 __syncwarp();
             };
 
@@ -601,9 +609,7 @@ static int dispatch_epi(int epi, const CUtensorMap& a, const CUtensorMap& b0, co
 using namespace qie;
 
 int g_gemm_l2_hints = 0;    // set through qie_tune(2, v)
-int g_gemm_split_tail = 0;  // qie_tune(4, v).  Off by default: the shorter tail wave gains 5-10 % per GEMM (measured with the
-                            // reduction disabled), but the finishing warp's serial L2 round trips over the partials cost as
-                            // much again (profiles/r01_ncu_summary.md); a bulk-copy landing zone in the idle ring is the fix.
+int g_gemm_split_tail = 1;  // qie_tune(4, v): 0 off, 1 long-K tiles only / two ranges (default), 9 wherever a split fits
 
 extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream) {
     QIE_REQUIRE(g && seq && g->a && g->out, QIE_EINVAL, "qie_gemm: null pointer");
@@ -693,7 +699,7 @@ extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream
     }
     const int tiles = cg == 2 ? pair_tiles : seq->batch * (t0 + t1) * p.n_blocks;
     cudaStream_t st = (cudaStream_t)stream;
-    // split-K tail (qie_tune key 4; default off, see g_gemm_split_tail): only when the persistent schedule ends in a partial wave that a K split can
+    // split-K tail (qie_tune key 4): only when the persistent schedule ends in a partial wave that a K split can
     // shorten, never for the QKV epilogue (row statistics over whole heads) or int8 (int32 partials would not survive fp32)
     p.tail_tiles = 0;
     p.tail_split = 1;
@@ -702,8 +708,14 @@ extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream
         const int tail = tiles % units, kblocks = (g->K + bk - 1) / bk;
         if (g_gemm_split_tail && cg == 2 && bn == 256 && tiles > units && tail > 0 && g->epilogue != QIE_EPI_QKV_NORM_ROPE &&
             g->fp8 != 2) {
+            // the gain is (1 - 1/split) of a tile, the reduction costs a fixed few microseconds: worth it for long-K tiles only
+            // (mode 1), or everywhere (mode 8 | 1, experiments / tests)
             int split = units / tail;
             if (split > 8) split = 8;
+            if (!(g_gemm_split_tail & 8)) {
+                if (split > 2) split = 2;
+                if (kblocks < 96) split = 1;
+            }
             while (split > 1 && kblocks / split < 6) --split;
             if (split > 1) {
                 static float* scratch = nullptr;
@@ -716,7 +728,7 @@ extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream
                 if (tail * split <= 96) {
                     p.tail_tiles = tail;
                     p.tail_split = split;
-                    p.tail_dbg = g_gemm_split_tail >> 1;
+                    p.tail_dbg = (g_gemm_split_tail >> 1) & 3;
                     p.scratch = scratch;
                     p.tickets = tickets;
                 }

@@ -495,7 +495,7 @@ extern "C" int qie_tune(int key, int value) {
     if (key == 1 && value >= 0 && value <= 200 * 1024) { qie::g_ln_smem = value; return QIE_OK; }
     if (key == 2 && value >= 0 && value <= 3) { g_gemm_l2_hints = value; return QIE_OK; }
     if (key == 3 && (value == 0 || value == 1)) { qie::g_ln_variant = value; return QIE_OK; }
-    if (key == 4 && value >= 0 && value <= 7) { g_gemm_split_tail = value; return QIE_OK; }   // bit 0 on/off; bits 1-2: timing experiments
+    if (key == 4 && value >= 0 && value <= 15) { g_gemm_split_tail = value; return QIE_OK; }   // bit 0 on/off; bits 1-2: timing experiments
     ::qie::set_error("qie_tune: bad key/value %d/%d", key, value);
     return QIE_EINVAL;
 }
