@@ -73,6 +73,8 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 }
 
 int unpack_rows(const void* x, void* out, int batch, int n, int n_pad, int C, cudaStream_t st);
+int ln_counters(int** out);
+int gemm_split_buffers(float** scratch_out, int** tickets_out);
 int attn_fwd_peers(const void* qkv_gathered, void* const* peer_out_dev, int n_tiles, const int* tile_valid_dev, int heads_local,
                    int sp_rows, int out_ld, int head_off, void* stream);
 
@@ -217,6 +219,12 @@ extern "C" int qie_create(const qie_model_cfg* cfg, int device, qie_handle** out
     QIE_REQUIRE(prop.major == 10, QIE_EARCH, "qie_create: device %d is sm_%d%d, this library is sm_100a only", device,
                 prop.major, prop.minor);
     QIE_CUDA_OK(cudaSetDevice(device));
+    {   // process-wide kernel scratch: allocate now, so that qie_forward stays allocation-free (CUDA-graph capturable)
+        int* c = nullptr; float* sc = nullptr; int* tk = nullptr;
+        int rc0 = ln_counters(&c);
+        if (!rc0) rc0 = gemm_split_buffers(&sc, &tk);
+        if (rc0) return rc0;
+    }
     qie_handle* h = new qie_handle();
     h->cfg = *cfg;
     h->device = device;

@@ -606,6 +606,23 @@ static int dispatch_epi(int epi, const CUtensorMap& a, const CUtensorMap& b0, co
 
 }  // namespace qie
 
+namespace qie {
+// scratch for the split-K tail partials (96 tiles x 256 x 256 fp32 = 24 MB) and its tickets; allocated at qie_create so that
+// qie_forward never allocates (one set per process: GEMMs of one device are issued on one stream at a time)
+int gemm_split_buffers(float** scratch_out, int** tickets_out) {
+    static float* scratch = nullptr;
+    static int* tickets = nullptr;
+    if (!scratch) {
+        QIE_CUDA_OK(cudaMalloc(&scratch, (size_t)96 * 2 * GEMM_BM * 256 * sizeof(float)));
+        QIE_CUDA_OK(cudaMalloc(&tickets, 96 * 8 * sizeof(int)));
+        QIE_CUDA_OK(cudaMemset(tickets, 0, 96 * 8 * sizeof(int)));
+    }
+    *scratch_out = scratch;
+    *tickets_out = tickets;
+    return QIE_OK;
+}
+}  // namespace qie
+
 using namespace qie;
 
 int g_gemm_l2_hints = 0;    // set through qie_tune(2, v)
@@ -718,13 +735,10 @@ extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream
             }
             while (split > 1 && kblocks / split < 6) --split;
             if (split > 1) {
-                static float* scratch = nullptr;
-                static int* tickets = nullptr;
-                if (!scratch) {
-                    QIE_CUDA_OK(cudaMalloc(&scratch, (size_t)96 * 2 * GEMM_BM * 256 * sizeof(float)));
-                    QIE_CUDA_OK(cudaMalloc(&tickets, 96 * 8 * sizeof(int)));
-                    QIE_CUDA_OK(cudaMemset(tickets, 0, 96 * 8 * sizeof(int)));
-                }
+                float* scratch = nullptr;
+                int* tickets = nullptr;
+                int rc0 = qie::gemm_split_buffers(&scratch, &tickets);
+                if (rc0) return rc0;
                 if (tail * split <= 96) {
                     p.tail_tiles = tail;
                     p.tail_split = split;

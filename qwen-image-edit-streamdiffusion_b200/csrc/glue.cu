@@ -490,6 +490,18 @@ int g_ln_variant = 1;                    // 1 = streaming persistent kernel (def
 }
 // experiment knobs (not part of the reference surface): 0 = adaLN threads per block, 1 = adaLN dynamic smem reservation
 extern int g_gemm_l2_hints, g_gemm_split_tail;   // gemm.cu
+namespace qie {
+// row counter + exit counter of ln_mod_stream_kernel; allocated at qie_create so that qie_forward never allocates
+int ln_counters(int** out) {
+    static int* counters = nullptr;
+    if (!counters) {
+        QIE_CUDA_OK(cudaMalloc(&counters, 2 * sizeof(int)));
+        QIE_CUDA_OK(cudaMemset(counters, 0, 2 * sizeof(int)));
+    }
+    *out = counters;
+    return QIE_OK;
+}
+}  // namespace qie
 extern "C" int qie_tune(int key, int value) {
     if (key == 0 && (value == 64 || value == 128 || value == 256 || value == 512)) { qie::g_ln_threads = value; return QIE_OK; }
     if (key == 1 && value >= 0 && value <= 200 * 1024) { qie::g_ln_smem = value; return QIE_OK; }
@@ -510,11 +522,9 @@ extern "C" int qie_ln_modulate(const float* x, const float* mod, long long mod_b
     // one wave overlap the loads of the next (one warp per row, the whole row in registers).
     if (g_ln_variant == 1 && D % 128 == 0 && (size_t)D * 4 * 16 + 256 <= 200 * 1024) {
         // streaming form: persistent CTAs, bulk-copy landing ring per warp, dynamic row hand-out
-        static int* counters = nullptr;
-        if (!counters) {
-            QIE_CUDA_OK(cudaMalloc(&counters, 2 * sizeof(int)));
-            QIE_CUDA_OK(cudaMemset(counters, 0, 2 * sizeof(int)));
-        }
+        int* counters = nullptr;
+        int rc0 = qie::ln_counters(&counters);
+        if (rc0) return rc0;
         const int sblocks = (int)std::min<long long>(sm_count(), (rows + 7) / 8);
         const size_t ssm = (size_t)D * 4 * 16 + 256;
         cudaStream_t sst = (cudaStream_t)stream;

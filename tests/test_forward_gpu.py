@@ -334,3 +334,35 @@ def test_streaming_frames_match_oracle():
         cos = torch.nn.functional.cosine_similarity(got.float().cpu().flatten(), want.flatten(), dim=0).item()
         assert cos >= 0.999, (f, cos)
         prev = want
+
+
+def test_forward_is_cuda_graph_capturable():
+    """include/qie.h: qie_forward enqueues on the caller's stream without allocating or synchronising in the steady state, so
+    the whole 2-block step can be captured once and replayed (what a serving loop does to drop the launch overhead)."""
+    ref_cfg = R.RefConfig(num_layers=2, attention_head_dim=128, num_attention_heads=2, joint_attention_dim=128)
+    cfg = qie_b200.QwenImageDiTConfig(num_layers=2, num_attention_heads=2, joint_attention_dim=128)
+    oracle = R.init_weights_(R.QwenImageTransformer2DModelRef(ref_cfg), seed=0)
+    model = qie_b200.B200QwenImageTransformer2DModel.from_state_dict(oracle.state_dict(), cfg, DEV)
+    shapes = [[(1, 16, 16), (1, 16, 16)]]
+    g = torch.Generator().manual_seed(44)
+    x = torch.randn(1, 512, 64, generator=g).bfloat16().to(DEV)
+    cond = (torch.randn(1, 19, 128, generator=g) * 3).bfloat16().to(DEV)
+    ts = torch.tensor([0.5], device=DEV)
+    eager = model(x, cond, None, ts, shapes, [19], return_dict=False)[0].clone()      # also builds the RoPE table (one-off sync)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        model(x, cond, None, ts, shapes, [19], return_dict=False)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = model(x, cond, None, ts, shapes, [19], return_dict=False)[0]
+    x2 = torch.randn(1, 512, 64, generator=g).bfloat16().to(DEV)
+    want2 = model(x2, cond, None, ts, shapes, [19], return_dict=False)[0].clone()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager)
+    x.copy_(x2)                       # new input in the captured buffer, same graph
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want2)
