@@ -1598,6 +1598,377 @@ static int launch_attn_pair3(const CUtensorMap& tm128, const AttnDev& p, dim3 gr
 }
 
 // =====================================================================================================================
+// Persistent form of pair3 ("pair3p", variant 0x1024): one CTA pair per TPC loops over work units (256 query rows of one
+// (batch, head)), so barrier set-up, TMEM allocation and the cluster syncs are paid once per launch, and the unit boundary is
+// pipelined: the producer loads the next unit's Q as soon as the last S MMA of the current unit has retired (q_empty), the K/V
+// rings simply continue, the issuer runs S(0) of the next unit under the last softmax / PV / epilogue of the current one
+// and only the first PV of a unit waits for the epilogue to have read O (o_free).  All tile barriers keep toggling across
+// units (parity = running tile count).  Same arithmetic as attn_pair3_kernel<POLY, 0, 0>.
+// =====================================================================================================================
+constexpr int AT7_SMEM = AT5_SMEM + 64;
+
+template <int POLY>
+__global__ void __launch_bounds__(AT5_THREADS, 1)
+attn_pair3p_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + ATT_TILE_BYTES;
+    uint8_t* sV = sK + AT5_KSTAGES * AT5_STAGE_BYTES;
+    float* xm = reinterpret_cast<float*>(sV + AT5_VSTAGES * AT5_STAGE_BYTES);   // [2 parities][2 WGs][128 rows] tile max
+    float* xl = xm + 512;                                                        // [2 parities][2 WGs][128 rows] partial row sums
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xl) + 2048);
+    uint64_t* q_full = bars;                       // leader
+    uint64_t* q_empty = bars + 1;                  // both: the S MMAs of a unit have retired, sQ may be overwritten
+    uint64_t* k_full = bars + 2;
+    uint64_t* k_empty = k_full + AT5_KSTAGES;
+    uint64_t* v_full = k_empty + AT5_KSTAGES;
+    uint64_t* v_empty = v_full + AT5_VSTAGES;
+    uint64_t* s_full = v_empty + AT5_VSTAGES;
+    uint64_t* s_free = s_full + 1;                 // leader, 16 warp arrivals
+    uint64_t* p_full = s_free + 1;                 // leader, 16 warp arrivals
+    uint64_t* pv_done = p_full + 1;
+    uint64_t* o_free = pv_done + 1;                // leader, 16 warp arrivals: the epilogue has read O
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
+
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int cta_rank = (int)cluster_ctarank();
+    const int rpb = p.seq.img_pad + p.seq.txt_pad;
+    const int n128 = rpb / ATT_TILE;
+    const int n_kv = (n128 + 1) / 2;
+    const int nq = (rpb + 255) / 256;
+    const int D = p.H * ATT_TILE;
+    const int n_units = nq * p.H * p.seq.batch;
+    const int unit0 = blockIdx.x >> 1, unit_step = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm128);
+        mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
+        for (int i = 0; i < AT5_KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+        for (int i = 0; i < AT5_VSTAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+        mbar_init(s_full, 1);
+        mbar_init(s_free, 16);
+        mbar_init(p_full, 16);
+        mbar_init(pv_done, 1);
+        mbar_init(o_free, 16);
+        fence_barrier_init();
+    }
+    if (warp == 9) tmem_alloc_cg2<512>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t COL_S = 128, COL_P = 384;
+
+    if (warp >= 8) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+      if (warp == 8) {
+        if (lane == 0) {
+            // ================= TMA producer =================
+            int ks = 0, vs = 0;
+            uint32_t kph = 0, vph = 0;
+            int nu = 0;
+            for (int u = unit0; u < n_units; u += unit_step, ++nu) {
+                const int qp = u % nq, head = (u / nq) % p.H, b = u / (nq * p.H);
+                const int row_base = b * rpb;
+                const int colQ = head * ATT_TILE, colK = D + head * ATT_TILE, colV = 2 * D + head * ATT_TILE;
+                int qr = qp * 256 + cta_rank * ATT_TILE;
+                if (qr >= rpb) qr = 0;
+                if (nu > 0) mbar_wait(q_empty, (nu - 1) & 1);            // the previous unit's S MMAs are done with sQ
+                if (cta_rank == 0) mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+                for (int hf = 0; hf < 2; ++hf)
+                    tma_load_2d_cg2(sQ + hf * ATT_HALF_BYTES, &tm128, colQ + hf * 64, row_base + qr, leader_smem_u32(q_full));
+                auto load_k = [&](int j) {
+                    mbar_wait(&k_empty[ks], kph ^ 1);
+                    if (cta_rank == 0) mbar_expect_tx(&k_full[ks], 2 * AT5_STAGE_BYTES);
+                    const uint32_t bar = leader_smem_u32(&k_full[ks]);
+                    for (int hf = 0; hf < 2; ++hf)
+                        tma_load_2d_cg2(sK + ks * AT5_STAGE_BYTES + hf * ATT_HALF_BYTES, &tm128, colK + hf * 64,
+                                        row_base + j * 256 + cta_rank * ATT_TILE, bar);
+                    if (++ks == AT5_KSTAGES) { ks = 0; kph ^= 1; }
+                };
+                auto load_v = [&](int j) {
+                    mbar_wait(&v_empty[vs], vph ^ 1);
+                    if (cta_rank == 0) mbar_expect_tx(&v_full[vs], 2 * AT5_STAGE_BYTES);
+                    const uint32_t bar = leader_smem_u32(&v_full[vs]);
+                    for (int hf = 0; hf < 2; ++hf)
+                        tma_load_2d_cg2(sV + vs * AT5_STAGE_BYTES + hf * ATT_HALF_BYTES, &tm128, colV + cta_rank * 64,
+                                        row_base + j * 256 + hf * ATT_TILE, bar);
+                    if (++vs == AT5_VSTAGES) { vs = 0; vph ^= 1; }
+                };
+                load_k(0);
+                for (int j = 0; j < n_kv; ++j) {
+                    if (j + 1 < n_kv) load_k(j + 1);
+                    load_v(j);
+                }
+            }
+        }
+      } else if (warp == 9) {
+        if (lane == 0 && cta_rank == 0) {
+            // ================= MMA issuer (leader) =================
+            constexpr uint32_t IDESC_S = umma_idesc_bf16(256, 256, false);
+            constexpr uint32_t IDESC_O = umma_idesc_bf16(256, 128, true);
+            int ks = 0, vs = 0;
+            uint32_t kph = 0, vph = 0;
+            const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(sQ));
+            auto issue_S = [&](bool last_of_unit) {
+                mbar_wait(&k_full[ks], kph);
+                tc_fence_after();
+                const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(sK + ks * AT5_STAGE_BYTES));
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const uint64_t off = (uint64_t)(((s >> 2) * ATT_HALF_BYTES + (s & 3) * 32) >> 4);
+                    umma_ss_f16_cg2(tmem_base + COL_S, dq + off, dk + off, IDESC_S, s ? 1u : 0u);
+                }
+                umma_commit_cg2(s_full, 3);
+                umma_commit_cg2(&k_empty[ks], 3);
+                if (last_of_unit) umma_commit_cg2(q_empty, 3);
+                if (++ks == AT5_KSTAGES) { ks = 0; kph ^= 1; }
+            };
+            int t = 0, nu = 0;                      // running tile / unit counts: barrier parities continue across units
+            for (int u = unit0; u < n_units; u += unit_step, ++nu) {
+                mbar_wait(q_full, nu & 1);
+                tc_fence_after();
+                if (t > 0) {                        // S(0) of this unit reuses the S buffer: the last tile of the previous unit is in registers
+                    mbar_wait(s_free, (t - 1) & 1);
+                    tc_fence_after();
+                }
+                issue_S(n_kv == 1);
+                for (int j = 0; j < n_kv; ++j, ++t) {
+                    if (j + 1 < n_kv) {
+                        mbar_wait(s_free, t & 1);
+                        tc_fence_after();
+                        issue_S(j + 2 == n_kv);
+                    }
+                    mbar_wait(&v_full[vs], vph);
+                    mbar_wait(p_full, t & 1);
+                    if (j == 0 && nu > 0) mbar_wait(o_free, (nu - 1) & 1);   // the previous unit's epilogue has read O
+                    tc_fence_after();
+                    const uint64_t dv = umma_desc_mnmajor_sw128(smem_u32(sV + vs * AT5_STAGE_BYTES), ATT_HALF_BYTES, 1024);
+#pragma unroll
+                    for (int s = 0; s < 16; ++s)
+                        umma_ts_f16_cg2(tmem_base, tmem_base + COL_P + s * 8, dv + (uint64_t)(s * 128), IDESC_O,
+                                        (j == 0 && s == 0) ? 0u : 1u);
+                    umma_commit_cg2(pv_done, 3);
+                    umma_commit_cg2(&v_empty[vs], 3);
+                    if (++vs == AT5_VSTAGES) { vs = 0; vph ^= 1; }
+                }
+            }
+        }
+      }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        // ================= softmax (warps 0-7) =================
+        const int wg = warp >> 2;
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        const uint32_t tS = tmem_base + lane_addr + COL_S + wg * 128;
+        const uint32_t tP = tmem_base + lane_addr + COL_P + wg * 64;
+        const uint32_t tO = tmem_base + lane_addr + wg * 64;
+        const float c = p.scale_log2;
+        const uint64_t c2 = pk2(c, c);
+        auto valid_rows = [&](int t128) -> int {
+            return t128 < n128 ? (p.tile_valid ? __ldg(p.tile_valid + t128) : kv_valid_rows(p.seq, t128)) : 0;
+        };
+        int t = 0, nu = 0;
+        for (int u = unit0; u < n_units; u += unit_step, ++nu) {
+            const int qp = u % nq, head = (u / nq) % p.H, b = u / (nq * p.H);
+            const int row_base = b * rpb;
+            const int q_row0 = qp * 256 + cta_rank * ATT_TILE;
+            const bool q_valid = q_row0 < rpb;
+            float m_ref = -INFINITY;
+            uint64_t l2 = pk2(0.f, 0.f);
+            int nv_next = valid_rows(wg);
+            for (int j = 0; j < n_kv; ++j, ++t) {
+                const int nv = nv_next;
+                mbar_wait(s_full, t & 1);
+                tc_fence_after();
+                uint32_t s[128];
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t(&dst)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[ch * 32]);
+                    tmem_ld32(tS + ch * 32, dst);
+                }
+                nv_next = valid_rows(2 * (j + 1) + wg);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(leader_smem_u32(s_free));
+                float m0 = -INFINITY, m1 = -INFINITY;
+                if (nv == ATT_TILE) {
+                    float m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 128; i += 8) {
+                        m0 = max3(m0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+                        m1 = max3(m1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+                        m2 = max3(m2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+                        m3 = max3(m3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+                    }
+                    m0 = fmaxf(m0, m2);
+                    m1 = fmaxf(m1, m3);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 128; ++i)
+                        if (i < nv) m0 = fmaxf(m0, __uint_as_float(s[i]));
+                }
+                float* xmj = xm + (t & 1) * 256;
+                xmj[wg * 128 + r] = fmaxf(m0, m1);
+                named_bar_sync(1 + quad, 64);
+                const float mx = fmaxf(fmaxf(m0, m1), xmj[(wg ^ 1) * 128 + r]) * c;
+                float alpha = 1.f;
+                const bool grow = mx > m_ref + 8.0f;
+                if (grow) {
+                    alpha = fast_exp2(m_ref - mx);
+                    m_ref = mx;
+                    l2 = fma2(l2, pk2(alpha, alpha), pk2(0.f, 0.f));
+                }
+                const uint64_t nm2 = pk2(-m_ref, -m_ref);
+                if (nv == ATT_TILE) {
+#pragma unroll
+                    for (int i = 0; i < 128; i += 2) {
+                        const uint64_t X = fma2(pk2u(s[i], s[i + 1]), c2, nm2);
+                        float x0, x1, e0, e1;
+                        upk2(X, x0, x1);
+                        if (((i >> 1) & 7) < POLY) {
+                            const uint64_t Xc = pk2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+                            const uint64_t T = add2(Xc, pk2(12582912.f, 12582912.f));
+                            const uint64_t N = add2(T, pk2(-12582912.f, -12582912.f));
+                            const uint64_t Fr = fma2(N, pk2(-1.f, -1.f), Xc);
+                            uint64_t P = fma2(Fr, pk2(0.0551716574f, 0.0551716574f), pk2(0.2426111400f, 0.2426111400f));
+                            P = fma2(P, Fr, pk2(0.6932609677f, 0.6932609677f));
+                            P = fma2(P, Fr, pk2(0.9999280572f, 0.9999280572f));
+                            float t0, t1, p0, p1;
+                            upk2(T, t0, t1);
+                            upk2(P, p0, p1);
+                            e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+                            e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+                        } else {
+                            e0 = fast_exp2(x0);
+                            e1 = fast_exp2(x1);
+                        }
+                        l2 = add2(l2, pk2(e0, e1));
+                        s[i >> 1] = pack_bf16(e0, e1);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 128; i += 2) {
+                        float x0, x1;
+                        upk2(fma2(pk2u(s[i], s[i + 1]), c2, nm2), x0, x1);
+                        const float e0 = i < nv ? fast_exp2(x0) : 0.f, e1 = i + 1 < nv ? fast_exp2(x1) : 0.f;
+                        l2 = add2(l2, pk2(e0, e1));
+                        s[i >> 1] = pack_bf16(e0, e1);
+                    }
+                }
+                if (j > 0) {
+                    // PV(j-1) reads the P buffer and owns O: it must have retired before either is touched
+                    mbar_wait(pv_done, (t - 1) & 1);
+                    tc_fence_after();
+                    if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll 1
+                        for (int ch = 0; ch < 2; ++ch) {
+                            uint32_t o[32];
+                            tmem_ld32(tO + ch * 32, o);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st32(tO + ch * 32, o);
+                        }
+                    }
+                }
+                // (j == 0: the last PV of the previous unit retired before this unit's epilogue-free P buffer is written —
+                //  the softmax warps waited for it in that unit's epilogue)
+                {
+                    uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+                    uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+                    tmem_st32(tP, lo);
+                    tmem_st32(tP + 32, hi);
+                    tmem_st_wait();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(leader_smem_u32(p_full));
+            }
+            // ---- epilogue of the unit ----
+            float l_lo, l_hi;
+            upk2(l2, l_lo, l_hi);
+            float* xlu = xl + (nu & 1) * 256;
+            xlu[wg * 128 + r] = l_lo + l_hi;
+            mbar_wait(pv_done, (t - 1) & 1);
+            tc_fence_after();
+            named_bar_sync(1 + quad, 64);
+            const float inv = 1.f / (xlu[r] + xlu[128 + r]);
+            uint32_t o0[32], o1[32];
+            tmem_ld32(tO, o0);
+            tmem_ld32(tO + 32, o1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(leader_smem_u32(o_free));      // O may be overwritten by the next unit's PV(0)
+            if (q_valid) {
+                __nv_bfloat16* orow = p.out + (long long)(row_base + q_row0 + r) * D + head * ATT_TILE + wg * 64;
+                if (p.peer_out) {
+                    const int srank = q_row0 / p.sp_rows;
+                    orow = reinterpret_cast<__nv_bfloat16*>(__ldg(reinterpret_cast<const unsigned long long*>(p.peer_out) + srank)) +
+                           (long long)(q_row0 - srank * p.sp_rows + r) * p.out_ld + (p.head_off + head) * ATT_TILE + wg * 64;
+                }
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(o0[q4 * 8 + i]) * inv;
+                    *reinterpret_cast<uint4*>(orow + q4 * 8) =
+                        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                }
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(o1[q4 * 8 + i]) * inv;
+                    *reinterpret_cast<uint4*>(orow + 32 + q4 * 8) =
+                        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                }
+            }
+        }
+    }
+
+    __syncwarp();
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 9) {
+        tc_fence_after();
+        tmem_dealloc_cg2<512>(tmem_base);
+    }
+}
+
+template <int POLY>
+static int launch_attn_pair3p(const CUtensorMap& tm128, const AttnDev& p, int n_units, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        QIE_CUDA_OK(cudaFuncSetAttribute(attn_pair3p_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT7_SMEM));
+        configured = true;
+    }
+    int clusters = sm_count() / 2;
+    if (clusters > n_units) clusters = n_units;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(AT5_THREADS);
+    cfg.dynamicSmemBytes = AT7_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_pair3p_kernel<POLY>, tm128, p));
+    QIE_LAUNCH_OK("attn_pair3p_kernel");
+    return QIE_OK;
+}
+
+// =====================================================================================================================
 // Decoupled single-CTA kernel ("dq"): two 128-row Q tiles per CTA (as attn_kernel), all barriers CTA-local, and the
 // softmax <-> tensor-pipe chain cut as in pair2: the S row goes to registers at once and the S buffer is released
 // (s_free) so S_t(j+1) runs while the exponentials of tile j are computed; P goes through a swizzled smem tile (SS PV).
@@ -1978,7 +2349,7 @@ static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int
     const int dq = (variant >> 3) & 1;
     const int pair3 = (variant >> 12) & 1;
     if (pair3) {
-        QIE_REQUIRE((variant & 0x60C) == 0 && (poly == 0 || poly == 2 || poly == 3 || poly == 4), QIE_EINVAL,
+        QIE_REQUIRE((variant & 0x608) == 0 && (poly == 0 || poly == 2 || poly == 3 || poly == 4), QIE_EINVAL,
                     "qie_attn_fwd: bad variant 0x%x", variant);
         variant &= ~0x1000;
     }
@@ -2011,6 +2382,11 @@ static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int
     cudaStream_t st = (cudaStream_t)stream;
     if (pair3) {  // CTA pair, 256-wide KV tiles, P in TMEM
         grid.x *= 2;
+        if (variant & 0x4) {                                   // bit 2: persistent form (one CTA pair per TPC loops over the units)
+            const int n_units = ((rpb + 255) / 256) * num_heads * seq->batch;
+            return poly == 3 ? launch_attn_pair3p<3>(tm, p, n_units, st) : poly == 0 ? launch_attn_pair3p<0>(tm, p, n_units, st)
+                                                                                       : launch_attn_pair3p<2>(tm, p, n_units, st);
+        }
         const int premax = (variant & 0x1) ? 1 : 0;          // bit 0: pipelined max pass (measured slower: S(j+1) completes too late to prefetch)
         const int spec = (variant & 0x2) ? 1 : 0;            // bit 1: speculative reference (no max pass in front of the exponentials;
                                                              // measured slower: 0.77 vs 0.69 ms, the in-loop max tracking raises register pressure)

@@ -307,7 +307,7 @@ def test_gemm_fp8(cta_group):
 @pytest.mark.parametrize("B,img,txt,H", [(1, 256, 128, 2), (1, 384, 128, 1), (2, 200, 19, 2), (1, 1024, 219, 3),
                                          (2, 520, 130, 2)])
 @pytest.mark.parametrize("variant", [0, 0x100, 0x01, 0x20, 0x31, 0x41, 0x102, 0x22, 0x42, 0x104, 0x24, 0x34, 0x108, 0x28,
-                                     0x1000, 0x1020, 0x1030, 0x1040, 0x1021, 0x1022, 0x1032])
+                                     0x1000, 0x1020, 0x1030, 0x1040, 0x1021, 0x1022, 0x1032, 0x1024, 0x1034])
 def test_attention(B, img, txt, H, variant):
     s = K.seq(B, img, txt)
     D = H * 128
@@ -338,7 +338,7 @@ def test_attention_large_scores_lazy_rescale():
     assert K.rel_err(got, ref) <= 2 ** -6
 
 
-@pytest.mark.parametrize("variant", [0, 0x1020, 0x1022])
+@pytest.mark.parametrize("variant", [0, 0x1020, 0x1022, 0x1024])
 @pytest.mark.parametrize("jump", [3.0, 40.0])
 def test_attention_score_jumps_between_tiles(variant, jump):
     """Keys whose scale jumps from one KV tile to the next: the lazy rescale path (moderate jump) and, for the speculative-
