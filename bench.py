@@ -199,7 +199,7 @@ def run_ours(args):
         model.set_precision(args.precision)
     if args.attn_variant:
         model.set_option(1, args.attn_variant)
-    for env, key in (("QIE_L2_HINTS", 2), ("QIE_LN_VARIANT", 3), ("QIE_SPLIT_TAIL", 4)):   # A/B switches (qie_tune keys)
+    for env, key in (("QIE_L2_HINTS", 2), ("QIE_LN_VARIANT", 3), ("QIE_SPLIT_TAIL", 4), ("QIE_GROUP_M", 5)):   # A/B switches (qie_tune keys)
         if os.environ.get(env):
             qie_b200.lib().qie_tune(key, int(os.environ[env]))
     g = torch.Generator(device=dev).manual_seed(1 + rank)

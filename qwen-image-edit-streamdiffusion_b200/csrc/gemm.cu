@@ -51,6 +51,7 @@ struct GemmDev {
     // split-K tail: the last `tail_tiles` tiles (the partial wave of the persistent schedule) are cut into `tail_split` K
     // ranges, one work item each, so the tail wave costs 1/tail_split of a tile; partial accumulators meet in `scratch`
     int tail_tiles, tail_split, tail_dbg;
+    int group_m;             // m-units per raster band (qie_tune key 5; 0 = GEMM_GROUP_M)
     float* scratch;          // [tail_tiles][tail_split][CG*128 rows][BN] fp32
     int* tickets;            // [tail_tiles][8 row slices]
     void* const* peer_out;   // QKV epilogue, sequence parallel: device table of the ranks' gathered q|k|v buffers (or NULL)
@@ -95,11 +96,11 @@ __device__ __forceinline__ MUnit decode_munit(const GemmDev& p, int mu) {
 // are resident at once cover ~8 m-units x ~9 n-blocks (A and W panels of a few MB each, L2-resident) instead of one m-unit
 // x all n-blocks (which streams the whole W matrix through L2 for every 256 rows: measured 5x the algorithmic DRAM reads).
 constexpr int GEMM_GROUP_M = 8;
-__device__ __forceinline__ void tile_to_mn(int tile, int m_units, int n_blocks, int& mu, int& nb) {
-    const int band = tile / (GEMM_GROUP_M * n_blocks);
-    const int first = band * GEMM_GROUP_M;
-    const int gm = min(GEMM_GROUP_M, m_units - first);
-    const int local = tile - band * GEMM_GROUP_M * n_blocks;
+__device__ __forceinline__ void tile_to_mn(int tile, int m_units, int n_blocks, int& mu, int& nb, int group_m = GEMM_GROUP_M) {
+    const int band = tile / (group_m * n_blocks);
+    const int first = band * group_m;
+    const int gm = min(group_m, m_units - first);
+    const int local = tile - band * group_m * n_blocks;
     mu = first + local % gm;
     nb = local / gm;
 }
@@ -196,7 +197,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int item = tile0; item < num_items; item += tile_step) {
                 const WorkItem wi = decode_item(item, num_tiles, p.tail_tiles, p.tail_split, k_blocks);
                 int mu, nb;
-                tile_to_mn(wi.tile, m_units, p.n_blocks, mu, nb);
+                tile_to_mn(wi.tile, m_units, p.n_blocks, mu, nb, p.group_m);
                 const MUnit m = decode_munit<CG>(p, mu);
                 const int seg_pad = m.s ? p.seq.txt_pad : p.seq.img_pad;
                 int ti = m.ti + cta_rank;
@@ -282,7 +283,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int item = tile0; item < num_items; item += tile_step) {
             const WorkItem wi = decode_item(item, num_tiles, p.tail_tiles, p.tail_split, k_blocks);
             int mu, nb;
-            tile_to_mn(wi.tile, m_units, p.n_blocks, mu, nb);
+            tile_to_mn(wi.tile, m_units, p.n_blocks, mu, nb, p.group_m);
             const MUnit m = decode_munit<CG>(p, mu);
             const int seg_pad = m.s ? p.seq.txt_pad : p.seq.img_pad;
             const int seg_rows = m.s ? p.seq.txt_rows : p.seq.img_rows;
@@ -626,6 +627,7 @@ int gemm_split_buffers(float** scratch_out, int** tickets_out) {
 using namespace qie;
 
 int g_gemm_l2_hints = 0;    // set through qie_tune(2, v)
+int g_gemm_group_m = 0;     // qie_tune(5, v): m-units per raster band, 0 = default
 int g_gemm_split_tail = 1;  // qie_tune(4, v): 0 off, 1 long-K tiles only / two ranges (default), 9 wherever a split fits
 
 extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream) {
@@ -675,6 +677,9 @@ extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream
     }
     p.model_dim = g->N / 3;
     p.l2_hints = g_gemm_l2_hints;
+    // raster band height: wide outputs (QKV, FF-up: >= 24 n-blocks) re-read A less with 16 m-units per band (ncu DRAM reads
+    // 339 -> 239 MB and 429 -> 290 MB per launch), the N = 3072 shapes are best at 8 (profiles/r01_gemm_traffic.json)
+    p.group_m = g_gemm_group_m > 0 ? g_gemm_group_m : (p.n_blocks >= 24 ? 16 : GEMM_GROUP_M);
     if (g->peer_out) {
         QIE_REQUIRE(g->epilogue == QIE_EPI_QKV_NORM_ROPE && seq->batch == 1 && g->sp_size >= 1 && g->sp_size <= 8 &&
                         g->sp_rank >= 0 && g->sp_rank < g->sp_size && (g->N / 3 / 128) % g->sp_size == 0 &&

@@ -489,7 +489,7 @@ int g_ln_threads = 128, g_ln_smem = 0;   // 128 threads (4 rows) per block measu
 int g_ln_variant = 1;                    // 1 = streaming persistent kernel (default), 0 = one warp per row, grid over rows
 }
 // experiment knobs (not part of the reference surface): 0 = adaLN threads per block, 1 = adaLN dynamic smem reservation
-extern int g_gemm_l2_hints, g_gemm_split_tail;   // gemm.cu
+extern int g_gemm_l2_hints, g_gemm_split_tail, g_gemm_group_m;   // gemm.cu
 namespace qie {
 // row counter + exit counter of ln_mod_stream_kernel; allocated at qie_create so that qie_forward never allocates
 int ln_counters(int** out) {
@@ -507,7 +507,8 @@ extern "C" int qie_tune(int key, int value) {
     if (key == 1 && value >= 0 && value <= 200 * 1024) { qie::g_ln_smem = value; return QIE_OK; }
     if (key == 2 && value >= 0 && value <= 3) { g_gemm_l2_hints = value; return QIE_OK; }
     if (key == 3 && (value == 0 || value == 1)) { qie::g_ln_variant = value; return QIE_OK; }
-    if (key == 4 && value >= 0 && value <= 15) { g_gemm_split_tail = value; return QIE_OK; }   // bit 0 on/off; bits 1-2: timing experiments
+    if (key == 4 && value >= 0 && value <= 15) { g_gemm_split_tail = value; return QIE_OK; }
+    if (key == 5 && value >= 0 && value <= 64) { g_gemm_group_m = value; return QIE_OK; }   // bit 0 on/off; bits 1-2: timing experiments
     ::qie::set_error("qie_tune: bad key/value %d/%d", key, value);
     return QIE_EINVAL;
 }

@@ -4,6 +4,11 @@ from pathlib import Path
 import math, torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent)); sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tests"))
 import kernels as K
+import os
+if os.environ.get("QIE_GROUP_M"):
+    K.L.check(K.L.lib().qie_tune(5, int(os.environ["QIE_GROUP_M"])))
+if os.environ.get("QIE_L2_HINTS"):
+    K.L.check(K.L.lib().qie_tune(2, int(os.environ["QIE_L2_HINTS"])))
 dev = "cuda:0"
 what = sys.argv[1]
 s = K.seq(1, 8192, 256)
