@@ -4,4 +4,5 @@ from .transformer import B200QwenImageTransformer2DModel, QwenImageDiTConfig, Tr
 from .pipeline import (StreamingDenoiser, cfg_euler_step, flowmatch_sigmas, model_timestep, pack_latents, run_denoise,  # noqa: F401
                        unpack_latents)
 from .parallel import (ParallelLayout, ShardPlan, UlyssesTransformer, exchange_velocities, make_layout, make_shard_plan,  # noqa: F401
-                       pack_heads, run_denoise_parallel, split_sizes, unpack_heads, emulate_fused_ulysses, PeerRankBuffers, make_peers)
+                       pack_heads, run_denoise_parallel, split_sizes, unpack_heads, emulate_fused_ulysses, PeerRankBuffers, make_peers, scatter_qkv_reference,
+                       scatter_attn_reference)

@@ -113,6 +113,26 @@ class PeerRankBuffers:
         self.ptrs = []
 
 
+def scatter_qkv_reference(qkv_local: torch.Tensor, gathered: Sequence[torch.Tensor], rank: int, size: int, heads: int) -> None:
+    """Host-side statement of what the QKV-GEMM epilogue does with `qie_peers` installed (csrc/gemm.cu, `scat`): head group g of
+    q|k|v of MY rows lands in rank g's gathered buffer [size*rows, 3*(H/size)*128] at rows [rank*rows, (rank+1)*rows).
+    Equivalent to pack_heads + all_to_all_single of the NCCL form; used by the CPU tests to pin the address arithmetic."""
+    rows = qkv_local.shape[0]
+    hl = heads // size
+    x = qkv_local.view(rows, 3, size, hl * 128)
+    for g in range(size):
+        gathered[g].view(size, rows, 3, hl * 128)[rank] = x[:, :, g]
+
+
+def scatter_attn_reference(o_gathered: torch.Tensor, attn_out: Sequence[torch.Tensor], rank: int, size: int, heads: int) -> None:
+    """... and what the attention epilogue does: my head group's output rows of rank s's tokens land in rank s's attention
+    buffer [rows, H*128] at head columns [rank*(H/size)*128, (rank+1)*(H/size)*128)."""
+    hl = heads // size
+    rows = o_gathered.shape[0] // size
+    for s_ in range(size):
+        attn_out[s_][:, rank * hl * 128:(rank + 1) * hl * 128] = o_gathered[s_ * rows:(s_ + 1) * rows]
+
+
 def make_peers(rank: int, size: int, rows_pad: int, gathers: Sequence[int], attn_outs: Sequence[int], tile_valid: torch.Tensor):
     pr = L.Peers()
     pr.rank, pr.size, pr.rows_pad = rank, size, rows_pad

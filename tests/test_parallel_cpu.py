@@ -144,3 +144,55 @@ def test_layout_ranks():
     lay = [qie_b200.make_layout(8, r, 2, new_group=lambda ranks: tuple(ranks)) for r in range(8)]
     assert [l.branch for l in lay] == [0, 0, 0, 0, 1, 1, 1, 1] and [l.sp_rank for l in lay] == [0, 1, 2, 3] * 2
     assert lay[5].sp_group == (4, 5, 6, 7) and lay[5].cfg_group == (1, 5)
+
+
+# ------------------------------------------------------------------ fused peer-memory exchange: address arithmetic on the host
+@pytest.mark.parametrize("P,H,rows", [(2, 4, 256), (4, 4, 128), (8, 24, 128), (2, 6, 384)])
+def test_fused_scatter_addressing_equals_pack_plus_all_to_all(P, H, rows):
+    """The destination layout the fused epilogues write (scatter_*_reference = the address arithmetic of csrc/gemm.cu and
+    csrc/attn.cu with qie_peers) is exactly what pack_heads + all_to_all / all_to_all + unpack_heads of the NCCL form
+    produce — all ranks simulated in one process."""
+    g = torch.Generator().manual_seed(P * 100 + H)
+    hl = H // P
+    qkv = [torch.randn(rows, 3 * H * 128, generator=g) for _ in range(P)]
+    gathered = [torch.zeros(P * rows, 3 * hl * 128) for _ in range(P)]
+    for r in range(P):
+        qie_b200.scatter_qkv_reference(qkv[r], gathered, r, P, H)
+    packed = [qie_b200.pack_heads(qkv[r], P, H) for r in range(P)]                  # [P(dest), rows, 3*hl*128] per source
+    for dst in range(P):
+        want = torch.stack([packed[src][dst] for src in range(P)])                    # what all_to_all_single delivers
+        assert torch.equal(gathered[dst].view(P, rows, 3 * hl * 128), want)
+    # attention output path
+    o = [torch.randn(P * rows, hl * 128, generator=g) for _ in range(P)]              # rank g: its heads, all tokens
+    attn = [torch.zeros(rows, H * 128) for _ in range(P)]
+    for r in range(P):
+        qie_b200.scatter_attn_reference(o[r], attn, r, P, H)
+    for dst in range(P):
+        recv = torch.stack([o[src].view(P, rows, hl * 128)[dst] for src in range(P)])   # all_to_all_single of o_full
+        assert torch.equal(attn[dst], qie_b200.unpack_heads(recv, P))
+
+
+def test_shard_plan_properties_hypothesis():
+    """Random (image tokens, text tokens, ranks): a plan either rejects the split (a rank would own an all-padding tile) or
+    covers every token exactly once with identical padding on every rank."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(1, 20000), st.integers(1, 1200), st.sampled_from([1, 2, 3, 4, 6, 8]))
+    def prop(img, txt, P):
+        try:
+            plans = [qie_b200.make_shard_plan(img, txt, P, r) for r in range(P)]
+        except ValueError:
+            return
+        assert sum(p.img_rows for p in plans) == img and sum(p.txt_rows for p in plans) == txt
+        assert len({(p.img_pad, p.txt_pad, p.tile_valid) for p in plans}) == 1
+        p0 = plans[0]
+        assert p0.img_pad % 128 == 0 and p0.txt_pad % 128 == 0
+        assert all(1 <= v <= 128 for v in p0.tile_valid) and sum(p0.tile_valid) == img + txt
+        off_i = off_t = 0
+        for p in plans:
+            assert (p.img_offset, p.txt_offset) == (off_i, off_t) and p.img_rows >= 1 and p.txt_rows >= 1
+            off_i += p.img_rows
+            off_t += p.txt_rows
+
+    prop()
