@@ -199,6 +199,8 @@ def run_ours(args):
         model.set_precision(args.precision)
     if args.attn_variant:
         model.set_option(1, args.attn_variant)
+    if os.environ.get("QIE_FUSE_LN"):       # A/B: adaLN fused into the gated-residual GEMM launches (qie_set_option key 3)
+        model.set_option(3, int(os.environ["QIE_FUSE_LN"]))
     for env, key in (("QIE_L2_HINTS", 2), ("QIE_LN_VARIANT", 3), ("QIE_SPLIT_TAIL", 4), ("QIE_GROUP_M", 5)):   # A/B switches (qie_tune keys)
         if os.environ.get(env):
             qie_b200.lib().qie_tune(key, int(os.environ[env]))

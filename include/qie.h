@@ -113,7 +113,8 @@ int qie_set_weights(qie_handle* h, const qie_weights* w);
  * cublaslt_int8.py / triton_int8_gemm.py named at README.md:136-141 */
 int qie_set_precision(qie_handle* h, int mode);
 /* tuning/debug knobs outside the reference surface: key 0 = fuse QK-norm+RoPE into the QKV GEMM epilogue (default 1),
- * key 1 = attention kernel variant, key 2 = record CUDA events around every kernel class inside qie_forward */
+ * key 1 = attention kernel variant, key 2 = record CUDA events around every kernel class inside qie_forward,
+ * key 3 = run the adaLN that follows out-proj / FF-down in the tail of that GEMM launch (default 0; whole-forward calls) */
 int qie_set_option(qie_handle* h, int key, int value);
 /* measurement aids: kernels launched by the library so far; event-timed ms / algorithmic work / launches per kernel
  * class since the last read (class 0 GEMM [FLOP], 1 attention [FLOP], 2 adaLN [bytes], 3 modulation GEMV [bytes], 4 other) */
@@ -259,6 +260,16 @@ typedef struct qie_gemm_args {
      * (see qie_peers): peer_out = DEVICE array of sp_size pointers to the ranks' gathered buffers */
     void* const* peer_out;
     int sp_rank, sp_size, sp_rows;
+    /* GATE_RESID only, N == ldo (the output rows are whole residual rows): fuse the LayerNorm + modulate that follows
+     * (qie_ln_modulate with the same arguments) into the tail of this launch — warps that have run out of tiles normalise
+     * the rows of every 256-row unit as soon as all of its n-blocks have been added.  ln_out NULL = off. */
+    void* ln_out;             /* bf16 [rows, N] */
+    void* ln_out8;            /* optional e4m3 / int8 copy + per-row scale, as qie_ln_modulate */
+    float* ln_out_scale;
+    const float* ln_mod;
+    long long ln_mod_bstride, ln_mod_sstride;
+    int ln_shift_off, ln_scale_off, ln_qmode;
+    float ln_eps;
 } qie_gemm_args;
 int qie_gemm(const qie_gemm_args* args, const qie_seq* seq, void* stream);
 

@@ -65,7 +65,10 @@ class GemmArgs(C.Structure):
                 ("gate", C.c_void_p), ("gate_bstride", C.c_longlong), ("gate_sstride", C.c_longlong),
                 ("rope", C.c_void_p), ("qk_norm_w", (C.c_void_p * 2) * 2),
                 ("fp8", C.c_int), ("a_scale", C.c_void_p), ("w_scale", _P2), ("block_n", C.c_int), ("cta_group", C.c_int),
-                ("peer_out", C.c_void_p), ("sp_rank", C.c_int), ("sp_size", C.c_int), ("sp_rows", C.c_int)]
+                ("peer_out", C.c_void_p), ("sp_rank", C.c_int), ("sp_size", C.c_int), ("sp_rows", C.c_int),
+                ("ln_out", C.c_void_p), ("ln_out8", C.c_void_p), ("ln_out_scale", C.c_void_p), ("ln_mod", C.c_void_p),
+                ("ln_mod_bstride", C.c_longlong), ("ln_mod_sstride", C.c_longlong), ("ln_shift_off", C.c_int),
+                ("ln_scale_off", C.c_int), ("ln_qmode", C.c_int), ("ln_eps", C.c_float)]
 
 
 class Peers(C.Structure):

@@ -75,6 +75,7 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 int unpack_rows(const void* x, void* out, int batch, int n, int n_pad, int C, cudaStream_t st);
 int ln_counters(int** out);
 int gemm_split_buffers(float** scratch_out, int** tickets_out);
+int gemm_ln_sync(int** out);
 int attn_fwd_peers(const void* qkv_gathered, void* const* peer_out_dev, int n_tiles, const int* tile_valid_dev, int heads_local,
                    int sp_rows, int out_ld, int head_off, void* stream);
 
@@ -90,6 +91,8 @@ struct qie_handle {
     bool has_weights;
     int precision;   // 0 bf16, 1 fp8
     int fuse_qk;     // 1: RMSNorm+RoPE in the QKV GEMM epilogue, 0: standalone kernel
+    int fuse_ln = 0; // 1: the adaLN after out-proj / FF-down runs in the tail of that GEMM launch (whole-forward calls only);
+                     // bit-identical and parity-tested, measured break-even (151.1 vs 151.0 ms per forward) -> off by default
     int attn_variant;
     qie_weights w;
     std::vector<qie_block_weights> blocks;
@@ -223,6 +226,7 @@ extern "C" int qie_create(const qie_model_cfg* cfg, int device, qie_handle** out
         int* c = nullptr; float* sc = nullptr; int* tk = nullptr;
         int rc0 = ln_counters(&c);
         if (!rc0) rc0 = gemm_split_buffers(&sc, &tk);
+        if (!rc0) rc0 = gemm_ln_sync(&tk);
         if (rc0) return rc0;
     }
     qie_handle* h = new qie_handle();
@@ -300,6 +304,7 @@ extern "C" int qie_set_option(qie_handle* h, int key, int value) {
     if (key == 0) h->fuse_qk = value;
     else if (key == 1) h->attn_variant = value;
     else if (key == 2) h->profile = value;
+    else if (key == 3) h->fuse_ln = value;
     else QIE_REQUIRE(false, QIE_EINVAL, "qie_set_option: unknown key %d", key);
     return QIE_OK;
 }
@@ -542,12 +547,20 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
 
     // ---- transformer blocks ----
     const int l_begin = layer < 0 ? 0 : layer, l_end = layer < 0 ? nb : (layer < nb ? layer + 1 : nb);
+    // whole-forward calls: every adaLN except the very first runs inside the gated-residual GEMM in front of it
+    const bool fuse_ln = h->fuse_ln && phases == QIE_PHASE_ALL && layer < 0 && D % 128 == 0 && D / 128 <= 24;
+    bool final_ln_done = false;
+    auto set_ln = [&](qie_gemm_args& g, const float* mv, long long bs, long long ss, int sh, int sc, bool q8) {
+        g.ln_out = xm; g.ln_mod = mv; g.ln_mod_bstride = bs; g.ln_mod_sstride = ss; g.ln_shift_off = sh; g.ln_scale_off = sc;
+        g.ln_eps = 1e-6f; g.ln_qmode = h->precision;
+        g.ln_out8 = q8 ? xm8 : nullptr; g.ln_out_scale = q8 ? xscale : nullptr;
+    };
     for (int l = l_begin; l < l_end; ++l) {
         const qie_block_weights& bw = h->blocks[l];
         const float* m = mod + (size_t)l * 12 * D;   // + b*modN + s*6D
         if (phases & QIE_PHASE_QKV) {
-        // adaLN 1 -> xm
-        if ((rc = run_ln(m, modN, 6LL * D, 0, D, fp8)))
+        // adaLN 1 -> xm (already produced by the previous block's FF-down launch when fused)
+        if (!(fuse_ln && l > l_begin) && (rc = run_ln(m, modN, 6LL * D, 0, D, fp8)))
             return rc;
         {   // QKV (+ QK-RMSNorm + RoPE)
             qie_gemm_args g{};
@@ -588,10 +601,11 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
                 if ((rc = qie_quant_rows(attn, attn8, xscale + rows, (long long)rows, D, h->precision, st))) return rc;
                 g.a = attn8; g.fp8 = fp8; g.a_scale = xscale + rows;
             }
+            if (fuse_ln) set_ln(g, m, modN, 6LL * D, 3 * D, 4 * D, fp8);      // adaLN 2 in the tail of this launch
             if ((rc = run_gemm(g))) return rc;
         }
         // adaLN 2 -> xm
-        if ((rc = run_ln(m, modN, 6LL * D, 3 * D, 4 * D, fp8)))
+        if (!fuse_ln && (rc = run_ln(m, modN, 6LL * D, 3 * D, 4 * D, fp8)))
             return rc;
         {   // FF up + GELU(tanh)
             qie_gemm_args g{};
@@ -618,6 +632,10 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
                 if ((rc = qie_quant_rows(ffh, ffh8, xscale + 2 * rows, (long long)rows, 4 * D, h->precision, st))) return rc;
                 g.a = ffh8; g.fp8 = fp8; g.a_scale = xscale + 2 * rows;
             }
+            if (fuse_ln) {      // the next block's adaLN 1, or norm_out after the last block, in the tail of this launch
+                if (l + 1 < l_end) set_ln(g, m + 12 * (size_t)D, modN, 6LL * D, 0, D, fp8);
+                else { set_ln(g, fin, 2LL * D, 0, D, 0, false); final_ln_done = true; }
+            }
             if ((rc = run_gemm(g))) return rc;
         }
         }   // QIE_PHASE_POST
@@ -625,7 +643,7 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
 
     // ---- norm_out (AdaLayerNormContinuous: scale first, then shift) + proj_out on the image stream ----
     if (!(phases & QIE_PHASE_END)) return QIE_OK;
-    if ((rc = run_ln(fin, 2LL * D, 0, D, 0, false))) return rc;
+    if (!final_ln_done && (rc = run_ln(fin, 2LL * D, 0, D, 0, false))) return rc;
     {
         qie_gemm_args g{};
         g.a = xm; g.w[0] = h->w.proj_out_w; g.bias[0] = h->w.proj_out_b;

@@ -404,6 +404,14 @@ __device__ __forceinline__ float gelu_tanh(float x) {
     return fmaf(hx, t, hx);
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+// LayerNorm + modulate arithmetic shared by every adaLN implementation (stand-alone kernels and the phase fused into the
+// gated-residual GEMM).  Explicit round-to-nearest ops: no FMA contraction, so all of them produce the same bits.
+__device__ __forceinline__ float ln_sq4(float a, float b, float c, float d) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fadd_rn(__fmul_rn(c, c), __fmul_rn(d, d)));
+}
+__device__ __forceinline__ float ln_apply(float x, float mean, float rstd, float scale, float shift) {
+    return __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(x, mean), rstd), __fadd_rn(1.f, scale)), shift);
+}
 #endif  // __CUDACC__
 
 }  // namespace qie

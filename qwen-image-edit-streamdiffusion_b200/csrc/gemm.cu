@@ -52,6 +52,17 @@ struct GemmDev {
     // ranges, one work item each, so the tail wave costs 1/tail_split of a tile; partial accumulators meet in `scratch`
     int tail_tiles, tail_split, tail_dbg;
     int group_m;             // m-units per raster band (qie_tune key 5; 0 = GEMM_GROUP_M)
+    // fused adaLN (GATE_RESID epilogue, N == ldo == model width): once a 256-row unit of the residual stream has received all
+    // of its n-blocks, warps that have run out of tiles LayerNorm+modulate its rows into ln_out (the A operand of the next GEMM)
+    int ln_fuse, ln_nv, ln_dbg;   // nv = N / 128
+    const float* ln_mod;
+    long long ln_mod_bstride, ln_mod_sstride;
+    int ln_shift_off, ln_scale_off, ln_qmode;
+    float ln_eps;
+    __nv_bfloat16* ln_out;
+    uint8_t* ln_out8;
+    float* ln_out_scale;
+    int* ln_sync;            // [0] job counter, [1] warps that left the LN phase, [2] error flag, [8 + mu] unit completion counts
     float* scratch;          // [tail_tiles][tail_split][CG*128 rows][BN] fp32
     int* tickets;            // [tail_tiles][8 row slices]
     void* const* peer_out;   // QKV epilogue, sequence parallel: device table of the ranks' gathered q|k|v buffers (or NULL)
@@ -64,7 +75,7 @@ struct GemmSmem {
     static constexpr int B_BYTES = (BN / CG) * GEMM_BK_BYTES;               // each CTA of a pair holds half of the W tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (196 * 1024) / STAGE_BYTES > 8 ? 8 : (196 * 1024) / STAGE_BYTES;
-    static constexpr int BAR_BYTES = 256;
+    static constexpr int BAR_BYTES = 512;                                   // ring + TMEM barriers, tmem slot, 16 LN landing barriers
     static constexpr int EPI_ROW_BYTES = 144;                               // 32 fp32 + 16 B pad: conflict-free both ways
     static constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_BYTES;               // per-warp transpose staging
     static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 4 * EPI_WARP_BYTES + 1024;   // +1024: manual alignment
@@ -536,6 +547,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     __syncwarp();   // staging tile is reused by the next chunk
                 }
             }
+            if constexpr (EPI == QIE_EPI_GATE_RESID_F32) {
+                if (p.ln_fuse && !dummy) {      // my 32 rows of this n-block are in the residual stream
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) atomicAdd(p.ln_sync + 8 + mu, 1);
+                }
+            }
             // release this accumulator stage back to the MMA warp (of the leader CTA)
             tc_fence_before();
             __syncwarp();
@@ -546,6 +564,171 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;
+            }
+        }
+        // ================= fused adaLN phase (epilogue warps that have run out of tiles) =================
+        if constexpr (EPI == QIE_EPI_GATE_RESID_F32) {
+            if (p.ln_fuse) {
+                constexpr int JOB_ROWS = 8, LAND = 2;          // rows per job; rows in flight per warp
+                const int jobs_per_unit = CG * GEMM_BM / JOB_ROWS, total_jobs = m_units * jobs_per_unit;
+                const int D = p.ln_nv * 128;
+                const float* x = reinterpret_cast<const float*>(p.out);
+                // The operand ring of this CTA is idle now (its last accumulator has been drained): every epilogue warp takes
+                // 48 KB of it as a landing zone for 1-D bulk copies of residual rows, four rows in flight per warp, so the
+                // LayerNorm phase is not bound by one-row-at-a-time L2 latency (4 warps per SM).
+                // Per warp 48 KB: two landing rows (24 KB) + the shift and scale vectors of the (batch, stream) it is working on
+                // (24 KB): with ~200 KB of the SM's memory carved out as shared, L1 cannot hold them and every row would pay
+                // dozens of serialised L2 round trips for them.
+                float* land = reinterpret_cast<float*>(smem + (size_t)warp * 49152);
+                float* modv = land + LAND * 3072;               // [shift D | scale D]
+                uint64_t* lbar = bars + 32 + warp * 4;          // behind the pipeline barriers (BAR_BYTES = 512): 2 rows + mod
+                uint32_t lph = 0;                               // phase bit per barrier
+                int mod_tag = -1;                               // (batch << 1 | stream) whose vectors are in modv
+                if (lane == 0) {
+                    for (int i = 0; i < 3; ++i) mbar_init(&lbar[i], 1);
+                    fence_barrier_init();
+                }
+                __syncwarp();
+                const uint32_t row_bytes = (uint32_t)D * 4;
+                for (;;) {
+                    int job = 0;
+                    if (lane == 0) job = atomicAdd(p.ln_sync, 1);
+                    job = __shfl_sync(0xffffffffu, job, 0);
+                    if (job >= total_jobs) break;
+                    const int jmu = job / jobs_per_unit, jr0 = (job - jmu * jobs_per_unit) * JOB_ROWS;
+                    const MUnit m = decode_munit<CG>(p, jmu);
+                    const int seg_pad = m.s ? p.seq.txt_pad : p.seq.img_pad;
+                    const int seg_rows = m.s ? p.seq.txt_rows : p.seq.img_rows;
+                    const int local0 = m.ti * GEMM_BM + jr0;                 // first row of the job inside its stream
+                    if (local0 >= seg_pad) continue;                         // the empty half of an odd last unit
+                    // rows of this unit are complete once every n-block has been added by every 32-row slice that exists
+                    const int halves = (m.ti + 1) * GEMM_BM < seg_pad && CG == 2 ? 2 : 1;
+                    const int target = p.n_blocks * 4 * halves;
+                    if (lane == 0) {
+                        const long long t0 = clock64();
+                        while (true) {
+                            int v;
+                            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.ln_sync + 8 + jmu) : "memory");
+                            if (v >= target) break;
+                            if (clock64() - t0 > 4000000000LL) {             // ~2 s: fail loudly instead of hanging
+                                atomicExch(p.ln_sync + 2, 1);
+                                break;
+                            }
+                            __nanosleep((p.ln_dbg & 2) ? 2000 : 64);
+                        }
+                    }
+                    __syncwarp();
+                    if (p.ln_dbg & 1) continue;
+                    auto issue_row = [&](int rr) {            // bulk copy of residual row rr of this job into its landing slot
+                        const int local = local0 + rr;
+                        if (rr < JOB_ROWS && local < seg_rows && lane == 0) {
+                            const long long row = (long long)m.b * rpb + (m.s ? p.seq.img_pad : 0) + local;
+                            uint64_t* lb = &lbar[rr % LAND];
+                            mbar_expect_tx(lb, row_bytes);
+                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                             smem_u32(land + (size_t)(rr % LAND) * 3072)),
+                                         "l"(x + row * D), "r"(row_bytes), "r"(smem_u32(lb))
+                                         : "memory");
+                        }
+                    };
+                    for (int rr = 0; rr < LAND; ++rr) issue_row(rr);
+                    if (mod_tag != (m.b << 1 | m.s)) {      // (re)load the modulation vectors of this (batch, stream)
+                        mod_tag = m.b << 1 | m.s;
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            const float* mrow0 = p.ln_mod + m.b * p.ln_mod_bstride + m.s * p.ln_mod_sstride;
+                            mbar_expect_tx(&lbar[2], 2 * row_bytes);
+                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                             smem_u32(modv)), "l"(mrow0 + p.ln_shift_off), "r"(row_bytes), "r"(smem_u32(&lbar[2]))
+                                         : "memory");
+                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                             smem_u32(modv + D)), "l"(mrow0 + p.ln_scale_off), "r"(row_bytes), "r"(smem_u32(&lbar[2]))
+                                         : "memory");
+                        }
+                        mbar_wait(&lbar[2], (lph >> 2) & 1);
+                        lph ^= 4u;
+                    }
+                    for (int rr = 0; rr < JOB_ROWS; ++rr) {
+                        const int local = local0 + rr;
+                        const long long row = (long long)m.b * rpb + (m.s ? p.seq.img_pad : 0) + local;
+                        __nv_bfloat16* orow = p.ln_out + row * D;
+                        if (local >= seg_rows) {      // pad rows stay exactly zero (as ln_mod_kernel keeps them)
+                            for (int i = 0; i < p.ln_nv; ++i) *reinterpret_cast<uint2*>(orow + (i * 32 + lane) * 4) = make_uint2(0u, 0u);
+                            if (p.ln_out8) {
+                                for (int i = 0; i < p.ln_nv; ++i) *reinterpret_cast<uint32_t*>(p.ln_out8 + row * D + (i * 32 + lane) * 4) = 0u;
+                                if (lane == 0) p.ln_out_scale[row] = 0.f;
+                            }
+                            continue;
+                        }
+                        const int slot = rr % LAND;
+                        mbar_wait(&lbar[slot], (lph >> slot) & 1);
+                        lph ^= 1u << slot;
+                        const float4* xr = reinterpret_cast<const float4*>(land + (size_t)slot * 3072);
+                        float4 v[24];
+                        float sum = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 24; ++i)
+                            if (i < p.ln_nv) {
+                                v[i] = xr[i * 32 + lane];
+                                sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+                            }
+                        fence_proxy_async_smem();       // my reads of the slot are ordered before the bulk copy that refills it
+                        __syncwarp();
+                        issue_row(rr + LAND);
+                        const float mean = warp_sum(sum) * (1.0f / D);
+                        float q = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 24; ++i)
+                            if (i < p.ln_nv) {
+                                float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+                                q += ln_sq4(a, bb, c, d);
+                            }
+                        const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + p.ln_eps);
+                        const float4* sh = reinterpret_cast<const float4*>(modv);
+                        const float4* sc = reinterpret_cast<const float4*>(modv + D);
+                        float amax = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 24; ++i)
+                            if (i < p.ln_nv) {
+                                const float4 h = sh[i * 32 + lane], c = sc[i * 32 + lane];
+                                v[i].x = ln_apply(v[i].x, mean, rstd, c.x, h.x);
+                                v[i].y = ln_apply(v[i].y, mean, rstd, c.y, h.y);
+                                v[i].z = ln_apply(v[i].z, mean, rstd, c.z, h.z);
+                                v[i].w = ln_apply(v[i].w, mean, rstd, c.w, h.w);
+                                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
+                                if (!(p.ln_dbg & 4))
+                                    *reinterpret_cast<uint2*>(orow + (i * 32 + lane) * 4) =
+                                        make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+                            }
+                        if (p.ln_out8) {
+                            amax = warp_max(amax);
+                            amax = __bfloat162float(__float2bfloat16(amax));
+                            const float qmax = p.ln_qmode == 2 ? 127.f : 448.f;
+                            const float scale = amax > 0.f ? amax / qmax : 1.f;
+#pragma unroll
+                            for (int i = 0; i < 24; ++i)
+                                if (i < p.ln_nv) {
+                                    const float4 bq = make_float4(__bfloat162float(__float2bfloat16(v[i].x)), __bfloat162float(__float2bfloat16(v[i].y)),
+                                                                  __bfloat162float(__float2bfloat16(v[i].z)), __bfloat162float(__float2bfloat16(v[i].w)));
+                                    *reinterpret_cast<uint32_t*>(p.ln_out8 + row * D + (i * 32 + lane) * 4) =
+                                        p.ln_qmode == 2 ? pack_s8x4(bq.x / scale, bq.y / scale, bq.z / scale, bq.w / scale)
+                                                        : pack_e4m3x4(bq.x / scale, bq.y / scale, bq.z / scale, bq.w / scale);
+                                }
+                            if (lane == 0) p.ln_out_scale[row] = scale;
+                        }
+                    }
+                }
+                // the last warp to leave re-arms the counters for the next launch
+                if (lane == 0) {
+                    __threadfence();
+                    if (atomicAdd(p.ln_sync + 1, 1) == (int)gridDim.x * 4 - 1) {
+                        for (int i = 0; i < m_units; ++i) p.ln_sync[8 + i] = 0;
+                        p.ln_sync[0] = 0;
+                        p.ln_sync[1] = 0;
+                        __threadfence();
+                    }
+                }
             }
         }
     }
@@ -622,12 +805,23 @@ int gemm_split_buffers(float** scratch_out, int** tickets_out) {
     *tickets_out = tickets;
     return QIE_OK;
 }
+// counters of the fused adaLN phase: [0] job counter, [1] exit counter, [2] error flag, [8 + m-unit] completion counts
+int gemm_ln_sync(int** out) {
+    static int* buf = nullptr;
+    if (!buf) {
+        QIE_CUDA_OK(cudaMalloc(&buf, 4096 * sizeof(int)));
+        QIE_CUDA_OK(cudaMemset(buf, 0, 4096 * sizeof(int)));
+    }
+    *out = buf;
+    return QIE_OK;
+}
 }  // namespace qie
 
 using namespace qie;
 
 int g_gemm_l2_hints = 0;    // set through qie_tune(2, v)
 int g_gemm_group_m = 0;     // qie_tune(5, v): m-units per raster band, 0 = default
+int g_gemm_ln_dbg = 0;      // qie_tune(6, v): timing experiments on the fused adaLN phase
 int g_gemm_split_tail = 1;  // qie_tune(4, v): 0 off, 1 long-K tiles only / two ranges (default), 9 wherever a split fits
 
 extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream) {
@@ -721,6 +915,31 @@ extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream
     }
     const int tiles = cg == 2 ? pair_tiles : seq->batch * (t0 + t1) * p.n_blocks;
     cudaStream_t st = (cudaStream_t)stream;
+    if (g->ln_out) {
+        const int m_units = cg == 2 ? pair_tiles / p.n_blocks : seq->batch * (t0 + t1);
+        QIE_REQUIRE(g->epilogue == QIE_EPI_GATE_RESID_F32 && g->ldo == g->N && g->N % 128 == 0 && g->N / 128 <= 24 && g->ln_mod &&
+                        g->streams == 3 && !g->out_compact && (g->ln_out8 == nullptr) == (g->ln_out_scale == nullptr) &&
+                        m_units + 8 <= 4096,
+                    QIE_EINVAL, "qie_gemm: fused adaLN needs the gated-residual epilogue over whole rows (N == ldo <= 3072), both streams");
+        QIE_REQUIRE(tiles >= 1 && sm_count() / cg >= 1, QIE_EINVAL, "qie_gemm: fused adaLN: empty launch");
+        int* sync = nullptr;
+        int rc0 = qie::gemm_ln_sync(&sync);
+        if (rc0) return rc0;
+        p.ln_fuse = 1;
+        p.ln_dbg = g_gemm_ln_dbg;
+        p.ln_nv = g->N / 128;
+        p.ln_mod = g->ln_mod;
+        p.ln_mod_bstride = g->ln_mod_bstride;
+        p.ln_mod_sstride = g->ln_mod_sstride;
+        p.ln_shift_off = g->ln_shift_off;
+        p.ln_scale_off = g->ln_scale_off;
+        p.ln_qmode = g->ln_qmode;
+        p.ln_eps = g->ln_eps;
+        p.ln_out = (__nv_bfloat16*)g->ln_out;
+        p.ln_out8 = (uint8_t*)g->ln_out8;
+        p.ln_out_scale = g->ln_out_scale;
+        p.ln_sync = sync;
+    }
     // split-K tail (qie_tune key 4): only when the persistent schedule ends in a partial wave that a K split can
     // shorten, never for the QKV epilogue (row statistics over whole heads) or int8 (int32 partials would not survive fp32)
     p.tail_tiles = 0;

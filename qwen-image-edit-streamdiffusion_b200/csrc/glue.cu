@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ x
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-        q += (a * a + bb * bb) + (c * c + d * d);
+        q += ln_sq4(a, bb, c, d);
     }
     const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
     const float* mrow = mod + b * mod_bstride + stream * mod_sstride;
@@ -114,10 +114,10 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ x
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         float4 h = sh[i * 32 + lane], c = sc[i * 32 + lane];
-        v[i].x = (v[i].x - mean) * rstd * (1.f + c.x) + h.x;
-        v[i].y = (v[i].y - mean) * rstd * (1.f + c.y) + h.y;
-        v[i].z = (v[i].z - mean) * rstd * (1.f + c.z) + h.z;
-        v[i].w = (v[i].w - mean) * rstd * (1.f + c.w) + h.w;
+        v[i].x = ln_apply(v[i].x, mean, rstd, c.x, h.x);
+        v[i].y = ln_apply(v[i].y, mean, rstd, c.y, h.y);
+        v[i].z = ln_apply(v[i].z, mean, rstd, c.z, h.z);
+        v[i].w = ln_apply(v[i].w, mean, rstd, c.w, h.w);
         amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
         *reinterpret_cast<uint2*>(orow + (i * 32 + lane) * 4) =
             make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256, 1) ln_mod_stream_kernel(const float* __re
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-                q += (a * a + bb * bb) + (c * c + d * d);
+                q += ln_sq4(a, bb, c, d);
             }
             const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
             const float* mrow = mod + b * mod_bstride + stream * mod_sstride;
@@ -227,10 +227,10 @@ __global__ void __launch_bounds__(256, 1) ln_mod_stream_kernel(const float* __re
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 float4 h = sh[i * 32 + lane], c = sc[i * 32 + lane];
-                v[i].x = (v[i].x - mean) * rstd * (1.f + c.x) + h.x;
-                v[i].y = (v[i].y - mean) * rstd * (1.f + c.y) + h.y;
-                v[i].z = (v[i].z - mean) * rstd * (1.f + c.z) + h.z;
-                v[i].w = (v[i].w - mean) * rstd * (1.f + c.w) + h.w;
+                v[i].x = ln_apply(v[i].x, mean, rstd, c.x, h.x);
+                v[i].y = ln_apply(v[i].y, mean, rstd, c.y, h.y);
+                v[i].z = ln_apply(v[i].z, mean, rstd, c.z, h.z);
+                v[i].w = ln_apply(v[i].w, mean, rstd, c.w, h.w);
                 amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
                 *reinterpret_cast<uint2*>(orow + (i * 32 + lane) * 4) =
                     make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
@@ -489,7 +489,7 @@ int g_ln_threads = 128, g_ln_smem = 0;   // 128 threads (4 rows) per block measu
 int g_ln_variant = 1;                    // 1 = streaming persistent kernel (default), 0 = one warp per row, grid over rows
 }
 // experiment knobs (not part of the reference surface): 0 = adaLN threads per block, 1 = adaLN dynamic smem reservation
-extern int g_gemm_l2_hints, g_gemm_split_tail, g_gemm_group_m;   // gemm.cu
+extern int g_gemm_l2_hints, g_gemm_split_tail, g_gemm_group_m, g_gemm_ln_dbg;   // gemm.cu
 namespace qie {
 // row counter + exit counter of ln_mod_stream_kernel; allocated at qie_create so that qie_forward never allocates
 int ln_counters(int** out) {
@@ -508,7 +508,8 @@ extern "C" int qie_tune(int key, int value) {
     if (key == 2 && value >= 0 && value <= 3) { g_gemm_l2_hints = value; return QIE_OK; }
     if (key == 3 && (value == 0 || value == 1)) { qie::g_ln_variant = value; return QIE_OK; }
     if (key == 4 && value >= 0 && value <= 15) { g_gemm_split_tail = value; return QIE_OK; }
-    if (key == 5 && value >= 0 && value <= 64) { g_gemm_group_m = value; return QIE_OK; }   // bit 0 on/off; bits 1-2: timing experiments
+    if (key == 5 && value >= 0 && value <= 64) { g_gemm_group_m = value; return QIE_OK; }
+    if (key == 6 && value >= 0 && value <= 7) { g_gemm_ln_dbg = value; return QIE_OK; }   // bit 0 on/off; bits 1-2: timing experiments
     ::qie::set_error("qie_tune: bad key/value %d/%d", key, value);
     return QIE_EINVAL;
 }

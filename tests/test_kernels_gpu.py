@@ -236,6 +236,34 @@ def test_gemm_split_k_tail(epi, img, txt, N, Kd):
     assert K.rel_err(gi, wi_) <= (5e-6 if epi == "gate_resid" else 2 ** -7) and K.rel_err(gt, wt_) <= (5e-6 if epi == "gate_resid" else 2 ** -7)
 
 
+@pytest.mark.parametrize("B,img,txt,N,Kd,q8", [(1, 8192, 256, 3072, 512, False), (2, 200, 19, 256, 256, False),
+                                                 (1, 4096 + 130, 219, 3072, 1024, True), (1, 384, 300, 512, 320, False)])
+def test_gemm_fused_adaln_equals_separate_kernel(B, img, txt, N, Kd, q8):
+    """GATE_RESID GEMM with the following LayerNorm+modulate fused into its tail (completion counters per 256-row unit, rows
+    normalised by warps that ran out of tiles) == the same GEMM followed by qie_ln_modulate: residual and adaLN output
+    bit-identical, twice in a row (the counters re-arm themselves)."""
+    s = K.seq(B, img, txt)
+    a, w, b = _gemm_case(s, N, Kd, seed=80)
+    rows = K.rows(s)
+    gate = randn(B, 2, 6 * N, seed=81)
+    res0 = randn(rows, N, seed=82)
+    sep = res0.clone()
+    K.gemm(s, a, w, b, sep, K.L.EPI_GATE_RESID_F32, gate=gate[:, :, 2 * N:], gate_bstride=12 * N, gate_sstride=6 * N, cta_group=2)
+    want = K.ln_modulate(s, sep, gate, 12 * N, 6 * N, 3 * N, 4 * N, N, fp8=q8)
+    for _ in range(2):
+        fused = res0.clone()
+        xm = torch.full((rows, N), 5.0, dtype=torch.bfloat16, device=DEV)
+        ln = dict(out=xm, mod=gate, bstride=12 * N, sstride=6 * N, shift_off=3 * N, scale_off=4 * N)
+        if q8:
+            ln.update(out8=torch.empty(rows, N, dtype=torch.uint8, device=DEV), scale=torch.empty(rows, dtype=torch.float32, device=DEV), qmode=1)
+        K.gemm(s, a, w, b, fused, K.L.EPI_GATE_RESID_F32, gate=gate[:, :, 2 * N:], gate_bstride=12 * N, gate_sstride=6 * N, cta_group=2, ln=ln)
+        assert torch.equal(fused, sep)
+        if q8:
+            assert torch.equal(xm, want[0]) and torch.equal(ln["out8"], want[1]) and torch.equal(ln["scale"], want[2])
+        else:
+            assert torch.equal(xm, want)
+
+
 def test_gemm_compact_single_stream():
     s = K.seq(2, 200, 19)
     N, Kd = 256, 64
