@@ -872,9 +872,8 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_consta
         if (lane == 0 && cta_rank == 0) {
             // ================= MMA issuer (leader) =================
             constexpr uint32_t IDESC_S = umma_idesc_bf16(256, 128, false);
-            constexpr uint32_t IDESC_O = umma_idesc_bf16(256, 128, true);   // B = V is MN-major
-            int ks = 0, vs = 0;
-            uint32_t kph = 0, vph = 0;
+            int ks = 0;
+            uint32_t kph = 0;
             auto issue_S = [&](int buf, int jt) {
                 mbar_wait(&k_full[ks], kph);
                 TRC(0, jt, 1);
@@ -890,20 +889,6 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_consta
                 TRC(0, jt, 2);
                 if (++ks == AT3_KSTAGES) { ks = 0; kph ^= 1; }
             };
-            auto issue_PV = [&](int buf, bool first) {
-                mbar_wait(&v_full[vs], vph);
-                tc_fence_after();
-                const uint32_t v = smem_u32(sV + vs * AT2_SLOT_BYTES), pp = smem_u32(sP + buf * ATT_TILE_BYTES);
-#pragma unroll
-                for (int s = 0; s < 8; ++s)     // 8 x 16 kv rows
-                    umma_ss_f16_cg2(tmem_base + 256 + buf * 128,
-                                    umma_desc_kmajor_sw128(pp + (s >> 2) * ATT_HALF_BYTES + (s & 3) * 32),
-                                    umma_desc_mnmajor_sw128(v + s * 2048, ATT_HALF_BYTES, 1024), IDESC_O,
-                                    (first && s == 0) ? 0u : 1u);
-                umma_commit_cg2(&pv_done[buf], 3);
-                umma_commit_cg2(&v_empty[vs], 3);
-                if (++vs == AT3_VSTAGES) { vs = 0; vph ^= 1; }
-            };
             // Two issuer threads so that neither kind of MMA queues behind the other's dependency:
             //   warp 1: S(j)  as soon as the stream's S buffer is free (s_free) and K_j has landed
             //   warp 2: PV(j) as soon as P(j) is in shared memory (p_full) and V_j has landed
@@ -917,7 +902,6 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_consta
                 tc_fence_after();
                 issue_S(j & 1, j);
             }
-            (void)issue_PV;
         }
     } else if (warp == 2) {
         if (lane == 0 && cta_rank == 0) {
