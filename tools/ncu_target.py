@@ -17,6 +17,17 @@ if what == "attn":
     qkv = torch.randn(K.rows(s), 3 * H * 128, device=dev).bfloat16()
     for v in ([int(x, 0) for x in sys.argv[2:]] or [1, 0, 1, 0]):
         K.attn(s, qkv, H, v)
+elif what == "glue":
+    D = 3072
+    x = torch.randn(K.rows(s), D, device=dev)
+    mod = torch.randn(1, 2, 6 * D, device=dev)
+    for _ in range(3):
+        K.ln_modulate(s, x, mod, 12 * D, 6 * D, 0, D, D)
+    temb = torch.randn(1, D, device=dev)
+    wmod = torch.randn(60 * 2 * 6 * D, D, device=dev).bfloat16()       # all 120 modulation matrices stacked (13.6 GB)
+    bmod = torch.randn(60 * 2 * 6 * D, device=dev)
+    for _ in range(2):
+        K.gemv(temb, wmod, bmod, 1)
 else:
     D = 3072
     M = K.rows(s)
