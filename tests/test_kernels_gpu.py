@@ -237,7 +237,8 @@ def test_gemm_split_k_tail(epi, img, txt, N, Kd):
 
 
 @pytest.mark.parametrize("B,img,txt,N,Kd,q8", [(1, 8192, 256, 3072, 512, False), (2, 200, 19, 256, 256, False),
-                                                 (1, 4096 + 130, 219, 3072, 1024, True), (1, 384, 300, 512, 320, False)])
+                                                 (1, 4096 + 130, 219, 3072, 1024, True), (1, 384, 300, 512, 320, False),
+                                                 (1, 8192, 256, 3072, 6144, False)])     # last: long K, the split-K tail is active too
 def test_gemm_fused_adaln_equals_separate_kernel(B, img, txt, N, Kd, q8):
     """GATE_RESID GEMM with the following LayerNorm+modulate fused into its tail (completion counters per 256-row unit, rows
     normalised by warps that ran out of tiles) == the same GEMM followed by qie_ln_modulate: residual and adaLN output
