@@ -165,7 +165,7 @@ def run_reference(args):
 
 
 def workload_config(args, n):
-    what = ("1024x1024 single-image edit, 2-step Lightning schedule, " if getattr(args, "workload", "1024x1ref") == "1024x1ref"
+    what = (f"1024x1024 single-image edit, {STEPS_PER_IMAGE}-step " + ("Lightning " if STEPS_PER_IMAGE == 2 else "") + "schedule, " if getattr(args, "workload", "1024x1ref") == "1024x1ref"
             else "512x512 frame with two reference images (one frame of BASELINE configs[4]), 4-step schedule, ")
     return {"workload": "Qwen-Image-Edit-2509 MMDiT denoise (60 blocks, D=3072, 24 heads, random-init), " + what +
                         ("true-CFG 4.0 (cond+uncond)" if args.cfg else "cond-only"),
@@ -375,12 +375,18 @@ def main():
     ap.add_argument("--workload", default="1024x1ref", choices=["1024x1ref", "512x2ref"],
                     help="1024x1ref = the headline (BASELINE configs[1]); 512x2ref = one frame of configs[4]: 512x512, two "
                          "reference images (3072 image tokens), 448 text tokens, 4 steps (use with --cfg)")
+    ap.add_argument("--sched-steps", type=int, default=0, help="denoise steps per image (0 = the workload's own: 2 for the "
+                    "headline; BASELINE configs[2] / configs[3] use 4)")
     args = ap.parse_args()
+    global METRIC, IMG_SHAPES, N_NOISE, N_IMG_TOK, T_TXT, STEPS_PER_IMAGE
     if args.workload == "512x2ref":
-        global METRIC, IMG_SHAPES, N_NOISE, N_IMG_TOK, T_TXT, STEPS_PER_IMAGE
         METRIC = "edited_512x512_two_image_frames_per_s_4step"
         IMG_SHAPES = [[(1, 32, 32), (1, 32, 32), (1, 32, 32)]]
         N_NOISE, N_IMG_TOK, T_TXT, STEPS_PER_IMAGE = 1024, 3072, 448, 4
+    if args.sched_steps > 0:
+        STEPS_PER_IMAGE = args.sched_steps
+        if args.workload == "1024x1ref":
+            METRIC = f"edited_1024x1024_images_per_s_{args.sched_steps}step"
     if args.impl == "reference":
         run_reference(args)
     else:
