@@ -2379,10 +2379,13 @@ static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int
         if (spec) {
             // fast launch with a speculative softmax reference, then the exact kernel, which returns at once unless the fast
             // one raised its overflow flag (a score 2^100 above every earlier score of its row: never on real activations)
-            static int* flags = nullptr;
+            static int* flags_dev[64] = {};      // one ring of flags per device of this process
             static unsigned next = 0;
-            if (!flags) QIE_CUDA_OK(cudaMalloc(&flags, 64 * sizeof(int)));
-            int* flag = flags + (next++ & 63);
+            int dev = 0;
+            QIE_CUDA_OK(cudaGetDevice(&dev));
+            QIE_REQUIRE(dev >= 0 && dev < 64, QIE_EINVAL, "device index %d out of range", dev);
+            if (!flags_dev[dev]) QIE_CUDA_OK(cudaMalloc(&flags_dev[dev], 64 * sizeof(int)));
+            int* flag = flags_dev[dev] + (next++ & 63);
             QIE_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int), st));
             p.overflow = flag;
             int rc2 = poly == 3 ? launch_attn_pair3<3, 0, 2>(tm, p, grid, st) : launch_attn_pair3<2, 0, 2>(tm, p, grid, st);

@@ -794,25 +794,31 @@ namespace qie {
 // scratch for the split-K tail partials (96 tiles x 256 x 256 fp32 = 24 MB) and its tickets; allocated at qie_create so that
 // qie_forward never allocates (one set per process: GEMMs of one device are issued on one stream at a time)
 int gemm_split_buffers(float** scratch_out, int** tickets_out) {
-    static float* scratch = nullptr;
-    static int* tickets = nullptr;
-    if (!scratch) {
-        QIE_CUDA_OK(cudaMalloc(&scratch, (size_t)96 * 2 * GEMM_BM * 256 * sizeof(float)));
-        QIE_CUDA_OK(cudaMalloc(&tickets, 96 * 8 * sizeof(int)));
-        QIE_CUDA_OK(cudaMemset(tickets, 0, 96 * 8 * sizeof(int)));
+    static float* scratch[64] = {};         // one set per device of this process
+    static int* tickets[64] = {};
+    int dev = 0;
+    QIE_CUDA_OK(cudaGetDevice(&dev));
+    QIE_REQUIRE(dev >= 0 && dev < 64, QIE_EINVAL, "device index %d out of range", dev);
+    if (!scratch[dev]) {
+        QIE_CUDA_OK(cudaMalloc(&scratch[dev], (size_t)96 * 2 * GEMM_BM * 256 * sizeof(float)));
+        QIE_CUDA_OK(cudaMalloc(&tickets[dev], 96 * 8 * sizeof(int)));
+        QIE_CUDA_OK(cudaMemset(tickets[dev], 0, 96 * 8 * sizeof(int)));
     }
-    *scratch_out = scratch;
-    *tickets_out = tickets;
+    *scratch_out = scratch[dev];
+    *tickets_out = tickets[dev];
     return QIE_OK;
 }
 // counters of the fused adaLN phase: [0] job counter, [1] exit counter, [2] error flag, [8 + m-unit] completion counts
 int gemm_ln_sync(int** out) {
-    static int* buf = nullptr;
-    if (!buf) {
-        QIE_CUDA_OK(cudaMalloc(&buf, 4096 * sizeof(int)));
-        QIE_CUDA_OK(cudaMemset(buf, 0, 4096 * sizeof(int)));
+    static int* buf[64] = {};
+    int dev = 0;
+    QIE_CUDA_OK(cudaGetDevice(&dev));
+    QIE_REQUIRE(dev >= 0 && dev < 64, QIE_EINVAL, "device index %d out of range", dev);
+    if (!buf[dev]) {
+        QIE_CUDA_OK(cudaMalloc(&buf[dev], 4096 * sizeof(int)));
+        QIE_CUDA_OK(cudaMemset(buf[dev], 0, 4096 * sizeof(int)));
     }
-    *out = buf;
+    *out = buf[dev];
     return QIE_OK;
 }
 }  // namespace qie

@@ -493,12 +493,15 @@ extern int g_gemm_l2_hints, g_gemm_split_tail, g_gemm_group_m, g_gemm_ln_dbg;   
 namespace qie {
 // row counter + exit counter of ln_mod_stream_kernel; allocated at qie_create so that qie_forward never allocates
 int ln_counters(int** out) {
-    static int* counters = nullptr;
-    if (!counters) {
-        QIE_CUDA_OK(cudaMalloc(&counters, 2 * sizeof(int)));
-        QIE_CUDA_OK(cudaMemset(counters, 0, 2 * sizeof(int)));
+    static int* counters[64] = {};          // one set per device of this process
+    int dev = 0;
+    QIE_CUDA_OK(cudaGetDevice(&dev));
+    QIE_REQUIRE(dev >= 0 && dev < 64, QIE_EINVAL, "device index %d out of range", dev);
+    if (!counters[dev]) {
+        QIE_CUDA_OK(cudaMalloc(&counters[dev], 2 * sizeof(int)));
+        QIE_CUDA_OK(cudaMemset(counters[dev], 0, 2 * sizeof(int)));
     }
-    *out = counters;
+    *out = counters[dev];
     return QIE_OK;
 }
 }  // namespace qie
