@@ -157,11 +157,65 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec_per_image * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, 1),
+            "config": workload_config(args, args.gpus),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def run_eager_gpu(args):
+    """Like-for-like GPU baseline: the kernels the reference's diffusers transformer dispatches on this GPU,
+    i.e. the restated module in bf16 PyTorch eager (cuBLAS linears, fused SDPA, elementwise ATen kernels).  `--layers` (default
+    4 here) full-width blocks at the headline sequence are timed with CUDA events and scaled to 60 blocks x forwards per image
+    by block count; none of this repo's kernels run.  Reported next to the headline, never as it."""
+    from oracle import qwen_mmdit_ref as R
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    cfg = R.FULL_CONFIG
+    D, n_blk = cfg.inner_dim, args.layers if args.layers < 60 else 4
+    blocks = [R.QwenImageTransformerBlock(D, cfg.num_attention_heads, cfg.attention_head_dim).eval() for _ in range(n_blk)]
+    with torch.no_grad():
+        for b in blocks:
+            for q in b.parameters():
+                q.normal_(0, 0.02)
+            b.to(dev, torch.bfloat16)
+    side = 64 if args.workload == "1024x1ref" else 32
+    shapes = [(1, side, side)] * (2 if args.workload == "1024x1ref" else 3)
+    fr = tuple(f.to(dev) for f in R.QwenEmbedRope(10000, list(cfg.axes_dims_rope), scale_rope=True)(shapes, [T_TXT]))
+    g = torch.Generator(device=dev).manual_seed(0)
+    h = torch.randn(1, N_IMG_TOK, D, generator=g, device=dev).bfloat16()
+    e = torch.randn(1, T_TXT, D, generator=g, device=dev).bfloat16()
+    temb = torch.randn(1, D, generator=g, device=dev).bfloat16()
+
+    def step():
+        with torch.no_grad():
+            x, y = h, e
+            for b in blocks:
+                y, x = b(x, y, temb, fr)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    with ClockSampler(dev.index or 0) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+    ms_blk = e0.elapsed_time(e1) / args.steps / n_blk
+    fwd = STEPS_PER_IMAGE * (2 if args.cfg else 1)
+    ms_img = ms_blk * 60 * fwd
+    print(json.dumps({"impl": "eager_gpu_oracle", "metric": METRIC, "value": 1e3 / ms_img, "unit": UNIT, "n_gpus": 1,
+                      "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_img, "higher_is_better": True,
+                      "dtype": "bf16", "data": "synthetic", "config": workload_config(args, 1), "clocks": clk.summary(),
+                      "sample": f"{n_blk} of 60 full-width blocks at {N_IMG_TOK}+{T_TXT} tokens in bf16 PyTorch eager "
+                                f"(torch {torch.__version__}: cuBLAS + fused SDPA), x{60 // n_blk} by block count; the top "
+                                "(embeddings, norm_out, proj_out: < 0.1 % of the FLOPs) is not included",
+                      "ms_per_block": ms_blk, "dit_forward_ms": ms_blk * 60,
+                      "step_tflops": fwd * flops_per_forward(60) / (ms_img * 1e-3) / 1e12, "gpu_launches": 0}), flush=True)
 
 
 def workload_config(args, n):
@@ -361,7 +415,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager"],
+                    help="ours = libqie.so; reference = the reference's CPU path (fp32 oracle on the host cores); eager = the "
+                         "oracle in bf16 PyTorch eager on the GPU (what diffusers dispatches), a reported side baseline")
     ap.add_argument("--cfg", action="store_true", help="true-CFG (cond + uncond forwards per step)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp8", "int8"])
     ap.add_argument("--layers", type=int, default=60)
@@ -389,6 +445,8 @@ def main():
             METRIC = f"edited_1024x1024_images_per_s_{args.sched_steps}step"
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "eager":
+        run_eager_gpu(args)
     else:
         run_ours(args)
 

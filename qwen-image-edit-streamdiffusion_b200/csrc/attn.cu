@@ -441,12 +441,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p) {
 
 template <bool P_TMEM, int POLY>
 static int launch_attn(const CUtensorMap& tm, const AttnDev& p, dim3 grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        QIE_CUDA_OK(cudaFuncSetAttribute(attn_kernel<P_TMEM, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(attn_kernel<P_TMEM, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          AttCfg<P_TMEM>::SMEM));
-        configured = true;
-    }
     attn_kernel<P_TMEM, POLY><<<grid, ATT_THREADS, AttCfg<P_TMEM>::SMEM, st>>>(tm, p);
     QIE_LAUNCH_OK("attn_kernel");
     return QIE_OK;
@@ -1106,11 +1102,7 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_consta
 
 template <int POLY, int DBG>
 static int launch_attn_pair2(const CUtensorMap& tm128, const CUtensorMap& tm64, const AttnDev& p, dim3 grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        QIE_CUDA_OK(cudaFuncSetAttribute(attn_pair2_kernel<POLY, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_SMEM));
-        configured = true;
-    }
+    QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(attn_pair2_kernel<POLY, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_SMEM));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(AT2_THREADS);
@@ -1559,11 +1551,7 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
 
 template <int POLY, int DBG, int PREMAX>
 static int launch_attn_pair3(const CUtensorMap& tm128, const AttnDev& p, dim3 grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        QIE_CUDA_OK(cudaFuncSetAttribute(attn_pair3_kernel<POLY, DBG, PREMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT5_SMEM));
-        configured = true;
-    }
+    QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(attn_pair3_kernel<POLY, DBG, PREMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT5_SMEM));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(AT5_THREADS);
@@ -1928,11 +1916,7 @@ attn_pair3p_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
 
 template <int POLY>
 static int launch_attn_pair3p(const CUtensorMap& tm128, const AttnDev& p, int n_units, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        QIE_CUDA_OK(cudaFuncSetAttribute(attn_pair3p_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT7_SMEM));
-        configured = true;
-    }
+    QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(attn_pair3p_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT7_SMEM));
     int clusters = sm_count() / 2;
     if (clusters > n_units) clusters = n_units;
     cudaLaunchConfig_t cfg{};
@@ -2242,11 +2226,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p) {
 
 template <int POLY>
 static int launch_attn_dq(const CUtensorMap& tm, const AttnDev& p, dim3 grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        QIE_CUDA_OK(cudaFuncSetAttribute(attn_dq_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT4_SMEM));
-        configured = true;
-    }
+    QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(attn_dq_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT4_SMEM));
     attn_dq_kernel<POLY><<<grid, ATT_THREADS, AT4_SMEM, st>>>(tm, p);
     QIE_LAUNCH_OK("attn_dq_kernel");
     return QIE_OK;
@@ -2254,11 +2234,7 @@ static int launch_attn_dq(const CUtensorMap& tm, const AttnDev& p, dim3 grid, cu
 
 template <int POLY>
 static int launch_attn_pair(const CUtensorMap& tm128, const CUtensorMap& tm64, const AttnDev& p, dim3 grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        QIE_CUDA_OK(cudaFuncSetAttribute(attn_pair_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM));
-        configured = true;
-    }
+    QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(attn_pair_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(AT2_THREADS);

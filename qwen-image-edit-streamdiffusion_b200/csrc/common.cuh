@@ -46,6 +46,24 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 
 int sm_count();
 
+// cudaFuncSetAttribute (dynamic shared-memory opt-in) applies to the current device only: one flag per device of this process
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool* slot() {
+        int dev = 0;
+        return (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) ? &done[dev] : nullptr;
+    }
+};
+#define QIE_CONFIGURE_ONCE(...)                                                        \
+    do {                                                                               \
+        static ::qie::PerDeviceOnce _once;                                             \
+        bool* _slot = _once.slot();                                                    \
+        if (!_slot || !*_slot) {                                                       \
+            QIE_CUDA_OK(__VA_ARGS__);                                                  \
+            if (_slot) *_slot = true;                                                  \
+        }                                                                              \
+    } while (0)
+
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------
 // device helpers

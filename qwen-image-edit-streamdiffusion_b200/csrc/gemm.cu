@@ -748,12 +748,8 @@ template <int BN, int EPI, int QT, int CG>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB0, const CUtensorMap& tmB1, const GemmDev& p,
                        int num_tiles, cudaStream_t st) {
     using S = GemmSmem<BN, CG>;
-    static bool configured = false;
-    if (!configured) {
-        QIE_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, EPI, QT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(gemm_kernel<BN, EPI, QT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          S::TOTAL));
-        configured = true;
-    }
     int units = sm_count() / CG;                 // CTAs (CG=1) or CTA pairs (CG=2) resident at once
     if (units > num_tiles) units = num_tiles;
     cudaLaunchConfig_t cfg{};

@@ -535,11 +535,7 @@ extern "C" int qie_ln_modulate(const float* x, const float* mod, long long mod_b
         cudaStream_t sst = (cudaStream_t)stream;
 #define QIE_LNS_CASE(NV)                                                                                             \
     case NV: {                                                                                                       \
-        static bool cfgd = false;                                                                                    \
-        if (!cfgd) {                                                                                                 \
-            QIE_CUDA_OK(cudaFuncSetAttribute(ln_mod_stream_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-            cfgd = true;                                                                                             \
-        }                                                                                                            \
+        QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(ln_mod_stream_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
         ln_mod_stream_kernel<NV><<<sblocks, 256, ssm, sst>>>(x, mod, mod_bstride, mod_sstride, shift_off, scale_off, \
                                                             (__nv_bfloat16*)out, (uint8_t*)out8, out_scale, qmode, eps, *seq, counters); \
         break;                                                                                                       \

@@ -127,6 +127,20 @@ class B200QwenImageTransformer2DModel(nn.Module):
     def device(self) -> torch.device:
         return self._device
 
+    def to(self, *args, **kwargs):
+        """`pipeline.to("cuda")` reaches every component (server.py:70-71).  The packed weights live where the module was
+        built and are bf16 by construction: the same device / bf16 is a no-op, anything else fails loudly instead of moving
+        only the bookkeeping parameter."""
+        device, dtype, _, _ = torch._C._nn._parse_to(*args, **kwargs)
+        if device is not None:
+            device = torch.device(device)
+            if device.type != "cuda" or (device.index is not None and device.index != (self._device.index or 0)):
+                raise L.QieError(f"the packed weights live on {self._device}; build the module on the target device "
+                                 f"instead of .to({device}) (there is no CPU path)")
+        if dtype is not None and dtype != torch.bfloat16:
+            raise L.QieError(f"the kernels store weights and activations in bf16; .to({dtype}) is not supported")
+        return self
+
     def cache_context(self, name: str):      # CacheMixin.cache_context("cond"/"uncond") — no-op here
         return contextlib.nullcontext()
 

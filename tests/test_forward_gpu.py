@@ -70,6 +70,12 @@ def test_output_object_and_dtype_surface():
     with ours.cache_context("cond"):
         pass
     assert next(ours.parameters()).device == torch.device(DEV)
+    # pipeline.to("cuda") / .eval() reach the module (server.py:70-71): no-ops here; a move off the device or to another dtype
+    # must fail loudly (there is no CPU path and the weights are packed bf16)
+    assert ours.to("cuda") is ours and ours.to(DEV) is ours and ours.to(torch.bfloat16) is ours and ours.eval() is ours
+    for bad in ("cpu", torch.float32):
+        with pytest.raises(qie_b200.QieError):
+            ours.to(bad)
 
 
 def test_truncated_stack_matches_oracle():
