@@ -195,24 +195,34 @@ def run_eager_gpu(args):
             for b in blocks:
                 y, x = b(x, y, temb, fr)
 
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(max(args.warmup, 3)):
         step()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    step()
+    e1.record()
+    torch.cuda.synchronize()
+    # a 60-block forward keeps the GPU at its power cap for hundreds of ms: repeat the sample for >= 3 s (warm, then timed) so
+    # that the blocks run at the sustained clock the headline arm sees, not at the burst clock of a 15 ms sample
+    reps = max(args.steps, int(3000.0 / max(e0.elapsed_time(e1), 1e-3)) + 1)
+    for _ in range(reps):
+        step()
     torch.cuda.synchronize()
     with ClockSampler(dev.index or 0) as clk:
         e0.record()
-        for _ in range(args.steps):
+        for _ in range(reps):
             step()
         e1.record()
         torch.cuda.synchronize()
-    ms_blk = e0.elapsed_time(e1) / args.steps / n_blk
+    ms_blk = e0.elapsed_time(e1) / reps / n_blk
     fwd = STEPS_PER_IMAGE * (2 if args.cfg else 1)
     ms_img = ms_blk * 60 * fwd
     print(json.dumps({"impl": "eager_gpu_oracle", "metric": METRIC, "value": 1e3 / ms_img, "unit": UNIT, "n_gpus": 1,
-                      "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_img, "higher_is_better": True,
+                      "steps": reps, "warmup": reps, "ms_per_step": ms_img, "higher_is_better": True,
                       "dtype": "bf16", "data": "synthetic", "config": workload_config(args, 1), "clocks": clk.summary(),
                       "sample": f"{n_blk} of 60 full-width blocks at {N_IMG_TOK}+{T_TXT} tokens in bf16 PyTorch eager "
-                                f"(torch {torch.__version__}: cuBLAS + fused SDPA), x{60 // n_blk} by block count; the top "
+                                f"(torch {torch.__version__}: cuBLAS + fused SDPA), repeated {reps}x back to back (>= 3 s at the power cap), x{60 // n_blk} "
+                                "by block count; the top "
                                 "(embeddings, norm_out, proj_out: < 0.1 % of the FLOPs) is not included",
                       "ms_per_block": ms_blk, "dit_forward_ms": ms_blk * 60,
                       "step_tflops": fwd * flops_per_forward(60) / (ms_img * 1e-3) / 1e12, "gpu_launches": 0}), flush=True)
@@ -255,7 +265,7 @@ def run_ours(args):
         model.set_option(1, args.attn_variant)
     if os.environ.get("QIE_FUSE_LN"):       # A/B: adaLN fused into the gated-residual GEMM launches (qie_set_option key 3)
         model.set_option(3, int(os.environ["QIE_FUSE_LN"]))
-    for env, key in (("QIE_L2_HINTS", 2), ("QIE_LN_VARIANT", 3), ("QIE_SPLIT_TAIL", 4), ("QIE_GROUP_M", 5)):   # A/B switches (qie_tune keys)
+    for env, key in (("QIE_L2_HINTS", 2), ("QIE_LN_VARIANT", 3), ("QIE_SPLIT_TAIL", 4), ("QIE_GROUP_M", 5), ("QIE_PDL", 7)):   # A/B switches (qie_tune keys)
         if os.environ.get(env):
             qie_b200.lib().qie_tune(key, int(os.environ[env]))
     g = torch.Generator(device=dev).manual_seed(1 + rank)

@@ -119,7 +119,12 @@ int qie_set_option(qie_handle* h, int key, int value);
 /* measurement aids: kernels launched by the library so far; event-timed ms / algorithmic work / launches per kernel
  * class since the last read (class 0 GEMM [FLOP], 1 attention [FLOP], 2 adaLN [bytes], 3 modulation GEMV [bytes], 4 other) */
 unsigned long long qie_launch_count(void);
-int qie_tune(int key, int value);   /* experiments: 0 adaLN threads/block, 1 adaLN smem reservation, 2 GEMM L2 hints (bit 0 weights evict-last, bit 1 activations evict-first) */
+/* process-wide experiment / launch knobs: 0 adaLN threads/block, 1 adaLN smem reservation, 2 GEMM L2 hints (bit 0 weights
+ * evict-last, bit 1 activations evict-first), 3 adaLN kernel form, 4 GEMM split-K tail, 5 GEMM raster band, 6 fused-adaLN
+ * timing experiments, 7 programmatic dependent launch of the GEMM / attention / adaLN kernels (0 off, 1 on).
+ * qie_tune_get returns the current value (>= 0) or QIE_EINVAL for an unknown key. */
+int qie_tune(int key, int value);
+int qie_tune_get(int key);
 int qie_profile_read(qie_handle* h, double* ms5, double* work5, int* launches5);
 /* host helper: pad a (img_rows, txt_rows) pair into the joint layout */
 int qie_make_seq(int batch, int img_rows, int txt_rows, qie_seq* out);

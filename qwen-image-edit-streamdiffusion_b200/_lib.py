@@ -91,6 +91,7 @@ SYMBOLS = {
     "qie_set_option": (_i, [_vp, _i, _i]),
     "qie_launch_count": (C.c_ulonglong, []),
     "qie_tune": (_i, [_i, _i]),
+    "qie_tune_get": (_i, [_i]),
     "qie_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i)]),
     "qie_make_seq": (_i, [_i, _i, _i, C.POINTER(Seq)]),
     "qie_workspace_bytes": (C.c_size_t, [_vp, C.POINTER(Seq)]),
@@ -152,6 +153,8 @@ def lib() -> C.CDLL:
             fn.restype, fn.argtypes = res, args
         if l.qie_version() != 1:
             raise QieError("libqie ABI version mismatch")
+        if os.environ.get("QIE_PDL"):       # A/B switch for whole test / bench runs: programmatic dependent launch (qie_tune key 7)
+            l.qie_tune(7, int(os.environ["QIE_PDL"]))
         _lib = l
     return _lib
 

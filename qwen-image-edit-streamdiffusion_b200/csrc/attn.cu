@@ -1172,6 +1172,7 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
     const int D = p.H * ATT_TILE;
     const int colQ = head * ATT_TILE, colK = D + head * ATT_TILE, colV = 2 * D + head * ATT_TILE;
     const int row_base = b * rpb;
+    griddep_launch_dependents();
     if (p.run_if && *p.run_if == 0) return;        // exact rerun behind a speculative launch: nothing overflowed, nothing to do
     [[maybe_unused]] const bool traced = DBG == 4 && p.trace && (blockIdx.x >> 1) == 3 && blockIdx.y == 9 && blockIdx.z == 0;
 
@@ -1192,6 +1193,7 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     constexpr uint32_t COL_S = 128, COL_P = 384;
+    griddep_wait();      // the prologue above overlapped the QKV GEMM's last wave; q|k|v are visible from here on
     // Register redistribution (the kernel is compiled for 384 threads x 168 registers): the control warpgroup (warps 8-11)
     // hands registers to the two softmax warpgroups, whose threads hold a whole 128-value score row.
 
@@ -1557,13 +1559,9 @@ static int launch_attn_pair3(const CUtensorMap& tm128, const AttnDev& p, dim3 gr
     cfg.blockDim = dim3(AT5_THREADS);
     cfg.dynamicSmemBytes = AT5_SMEM;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = launch_attrs(attr, 2, /*pdl_ok=*/p.run_if == nullptr);   // the exact rerun reads its flag on entry
     QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_pair3_kernel<POLY, DBG, PREMAX>, tm128, p));
     QIE_LAUNCH_OK("attn_pair3_kernel");
     return QIE_OK;

@@ -46,6 +46,29 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 
 int sm_count();
 
+// Programmatic dependent launch (qie_tune key 7): the three per-block kernels (GEMM, attention, adaLN) are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization; each signals griddepcontrol.launch_dependents on entry and runs its
+// prologue (barrier init, TMEM allocation, tensor-map prefetch, cluster sync) while the previous kernel drains its last wave,
+// then griddepcontrol.wait's for that kernel's memory before touching global memory.
+extern int g_pdl;
+// fills attr[0..] with the cluster dimension (when > 1) and, if enabled, the programmatic-serialisation attribute
+inline int launch_attrs(cudaLaunchAttribute* attr, int cluster_x, bool pdl_ok = true) {
+    int n = 0;
+    if (cluster_x > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster_x;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (g_pdl && pdl_ok) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    return n;
+}
+
 // cudaFuncSetAttribute (dynamic shared-memory opt-in) applies to the current device only: one flag per device of this process
 struct PerDeviceOnce {
     bool done[64] = {};
@@ -72,6 +95,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+// ---- programmatic dependent launch ----
+// the next kernel of the stream (if launched with the programmatic-serialisation attribute) may start its prologue
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// blocks until the previous kernel of the stream has completed and its memory is visible (no-op without the attribute)
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- mbarrier ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -160,6 +160,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint64_t* tempty_bar = bars + 2 * STAGES + 2;// [2]        (CG=2: only the leader's copy is used)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
+    griddep_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
     const int u0 = (p.streams & 1) ? units_in_stream<CG>(p.seq.img_pad) : 0;
@@ -194,6 +195,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();      // everything above overlapped the previous kernel's tail; its output is visible from here on
 
     if (warp == 4) {
         if (lane == 0) {
@@ -757,13 +759,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB0, const CU
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = S::TOTAL;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = launch_attrs(attr, CG);
     QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, QT, CG>, tmA, tmB0, tmB1, p));
     QIE_LAUNCH_OK("gemm_kernel");
     return QIE_OK;
@@ -821,6 +819,7 @@ int gemm_ln_sync(int** out) {
 
 using namespace qie;
 
+int qie::g_pdl = 0;          // qie_tune(7, v): programmatic dependent launch of the per-block kernels
 int g_gemm_l2_hints = 0;    // set through qie_tune(2, v)
 int g_gemm_group_m = 0;     // qie_tune(5, v): m-units per raster band, 0 = default
 int g_gemm_ln_dbg = 0;      // qie_tune(6, v): timing experiments on the fused adaLN phase

@@ -157,12 +157,14 @@ __global__ void __launch_bounds__(256, 1) ln_mod_stream_kernel(const float* __re
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)8 * 2 * ROW_BYTES) + warp * 2;
     const int rpb = seq.img_pad + seq.txt_pad;
     const int rows = seq.batch * rpb;
+    griddep_launch_dependents();
     if (lane == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         fence_barrier_init();
     }
     __syncwarp();
+    griddep_wait();      // the residual stream written by the previous GEMM is visible from here on
     const int total_warps = gridDim.x * 8, gwarp = blockIdx.x * 8 + warp;
     auto fetch = [&]() -> int {               // rows beyond the static prefix (two per warp) come from the counter
         int r = 0;
@@ -513,7 +515,23 @@ extern "C" int qie_tune(int key, int value) {
     if (key == 4 && value >= 0 && value <= 15) { g_gemm_split_tail = value; return QIE_OK; }
     if (key == 5 && value >= 0 && value <= 64) { g_gemm_group_m = value; return QIE_OK; }
     if (key == 6 && value >= 0 && value <= 7) { g_gemm_ln_dbg = value; return QIE_OK; }   // bit 0 on/off; bits 1-2: timing experiments
+    if (key == 7 && (value == 0 || value == 1)) { qie::g_pdl = value; return QIE_OK; }   // programmatic dependent launch
     ::qie::set_error("qie_tune: bad key/value %d/%d", key, value);
+    return QIE_EINVAL;
+}
+
+extern "C" int qie_tune_get(int key) {
+    switch (key) {
+        case 0: return qie::g_ln_threads;
+        case 1: return qie::g_ln_smem;
+        case 2: return g_gemm_l2_hints;
+        case 3: return qie::g_ln_variant;
+        case 4: return g_gemm_split_tail;
+        case 5: return g_gemm_group_m;
+        case 6: return g_gemm_ln_dbg;
+        case 7: return qie::g_pdl;
+    }
+    ::qie::set_error("qie_tune_get: bad key %d", key);
     return QIE_EINVAL;
 }
 
@@ -536,8 +554,16 @@ extern "C" int qie_ln_modulate(const float* x, const float* mod, long long mod_b
 #define QIE_LNS_CASE(NV)                                                                                             \
     case NV: {                                                                                                       \
         QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(ln_mod_stream_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-        ln_mod_stream_kernel<NV><<<sblocks, 256, ssm, sst>>>(x, mod, mod_bstride, mod_sstride, shift_off, scale_off, \
-                                                            (__nv_bfloat16*)out, (uint8_t*)out8, out_scale, qmode, eps, *seq, counters); \
+        cudaLaunchConfig_t lcfg{};                                                                                   \
+        lcfg.gridDim = dim3(sblocks);                                                                                \
+        lcfg.blockDim = dim3(256);                                                                                   \
+        lcfg.dynamicSmemBytes = ssm;                                                                                 \
+        lcfg.stream = sst;                                                                                           \
+        cudaLaunchAttribute lattr[2];                                                                                \
+        lcfg.attrs = lattr;                                                                                          \
+        lcfg.numAttrs = launch_attrs(lattr, 1);                                                                      \
+        QIE_CUDA_OK(cudaLaunchKernelEx(&lcfg, ln_mod_stream_kernel<NV>, x, mod, mod_bstride, mod_sstride, shift_off, scale_off, \
+                                       (__nv_bfloat16*)out, (uint8_t*)out8, out_scale, qmode, eps, *seq, counters)); \
         break;                                                                                                       \
     }
         switch (D / 128) {

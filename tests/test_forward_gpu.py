@@ -395,3 +395,44 @@ def test_fused_adaln_forward_is_bit_identical(precision):
     fused = model(x, cond, None, ts, shapes, [37, 37], return_dict=False)[0].clone()
     fused2 = model(x, cond, None, ts, shapes, [37, 37], return_dict=False)[0]
     assert torch.equal(fused, separate) and torch.equal(fused2, separate)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp8"])
+def test_programmatic_dependent_launch_is_bit_identical(precision):
+    """qie_tune(7, v): GEMM / attention / adaLN launched with the programmatic-serialisation attribute (prologue under the
+    previous kernel's tail, griddepcontrol.wait before the first global access) vs plain stream order — eager, repeated
+    (a race would show as run-to-run differences) and captured in a CUDA graph."""
+    ref_cfg = R.RefConfig(num_layers=3, attention_head_dim=128, num_attention_heads=2, joint_attention_dim=128)
+    cfg = qie_b200.QwenImageDiTConfig(num_layers=3, num_attention_heads=2, joint_attention_dim=128)
+    oracle = R.init_weights_(R.QwenImageTransformer2DModelRef(ref_cfg), seed=0)
+    model = qie_b200.B200QwenImageTransformer2DModel.from_state_dict(oracle.state_dict(), cfg, DEV)
+    if precision != "bf16":
+        model.set_precision(precision)
+    shapes = [[(1, 32, 32), (1, 24, 20)]] * 2
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(2, 1504, 64, generator=g).bfloat16().to(DEV)
+    cond = (torch.randn(2, 37, 128, generator=g) * 3).bfloat16().to(DEV)
+    ts = torch.tensor([0.5, 0.5], device=DEV)
+    lib = qie_b200.lib()
+    prev = lib.qie_tune_get(7)
+    try:
+        assert lib.qie_tune(7, 0) == 0
+        plain = model(x, cond, None, ts, shapes, [37, 37], return_dict=False)[0].clone()
+        assert lib.qie_tune(7, 1) == 0
+        for _ in range(5):
+            got = model(x, cond, None, ts, shapes, [37, 37], return_dict=False)[0]
+            assert torch.equal(got, plain)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            model(x, cond, None, ts, shapes, [37, 37], return_dict=False)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = model(x, cond, None, ts, shapes, [37, 37], return_dict=False)[0]
+        for _ in range(3):
+            graph.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(out, plain)
+    finally:
+        lib.qie_tune(7, prev)
