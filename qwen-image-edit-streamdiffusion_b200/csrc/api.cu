@@ -259,6 +259,8 @@ extern "C" int qie_destroy(qie_handle* h) {
     cudaFree(h->d_sched_fin);
     cudaFree(h->d_peer_tab);
     for (float* p : h->d_prompt) cudaFree(p);
+    for (auto& p : h->prof) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
     return QIE_OK;
 }
