@@ -436,3 +436,24 @@ def test_programmatic_dependent_launch_is_bit_identical(precision):
             assert torch.equal(out, plain)
     finally:
         lib.qie_tune(7, prev)
+
+
+@pytest.mark.slow
+def test_long_sequence_256x256_latent_tiny_model():
+    """BASELINE.json configs[0] read literally: a 256x256 latent = 128x128 packed tokens of noise plus as many
+    reference tokens -> 32768 image tokens + ragged text through the reduced-width 2-block model, single step at sigma = 1.
+    The longest sequence the suite runs: 129 KV tiles of 256 rows per head, RoPE h/w indices -64..63."""
+    ref_cfg, our_cfg = small_cfg(layers=2)
+    oracle, ours = build_pair(ref_cfg, our_cfg)
+    oracle = oracle.to(DEV)
+    shapes = [[(1, 128, 128), (1, 128, 128)]]
+    hidden, enc = R.make_inputs(ref_cfg, shapes, 19, seed=1)
+    hidden, enc = bf16_round(hidden).to(DEV), bf16_round(enc).to(DEV)
+    ts = torch.tensor([1.0], device=DEV)
+    with torch.no_grad():
+        ref = oracle(hidden, enc, None, ts, shapes, [19])[0]
+    got = ours(hidden_states=hidden, encoder_hidden_states=enc, timestep=ts, img_shapes=shapes, txt_seq_lens=[19],
+               return_dict=False)[0]
+    assert got.shape == (1, 32768, 64)
+    err = K.rel_err(got, ref)
+    assert err <= VEL_TOL, err
