@@ -51,3 +51,34 @@ def test_cuda_arm_refuses_to_run_without_a_device(bench, monkeypatch):
     with pytest.raises(SystemExit) as e:
         bench.main()
     assert "no CPU fallback" in str(e.value)
+
+
+def _run_bench(args, env_extra):
+    import os
+    import subprocess
+    env = dict(os.environ, QIE_BENCH_CPU_SAMPLE_S="0.2", **env_extra)
+    return subprocess.run([sys.executable, str(ROOT / "bench.py")] + args, env=env, capture_output=True, text=True, timeout=600)
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference`: ONE JSON line on rank 0 with the keys the driver reads (same metric / unit / config as the
+    CUDA arm, impl = reference, cpu_baseline describing this run, e2e repeating the value with zero copy bytes)."""
+    import json
+    r = _run_bench(["--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "0"], {})
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "edited_1024x1024_images_per_s_2step_lightning" and d["unit"] == "img/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["vs_baseline"] is None
+    assert d["value"] > 0 and d["ms_per_step"] == pytest.approx(1e3 / d["value"], rel=1e-6)
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert "full-width" in d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("Qwen-Image-Edit-2509 MMDiT denoise") and d["gpu_launches"] == 0
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    r = _run_bench(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                   {"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
