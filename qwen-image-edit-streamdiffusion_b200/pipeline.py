@@ -17,6 +17,11 @@ from . import _lib as L
 
 def flowmatch_sigmas(num_steps: int, image_seq_len: int) -> np.ndarray:
     """FlowMatchEulerDiscreteScheduler.set_timesteps(sigmas=linspace(1,1/N,N), mu=calculate_shift(seq)) -> N+1 sigmas."""
+    if num_steps < 2:
+        # upstream's stretch-to-terminal computes 1 - (1 - sigma) / ((1 - sigma[-1]) / 0.98): with the single sigma 1.0 that is
+        # 0 / 0 -> NaN timesteps (and NaN images) without any error; fail loudly instead
+        raise L.QieError("the dynamic-shift schedule needs at least 2 steps (one step is 0/0 in the reference scheduler); "
+                         "pass explicit `sigmas` to run_denoise for a single-step update")
     buf = (C.c_float * (num_steps + 1))()
     L.check(L.lib().qie_flowmatch_sigmas(num_steps, image_seq_len, buf), "qie_flowmatch_sigmas")
     return np.array(buf[:], dtype=np.float32)

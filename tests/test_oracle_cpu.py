@@ -294,3 +294,48 @@ def test_streaming_denoiser_host_logic_matches_oracle_schedule():
         assert sd.forwards_per_frame() == (4 if key else 1)
         prev = out
     assert sd.frame_count == 7
+
+
+# ------------------------------------------------------------------ properties over random shapes (hypothesis)
+def test_sigma_schedule_properties_library_vs_oracle():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(n=st.integers(2, 50), seq=st.integers(16, 16384))
+    def check(n, seq):
+        lib_s, ref_s = qie_b200.flowmatch_sigmas(n, seq), R.ref_flowmatch_sigmas(n, seq)
+        assert lib_s.shape == (n + 1,) and np.allclose(lib_s, ref_s, atol=2e-6)
+        assert lib_s[-1] == 0.0 and abs(lib_s[-2] - 0.02) < 1e-6                    # stretched to shift_terminal, then 0 appended
+        assert np.all(np.diff(lib_s) < 0)                                          # strictly decreasing
+        assert abs(lib_s[0] - 1.0) < 1e-6
+
+    check()
+    # one step: the reference scheduler's stretch is 0/0 (NaN schedule, silently); the host wrapper refuses instead
+    with np.errstate(invalid="ignore"):
+        assert np.isnan(R.ref_flowmatch_sigmas(1, 4096)[0])
+    with pytest.raises(qie_b200.QieError, match="at least 2 steps"):
+        qie_b200.flowmatch_sigmas(1, 4096)
+
+
+def test_rope_table_library_vs_oracle_random_image_lists():
+    """qie_rope_table_host against QwenEmbedRope for random lists of 1-3 images with odd / even grids and ragged text."""
+    from hypothesis import given, settings, strategies as st
+
+    cfg = L.ModelCfg(1, 1, 128, 64, 64, 64, (C.c_int * 3)(16, 56, 56))
+    rope = R.QwenEmbedRope(10000, [16, 56, 56], scale_rope=True)
+    grid = st.tuples(st.just(1), st.integers(1, 24), st.integers(1, 24))
+
+    @settings(max_examples=25, deadline=None)
+    @given(shapes=st.lists(grid, min_size=1, max_size=3), T=st.integers(1, 300))
+    def check(shapes, T):
+        n_img = sum(f * h * w for f, h, w in shapes)
+        seq = qie_b200.make_seq(1, n_img, T)
+        flat = [v for s in shapes for v in s]
+        buf = (C.c_float * ((seq.img_pad + seq.txt_pad) * 128))()
+        L.check(L.lib().qie_rope_table_host(C.byref(cfg), (C.c_int * len(flat))(*flat), len(shapes), C.byref(seq), buf))
+        tab = torch.frombuffer(buf, dtype=torch.float32).reshape(-1, 64, 2)
+        img, txt = rope([tuple(s) for s in shapes], [T])
+        assert torch.allclose(tab[:n_img], torch.view_as_real(img), atol=3e-6)
+        assert torch.allclose(tab[seq.img_pad:seq.img_pad + T], torch.view_as_real(txt), atol=3e-6)
+
+    check()
