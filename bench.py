@@ -167,14 +167,14 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def run_eager_gpu(args):
+def run_eager_gpu(args, emit=True, min_ms=3000.0):
     """Like-for-like GPU baseline: the kernels the reference's diffusers transformer dispatches on this GPU,
     i.e. the restated module in bf16 PyTorch eager (cuBLAS linears, fused SDPA, elementwise ATen kernels).  `--layers` (default
     4 here) full-width blocks at the headline sequence are timed with CUDA events and scaled to 60 blocks x forwards per image
     by block count; none of this repo's kernels run.  Reported next to the headline, never as it."""
     from oracle import qwen_mmdit_ref as R
     if int(os.environ.get("RANK", "0")) != 0:
-        return
+        return None
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     cfg = R.FULL_CONFIG
     D, n_blk = cfg.inner_dim, args.layers if args.layers < 60 else 4
@@ -207,7 +207,7 @@ def run_eager_gpu(args):
     torch.cuda.synchronize()
     # a 60-block forward keeps the GPU at its power cap for hundreds of ms: repeat the sample for >= 3 s (warm, then timed) so
     # that the blocks run at the sustained clock the headline arm sees, not at the burst clock of a 15 ms sample
-    reps = max(args.steps, int(3000.0 / max(e0.elapsed_time(e1), 1e-3)) + 1)
+    reps = max(args.steps, int(min_ms / max(e0.elapsed_time(e1), 1e-3)) + 1)
     for _ in range(reps):
         step()
     torch.cuda.synchronize()
@@ -220,15 +220,20 @@ def run_eager_gpu(args):
     ms_blk = e0.elapsed_time(e1) / reps / n_blk
     fwd = STEPS_PER_IMAGE * (2 if args.cfg else 1)
     ms_img = ms_blk * 60 * fwd
-    print(json.dumps({"impl": "eager_gpu_oracle", "metric": METRIC, "value": 1e3 / ms_img, "unit": UNIT, "n_gpus": 1,
-                      "steps": reps, "warmup": reps, "ms_per_step": ms_img, "higher_is_better": True,
-                      "dtype": "bf16", "data": "synthetic", "config": workload_config(args, 1), "clocks": clk.summary(),
-                      "sample": f"{n_blk} of 60 full-width blocks at {N_IMG_TOK}+{T_TXT} tokens in bf16 PyTorch eager "
-                                f"(torch {torch.__version__}: cuBLAS + fused SDPA), repeated {reps}x back to back (>= 3 s at the power cap), x{60 // n_blk} "
-                                "by block count; the top "
-                                "(embeddings, norm_out, proj_out: < 0.1 % of the FLOPs) is not included",
-                      "ms_per_block": ms_blk, "dit_forward_ms": ms_blk * 60,
-                      "step_tflops": fwd * flops_per_forward(60) / (ms_img * 1e-3) / 1e12, "gpu_launches": 0}), flush=True)
+    line = {"impl": "eager_gpu_oracle", "metric": METRIC, "value": 1e3 / ms_img, "unit": UNIT, "n_gpus": 1,
+            "steps": reps, "warmup": reps, "ms_per_step": ms_img, "higher_is_better": True,
+            "dtype": "bf16", "data": "synthetic", "config": workload_config(args, 1), "clocks": clk.summary(),
+            "sample": f"{n_blk} of 60 full-width blocks at {N_IMG_TOK}+{T_TXT} tokens in bf16 PyTorch eager "
+                      f"(torch {torch.__version__}: cuBLAS + fused SDPA), repeated {reps}x back to back (>= {min_ms / 1e3:.0f} s at the power cap), x{60 // n_blk} "
+                      "by block count; the top "
+                      "(embeddings, norm_out, proj_out: < 0.1 % of the FLOPs) is not included",
+            "ms_per_block": ms_blk, "dit_forward_ms": ms_blk * 60,
+            "step_tflops": fwd * flops_per_forward(60) / (ms_img * 1e-3) / 1e12, "gpu_launches": 0}
+    del blocks, h, e, temb
+    torch.cuda.empty_cache()
+    if emit:
+        print(json.dumps(line), flush=True)
+    return line
 
 
 def workload_config(args, n):
@@ -241,6 +246,109 @@ def workload_config(args, n):
             "parallelism": (f"dp{n}: one independent frame stream per GPU, weights replicated, no data-path collective"
                             if args.mode == "dp" else f"{args.mode}{' (fused peer-memory exchange)' if args.fused else ' (NCCL all-to-all)' if 'ulysses' in args.mode else ''} over {n} GPUs: ONE frame, weights replicated"),
             "l2": "inputs larger than L2: 40.9 GB of weights + 0.6 GB of activations stream through the 126 MB L2 every forward"}
+
+
+# ------------------------------------------------------------------------------------------------
+# strong-scaling leg: ONE true-CFG frame spread over all ranks (the partition north_star names), checked in-process
+# ------------------------------------------------------------------------------------------------
+def strong_mode(world):
+    if world == 1:
+        return "single", 1, 1
+    if world == 2:
+        return "cfgpair", 2, 1
+    if world % 2 == 0 and 24 % (world // 2) == 0:
+        return f"cfgpair x fused-ulysses{world // 2}", 2, world // 2
+    if 24 % world == 0:
+        return f"fused-ulysses{world}", 1, world
+    return None, 0, 0
+
+
+def strong_leg(args, model, dev, world, rank, timed):
+    """ONE edited frame with true CFG (2 steps x (cond + uncond) = 4 forwards) over all N GPUs: CFG pair at N = 2, CFG pair x
+    fused (peer-memory) Ulysses at N = 4 / 8.  Every rank first runs the same frame alone (the N = 1 time measured on this box
+    in this run, and the reference result), then the group runs it together; the final latents must agree (CFG pair: bit for
+    bit; sequence parallel: <= 1e-2 max-rel, only the attention reduction order differs).  Returns the `strong` record; raises
+    SystemExit(1) after printing it when the partition is wrong."""
+    import torch.distributed as dist
+    import qie_b200
+    mode, branches, sp = strong_mode(world)
+    if mode is None:
+        return {"mode": None, "skipped": f"{world} ranks do not factor into cfg branches x a divisor of 24 heads"}
+    cfg = model.cfg
+    g = torch.Generator(device=dev).manual_seed(1)            # one frame: identical inputs on every rank
+    lat = torch.randn(1, N_NOISE, 64, generator=g, device=dev).bfloat16()
+    img_lat = torch.randn(1, N_IMG_TOK - N_NOISE, 64, generator=g, device=dev).bfloat16()
+    cond = (torch.randn(1, T_TXT, cfg.joint_attention_dim, generator=g, device=dev) * 3).bfloat16()
+    unc = (torch.randn(1, T_TXT, cfg.joint_attention_dim, generator=g, device=dev) * 3).bfloat16()
+
+    def single():
+        return qie_b200.run_denoise(model, lat, img_lat, cond, IMG_SHAPES, STEPS_PER_IMAGE, unc, 4.0)
+
+    for _ in range(2):
+        ref = single()
+    n1_ms = timed(single, max(2, args.steps // 2)) / max(2, args.steps // 2)      # max over ranks of the same single-GPU frame
+    rec = {"mode": mode, "frame": f"true-CFG 4.0, {STEPS_PER_IMAGE} steps = {2 * STEPS_PER_IMAGE} forwards of {N_IMG_TOK}+{T_TXT} tokens",
+           "n1_ms_per_frame": n1_ms, "n1_how": "the same frame on ONE GPU of this box (every rank runs it alone; max over ranks)"}
+    if world == 1:
+        rec.update({"ms_per_frame": n1_ms, "efficiency_vs_n1": 1.0, "parity_err": 0.0, "barrier_timeouts": 0,
+                    "exchange_bytes": 0})
+        return rec
+    layout = qie_b200.make_layout(world, rank, branches)
+    runner = model
+    if layout.sp_size > 1:
+        runner = qie_b200.UlyssesTransformer(model, layout.sp_group, fused=True)
+
+    def frame():
+        return qie_b200.run_denoise_parallel(runner, layout, lat, img_lat, cond, unc, IMG_SHAPES, STEPS_PER_IMAGE, 4.0)
+
+    for _ in range(3):                  # eager, graph capture, first replay
+        got = frame()
+    ms = timed(frame, args.steps) / args.steps
+    got = frame()
+    torch.cuda.synchronize()
+    err = ((got.float() - ref.float()).abs().max() / ref.float().abs().max()).item()
+    errs = torch.tensor([err], device=dev)
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    timeouts = torch.tensor([qie_b200.lib().qie_peer_barrier_timeouts()], device=dev)
+    dist.all_reduce(timeouts, op=dist.ReduceOp.MAX)
+    fwd = 2 * STEPS_PER_IMAGE // branches        # forwards each rank takes part in
+    xbytes = 0
+    prof = None
+    if layout.sp_size > 1:
+        plan = qie_b200.make_shard_plan(N_IMG_TOK, T_TXT, layout.sp_size, layout.sp_rank)
+        xbytes = fwd * qie_b200.exchange_bytes_per_forward(plan, 1, cfg.num_attention_heads, cfg.num_layers)
+        # where the time of a sequence-parallel forward goes on this rank: per-class CUDA events of eager launches (no graph)
+        model.profile(True)
+        frame()
+        torch.cuda.synchronize()
+        tl = model.read_timeline(8192)
+        pr = model.read_profile()
+        t0 = time.perf_counter()
+        frame()
+        torch.cuda.synchronize()
+        eager_ms = (time.perf_counter() - t0) * 1e3
+        model.read_profile()
+        model.profile(False)
+        busy = sum(v["ms"] for v in pr.values())
+        span = max((a + d for a, d, _ in tl), default=0.0)
+        prof = {"per_frame_ms": {k: round(v["ms"], 3) for k, v in pr.items()}, "launches": {k: v["launches"] for k, v in pr.items()},
+                "kernel_busy_ms": round(busy, 3), "eager_frame_ms_host_clock": round(eager_ms, 3),
+                "first_to_last_launch_ms": round(span, 3),
+                "note": "rank 0, one frame launched eagerly with an event pair around every launch (the timed frames replay CUDA "
+                        "graphs); barrier = time inside peer_barrier_kernel = waiting for the slowest rank + NVLink flag round trip"}
+    if branches == 2:
+        xbytes += STEPS_PER_IMAGE * N_NOISE * 64 * 2         # the velocity all-gather of the CFG pair (NCCL, 512 KB per step)
+    rec.update({"ms_per_frame": ms, "efficiency_vs_n1": n1_ms / (world * ms), "speedup_vs_n1": n1_ms / ms,
+                "parity_err": float(errs.item()), "parity_tolerance": 0.0 if sp == 1 else 1e-2,
+                "barrier_timeouts": int(timeouts.item()), "exchange_bytes": int(xbytes),
+                "exchange_bytes_note": "bytes ONE rank stores into other GPUs' memory per frame (epilogue peer stores over NVLink "
+                                       "+ the CFG-pair velocity all-gather)", "profile": prof})
+    if hasattr(runner, "close"):
+        runner.close()
+    bad = rec["parity_err"] > rec["parity_tolerance"] or rec["barrier_timeouts"] != 0 or not (rec["parity_err"] == rec["parity_err"])
+    if bad:
+        rec["failed"] = "parity or barrier check failed"
+    return rec
 
 
 # ------------------------------------------------------------------------------------------------
@@ -266,8 +374,6 @@ def run_ours(args):
         model.set_precision(args.precision)
     if args.attn_variant:
         model.set_option(1, args.attn_variant)
-    if os.environ.get("QIE_FUSE_LN"):       # A/B: adaLN fused into the gated-residual GEMM launches (qie_set_option key 3)
-        model.set_option(3, int(os.environ["QIE_FUSE_LN"]))
     for env, key in (("QIE_L2_HINTS", 2), ("QIE_LN_VARIANT", 3), ("QIE_SPLIT_TAIL", 4), ("QIE_GROUP_M", 5), ("QIE_PDL", 7)):   # A/B switches (qie_tune keys)
         if os.environ.get(env):
             qie_b200.lib().qie_tune(key, int(os.environ[env]))
@@ -374,21 +480,33 @@ def run_ours(args):
     prof = model.read_profile()
     model.profile(False)
     sus, burst, hbm, which = peaks()
-    traffic = None      # dram__bytes_read.sum + dram__bytes_write.sum per gemm_kernel launch, from the committed ncu capture
-    tp = ROOT / "profiles" / "r01_gemm_traffic.json"
+    # dram__bytes_read.sum + dram__bytes_write.sum per gemm_kernel launch: from the ncu --set full capture of THIS round's build
+    # (profiles/r02_gemm_traffic.json names the commit it was taken from); null when no capture of the current kernels exists
+    traffic, traffic_src = None, None
+    tp = ROOT / "profiles" / "r02_gemm_traffic.json"
     if tp.exists() and args.precision == "bf16":
-        traffic = json.loads(tp.read_text()).get("gemm_kernel_avg_dram_bytes_per_launch")
+        tj = json.loads(tp.read_text())
+        traffic, traffic_src = tj.get("gemm_kernel_avg_dram_bytes_per_launch"), tj.get("source")
     gm, at = prof["gemm"], prof["attention"]
     gemm_tf = gm["work"] / (gm["ms"] * 1e-3) / 1e12 if gm["ms"] else 0.0
     attn_tf = at["work"] / (at["ms"] * 1e-3) / 1e12 if at["ms"] else 0.0
     tot_ms = sum(v["ms"] for v in prof.values())
     roofline = {"bound": "tensor", "kernel": f"gemm_kernel (tcgen05 {args.precision}, all linears of the step)",
                 "achieved": gemm_tf, "peak": sus, "unit": "TFLOP/s", "frac": gemm_tf / sus, "traffic": traffic,
-                "traffic_note": "bytes per launch averaged over the 4 per-block GEMM shapes, ncu --set full (profiles/r01_gemm_traffic.json); "
-                                "algorithmic operand+output bytes average 420 MB per launch",
+                "traffic_note": "bytes per launch averaged over the 4 per-block GEMM shapes, ncu --set full "
+                                f"({traffic_src or 'no capture of this build'}); algorithmic operand+output bytes average 420 MB per launch",
                 "peak_source": f"{which} bf16_tflops_sustained (kernel timed inside a long step); burst {burst}",
                 "launches_per_step": gm["launches"] / args.steps, "avg_launch_ms": gm["ms"] / max(gm["launches"], 1),
                 "share_of_step": gm["ms"] / tot_ms if tot_ms else None,
+                # the other kernel classes at the top level too (same live event timing; attention against the same tensor peak,
+                # adaLN / modulation GEMV against the measured HBM copy peak)
+                "attention_achieved": attn_tf, "attention_frac": attn_tf / sus, "attention_frac_of_burst": attn_tf / burst,
+                "attention_share_of_step": at["ms"] / tot_ms if tot_ms else None,
+                "adaln_achieved_gbs": prof["adaln"]["work"] / (prof["adaln"]["ms"] * 1e-3) / 1e9 if prof["adaln"]["ms"] else 0,
+                "adaln_frac": (prof["adaln"]["work"] / (prof["adaln"]["ms"] * 1e-3) / 1e9 / hbm) if prof["adaln"]["ms"] else 0,
+                "adaln_share_of_step": prof["adaln"]["ms"] / tot_ms if tot_ms else None,
+                "mod_gemv_frac": (prof["mod_gemv"]["work"] / (prof["mod_gemv"]["ms"] * 1e-3) / 1e9 / hbm) if prof["mod_gemv"]["ms"] else 0,
+                "frac_of_burst": gemm_tf / burst,
                 "attention": {"achieved": attn_tf, "frac": attn_tf / sus, "share_of_step": at["ms"] / tot_ms if tot_ms else None,
                               "avg_launch_ms": at["ms"] / max(at["launches"], 1)},
                 "adaln": {"achieved_gbs": prof["adaln"]["work"] / (prof["adaln"]["ms"] * 1e-3) / 1e9 if prof["adaln"]["ms"] else 0,
@@ -397,6 +515,16 @@ def run_ours(args):
                              "peak_gbs": hbm, "share_of_step": prof["mod_gemv"]["ms"] / tot_ms if tot_ms else None},
                 "event_sum_ms_per_step": tot_ms / args.steps,      # sum of the per-kernel event intervals; the rest of ms_per_step is inter-kernel gaps
                 "step_tflops": STEPS_PER_IMAGE * (2 if args.cfg else 1) * flops_per_forward(args.layers) / (ms_step * 1e-3) / 1e12}
+
+    strong = None
+    if args.mode == "dp" and not args.no_strong and args.precision == "bf16" and args.workload == "1024x1ref" and not args.cache:
+        strong = strong_leg(args, model, dev, world, rank, timed)
+
+    eager = None
+    if rank == 0 and world == 1 and not args.no_eager_baseline and args.workload == "1024x1ref":
+        e = run_eager_gpu(args, emit=False, min_ms=2000.0)
+        eager = {"ms_per_forward": e["dit_forward_ms"], "value": e["value"], "unit": UNIT, "sample": e["sample"],
+                 "clocks": e["clocks"], "speedup_of_this_repo": e["ms_per_step"] / ms_step}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -417,10 +545,14 @@ def run_ours(args):
                 "e2e": {"value": frames * 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "dit_forward_ms": ms_step / (STEPS_PER_IMAGE * (2 if args.cfg else 1))}
+                "dit_forward_ms": ms_step / (STEPS_PER_IMAGE * (2 if args.cfg else 1)),
+                "strong": strong, "gpu_eager_baseline": eager}
         print(json.dumps(line), flush=True)
+    failed = bool(strong and strong.get("failed"))
     if world > 1:
         dist.destroy_process_group()
+    if failed:
+        raise SystemExit(1)
 
 
 def main():
@@ -441,6 +573,8 @@ def main():
     ap.add_argument("--fused", action="store_true", help="ulysses modes: exchange q|k|v and the attention output through "
                     "epilogue stores into peer memory (NVLink) instead of NCCL all-to-alls")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (ONE true-CFG frame over all ranks)")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the bf16 PyTorch-eager GPU side baseline (N = 1)")
     ap.add_argument("--workload", default="1024x1ref", choices=["1024x1ref", "512x2ref"],
                     help="1024x1ref = the headline (BASELINE configs[1]); 512x2ref = one frame of configs[4]: 512x512, two "
                          "reference images (3072 image tokens), 448 text tokens, 4 steps (use with --cfg)")

@@ -15,6 +15,10 @@
  *     no entry point synchronises the device in the steady state, none allocates inside
  *     qie_forward (CUDA-graph capturable).
  *   - the library never frees caller memory; caller keeps weights/workspace alive.
+ *   - threading: a handle (its timestep / modulation buffers) and a workspace serve ONE forward at a time; concurrent
+ *     forwards (cond / uncond on two streams, README.md:127-128) take one handle + workspace per stream.  Kernel-internal
+ *     scratch (row counters, split-K partials) is kept per (device, stream), so launches on different streams never share
+ *     mutable state; at most 8 distinct streams per device are served (QIE_ESTATE beyond).
  *   - sm_100a only: on any other device qie_create returns QIE_EARCH.  There is no CPU path.
  *
  * Joint sequence layout used by all per-token entry points ("qie_seq"):
@@ -113,19 +117,22 @@ int qie_set_weights(qie_handle* h, const qie_weights* w);
  * cublaslt_int8.py / triton_int8_gemm.py named at README.md:136-141 */
 int qie_set_precision(qie_handle* h, int mode);
 /* tuning/debug knobs outside the reference surface: key 0 = fuse QK-norm+RoPE into the QKV GEMM epilogue (default 1),
- * key 1 = attention kernel variant, key 2 = record CUDA events around every kernel class inside qie_forward,
- * key 3 = run the adaLN that follows out-proj / FF-down in the tail of that GEMM launch (default 0; whole-forward calls) */
+ * key 1 = attention kernel variant, key 2 = record CUDA events around every kernel class inside qie_forward */
 int qie_set_option(qie_handle* h, int key, int value);
 /* measurement aids: kernels launched by the library so far; event-timed ms / algorithmic work / launches per kernel
- * class since the last read (class 0 GEMM [FLOP], 1 attention [FLOP], 2 adaLN [bytes], 3 modulation GEMV [bytes], 4 other) */
+ * class since the last read (class 0 GEMM [FLOP], 1 attention [FLOP], 2 adaLN [bytes], 3 modulation GEMV [bytes], 4 other,
+ * 5 peer barrier); arrays of QIE_PROFILE_CLASSES entries.  qie_profile_timeline lists the launches recorded since the last
+ * qie_profile_read (start offset from the first one, duration, class) without consuming them. */
+#define QIE_PROFILE_CLASSES 6
 unsigned long long qie_launch_count(void);
 /* process-wide experiment / launch knobs: 0 adaLN threads/block, 1 adaLN smem reservation, 2 GEMM L2 hints (bit 0 weights
- * evict-last, bit 1 activations evict-first), 3 adaLN kernel form, 4 GEMM split-K tail, 5 GEMM raster band, 6 fused-adaLN
- * timing experiments, 7 programmatic dependent launch of the GEMM / attention / adaLN kernels (0 off, 1 on).
+ * evict-last, bit 1 activations evict-first), 3 adaLN kernel form, 4 GEMM split-K tail, 5 GEMM raster band,
+ * 7 programmatic dependent launch of the GEMM / attention / adaLN kernels (0 off, 1 on).
  * qie_tune_get returns the current value (>= 0) or QIE_EINVAL for an unknown key. */
 int qie_tune(int key, int value);
 int qie_tune_get(int key);
-int qie_profile_read(qie_handle* h, double* ms5, double* work5, int* launches5);
+int qie_profile_read(qie_handle* h, double* ms, double* work, int* launches);
+int qie_profile_timeline(qie_handle* h, float* start_ms, float* dur_ms, int* cls, int max_n);
 /* host helper: pad a (img_rows, txt_rows) pair into the joint layout */
 int qie_make_seq(int batch, int img_rows, int txt_rows, qie_seq* out);
 size_t qie_workspace_bytes(const qie_handle* h, const qie_seq* seq);
@@ -172,30 +179,52 @@ int qie_attn_fwd_tiles(const void* qkv, void* out, int n_tiles, const int* tile_
  *   - the QKV GEMM epilogue (RMSNorm + RoPE applied) writes head group g of q|k|v into rank g's gathered buffer
  *     qkv_gather[g] [size*rows_pad, 3*(H/size)*128] at row (my_rank*rows_pad + local row);
  *   - the attention epilogue of rank g writes its heads' output for the tokens of rank s into attn_out[s] [rows_pad, H*128].
+ *   - the END phase stores the rank's velocity rows into every rank's velocity buffer vel[s] [batch, img_total, out_dim].
  * The only synchronisation left is qie_peer_barrier between the phases (one flag store per peer + one spin per peer).
  * Buffers must be peer-accessible: allocate them with qie_peer_alloc and exchange the 64-byte handles between the
  * ranks (torch.distributed all_gather of bytes), map with qie_peer_open.  Single-GPU emulation (tests): point the
  * tables at local buffers of the emulated ranks and run the ranks' phases one after the other, without the barrier. */
 typedef struct qie_peers {
     int rank, size;          /* my rank in the sequence-parallel group, group size (2..8, divides num_heads) */
-    int rows_pad;            /* img_pad + txt_pad of a token shard (identical on every rank) */
-    void* qkv_gather[8];     /* rank g's gathered q|k|v buffer (peer-mapped device pointers; [rank] is my own) */
+    int batch;               /* frames per forward (all of them stay inside the group) */
+    int img_pad, txt_pad;    /* padded rows of ONE rank's image / text shard as qie_sp_shard returns them (identical on every rank) */
+    int img_total, txt_total;/* tokens of the whole (unsharded) sequence of one frame */
+    void* qkv_gather[8];     /* rank g's gathered q|k|v buffer bf16 [batch][size*img_pad + pad128(txt_total)][3*(H/size)*128]:
+                              * image shard of rank r at rows [r*img_pad, ...), ALL text tokens contiguous behind the image shards
+                              * (the gathered sequence is as long as the single-GPU one: no per-rank text padding inside it) */
     void* attn_out[8];       /* rank s's attention-output buffer = its workspace + qie_workspace_offset(..., 1) */
-    const int* tile_valid;   /* device int[size*rows_pad/128]: valid rows of every 128-row tile of the gathered sequence */
+    void* vel[8];            /* rank s's velocity buffer bf16 [batch][img_total][out_dim]: every rank receives all rows */
+    void* flags[8];          /* rank s's barrier words: 16 zero-initialised uint32 ([0..7] arrivals, [8] its barrier count) */
 } qie_peers;
-/* installs (or with NULL removes) the peer tables used by the QKV and ATTN phases of qie_forward_phase on `stream` */
+/* installs (or with NULL removes) the peer tables of ONE geometry (batch, img_total, txt_total); call it again whenever the
+ * geometry of the next forward differs (cheap: host-side, the tile list of each geometry is built once and kept).  A forward whose
+ * seq / sp do not match the installed geometry returns QIE_ESTATE.  qie_set_peers(h, NULL, ...) returns QIE_ECUDA (once) if a
+ * barrier of the dissolved group had timed out. */
 int qie_set_peers(qie_handle* h, const qie_peers* peers, void* stream);
+/* host helper: token shard of `rank` (image and text tokens each split contiguously, the first total % size ranks own one
+ * more) -> local layout + placement; QIE_ESHAPE when a rank would own an all-padding 128-row tile */
+int qie_sp_shard(int batch, int img_total, int txt_total, int size, int rank, qie_seq* seq_out, qie_sp* sp_out);
+/* host helper: valid rows of every 128-row tile of the gathered sequence; returns the tile count */
+int qie_sp_tile_valid_host(int img_total, int txt_total, int size, int* out_host, int max_tiles);
 /* cudaMalloc'ed, zero-filled, IPC-exportable device buffer; handle_out receives the 64-byte cudaIpcMemHandle_t */
 int qie_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle_out64);
 int qie_peer_free(void* dev_ptr);
 /* maps a buffer exported by another process of this node (enables peer access to its device on first use) */
 int qie_peer_open(const unsigned char* handle64, void** dev_ptr);
 int qie_peer_close(void* dev_ptr);
-/* all-ranks barrier on `stream` with system-scope release/acquire: flags[r] is rank r's array of 8 uint32 (peer-mapped,
- * zero-initialised); every call must use epoch = previous epoch + 1 (starting at 1) on every rank.  The kernel gives up
- * (sets a sticky error, see qie_peer_barrier_timeouts) after ~2 s instead of hanging the GPU. */
-int qie_peer_barrier(void* const* flags_host /* [size] */, int rank, int size, unsigned epoch, void* stream);
+/* all-ranks barrier of the installed group on `stream`, system-scope release/acquire over the ranks' flag words.  The epoch
+ * lives in device memory (flags[rank][8]) and is advanced by the kernel itself, so the launch is replayable from a CUDA graph;
+ * every rank must execute the same sequence of barriers.  A barrier that waits longer than ~2 s gives up and raises a sticky,
+ * process-wide error: every later qie_forward / qie_forward_phase / qie_forward_sp returns QIE_ECUDA (see qie_last_error). */
+int qie_peer_barrier(qie_handle* h, void* stream);
+/* 0, or 1 once a barrier has timed out (read from mapped host memory: no stream is synchronised) */
 int qie_peer_barrier_timeouts(void);
+/* The whole sequence-parallel forward of this rank as ONE call (peers installed): BEGIN, per block QKV -> barrier -> ATTN ->
+ * barrier -> POST, END -> barrier; `out_full` bf16 [batch, img_total, out_dim] receives the velocity of ALL tokens (every rank's
+ * END stores its rows into every rank's `vel` buffer).  No allocation, no host synchronisation: CUDA-graph capturable. */
+int qie_forward_sp(qie_handle* h, const void* hidden_local, const void* enc_local, const float* timestep,
+                   const int* img_shapes_host, int n_img, const qie_seq* seq, const qie_sp* sp, void* out_full,
+                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- exact caches ("next" row N1): replaces cached_pipeline_v2.py (README.md:125) and the
  * precompute_conditions stub of qwen_realtime.py:140-165.  temb, every block's modulation vectors and the final
@@ -261,31 +290,24 @@ typedef struct qie_gemm_args {
     const float* w_scale[2];
     int block_n;              /* 0 = auto */
     int cta_group;            /* 0 = auto, 1 = one CTA per 128-row tile, 2 = CTA pair per 256-row tile (tcgen05 cta_group::2) */
-    /* QKV_NORM_ROPE only, batch 1: scatter the output over the sequence-parallel group instead of writing `out`
-     * (see qie_peers): peer_out = DEVICE array of sp_size pointers to the ranks' gathered buffers */
+    /* QKV_NORM_ROPE only: scatter the output over the sequence-parallel group instead of writing `out` (see qie_peers):
+     * peer_out = DEVICE array of sp_size pointers to the ranks' gathered buffers [batch][sp_gathered_rows][3*(H/sp_size)*128];
+     * a valid image row i of batch b goes to row b*sp_gathered_rows + sp_rank*img_pad + i, a valid text row i to row
+     * b*sp_gathered_rows + sp_txt_row0 + i (sp_txt_row0 = sp_size*img_pad + first text token of this rank) */
     void* const* peer_out;
-    int sp_rank, sp_size, sp_rows;
-    /* GATE_RESID only, N == ldo (the output rows are whole residual rows): fuse the LayerNorm + modulate that follows
-     * (qie_ln_modulate with the same arguments) into the tail of this launch — warps that have run out of tiles normalise
-     * the rows of every 256-row unit as soon as all of its n-blocks have been added.  ln_out NULL = off. */
-    void* ln_out;             /* bf16 [rows, N] */
-    void* ln_out8;            /* optional e4m3 / int8 copy + per-row scale, as qie_ln_modulate */
-    float* ln_out_scale;
-    const float* ln_mod;
-    long long ln_mod_bstride, ln_mod_sstride;
-    int ln_shift_off, ln_scale_off, ln_qmode;
-    float ln_eps;
+    int sp_rank, sp_size, sp_gathered_rows, sp_txt_row0;
+    /* GELU_BF16 / BF16 epilogues feeding an 8-bit GEMM (fp8 / int8 modes): when q8_amax is set the epilogue also folds
+     * max|out| of every output row into q8_amax[row] (fp32, atomicMax on the bit pattern; the caller zeroes it) so that the
+     * per-token quantiser that follows needs no separate max pass */
+    float* q8_amax;
 } qie_gemm_args;
 int qie_gemm(const qie_gemm_args* args, const qie_seq* seq, void* stream);
 
 /* joint attention over all valid rows of each batch element; qkv bf16 [rows, 3*H*128] (q|k|v), q and k already
  * normed + roped; out bf16 [rows, H*128].  replaces F.scaled_dot_product_attention in
- * QwenDoubleStreamAttnProcessor2_0. variant: 0 default. */
+ * QwenDoubleStreamAttnProcessor2_0. variant: 0 = tuned default (CTA-pair kernel); 0x8 selects the single-CTA
+ * fallback kernel; bits 4..7 = how many of every 8 score pairs use the FMA-pipe polynomial exp2 (0x100 = none, 2, 3, 4). */
 int qie_attn_fwd(const void* qkv, void* out, const qie_seq* seq, int num_heads, int variant, void* stream);
-/* Timing experiment (not part of the reference surface): device buffer of 2*5*32*8 uint64 that the trace build of the
- * attention kernel (variant 0x804) fills with per-role clock64 stamps of one CTA pair; NULL disables. */
-int qie_attn_set_trace(void* dev_buf);
-
 /* LayerNorm(no affine, eps) + x*(1+scale)+shift; x fp32 [rows, D] -> out bf16 [rows, D].
  * shift/scale for (b, stream) at mod[b*mod_bstride + stream*mod_sstride + {shift_off,scale_off} + c].
  * if out8/out_scale non-NULL also emits e4m3 rows with per-row scale (for the FP8 GEMMs). */

@@ -5,4 +5,4 @@ from .pipeline import (StreamingDenoiser, cfg_euler_step, flowmatch_sigmas, mode
                        unpack_latents)
 from .parallel import (ParallelLayout, ShardPlan, UlyssesTransformer, exchange_velocities, make_layout, make_shard_plan,  # noqa: F401
                        pack_heads, run_denoise_parallel, split_sizes, unpack_heads, emulate_fused_ulysses, PeerRankBuffers, make_peers, scatter_qkv_reference,
-                       scatter_attn_reference)
+                       scatter_attn_reference, exchange_bytes_per_forward)

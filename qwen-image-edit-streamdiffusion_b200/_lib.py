@@ -65,15 +65,17 @@ class GemmArgs(C.Structure):
                 ("gate", C.c_void_p), ("gate_bstride", C.c_longlong), ("gate_sstride", C.c_longlong),
                 ("rope", C.c_void_p), ("qk_norm_w", (C.c_void_p * 2) * 2),
                 ("fp8", C.c_int), ("a_scale", C.c_void_p), ("w_scale", _P2), ("block_n", C.c_int), ("cta_group", C.c_int),
-                ("peer_out", C.c_void_p), ("sp_rank", C.c_int), ("sp_size", C.c_int), ("sp_rows", C.c_int),
-                ("ln_out", C.c_void_p), ("ln_out8", C.c_void_p), ("ln_out_scale", C.c_void_p), ("ln_mod", C.c_void_p),
-                ("ln_mod_bstride", C.c_longlong), ("ln_mod_sstride", C.c_longlong), ("ln_shift_off", C.c_int),
-                ("ln_scale_off", C.c_int), ("ln_qmode", C.c_int), ("ln_eps", C.c_float)]
+                ("peer_out", C.c_void_p), ("sp_rank", C.c_int), ("sp_size", C.c_int), ("sp_gathered_rows", C.c_int),
+                ("sp_txt_row0", C.c_int), ("q8_amax", C.c_void_p)]
 
 
 class Peers(C.Structure):
-    _fields_ = [("rank", C.c_int), ("size", C.c_int), ("rows_pad", C.c_int), ("qkv_gather", C.c_void_p * 8),
-                ("attn_out", C.c_void_p * 8), ("tile_valid", C.c_void_p)]
+    _fields_ = [("rank", C.c_int), ("size", C.c_int), ("batch", C.c_int), ("img_pad", C.c_int), ("txt_pad", C.c_int),
+                ("img_total", C.c_int), ("txt_total", C.c_int), ("qkv_gather", C.c_void_p * 8), ("attn_out", C.c_void_p * 8),
+                ("vel", C.c_void_p * 8), ("flags", C.c_void_p * 8)]
+
+
+PROFILE_CLASSES = 6
 
 
 EPI_BF16, EPI_GELU_BF16, EPI_F32, EPI_GATE_RESID_F32, EPI_QKV_NORM_ROPE = range(5)
@@ -93,6 +95,7 @@ SYMBOLS = {
     "qie_tune": (_i, [_i, _i]),
     "qie_tune_get": (_i, [_i]),
     "qie_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i)]),
+    "qie_profile_timeline": (_i, [_vp, C.POINTER(_f), C.POINTER(_f), C.POINTER(_i), _i]),
     "qie_make_seq": (_i, [_i, _i, _i, C.POINTER(Seq)]),
     "qie_workspace_bytes": (C.c_size_t, [_vp, C.POINTER(Seq)]),
     "qie_forward": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_i), _i, C.POINTER(Seq), _vp, _vp, C.c_size_t, _i, _vp]),
@@ -105,8 +108,11 @@ SYMBOLS = {
     "qie_peer_free": (_i, [_vp]),
     "qie_peer_open": (_i, [C.c_char_p, C.POINTER(_vp)]),
     "qie_peer_close": (_i, [_vp]),
-    "qie_peer_barrier": (_i, [C.POINTER(_vp), _i, _i, C.c_uint, _vp]),
+    "qie_peer_barrier": (_i, [_vp, _vp]),
     "qie_peer_barrier_timeouts": (_i, []),
+    "qie_sp_shard": (_i, [_i, _i, _i, _i, _i, C.POINTER(Seq), C.POINTER(Sp)]),
+    "qie_sp_tile_valid_host": (_i, [_i, _i, _i, C.POINTER(_i), _i]),
+    "qie_forward_sp": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_i), _i, C.POINTER(Seq), C.POINTER(Sp), _vp, _vp, C.c_size_t, _vp]),
     "qie_cache_schedule": (_i, [_vp, C.POINTER(_f), _i, _vp]),
     "qie_cache_prompt": (_i, [_vp, _i, _vp, _i, _vp]),
     "qie_cache_select": (_i, [_vp, C.POINTER(_i), _i, _i]),
@@ -117,7 +123,6 @@ SYMBOLS = {
     "qie_rope_table_host": (_i, [C.POINTER(ModelCfg), C.POINTER(_i), _i, C.POINTER(Seq), C.POINTER(_f)]),
     "qie_gemm": (_i, [C.POINTER(GemmArgs), C.POINTER(Seq), _vp]),
     "qie_attn_fwd": (_i, [_vp, _vp, C.POINTER(Seq), _i, _i, _vp]),
-    "qie_attn_set_trace": (_i, [_vp]),
     "qie_ln_modulate": (_i, [_vp, _vp, _ll, _ll, _i, _i, _vp, _vp, _vp, _i, _i, _f, C.POINTER(Seq), _vp]),
     "qie_gemv": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp]),
     "qie_timestep_proj": (_i, [_vp, _vp, _i, _i, _vp]),

@@ -73,11 +73,65 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 }
 
 int unpack_rows(const void* x, void* out, int batch, int n, int n_pad, int C, cudaStream_t st);
-int ln_counters(int** out);
-int gemm_split_buffers(float** scratch_out, int** tickets_out);
-int gemm_ln_sync(int** out);
-int attn_fwd_peers(const void* qkv_gathered, void* const* peer_out_dev, int n_tiles, const int* tile_valid_dev, int heads_local,
-                   int sp_rows, int out_ld, int head_off, void* stream);
+int attn_fwd_peers(const void* qkv_gathered, void* const* peer_out_dev, const qie_peers* pr, const int* tile_valid_dev,
+                   int heads_local, int out_ld, void* stream);
+int peer_bcast_rows(const void* src, void* const* peer_vel_dev, const qie_peers* pr, int img_rows, int img_offset, int C,
+                    cudaStream_t st);
+int peer_barrier_launch(const qie_peers* pr, cudaStream_t st);
+
+// ---- per-(device, stream) kernel scratch (common.cuh) ----
+namespace {
+struct ScratchPool {
+    bool ready = false;
+    StreamScratch set[QIE_SCRATCH_SETS];
+    cudaStream_t owner[QIE_SCRATCH_SETS];
+    int used = 0;
+};
+ScratchPool g_pool[64];
+std::mutex g_pool_mu;
+}  // namespace
+
+int stream_scratch_reserve() {
+    int dev = 0;
+    QIE_CUDA_OK(cudaGetDevice(&dev));
+    QIE_REQUIRE(dev >= 0 && dev < 64, QIE_EINVAL, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    ScratchPool& p = g_pool[dev];
+    if (p.ready) return QIE_OK;
+    for (int i = 0; i < QIE_SCRATCH_SETS; ++i) {
+        QIE_CUDA_OK(cudaMalloc(&p.set[i].ln_counters, 2 * sizeof(int)));
+        QIE_CUDA_OK(cudaMemset(p.set[i].ln_counters, 0, 2 * sizeof(int)));
+        QIE_CUDA_OK(cudaMalloc(&p.set[i].split_scratch, (size_t)SPLIT_SCRATCH_TILES * 256 * 256 * sizeof(float)));
+        QIE_CUDA_OK(cudaMalloc(&p.set[i].split_tickets, SPLIT_SCRATCH_TILES * 8 * sizeof(int)));
+        QIE_CUDA_OK(cudaMemset(p.set[i].split_tickets, 0, SPLIT_SCRATCH_TILES * 8 * sizeof(int)));
+    }
+    p.ready = true;
+    return QIE_OK;
+}
+
+int stream_scratch(cudaStream_t st, StreamScratch* out) {
+    int dev = 0;
+    QIE_CUDA_OK(cudaGetDevice(&dev));
+    QIE_REQUIRE(dev >= 0 && dev < 64, QIE_EINVAL, "device index %d out of range", dev);
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        ScratchPool& p = g_pool[dev];
+        if (p.ready) {
+            for (int i = 0; i < p.used; ++i)
+                if (p.owner[i] == st) { *out = p.set[i]; return QIE_OK; }
+            QIE_REQUIRE(p.used < QIE_SCRATCH_SETS, QIE_ESTATE,
+                        "libqie kernels were launched on more than %d distinct streams of device %d (one scratch set per stream)",
+                        QIE_SCRATCH_SETS, dev);
+            p.owner[p.used] = st;
+            *out = p.set[p.used++];
+            return QIE_OK;
+        }
+    }
+    // per-kernel entry points used without a handle on this device (unit tests): allocate the pool now (not capturable)
+    int rc = stream_scratch_reserve();
+    if (rc) return rc;
+    return stream_scratch(st, out);
+}
 
 // -------------------------------------------------------------------------------------------
 // model handle
@@ -91,8 +145,6 @@ struct qie_handle {
     bool has_weights;
     int precision;   // 0 bf16, 1 fp8
     int fuse_qk;     // 1: RMSNorm+RoPE in the QKV GEMM epilogue, 0: standalone kernel
-    int fuse_ln = 0; // 1: the adaLN after out-proj / FF-down runs in the tail of that GEMM launch (whole-forward calls only);
-                     // bit-identical and parity-tested, measured break-even (151.1 vs 151.0 ms per forward) -> off by default
     int attn_variant;
     qie_weights w;
     std::vector<qie_block_weights> blocks;
@@ -110,11 +162,16 @@ struct qie_handle {
     int prompt_rows[4] = {0, 0, 0, 0};
     int sel_sched[8] = {-1, -1, -1, -1, -1, -1, -1, -1};         // per batch row, -1 = compute
     int sel_prompt = -1;
-    // fused Ulysses exchange (qie_set_peers): host copy + device table [0..7] qkv_gather, [8..15] attn_out
+    // fused Ulysses exchange (qie_set_peers): host copy + device table [0..7] qkv_gather, [8..15] attn_out, [16..23] vel
     bool has_peers = false;
     qie_peers peers{};
     void** d_peer_tab = nullptr;
-    // optional per-kernel-class CUDA-event timing (bench.py roofline): class 0 gemm, 1 attention, 2 adaLN, 3 gemv, 4 other
+    void* peer_tab_host[24] = {};            // what d_peer_tab holds (re-uploaded only when an address changes)
+    const int* d_tile_valid = nullptr;       // valid rows per 128-row tile of the gathered sequence of the installed geometry
+    struct TileEntry { int img_total, txt_total, size; int* d; };
+    std::vector<TileEntry> tile_cache;       // one list per geometry, kept until qie_destroy (captured graphs point at them)
+    // optional per-kernel-class CUDA-event timing (bench.py roofline): class 0 gemm, 1 attention, 2 adaLN, 3 gemv, 4 other,
+    // 5 peer barrier (sequence-parallel forward)
     int profile;
     struct Prof { int cls; cudaEvent_t a, b; double work; };
     std::vector<Prof> prof;
@@ -146,14 +203,17 @@ extern "C" int qie_make_seq(int batch, int img_rows, int txt_rows, qie_seq* out)
 // FlowMatchEulerDiscreteScheduler.set_timesteps(sigmas=linspace(1, 1/N, N), mu=calculate_shift(seq)) with the
 // Qwen-Image scheduler config (dynamic exponential shifting, shift_terminal 0.02)  — SURVEY A.8
 extern "C" int qie_flowmatch_sigmas(int num_steps, int image_seq_len, float* s) {
-    QIE_REQUIRE(s && num_steps >= 1 && image_seq_len > 0, QIE_EINVAL, "qie_flowmatch_sigmas: bad argument");
+    QIE_REQUIRE(s && image_seq_len > 0, QIE_EINVAL, "qie_flowmatch_sigmas: bad argument");
+    // one step: the stretch to the terminal sigma is (1 - s) / ((1 - s_last) / 0.98) with s = s_last = 1 -> 0 / 0 = NaN timesteps
+    // in the reference scheduler (no error there); refuse instead of returning NaN
+    QIE_REQUIRE(num_steps >= 2, QIE_EINVAL, "qie_flowmatch_sigmas: the dynamic-shift schedule needs at least 2 steps (got %d)",
+                num_steps);
     const double m = (0.9 - 0.5) / (8192.0 - 256.0), b = 0.5 - m * 256.0;
     const double mu = image_seq_len * m + b, emu = exp(mu);
     std::vector<double> sig(num_steps);
     for (int i = 0; i < num_steps; ++i) {
         // np.linspace(1, 1/N, N) in float32
-        const float lin = num_steps == 1 ? 1.0f
-                                         : (float)(1.0 + (double)i * ((1.0 / num_steps - 1.0) / (num_steps - 1)));
+        const float lin = (float)(1.0 + (double)i * ((1.0 / num_steps - 1.0) / (num_steps - 1)));
         sig[i] = emu / (emu + (1.0 / (double)lin - 1.0));
     }
     const double scale = (1.0 - sig[num_steps - 1]) / (1.0 - 0.02);
@@ -222,11 +282,8 @@ extern "C" int qie_create(const qie_model_cfg* cfg, int device, qie_handle** out
     QIE_REQUIRE(prop.major == 10, QIE_EARCH, "qie_create: device %d is sm_%d%d, this library is sm_100a only", device,
                 prop.major, prop.minor);
     QIE_CUDA_OK(cudaSetDevice(device));
-    {   // process-wide kernel scratch: allocate now, so that qie_forward stays allocation-free (CUDA-graph capturable)
-        int* c = nullptr; float* sc = nullptr; int* tk = nullptr;
-        int rc0 = ln_counters(&c);
-        if (!rc0) rc0 = gemm_split_buffers(&sc, &tk);
-        if (!rc0) rc0 = gemm_ln_sync(&tk);
+    {   // kernel scratch pool of this device: allocate now, so that qie_forward stays allocation-free (CUDA-graph capturable)
+        int rc0 = stream_scratch_reserve();
         if (rc0) return rc0;
     }
     qie_handle* h = new qie_handle();
@@ -258,6 +315,7 @@ extern "C" int qie_destroy(qie_handle* h) {
     cudaFree(h->d_sched_mod);
     cudaFree(h->d_sched_fin);
     cudaFree(h->d_peer_tab);
+    for (auto& e : h->tile_cache) cudaFree(e.d);
     for (float* p : h->d_prompt) cudaFree(p);
     for (auto& p : h->prof) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -306,7 +364,6 @@ extern "C" int qie_set_option(qie_handle* h, int key, int value) {
     if (key == 0) h->fuse_qk = value;
     else if (key == 1) h->attn_variant = value;
     else if (key == 2) h->profile = value;
-    else if (key == 3) h->fuse_ln = value;
     else QIE_REQUIRE(false, QIE_EINVAL, "qie_set_option: unknown key %d", key);
     return QIE_OK;
 }
@@ -340,10 +397,25 @@ Ws carve(const qie_handle* h, const qie_seq* s) {
 
 extern "C" unsigned long long qie_launch_count(void) { return g_launches; }
 
-// sums the event-timed durations recorded since the last read; arrays of 5 classes (see qie_handle::profile)
+// per-launch timeline of the events recorded since the last read (does not consume them): start offset from the first recorded
+// launch and duration in ms, kernel class; returns the number of entries written (<= max_n) or a negative status
+extern "C" int qie_profile_timeline(qie_handle* h, float* start_ms, float* dur_ms, int* cls, int max_n) {
+    QIE_REQUIRE(h && start_ms && dur_ms && cls && max_n >= 0, QIE_EINVAL, "qie_profile_timeline: bad argument");
+    int n = 0;
+    for (auto& p : h->prof) {
+        if (n >= max_n) break;
+        QIE_CUDA_OK(cudaEventSynchronize(p.b));
+        QIE_CUDA_OK(cudaEventElapsedTime(&start_ms[n], h->prof.front().a, p.a));
+        QIE_CUDA_OK(cudaEventElapsedTime(&dur_ms[n], p.a, p.b));
+        cls[n++] = p.cls;
+    }
+    return n;
+}
+
+// sums the event-timed durations recorded since the last read; arrays of QIE_PROFILE_CLASSES classes (see qie_handle::profile)
 extern "C" int qie_profile_read(qie_handle* h, double* ms, double* work, int* launches) {
     QIE_REQUIRE(h && ms && work && launches, QIE_EINVAL, "qie_profile_read: null pointer");
-    for (int i = 0; i < 5; ++i) { ms[i] = 0; work[i] = 0; launches[i] = 0; }
+    for (int i = 0; i < QIE_PROFILE_CLASSES; ++i) { ms[i] = 0; work[i] = 0; launches[i] = 0; }
     for (auto& p : h->prof) {
         QIE_CUDA_OK(cudaEventSynchronize(p.b));
         float t = 0.f;
@@ -378,9 +450,10 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
                         const int* img_shapes_host, int n_img, const qie_seq* seq, const qie_sp* sp, void* out,
                         void* workspace, size_t workspace_bytes, int n_blocks, void* stream) {
     QIE_REQUIRE(h && seq && workspace, QIE_EINVAL, "qie_forward: null pointer");
+    if (int rc_sticky = peer_sticky_error()) return rc_sticky;   // a peer barrier of an earlier launch timed out
     if (phases & QIE_PHASE_BEGIN)
         QIE_REQUIRE(hidden && enc && timestep && img_shapes_host, QIE_EINVAL, "qie_forward: null input pointer");
-    if (phases & QIE_PHASE_END) QIE_REQUIRE(out, QIE_EINVAL, "qie_forward: null output pointer");
+    if (phases & QIE_PHASE_END) QIE_REQUIRE(out || h->has_peers, QIE_EINVAL, "qie_forward: null output pointer");
     QIE_REQUIRE(h->has_weights, QIE_ESTATE, "qie_forward: weights not set");
     QIE_REQUIRE(seq->batch >= 1 && seq->batch <= 8, QIE_ESHAPE, "qie_forward: batch must be 1..8");
     qie_seq chk;
@@ -423,20 +496,22 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
             // my head group over the gathered sequence of every rank; the epilogue stores each token's output into the
             // attention buffer of the rank that owns the token
             const qie_peers& pr = h->peers;
-            const int hl = h->cfg.num_heads / pr.size, n_tiles = pr.size * pr.rows_pad / 128;
-            const double S = (double)n_tiles * 128;
-            ProfScope ps(h, st, 1, 4.0 * S * S * 128.0 * hl);
-            return attn_fwd_peers(pr.qkv_gather[pr.rank], h->d_peer_tab + 8, n_tiles, pr.tile_valid, hl, pr.rows_pad, D,
-                                  pr.rank * hl, st);
+            const int hl = h->cfg.num_heads / pr.size;
+            const double S = (double)pr.img_total + pr.txt_total;
+            ProfScope ps(h, st, 1, 4.0 * S * S * 128.0 * hl * pr.batch);
+            return attn_fwd_peers(pr.qkv_gather[pr.rank], h->d_peer_tab + 8, &pr, h->d_tile_valid, hl, D, st);
         }
         const double S = seq->img_rows + seq->txt_rows;
         ProfScope ps(h, st, 1, 4.0 * S * S * 128.0 * h->cfg.num_heads * B);
         return qie_attn_fwd(qkv, attn, seq, h->cfg.num_heads, h->attn_variant, st);
     };
-    if (h->has_peers && (phases & (QIE_PHASE_QKV | QIE_PHASE_ATTN)))
-        QIE_REQUIRE(B == 1 && h->peers.rows_pad == rpb && h->fuse_qk && sp && sp->size == h->peers.size &&
-                        sp->rank == h->peers.rank,
-                    QIE_ESTATE, "qie_forward_phase: installed peers do not match this call (batch 1, same shard padding, same rank)");
+    if (h->has_peers && (phases & (QIE_PHASE_QKV | QIE_PHASE_ATTN | QIE_PHASE_END)))
+        QIE_REQUIRE(B == h->peers.batch && h->peers.img_pad == seq->img_pad && h->peers.txt_pad == seq->txt_pad && h->fuse_qk &&
+                        sp && sp->size == h->peers.size && sp->rank == h->peers.rank && sp->img_total == h->peers.img_total &&
+                        sp->txt_total == h->peers.txt_total,
+                    QIE_ESTATE, "qie_forward_phase: the installed peers describe another geometry (batch %d, shard %d+%d rows, "
+                    "%d+%d tokens): call qie_set_peers for this one", h->peers.batch, h->peers.img_pad, h->peers.txt_pad,
+                    h->peers.img_total, h->peers.txt_total);
     auto run_ln = [&](const float* mv, long long bs, long long ss, int sh, int sc, bool q8) -> int {
         ProfScope ps(h, st, 2, valid_rows * D * 6.0);
         return qie_ln_modulate(resid, mv, bs, ss, sh, sc, xm, q8 ? xm8 : nullptr, q8 ? xscale : nullptr, h->precision, D,
@@ -464,7 +539,7 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
                 if (rc) return rc;
             } else {
                 // sequence-parallel shard: build the table of the WHOLE sequence, keep the rows this rank owns
-                QIE_REQUIRE(seq->batch == 1 && sp->img_offset + seq->img_rows <= sp->img_total &&
+                QIE_REQUIRE(sp->img_offset + seq->img_rows <= sp->img_total &&
                                 sp->txt_offset + seq->txt_rows <= sp->txt_total,
                             QIE_ESHAPE, "qie_forward: bad sequence-parallel shard");
                 qie_seq full;
@@ -549,21 +624,12 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
 
     // ---- transformer blocks ----
     const int l_begin = layer < 0 ? 0 : layer, l_end = layer < 0 ? nb : (layer < nb ? layer + 1 : nb);
-    // whole-forward calls: every adaLN except the very first runs inside the gated-residual GEMM in front of it
-    const bool fuse_ln = h->fuse_ln && phases == QIE_PHASE_ALL && layer < 0 && D % 128 == 0 && D / 128 <= 24;
-    bool final_ln_done = false;
-    auto set_ln = [&](qie_gemm_args& g, const float* mv, long long bs, long long ss, int sh, int sc, bool q8) {
-        g.ln_out = xm; g.ln_mod = mv; g.ln_mod_bstride = bs; g.ln_mod_sstride = ss; g.ln_shift_off = sh; g.ln_scale_off = sc;
-        g.ln_eps = 1e-6f; g.ln_qmode = h->precision;
-        g.ln_out8 = q8 ? xm8 : nullptr; g.ln_out_scale = q8 ? xscale : nullptr;
-    };
     for (int l = l_begin; l < l_end; ++l) {
         const qie_block_weights& bw = h->blocks[l];
         const float* m = mod + (size_t)l * 12 * D;   // + b*modN + s*6D
         if (phases & QIE_PHASE_QKV) {
-        // adaLN 1 -> xm (already produced by the previous block's FF-down launch when fused)
-        if (!(fuse_ln && l > l_begin) && (rc = run_ln(m, modN, 6LL * D, 0, D, fp8)))
-            return rc;
+        // adaLN 1 -> xm
+        if ((rc = run_ln(m, modN, 6LL * D, 0, D, fp8))) return rc;
         {   // QKV (+ QK-RMSNorm + RoPE)
             qie_gemm_args g{};
             g.N = 3 * D; g.K = D; g.streams = 3; g.out = qkv; g.ldo = 3 * D;
@@ -578,7 +644,10 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
             }
             g.a = fp8 ? xm8 : xm; g.fp8 = fp8; g.a_scale = xscale;
             if (h->has_peers) {   // epilogue scatters q|k|v of head group g into rank g's gathered buffer (peer stores)
-                g.peer_out = h->d_peer_tab; g.sp_rank = h->peers.rank; g.sp_size = h->peers.size; g.sp_rows = h->peers.rows_pad;
+                const qie_peers& pr = h->peers;
+                g.peer_out = h->d_peer_tab; g.sp_rank = pr.rank; g.sp_size = pr.size;
+                g.sp_gathered_rows = pr.size * pr.img_pad + (pr.txt_total + 127) / 128 * 128;
+                g.sp_txt_row0 = pr.size * pr.img_pad + sp->txt_offset;
             }
             if ((rc = run_gemm(g))) return rc;
             if (!h->fuse_qk) {
@@ -603,12 +672,10 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
                 if ((rc = qie_quant_rows(attn, attn8, xscale + rows, (long long)rows, D, h->precision, st))) return rc;
                 g.a = attn8; g.fp8 = fp8; g.a_scale = xscale + rows;
             }
-            if (fuse_ln) set_ln(g, m, modN, 6LL * D, 3 * D, 4 * D, fp8);      // adaLN 2 in the tail of this launch
             if ((rc = run_gemm(g))) return rc;
         }
         // adaLN 2 -> xm
-        if (!fuse_ln && (rc = run_ln(m, modN, 6LL * D, 3 * D, 4 * D, fp8)))
-            return rc;
+        if ((rc = run_ln(m, modN, 6LL * D, 3 * D, 4 * D, fp8))) return rc;
         {   // FF up + GELU(tanh)
             qie_gemm_args g{};
             g.N = 4 * D; g.K = D; g.streams = 3; g.out = ffh; g.ldo = 4 * D; g.epilogue = QIE_EPI_GELU_BF16;
@@ -634,10 +701,6 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
                 if ((rc = qie_quant_rows(ffh, ffh8, xscale + 2 * rows, (long long)rows, 4 * D, h->precision, st))) return rc;
                 g.a = ffh8; g.fp8 = fp8; g.a_scale = xscale + 2 * rows;
             }
-            if (fuse_ln) {      // the next block's adaLN 1, or norm_out after the last block, in the tail of this launch
-                if (l + 1 < l_end) set_ln(g, m + 12 * (size_t)D, modN, 6LL * D, 0, D, fp8);
-                else { set_ln(g, fin, 2LL * D, 0, D, 0, false); final_ln_done = true; }
-            }
             if ((rc = run_gemm(g))) return rc;
         }
         }   // QIE_PHASE_POST
@@ -645,13 +708,20 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
 
     // ---- norm_out (AdaLayerNormContinuous: scale first, then shift) + proj_out on the image stream ----
     if (!(phases & QIE_PHASE_END)) return QIE_OK;
-    if (!final_ln_done && (rc = run_ln(fin, 2LL * D, 0, D, 0, false))) return rc;
+    if ((rc = run_ln(fin, 2LL * D, 0, D, 0, false))) return rc;
     {
         qie_gemm_args g{};
         g.a = xm; g.w[0] = h->w.proj_out_w; g.bias[0] = h->w.proj_out_b;
         g.out = outp; g.out_compact = 1; g.ldo = h->cfg.out_dim; g.N = h->cfg.out_dim; g.K = D; g.streams = 1;
         g.epilogue = QIE_EPI_BF16;
         if ((rc = run_gemm(g))) return rc;
+    }
+    if (h->has_peers) {
+        // sequence parallel: every rank of the group needs the whole velocity for the (replicated) Euler update — my rows go
+        // straight into every rank's velocity buffer (NVLink peer stores); the caller's barrier makes them visible
+        if ((rc = peer_bcast_rows(outp, h->d_peer_tab + 16, &h->peers, seq->img_rows, sp->img_offset, h->cfg.out_dim, st)))
+            return rc;
+        if (!out) return QIE_OK;
     }
     if (seq->img_pad == seq->img_rows) {
         QIE_CUDA_OK(cudaMemcpyAsync(out, outp, (size_t)B * seq->img_rows * h->cfg.out_dim * 2, cudaMemcpyDeviceToDevice,
@@ -678,27 +748,143 @@ extern "C" int qie_forward_phase(qie_handle* h, int phases, int layer, const voi
                         workspace_bytes, n_blocks, stream);
 }
 
+// Shard of `rank` in a sequence-parallel group of `size`: image tokens and text tokens are each split contiguously, the first
+// (total % size) ranks own one token more.  Fills the local layout (`seq_out`, per-rank padding identical on every rank) and the
+// placement inside the whole sequence (`sp_out`).  Mirrors parallel.make_shard_plan.
+extern "C" int qie_sp_shard(int batch, int img_total, int txt_total, int size, int rank, qie_seq* seq_out, qie_sp* sp_out) {
+    QIE_REQUIRE(seq_out && sp_out && batch >= 1 && size >= 1 && size <= 8 && rank >= 0 && rank < size, QIE_EINVAL,
+                "qie_sp_shard: bad argument");
+    QIE_REQUIRE(img_total >= size && txt_total >= size, QIE_ESHAPE,
+                "qie_sp_shard: every rank needs at least one image and one text token (img=%d, txt=%d, P=%d)", img_total,
+                txt_total, size);
+    auto share = [&](int total, int r) { return total / size + (r < total % size ? 1 : 0); };
+    auto offset = [&](int total, int r) { return r * (total / size) + (r < total % size ? r : total % size); };
+    auto pad = [](int n) { return (n + 127) / 128 * 128; };
+    QIE_REQUIRE(pad(share(img_total, 0)) == pad(share(img_total, size - 1)) &&
+                    pad(share(txt_total, 0)) == pad(share(txt_total, size - 1)),
+                QIE_ESHAPE, "qie_sp_shard: shards straddle a 128-row boundary (a rank would own an all-padding tile)");
+    seq_out->batch = batch;
+    seq_out->img_rows = share(img_total, rank);
+    seq_out->txt_rows = share(txt_total, rank);
+    seq_out->img_pad = pad(share(img_total, 0));
+    seq_out->txt_pad = pad(share(txt_total, 0));
+    sp_out->rank = rank;
+    sp_out->size = size;
+    sp_out->img_total = img_total;
+    sp_out->txt_total = txt_total;
+    sp_out->img_offset = offset(img_total, rank);
+    sp_out->txt_offset = offset(txt_total, rank);
+    return QIE_OK;
+}
+
+// Valid rows of every 128-row tile of the gathered sequence [rank 0 image shard | ... | rank P-1 image shard | all text tokens]
+extern "C" int qie_sp_tile_valid_host(int img_total, int txt_total, int size, int* out, int max_tiles) {
+    QIE_REQUIRE(out && size >= 1 && size <= 8, QIE_EINVAL, "qie_sp_tile_valid_host: bad argument");
+    qie_seq s;
+    qie_sp p;
+    int rc = qie_sp_shard(1, img_total, txt_total, size, 0, &s, &p);
+    if (rc) return rc;
+    const int n = (size * s.img_pad + (txt_total + 127) / 128 * 128) / 128;
+    QIE_REQUIRE(n <= max_tiles, QIE_ENOMEM, "qie_sp_tile_valid_host: %d tiles, room for %d", n, max_tiles);
+    int k = 0;
+    for (int r = 0; r < size; ++r) {
+        const int rows = img_total / size + (r < img_total % size ? 1 : 0);
+        for (int t = 0; t < s.img_pad / 128; ++t) out[k++] = rows - t * 128 < 128 ? rows - t * 128 : 128;
+    }
+    for (int t = 0; t * 128 < txt_total; ++t) out[k++] = txt_total - t * 128 < 128 ? txt_total - t * 128 : 128;
+    return k;
+}
+
 extern "C" int qie_set_peers(qie_handle* h, const qie_peers* peers, void* stream) {
     QIE_REQUIRE(h, QIE_EINVAL, "qie_set_peers: null handle");
     if (!peers) {
         h->has_peers = false;
-        return QIE_OK;
+        return peer_sticky_error(/*clear=*/true);     // reports (once) a barrier timeout of the group that is being dissolved
     }
     QIE_REQUIRE(peers->size >= 2 && peers->size <= 8 && peers->rank >= 0 && peers->rank < peers->size &&
-                    h->cfg.num_heads % peers->size == 0 && peers->rows_pad > 0 && peers->rows_pad % 128 == 0 && peers->tile_valid,
-                QIE_EINVAL, "qie_set_peers: bad group (size %d rank %d rows_pad %d)", peers->size, peers->rank, peers->rows_pad);
-    for (int i = 0; i < peers->size; ++i)
-        QIE_REQUIRE(peers->qkv_gather[i] && peers->attn_out[i], QIE_EINVAL, "qie_set_peers: buffer of rank %d is null", i);
-    if (!h->d_peer_tab) QIE_CUDA_OK(cudaMalloc(&h->d_peer_tab, 16 * sizeof(void*)));
-    void* tab[16] = {};
+                    h->cfg.num_heads % peers->size == 0 && peers->batch >= 1 && peers->batch <= 8,
+                QIE_EINVAL, "qie_set_peers: bad group (size %d rank %d batch %d)", peers->size, peers->rank, peers->batch);
+    qie_seq s;
+    qie_sp p;
+    int rc = qie_sp_shard(peers->batch, peers->img_total, peers->txt_total, peers->size, peers->rank, &s, &p);
+    if (rc) return rc;
+    QIE_REQUIRE(s.img_pad == peers->img_pad && s.txt_pad == peers->txt_pad, QIE_ESHAPE,
+                "qie_set_peers: shard padding %d+%d does not match qie_sp_shard (%d+%d)", peers->img_pad, peers->txt_pad,
+                s.img_pad, s.txt_pad);
+    void* tab[24] = {};
     for (int i = 0; i < peers->size; ++i) {
+        QIE_REQUIRE(peers->qkv_gather[i] && peers->attn_out[i] && peers->vel[i] && peers->flags[i], QIE_EINVAL,
+                    "qie_set_peers: a buffer of rank %d is null", i);
         tab[i] = peers->qkv_gather[i];
         tab[8 + i] = peers->attn_out[i];
+        tab[16 + i] = peers->vel[i];
     }
-    // pageable source: the runtime stages it before returning, so `tab` may live on this stack; ordered on `stream`
-    QIE_CUDA_OK(cudaMemcpyAsync(h->d_peer_tab, tab, sizeof(tab), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!h->d_peer_tab) {
+        QIE_CUDA_OK(cudaMalloc(&h->d_peer_tab, sizeof(tab)));
+        memset(h->peer_tab_host, 0xff, sizeof(h->peer_tab_host));
+    }
+    if (memcmp(tab, h->peer_tab_host, sizeof(tab)) != 0) {
+        // pageable source: the runtime stages it before returning, so `tab` may live on this stack; ordered on `stream`
+        QIE_CUDA_OK(cudaMemcpyAsync(h->d_peer_tab, tab, sizeof(tab), cudaMemcpyHostToDevice, st));
+        memcpy(h->peer_tab_host, tab, sizeof(tab));
+    }
+    // tile list of this geometry (kept for the lifetime of the handle: captured graphs keep pointing at it)
+    int* d_tiles = nullptr;
+    for (auto& e : h->tile_cache)
+        if (e.img_total == peers->img_total && e.txt_total == peers->txt_total && e.size == peers->size) d_tiles = e.d;
+    if (!d_tiles) {
+        int tiles[1024];
+        const int n = qie_sp_tile_valid_host(peers->img_total, peers->txt_total, peers->size, tiles, 1024);
+        if (n < 0) return n;
+        QIE_CUDA_OK(cudaMalloc(&d_tiles, n * sizeof(int)));
+        QIE_CUDA_OK(cudaMemcpyAsync(d_tiles, tiles, n * sizeof(int), cudaMemcpyHostToDevice, st));
+        QIE_CUDA_OK(cudaStreamSynchronize(st));      // `tiles` lives on this stack; only when a new geometry appears
+        h->tile_cache.push_back({peers->img_total, peers->txt_total, peers->size, d_tiles});
+    }
+    h->d_tile_valid = d_tiles;
     h->peers = *peers;
     h->has_peers = true;
+    return QIE_OK;
+}
+
+// all-ranks barrier of the installed group on `stream` (device-side epochs: replayable inside a CUDA graph)
+extern "C" int qie_peer_barrier(qie_handle* h, void* stream) {
+    QIE_REQUIRE(h && h->has_peers, QIE_ESTATE, "qie_peer_barrier: no peers installed");
+    ProfScope ps(h, (cudaStream_t)stream, 5, 0.0);
+    return peer_barrier_launch(&h->peers, (cudaStream_t)stream);
+}
+
+// One call = the whole sequence-parallel forward of this rank (fused peer-memory exchange): BEGIN, then per block
+// QKV -> barrier -> ATTN -> barrier -> POST, then END (velocity rows stored into every rank's buffer) -> barrier -> copy of the
+// whole velocity into `out_full` [B, img_total, out_dim].  No host synchronisation, no allocation: capturable in a CUDA graph.
+extern "C" int qie_forward_sp(qie_handle* h, const void* hidden_local, const void* enc_local, const float* timestep,
+                              const int* img_shapes_host, int n_img, const qie_seq* seq, const qie_sp* sp, void* out_full,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+    QIE_REQUIRE(h && h->has_peers, QIE_ESTATE, "qie_forward_sp: no peers installed (qie_set_peers)");
+    QIE_REQUIRE(sp && out_full, QIE_EINVAL, "qie_forward_sp: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = forward_impl(h, QIE_PHASE_BEGIN, -1, hidden_local, enc_local, timestep, img_shapes_host, n_img, seq, sp, nullptr,
+                          workspace, workspace_bytes, -1, stream);
+    if (rc) return rc;
+    for (int l = 0; l < h->cfg.num_layers; ++l) {
+        // adaLN1 + QKV GEMM: the epilogue stores q|k|v of head group g into rank g's gather buffer
+        if ((rc = forward_impl(h, QIE_PHASE_QKV, l, nullptr, nullptr, nullptr, img_shapes_host, n_img, seq, sp, nullptr, workspace,
+                               workspace_bytes, -1, stream))) return rc;
+        if ((rc = qie_peer_barrier(h, stream))) return rc;      // everybody's q|k|v has landed in my gather buffer
+        // attention of my heads over all tokens: the epilogue stores into the token owners' attention buffers
+        if ((rc = forward_impl(h, QIE_PHASE_ATTN, l, nullptr, nullptr, nullptr, nullptr, 0, seq, sp, nullptr, workspace,
+                               workspace_bytes, -1, stream))) return rc;
+        if ((rc = qie_peer_barrier(h, stream))) return rc;      // everybody's heads have landed in my attention buffer
+        if ((rc = forward_impl(h, QIE_PHASE_POST, l, nullptr, nullptr, nullptr, nullptr, 0, seq, sp, nullptr, workspace,
+                               workspace_bytes, -1, stream))) return rc;
+    }
+    if ((rc = forward_impl(h, QIE_PHASE_END, -1, nullptr, nullptr, nullptr, nullptr, 0, seq, sp, nullptr, workspace,
+                           workspace_bytes, -1, stream))) return rc;
+    if ((rc = qie_peer_barrier(h, stream))) return rc;          // the whole velocity is in my buffer
+    const qie_peers& pr = h->peers;
+    QIE_CUDA_OK(cudaMemcpyAsync(out_full, pr.vel[pr.rank], (size_t)pr.batch * pr.img_total * h->cfg.out_dim * 2,
+                                cudaMemcpyDeviceToDevice, st));
     return QIE_OK;
 }
 

@@ -2,7 +2,11 @@
 // Replaces F.scaled_dot_product_attention(q, k, v) over the concatenated sequence inside
 // QwenDoubleStreamAttnProcessor2_0; q,k arrive RMS-normed + roped (QKV GEMM epilogue).
 //
-// One CTA = one (batch, head) x 256 query rows = two 128-row Q tiles that ping-pong on the tensor pipe:
+// Two kernels: attn_pair_kernel (default: a CTA pair per 256 query rows, cta_group::2 MMAs, 256-wide KV tiles, P in TMEM) and
+// attn_kernel (single-CTA fallback, variant bit 0x8; also the A/B yard-stick).  The kernels that lost the round-1 A/B runs
+// (first pair kernels, persistent / speculative / traced builds) live in the git history (commit 550b982 and before).
+//
+// attn_kernel: one CTA = one (batch, head) x 256 query rows = two 128-row Q tiles that ping-pong on the tensor pipe:
 //   warp 0 / lane 0 : TMA producer (Q tiles once; K_j, V_j tiles through a ring, 128 rows x 128 dims each)
 //   warp 1 / lane 0 : MMA issuer   S_t = Q_t K_j^T (SS, K-major x K-major)          -> TMEM S_t (128 x 128 fp32)
 //                                  O_t += P_t V_j  (P_t from TMEM [TS] or smem [SS], V MN-major) -> TMEM O_t
@@ -19,7 +23,6 @@
 namespace qie {
 
 constexpr int ATT_THREADS = 384;
-#define QIE_ATTN_DEFAULT_VARIANT 0x1020   /* CTA pair, 256-wide KV tiles, P in TMEM (pair3), 2 of 8 score pairs on the FMA-pipe polynomial: best measured */
 constexpr int ATT_TILE = 128;                       // q rows per tile, kv rows per tile, head dim
 constexpr int ATT_HALF_BYTES = ATT_TILE * 128;      // 128 rows x 64 bf16 (one swizzled half tile) = 16 KB
 constexpr int ATT_TILE_BYTES = 2 * ATT_HALF_BYTES;  // 32 KB
@@ -38,30 +41,17 @@ struct AttnDev {
     float scale_log2;        // softmax scale * log2(e)
     uint32_t v_lbo, v_sbo;   // V (MN-major) descriptor strides, bytes
     uint32_t v_kstep;        // byte advance of the V descriptor per 16 kv rows
-    const int* tile_valid;   // optional: valid rows per 128-row KV tile (sequence-parallel layout); NULL = from seq
-    unsigned long long* trace;   // timing experiment (pair2 DBG 4): clock64 stamps of one cluster, see tools/attn_trace.py
-    // sequence-parallel scatter of the output (pair3 only; qie_peers): query tile rows [s*sp_rows, (s+1)*sp_rows) belong to the
-    // tokens of rank s and go to peer_out[s] [sp_rows, out_ld] at head column (head_off + head) * 128
+    const int* tile_valid;   // optional: valid rows per 128-row KV tile (gathered sequence-parallel layout); NULL = from seq
+    // sequence-parallel scatter of the output (pair kernel only; qie_peers).  The sequence is the gathered layout
+    // [rank 0 image shard (sp_img_pad rows) | ... | rank P-1 image shard | all text tokens]; query row qg of batch b belongs to
+    //   image: rank s = qg / sp_img_pad, local row qg % sp_img_pad
+    //   text : token t = qg - sp_img_region, owned by rank s (the first sp_txt_rem ranks own sp_txt_base + 1 tokens), local row
+    //          sp_img_pad + (t - first token of s)
+    // and goes to peer_out[s] [batch][sp_rows_pad][out_ld] at head column (head_off + head) * 128
     void* const* peer_out;
-    int sp_rows, out_ld, head_off;
-    // speculative-reference build of pair3: `overflow` is raised when a score exceeded the running reference by more than 2^100
-    // (its P tile is then unusable); the exact build launched right behind it only runs when `run_if` points at a raised flag
-    int* overflow;
-    const int* run_if;
+    int sp_img_pad, sp_img_region, sp_rows_pad, sp_txt_total, sp_txt_base, sp_txt_rem;
+    int out_ld, head_off;
 };
-
-// trace layout: [cta_rank 2][role 11][tile 32][event 8]; roles: 0 S issuer, 1 PV issuer, 2 + wg*4 + quad softmax warps, 10 TMA producer
-constexpr int TR_NJ = 32, TR_NEV = 8, TR_ROLES = 11;
-__device__ __forceinline__ unsigned long long clk64() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
-    return t;
-}
-#define TRC(role, j, ev)                                                                                   \
-    do {                                                                                                   \
-        if (DBG == 4 && traced && (j) < TR_NJ)                                                             \
-            p.trace[((cta_rank * TR_ROLES + (role)) * TR_NJ + (j)) * TR_NEV + (ev)] = clk64();             \
-    } while (0)
 
 __device__ __forceinline__ int kv_valid_rows(const qie_seq& s, int j) {
     const int r0 = j * ATT_TILE;
@@ -448,682 +438,9 @@ static int launch_attn(const CUtensorMap& tm, const AttnDev& p, dim3 grid, cudaS
     return QIE_OK;
 }
 
-// Single-pass softmax tile for a FULL 128-column tile when a finite reference m is already known: p = exp2(s*c - m) is
-// computed straight away while the maximum of x = s*c - m is tracked; the caller redoes the tile (rare) only when some
-// row's x exceeded the lazy-rescale threshold.  Saves the separate row-max pass (4 TMEM loads + waits) of every tile.
-template <int POLY>
-__device__ __forceinline__ float softmax_fast(uint32_t tS, uint64_t c2, uint64_t nm2, uint64_t& l2, uint32_t (&pw)[64]) {
-    uint32_t sa[32], sb[32];
-    float m0 = -INFINITY, m1 = -INFINITY;
-    tmem_ld32(tS, sa);
-    tmem_ld_wait();
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-        uint32_t(&cur)[32] = (ch & 1) ? sb : sa;
-        uint32_t(&nxt)[32] = (ch & 1) ? sa : sb;
-        if (ch < 3) tmem_ld32(tS + (ch + 1) * 32, nxt);
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-            const uint64_t X = fma2(pk2u(cur[i], cur[i + 1]), c2, nm2);
-            float x0, x1, e0, e1;
-            upk2(X, x0, x1);
-            if ((i >> 1) & 1) m1 = max3(m1, x0, x1);
-            else m0 = max3(m0, x0, x1);
-            if (((i >> 1) & 7) < POLY) {
-                const uint64_t Xc = pk2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
-                const uint64_t T = add2(Xc, pk2(12582912.f, 12582912.f));
-                const uint64_t N = add2(T, pk2(-12582912.f, -12582912.f));
-                const uint64_t Fr = fma2(N, pk2(-1.f, -1.f), Xc);
-                uint64_t P = fma2(Fr, pk2(0.0551716574f, 0.0551716574f), pk2(0.2426111400f, 0.2426111400f));
-                P = fma2(P, Fr, pk2(0.6932609677f, 0.6932609677f));
-                P = fma2(P, Fr, pk2(0.9999280572f, 0.9999280572f));
-                float t0, t1, p0, p1;
-                upk2(T, t0, t1);
-                upk2(P, p0, p1);
-                e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-                e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
-            } else {
-                e0 = fast_exp2(x0);
-                e1 = fast_exp2(x1);
-            }
-            l2 = add2(l2, pk2(e0, e1));
-            pw[ch * 16 + (i >> 1)] = pack_bf16(e0, e1);
-        }
-        if (ch < 3) tmem_ld_wait();
-    }
-    return fmaxf(m0, m1);
-}
-
 // =====================================================================================================================
-// CTA-pair attention (cta_group::2).  A cluster of two CTAs owns 256 query rows of one (batch, head): CTA r holds Q rows
-// [128 r, 128 r + 128).  Every MMA is ONE 256-row tcgen05.mma.cta_group::2 issued by the leader:
-//     S  = Q K_j^T : each CTA stages HALF of K_j (64 kv rows)   -> K smem reads and L2->SM bytes halved vs the 1-CTA tile
-//     O += P V_j   : P from each CTA's TMEM (TS), each CTA stages HALF of V_j (64 of the 128 head dims, MN-major)
-// One Q tile per SM leaves TMEM room for TWO independent softmax streams: warpgroup b owns the KV tiles j = b (mod 2),
-// with its own S buffer, its own running (max, sum) and its own O accumulator (S0 | S1 | O0 | O1 = 512 columns) — a
-// split-KV decomposition inside the CTA, merged once in the epilogue (O = sum_b 2^(m_b-m) O_b / sum_b 2^(m_b-m) l_b).
-// There is no per-tile synchronisation between the warpgroups, so while one is on the MUFU (exp2) the other reads TMEM /
-// reduces maxima, and the tensor pipe always has the other stream's S / PV to run: S_b(j+2) is issued right after PV_b(j).
-// Work unit = 256 query rows on one TPC -> 792 units on 74 TPCs for config 2 (10.7 rounds, 97 % balance; 89 % before).
-// =====================================================================================================================
-constexpr int AT2_THREADS = 384;
-constexpr int AT2_SLOT_BYTES = 16 * 1024;      // half of a K or V tile
-constexpr int AT2_STAGES = 10;
-constexpr int AT2_SMEM = ATT_TILE_BYTES + AT2_STAGES * AT2_SLOT_BYTES + 2048 + 512 + 1024;
-
-template <int POLY>
-__global__ void __launch_bounds__(AT2_THREADS, 1)
-attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm64, const AttnDev p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                                       // [2 d-halves][128 rows x 128 B]
-    uint8_t* sKV = smem + ATT_TILE_BYTES;                     // [stages][16 KB]
-    float2* xchg = reinterpret_cast<float2*>(sKV + AT2_STAGES * AT2_SLOT_BYTES);   // [2 WGs][128 rows] (m_ref, l)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xchg) + 2048);
-    uint64_t* q_full = bars;                       // leader
-    uint64_t* kv_full = bars + 1;                  // [stages] leader
-    uint64_t* kv_empty = kv_full + AT2_STAGES;     // [stages] both (multicast commit)
-    uint64_t* s_full = kv_empty + AT2_STAGES;      // [2] both
-    uint64_t* p_full = s_full + 2;                 // [2] leader, 8 warp arrivals (4 softmax warps x 2 CTAs)
-    uint64_t* pv_done = p_full + 2;                // [2] both
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
-
-    const int warp = threadIdx.x >> 5, lane = lane_id();
-    const int cta_rank = (int)cluster_ctarank();
-    const int rpb = p.seq.img_pad + p.seq.txt_pad;
-    const int n_kv = rpb / ATT_TILE;               // >= 2 (both streams are non-empty)
-    const int head = blockIdx.y, b = blockIdx.z;
-    const int q_row0 = (blockIdx.x >> 1) * 2 * ATT_TILE + cta_rank * ATT_TILE;   // my Q tile, row inside the batch element
-    const bool q_valid = q_row0 < rpb;
-    const int D = p.H * ATT_TILE;
-    const int colQ = head * ATT_TILE, colK = D + head * ATT_TILE, colV = 2 * D + head * ATT_TILE;
-    const int row_base = b * rpb;
-
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tm128);
-        tma_prefetch_desc(&tm64);
-        mbar_init(q_full, 1);
-        for (int i = 0; i < AT2_STAGES; ++i) {
-            mbar_init(&kv_full[i], 1);
-            mbar_init(&kv_empty[i], 1);
-        }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&s_full[i], 1);
-            mbar_init(&p_full[i], 8);
-            mbar_init(&pv_done[i], 1);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc_cg2<512>(tmem_slot);
-    tc_fence_before();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            // ================= TMA producer (each CTA: own Q tile, its half of every K / V tile) =================
-            if (cta_rank == 0) mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
-            const int qr = q_valid ? q_row0 : 0;     // an out-of-range peer tile still feeds the pair MMA (never stored)
-            for (int hf = 0; hf < 2; ++hf)
-                tma_load_2d_cg2(sQ + hf * ATT_HALF_BYTES, &tm128, colQ + hf * 64, row_base + qr, leader_smem_u32(q_full));
-            int stage = 0;
-            uint32_t phase = 0;
-            auto load = [&](bool is_v, int j) {
-                mbar_wait(&kv_empty[stage], phase ^ 1);
-                if (cta_rank == 0) mbar_expect_tx(&kv_full[stage], 2 * AT2_SLOT_BYTES);
-                const uint32_t bar = leader_smem_u32(&kv_full[stage]);
-                uint8_t* dst = sKV + stage * AT2_SLOT_BYTES;
-                if (is_v) {      // 128 kv rows x my 64 head dims
-                    tma_load_2d_cg2(dst, &tm128, colV + cta_rank * 64, row_base + j * ATT_TILE, bar);
-                } else {         // my 64 kv rows x 128 head dims, as two 64-dim halves of 8 KB
-                    for (int hf = 0; hf < 2; ++hf)
-                        tma_load_2d_cg2(dst + hf * 8192, &tm64, colK + hf * 64, row_base + j * ATT_TILE + cta_rank * 64, bar);
-                }
-                if (++stage == AT2_STAGES) {
-                    stage = 0;
-                    phase ^= 1;
-                }
-            };
-            load(false, 0);
-            load(false, 1);
-            for (int j = 0; j < n_kv; ++j) {
-                load(true, j);
-                if (j + 2 < n_kv) load(false, j + 2);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0 && cta_rank == 0) {
-            // ================= MMA issuer (leader) =================
-            constexpr uint32_t IDESC_S = umma_idesc_bf16(256, 128, false);
-            constexpr uint32_t IDESC_O = umma_idesc_bf16(256, 128, true);   // B = V is MN-major
-            int stage = 0;
-            uint32_t phase = 0;
-            auto next_slot = [&]() -> uint32_t {      // waits for the next ring slot, returns its smem address
-                mbar_wait(&kv_full[stage], phase);
-                tc_fence_after();
-                return smem_u32(sKV + stage * AT2_SLOT_BYTES);
-            };
-            auto release_slot = [&]() {
-                umma_commit_cg2(&kv_empty[stage], 3);
-                if (++stage == AT2_STAGES) {
-                    stage = 0;
-                    phase ^= 1;
-                }
-            };
-            auto issue_S = [&](int buf) {
-                const uint32_t k = next_slot(), q = smem_u32(sQ);
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {   // 8 x 16 head dims
-                    umma_ss_f16_cg2(tmem_base + buf * 128,
-                                    umma_desc_kmajor_sw128(q + (s >> 2) * ATT_HALF_BYTES + (s & 3) * 32),
-                                    umma_desc_kmajor_sw128(k + (s >> 2) * 8192 + (s & 3) * 32), IDESC_S, s ? 1u : 0u);
-                }
-                umma_commit_cg2(&s_full[buf], 3);
-                release_slot();
-            };
-            mbar_wait(q_full, 0);
-            tc_fence_after();
-            issue_S(0);
-            issue_S(1);
-            for (int j = 0; j < n_kv; ++j) {
-                const int buf = j & 1;
-                const uint32_t v = next_slot();
-                mbar_wait(&p_full[buf], (j >> 1) & 1);     // both CTAs: P(j) in TMEM over S_buf, O_buf rescaled
-                tc_fence_after();
-#pragma unroll
-                for (int s = 0; s < 8; ++s)     // 8 x 16 kv rows; A = P (8 packed columns per step)
-                    umma_ts_f16_cg2(tmem_base + 256 + buf * 128, tmem_base + buf * 128 + s * 8,
-                                    umma_desc_mnmajor_sw128(v + s * 2048, ATT_HALF_BYTES, 1024), IDESC_O,
-                                    (j < 2 && s == 0) ? 0u : 1u);
-                umma_commit_cg2(&pv_done[buf], 3);
-                release_slot();
-                if (j + 2 < n_kv) issue_S(buf);            // in order after PV(j): may overwrite the aliased P(j)
-            }
-        }
-    } else if (warp >= 4) {
-        // ================= softmax: warpgroup wg (warps 4-7 / 8-11) owns KV tiles j = wg, wg+2, ... =================
-        const int wg = (warp - 4) >> 2;
-        const int quad = warp & 3;
-        const int r = quad * 32 + lane;                    // row inside my Q tile == TMEM lane
-        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        const uint32_t tS = tmem_base + lane_addr + wg * 128;
-        const uint32_t tO = tmem_base + lane_addr + 256 + wg * 128;
-        const float c = p.scale_log2;
-        const uint64_t c2 = pk2(c, c);
-        float m_ref = -INFINITY;
-        uint64_t l2 = pk2(0.f, 0.f);
-        int it = 0;
-        for (int j = wg; j < n_kv; j += 2, ++it) {
-            const int nv = p.tile_valid ? __ldg(p.tile_valid + j) : kv_valid_rows(p.seq, j);
-            const bool full = nv == ATT_TILE;
-            mbar_wait(&s_full[wg], it & 1);
-            tc_fence_after();
-            uint32_t pw[64];
-            bool done = false;
-            if (full && it > 0) {
-                // fast path: one pass against the current reference; redo only if a row max grew by more than the threshold
-                const uint64_t l2_before = l2;
-                const float xmax = softmax_fast<POLY>(tS, c2, pk2(-m_ref, -m_ref), l2, pw);
-                done = !__any_sync(0xffffffffu, xmax > 8.0f);
-                if (!done) l2 = l2_before;
-            }
-            if (!done) {
-                float mx = (full ? row_max<true>(tS, nv) : row_max<false>(tS, nv)) * c;
-                float alpha = 1.f;
-                const bool grow = mx > m_ref + 8.0f;
-                if (grow) {
-                    alpha = fast_exp2(m_ref - mx);
-                    m_ref = mx;
-                    l2 = fma2(l2, pk2(alpha, alpha), pk2(0.f, 0.f));
-                }
-                if (it > 0 && __any_sync(0xffffffffu, grow)) {
-                    // s_full of this tile was committed after PV of my previous tile in issue order: O_wg is quiescent
-#pragma unroll 1
-                    for (int ch = 0; ch < 4; ++ch) {
-                        uint32_t o[32];
-                        tmem_ld32(tO + ch * 32, o);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st32(tO + ch * 32, o);
-                    }
-                    tmem_st_wait();
-                }
-                const uint64_t nm2 = pk2(-m_ref, -m_ref);
-                if (full) softmax_pass2<true, true, POLY>(tS, nv, c2, nm2, l2, pw, nullptr, r);
-                else softmax_pass2<false, true, POLY>(tS, nv, c2, nm2, l2, pw, nullptr, r);
-            }
-            {
-                uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&pw[0]);
-                uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&pw[32]);
-                tmem_st32(tS, lo);
-                tmem_st32(tS + 32, hi);
-                tmem_st_wait();
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(leader_smem_u32(&p_full[wg]));
-        }
-        // ---- epilogue: merge the two softmax streams of this row, O / l -> bf16 -> global ----
-        float l_lo, l_hi;
-        upk2(l2, l_lo, l_hi);
-        xchg[wg * 128 + r] = make_float2(m_ref, l_lo + l_hi);
-        mbar_wait(&pv_done[wg], (it - 1) & 1);             // my last PV retired (it >= 1)
-        tc_fence_after();
-        tc_fence_before();
-        named_bar_sync(1, 256);                            // both streams of every row are final
-        tc_fence_after();
-        const float2 mine = xchg[wg * 128 + r], other = xchg[(wg ^ 1) * 128 + r];
-        const float m = fmaxf(mine.x, other.x);
-        const float a_me = fast_exp2(mine.x - m), a_ot = fast_exp2(other.x - m);
-        const float inv = 1.f / (mine.y * a_me + other.y * a_ot);
-        const float f0 = (wg == 0 ? a_me : a_ot) * inv, f1 = (wg == 0 ? a_ot : a_me) * inv;   // factors of O0, O1
-        if (q_valid) {
-            // warpgroup wg writes head dims [64 wg, 64 wg + 64) of its rows
-            const uint32_t tO0 = tmem_base + lane_addr + 256 + wg * 64, tO1 = tO0 + 128;
-            __nv_bfloat16* orow = p.out + (long long)(row_base + q_row0 + r) * D + head * ATT_TILE + wg * 64;
-#pragma unroll 1
-            for (int ch = 0; ch < 2; ++ch) {
-                uint32_t o0[32], o1[32];
-                tmem_ld32(tO0 + ch * 32, o0);
-                tmem_ld32(tO1 + ch * 32, o1);
-                tmem_ld_wait();
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    float v[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        v[i] = __uint_as_float(o0[q4 * 8 + i]) * f0 + __uint_as_float(o1[q4 * 8 + i]) * f1;
-                    *reinterpret_cast<uint4*>(orow + ch * 32 + q4 * 8) =
-                        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                }
-            }
-        }
-    }
-
-    __syncwarp();
-    tc_fence_before();
-    cluster_sync_all();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc_cg2<512>(tmem_base);
-    }
-}
-
-// =====================================================================================================================
-// CTA-pair attention, decoupled variant ("pair2").  Same work split as attn_pair_kernel (cluster of 2 CTAs = 256 query
-// rows, one Q tile per CTA, cta_group::2 MMAs, two split-KV softmax streams with their own O accumulators), but the
-// softmax -> tensor-pipe chain of a stream is cut in two places:
-//   * the whole S row (128 fp32) is pulled into registers first and the S buffer is handed back at once (s_free), so
-//     S(j+2) of the stream is computed WHILE the exponentials of tile j are still running;
-//   * P goes to a swizzled shared-memory tile (SS PV MMA) instead of aliasing S in TMEM.
-// K and V travel through separate rings (consumption orders S(0),S(1),.. and PV(0),PV(1),.. are both ascending).
-// Issue order of the leader: S(0) S(1) | S(2) S(3) PV(0) PV(1) | S(4) S(5) PV(2) PV(3) | ...
-// =====================================================================================================================
-constexpr int AT3_KSTAGES = 4, AT3_VSTAGES = 3;   // 96 KB (Q + 2 P tiles) + 7 x 16 KB slots fit the 227 KB limit
-constexpr int AT3_SMEM = ATT_TILE_BYTES * 3 + (AT3_KSTAGES + AT3_VSTAGES) * AT2_SLOT_BYTES + 2048 + 512 + 1024;
-
-template <int POLY, int DBG>
-__global__ void __launch_bounds__(AT2_THREADS, 1)
-attn_pair2_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm64, const AttnDev p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                                       // [2 d-halves][128 rows x 128 B]
-    uint8_t* sP = smem + ATT_TILE_BYTES;                      // [2 streams][2 kv-halves][128 rows x 128 B]
-    uint8_t* sK = smem + 3 * ATT_TILE_BYTES;                  // [K stages][16 KB]
-    uint8_t* sV = sK + AT3_KSTAGES * AT2_SLOT_BYTES;          // [V stages][16 KB]
-    float2* xchg = reinterpret_cast<float2*>(sV + AT3_VSTAGES * AT2_SLOT_BYTES);   // [2 WGs][128 rows] (m_ref, l)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xchg) + 2048);
-    uint64_t* q_full = bars;                       // leader
-    uint64_t* k_full = bars + 1;                   // [K stages] leader
-    uint64_t* k_empty = k_full + AT3_KSTAGES;      // both
-    uint64_t* v_full = k_empty + AT3_KSTAGES;      // [V stages] leader
-    uint64_t* v_empty = v_full + AT3_VSTAGES;      // both
-    uint64_t* s_full = v_empty + AT3_VSTAGES;      // [2] both
-    uint64_t* s_free = s_full + 2;                 // [2] leader, 8 warp arrivals: S_b is in registers everywhere
-    uint64_t* p_full = s_free + 2;                 // [2] leader, 8 warp arrivals: P_b is in shared memory
-    uint64_t* pv_done = p_full + 2;                // [2] both
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
-
-    const int warp = threadIdx.x >> 5, lane = lane_id();
-    const int cta_rank = (int)cluster_ctarank();
-    const int rpb = p.seq.img_pad + p.seq.txt_pad;
-    const int n_kv = rpb / ATT_TILE;               // >= 2
-    const int head = blockIdx.y, b = blockIdx.z;
-    const int q_row0 = (blockIdx.x >> 1) * 2 * ATT_TILE + cta_rank * ATT_TILE;
-    const bool q_valid = q_row0 < rpb;
-    const int D = p.H * ATT_TILE;
-    const int colQ = head * ATT_TILE, colK = D + head * ATT_TILE, colV = 2 * D + head * ATT_TILE;
-    const int row_base = b * rpb;
-    [[maybe_unused]] const bool traced = DBG == 4 && p.trace && (blockIdx.x >> 1) == 3 && blockIdx.y == 9 && blockIdx.z == 0;
-
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tm128);
-        tma_prefetch_desc(&tm64);
-        mbar_init(q_full, 1);
-        for (int i = 0; i < AT3_KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
-        for (int i = 0; i < AT3_VSTAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&s_full[i], 1);
-            mbar_init(&s_free[i], 8);
-            mbar_init(&p_full[i], 8);
-            mbar_init(&pv_done[i], 1);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc_cg2<512>(tmem_slot);
-    tc_fence_before();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            // ================= TMA producer =================
-            if (cta_rank == 0) mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
-            const int qr = q_valid ? q_row0 : 0;
-            for (int hf = 0; hf < 2; ++hf)
-                tma_load_2d_cg2(sQ + hf * ATT_HALF_BYTES, &tm128, colQ + hf * 64, row_base + qr, leader_smem_u32(q_full));
-            int ks = 0, vs = 0;
-            uint32_t kph = 0, vph = 0;
-            auto load_k = [&](int j) {       // my 64 kv rows x 128 head dims, as two 64-dim halves of 8 KB
-                mbar_wait(&k_empty[ks], kph ^ 1);
-                TRC(10, j, 0);
-                if (DBG == 3 && j >= 4) {     // timing experiment: no K/V traffic after the first tiles (stale smem, wrong results)
-                    if (cta_rank == 0) mbar_arrive(&k_full[ks]);
-                    if (++ks == AT3_KSTAGES) { ks = 0; kph ^= 1; }
-                    return;
-                }
-                if (cta_rank == 0) mbar_expect_tx(&k_full[ks], 2 * AT2_SLOT_BYTES);
-                const uint32_t bar = leader_smem_u32(&k_full[ks]);
-                for (int hf = 0; hf < 2; ++hf)
-                    tma_load_2d_cg2(sK + ks * AT2_SLOT_BYTES + hf * 8192, &tm64, colK + hf * 64,
-                                    row_base + j * ATT_TILE + cta_rank * 64, bar);
-                if (++ks == AT3_KSTAGES) { ks = 0; kph ^= 1; }
-            };
-            auto load_v = [&](int j) {       // 128 kv rows x my 64 head dims
-                mbar_wait(&v_empty[vs], vph ^ 1);
-                TRC(10, j, 1);
-                if (DBG == 3 && j >= 4) {
-                    if (cta_rank == 0) mbar_arrive(&v_full[vs]);
-                    if (++vs == AT3_VSTAGES) { vs = 0; vph ^= 1; }
-                    return;
-                }
-                if (cta_rank == 0) mbar_expect_tx(&v_full[vs], 2 * AT2_SLOT_BYTES);
-                tma_load_2d_cg2(sV + vs * AT2_SLOT_BYTES, &tm128, colV + cta_rank * 64, row_base + j * ATT_TILE,
-                                leader_smem_u32(&v_full[vs]));
-                if (++vs == AT3_VSTAGES) { vs = 0; vph ^= 1; }
-            };
-            load_k(0);
-            load_k(1);
-            for (int j0 = 0; j0 < n_kv; j0 += 2) {
-                for (int t = 0; t < 2; ++t)
-                    if (j0 + t + 2 < n_kv) load_k(j0 + t + 2);
-                for (int t = 0; t < 2; ++t)
-                    if (j0 + t < n_kv) load_v(j0 + t);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0 && cta_rank == 0) {
-            // ================= MMA issuer (leader) =================
-            constexpr uint32_t IDESC_S = umma_idesc_bf16(256, 128, false);
-            int ks = 0;
-            uint32_t kph = 0;
-            auto issue_S = [&](int buf, int jt) {
-                mbar_wait(&k_full[ks], kph);
-                TRC(0, jt, 1);
-                tc_fence_after();
-                const uint32_t k = smem_u32(sK + ks * AT2_SLOT_BYTES), q = smem_u32(sQ);
-#pragma unroll
-                for (int s = 0; s < 8; ++s)
-                    umma_ss_f16_cg2(tmem_base + buf * 128,
-                                    umma_desc_kmajor_sw128(q + (s >> 2) * ATT_HALF_BYTES + (s & 3) * 32),
-                                    umma_desc_kmajor_sw128(k + (s >> 2) * 8192 + (s & 3) * 32), IDESC_S, s ? 1u : 0u);
-                umma_commit_cg2(&s_full[buf], 3);
-                umma_commit_cg2(&k_empty[ks], 3);
-                TRC(0, jt, 2);
-                if (++ks == AT3_KSTAGES) { ks = 0; kph ^= 1; }
-            };
-            // Two issuer threads so that neither kind of MMA queues behind the other's dependency:
-            //   warp 1: S(j)  as soon as the stream's S buffer is free (s_free) and K_j has landed
-            //   warp 2: PV(j) as soon as P(j) is in shared memory (p_full) and V_j has landed
-            mbar_wait(q_full, 0);
-            tc_fence_after();
-            issue_S(0, 0);
-            issue_S(1, 1);
-            for (int j = 2; j < n_kv; ++j) {
-                mbar_wait(&s_free[j & 1], ((j - 2) >> 1) & 1);   // S(j-2) of this stream is in registers in both CTAs
-                TRC(0, j, 0);
-                tc_fence_after();
-                issue_S(j & 1, j);
-            }
-        }
-    } else if (warp == 2) {
-        if (lane == 0 && cta_rank == 0) {
-            constexpr uint32_t IDESC_O = umma_idesc_bf16(256, 128, true);   // B = V is MN-major
-            int vs = 0;
-            uint32_t vph = 0;
-            for (int j = 0; j < n_kv; ++j) {
-                const int buf = j & 1;
-                mbar_wait(&v_full[vs], vph);
-                TRC(1, j, 0);
-                mbar_wait(&p_full[buf], (j >> 1) & 1);           // P(j) is in shared memory in both CTAs, O_buf rescaled
-                TRC(1, j, 1);
-                tc_fence_after();
-                const uint32_t v = smem_u32(sV + vs * AT2_SLOT_BYTES), pp = smem_u32(sP + buf * ATT_TILE_BYTES);
-#pragma unroll
-                for (int s = 0; s < 8; ++s)     // 8 x 16 kv rows
-                    umma_ss_f16_cg2(tmem_base + 256 + buf * 128,
-                                    umma_desc_kmajor_sw128(pp + (s >> 2) * ATT_HALF_BYTES + (s & 3) * 32),
-                                    umma_desc_mnmajor_sw128(v + s * 2048, ATT_HALF_BYTES, 1024), IDESC_O,
-                                    (j < 2 && s == 0) ? 0u : 1u);
-                umma_commit_cg2(&pv_done[buf], 3);
-                umma_commit_cg2(&v_empty[vs], 3);
-                TRC(1, j, 2);
-                if (++vs == AT3_VSTAGES) { vs = 0; vph ^= 1; }
-            }
-        }
-    } else if (warp >= 4) {
-        // ================= softmax streams =================
-        const int wg = (warp - 4) >> 2;
-        const int quad = warp & 3;
-        const int r = quad * 32 + lane;
-        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        const uint32_t tS = tmem_base + lane_addr + wg * 128;
-        const uint32_t tO = tmem_base + lane_addr + 256 + wg * 128;
-        uint8_t* prow = sP + wg * ATT_TILE_BYTES + r * 128;
-        const float c = p.scale_log2;
-        const uint64_t c2 = pk2(c, c);
-        float m_ref = -INFINITY;
-        uint64_t l2 = pk2(0.f, 0.f);
-        int it = 0;
-        [[maybe_unused]] const bool traced_all = traced;
-        for (int j = wg; j < n_kv; j += 2, ++it) {
-            [[maybe_unused]] const bool traced = traced_all && lane == 0;
-            const int nv = p.tile_valid ? __ldg(p.tile_valid + j) : kv_valid_rows(p.seq, j);
-            mbar_wait(&s_full[wg], it & 1);
-            TRC(2 + wg * 4 + quad, j, 0);
-            tc_fence_after();
-            uint32_t s[128];
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t(&dst)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[ch * 32]);
-                tmem_ld32(tS + ch * 32, dst);
-            }
-            tmem_ld_wait();
-            TRC(2 + wg * 4 + quad, j, 1);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(leader_smem_u32(&s_free[wg]));   // the tensor pipe may refill S_wg now
-            // ---- row max from registers ----
-            float m0 = -INFINITY, m1 = -INFINITY;
-            if (DBG & 2) {
-                m0 = 0.f;             // timing experiment: no max pass
-            } else if (nv == ATT_TILE) {
-#pragma unroll
-                for (int i = 0; i < 128; i += 4) {
-                    m0 = max3(m0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-                    m1 = max3(m1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 128; ++i)
-                    if (i < nv) m0 = fmaxf(m0, __uint_as_float(s[i]));
-            }
-            const float mx = fmaxf(m0, m1) * c;
-            if (DBG == 4 && mx == 12345.678f) m_ref = 0.f;   // (keeps the stamp below after the max pass)
-            TRC(2 + wg * 4 + quad, j, 2);
-            float alpha = 1.f;
-            const bool grow = mx > m_ref + 8.0f;
-            if (grow) {
-                alpha = fast_exp2(m_ref - mx);
-                m_ref = mx;
-                l2 = fma2(l2, pk2(alpha, alpha), pk2(0.f, 0.f));
-            }
-            const uint64_t nm2 = pk2(-m_ref, -m_ref);
-            // ---- exponentials in place: s[i/2] <- bf16x2(p_i, p_i+1) ----
-            if (nv == ATT_TILE) {
-#pragma unroll
-                for (int i = 0; i < 128; i += 2) {
-                    const uint64_t X = fma2(pk2u(s[i], s[i + 1]), c2, nm2);
-                    float x0, x1, e0, e1;
-                    upk2(X, x0, x1);
-                    if (((i >> 1) & 7) < POLY) {
-                        const uint64_t Xc = pk2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
-                        const uint64_t T = add2(Xc, pk2(12582912.f, 12582912.f));
-                        const uint64_t N = add2(T, pk2(-12582912.f, -12582912.f));
-                        const uint64_t Fr = fma2(N, pk2(-1.f, -1.f), Xc);
-                        uint64_t P = fma2(Fr, pk2(0.0551716574f, 0.0551716574f), pk2(0.2426111400f, 0.2426111400f));
-                        P = fma2(P, Fr, pk2(0.6932609677f, 0.6932609677f));
-                        P = fma2(P, Fr, pk2(0.9999280572f, 0.9999280572f));
-                        float t0, t1, p0, p1;
-                        upk2(T, t0, t1);
-                        upk2(P, p0, p1);
-                        e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-                        e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
-                    } else if (DBG & 1) {     // timing experiment: no MUFU (results are wrong)
-                        e0 = x0 * 0.5f;
-                        e1 = x1 * 0.5f;
-                    } else {
-                        e0 = fast_exp2(x0);
-                        e1 = fast_exp2(x1);
-                    }
-                    l2 = add2(l2, pk2(e0, e1));
-                    s[i >> 1] = pack_bf16(e0, e1);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 128; i += 2) {
-                    float x0, x1;
-                    upk2(fma2(pk2u(s[i], s[i + 1]), c2, nm2), x0, x1);
-                    const float e0 = i < nv ? fast_exp2(x0) : 0.f, e1 = i + 1 < nv ? fast_exp2(x1) : 0.f;
-                    l2 = add2(l2, pk2(e0, e1));
-                    s[i >> 1] = pack_bf16(e0, e1);
-                }
-            }
-            TRC(2 + wg * 4 + quad, j, 3);
-            if (it > 0) {
-                // my previous PV (it reads the P tile and owns O_wg) must have retired before P / O are touched
-                mbar_wait(&pv_done[wg], (it - 1) & 1);
-                TRC(2 + wg * 4 + quad, j, 4);
-                tc_fence_after();
-                if (__any_sync(0xffffffffu, grow)) {
-#pragma unroll 1
-                    for (int ch = 0; ch < 4; ++ch) {
-                        uint32_t o[32];
-                        tmem_ld32(tO + ch * 32, o);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st32(tO + ch * 32, o);
-                    }
-                    tmem_st_wait();
-                }
-            }
-            // P row -> 128B-swizzled K-major tile: kv columns 0-63 in half 0, 64-127 in half 1; 16 B chunk index ^ (row & 7)
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const int chunk = (q & 7) ^ (r & 7);
-                *reinterpret_cast<uint4*>(prow + (q >> 3) * ATT_HALF_BYTES + chunk * 16) =
-                    make_uint4(s[q * 4], s[q * 4 + 1], s[q * 4 + 2], s[q * 4 + 3]);
-            }
-            TRC(2 + wg * 4 + quad, j, 5);
-            fence_proxy_async_smem();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(leader_smem_u32(&p_full[wg]));
-            TRC(2 + wg * 4 + quad, j, 6);
-        }
-        // ---- epilogue: merge the two streams of this row ----
-        float l_lo, l_hi;
-        upk2(l2, l_lo, l_hi);
-        xchg[wg * 128 + r] = make_float2(m_ref, l_lo + l_hi);
-        mbar_wait(&pv_done[wg], (it - 1) & 1);
-        tc_fence_after();
-        tc_fence_before();
-        named_bar_sync(1, 256);
-        tc_fence_after();
-        const float2 mine = xchg[wg * 128 + r], other = xchg[(wg ^ 1) * 128 + r];
-        const float m = fmaxf(mine.x, other.x);
-        const float a_me = fast_exp2(mine.x - m), a_ot = fast_exp2(other.x - m);
-        const float inv = 1.f / (mine.y * a_me + other.y * a_ot);
-        const float f0 = (wg == 0 ? a_me : a_ot) * inv, f1 = (wg == 0 ? a_ot : a_me) * inv;
-        if (q_valid) {
-            const uint32_t tO0 = tmem_base + lane_addr + 256 + wg * 64, tO1 = tO0 + 128;
-            __nv_bfloat16* orow = p.out + (long long)(row_base + q_row0 + r) * D + head * ATT_TILE + wg * 64;
-#pragma unroll 1
-            for (int ch = 0; ch < 2; ++ch) {
-                uint32_t o0[32], o1[32];
-                tmem_ld32(tO0 + ch * 32, o0);
-                tmem_ld32(tO1 + ch * 32, o1);
-                tmem_ld_wait();
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    float v[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        v[i] = __uint_as_float(o0[q4 * 8 + i]) * f0 + __uint_as_float(o1[q4 * 8 + i]) * f1;
-                    *reinterpret_cast<uint4*>(orow + ch * 32 + q4 * 8) =
-                        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                }
-            }
-        }
-    }
-
-    __syncwarp();
-    tc_fence_before();
-    cluster_sync_all();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc_cg2<512>(tmem_base);
-    }
-}
-
-template <int POLY, int DBG>
-static int launch_attn_pair2(const CUtensorMap& tm128, const CUtensorMap& tm64, const AttnDev& p, dim3 grid, cudaStream_t st) {
-    QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(attn_pair2_kernel<POLY, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_SMEM));
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(AT2_THREADS);
-    cfg.dynamicSmemBytes = AT3_SMEM;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_pair2_kernel<POLY, DBG>, tm128, tm64, p));
-    QIE_LAUNCH_OK("attn_pair2_kernel");
-    return QIE_OK;
-}
-
-// =====================================================================================================================
-// CTA-pair attention with 256-wide KV tiles ("pair3").  The trace of pair2 (tools/attn_trace.py, profiles/) showed the
-// tensor pipe itself to be the limiter: a 256 x 128 x 16 SS MMA needs 4 KB of A and 4 KB of B per SM every 64 cycles =
-// 128 B/clk of operand ingest, and runs at ~2/3 of the nominal rate (the GEMM shows the same for block_n 128 vs 256).
+// CTA-pair attention with 256-wide KV tiles (default kernel).  The round-1 traces showed the tensor pipe's operand ingest to be
+// the limiter of 128-wide tiles: a 256 x 128 x 16 SS MMA needs 4 KB of A and 4 KB of B per SM every 64 cycles = 128 B/clk.
 // This kernel raises the arithmetic intensity of both MMAs:
 //   S = Q K_j^T   : one 256 x 256 x 128 SS MMA group per 256 KV rows (96 B/clk of operands, the GEMM main-loop shape)
 //   O += P_j V_j  : P (bf16) lives in TMEM and is the A operand (TS MMA), so only V comes from shared memory (64 B/clk)
@@ -1136,11 +453,11 @@ static int launch_attn_pair2(const CUtensorMap& tm128, const CUtensorMap& tm64, 
 constexpr int AT5_KSTAGES = 3, AT5_VSTAGES = 2;
 constexpr int AT5_THREADS = 384;              // warps 0-7 softmax (two warpgroups), warp 8 TMA, warp 9 MMA issuer, 10-11 idle
 constexpr int AT5_STAGE_BYTES = 32 * 1024;     // K: my 128 kv rows x 128 dims; V: 256 kv rows x my 64 dims
-constexpr int AT5_SMEM = ATT_TILE_BYTES + (AT5_KSTAGES + AT5_VSTAGES) * AT5_STAGE_BYTES + 2048 + 1024 + 2048 + 512 + 1024;
+constexpr int AT5_SMEM = ATT_TILE_BYTES + (AT5_KSTAGES + AT5_VSTAGES) * AT5_STAGE_BYTES + 2048 + 1024 + 512 + 1024;
 
-template <int POLY, int DBG, int PREMAX>
+template <int POLY>
 __global__ void __launch_bounds__(AT5_THREADS, 1)
-attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
+attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;                                       // [2 d-halves][128 rows x 128 B]
@@ -1148,8 +465,7 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
     uint8_t* sV = sK + AT5_KSTAGES * AT5_STAGE_BYTES;         // [V stages][256 kv rows x 128 B (my 64 dims)]
     float* xm = reinterpret_cast<float*>(sV + AT5_VSTAGES * AT5_STAGE_BYTES);   // [2 parities][2 WGs][128 rows] tile max
     float* xl = xm + 512;                                                        // [2 WGs][128 rows] partial row sums
-    float* xr = xl + 256;                                                        // [2 parities][2 WGs][128 rows] running max (scaled)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xr) + 2048);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xl + 256);
     uint64_t* q_full = bars;                       // leader
     uint64_t* k_full = bars + 1;                   // [K stages] leader
     uint64_t* k_empty = k_full + AT5_KSTAGES;      // both
@@ -1173,8 +489,6 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
     const int colQ = head * ATT_TILE, colK = D + head * ATT_TILE, colV = 2 * D + head * ATT_TILE;
     const int row_base = b * rpb;
     griddep_launch_dependents();
-    if (p.run_if && *p.run_if == 0) return;        // exact rerun behind a speculative launch: nothing overflowed, nothing to do
-    [[maybe_unused]] const bool traced = DBG == 4 && p.trace && (blockIdx.x >> 1) == 3 && blockIdx.y == 9 && blockIdx.z == 0;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm128);
@@ -1210,7 +524,6 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
             uint32_t kph = 0, vph = 0;
             auto load_k = [&](int j) {       // my 128 kv rows (half of the 256-row tile) x 128 head dims, two 64-dim halves
                 mbar_wait(&k_empty[ks], kph ^ 1);
-                TRC(10, j, 0);
                 if (cta_rank == 0) mbar_expect_tx(&k_full[ks], 2 * AT5_STAGE_BYTES);
                 const uint32_t bar = leader_smem_u32(&k_full[ks]);
                 for (int hf = 0; hf < 2; ++hf)
@@ -1220,7 +533,6 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
             };
             auto load_v = [&](int j) {       // 256 kv rows x my 64 head dims
                 mbar_wait(&v_empty[vs], vph ^ 1);
-                TRC(10, j, 1);
                 if (cta_rank == 0) mbar_expect_tx(&v_full[vs], 2 * AT5_STAGE_BYTES);
                 const uint32_t bar = leader_smem_u32(&v_full[vs]);
                 for (int hf = 0; hf < 2; ++hf)
@@ -1244,9 +556,8 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
             int ks = 0, vs = 0;
             uint32_t kph = 0, vph = 0;
             const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(sQ));
-            auto issue_S = [&](int jt) {
+            auto issue_S = [&]() {
                 mbar_wait(&k_full[ks], kph);
-                TRC(0, jt, 1);
                 tc_fence_after();
                 const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(sK + ks * AT5_STAGE_BYTES));
 #pragma unroll
@@ -1256,23 +567,19 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
                 }
                 umma_commit_cg2(s_full, 3);
                 umma_commit_cg2(&k_empty[ks], 3);
-                TRC(0, jt, 2);
                 if (++ks == AT5_KSTAGES) { ks = 0; kph ^= 1; }
             };
             mbar_wait(q_full, 0);
             tc_fence_after();
-            issue_S(0);
+            issue_S();
             for (int j = 0; j < n_kv; ++j) {
                 if (j + 1 < n_kv) {
                     mbar_wait(s_free, j & 1);                // S(j) is in registers in both CTAs
-                    TRC(0, j + 1, 0);
                     tc_fence_after();
-                    issue_S(j + 1);
+                    issue_S();
                 }
                 mbar_wait(&v_full[vs], vph);
-                TRC(1, j, 0);
                 mbar_wait(p_full, j & 1);                    // P(j) is in TMEM in both CTAs, O rescaled
-                TRC(1, j, 1);
                 tc_fence_after();
                 const uint64_t dv = umma_desc_mnmajor_sw128(smem_u32(sV + vs * AT5_STAGE_BYTES), ATT_HALF_BYTES, 1024);
 #pragma unroll
@@ -1281,23 +588,9 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
                                     (j == 0 && s == 0) ? 0u : 1u);
                 umma_commit_cg2(pv_done, 3);
                 umma_commit_cg2(&v_empty[vs], 3);
-                TRC(1, j, 2);
                 if (++vs == AT5_VSTAGES) { vs = 0; vph ^= 1; }
             }
         }
-      } else if (warp == 10 && DBG == 4) {
-        // trace build only: an observer that stamps when the S / PV MMA groups really complete
-        if (lane == 0)
-            for (int j = 0; j < n_kv; ++j) {
-                mbar_wait(s_full, j & 1);
-                TRC(1, j, 3);
-            }
-      } else if (warp == 11 && DBG == 4) {
-        if (lane == 0)
-            for (int j = 0; j < n_kv; ++j) {
-                mbar_wait(pv_done, j & 1);
-                TRC(1, j, 4);
-            }
       }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
@@ -1313,27 +606,13 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
         const uint64_t c2 = pk2(c, c);
         float m_ref = -INFINITY;
         uint64_t l2 = pk2(0.f, 0.f);
-        [[maybe_unused]] const bool traced_all = traced;
         auto valid_rows = [&](int t128) -> int {     // valid kv rows of my half of a 256-row tile
             return t128 < n128 ? (p.tile_valid ? __ldg(p.tile_valid + t128) : kv_valid_rows(p.seq, t128)) : 0;
         };
         int nv_next = valid_rows(wg);
-        // Software pipelining of the max pass: while the exponentials of tile j keep the MUFU busy, the row max of tile j+1
-        // (whose S is already complete in TMEM) is reduced on the ALU pipe from 32-column chunks; tile j+1 then starts
-        // its exponentials right after the TMEM load.
-        bool have_pre = false;
-        float pre_max = -INFINITY;
-        // PREMAX == 2, speculative reference: from the second tile on there is no max pass in front of the exponentials.  The
-        // reference is the largest score both warpgroups have seen in EARLIER tiles (exchanged through shared memory one tile
-        // late); the current tile's maximum is tracked inside the exponential loop on the otherwise idle ALU pipe.  Scores above
-        // the reference just give P > 1 (fp32 / bf16 have the range; O and l share the reference, so the result is exact); only a
-        // jump of more than 2^100 within one tile would overflow, which raises p.overflow and reruns the exact kernel.
-        float m_run = -INFINITY;
         for (int j = 0; j < n_kv; ++j) {
-            [[maybe_unused]] const bool traced = traced_all && lane == 0;
             const int nv = nv_next;
             mbar_wait(s_full, j & 1);
-            TRC(2 + wg * 4 + quad, j, 0);
             tc_fence_after();
             uint32_t s[128];
 #pragma unroll
@@ -1343,17 +622,12 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
             }
             nv_next = valid_rows(2 * (j + 1) + wg);          // its constant-bank / global latency hides under the TMEM load
             tmem_ld_wait();
-            TRC(2 + wg * 4 + quad, j, 1);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(leader_smem_u32(s_free));   // the tensor pipe may refill S now
             // ---- row max of my 128 columns, then the row max of the whole 256-wide tile through shared memory ----
-            const bool spec = PREMAX == 2 && j > 0;
             float m0 = -INFINITY, m1 = -INFINITY;
-            if (spec) {
-            } else if (have_pre) {
-                m0 = pre_max;
-            } else if (nv == ATT_TILE) {
+            if (nv == ATT_TILE) {
                 float m2 = -INFINITY, m3 = -INFINITY;     // four chains of 16 instead of two of 32
 #pragma unroll
                 for (int i = 0; i < 128; i += 8) {
@@ -1369,22 +643,10 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
                 for (int i = 0; i < 128; ++i)
                     if (i < nv) m0 = fmaxf(m0, __uint_as_float(s[i]));
             }
-            float mx;
-            if (spec) {
-                named_bar_sync(1 + quad, 64);                 // my partner has published its running max of tile j-1
-                mx = fmaxf(m_run, xr[((j - 1) & 1) * 256 + (wg ^ 1) * 128 + r]);
-            } else {
-                float* xmj = xm + (j & 1) * 256;
-                xmj[wg * 128 + r] = fmaxf(m0, m1);
-                named_bar_sync(1 + quad, 64);                 // only my partner warp (same rows, other warpgroup)
-                mx = fmaxf(fmaxf(m0, m1), xmj[(wg ^ 1) * 128 + r]) * c;
-                if (PREMAX == 2) {
-                    m_run = mx;
-                    xr[(j & 1) * 256 + wg * 128 + r] = mx;
-                }
-            }
-            if (DBG == 4 && mx == 12345.678f) m_ref = 0.f;
-            TRC(2 + wg * 4 + quad, j, 2);
+            float* xmj = xm + (j & 1) * 256;
+            xmj[wg * 128 + r] = fmaxf(m0, m1);
+            named_bar_sync(1 + quad, 64);                 // only my partner warp (same rows, other warpgroup)
+            const float mx = fmaxf(fmaxf(m0, m1), xmj[(wg ^ 1) * 128 + r]) * c;
             float alpha = 1.f;
             const bool grow = mx > m_ref + 8.0f;      // identical decision in both warpgroups (same row, same inputs)
             if (grow) {
@@ -1394,46 +656,14 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
             }
             const uint64_t nm2 = pk2(-m_ref, -m_ref);
             // ---- exponentials in place: s[i/2] <- bf16x2(p_i, p_i+1) ----
-            have_pre = false;
-            [[maybe_unused]] float xt0 = -INFINITY, xt1 = -INFINITY;      // max of (score - reference) over my columns of this tile
             if (nv == ATT_TILE) {
-                const bool can_pre = PREMAX == 1 && j + 1 < n_kv && nv_next == ATT_TILE;
-                bool pre_on = false;
-                int pre_done = 0;
-                float q0 = -INFINITY, q1 = -INFINITY, q2 = -INFINITY, q3 = -INFINITY;
-                auto premax_to = [&](int target) {
-                    if (can_pre && !pre_on) {
-                        pre_on = __all_sync(0xffffffffu, mbar_test_wait(s_full, (j + 1) & 1));   // S(j+1) complete? (non-blocking)
-                        if (pre_on) tc_fence_after();
-                    }
-                    if (pre_on) {
-#pragma unroll 1
-                        for (; pre_done < target; ++pre_done) {
-                            uint32_t t[32];
-                            tmem_ld32(tS + pre_done * 32, t);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int i = 0; i < 32; i += 8) {
-                                q0 = max3(q0, __uint_as_float(t[i]), __uint_as_float(t[i + 1]));
-                                q1 = max3(q1, __uint_as_float(t[i + 2]), __uint_as_float(t[i + 3]));
-                                q2 = max3(q2, __uint_as_float(t[i + 4]), __uint_as_float(t[i + 5]));
-                                q3 = max3(q3, __uint_as_float(t[i + 6]), __uint_as_float(t[i + 7]));
-                            }
-                        }
-                    }
-                };
 #pragma unroll
                 for (int i = 0; i < 128; i += 2) {
-                    if (i == 64) premax_to(2);
-                    if (i == 96) premax_to(3);
                     const uint64_t X = fma2(pk2u(s[i], s[i + 1]), c2, nm2);
                     float x0, x1, e0, e1;
                     upk2(X, x0, x1);
-                    if (PREMAX == 2) {
-                        if (i & 2) xt1 = max3(xt1, x0, x1);
-                        else xt0 = max3(xt0, x0, x1);
-                    }
                     if (((i >> 1) & 7) < POLY) {
+                        // FMA-pipe exp2 (the MUFU is the co-bottleneck): x = n + f, 2^f by a degree-3 polynomial, 2^n via the exponent
                         const uint64_t Xc = pk2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
                         const uint64_t T = add2(Xc, pk2(12582912.f, 12582912.f));
                         const uint64_t N = add2(T, pk2(-12582912.f, -12582912.f));
@@ -1453,36 +683,19 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
                     l2 = add2(l2, pk2(e0, e1));
                     s[i >> 1] = pack_bf16(e0, e1);
                 }
-                premax_to(4);
-                if (pre_on) {
-                    have_pre = true;
-                    pre_max = fmaxf(fmaxf(q0, q1), fmaxf(q2, q3));
-                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 128; i += 2) {
                     float x0, x1;
                     upk2(fma2(pk2u(s[i], s[i + 1]), c2, nm2), x0, x1);
                     const float e0 = i < nv ? fast_exp2(x0) : 0.f, e1 = i + 1 < nv ? fast_exp2(x1) : 0.f;
-                    if (PREMAX == 2) {
-                        if (i < nv) xt0 = fmaxf(xt0, x0);
-                        if (i + 1 < nv) xt1 = fmaxf(xt1, x1);
-                    }
                     l2 = add2(l2, pk2(e0, e1));
                     s[i >> 1] = pack_bf16(e0, e1);
                 }
             }
-            if (spec) {
-                const float xmax = fmaxf(xt0, xt1);
-                m_run = fmaxf(m_run, xmax + m_ref);
-                xr[(j & 1) * 256 + wg * 128 + r] = m_run;
-                if (__any_sync(0xffffffffu, xmax > 100.f) && lane == 0) atomicOr(p.overflow, 1);
-            }
-            TRC(2 + wg * 4 + quad, j, 3);
             if (j > 0) {
                 // PV(j-1) reads the P buffer and owns O: it must have retired before either is touched
                 mbar_wait(pv_done, (j - 1) & 1);
-                TRC(2 + wg * 4 + quad, j, 4);
                 tc_fence_after();
                 if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll 1
@@ -1503,12 +716,9 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
                 tmem_st32(tP + 32, hi);
                 tmem_st_wait();
             }
-            TRC(2 + wg * 4 + quad, j, 5);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(leader_smem_u32(p_full));
-            TRC(2 + wg * 4 + quad, j, 6);
-            TRC(2 + wg * 4 + quad, j, 7);
         }
         // ---- epilogue: O / (l_wg0 + l_wg1) -> bf16 -> global; warpgroup wg stores head dims [64 wg, 64 wg + 64) ----
         float l_lo, l_hi;
@@ -1518,13 +728,28 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
         tc_fence_after();
         named_bar_sync(1 + quad, 64);
         const float inv = 1.f / (xl[r] + xl[128 + r]);
-        if (q_valid) {
-            __nv_bfloat16* orow = p.out + (long long)(row_base + q_row0 + r) * D + head * ATT_TILE + wg * 64;
-            if (p.peer_out) {      // a 128-row query tile never straddles two ranks' shards (sp_rows % 128 == 0)
-                const int srank = q_row0 / p.sp_rows;
-                orow = reinterpret_cast<__nv_bfloat16*>(__ldg(reinterpret_cast<const unsigned long long*>(p.peer_out) + srank)) +
-                       (long long)(q_row0 - srank * p.sp_rows + r) * p.out_ld + (p.head_off + head) * ATT_TILE + wg * 64;
+        bool store = q_valid;
+        __nv_bfloat16* orow = p.out + (long long)(row_base + q_row0 + r) * D + head * ATT_TILE + wg * 64;
+        if (p.peer_out && q_valid) {
+            // gathered sequence-parallel layout: this row's token is owned by rank `srank` (see AttnDev); NVLink peer store
+            const int qg = q_row0 + r;
+            int srank, local;
+            if (qg < p.sp_img_region) {
+                srank = qg / p.sp_img_pad;
+                local = qg - srank * p.sp_img_pad;
+            } else {
+                const int t = qg - p.sp_img_region, cut = p.sp_txt_rem * (p.sp_txt_base + 1);
+                store = t < p.sp_txt_total;               // pad rows of the text region belong to nobody
+                int first;
+                if (t < cut) { srank = t / (p.sp_txt_base + 1); first = srank * (p.sp_txt_base + 1); }
+                else { srank = p.sp_txt_rem + (t - cut) / p.sp_txt_base; first = cut + (srank - p.sp_txt_rem) * p.sp_txt_base; }
+                local = p.sp_img_pad + (t - first);
             }
+            if (store)
+                orow = reinterpret_cast<__nv_bfloat16*>(__ldg(reinterpret_cast<const unsigned long long*>(p.peer_out) + srank)) +
+                       ((long long)b * p.sp_rows_pad + local) * p.out_ld + (p.head_off + head) * ATT_TILE + wg * 64;
+        }
+        if (store) {
 #pragma unroll 1
             for (int ch = 0; ch < 2; ++ch) {
                 uint32_t o[32];
@@ -1551,9 +776,9 @@ attn_pair3_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
     }
 }
 
-template <int POLY, int DBG, int PREMAX>
-static int launch_attn_pair3(const CUtensorMap& tm128, const AttnDev& p, dim3 grid, cudaStream_t st) {
-    QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(attn_pair3_kernel<POLY, DBG, PREMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT5_SMEM));
+template <int POLY>
+static int launch_attn_pair(const CUtensorMap& tm128, const AttnDev& p, dim3 grid, cudaStream_t st) {
+    QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(attn_pair_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT5_SMEM));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(AT5_THREADS);
@@ -1561,691 +786,8 @@ static int launch_attn_pair3(const CUtensorMap& tm128, const AttnDev& p, dim3 gr
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     cfg.attrs = attr;
-    cfg.numAttrs = launch_attrs(attr, 2, /*pdl_ok=*/p.run_if == nullptr);   // the exact rerun reads its flag on entry
-    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_pair3_kernel<POLY, DBG, PREMAX>, tm128, p));
-    QIE_LAUNCH_OK("attn_pair3_kernel");
-    return QIE_OK;
-}
-
-// =====================================================================================================================
-// Persistent form of pair3 ("pair3p", variant 0x1024): one CTA pair per TPC loops over work units (256 query rows of one
-// (batch, head)), so barrier set-up, TMEM allocation and the cluster syncs are paid once per launch, and the unit boundary is
-// pipelined: the producer loads the next unit's Q as soon as the last S MMA of the current unit has retired (q_empty), the K/V
-// rings simply continue, the issuer runs S(0) of the next unit under the last softmax / PV / epilogue of the current one
-// and only the first PV of a unit waits for the epilogue to have read O (o_free).  All tile barriers keep toggling across
-// units (parity = running tile count).  Same arithmetic as attn_pair3_kernel<POLY, 0, 0>.
-// =====================================================================================================================
-constexpr int AT7_SMEM = AT5_SMEM + 64;
-
-template <int POLY>
-__global__ void __launch_bounds__(AT5_THREADS, 1)
-attn_pair3p_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;
-    uint8_t* sK = smem + ATT_TILE_BYTES;
-    uint8_t* sV = sK + AT5_KSTAGES * AT5_STAGE_BYTES;
-    float* xm = reinterpret_cast<float*>(sV + AT5_VSTAGES * AT5_STAGE_BYTES);   // [2 parities][2 WGs][128 rows] tile max
-    float* xl = xm + 512;                                                        // [2 parities][2 WGs][128 rows] partial row sums
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xl) + 2048);
-    uint64_t* q_full = bars;                       // leader
-    uint64_t* q_empty = bars + 1;                  // both: the S MMAs of a unit have retired, sQ may be overwritten
-    uint64_t* k_full = bars + 2;
-    uint64_t* k_empty = k_full + AT5_KSTAGES;
-    uint64_t* v_full = k_empty + AT5_KSTAGES;
-    uint64_t* v_empty = v_full + AT5_VSTAGES;
-    uint64_t* s_full = v_empty + AT5_VSTAGES;
-    uint64_t* s_free = s_full + 1;                 // leader, 16 warp arrivals
-    uint64_t* p_full = s_free + 1;                 // leader, 16 warp arrivals
-    uint64_t* pv_done = p_full + 1;
-    uint64_t* o_free = pv_done + 1;                // leader, 16 warp arrivals: the epilogue has read O
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
-
-    const int warp = threadIdx.x >> 5, lane = lane_id();
-    const int cta_rank = (int)cluster_ctarank();
-    const int rpb = p.seq.img_pad + p.seq.txt_pad;
-    const int n128 = rpb / ATT_TILE;
-    const int n_kv = (n128 + 1) / 2;
-    const int nq = (rpb + 255) / 256;
-    const int D = p.H * ATT_TILE;
-    const int n_units = nq * p.H * p.seq.batch;
-    const int unit0 = blockIdx.x >> 1, unit_step = gridDim.x >> 1;
-
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tm128);
-        mbar_init(q_full, 1);
-        mbar_init(q_empty, 1);
-        for (int i = 0; i < AT5_KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
-        for (int i = 0; i < AT5_VSTAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-        mbar_init(s_full, 1);
-        mbar_init(s_free, 16);
-        mbar_init(p_full, 16);
-        mbar_init(pv_done, 1);
-        mbar_init(o_free, 16);
-        fence_barrier_init();
-    }
-    if (warp == 9) tmem_alloc_cg2<512>(tmem_slot);
-    tc_fence_before();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t COL_S = 128, COL_P = 384;
-
-    if (warp >= 8) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-      if (warp == 8) {
-        if (lane == 0) {
-            // ================= TMA producer =================
-            int ks = 0, vs = 0;
-            uint32_t kph = 0, vph = 0;
-            int nu = 0;
-            for (int u = unit0; u < n_units; u += unit_step, ++nu) {
-                const int qp = u % nq, head = (u / nq) % p.H, b = u / (nq * p.H);
-                const int row_base = b * rpb;
-                const int colQ = head * ATT_TILE, colK = D + head * ATT_TILE, colV = 2 * D + head * ATT_TILE;
-                int qr = qp * 256 + cta_rank * ATT_TILE;
-                if (qr >= rpb) qr = 0;
-                if (nu > 0) mbar_wait(q_empty, (nu - 1) & 1);            // the previous unit's S MMAs are done with sQ
-                if (cta_rank == 0) mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
-                for (int hf = 0; hf < 2; ++hf)
-                    tma_load_2d_cg2(sQ + hf * ATT_HALF_BYTES, &tm128, colQ + hf * 64, row_base + qr, leader_smem_u32(q_full));
-                auto load_k = [&](int j) {
-                    mbar_wait(&k_empty[ks], kph ^ 1);
-                    if (cta_rank == 0) mbar_expect_tx(&k_full[ks], 2 * AT5_STAGE_BYTES);
-                    const uint32_t bar = leader_smem_u32(&k_full[ks]);
-                    for (int hf = 0; hf < 2; ++hf)
-                        tma_load_2d_cg2(sK + ks * AT5_STAGE_BYTES + hf * ATT_HALF_BYTES, &tm128, colK + hf * 64,
-                                        row_base + j * 256 + cta_rank * ATT_TILE, bar);
-                    if (++ks == AT5_KSTAGES) { ks = 0; kph ^= 1; }
-                };
-                auto load_v = [&](int j) {
-                    mbar_wait(&v_empty[vs], vph ^ 1);
-                    if (cta_rank == 0) mbar_expect_tx(&v_full[vs], 2 * AT5_STAGE_BYTES);
-                    const uint32_t bar = leader_smem_u32(&v_full[vs]);
-                    for (int hf = 0; hf < 2; ++hf)
-                        tma_load_2d_cg2(sV + vs * AT5_STAGE_BYTES + hf * ATT_HALF_BYTES, &tm128, colV + cta_rank * 64,
-                                        row_base + j * 256 + hf * ATT_TILE, bar);
-                    if (++vs == AT5_VSTAGES) { vs = 0; vph ^= 1; }
-                };
-                load_k(0);
-                for (int j = 0; j < n_kv; ++j) {
-                    if (j + 1 < n_kv) load_k(j + 1);
-                    load_v(j);
-                }
-            }
-        }
-      } else if (warp == 9) {
-        if (lane == 0 && cta_rank == 0) {
-            // ================= MMA issuer (leader) =================
-            constexpr uint32_t IDESC_S = umma_idesc_bf16(256, 256, false);
-            constexpr uint32_t IDESC_O = umma_idesc_bf16(256, 128, true);
-            int ks = 0, vs = 0;
-            uint32_t kph = 0, vph = 0;
-            const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(sQ));
-            auto issue_S = [&](bool last_of_unit) {
-                mbar_wait(&k_full[ks], kph);
-                tc_fence_after();
-                const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(sK + ks * AT5_STAGE_BYTES));
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    const uint64_t off = (uint64_t)(((s >> 2) * ATT_HALF_BYTES + (s & 3) * 32) >> 4);
-                    umma_ss_f16_cg2(tmem_base + COL_S, dq + off, dk + off, IDESC_S, s ? 1u : 0u);
-                }
-                umma_commit_cg2(s_full, 3);
-                umma_commit_cg2(&k_empty[ks], 3);
-                if (last_of_unit) umma_commit_cg2(q_empty, 3);
-                if (++ks == AT5_KSTAGES) { ks = 0; kph ^= 1; }
-            };
-            int t = 0, nu = 0;                      // running tile / unit counts: barrier parities continue across units
-            for (int u = unit0; u < n_units; u += unit_step, ++nu) {
-                mbar_wait(q_full, nu & 1);
-                tc_fence_after();
-                if (t > 0) {                        // S(0) of this unit reuses the S buffer: the last tile of the previous unit is in registers
-                    mbar_wait(s_free, (t - 1) & 1);
-                    tc_fence_after();
-                }
-                issue_S(n_kv == 1);
-                for (int j = 0; j < n_kv; ++j, ++t) {
-                    if (j + 1 < n_kv) {
-                        mbar_wait(s_free, t & 1);
-                        tc_fence_after();
-                        issue_S(j + 2 == n_kv);
-                    }
-                    mbar_wait(&v_full[vs], vph);
-                    mbar_wait(p_full, t & 1);
-                    if (j == 0 && nu > 0) mbar_wait(o_free, (nu - 1) & 1);   // the previous unit's epilogue has read O
-                    tc_fence_after();
-                    const uint64_t dv = umma_desc_mnmajor_sw128(smem_u32(sV + vs * AT5_STAGE_BYTES), ATT_HALF_BYTES, 1024);
-#pragma unroll
-                    for (int s = 0; s < 16; ++s)
-                        umma_ts_f16_cg2(tmem_base, tmem_base + COL_P + s * 8, dv + (uint64_t)(s * 128), IDESC_O,
-                                        (j == 0 && s == 0) ? 0u : 1u);
-                    umma_commit_cg2(pv_done, 3);
-                    umma_commit_cg2(&v_empty[vs], 3);
-                    if (++vs == AT5_VSTAGES) { vs = 0; vph ^= 1; }
-                }
-            }
-        }
-      }
-    } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-        // ================= softmax (warps 0-7) =================
-        const int wg = warp >> 2;
-        const int quad = warp & 3;
-        const int r = quad * 32 + lane;
-        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        const uint32_t tS = tmem_base + lane_addr + COL_S + wg * 128;
-        const uint32_t tP = tmem_base + lane_addr + COL_P + wg * 64;
-        const uint32_t tO = tmem_base + lane_addr + wg * 64;
-        const float c = p.scale_log2;
-        const uint64_t c2 = pk2(c, c);
-        auto valid_rows = [&](int t128) -> int {
-            return t128 < n128 ? (p.tile_valid ? __ldg(p.tile_valid + t128) : kv_valid_rows(p.seq, t128)) : 0;
-        };
-        int t = 0, nu = 0;
-        for (int u = unit0; u < n_units; u += unit_step, ++nu) {
-            const int qp = u % nq, head = (u / nq) % p.H, b = u / (nq * p.H);
-            const int row_base = b * rpb;
-            const int q_row0 = qp * 256 + cta_rank * ATT_TILE;
-            const bool q_valid = q_row0 < rpb;
-            float m_ref = -INFINITY;
-            uint64_t l2 = pk2(0.f, 0.f);
-            int nv_next = valid_rows(wg);
-            for (int j = 0; j < n_kv; ++j, ++t) {
-                const int nv = nv_next;
-                mbar_wait(s_full, t & 1);
-                tc_fence_after();
-                uint32_t s[128];
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t(&dst)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[ch * 32]);
-                    tmem_ld32(tS + ch * 32, dst);
-                }
-                nv_next = valid_rows(2 * (j + 1) + wg);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(leader_smem_u32(s_free));
-                float m0 = -INFINITY, m1 = -INFINITY;
-                if (nv == ATT_TILE) {
-                    float m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-                    for (int i = 0; i < 128; i += 8) {
-                        m0 = max3(m0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-                        m1 = max3(m1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-                        m2 = max3(m2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
-                        m3 = max3(m3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
-                    }
-                    m0 = fmaxf(m0, m2);
-                    m1 = fmaxf(m1, m3);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 128; ++i)
-                        if (i < nv) m0 = fmaxf(m0, __uint_as_float(s[i]));
-                }
-                float* xmj = xm + (t & 1) * 256;
-                xmj[wg * 128 + r] = fmaxf(m0, m1);
-                named_bar_sync(1 + quad, 64);
-                const float mx = fmaxf(fmaxf(m0, m1), xmj[(wg ^ 1) * 128 + r]) * c;
-                float alpha = 1.f;
-                const bool grow = mx > m_ref + 8.0f;
-                if (grow) {
-                    alpha = fast_exp2(m_ref - mx);
-                    m_ref = mx;
-                    l2 = fma2(l2, pk2(alpha, alpha), pk2(0.f, 0.f));
-                }
-                const uint64_t nm2 = pk2(-m_ref, -m_ref);
-                if (nv == ATT_TILE) {
-#pragma unroll
-                    for (int i = 0; i < 128; i += 2) {
-                        const uint64_t X = fma2(pk2u(s[i], s[i + 1]), c2, nm2);
-                        float x0, x1, e0, e1;
-                        upk2(X, x0, x1);
-                        if (((i >> 1) & 7) < POLY) {
-                            const uint64_t Xc = pk2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
-                            const uint64_t T = add2(Xc, pk2(12582912.f, 12582912.f));
-                            const uint64_t N = add2(T, pk2(-12582912.f, -12582912.f));
-                            const uint64_t Fr = fma2(N, pk2(-1.f, -1.f), Xc);
-                            uint64_t P = fma2(Fr, pk2(0.0551716574f, 0.0551716574f), pk2(0.2426111400f, 0.2426111400f));
-                            P = fma2(P, Fr, pk2(0.6932609677f, 0.6932609677f));
-                            P = fma2(P, Fr, pk2(0.9999280572f, 0.9999280572f));
-                            float t0, t1, p0, p1;
-                            upk2(T, t0, t1);
-                            upk2(P, p0, p1);
-                            e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-                            e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
-                        } else {
-                            e0 = fast_exp2(x0);
-                            e1 = fast_exp2(x1);
-                        }
-                        l2 = add2(l2, pk2(e0, e1));
-                        s[i >> 1] = pack_bf16(e0, e1);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 128; i += 2) {
-                        float x0, x1;
-                        upk2(fma2(pk2u(s[i], s[i + 1]), c2, nm2), x0, x1);
-                        const float e0 = i < nv ? fast_exp2(x0) : 0.f, e1 = i + 1 < nv ? fast_exp2(x1) : 0.f;
-                        l2 = add2(l2, pk2(e0, e1));
-                        s[i >> 1] = pack_bf16(e0, e1);
-                    }
-                }
-                if (j > 0) {
-                    // PV(j-1) reads the P buffer and owns O: it must have retired before either is touched
-                    mbar_wait(pv_done, (t - 1) & 1);
-                    tc_fence_after();
-                    if (__any_sync(0xffffffffu, grow)) {
-#pragma unroll 1
-                        for (int ch = 0; ch < 2; ++ch) {
-                            uint32_t o[32];
-                            tmem_ld32(tO + ch * 32, o);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                            tmem_st32(tO + ch * 32, o);
-                        }
-                    }
-                }
-                // (j == 0: the last PV of the previous unit retired before this unit's epilogue-free P buffer is written —
-                //  the softmax warps waited for it in that unit's epilogue)
-                {
-                    uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
-                    uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
-                    tmem_st32(tP, lo);
-                    tmem_st32(tP + 32, hi);
-                    tmem_st_wait();
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(leader_smem_u32(p_full));
-            }
-            // ---- epilogue of the unit ----
-            float l_lo, l_hi;
-            upk2(l2, l_lo, l_hi);
-            float* xlu = xl + (nu & 1) * 256;
-            xlu[wg * 128 + r] = l_lo + l_hi;
-            mbar_wait(pv_done, (t - 1) & 1);
-            tc_fence_after();
-            named_bar_sync(1 + quad, 64);
-            const float inv = 1.f / (xlu[r] + xlu[128 + r]);
-            uint32_t o0[32], o1[32];
-            tmem_ld32(tO, o0);
-            tmem_ld32(tO + 32, o1);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(leader_smem_u32(o_free));      // O may be overwritten by the next unit's PV(0)
-            if (q_valid) {
-                __nv_bfloat16* orow = p.out + (long long)(row_base + q_row0 + r) * D + head * ATT_TILE + wg * 64;
-                if (p.peer_out) {
-                    const int srank = q_row0 / p.sp_rows;
-                    orow = reinterpret_cast<__nv_bfloat16*>(__ldg(reinterpret_cast<const unsigned long long*>(p.peer_out) + srank)) +
-                           (long long)(q_row0 - srank * p.sp_rows + r) * p.out_ld + (p.head_off + head) * ATT_TILE + wg * 64;
-                }
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    float v[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(o0[q4 * 8 + i]) * inv;
-                    *reinterpret_cast<uint4*>(orow + q4 * 8) =
-                        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                }
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    float v[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(o1[q4 * 8 + i]) * inv;
-                    *reinterpret_cast<uint4*>(orow + 32 + q4 * 8) =
-                        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                }
-            }
-        }
-    }
-
-    __syncwarp();
-    tc_fence_before();
-    cluster_sync_all();
-    if (warp == 9) {
-        tc_fence_after();
-        tmem_dealloc_cg2<512>(tmem_base);
-    }
-}
-
-template <int POLY>
-static int launch_attn_pair3p(const CUtensorMap& tm128, const AttnDev& p, int n_units, cudaStream_t st) {
-    QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(attn_pair3p_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT7_SMEM));
-    int clusters = sm_count() / 2;
-    if (clusters > n_units) clusters = n_units;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(AT5_THREADS);
-    cfg.dynamicSmemBytes = AT7_SMEM;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_pair3p_kernel<POLY>, tm128, p));
-    QIE_LAUNCH_OK("attn_pair3p_kernel");
-    return QIE_OK;
-}
-
-// =====================================================================================================================
-// Decoupled single-CTA kernel ("dq"): two 128-row Q tiles per CTA (as attn_kernel), all barriers CTA-local, and the
-// softmax <-> tensor-pipe chain cut as in pair2: the S row goes to registers at once and the S buffer is released
-// (s_free) so S_t(j+1) runs while the exponentials of tile j are computed; P goes through a swizzled smem tile (SS PV).
-// Issue order: S0(0) S1(0) | S0(j+1) S1(j+1) PV0(j) PV1(j) | ...   Ring order: K0, K1, V0, K2, V1, ...
-// =====================================================================================================================
-constexpr int AT4_STAGES = 3;
-constexpr int AT4_SMEM = (4 + AT4_STAGES) * ATT_TILE_BYTES + 512 + 1024;
-
-template <int POLY>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
-attn_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                                   // [2 tiles][2 halves][128 x 128 B]
-    uint8_t* sP = smem + 2 * ATT_TILE_BYTES;              // [2 tiles][2 halves]
-    uint8_t* sKV = smem + 4 * ATT_TILE_BYTES;             // [stages][2 halves]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (4 + AT4_STAGES) * ATT_TILE_BYTES);
-    uint64_t* q_full = bars;
-    uint64_t* kv_full = bars + 1;
-    uint64_t* kv_empty = kv_full + AT4_STAGES;
-    uint64_t* s_full = kv_empty + AT4_STAGES;      // [2]
-    uint64_t* s_free = s_full + 2;                 // [2] 4 warp arrivals
-    uint64_t* p_full = s_free + 2;                 // [2] 4 warp arrivals
-    uint64_t* pv_done = p_full + 2;                // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
-
-    const int warp = threadIdx.x >> 5, lane = lane_id();
-    const int rpb = p.seq.img_pad + p.seq.txt_pad;
-    const int n_kv = rpb / ATT_TILE;
-    const int head = blockIdx.y, b = blockIdx.z;
-    const int q_row0 = blockIdx.x * 2 * ATT_TILE;
-    const bool tile1_on = q_row0 + ATT_TILE < rpb;
-    const int nt = tile1_on ? 2 : 1;
-    const int D = p.H * ATT_TILE;
-    const int colQ = head * ATT_TILE, colK = D + head * ATT_TILE, colV = 2 * D + head * ATT_TILE;
-    const int row_base = b * rpb;
-
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tmQKV);
-        mbar_init(q_full, 1);
-        for (int i = 0; i < AT4_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-        for (int t = 0; t < 2; ++t) {
-            mbar_init(&s_full[t], 1);
-            mbar_init(&s_free[t], 4);
-            mbar_init(&p_full[t], 4);
-            mbar_init(&pv_done[t], 1);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc<512>(tmem_slot);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            // ================= TMA producer: Q tiles, then K0, K1, V0, K2, V1, ... =================
-            mbar_expect_tx(q_full, nt * ATT_TILE_BYTES);
-            for (int t = 0; t < nt; ++t)
-                for (int hf = 0; hf < 2; ++hf)
-                    tma_load_2d(sQ + t * ATT_TILE_BYTES + hf * ATT_HALF_BYTES, &tmQKV, colQ + hf * 64,
-                                row_base + q_row0 + t * ATT_TILE, q_full);
-            int stage = 0;
-            uint32_t phase = 0;
-            auto load = [&](int col, int j) {
-                mbar_wait(&kv_empty[stage], phase ^ 1);
-                mbar_expect_tx(&kv_full[stage], ATT_TILE_BYTES);
-                for (int hf = 0; hf < 2; ++hf)
-                    tma_load_2d(sKV + stage * ATT_TILE_BYTES + hf * ATT_HALF_BYTES, &tmQKV, col + hf * 64,
-                                row_base + j * ATT_TILE, &kv_full[stage]);
-                if (++stage == AT4_STAGES) { stage = 0; phase ^= 1; }
-            };
-            load(colK, 0);
-            for (int j = 0; j < n_kv; ++j) {
-                if (j + 1 < n_kv) load(colK, j + 1);
-                load(colV, j);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // ================= MMA issuer =================
-            constexpr uint32_t IDESC_S = umma_idesc_bf16(128, 128, false);
-            constexpr uint32_t IDESC_O = umma_idesc_bf16(128, 128, true);
-            int stage = 0;
-            uint32_t phase = 0;
-            auto wait_slot = [&]() -> uint32_t {
-                mbar_wait(&kv_full[stage], phase);
-                tc_fence_after();
-                return smem_u32(sKV + stage * ATT_TILE_BYTES);
-            };
-            auto release_slot = [&]() {
-                umma_commit(&kv_empty[stage]);
-                if (++stage == AT4_STAGES) { stage = 0; phase ^= 1; }
-            };
-            auto issue_S = [&](int t, uint32_t k) {
-                const uint32_t q = smem_u32(sQ + t * ATT_TILE_BYTES);
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    const uint32_t off = (s >> 2) * ATT_HALF_BYTES + (s & 3) * 32;
-                    umma_ss_f16(tmem_base + t * 128, umma_desc_kmajor_sw128(q + off), umma_desc_kmajor_sw128(k + off),
-                                IDESC_S, s ? 1u : 0u);
-                }
-                umma_commit(&s_full[t]);
-            };
-            auto issue_PV = [&](int t, uint32_t v, bool first) {
-                const uint32_t pp = smem_u32(sP + t * ATT_TILE_BYTES);
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    const uint32_t aoff = (s >> 2) * ATT_HALF_BYTES + (s & 3) * 32;
-                    umma_ss_f16(tmem_base + 256 + t * 128, umma_desc_kmajor_sw128(pp + aoff),
-                                umma_desc_mnmajor_sw128(v + s * 2048, ATT_HALF_BYTES, 1024), IDESC_O,
-                                (first && s == 0) ? 0u : 1u);
-                }
-                umma_commit(&pv_done[t]);
-            };
-            mbar_wait(q_full, 0);
-            tc_fence_after();
-            {
-                const uint32_t k = wait_slot();
-                for (int t = 0; t < nt; ++t) issue_S(t, k);
-                release_slot();
-            }
-            for (int j = 0; j < n_kv; ++j) {
-                if (j + 1 < n_kv) {
-                    const uint32_t k = wait_slot();
-                    for (int t = 0; t < nt; ++t) {
-                        mbar_wait(&s_free[t], j & 1);          // S_t(j) is in registers
-                        tc_fence_after();
-                        issue_S(t, k);
-                    }
-                    release_slot();
-                }
-                const uint32_t v = wait_slot();
-                for (int t = 0; t < nt; ++t) {
-                    mbar_wait(&p_full[t], j & 1);              // P_t(j) in smem, O_t rescaled
-                    tc_fence_after();
-                    issue_PV(t, v, j == 0);
-                }
-                release_slot();
-            }
-        }
-    } else if (warp >= 4) {
-        // ================= softmax warpgroups (one per Q tile) =================
-        const int t = (warp - 4) >> 2;
-        if (t == 0 || tile1_on) {
-            const int quad = warp & 3;
-            const int r = quad * 32 + lane;
-            const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-            const uint32_t tS = tmem_base + lane_addr + t * 128;
-            const uint32_t tO = tmem_base + lane_addr + 256 + t * 128;
-            uint8_t* prow = sP + t * ATT_TILE_BYTES + r * 128;
-            const float c = p.scale_log2;
-            const uint64_t c2 = pk2(c, c);
-            float m_ref = -INFINITY;
-            uint64_t l2 = pk2(0.f, 0.f);
-            for (int j = 0; j < n_kv; ++j) {
-                const int nv = p.tile_valid ? __ldg(p.tile_valid + j) : kv_valid_rows(p.seq, j);
-                mbar_wait(&s_full[t], j & 1);
-                tc_fence_after();
-                uint32_t s[128];
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t(&dst)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[ch * 32]);
-                    tmem_ld32(tS + ch * 32, dst);
-                }
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s_free[t]);        // the tensor pipe may refill S_t now
-                float m0 = -INFINITY, m1 = -INFINITY;
-                if (nv == ATT_TILE) {
-#pragma unroll
-                    for (int i = 0; i < 128; i += 4) {
-                        m0 = max3(m0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-                        m1 = max3(m1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 128; ++i)
-                        if (i < nv) m0 = fmaxf(m0, __uint_as_float(s[i]));
-                }
-                const float mx = fmaxf(m0, m1) * c;
-                float alpha = 1.f;
-                const bool grow = mx > m_ref + 8.0f;
-                if (grow) {
-                    alpha = fast_exp2(m_ref - mx);
-                    m_ref = mx;
-                    l2 = fma2(l2, pk2(alpha, alpha), pk2(0.f, 0.f));
-                }
-                const uint64_t nm2 = pk2(-m_ref, -m_ref);
-                if (nv == ATT_TILE) {
-#pragma unroll
-                    for (int i = 0; i < 128; i += 2) {
-                        const uint64_t X = fma2(pk2u(s[i], s[i + 1]), c2, nm2);
-                        float x0, x1, e0, e1;
-                        upk2(X, x0, x1);
-                        if (((i >> 1) & 7) < POLY) {
-                            const uint64_t Xc = pk2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
-                            const uint64_t T = add2(Xc, pk2(12582912.f, 12582912.f));
-                            const uint64_t N = add2(T, pk2(-12582912.f, -12582912.f));
-                            const uint64_t Fr = fma2(N, pk2(-1.f, -1.f), Xc);
-                            uint64_t P = fma2(Fr, pk2(0.0551716574f, 0.0551716574f), pk2(0.2426111400f, 0.2426111400f));
-                            P = fma2(P, Fr, pk2(0.6932609677f, 0.6932609677f));
-                            P = fma2(P, Fr, pk2(0.9999280572f, 0.9999280572f));
-                            float t0, t1, p0, p1;
-                            upk2(T, t0, t1);
-                            upk2(P, p0, p1);
-                            e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-                            e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
-                        } else {
-                            e0 = fast_exp2(x0);
-                            e1 = fast_exp2(x1);
-                        }
-                        l2 = add2(l2, pk2(e0, e1));
-                        s[i >> 1] = pack_bf16(e0, e1);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 128; i += 2) {
-                        float x0, x1;
-                        upk2(fma2(pk2u(s[i], s[i + 1]), c2, nm2), x0, x1);
-                        const float e0 = i < nv ? fast_exp2(x0) : 0.f, e1 = i + 1 < nv ? fast_exp2(x1) : 0.f;
-                        l2 = add2(l2, pk2(e0, e1));
-                        s[i >> 1] = pack_bf16(e0, e1);
-                    }
-                }
-                if (j > 0) {
-                    mbar_wait(&pv_done[t], (j - 1) & 1);       // PV_t(j-1) has released the P tile and O_t
-                    tc_fence_after();
-                    if (__any_sync(0xffffffffu, grow)) {
-#pragma unroll 1
-                        for (int ch = 0; ch < 4; ++ch) {
-                            uint32_t o[32];
-                            tmem_ld32(tO + ch * 32, o);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                            tmem_st32(tO + ch * 32, o);
-                        }
-                        tmem_st_wait();
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const int chunk = (q & 7) ^ (r & 7);
-                    *reinterpret_cast<uint4*>(prow + (q >> 3) * ATT_HALF_BYTES + chunk * 16) =
-                        make_uint4(s[q * 4], s[q * 4 + 1], s[q * 4 + 2], s[q * 4 + 3]);
-                }
-                fence_proxy_async_smem();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&p_full[t]);
-            }
-            mbar_wait(&pv_done[t], (n_kv - 1) & 1);
-            tc_fence_after();
-            float l_lo, l_hi;
-            upk2(l2, l_lo, l_hi);
-            const float inv = 1.f / (l_lo + l_hi);
-            __nv_bfloat16* orow = p.out + (long long)(row_base + q_row0 + t * ATT_TILE + r) * D + head * ATT_TILE;
-#pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t o[32];
-                tmem_ld32(tO + ch * 32, o);
-                tmem_ld_wait();
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    uint4 u;
-                    u.x = pack_bf16(__uint_as_float(o[q4 * 8 + 0]) * inv, __uint_as_float(o[q4 * 8 + 1]) * inv);
-                    u.y = pack_bf16(__uint_as_float(o[q4 * 8 + 2]) * inv, __uint_as_float(o[q4 * 8 + 3]) * inv);
-                    u.z = pack_bf16(__uint_as_float(o[q4 * 8 + 4]) * inv, __uint_as_float(o[q4 * 8 + 5]) * inv);
-                    u.w = pack_bf16(__uint_as_float(o[q4 * 8 + 6]) * inv, __uint_as_float(o[q4 * 8 + 7]) * inv);
-                    *reinterpret_cast<uint4*>(orow + ch * 32 + q4 * 8) = u;
-                }
-            }
-        }
-    }
-
-    __syncwarp();
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc<512>(tmem_base);
-    }
-}
-
-template <int POLY>
-static int launch_attn_dq(const CUtensorMap& tm, const AttnDev& p, dim3 grid, cudaStream_t st) {
-    QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(attn_dq_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT4_SMEM));
-    attn_dq_kernel<POLY><<<grid, ATT_THREADS, AT4_SMEM, st>>>(tm, p);
-    QIE_LAUNCH_OK("attn_dq_kernel");
-    return QIE_OK;
-}
-
-template <int POLY>
-static int launch_attn_pair(const CUtensorMap& tm128, const CUtensorMap& tm64, const AttnDev& p, dim3 grid, cudaStream_t st) {
-    QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(attn_pair_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM));
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(AT2_THREADS);
-    cfg.dynamicSmemBytes = AT2_SMEM;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_pair_kernel<POLY>, tm128, tm64, p));
+    cfg.numAttrs = launch_attrs(attr, 2);
+    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_pair_kernel<POLY>, tm128, p));
     QIE_LAUNCH_OK("attn_pair_kernel");
     return QIE_OK;
 }
@@ -2254,15 +796,13 @@ static int launch_attn_pair(const CUtensorMap& tm128, const CUtensorMap& tm64, c
 
 using namespace qie;
 
-struct AttnScatter { void* const* peer_out; int sp_rows, out_ld, head_off; };
+struct AttnScatter {
+    void* const* peer_out;
+    const qie_peers* pr;
+    int out_ld, head_off;
+};
 static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int* tile_valid, int num_heads, int variant,
                        void* stream, const AttnScatter* sc = nullptr);
-static unsigned long long* g_attn_trace = nullptr;
-// timing experiment: device buffer of 2*5*32*8 u64 that variant 0x804 (pair2 trace build) fills with clock64 stamps
-extern "C" int qie_attn_set_trace(void* dev_buf) {
-    g_attn_trace = (unsigned long long*)dev_buf;
-    return QIE_OK;
-}
 
 extern "C" int qie_attn_fwd_tiles(const void* qkv, void* out, int n_tiles, const int* tile_valid_dev, int num_heads,
                                   int variant, void* stream) {
@@ -2273,9 +813,9 @@ extern "C" int qie_attn_fwd_tiles(const void* qkv, void* out, int n_tiles, const
     return attn_launch(qkv, out, &s, tile_valid_dev, num_heads, variant, stream);
 }
 
-// variant bit 0: 0 = P through TMEM (TS MMA), 1 = P through shared memory (SS MMA);
-// variant bits 4..7: how many of every 8 score pairs take the FMA-pipe polynomial exp2 instead of MUFU.EX2 (0, 2, 3, 4);
-// variant 0 selects the tuned default.
+// variant 0 = the tuned default (CTA-pair kernel, 2 of every 8 score pairs on the FMA-pipe polynomial exp2).  Explicit choices:
+// bit 3 (0x8) = single-CTA fallback kernel; bits 4..7 = how many of every 8 score pairs take the polynomial (0 with bit 8
+// (0x100) set = all MUFU, 2, 3, 4).
 extern "C" int qie_attn_fwd(const void* qkv, void* out, const qie_seq* seq, int num_heads, int variant, void* stream) {
     QIE_REQUIRE(qkv && out && seq, QIE_EINVAL, "qie_attn_fwd: null pointer");
     QIE_REQUIRE(seq->img_pad % 128 == 0 && seq->txt_pad % 128 == 0 && seq->batch > 0 && num_heads > 0 &&
@@ -2288,30 +828,22 @@ extern "C" int qie_attn_fwd(const void* qkv, void* out, const qie_seq* seq, int 
 // attention of one rank of a sequence-parallel group over its gathered q|k|v, output scattered to the token owners
 // (called by the ATTN phase of qie_forward_phase when peers are installed)
 namespace qie {
-int attn_fwd_peers(const void* qkv_gathered, void* const* peer_out_dev, int n_tiles, const int* tile_valid_dev, int heads_local,
-                   int sp_rows, int out_ld, int head_off, void* stream) {
-    QIE_REQUIRE(qkv_gathered && peer_out_dev && tile_valid_dev && n_tiles > 0 && heads_local > 0 && sp_rows % 128 == 0,
-                QIE_EINVAL, "attn_fwd_peers: bad argument");
+int attn_fwd_peers(const void* qkv_gathered, void* const* peer_out_dev, const qie_peers* pr, const int* tile_valid_dev,
+                   int heads_local, int out_ld, void* stream) {
+    QIE_REQUIRE(qkv_gathered && peer_out_dev && pr && tile_valid_dev && heads_local > 0, QIE_EINVAL, "attn_fwd_peers: bad argument");
     qie_seq s{};
-    s.batch = 1;
-    s.img_rows = s.img_pad = n_tiles * 128;
-    AttnScatter sc{peer_out_dev, sp_rows, out_ld, head_off};
-    return attn_launch(qkv_gathered, const_cast<void*>(qkv_gathered) /* unused */, &s, tile_valid_dev, heads_local, 0x1020, stream, &sc);
+    s.batch = pr->batch;
+    s.img_rows = s.img_pad = pr->size * pr->img_pad + (pr->txt_total + 127) / 128 * 128;
+    AttnScatter sc{peer_out_dev, pr, out_ld, pr->rank * heads_local};
+    return attn_launch(qkv_gathered, const_cast<void*>(qkv_gathered) /* unused */, &s, tile_valid_dev, heads_local, 0, stream, &sc);
 }
 }  // namespace qie
 
 static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int* tile_valid, int num_heads, int variant,
                        void* stream, const AttnScatter* sc) {
-    if (variant == 0) variant = QIE_ATTN_DEFAULT_VARIANT;     // bit 8 (0x100) marks an explicit choice, e.g. 0x100 = TMEM P, all-MUFU
-    const int poly = (variant >> 4) & 15, psmem = variant & 1, pair = (variant >> 1) & 1, pair2 = (variant >> 2) & 1;
-    const int dq = (variant >> 3) & 1;
-    const int pair3 = (variant >> 12) & 1;
-    if (pair3) {
-        QIE_REQUIRE((variant & 0x608) == 0 && (poly == 0 || poly == 2 || poly == 3 || poly == 4), QIE_EINVAL,
-                    "qie_attn_fwd: bad variant 0x%x", variant);
-        variant &= ~0x1000;
-    }
-    QIE_REQUIRE((variant & ~0xFFF) == 0 && !(dq && (pair || pair2 || psmem)) && !(pair2 && (pair || psmem)) && (poly == 0 || poly == 2 || poly == 3 || poly == 4) && !(pair && psmem), QIE_EINVAL,
+    if (variant == 0) variant = 0x20;
+    const int poly = (variant >> 4) & 15, single = (variant >> 3) & 1;
+    QIE_REQUIRE((variant & ~0x1F8) == 0 && (poly == 0 || poly == 2 || poly == 3 || poly == 4), QIE_EINVAL,
                 "qie_attn_fwd: bad variant 0x%x", variant);
     const int rpb = seq->img_pad + seq->txt_pad;
     const int D = num_heads * 128;
@@ -2324,9 +856,15 @@ static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int
     p.tile_valid = tile_valid;
     p.out = (__nv_bfloat16*)out;
     if (sc) {
-        QIE_REQUIRE(pair3 && seq->batch == 1, QIE_EINVAL, "attention output scatter needs the pair3 kernel and batch 1");
+        QIE_REQUIRE(!single, QIE_EINVAL, "the attention output scatter needs the CTA-pair kernel");
+        const qie_peers* pr = sc->pr;
         p.peer_out = sc->peer_out;
-        p.sp_rows = sc->sp_rows;
+        p.sp_img_pad = pr->img_pad;
+        p.sp_img_region = pr->size * pr->img_pad;
+        p.sp_rows_pad = pr->img_pad + pr->txt_pad;
+        p.sp_txt_total = pr->txt_total;
+        p.sp_txt_base = pr->txt_total / pr->size;
+        p.sp_txt_rem = pr->txt_total % pr->size;
         p.out_ld = sc->out_ld;
         p.head_off = sc->head_off;
     }
@@ -2338,85 +876,20 @@ static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int
     p.v_kstep = 2048;
     dim3 grid((rpb + 255) / 256, num_heads, seq->batch);
     cudaStream_t st = (cudaStream_t)stream;
-    if (pair3) {  // CTA pair, 256-wide KV tiles, P in TMEM
-        grid.x *= 2;
-        if (variant & 0x4) {                                   // bit 2: persistent form (one CTA pair per TPC loops over the units)
-            const int n_units = ((rpb + 255) / 256) * num_heads * seq->batch;
-            return poly == 3 ? launch_attn_pair3p<3>(tm, p, n_units, st) : poly == 0 ? launch_attn_pair3p<0>(tm, p, n_units, st)
-                                                                                       : launch_attn_pair3p<2>(tm, p, n_units, st);
-        }
-        const int premax = (variant & 0x1) ? 1 : 0;          // bit 0: pipelined max pass (measured slower: S(j+1) completes too late to prefetch)
-        const int spec = (variant & 0x2) ? 1 : 0;            // bit 1: speculative reference (no max pass in front of the exponentials;
-                                                             // measured slower: 0.77 vs 0.69 ms, the in-loop max tracking raises register pressure)
-        if (variant & 0x800) { p.trace = g_attn_trace; return premax ? launch_attn_pair3<2, 4, 1>(tm, p, grid, st) : launch_attn_pair3<2, 4, 0>(tm, p, grid, st); }
-        if (premax) return launch_attn_pair3<2, 0, 1>(tm, p, grid, st);
-        if (spec) {
-            // fast launch with a speculative softmax reference, then the exact kernel, which returns at once unless the fast
-            // one raised its overflow flag (a score 2^100 above every earlier score of its row: never on real activations)
-            static int* flags_dev[64] = {};      // one ring of flags per device of this process
-            static unsigned next = 0;
-            int dev = 0;
-            QIE_CUDA_OK(cudaGetDevice(&dev));
-            QIE_REQUIRE(dev >= 0 && dev < 64, QIE_EINVAL, "device index %d out of range", dev);
-            if (!flags_dev[dev]) QIE_CUDA_OK(cudaMalloc(&flags_dev[dev], 64 * sizeof(int)));
-            int* flag = flags_dev[dev] + (next++ & 63);
-            QIE_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int), st));
-            p.overflow = flag;
-            int rc2 = poly == 3 ? launch_attn_pair3<3, 0, 2>(tm, p, grid, st) : launch_attn_pair3<2, 0, 2>(tm, p, grid, st);
-            if (rc2) return rc2;
-            p.overflow = nullptr;
-            p.run_if = flag;
-            return launch_attn_pair3<2, 0, 0>(tm, p, grid, st);
-        }
+    if (single) {
         switch (poly) {
-            case 0: return launch_attn_pair3<0, 0, 0>(tm, p, grid, st);
-            case 2: return launch_attn_pair3<2, 0, 0>(tm, p, grid, st);
-            case 3: return launch_attn_pair3<3, 0, 0>(tm, p, grid, st);
-            case 4: return launch_attn_pair3<4, 0, 0>(tm, p, grid, st);
+            case 0: return launch_attn<true, 0>(tm, p, grid, st);
+            case 2: return launch_attn<true, 2>(tm, p, grid, st);
+            case 3: return launch_attn<true, 3>(tm, p, grid, st);
+            case 4: return launch_attn<true, 4>(tm, p, grid, st);
         }
     }
-    if (dq) {     // decoupled single-CTA kernel
-        switch (poly) {
-            case 0: return launch_attn_dq<0>(tm, p, grid, st);
-            case 2: return launch_attn_dq<2>(tm, p, grid, st);
-            case 3: return launch_attn_dq<3>(tm, p, grid, st);
-            case 4: return launch_attn_dq<4>(tm, p, grid, st);
-        }
-    }
-    if (pair || pair2) {   // CTA-pair kernels: two CTAs per 256 query rows, K tiles staged as 64-row halves
-        CUtensorMap tm64;
-        rc = make_tmap_2d(&tm64, qkv, (uint64_t)seq->batch * rpb, (uint64_t)3 * D, (uint64_t)3 * D * 2, 64, 64, 2);
-        if (rc) return rc;
-        grid.x *= 2;
-        if (pair2) {
-            const int dbg = (variant >> 9) & 7;      // timing experiments (0x200: no MUFU, 0x400: no max pass, 0x800: trace)
-            if (dbg == 4) { p.trace = g_attn_trace; return launch_attn_pair2<2, 4>(tm, tm64, p, grid, st); }
-            if (dbg == 1) return launch_attn_pair2<0, 1>(tm, tm64, p, grid, st);
-            if (dbg == 2) return launch_attn_pair2<0, 2>(tm, tm64, p, grid, st);
-            if (dbg == 3) return launch_attn_pair2<0, 3>(tm, tm64, p, grid, st);
-            switch (poly) {
-                case 0: return launch_attn_pair2<0, 0>(tm, tm64, p, grid, st);
-                case 2: return launch_attn_pair2<2, 0>(tm, tm64, p, grid, st);
-                case 3: return launch_attn_pair2<3, 0>(tm, tm64, p, grid, st);
-                case 4: return launch_attn_pair2<4, 0>(tm, tm64, p, grid, st);
-            }
-        }
-        switch (poly) {
-            case 0: return launch_attn_pair<0>(tm, tm64, p, grid, st);
-            case 2: return launch_attn_pair<2>(tm, tm64, p, grid, st);
-            case 3: return launch_attn_pair<3>(tm, tm64, p, grid, st);
-            case 4: return launch_attn_pair<4>(tm, tm64, p, grid, st);
-        }
-    }
-#define QIE_ATTN_CASE(P)                                               \
-    case P:                                                            \
-        return psmem ? launch_attn<false, P>(tm, p, grid, st) : launch_attn<true, P>(tm, p, grid, st);
+    grid.x *= 2;     // a cluster of two CTAs per 256 query rows
     switch (poly) {
-        QIE_ATTN_CASE(0)
-        QIE_ATTN_CASE(2)
-        QIE_ATTN_CASE(3)
-        QIE_ATTN_CASE(4)
+        case 0: return launch_attn_pair<0>(tm, p, grid, st);
+        case 2: return launch_attn_pair<2>(tm, p, grid, st);
+        case 3: return launch_attn_pair<3>(tm, p, grid, st);
+        case 4: return launch_attn_pair<4>(tm, p, grid, st);
     }
-#undef QIE_ATTN_CASE
     return QIE_EINVAL;
 }

@@ -45,6 +45,22 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
                  uint32_t box_rows, uint32_t box_cols, int elt_bytes);
 
 int sm_count();
+// QIE_ECUDA (with the message set) once a peer barrier of this process has timed out, else QIE_OK; `clear` re-arms the flag
+int peer_sticky_error(bool clear = false);
+
+// Mutable kernel scratch (row counters of ln_mod_stream_kernel, split-K tail partials and tickets of gemm_kernel) is one set
+// per (device, stream): launches on one stream are serialised, launches on different streams never share a set.  The sets of a
+// device come from a fixed pool allocated by the first qie_create on that device, so handing one to a new stream allocates
+// nothing (qie_forward stays CUDA-graph capturable); the pool is exhausted after QIE_SCRATCH_SETS distinct streams per device.
+constexpr int SPLIT_SCRATCH_TILES = 96;      // split-K parts of 256 x 256 fp32 per set (24 MB)
+constexpr int QIE_SCRATCH_SETS = 8;
+struct StreamScratch {
+    int* ln_counters;        // [2]  next row, warps that left
+    float* split_scratch;    // [SPLIT_SCRATCH_TILES][256][256]
+    int* split_tickets;      // [SPLIT_SCRATCH_TILES][8]
+};
+int stream_scratch_reserve();                              // allocates the pool of the current device (idempotent)
+int stream_scratch(cudaStream_t st, StreamScratch* out);   // the set of (current device, st)
 
 // Programmatic dependent launch (qie_tune key 7): the three per-block kernels (GEMM, attention, adaLN) are launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization; each signals griddepcontrol.launch_dependents on entry and runs its

@@ -52,21 +52,13 @@ struct GemmDev {
     // ranges, one work item each, so the tail wave costs 1/tail_split of a tile; partial accumulators meet in `scratch`
     int tail_tiles, tail_split, tail_dbg;
     int group_m;             // m-units per raster band (qie_tune key 5; 0 = GEMM_GROUP_M)
-    // fused adaLN (GATE_RESID epilogue, N == ldo == model width): once a 256-row unit of the residual stream has received all
-    // of its n-blocks, warps that have run out of tiles LayerNorm+modulate its rows into ln_out (the A operand of the next GEMM)
-    int ln_fuse, ln_nv, ln_dbg;   // nv = N / 128
-    const float* ln_mod;
-    long long ln_mod_bstride, ln_mod_sstride;
-    int ln_shift_off, ln_scale_off, ln_qmode;
-    float ln_eps;
-    __nv_bfloat16* ln_out;
-    uint8_t* ln_out8;
-    float* ln_out_scale;
-    int* ln_sync;            // [0] job counter, [1] warps that left the LN phase, [2] error flag, [8 + mu] unit completion counts
     float* scratch;          // [tail_tiles][tail_split][CG*128 rows][BN] fp32
     int* tickets;            // [tail_tiles][8 row slices]
     void* const* peer_out;   // QKV epilogue, sequence parallel: device table of the ranks' gathered q|k|v buffers (or NULL)
-    int sp_rank, sp_hl, sp_rows;   // my rank, heads per rank, rows of one rank's shard in the gathered layout
+    int sp_rank, sp_hl;            // my rank, heads per rank
+    int sp_gathered_rows;          // rows of one batch element in the gathered layout [P image shards | all text tokens]
+    int sp_txt_row0;               // gathered row of my first text token
+    float* q8_amax;                // optional: per-row max|out| folded in by the bf16 epilogues (feeds the 8-bit quantiser)
 };
 
 template <int BN, int CG>
@@ -457,7 +449,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                     const bool normed = EPI == QIE_EPI_QKV_NORM_ROPE && which != 2;
                     // sequence-parallel scatter: this 32-column chunk belongs to one head, i.e. to one destination rank;
-                    // its rows go to row (my_rank * shard_rows + local row) of that rank's gathered [q|k|v] buffer
+                    // image rows go to row (my_rank * img_pad + local row) of that rank's gathered [q|k|v] buffer, text rows
+                    // behind the image shards of all ranks at their index in the whole text sequence
                     [[maybe_unused]] __nv_bfloat16* scat = nullptr;
                     [[maybe_unused]] long long scat_ld = 0;
                     if constexpr (EPI == QIE_EPI_QKV_NORM_ROPE) {
@@ -465,7 +458,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             const int head = (n0 - which * p.model_dim) >> 7, g = head / p.sp_hl;
                             scat_ld = 3LL * p.sp_hl * 128;
                             scat = reinterpret_cast<__nv_bfloat16*>(__ldg(reinterpret_cast<const unsigned long long*>(p.peer_out) + g)) +
-                                   ((long long)p.sp_rank * p.sp_rows + jrow0_in_batch) * scat_ld +
+                                   ((long long)m.b * p.sp_gathered_rows + (m.s ? p.sp_txt_row0 : p.sp_rank * p.seq.img_pad) + local0) * scat_ld +
                                    (which * p.sp_hl + (head - g * p.sp_hl)) * 128 + (n0 & 127) + c4;
                         }
                     }
@@ -540,20 +533,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (orow0 + rr) * p.ldo + n0 + c4) = v;
                         } else {
                             const uint2 u = valid ? make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w)) : make_uint2(0u, 0u);
-                            if (EPI == QIE_EPI_QKV_NORM_ROPE && scat)
-                                *reinterpret_cast<uint2*>(scat + rr * scat_ld) = u;     // NVLink peer store (or local when g == my rank)
-                            else
+                            if (EPI == QIE_EPI_QKV_NORM_ROPE && scat) {
+                                // NVLink peer store (or local when g == my rank); pad rows are not stored: in the gathered text
+                                // region they are another rank's tokens
+                                if (valid) *reinterpret_cast<uint2*>(scat + rr * scat_ld) = u;
+                            } else
                                 *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (orow0 + rr) * p.ldo + n0 + c4) = u;
                         }
                     }
                     __syncwarp();   // staging tile is reused by the next chunk
-                }
-            }
-            if constexpr (EPI == QIE_EPI_GATE_RESID_F32) {
-                if (p.ln_fuse && !dummy) {      // my 32 rows of this n-block are in the residual stream
-                    __threadfence();
-                    __syncwarp();
-                    if (lane == 0) atomicAdd(p.ln_sync + 8 + mu, 1);
                 }
             }
             // release this accumulator stage back to the MMA warp (of the leader CTA)
@@ -566,171 +554,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;
-            }
-        }
-        // ================= fused adaLN phase (epilogue warps that have run out of tiles) =================
-        if constexpr (EPI == QIE_EPI_GATE_RESID_F32) {
-            if (p.ln_fuse) {
-                constexpr int JOB_ROWS = 8, LAND = 2;          // rows per job; rows in flight per warp
-                const int jobs_per_unit = CG * GEMM_BM / JOB_ROWS, total_jobs = m_units * jobs_per_unit;
-                const int D = p.ln_nv * 128;
-                const float* x = reinterpret_cast<const float*>(p.out);
-                // The operand ring of this CTA is idle now (its last accumulator has been drained): every epilogue warp takes
-                // 48 KB of it as a landing zone for 1-D bulk copies of residual rows, four rows in flight per warp, so the
-                // LayerNorm phase is not bound by one-row-at-a-time L2 latency (4 warps per SM).
-                // Per warp 48 KB: two landing rows (24 KB) + the shift and scale vectors of the (batch, stream) it is working on
-                // (24 KB): with ~200 KB of the SM's memory carved out as shared, L1 cannot hold them and every row would pay
-                // dozens of serialised L2 round trips for them.
-                float* land = reinterpret_cast<float*>(smem + (size_t)warp * 49152);
-                float* modv = land + LAND * 3072;               // [shift D | scale D]
-                uint64_t* lbar = bars + 32 + warp * 4;          // behind the pipeline barriers (BAR_BYTES = 512): 2 rows + mod
-                uint32_t lph = 0;                               // phase bit per barrier
-                int mod_tag = -1;                               // (batch << 1 | stream) whose vectors are in modv
-                if (lane == 0) {
-                    for (int i = 0; i < 3; ++i) mbar_init(&lbar[i], 1);
-                    fence_barrier_init();
-                }
-                __syncwarp();
-                const uint32_t row_bytes = (uint32_t)D * 4;
-                for (;;) {
-                    int job = 0;
-                    if (lane == 0) job = atomicAdd(p.ln_sync, 1);
-                    job = __shfl_sync(0xffffffffu, job, 0);
-                    if (job >= total_jobs) break;
-                    const int jmu = job / jobs_per_unit, jr0 = (job - jmu * jobs_per_unit) * JOB_ROWS;
-                    const MUnit m = decode_munit<CG>(p, jmu);
-                    const int seg_pad = m.s ? p.seq.txt_pad : p.seq.img_pad;
-                    const int seg_rows = m.s ? p.seq.txt_rows : p.seq.img_rows;
-                    const int local0 = m.ti * GEMM_BM + jr0;                 // first row of the job inside its stream
-                    if (local0 >= seg_pad) continue;                         // the empty half of an odd last unit
-                    // rows of this unit are complete once every n-block has been added by every 32-row slice that exists
-                    const int halves = (m.ti + 1) * GEMM_BM < seg_pad && CG == 2 ? 2 : 1;
-                    const int target = p.n_blocks * 4 * halves;
-                    if (lane == 0) {
-                        const long long t0 = clock64();
-                        while (true) {
-                            int v;
-                            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.ln_sync + 8 + jmu) : "memory");
-                            if (v >= target) break;
-                            if (clock64() - t0 > 4000000000LL) {             // ~2 s: fail loudly instead of hanging
-                                atomicExch(p.ln_sync + 2, 1);
-                                break;
-                            }
-                            __nanosleep((p.ln_dbg & 2) ? 2000 : 64);
-                        }
-                    }
-                    __syncwarp();
-                    if (p.ln_dbg & 1) continue;
-                    auto issue_row = [&](int rr) {            // bulk copy of residual row rr of this job into its landing slot
-                        const int local = local0 + rr;
-                        if (rr < JOB_ROWS && local < seg_rows && lane == 0) {
-                            const long long row = (long long)m.b * rpb + (m.s ? p.seq.img_pad : 0) + local;
-                            uint64_t* lb = &lbar[rr % LAND];
-                            mbar_expect_tx(lb, row_bytes);
-                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                             smem_u32(land + (size_t)(rr % LAND) * 3072)),
-                                         "l"(x + row * D), "r"(row_bytes), "r"(smem_u32(lb))
-                                         : "memory");
-                        }
-                    };
-                    for (int rr = 0; rr < LAND; ++rr) issue_row(rr);
-                    if (mod_tag != (m.b << 1 | m.s)) {      // (re)load the modulation vectors of this (batch, stream)
-                        mod_tag = m.b << 1 | m.s;
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) {
-                            const float* mrow0 = p.ln_mod + m.b * p.ln_mod_bstride + m.s * p.ln_mod_sstride;
-                            mbar_expect_tx(&lbar[2], 2 * row_bytes);
-                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                             smem_u32(modv)), "l"(mrow0 + p.ln_shift_off), "r"(row_bytes), "r"(smem_u32(&lbar[2]))
-                                         : "memory");
-                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                             smem_u32(modv + D)), "l"(mrow0 + p.ln_scale_off), "r"(row_bytes), "r"(smem_u32(&lbar[2]))
-                                         : "memory");
-                        }
-                        mbar_wait(&lbar[2], (lph >> 2) & 1);
-                        lph ^= 4u;
-                    }
-                    for (int rr = 0; rr < JOB_ROWS; ++rr) {
-                        const int local = local0 + rr;
-                        const long long row = (long long)m.b * rpb + (m.s ? p.seq.img_pad : 0) + local;
-                        __nv_bfloat16* orow = p.ln_out + row * D;
-                        if (local >= seg_rows) {      // pad rows stay exactly zero (as ln_mod_kernel keeps them)
-                            for (int i = 0; i < p.ln_nv; ++i) *reinterpret_cast<uint2*>(orow + (i * 32 + lane) * 4) = make_uint2(0u, 0u);
-                            if (p.ln_out8) {
-                                for (int i = 0; i < p.ln_nv; ++i) *reinterpret_cast<uint32_t*>(p.ln_out8 + row * D + (i * 32 + lane) * 4) = 0u;
-                                if (lane == 0) p.ln_out_scale[row] = 0.f;
-                            }
-                            continue;
-                        }
-                        const int slot = rr % LAND;
-                        mbar_wait(&lbar[slot], (lph >> slot) & 1);
-                        lph ^= 1u << slot;
-                        const float4* xr = reinterpret_cast<const float4*>(land + (size_t)slot * 3072);
-                        float4 v[24];
-                        float sum = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 24; ++i)
-                            if (i < p.ln_nv) {
-                                v[i] = xr[i * 32 + lane];
-                                sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-                            }
-                        fence_proxy_async_smem();       // my reads of the slot are ordered before the bulk copy that refills it
-                        __syncwarp();
-                        issue_row(rr + LAND);
-                        const float mean = warp_sum(sum) * (1.0f / D);
-                        float q = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 24; ++i)
-                            if (i < p.ln_nv) {
-                                float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-                                q += ln_sq4(a, bb, c, d);
-                            }
-                        const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + p.ln_eps);
-                        const float4* sh = reinterpret_cast<const float4*>(modv);
-                        const float4* sc = reinterpret_cast<const float4*>(modv + D);
-                        float amax = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 24; ++i)
-                            if (i < p.ln_nv) {
-                                const float4 h = sh[i * 32 + lane], c = sc[i * 32 + lane];
-                                v[i].x = ln_apply(v[i].x, mean, rstd, c.x, h.x);
-                                v[i].y = ln_apply(v[i].y, mean, rstd, c.y, h.y);
-                                v[i].z = ln_apply(v[i].z, mean, rstd, c.z, h.z);
-                                v[i].w = ln_apply(v[i].w, mean, rstd, c.w, h.w);
-                                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
-                                if (!(p.ln_dbg & 4))
-                                    *reinterpret_cast<uint2*>(orow + (i * 32 + lane) * 4) =
-                                        make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
-                            }
-                        if (p.ln_out8) {
-                            amax = warp_max(amax);
-                            amax = __bfloat162float(__float2bfloat16(amax));
-                            const float qmax = p.ln_qmode == 2 ? 127.f : 448.f;
-                            const float scale = amax > 0.f ? amax / qmax : 1.f;
-#pragma unroll
-                            for (int i = 0; i < 24; ++i)
-                                if (i < p.ln_nv) {
-                                    const float4 bq = make_float4(__bfloat162float(__float2bfloat16(v[i].x)), __bfloat162float(__float2bfloat16(v[i].y)),
-                                                                  __bfloat162float(__float2bfloat16(v[i].z)), __bfloat162float(__float2bfloat16(v[i].w)));
-                                    *reinterpret_cast<uint32_t*>(p.ln_out8 + row * D + (i * 32 + lane) * 4) =
-                                        p.ln_qmode == 2 ? pack_s8x4(bq.x / scale, bq.y / scale, bq.z / scale, bq.w / scale)
-                                                        : pack_e4m3x4(bq.x / scale, bq.y / scale, bq.z / scale, bq.w / scale);
-                                }
-                            if (lane == 0) p.ln_out_scale[row] = scale;
-                        }
-                    }
-                }
-                // the last warp to leave re-arms the counters for the next launch
-                if (lane == 0) {
-                    __threadfence();
-                    if (atomicAdd(p.ln_sync + 1, 1) == (int)gridDim.x * 4 - 1) {
-                        for (int i = 0; i < m_units; ++i) p.ln_sync[8 + i] = 0;
-                        p.ln_sync[0] = 0;
-                        p.ln_sync[1] = 0;
-                        __threadfence();
-                    }
-                }
             }
         }
     }
@@ -784,45 +607,12 @@ static int dispatch_epi(int epi, const CUtensorMap& a, const CUtensorMap& b0, co
 
 }  // namespace qie
 
-namespace qie {
-// scratch for the split-K tail partials (96 tiles x 256 x 256 fp32 = 24 MB) and its tickets; allocated at qie_create so that
-// qie_forward never allocates (one set per process: GEMMs of one device are issued on one stream at a time)
-int gemm_split_buffers(float** scratch_out, int** tickets_out) {
-    static float* scratch[64] = {};         // one set per device of this process
-    static int* tickets[64] = {};
-    int dev = 0;
-    QIE_CUDA_OK(cudaGetDevice(&dev));
-    QIE_REQUIRE(dev >= 0 && dev < 64, QIE_EINVAL, "device index %d out of range", dev);
-    if (!scratch[dev]) {
-        QIE_CUDA_OK(cudaMalloc(&scratch[dev], (size_t)96 * 2 * GEMM_BM * 256 * sizeof(float)));
-        QIE_CUDA_OK(cudaMalloc(&tickets[dev], 96 * 8 * sizeof(int)));
-        QIE_CUDA_OK(cudaMemset(tickets[dev], 0, 96 * 8 * sizeof(int)));
-    }
-    *scratch_out = scratch[dev];
-    *tickets_out = tickets[dev];
-    return QIE_OK;
-}
-// counters of the fused adaLN phase: [0] job counter, [1] exit counter, [2] error flag, [8 + m-unit] completion counts
-int gemm_ln_sync(int** out) {
-    static int* buf[64] = {};
-    int dev = 0;
-    QIE_CUDA_OK(cudaGetDevice(&dev));
-    QIE_REQUIRE(dev >= 0 && dev < 64, QIE_EINVAL, "device index %d out of range", dev);
-    if (!buf[dev]) {
-        QIE_CUDA_OK(cudaMalloc(&buf[dev], 4096 * sizeof(int)));
-        QIE_CUDA_OK(cudaMemset(buf[dev], 0, 4096 * sizeof(int)));
-    }
-    *out = buf[dev];
-    return QIE_OK;
-}
-}  // namespace qie
 
 using namespace qie;
 
 int qie::g_pdl = 0;          // qie_tune(7, v): programmatic dependent launch of the per-block kernels
 int g_gemm_l2_hints = 0;    // set through qie_tune(2, v)
 int g_gemm_group_m = 0;     // qie_tune(5, v): m-units per raster band, 0 = default
-int g_gemm_ln_dbg = 0;      // qie_tune(6, v): timing experiments on the fused adaLN phase
 int g_gemm_split_tail = 1;  // qie_tune(4, v): 0 off, 1 long-K tiles only / two ranges (default), 9 wherever a split fits
 
 extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream) {
@@ -876,14 +666,17 @@ extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream
     // 339 -> 239 MB and 429 -> 290 MB per launch), the N = 3072 shapes are best at 8 (profiles/r01_gemm_traffic.json)
     p.group_m = g_gemm_group_m > 0 ? g_gemm_group_m : (p.n_blocks >= 24 ? 16 : GEMM_GROUP_M);
     if (g->peer_out) {
-        QIE_REQUIRE(g->epilogue == QIE_EPI_QKV_NORM_ROPE && seq->batch == 1 && g->sp_size >= 1 && g->sp_size <= 8 &&
+        QIE_REQUIRE(g->epilogue == QIE_EPI_QKV_NORM_ROPE && g->sp_size >= 1 && g->sp_size <= 8 &&
                         g->sp_rank >= 0 && g->sp_rank < g->sp_size && (g->N / 3 / 128) % g->sp_size == 0 &&
-                        g->sp_rows == seq->img_pad + seq->txt_pad && g->streams == 3,
-                    QIE_EINVAL, "qie_gemm: peer scatter needs the QKV epilogue, batch 1, both streams, heads %% sp_size == 0");
+                        g->sp_gathered_rows >= g->sp_size * seq->img_pad && g->sp_txt_row0 >= g->sp_size * seq->img_pad &&
+                        g->sp_txt_row0 + seq->txt_rows <= g->sp_gathered_rows && g->streams == 3,
+                    QIE_EINVAL, "qie_gemm: peer scatter needs the QKV epilogue, both streams, heads %% sp_size == 0 and a gathered "
+                    "layout that holds every rank's image shard and the text tokens");
         p.peer_out = g->peer_out;
         p.sp_rank = g->sp_rank;
         p.sp_hl = g->N / 3 / 128 / g->sp_size;
-        p.sp_rows = g->sp_rows;
+        p.sp_gathered_rows = g->sp_gathered_rows;
+        p.sp_txt_row0 = g->sp_txt_row0;
     }
     if (g->epilogue == QIE_EPI_QKV_NORM_ROPE) {
         QIE_REQUIRE(g->N % 3 == 0 && p.model_dim % bn == 0 && bn >= 128 && g->rope, QIE_ESHAPE,
@@ -899,7 +692,13 @@ extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream
     const int t0 = (g->streams & 1) ? seq->img_pad / 128 : 0, t1 = (g->streams & 2) ? seq->txt_pad / 128 : 0;
     const int pair_tiles = seq->batch * ((t0 + 1) / 2 + (t1 + 1) / 2) * p.n_blocks;
     int cg = g->cta_group;
-    if (cg == 0) cg = (bn >= 128 && pair_tiles >= sm_count() / 2) ? 2 : 1;
+    if (cg == 0) {
+        // a CTA pair and a single CTA finish a 128-row block of a tile in the same time: take the form with fewer waves (small
+        // sequence-parallel shards: 9 blocks x 48 n-blocks are 3 waves of 148 CTAs but 4 waves of 74 pairs), pairs on a tie
+        const int sms = sm_count(), single_tiles = seq->batch * (t0 + t1) * p.n_blocks;
+        const int waves2 = (pair_tiles + sms / 2 - 1) / (sms / 2), waves1 = (single_tiles + sms - 1) / sms;
+        cg = (bn >= 128 && pair_tiles >= sms / 2 && waves2 <= waves1) ? 2 : 1;
+    }
     QIE_REQUIRE(cg == 1 || (cg == 2 && bn >= 128), QIE_EINVAL, "qie_gemm: cta_group must be 1 or 2 (2 needs block_n >= 128)");
 
     const int rpb = seq->img_pad + seq->txt_pad;
@@ -916,31 +715,6 @@ extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream
     }
     const int tiles = cg == 2 ? pair_tiles : seq->batch * (t0 + t1) * p.n_blocks;
     cudaStream_t st = (cudaStream_t)stream;
-    if (g->ln_out) {
-        const int m_units = cg == 2 ? pair_tiles / p.n_blocks : seq->batch * (t0 + t1);
-        QIE_REQUIRE(g->epilogue == QIE_EPI_GATE_RESID_F32 && g->ldo == g->N && g->N % 128 == 0 && g->N / 128 <= 24 && g->ln_mod &&
-                        g->streams == 3 && !g->out_compact && (g->ln_out8 == nullptr) == (g->ln_out_scale == nullptr) &&
-                        m_units + 8 <= 4096,
-                    QIE_EINVAL, "qie_gemm: fused adaLN needs the gated-residual epilogue over whole rows (N == ldo <= 3072), both streams");
-        QIE_REQUIRE(tiles >= 1 && sm_count() / cg >= 1, QIE_EINVAL, "qie_gemm: fused adaLN: empty launch");
-        int* sync = nullptr;
-        int rc0 = qie::gemm_ln_sync(&sync);
-        if (rc0) return rc0;
-        p.ln_fuse = 1;
-        p.ln_dbg = g_gemm_ln_dbg;
-        p.ln_nv = g->N / 128;
-        p.ln_mod = g->ln_mod;
-        p.ln_mod_bstride = g->ln_mod_bstride;
-        p.ln_mod_sstride = g->ln_mod_sstride;
-        p.ln_shift_off = g->ln_shift_off;
-        p.ln_scale_off = g->ln_scale_off;
-        p.ln_qmode = g->ln_qmode;
-        p.ln_eps = g->ln_eps;
-        p.ln_out = (__nv_bfloat16*)g->ln_out;
-        p.ln_out8 = (uint8_t*)g->ln_out8;
-        p.ln_out_scale = g->ln_out_scale;
-        p.ln_sync = sync;
-    }
     // split-K tail (qie_tune key 4): only when the persistent schedule ends in a partial wave that a K split can
     // shorten, never for the QKV epilogue (row statistics over whole heads) or int8 (int32 partials would not survive fp32)
     p.tail_tiles = 0;
@@ -960,11 +734,12 @@ extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream
             }
             while (split > 1 && kblocks / split < 6) --split;
             if (split > 1) {
-                float* scratch = nullptr;
-                int* tickets = nullptr;
-                int rc0 = qie::gemm_split_buffers(&scratch, &tickets);
+                qie::StreamScratch sc;
+                int rc0 = qie::stream_scratch(st, &sc);
                 if (rc0) return rc0;
-                if (tail * split <= 96) {
+                float* scratch = sc.split_scratch;
+                int* tickets = sc.split_tickets;
+                if (tail * split <= qie::SPLIT_SCRATCH_TILES) {
                     p.tail_tiles = tail;
                     p.tail_split = split;
                     p.tail_dbg = (g_gemm_split_tail >> 1) & 3;

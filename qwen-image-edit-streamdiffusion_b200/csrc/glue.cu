@@ -491,22 +491,7 @@ int g_ln_threads = 128, g_ln_smem = 0;   // 128 threads (4 rows) per block measu
 int g_ln_variant = 1;                    // 1 = streaming persistent kernel (default), 0 = one warp per row, grid over rows
 }
 // experiment knobs (not part of the reference surface): 0 = adaLN threads per block, 1 = adaLN dynamic smem reservation
-extern int g_gemm_l2_hints, g_gemm_split_tail, g_gemm_group_m, g_gemm_ln_dbg;   // gemm.cu
-namespace qie {
-// row counter + exit counter of ln_mod_stream_kernel; allocated at qie_create so that qie_forward never allocates
-int ln_counters(int** out) {
-    static int* counters[64] = {};          // one set per device of this process
-    int dev = 0;
-    QIE_CUDA_OK(cudaGetDevice(&dev));
-    QIE_REQUIRE(dev >= 0 && dev < 64, QIE_EINVAL, "device index %d out of range", dev);
-    if (!counters[dev]) {
-        QIE_CUDA_OK(cudaMalloc(&counters[dev], 2 * sizeof(int)));
-        QIE_CUDA_OK(cudaMemset(counters[dev], 0, 2 * sizeof(int)));
-    }
-    *out = counters[dev];
-    return QIE_OK;
-}
-}  // namespace qie
+extern int g_gemm_l2_hints, g_gemm_split_tail, g_gemm_group_m;   // gemm.cu
 extern "C" int qie_tune(int key, int value) {
     if (key == 0 && (value == 64 || value == 128 || value == 256 || value == 512)) { qie::g_ln_threads = value; return QIE_OK; }
     if (key == 1 && value >= 0 && value <= 200 * 1024) { qie::g_ln_smem = value; return QIE_OK; }
@@ -514,7 +499,6 @@ extern "C" int qie_tune(int key, int value) {
     if (key == 3 && (value == 0 || value == 1)) { qie::g_ln_variant = value; return QIE_OK; }
     if (key == 4 && value >= 0 && value <= 15) { g_gemm_split_tail = value; return QIE_OK; }
     if (key == 5 && value >= 0 && value <= 64) { g_gemm_group_m = value; return QIE_OK; }
-    if (key == 6 && value >= 0 && value <= 7) { g_gemm_ln_dbg = value; return QIE_OK; }   // bit 0 on/off; bits 1-2: timing experiments
     if (key == 7 && (value == 0 || value == 1)) { qie::g_pdl = value; return QIE_OK; }   // programmatic dependent launch
     ::qie::set_error("qie_tune: bad key/value %d/%d", key, value);
     return QIE_EINVAL;
@@ -528,7 +512,6 @@ extern "C" int qie_tune_get(int key) {
         case 3: return qie::g_ln_variant;
         case 4: return g_gemm_split_tail;
         case 5: return g_gemm_group_m;
-        case 6: return g_gemm_ln_dbg;
         case 7: return qie::g_pdl;
     }
     ::qie::set_error("qie_tune_get: bad key %d", key);
@@ -545,9 +528,10 @@ extern "C" int qie_ln_modulate(const float* x, const float* mod, long long mod_b
     // one wave overlap the loads of the next (one warp per row, the whole row in registers).
     if (g_ln_variant == 1 && D % 128 == 0 && (size_t)D * 4 * 16 + 256 <= 200 * 1024) {
         // streaming form: persistent CTAs, bulk-copy landing ring per warp, dynamic row hand-out
-        int* counters = nullptr;
-        int rc0 = qie::ln_counters(&counters);
+        qie::StreamScratch scr;
+        int rc0 = qie::stream_scratch((cudaStream_t)stream, &scr);
         if (rc0) return rc0;
+        int* counters = scr.ln_counters;
         const int sblocks = (int)std::min<long long>(sm_count(), (rows + 7) / 8);
         const size_t ssm = (size_t)D * 4 * 16 + 256;
         cudaStream_t sst = (cudaStream_t)stream;

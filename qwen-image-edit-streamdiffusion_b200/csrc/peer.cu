@@ -3,22 +3,59 @@
 // The data itself is moved by the GEMM / attention epilogues (peer stores over NVLink), not here.
 #include <string.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace qie {
 
-__device__ int g_barrier_timeouts = 0;
+// Sticky failure flag of the peer barriers: one word of mapped, pinned host memory per process, so that the host can read it
+// without synchronising any stream.  A barrier that gives up (a rank is missing or late by > 2 s) raises it; every later
+// qie_forward* call of this process then returns QIE_ECUDA instead of computing on half-written buffers.
+static volatile int* g_sticky_host = nullptr;
+static int* g_sticky_dev = nullptr;
+static std::mutex g_sticky_mu;
+
+static int sticky_init() {
+    std::lock_guard<std::mutex> lk(g_sticky_mu);
+    if (g_sticky_host) return QIE_OK;
+    int* p = nullptr;
+    QIE_CUDA_OK(cudaHostAlloc(&p, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(p, 0, 64);
+    QIE_CUDA_OK(cudaHostGetDevicePointer(&g_sticky_dev, p, 0));
+    g_sticky_host = p;
+    return QIE_OK;
+}
+
+int peer_sticky_error(bool clear) {
+    if (!g_sticky_host || *g_sticky_host == 0) return QIE_OK;
+    const int n = *g_sticky_host;
+    if (clear) *g_sticky_host = 0;
+    (void)n;
+    set_error("a peer barrier of the sequence-parallel group timed out: a rank is missing or more than 2 s late; everything "
+              "computed after it is invalid");
+    return QIE_ECUDA;
+}
 
 struct PeerFlags {
     unsigned* p[8];
 };
 
 // One thread per peer: publish my arrival in the peer's flag array, then wait for the peer's arrival in mine.
-// flags[r][s] = last epoch at which rank s arrived at rank r.  Epochs only grow, so a fast rank that is already one
-// barrier ahead still satisfies the `>=` test of a slow one.
-__global__ void peer_barrier_kernel(PeerFlags f, int rank, int size, unsigned epoch) {
+// flags[r][s] = last epoch at which rank s arrived at rank r; flags[r][8] = rank r's own barrier count (device-side, so the
+// kernel can be replayed from a CUDA graph: every rank executes the same sequence of barriers, the counts stay in step).
+// Epochs only grow, so a fast rank that is already one barrier ahead still satisfies the `>=` test of a slow one.
+__global__ void peer_barrier_kernel(PeerFlags f, int rank, int size, int* sticky) {
+    __shared__ unsigned epoch_s;
     const int t = threadIdx.x;
+    if (t == 0) {
+        unsigned* ctr = f.p[rank] + 8;
+        epoch_s = *ctr + 1;
+        *ctr = epoch_s;
+    }
+    __syncthreads();
     if (t >= size) return;
+    const unsigned epoch = epoch_s;
     __threadfence_system();   // the peer stores of the kernels before this one are ordered before the flag
     unsigned* theirs = f.p[t] + rank;
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
@@ -31,12 +68,48 @@ __global__ void peer_barrier_kernel(PeerFlags f, int rank, int size, unsigned ep
         if ((int)(v - epoch) >= 0) break;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         if (t1 - t0 > 2000000000ull) {   // 2 s: a rank is missing; fail loudly instead of hanging the GPU
-            atomicAdd(&g_barrier_timeouts, 1);
+            *reinterpret_cast<volatile int*>(sticky) = 1;   // plain store: host-mapped memory has no portable atomics
             break;
         }
         __nanosleep(100);
     }
     __threadfence_system();
+}
+
+// my [B][img_rows][C] velocity rows (compact [B][img_pad][C] source) -> rows [img_offset, img_offset + img_rows) of every rank's
+// [B][img_total][C] velocity buffer: 16-byte peer stores, one (row, 16 B) element per thread per peer
+__global__ void peer_bcast_rows_kernel(const uint4* __restrict__ src, void* const* __restrict__ vel, int size, int batch,
+                                       int img_rows, int img_pad, int img_total, int img_offset, int c16) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)batch * img_rows * c16) return;
+    const int c = (int)(i % c16);
+    const long long r = i / c16;
+    const int row = (int)(r % img_rows), b = (int)(r / img_rows);
+    const uint4 v = src[((long long)b * img_pad + row) * c16 + c];
+    for (int g = 0; g < size; ++g) {
+        uint4* dst = reinterpret_cast<uint4*>(__ldg(reinterpret_cast<const unsigned long long*>(vel) + g));
+        dst[((long long)b * img_total + img_offset + row) * c16 + c] = v;
+    }
+}
+
+int peer_bcast_rows(const void* src, void* const* peer_vel_dev, const qie_peers* pr, int img_rows, int img_offset, int C,
+                    cudaStream_t st) {
+    QIE_REQUIRE(src && peer_vel_dev && pr && C % 8 == 0, QIE_EINVAL, "peer_bcast_rows: bad argument");
+    const long long total = (long long)pr->batch * img_rows * (C / 8);
+    peer_bcast_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint4*)src, peer_vel_dev, pr->size, pr->batch,
+                                                                            img_rows, pr->img_pad, pr->img_total, img_offset, C / 8);
+    QIE_LAUNCH_OK("peer_bcast_rows_kernel");
+    return QIE_OK;
+}
+
+int peer_barrier_launch(const qie_peers* pr, cudaStream_t st) {
+    int rc = sticky_init();
+    if (rc) return rc;
+    PeerFlags f{};
+    for (int i = 0; i < pr->size; ++i) f.p[i] = (unsigned*)pr->flags[i];
+    peer_barrier_kernel<<<1, 32, 0, st>>>(f, pr->rank, pr->size, g_sticky_dev);
+    QIE_LAUNCH_OK("peer_barrier_kernel");
+    return QIE_OK;
 }
 
 }  // namespace qie
@@ -80,21 +153,5 @@ extern "C" int qie_peer_close(void* dev_ptr) {
     return QIE_OK;
 }
 
-extern "C" int qie_peer_barrier(void* const* flags_host, int rank, int size, unsigned epoch, void* stream) {
-    QIE_REQUIRE(flags_host && size >= 1 && size <= 8 && rank >= 0 && rank < size && epoch > 0, QIE_EINVAL,
-                "qie_peer_barrier: bad argument");
-    PeerFlags f{};
-    for (int i = 0; i < size; ++i) {
-        QIE_REQUIRE(flags_host[i], QIE_EINVAL, "qie_peer_barrier: flags of rank %d are null", i);
-        f.p[i] = (unsigned*)flags_host[i];
-    }
-    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, rank, size, epoch);
-    QIE_LAUNCH_OK("peer_barrier_kernel");
-    return QIE_OK;
-}
-
-extern "C" int qie_peer_barrier_timeouts(void) {
-    int n = 0;
-    if (cudaMemcpyFromSymbol(&n, g_barrier_timeouts, sizeof(int)) != cudaSuccess) return -1;
-    return n;
-}
+// number of peer-barrier timeouts of this process so far (sticky; read without synchronising; see peer_sticky_error)
+extern "C" int qie_peer_barrier_timeouts(void) { return g_sticky_host ? *g_sticky_host : 0; }

@@ -26,7 +26,7 @@ from . import _lib as L
 
 
 # ------------------------------------------------------------------------------------------------
-# host-side planning
+# host-side planning (mirror of qie_sp_shard / qie_sp_tile_valid_host in csrc/api.cu)
 # ------------------------------------------------------------------------------------------------
 def _pad128(n: int) -> int:
     return (n + 127) // 128 * 128
@@ -44,11 +44,31 @@ class ShardPlan:
     txt_rows: int
     img_pad: int          # identical on every rank
     txt_pad: int          # identical on every rank
-    tile_valid: tuple     # valid rows of every 128-row tile of the gathered (rank-major) sequence
+    tile_valid: tuple     # valid rows of every 128-row tile of the GATHERED sequence [P image shards | all text tokens]
 
     @property
     def rows_pad(self) -> int:
         return self.img_pad + self.txt_pad
+
+    @property
+    def gathered_rows(self) -> int:
+        """rows of one frame in the gathered layout of the fused exchange: every rank's padded image shard, then ALL text
+        tokens contiguously — as long as the single-GPU sequence (no per-rank text padding inside it)"""
+        return self.size * self.img_pad + _pad128(self.txt_total)
+
+    @property
+    def txt_row0(self) -> int:
+        """gathered row of this rank's first text token"""
+        return self.size * self.img_pad + self.txt_offset
+
+    def rank_major_tiles(self) -> tuple:
+        """tile list of the rank-major layout [rank][img_pad | txt_pad] the NCCL all-to-all form produces"""
+        im, tx = split_sizes(self.img_total, self.size), split_sizes(self.txt_total, self.size)
+        tiles = []
+        for r in range(self.size):
+            for n, pad in ((im[r], self.img_pad), (tx[r], self.txt_pad)):
+                tiles += [min(128, n - t * 128) for t in range(pad // 128)]
+        return tuple(tiles)
 
 
 def split_sizes(total: int, parts: int) -> List[int]:
@@ -67,8 +87,8 @@ def make_shard_plan(img_total: int, txt_total: int, size: int, rank: int) -> Sha
         raise ValueError("shards straddle a 128-row boundary: a rank would own an all-padding tile")
     tiles = []
     for r in range(size):
-        for n, pad in ((im[r], img_pad), (tx[r], txt_pad)):
-            tiles += [min(128, n - t * 128) for t in range(pad // 128)]
+        tiles += [min(128, im[r] - t * 128) for t in range(img_pad // 128)]
+    tiles += [min(128, txt_total - t * 128) for t in range(_pad128(txt_total) // 128)]
     return ShardPlan(size, rank, img_total, txt_total, sum(im[:rank]), im[rank], sum(tx[:rank]), tx[rank], img_pad, txt_pad,
                      tuple(tiles))
 
@@ -86,26 +106,37 @@ def unpack_heads(o_recv: torch.Tensor, size: int) -> torch.Tensor:
     return o_recv.permute(1, 0, 2).reshape(rows, size * w)
 
 
+def exchange_bytes_per_forward(plan: ShardPlan, batch: int, heads: int, layers: int, out_dim: int = 64) -> int:
+    """bytes one rank stores into OTHER ranks' memory per forward of the fused exchange: per block the q|k|v of its tokens for
+    the other ranks' head groups and the attention output of its head group for the other ranks' tokens, plus its velocity rows"""
+    P = plan.size
+    rows = plan.img_rows + plan.txt_rows
+    D = heads * 128
+    qkv = rows * 3 * D * 2 * (P - 1) // P
+    att = (plan.img_total + plan.txt_total - rows) * (D // P) * 2
+    return batch * (layers * (qkv + att) + plan.img_rows * out_dim * 2 * (P - 1))
+
+
 # ------------------------------------------------------------------------------------------------
 # peer-memory buffers of the fused exchange (qie_peers in include/qie.h)
 # ------------------------------------------------------------------------------------------------
 class PeerRankBuffers:
     """What ONE rank of a sequence-parallel group owns: its workspace (the attention-output buffer lives inside), the
-    gathered q|k|v buffer of its head group and its barrier flags, all cudaMalloc'ed by libqie so that they can be
-    exported over CUDA IPC and written by the other ranks' kernels through NVLink."""
+    gathered q|k|v buffer of its head group, its velocity buffer and its barrier words, all cudaMalloc'ed by libqie so that
+    they can be exported over CUDA IPC and written by the other ranks' kernels through NVLink."""
 
-    def __init__(self, ws_bytes: int, gather_bytes: int):
+    def __init__(self, ws_bytes: int, gather_bytes: int, vel_bytes: int):
         lib = L.lib()
         self.ptrs, self.handles = [], []
-        for n in (ws_bytes, gather_bytes, 256):
+        for n in (ws_bytes, gather_bytes, vel_bytes, 256):
             p, h = C.c_void_p(), C.create_string_buffer(64)
             L.check(lib.qie_peer_alloc(n, C.byref(p), h), "qie_peer_alloc")
             if n == ws_bytes and p.value % 1024:      # qie_forward wants a 1 KB aligned workspace; large cudaMallocs are
                 raise L.QieError("cudaMalloc returned a workspace that is not 1 KB aligned")
             self.ptrs.append(p.value)
             self.handles.append(h.raw)
-        self.ws, self.gather, self.flags = self.ptrs
-        self.ws_bytes = ws_bytes
+        self.ws, self.gather, self.vel, self.flags = self.ptrs
+        self.sizes = (ws_bytes, gather_bytes, vel_bytes)
 
     def free(self):
         for p in self.ptrs:
@@ -113,47 +144,87 @@ class PeerRankBuffers:
         self.ptrs = []
 
 
-def scatter_qkv_reference(qkv_local: torch.Tensor, gathered: Sequence[torch.Tensor], rank: int, size: int, heads: int) -> None:
+def scatter_qkv_reference(qkv_local: torch.Tensor, gathered: Sequence[torch.Tensor], plan: ShardPlan, heads: int) -> None:
     """Host-side statement of what the QKV-GEMM epilogue does with `qie_peers` installed (csrc/gemm.cu, `scat`): head group g of
-    q|k|v of MY rows lands in rank g's gathered buffer [size*rows, 3*(H/size)*128] at rows [rank*rows, (rank+1)*rows).
-    Equivalent to pack_heads + all_to_all_single of the NCCL form; used by the CPU tests to pin the address arithmetic."""
+    q|k|v of MY valid rows lands in rank g's gathered buffer [gathered_rows, 3*(H/size)*128] — image rows at
+    rank*img_pad + i, text rows at size*img_pad + txt_offset + i.  Used by the CPU tests to pin the address arithmetic."""
     rows = qkv_local.shape[0]
-    hl = heads // size
-    x = qkv_local.view(rows, 3, size, hl * 128)
-    for g in range(size):
-        gathered[g].view(size, rows, 3, hl * 128)[rank] = x[:, :, g]
+    hl = heads // plan.size
+    x = qkv_local.view(rows, 3, plan.size, hl * 128)
+    for g in range(plan.size):
+        dst = gathered[g].view(plan.gathered_rows, 3, hl * 128)
+        dst[plan.rank * plan.img_pad: plan.rank * plan.img_pad + plan.img_rows] = x[:plan.img_rows, :, g]
+        dst[plan.txt_row0: plan.txt_row0 + plan.txt_rows] = x[plan.img_pad: plan.img_pad + plan.txt_rows, :, g]
 
 
-def scatter_attn_reference(o_gathered: torch.Tensor, attn_out: Sequence[torch.Tensor], rank: int, size: int, heads: int) -> None:
+def scatter_attn_reference(o_gathered: torch.Tensor, attn_out: Sequence[torch.Tensor], plans: Sequence[ShardPlan], rank: int,
+                           heads: int) -> None:
     """... and what the attention epilogue does: my head group's output rows of rank s's tokens land in rank s's attention
-    buffer [rows, H*128] at head columns [rank*(H/size)*128, (rank+1)*(H/size)*128)."""
+    buffer [rows_pad, H*128] at head columns [rank*(H/size)*128, (rank+1)*(H/size)*128)."""
+    size = plans[0].size
     hl = heads // size
-    rows = o_gathered.shape[0] // size
-    for s_ in range(size):
-        attn_out[s_][:, rank * hl * 128:(rank + 1) * hl * 128] = o_gathered[s_ * rows:(s_ + 1) * rows]
+    cols = slice(rank * hl * 128, (rank + 1) * hl * 128)
+    for s_, p in enumerate(plans):
+        attn_out[s_][:p.img_rows, cols] = o_gathered[s_ * p.img_pad: s_ * p.img_pad + p.img_rows]
+        attn_out[s_][p.img_pad: p.img_pad + p.txt_rows, cols] = o_gathered[p.txt_row0: p.txt_row0 + p.txt_rows]
 
 
-def make_peers(rank: int, size: int, rows_pad: int, gathers: Sequence[int], attn_outs: Sequence[int], tile_valid: torch.Tensor):
+def make_peers(plan: ShardPlan, batch: int, gathers: Sequence[int], attn_outs: Sequence[int], vels: Sequence[int],
+               flags: Sequence[int]):
     pr = L.Peers()
-    pr.rank, pr.size, pr.rows_pad = rank, size, rows_pad
-    for i in range(size):
+    pr.rank, pr.size, pr.batch = plan.rank, plan.size, batch
+    pr.img_pad, pr.txt_pad, pr.img_total, pr.txt_total = plan.img_pad, plan.txt_pad, plan.img_total, plan.txt_total
+    for i in range(plan.size):
         pr.qkv_gather[i] = gathers[i]
         pr.attn_out[i] = attn_outs[i]
-    pr.tile_valid = tile_valid.data_ptr()
+        pr.vel[i] = vels[i]
+        pr.flags[i] = flags[i]
     return pr
+
+
+def _flat_shapes(img_shapes):
+    shapes = img_shapes[0] if isinstance(img_shapes[0][0], (list, tuple)) else img_shapes
+    return [int(v) for fhw in shapes for v in fhw]
 
 
 # ------------------------------------------------------------------------------------------------
 # Ulysses sequence-parallel transformer
 # ------------------------------------------------------------------------------------------------
+class _Geometry:
+    """per (batch, image tokens, text tokens, img_shapes) state of the fused path: shard plan, C structs, static input /
+    output buffers (fixed addresses: the forward is replayed from a CUDA graph) and the captured graph"""
+
+    def __init__(self, t, B, S_i, T, flat, size, rank):
+        dev = t.device
+        self.B, self.S_i, self.T, self.flat = B, S_i, T, flat
+        self.plan = p = make_shard_plan(S_i, T, size, rank)
+        self.seq = L.Seq(B, p.img_rows, p.txt_rows, p.img_pad, p.txt_pad)
+        self.sp = L.Sp(p.rank, p.size, p.img_total, p.txt_total, p.img_offset, p.txt_offset)
+        self.shp = (C.c_int * len(flat))(*flat)
+        hl = t.cfg.num_attention_heads // size
+        self.ws_bytes = L.lib().qie_workspace_bytes(t._handle, C.byref(self.seq))
+        self.gather_bytes = B * p.gathered_rows * 3 * hl * 128 * 2
+        self.vel_bytes = B * S_i * t.cfg.out_dim * 2
+        self.hs = torch.empty(B, p.img_rows, t.cfg.in_channels, dtype=torch.bfloat16, device=dev)
+        self.enc = torch.empty(B, p.txt_rows, t.cfg.joint_attention_dim, dtype=torch.bfloat16, device=dev)
+        self.ts = torch.empty(B, dtype=torch.float32, device=dev)
+        self.out = torch.empty(B, S_i, t.cfg.out_dim, dtype=torch.bfloat16, device=dev)
+        self.graph = None
+        self.calls = 0
+
+
 class UlyssesTransformer:
     """Wraps a B200QwenImageTransformer2DModel; same call surface, the work of ONE forward is spread over `group`.
 
-    fused=False: NCCL all-to-alls between the phases (baseline form).
+    fused=False: NCCL all-to-alls between the phases (baseline form, batch 1).
     fused=True : the QKV-GEMM and attention epilogues store straight into the peers' buffers over NVLink (CUDA IPC mapped
-                 memory) and the phases are separated by qie_peer_barrier only — no pack / all-to-all / unpack kernels."""
+                 memory), the END phase stores the velocity rows into every rank's buffer, and the phases are separated by
+                 qie_peer_barrier only — no pack / all-to-all / unpack kernels, no NCCL on the data path.  The whole forward is
+                 ONE C call (qie_forward_sp), captured in a CUDA graph on its second use (`graphs=True`) and replayed from then
+                 on; `pdl=True` launches the per-block kernels with programmatic dependent launch (their prologues overlap the
+                 previous kernel's tail).  Any batch size: the frames of a batch stay whole inside the group."""
 
-    def __init__(self, transformer, group=None, fused: bool = False):
+    def __init__(self, transformer, group=None, fused: bool = False, graphs: bool = True, pdl: bool = True):
         self.t = transformer
         self.group = group
         self.size = dist.get_world_size(group)
@@ -163,68 +234,93 @@ class UlyssesTransformer:
         self.config = transformer.config
         self._tile_cache = {}
         self.fused = fused
-        self._peer_state = None      # (key, PeerRankBuffers, opened pointers, Peers struct, flag table)
-        self._epoch = 0
+        self.graphs = graphs
+        if fused and pdl:
+            L.check(L.lib().qie_tune(7, 1), "qie_tune")
+        self._geo = {}               # geometry key -> _Geometry
+        self._bufs = None            # (PeerRankBuffers, opened pointers, per-rank pointer lists)
+        self._installed = None       # geometry key whose peers are installed in the handle
 
     # ---- fused path -------------------------------------------------------------------------------------------------
-    def _peer_setup(self, plan: "ShardPlan", seq, tiles: torch.Tensor):
+    def _ensure_buffers(self, geo: _Geometry):
+        """(re)allocates the IPC-shared buffers when `geo` needs more room than any geometry before it (collective: every
+        rank sees the same geometries in the same order) and exchanges the handles"""
+        need = (geo.ws_bytes, geo.gather_bytes, geo.vel_bytes)
+        if self._bufs is not None and all(h >= n for h, n in zip(self._bufs[0].sizes, need)):
+            return
+        sizes = need if self._bufs is None else tuple(max(h, n) for h, n in zip(self._bufs[0].sizes, need))
+        self._release_buffers()
         t, lib, P = self.t, L.lib(), self.size
-        hl = t.cfg.num_attention_heads // P
-        key = (plan.img_pad, plan.txt_pad, P)
-        if self._peer_state is not None and self._peer_state[0] == key:
-            return self._peer_state
-        if self._peer_state is not None:
-            raise L.QieError("the fused Ulysses path keeps one shard geometry per wrapper; build a new UlyssesTransformer")
-        ws_bytes = lib.qie_workspace_bytes(t._handle, C.byref(seq))
-        mine = PeerRankBuffers(ws_bytes, P * plan.rows_pad * 3 * hl * 128 * 2)
+        mine = PeerRankBuffers(*sizes)
         dev = t.device
         blob = torch.frombuffer(bytearray(b"".join(mine.handles)), dtype=torch.uint8).to(dev)
         allb = torch.empty(P * blob.numel(), dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(allb, blob, group=self.group)
-        allb = allb.cpu().view(P, 3, 64)
-        ws_p, gather_p, flag_p, opened = [], [], [], []
+        allb = allb.cpu().view(P, 4, 64)
+        per_rank, opened = [], []
         for r in range(P):
             if r == self.rank:
-                ptrs = (mine.ws, mine.gather, mine.flags)
+                ptrs = list(mine.ptrs)
             else:
                 ptrs = []
-                for i in range(3):
+                for i in range(4):
                     q = C.c_void_p()
                     L.check(lib.qie_peer_open(bytes(allb[r, i].tolist()), C.byref(q)), "qie_peer_open")
                     ptrs.append(q.value)
                     opened.append(q.value)
-            ws_p.append(ptrs[0]); gather_p.append(ptrs[1]); flag_p.append(ptrs[2])
-        off = lib.qie_workspace_offset(t._handle, C.byref(seq), 1)
-        peers = make_peers(self.rank, P, plan.rows_pad, gather_p, [w + off for w in ws_p], tiles)
-        L.check(lib.qie_set_peers(t._handle, C.byref(peers), L.cur_stream()), "qie_set_peers")
-        flags = (C.c_void_p * P)(*flag_p)
-        self._peer_state = (key, mine, opened, peers, flags)
-        return self._peer_state
+            per_rank.append(ptrs)
+        self._bufs = (mine, opened, per_rank)
+        for g in self._geo.values():          # captured graphs point into the old buffers
+            g.graph = None
+            g.calls = 0
+        self._installed = None
 
-    def _barrier(self, flags):
-        self._epoch += 1
-        L.check(L.lib().qie_peer_barrier(flags, self.rank, self.size, self._epoch, L.cur_stream()), "qie_peer_barrier")
+    def _release_buffers(self):
+        if self._bufs is None:
+            return
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        L.lib().qie_set_peers(self.t._handle, None, None)
+        for q in self._bufs[1]:
+            L.lib().qie_peer_close(C.c_void_p(q))
+        dist.barrier(group=self.group)
+        self._bufs[0].free()
+        self._bufs = None
+        self._installed = None
+
+    def _install(self, key, geo: _Geometry):
+        if self._installed == key:
+            return
+        t, lib = self.t, L.lib()
+        per_rank = self._bufs[2]
+        off = lib.qie_workspace_offset(t._handle, C.byref(geo.seq), 1)
+        peers = make_peers(geo.plan, geo.B, [p[1] for p in per_rank], [p[0] + off for p in per_rank], [p[2] for p in per_rank],
+                           [p[3] for p in per_rank])
+        L.check(lib.qie_set_peers(t._handle, C.byref(peers), L.cur_stream()), "qie_set_peers")
+        self._installed = key
 
     def close(self):
-        if self._peer_state is not None:
-            torch.cuda.synchronize()
-            dist.barrier(group=self.group)
-            L.lib().qie_set_peers(self.t._handle, None, None)
-            for q in self._peer_state[2]:
-                L.lib().qie_peer_close(C.c_void_p(q))
-            dist.barrier(group=self.group)
-            self._peer_state[1].free()
-            self._peer_state = None
+        self._geo = {}
+        self._release_buffers()
+
+    def check_barriers(self):
+        """raises once a peer barrier of this process has timed out (sticky flag in mapped host memory: no stream is
+        synchronised by the read, so it is cheap enough to call after every forward)"""
+        if L.lib().qie_peer_barrier_timeouts():
+            raise L.QieError("a peer barrier of the sequence-parallel group timed out: a rank is missing or more than 2 s late; "
+                             "the results after it are invalid")
 
     def cache_context(self, name):
         return self.t.cache_context(name)
 
     def __call__(self, hidden_states, encoder_hidden_states=None, encoder_hidden_states_mask=None, timestep=None,
                  img_shapes=None, txt_seq_lens=None, guidance=None, attention_kwargs=None, return_dict=True, **_):
+        if self.fused:
+            return self._call_fused(hidden_states, encoder_hidden_states, timestep, img_shapes, return_dict)
         t, lib = self.t, L.lib()
         B, S_i, _ = hidden_states.shape
         if B != 1:
-            raise L.QieError("sequence parallelism is implemented for batch 1 (run frames as replicas / CFG branches)")
+            raise L.QieError("the NCCL form of the sequence-parallel forward is a batch-1 baseline; use fused=True for batches")
         T = encoder_hidden_states.shape[1]
         plan = make_shard_plan(S_i, T, self.size, self.rank)
         dev = t.device
@@ -232,12 +328,10 @@ class UlyssesTransformer:
         sp = L.Sp(plan.rank, plan.size, plan.img_total, plan.txt_total, plan.img_offset, plan.txt_offset)
         D, H, P = t.cfg.inner_dim, t.cfg.num_attention_heads, self.size
         rows = plan.rows_pad
-        key = plan.tile_valid
+        key = plan.rank_major_tiles()
         if key not in self._tile_cache:
-            self._tile_cache[key] = torch.tensor(plan.tile_valid, dtype=torch.int32, device=dev)
+            self._tile_cache[key] = torch.tensor(key, dtype=torch.int32, device=dev)
         tiles = self._tile_cache[key]
-        if self.fused:
-            return self._call_fused(hidden_states, encoder_hidden_states, timestep, img_shapes, plan, seq, sp, tiles, return_dict)
         ws = t._workspace(seq)
         base = (ws.data_ptr() + 1023) // 1024 * 1024
         ws_bytes = ws.numel() - (base - ws.data_ptr())
@@ -250,8 +344,7 @@ class UlyssesTransformer:
         hs = hidden_states[:, plan.img_offset: plan.img_offset + plan.img_rows].to(torch.bfloat16).contiguous()
         enc = encoder_hidden_states[:, plan.txt_offset: plan.txt_offset + plan.txt_rows].to(dev, torch.bfloat16).contiguous()
         ts = timestep.to(device=dev, dtype=torch.float32).reshape(-1).expand(1).contiguous()
-        shapes = img_shapes[0] if isinstance(img_shapes[0][0], (list, tuple)) else img_shapes
-        flat = [int(v) for fhw in shapes for v in fhw]
+        flat = _flat_shapes(img_shapes)
         shp = (C.c_int * len(flat))(*flat)
         out_local = torch.empty(1, plan.img_rows, t.cfg.out_dim, dtype=torch.bfloat16, device=dev)
         hl = H // P
@@ -291,33 +384,45 @@ class UlyssesTransformer:
         dist.all_gather(parts, out_local[0].contiguous(), group=self.group)
         return torch.cat(parts, 0).unsqueeze(0)
 
-    def _call_fused(self, hidden_states, encoder_hidden_states, timestep, img_shapes, plan, seq, sp, tiles, return_dict):
+    def _call_fused(self, hidden_states, encoder_hidden_states, timestep, img_shapes, return_dict):
         t, lib, dev = self.t, L.lib(), self.t.device
-        _, mine, _, _, flags = self._peer_setup(plan, seq, tiles)
-        S_i = hidden_states.shape[1]
-        hs = hidden_states[:, plan.img_offset: plan.img_offset + plan.img_rows].to(torch.bfloat16).contiguous()
-        enc = encoder_hidden_states[:, plan.txt_offset: plan.txt_offset + plan.txt_rows].to(dev, torch.bfloat16).contiguous()
-        ts = timestep.to(device=dev, dtype=torch.float32).reshape(-1).expand(1).contiguous()
-        shapes = img_shapes[0] if isinstance(img_shapes[0][0], (list, tuple)) else img_shapes
-        flat = [int(v) for fhw in shapes for v in fhw]
-        shp = (C.c_int * len(flat))(*flat)
-        out_local = torch.empty(1, plan.img_rows, t.cfg.out_dim, dtype=torch.bfloat16, device=dev)
-
-        def phase(mask, layer):
-            L.check(lib.qie_forward_phase(t._handle, mask, layer, L.ptr(hs), L.ptr(enc), L.ptr(ts), shp, len(flat) // 3,
-                                          C.byref(seq), C.byref(sp), L.ptr(out_local), C.c_void_p(mine.ws), mine.ws_bytes, -1,
-                                          L.cur_stream()), "qie_forward_phase")
-
+        B, S_i, _ = hidden_states.shape
+        T = encoder_hidden_states.shape[1]
+        flat = _flat_shapes(img_shapes)
+        key = (B, S_i, T, tuple(flat))
+        geo = self._geo.get(key)
+        if geo is None:
+            geo = self._geo[key] = _Geometry(t, B, S_i, T, flat, self.size, self.rank)
+        p = geo.plan
         with torch.cuda.device(dev):
-            phase(1, -1)
-            for l in range(t.cfg.num_layers):
-                phase(2, l)              # adaLN1 + QKV GEMM: the epilogue stores q|k|v of head group g into rank g's gather buffer
-                self._barrier(flags)     # everybody's q|k|v has landed in my gather buffer
-                phase(4, l)              # attention of my heads over all tokens: the epilogue stores into the token owners' buffers
-                self._barrier(flags)     # everybody's heads have landed in my attention buffer (and my gather buffer is free again)
-                phase(8, l)              # out-proj, adaLN2, FF on my tokens
-            phase(16, -1)
-            out = self._gather_velocity(out_local, S_i)
+            self._ensure_buffers(geo)
+            self._install(key, geo)
+            mine = self._bufs[0]
+            geo.hs.copy_(hidden_states[:, p.img_offset: p.img_offset + p.img_rows])
+            geo.enc.copy_(encoder_hidden_states[:, p.txt_offset: p.txt_offset + p.txt_rows])
+            geo.ts.copy_(timestep.to(device=dev, dtype=torch.float32).reshape(-1).expand(B))
+
+            def run():
+                L.check(lib.qie_forward_sp(t._handle, L.ptr(geo.hs), L.ptr(geo.enc), L.ptr(geo.ts), geo.shp, len(flat) // 3,
+                                           C.byref(geo.seq), C.byref(geo.sp), L.ptr(geo.out), C.c_void_p(mine.ws), mine.sizes[0],
+                                           L.cur_stream()), "qie_forward_sp")
+
+            profiling = getattr(t, "_profiling", False)      # per-kernel CUDA events are recorded by eager launches only
+            if geo.graph is not None and not profiling:
+                geo.graph.replay()
+            elif self.graphs and geo.calls >= 1 and not profiling:
+                # second use of this geometry: every lazily built table exists (RoPE rows, tile list, kernel attributes), so the
+                # call neither allocates nor synchronises any more and can be recorded
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    run()
+                geo.graph = g
+                g.replay()
+            else:
+                run()
+            geo.calls += 1
+            self.check_barriers()
+            out = geo.out.clone()
         out = out.to(hidden_states.dtype) if hidden_states.dtype != torch.bfloat16 else out
         return (out,) if not return_dict else type("Out", (), {"sample": out})()
 
@@ -326,32 +431,31 @@ def emulate_fused_ulysses(transformer, size: int, hidden_states, encoder_hidden_
     """Single-GPU emulation of the fused peer-memory path (tests): the `size` ranks live in ONE process on one device, the
     peer tables point at each emulated rank's local buffers, and the ranks' phases run one after the other on one stream
     (stream order replaces qie_peer_barrier; kernels that wait on one another must not share a GPU).  Everything else —
-    shard plan, scatter addressing in the QKV-GEMM and attention epilogues, tile list — is the code the real path runs."""
+    shard plan, scatter addressing in the QKV-GEMM / attention / velocity epilogues, tile list — is the code the real path
+    runs.  Returns the velocity buffer of every emulated rank ([size][B, S_i, out_dim]; all must be equal)."""
     t, lib, dev = transformer, L.lib(), transformer.device
-    S_i, T = hidden_states.shape[1], encoder_hidden_states.shape[1]
+    B, S_i, T = hidden_states.shape[0], hidden_states.shape[1], encoder_hidden_states.shape[1]
     H = t.cfg.num_attention_heads
     hl = H // size
     plans = [make_shard_plan(S_i, T, size, r) for r in range(size)]
-    rows = plans[0].rows_pad
-    tiles = torch.tensor(plans[0].tile_valid, dtype=torch.int32, device=dev)
-    seqs = [L.Seq(1, p.img_rows, p.txt_rows, p.img_pad, p.txt_pad) for p in plans]
+    seqs = [L.Seq(B, p.img_rows, p.txt_rows, p.img_pad, p.txt_pad) for p in plans]
     sps = [L.Sp(p.rank, p.size, p.img_total, p.txt_total, p.img_offset, p.txt_offset) for p in plans]
     ws_bytes = max(lib.qie_workspace_bytes(t._handle, C.byref(s)) for s in seqs)
-    bufs = [PeerRankBuffers(ws_bytes, size * rows * 3 * hl * 128 * 2) for _ in range(size)]
+    vel_bytes = B * S_i * t.cfg.out_dim * 2
+    bufs = [PeerRankBuffers(ws_bytes, B * plans[0].gathered_rows * 3 * hl * 128 * 2, vel_bytes) for _ in range(size)]
     off = lib.qie_workspace_offset(t._handle, C.byref(seqs[0]), 1)
-    peers = [make_peers(r, size, rows, [b.gather for b in bufs], [b.ws + off for b in bufs], tiles) for r in range(size)]
-    ts = timestep.to(device=dev, dtype=torch.float32).reshape(-1).expand(1).contiguous()
-    shapes = img_shapes[0] if isinstance(img_shapes[0][0], (list, tuple)) else img_shapes
-    flat = [int(v) for fhw in shapes for v in fhw]
+    peers = [make_peers(plans[r], B, [b.gather for b in bufs], [b.ws + off for b in bufs], [b.vel for b in bufs],
+                        [b.flags for b in bufs]) for r in range(size)]
+    ts = timestep.to(device=dev, dtype=torch.float32).reshape(-1).expand(B).contiguous()
+    flat = _flat_shapes(img_shapes)
     shp = (C.c_int * len(flat))(*flat)
     hs = [hidden_states[:, p.img_offset: p.img_offset + p.img_rows].to(torch.bfloat16).contiguous() for p in plans]
     enc = [encoder_hidden_states[:, p.txt_offset: p.txt_offset + p.txt_rows].to(dev, torch.bfloat16).contiguous() for p in plans]
-    outs = [torch.empty(1, p.img_rows, t.cfg.out_dim, dtype=torch.bfloat16, device=dev) for p in plans]
 
     def phase(r, mask, layer):
         L.check(lib.qie_set_peers(t._handle, C.byref(peers[r]), L.cur_stream()), "qie_set_peers")
         L.check(lib.qie_forward_phase(t._handle, mask, layer, L.ptr(hs[r]), L.ptr(enc[r]), L.ptr(ts), shp, len(flat) // 3,
-                                      C.byref(seqs[r]), C.byref(sps[r]), L.ptr(outs[r]), C.c_void_p(bufs[r].ws), ws_bytes, -1,
+                                      C.byref(seqs[r]), C.byref(sps[r]), None, C.c_void_p(bufs[r].ws), ws_bytes, -1,
                                       L.cur_stream()), "qie_forward_phase")
 
     try:
@@ -363,14 +467,28 @@ def emulate_fused_ulysses(transformer, size: int, hidden_states, encoder_hidden_
                     for r in range(size):
                         phase(r, m, l)
             for r in range(size):
-                phase(r, 16, -1)
+                phase(r, 16, -1)           # velocity rows of rank r -> every emulated rank's velocity buffer
+            torch.cuda.synchronize()
+            outs = []
+            for b in bufs:
+                o = torch.empty(B, S_i, t.cfg.out_dim, dtype=torch.bfloat16, device=dev)
+                _memcpy_d2d(o, b.vel, vel_bytes)
+                outs.append(o)
             torch.cuda.synchronize()
     finally:
         lib.qie_set_peers(t._handle, None, None)
         torch.cuda.synchronize()
         for b in bufs:
             b.free()
-    return torch.cat([o[0] for o in outs], 0).unsqueeze(0)
+    return outs
+
+
+def _memcpy_d2d(dst: torch.Tensor, src_ptr: int, nbytes: int) -> None:
+    """device-to-device copy from a raw libqie allocation into a torch tensor (cudart through torch's own binding)"""
+    rt = torch.cuda.cudart()
+    err = rt.cudaMemcpy(dst.data_ptr(), src_ptr, nbytes, 3)      # cudaMemcpyDeviceToDevice
+    if int(err) != 0:
+        raise L.QieError(f"cudaMemcpy failed with {err}")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -425,18 +543,29 @@ def run_denoise_parallel(transformer, layout: ParallelLayout, latents, image_lat
     """The denoise loop of pipeline.run_denoise with the two CFG branches on different ranks (and, if the transformer is a
     UlyssesTransformer, each forward spread over the branch's ranks).  `step_fn` defaults to the fused CUDA CFG+Euler kernel."""
     from .pipeline import cfg_euler_step, flowmatch_sigmas, model_timestep
+    if step_fn is None:          # the fused CUDA CFG+Euler kernel works on bf16 latents (the pipeline's dtype), as run_denoise
+        latents, image_latents = latents.to(torch.bfloat16), image_latents.to(torch.bfloat16)
     step_fn = step_fn or cfg_euler_step
     timestep_fn = timestep_fn or model_timestep
-    latents = latents.clone()
+    latents = latents.contiguous().clone()
     B, n, _ = latents.shape
     sig = np.asarray(sigmas, dtype=np.float32) if sigmas is not None else flowmatch_sigmas(num_inference_steps, n)
     embeds = prompt_embeds if layout.branch == 0 else negative_prompt_embeds
+    do_cfg = true_cfg_scale > 1 and negative_prompt_embeds is not None
     for i in range(num_inference_steps):
         x = torch.cat([latents, image_latents], dim=1)
         ts = timestep_fn(float(sig[i]), B, latents.device)
-        v = transformer(hidden_states=x, timestep=ts, encoder_hidden_states=embeds, img_shapes=img_shapes,
-                        txt_seq_lens=[embeds.shape[1]] * B, return_dict=False)[0][:, :n].contiguous()
-        vc, vu = exchange_velocities(v, layout)
+
+        def fwd(e):
+            return transformer(hidden_states=x, timestep=ts, encoder_hidden_states=e, img_shapes=img_shapes,
+                               txt_seq_lens=[e.shape[1]] * B, return_dict=False)[0][:, :n].contiguous()
+
+        v = fwd(embeds)
+        if layout.cfg_branches == 1:
+            # pure sequence parallelism: both CFG forwards run on this group, one after the other
+            vc, vu = v, (fwd(negative_prompt_embeds) if do_cfg else None)
+        else:
+            vc, vu = exchange_velocities(v, layout)
         if collect is not None:
             collect.append((vc.clone(), None if vu is None else vu.clone()))
         latents = step_fn(latents, vc, vu, true_cfg_scale, float(sig[i]), float(sig[i + 1]))

@@ -381,16 +381,28 @@ class B200QwenImageTransformer2DModel(nn.Module):
         L.check(L.lib().qie_cache_select(self._handle, idx, B if idx is not None else 0, slot), "qie_cache_select")
 
     # ------------------------------------------------------------------ measurement aids
-    PROFILE_CLASSES = ("gemm", "attention", "adaln", "mod_gemv", "other")
+    PROFILE_CLASSES = ("gemm", "attention", "adaln", "mod_gemv", "other", "barrier")
+    _profiling = False
 
     def profile(self, on: bool):
         """record CUDA events around every kernel class inside qie_forward (read with read_profile)."""
+        self._profiling = bool(on)
         return self.set_option(2, 1 if on else 0)
 
     def read_profile(self) -> Dict[str, Dict[str, float]]:
-        ms, work, n = (C.c_double * 5)(), (C.c_double * 5)(), (C.c_int * 5)()
+        n_cls = L.PROFILE_CLASSES
+        ms, work, n = (C.c_double * n_cls)(), (C.c_double * n_cls)(), (C.c_int * n_cls)()
         L.check(L.lib().qie_profile_read(self._handle, ms, work, n), "qie_profile_read")
         return {k: {"ms": ms[i], "work": work[i], "launches": n[i]} for i, k in enumerate(self.PROFILE_CLASSES)}
+
+    def read_timeline(self, max_n: int = 4096):
+        """[(start_ms, duration_ms, class name)] of every launch recorded since the last read_profile (call it BEFORE
+        read_profile, which consumes the events): where the time of one forward goes, gaps between the kernels included."""
+        st, du, cl = (C.c_float * max_n)(), (C.c_float * max_n)(), (C.c_int * max_n)()
+        n = L.lib().qie_profile_timeline(self._handle, st, du, cl, max_n)
+        if n < 0:
+            L.check(n, "qie_profile_timeline")
+        return [(st[i], du[i], self.PROFILE_CLASSES[cl[i]]) for i in range(n)]
 
     # ------------------------------------------------------------------ forward
     def _workspace(self, seq: L.Seq) -> torch.Tensor:

@@ -7,3 +7,4 @@ run glue tests/test_kernels_gpu.py -k "cfg_euler or ln_modulate or gemv or times
 run gemm tests/test_kernels_gpu.py -k "gemm"
 run attn tests/test_kernels_gpu.py -k "attention"
 run forward tests/test_forward_gpu.py
+run parallel tests/test_parallel_gpu.py

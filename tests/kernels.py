@@ -30,7 +30,7 @@ def from_joint(s, x):
 
 
 def gemm(s, a, w, bias, out, epilogue, streams=3, a_compact=0, out_compact=0, gate=None, gate_bstride=0,
-         gate_sstride=0, rope=None, qk_norm_w=None, block_n=0, fp8=False, a_scale=None, w_scale=None, cta_group=0, ln=None):
+         gate_sstride=0, rope=None, qk_norm_w=None, block_n=0, fp8=False, a_scale=None, w_scale=None, cta_group=0):
     g = L.GemmArgs()
     g.a = a.data_ptr(); g.a_compact = a_compact
     for i in range(2):
@@ -55,12 +55,6 @@ def gemm(s, a, w, bias, out, epilogue, streams=3, a_compact=0, out_compact=0, ga
         g.a_scale = a_scale.data_ptr()
     g.block_n = block_n
     g.cta_group = cta_group
-    if ln is not None:       # dict(out, mod, bstride, sstride, shift_off, scale_off[, out8, scale, qmode]): fused adaLN
-        g.ln_out = ln["out"].data_ptr(); g.ln_mod = ln["mod"].data_ptr()
-        g.ln_mod_bstride, g.ln_mod_sstride = ln["bstride"], ln["sstride"]
-        g.ln_shift_off, g.ln_scale_off, g.ln_eps = ln["shift_off"], ln["scale_off"], 1e-6
-        if ln.get("out8") is not None:
-            g.ln_out8 = ln["out8"].data_ptr(); g.ln_out_scale = ln["scale"].data_ptr(); g.ln_qmode = ln.get("qmode", 1)
     L.check(L.lib().qie_gemm(C.byref(g), C.byref(s), L.cur_stream()), "qie_gemm")
     return out
 

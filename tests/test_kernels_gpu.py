@@ -236,35 +236,6 @@ def test_gemm_split_k_tail(epi, img, txt, N, Kd):
     assert K.rel_err(gi, wi_) <= (5e-6 if epi == "gate_resid" else 2 ** -7) and K.rel_err(gt, wt_) <= (5e-6 if epi == "gate_resid" else 2 ** -7)
 
 
-@pytest.mark.parametrize("B,img,txt,N,Kd,q8", [(1, 8192, 256, 3072, 512, False), (2, 200, 19, 256, 256, False),
-                                                 (1, 4096 + 130, 219, 3072, 1024, True), (1, 384, 300, 512, 320, False),
-                                                 (1, 8192, 256, 3072, 6144, False)])     # last: long K, the split-K tail is active too
-def test_gemm_fused_adaln_equals_separate_kernel(B, img, txt, N, Kd, q8):
-    """GATE_RESID GEMM with the following LayerNorm+modulate fused into its tail (completion counters per 256-row unit, rows
-    normalised by warps that ran out of tiles) == the same GEMM followed by qie_ln_modulate: residual and adaLN output
-    bit-identical, twice in a row (the counters re-arm themselves)."""
-    s = K.seq(B, img, txt)
-    a, w, b = _gemm_case(s, N, Kd, seed=80)
-    rows = K.rows(s)
-    gate = randn(B, 2, 6 * N, seed=81)
-    res0 = randn(rows, N, seed=82)
-    sep = res0.clone()
-    K.gemm(s, a, w, b, sep, K.L.EPI_GATE_RESID_F32, gate=gate[:, :, 2 * N:], gate_bstride=12 * N, gate_sstride=6 * N, cta_group=2)
-    want = K.ln_modulate(s, sep, gate, 12 * N, 6 * N, 3 * N, 4 * N, N, fp8=q8)
-    for _ in range(2):
-        fused = res0.clone()
-        xm = torch.full((rows, N), 5.0, dtype=torch.bfloat16, device=DEV)
-        ln = dict(out=xm, mod=gate, bstride=12 * N, sstride=6 * N, shift_off=3 * N, scale_off=4 * N)
-        if q8:
-            ln.update(out8=torch.empty(rows, N, dtype=torch.uint8, device=DEV), scale=torch.empty(rows, dtype=torch.float32, device=DEV), qmode=1)
-        K.gemm(s, a, w, b, fused, K.L.EPI_GATE_RESID_F32, gate=gate[:, :, 2 * N:], gate_bstride=12 * N, gate_sstride=6 * N, cta_group=2, ln=ln)
-        assert torch.equal(fused, sep)
-        if q8:
-            assert torch.equal(xm, want[0]) and torch.equal(ln["out8"], want[1]) and torch.equal(ln["scale"], want[2])
-        else:
-            assert torch.equal(xm, want)
-
-
 def test_gemm_compact_single_stream():
     s = K.seq(2, 200, 19)
     N, Kd = 256, 64
@@ -335,8 +306,7 @@ def test_gemm_fp8(cta_group):
 # ------------------------------------------------------------------ attention
 @pytest.mark.parametrize("B,img,txt,H", [(1, 256, 128, 2), (1, 384, 128, 1), (2, 200, 19, 2), (1, 1024, 219, 3),
                                          (2, 520, 130, 2)])
-@pytest.mark.parametrize("variant", [0, 0x100, 0x01, 0x20, 0x31, 0x41, 0x102, 0x22, 0x42, 0x104, 0x24, 0x34, 0x108, 0x28,
-                                     0x1000, 0x1020, 0x1030, 0x1040, 0x1021, 0x1022, 0x1032, 0x1024, 0x1034])
+@pytest.mark.parametrize("variant", [0, 0x100, 0x20, 0x30, 0x40, 0x108, 0x28])     # CTA-pair kernel (default) / 0x8: single-CTA fallback
 def test_attention(B, img, txt, H, variant):
     s = K.seq(B, img, txt)
     D = H * 128
@@ -367,11 +337,10 @@ def test_attention_large_scores_lazy_rescale():
     assert K.rel_err(got, ref) <= 2 ** -6
 
 
-@pytest.mark.parametrize("variant", [0, 0x1020, 0x1022, 0x1024])
+@pytest.mark.parametrize("variant", [0, 0x28])
 @pytest.mark.parametrize("jump", [3.0, 40.0])
 def test_attention_score_jumps_between_tiles(variant, jump):
-    """Keys whose scale jumps from one KV tile to the next: the lazy rescale path (moderate jump) and, for the speculative-
-    reference build 0x1022, the overflow flag + exact rerun (a jump far beyond 2^100 in the exponent)."""
+    """Keys whose scale jumps from one KV tile to the next: the lazy rescale path of both kernels."""
     s = K.seq(1, 768, 128)
     H, D = 1, 128
     qkv = randn(K.rows(s), 3 * D, seed=92, dtype=torch.bfloat16)

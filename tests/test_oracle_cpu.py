@@ -315,6 +315,11 @@ def test_sigma_schedule_properties_library_vs_oracle():
         assert np.isnan(R.ref_flowmatch_sigmas(1, 4096)[0])
     with pytest.raises(qie_b200.QieError, match="at least 2 steps"):
         qie_b200.flowmatch_sigmas(1, 4096)
+    # ... and so does the C entry point itself (a caller that binds libqie directly must not get NaN sigmas with QIE_OK)
+    import ctypes as C
+    buf = (C.c_float * 2)()
+    lib = qie_b200.lib()
+    assert lib.qie_flowmatch_sigmas(1, 4096, buf) == -1 and b"at least 2 steps" in lib.qie_last_error()
 
 
 def test_rope_table_library_vs_oracle_random_image_lists():

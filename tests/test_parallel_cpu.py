@@ -54,8 +54,33 @@ def test_shard_plan_covers_sequence(img, txt, P):
         assert a.img_offset + a.img_rows == b.img_offset and a.txt_offset + a.txt_rows == b.txt_offset
         assert (a.img_pad, a.txt_pad, a.tile_valid) == (b.img_pad, b.txt_pad, b.tile_valid)
     p0 = plans[0]
-    assert len(p0.tile_valid) == P * p0.rows_pad // 128 and min(p0.tile_valid) >= 1
+    assert len(p0.tile_valid) == p0.gathered_rows // 128 and min(p0.tile_valid) >= 1
     assert sum(p0.tile_valid) == img + txt
+    # the gathered sequence of the fused exchange is never longer than the single-GPU one (text is not padded per rank)
+    assert p0.gathered_rows <= P * p0.img_pad + (txt + 127) // 128 * 128
+    rm = p0.rank_major_tiles()
+    assert len(rm) == P * p0.rows_pad // 128 and sum(rm) == img + txt
+
+
+@pytest.mark.parametrize("img,txt,P", [(8192, 256, 4), (8192, 219, 2), (3072, 427, 8), (8192, 256, 8), (250, 19, 2), (700, 150, 3)])
+def test_library_shard_plan_equals_python_plan(img, txt, P):
+    """qie_sp_shard / qie_sp_tile_valid_host (host-only entry points of libqie.so; what qie_set_peers derives the tile list of
+    the gathered sequence from) agree with parallel.make_shard_plan for every rank."""
+    import ctypes as C
+    from qie_b200 import _lib as L
+    lib = qie_b200.lib()
+    for r in range(P):
+        p = qie_b200.make_shard_plan(img, txt, P, r)
+        s, sp = L.Seq(), L.Sp()
+        assert lib.qie_sp_shard(3, img, txt, P, r, C.byref(s), C.byref(sp)) == 0
+        assert (s.batch, s.img_rows, s.txt_rows, s.img_pad, s.txt_pad) == (3, p.img_rows, p.txt_rows, p.img_pad, p.txt_pad)
+        assert (sp.rank, sp.size, sp.img_total, sp.txt_total, sp.img_offset, sp.txt_offset) == (r, P, img, txt, p.img_offset, p.txt_offset)
+    buf = (C.c_int * 1024)()
+    n = lib.qie_sp_tile_valid_host(img, txt, P, buf, 1024)
+    assert tuple(buf[:n]) == p.tile_valid
+    assert lib.qie_sp_tile_valid_host(img, txt, P, buf, 2) == -4          # QIE_ENOMEM: no room
+    s, sp = L.Seq(), L.Sp()
+    assert lib.qie_sp_shard(1, 8192, 257, 2, 0, C.byref(s), C.byref(sp)) == -2     # QIE_ESHAPE, like the Python plan
 
 
 def test_shard_plan_rejects_bad_splits():
@@ -90,7 +115,7 @@ def _ulysses_worker(rank, world, img, txt, H):
     dist.all_to_all_single(recv, send)
     hl = H // world
     full = recv.view(world * plan.rows_pad, 3, hl, 128)
-    valid = torch.cat([torch.arange(128) < n for n in plan.tile_valid])            # tile_valid semantics of qie_attn_fwd_tiles
+    valid = torch.cat([torch.arange(128) < n for n in plan.rank_major_tiles()])    # tile_valid semantics of qie_attn_fwd_tiles
     q, k, v = (full[:, i].transpose(0, 1) for i in range(3))                        # [hl, rows, 128]
     mask = valid[None, None, :].expand(1, full.shape[0], -1)
     o = F.scaled_dot_product_attention(q[None], k[None], v[None], attn_mask=mask)[0].transpose(0, 1)   # [rows, hl, 128]
@@ -147,29 +172,71 @@ def test_layout_ranks():
 
 
 # ------------------------------------------------------------------ fused peer-memory exchange: address arithmetic on the host
-@pytest.mark.parametrize("P,H,rows", [(2, 4, 256), (4, 4, 128), (8, 24, 128), (2, 6, 384)])
-def test_fused_scatter_addressing_equals_pack_plus_all_to_all(P, H, rows):
+@pytest.mark.parametrize("P,H,img,txt", [(2, 4, 250, 19), (4, 4, 1000, 300), (8, 8, 1024, 256), (2, 6, 384, 130), (3, 3, 700, 150)])
+def test_fused_scatter_addressing_reproduces_single_process_attention(P, H, img, txt):
     """The destination layout the fused epilogues write (scatter_*_reference = the address arithmetic of csrc/gemm.cu and
-    csrc/attn.cu with qie_peers) is exactly what pack_heads + all_to_all / all_to_all + unpack_heads of the NCCL form
-    produce — all ranks simulated in one process."""
+    csrc/attn.cu with qie_peers): every rank's gathered buffer holds [rank 0 image shard | ... | all text tokens] of its head
+    group, attention over it with the plan's tile list equals single-process attention, and the output scatter hands every rank
+    the rows of its own tokens — all ranks simulated in one process."""
     g = torch.Generator().manual_seed(P * 100 + H)
     hl = H // P
-    qkv = [torch.randn(rows, 3 * H * 128, generator=g) for _ in range(P)]
-    gathered = [torch.zeros(P * rows, 3 * hl * 128) for _ in range(P)]
-    for r in range(P):
-        qie_b200.scatter_qkv_reference(qkv[r], gathered, r, P, H)
-    packed = [qie_b200.pack_heads(qkv[r], P, H) for r in range(P)]                  # [P(dest), rows, 3*hl*128] per source
-    for dst in range(P):
-        want = torch.stack([packed[src][dst] for src in range(P)])                    # what all_to_all_single delivers
-        assert torch.equal(gathered[dst].view(P, rows, 3 * hl * 128), want)
-    # attention output path
-    o = [torch.randn(P * rows, hl * 128, generator=g) for _ in range(P)]              # rank g: its heads, all tokens
-    attn = [torch.zeros(rows, H * 128) for _ in range(P)]
-    for r in range(P):
-        qie_b200.scatter_attn_reference(o[r], attn, r, P, H)
-    for dst in range(P):
-        recv = torch.stack([o[src].view(P, rows, hl * 128)[dst] for src in range(P)])   # all_to_all_single of o_full
-        assert torch.equal(attn[dst], qie_b200.unpack_heads(recv, P))
+    full = torch.randn(img + txt, 3, H, 128, generator=g)                      # [img tokens; txt tokens]
+    plans = [qie_b200.make_shard_plan(img, txt, P, r) for r in range(P)]
+    p0 = plans[0]
+    gathered = [torch.zeros(p0.gathered_rows, 3 * hl * 128) for _ in range(P)]
+    for p in plans:
+        local = torch.zeros(p.rows_pad, 3, H, 128)
+        local[:p.img_rows] = full[p.img_offset: p.img_offset + p.img_rows]
+        local[p.img_pad: p.img_pad + p.txt_rows] = full[img + p.txt_offset: img + p.txt_offset + p.txt_rows]
+        qie_b200.scatter_qkv_reference(local.view(p.rows_pad, -1), gathered, p, H)
+    valid = torch.cat([torch.arange(128) < n for n in p0.tile_valid])
+    assert int(valid.sum()) == img + txt and valid.numel() == p0.gathered_rows
+    ref = F.scaled_dot_product_attention(*(full[:, i].transpose(0, 1)[None] for i in range(3)))[0].transpose(0, 1)   # [S, H, 128]
+    attn = [torch.zeros(p0.rows_pad, H * 128) for _ in range(P)]
+    for gk in range(P):
+        x = gathered[gk].view(p0.gathered_rows, 3, hl, 128)
+        # the gathered buffer holds exactly the tokens of the whole sequence, in order, for head group gk
+        assert torch.equal(x[valid], full[:, :, gk * hl:(gk + 1) * hl])
+        q, k, v = (x[:, i].transpose(0, 1)[None] for i in range(3))
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=valid[None, None, None, :])[0].transpose(0, 1)
+        qie_b200.scatter_attn_reference(o.reshape(p0.gathered_rows, hl * 128), attn, plans, gk, H)
+    for p in plans:
+        mine = attn[p.rank].view(p0.rows_pad, H, 128)
+        assert torch.allclose(mine[:p.img_rows], ref[p.img_offset: p.img_offset + p.img_rows], atol=1e-5)
+        assert torch.allclose(mine[p.img_pad: p.img_pad + p.txt_rows], ref[img + p.txt_offset: img + p.txt_offset + p.txt_rows], atol=1e-5)
+        assert not mine[p.img_rows: p.img_pad].any() and not mine[p.img_pad + p.txt_rows:].any()     # pad rows untouched
+
+
+def test_exchange_bytes_accounting():
+    p = qie_b200.make_shard_plan(8192, 256, 4, 1)
+    rows, D = p.img_rows + p.txt_rows, 3072
+    per_block = rows * 3 * D * 2 * 3 // 4 + (8448 - rows) * (D // 4) * 2
+    assert qie_b200.exchange_bytes_per_forward(p, 1, 24, 60) == 60 * per_block + p.img_rows * 64 * 2 * 3
+
+
+def test_pure_sequence_parallel_layout_runs_both_cfg_forwards():
+    """run_denoise_parallel with one CFG branch (all ranks in ONE sequence-parallel group) must still apply true CFG: both
+    forwards run on the group (they were silently dropped)."""
+    m = R.init_weights_(R.QwenImageTransformer2DModelRef(R.TINY_CONFIG), seed=0).eval()
+    shapes = [[(1, 8, 8), (1, 8, 8)]]
+    g = torch.Generator().manual_seed(3)
+    lat, img_lat = torch.randn(1, 64, 64, generator=g), torch.randn(1, 64, 64, generator=g)
+    cond, unc = torch.randn(1, 9, 64, generator=g), torch.randn(1, 5, 64, generator=g)
+    layout = qie_b200.make_layout(1, 0, 1)
+
+    def step(latents, vc, vu, scale, s, s_next):
+        return R.ref_euler_step(latents, R.ref_cfg_combine(vc, vu, scale) if vu is not None else vc, s, s_next)
+
+    def tsf(sigma, B, device):
+        return R.ref_timestep_for_model(sigma, torch.float32).expand(B)
+
+    with torch.no_grad():
+        got = qie_b200.run_denoise_parallel(m, layout, lat, img_lat, cond, unc, shapes, 3, 4.0,
+                                            sigmas=R.ref_flowmatch_sigmas(3, 64), step_fn=step, timestep_fn=tsf)
+        ref = R.ref_run_denoise(m, lat, img_lat, cond, shapes, 3, unc, 4.0)
+        cond_only = R.ref_run_denoise(m, lat, img_lat, cond, shapes, 3, None, 1.0)
+    assert float((got - ref).abs().max()) < 1e-5
+    assert float((got - cond_only).abs().max()) > 1e-3       # i.e. the uncond branch really contributed
 
 
 def test_shard_plan_properties_hypothesis():
@@ -185,7 +252,7 @@ def test_shard_plan_properties_hypothesis():
         except ValueError:
             return
         assert sum(p.img_rows for p in plans) == img and sum(p.txt_rows for p in plans) == txt
-        assert len({(p.img_pad, p.txt_pad, p.tile_valid) for p in plans}) == 1
+        assert len({(p.img_pad, p.txt_pad, p.tile_valid, p.gathered_rows) for p in plans}) == 1
         p0 = plans[0]
         assert p0.img_pad % 128 == 0 and p0.txt_pad % 128 == 0
         assert all(1 <= v <= 128 for v in p0.tile_valid) and sum(p0.tile_valid) == img + txt

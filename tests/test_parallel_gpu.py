@@ -23,10 +23,11 @@ def test_attention_over_explicit_tile_list():
     rows = 3 * plan.rows_pad
     g = torch.Generator(device=dev).manual_seed(0)
     qkv = torch.randn(rows, 3 * H * 128, generator=g, device=dev).bfloat16()
-    tiles = torch.tensor(plan.tile_valid, dtype=torch.int32, device=dev)
+    tv = plan.rank_major_tiles()
+    tiles = torch.tensor(tv, dtype=torch.int32, device=dev)
     out = torch.empty(rows, H * 128, dtype=torch.bfloat16, device=dev)
     L.check(L.lib().qie_attn_fwd_tiles(L.ptr(qkv), L.ptr(out), rows // 128, L.ptr(tiles), H, 0, L.cur_stream()))
-    valid = torch.cat([torch.arange(128, device=dev) < n for n in plan.tile_valid])
+    valid = torch.cat([torch.arange(128, device=dev) < n for n in tv])
     x = qkv.float().view(rows, 3, H, 128)
     q, k, v = (x[:, i].transpose(0, 1)[None] for i in range(3))
     ref = F.scaled_dot_product_attention(q, k, v, attn_mask=valid[None, None, None, :])[0].transpose(0, 1).reshape(rows, -1)
@@ -41,27 +42,68 @@ def _tiny_model(dev, layers=3, heads=4):
     return qie_b200.B200QwenImageTransformer2DModel.from_state_dict(oracle.state_dict(), cfg, dev)
 
 
-@pytest.mark.parametrize("size,heads,img,txt", [(2, 4, (16, 16, 12, 10), 37), (4, 4, (32, 32, 32, 32), 300),
-                                                (2, 4, (16, 16, 16, 16), 256), (2, 6, (16, 16, 12, 10), 37)])
-def test_fused_peer_exchange_emulated_on_one_gpu(size, heads, img, txt):
-    """The fused Ulysses exchange (QKV-GEMM epilogue and attention epilogue storing straight into the consumer ranks'
-    buffers, include/qie.h qie_peers) with the ranks emulated one after the other on ONE device: same addressing code as
-    the multi-GPU path, stream order instead of qie_peer_barrier.  Must equal the single-GPU forward."""
+@pytest.mark.parametrize("size,heads,img,txt,B", [(2, 4, (16, 16, 12, 10), 37, 1), (4, 4, (32, 32, 32, 32), 300, 1),
+                                                  (2, 4, (16, 16, 16, 16), 256, 1), (2, 6, (16, 16, 12, 10), 37, 1),
+                                                  (4, 4, (16, 16, 16, 16), 427, 3), (8, 8, (32, 32, 32, 32), 256, 1)])
+def test_fused_peer_exchange_emulated_on_one_gpu(size, heads, img, txt, B):
+    """The fused Ulysses exchange (QKV-GEMM epilogue, attention epilogue and the velocity rows storing straight into the
+    consumer ranks' buffers, include/qie.h qie_peers) with the ranks emulated one after the other on ONE device: same
+    addressing code as the multi-GPU path, stream order instead of qie_peer_barrier.  Must equal the single-GPU forward
+     on every emulated rank, also for a batch of frames (configs[4]: the batch stays whole inside the group)."""
     dev = torch.device("cuda", 0)
     model = _tiny_model(dev, heads=heads)      # heads 6 over 2 ranks: a 256-column GEMM tile (2 heads) straddles two ranks
     shapes = [[(1, img[0], img[1]), (1, img[2], img[3])]]
     n0, n1 = img[0] * img[1], img[2] * img[3]
     g = torch.Generator().manual_seed(11)
-    x = torch.randn(1, n0 + n1, 64, generator=g).bfloat16().to(dev)
-    cond = (torch.randn(1, txt, 128, generator=g) * 3).bfloat16().to(dev)
-    ts = torch.tensor([0.5], device=dev)
-    single = model(x, cond, None, ts, shapes, [txt], return_dict=False)[0]
+    x = torch.randn(B, n0 + n1, 64, generator=g).bfloat16().to(dev)
+    cond = (torch.randn(B, txt, 128, generator=g) * 3).bfloat16().to(dev)
+    ts = torch.full((B,), 0.5, device=dev)
+    single = model(x, cond, None, ts, shapes, [txt] * B, return_dict=False)[0]
     multi = qie_b200.emulate_fused_ulysses(model, size, x, cond, ts, shapes)
-    err = ((multi.float() - single.float()).abs().max() / single.float().abs().max()).item()
-    assert err <= 1e-2, err
+    assert len(multi) == size
+    for m in multi:       # every rank ends up with the whole velocity
+        err = ((m.float() - single.float()).abs().max() / single.float().abs().max()).item()
+        assert err <= 1e-2, err
+    assert all(torch.equal(m, multi[0]) for m in multi)
     # and the handle is back to the plain path afterwards
-    again = model(x, cond, None, ts, shapes, [txt], return_dict=False)[0]
+    again = model(x, cond, None, ts, shapes, [txt] * B, return_dict=False)[0]
     assert torch.equal(again, single)
+
+
+def test_fused_peer_exchange_two_text_lengths_same_padding():
+    """cond / uncond prompts of different length that pad to the same shard size must not share a tile
+    list — the library derives the valid-row list from the geometry installed by qie_set_peers, and a forward whose geometry
+    differs from the installed one is refused (QIE_ESTATE) instead of masking with a stale list."""
+    dev = torch.device("cuda", 0)
+    model = _tiny_model(dev, heads=4)
+    shapes = [[(1, 16, 16), (1, 12, 10)]]
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 376, 64, generator=g).bfloat16().to(dev)
+    ts = torch.tensor([0.25], device=dev)
+    for T in (37, 22, 37):
+        cond = (torch.randn(1, T, 128, generator=g) * 3).bfloat16().to(dev)
+        single = model(x, cond, None, ts, shapes, [T], return_dict=False)[0]
+        multi = qie_b200.emulate_fused_ulysses(model, 2, x, cond, ts, shapes)[0]
+        assert ((multi.float() - single.float()).abs().max() / single.float().abs().max()).item() <= 1e-2
+    # a forward phase against peers of another geometry is an error, not a silent mis-mask
+    import ctypes as C
+    plan = qie_b200.make_shard_plan(376, 37, 2, 0)
+    bufs = [qie_b200.PeerRankBuffers(1 << 20, 1 << 20, 1 << 16) for _ in range(2)]
+    peers = qie_b200.make_peers(plan, 1, [b.gather for b in bufs], [b.ws for b in bufs], [b.vel for b in bufs], [b.flags for b in bufs])
+    lib = L.lib()
+    L.check(lib.qie_set_peers(model._handle, C.byref(peers), L.cur_stream()))
+    other = qie_b200.make_shard_plan(376, 22, 2, 0)
+    seq = L.Seq(1, other.img_rows, other.txt_rows, other.img_pad, other.txt_pad)
+    sp = L.Sp(0, 2, 376, 22, 0, 0)
+    ws = torch.empty(lib.qie_workspace_bytes(model._handle, C.byref(seq)) + 1024, dtype=torch.uint8, device=dev)
+    base = (ws.data_ptr() + 1023) // 1024 * 1024
+    rc = lib.qie_forward_phase(model._handle, 4, 0, None, None, None, None, 0, C.byref(seq), C.byref(sp), None, C.c_void_p(base),
+                               ws.numel() - 1024, -1, L.cur_stream())
+    assert rc == -6 and b"another geometry" in lib.qie_last_error()
+    assert lib.qie_set_peers(model._handle, None, None) == 0
+    torch.cuda.synchronize()
+    for b in bufs:
+        b.free()
 
 
 def _worker(rank, world, q):
@@ -92,12 +134,19 @@ def _worker(rank, world, q):
         sp = qie_b200.UlyssesTransformer(model, None)
         multi = sp(x, cond, None, ts, shapes, [37], return_dict=False)[0]
         e_sp = ((multi.float() - single.float()).abs().max() / single.float().abs().max()).item()
-        # --- the same with the fused peer-memory exchange (CUDA IPC mapped buffers, epilogue stores over NVLink)
+        # --- the same with the fused peer-memory exchange (CUDA IPC mapped buffers, epilogue stores over NVLink): eager call,
+        # graph capture on the second call, replay on the third; then another text length under the same padding (its own
+        # geometry / tile list / graph) and a batch of two frames
         fsp = qie_b200.UlyssesTransformer(model, None, fused=True)
-        fused = fsp(x, cond, None, ts, shapes, [37], return_dict=False)[0]
-        fused2 = fsp(x, cond, None, ts, shapes, [37], return_dict=False)[0]       # buffers / epochs are reused
+        rel = lambda a, b: ((a.float() - b.float()).abs().max() / b.float().abs().max()).item()
+        e_f = max(rel(fsp(x, cond, None, ts, shapes, [37], return_dict=False)[0], single) for _ in range(3))
+        single_u = model(x, unc, None, ts, shapes, [22], return_dict=False)[0]
+        e_f = max([e_f] + [rel(fsp(x, unc, None, ts, shapes, [22], return_dict=False)[0], single_u) for _ in range(3)])
+        e_f = max(e_f, rel(fsp(x, cond, None, ts, shapes, [37], return_dict=False)[0], single))     # back to the first geometry
+        x2, c2, t2 = torch.cat([x, x.flip(1)], 0), torch.cat([cond, cond.flip(1)], 0), torch.tensor([0.5, 0.25], device=dev)
+        single_b = model(x2, c2, None, t2, shapes, [37, 37], return_dict=False)[0]
+        e_f = max([e_f] + [rel(fsp(x2, c2, None, t2, shapes, [37, 37], return_dict=False)[0], single_b) for _ in range(3)])
         fsp.close()
-        e_f = max(((f.float() - single.float()).abs().max() / single.float().abs().max()).item() for f in (fused, fused2))
         e_sp = max(e_sp, e_f)
         assert qie_b200.lib().qie_peer_barrier_timeouts() == 0
         # --- CFG pair vs one GPU

@@ -59,7 +59,7 @@ def test_gemm_kernels_issue_tcgen05_from_tma_fed_shared_memory(sass):
 
 
 def test_attention_kernel_keeps_p_in_tmem_and_uses_packed_math(sass):
-    att = kernels(sass, "attn_pair3_kernel")
+    att = kernels(sass, "attn_pair_kernel")
     assert att
     for name, text in att.items():
         assert "UTCHMMA.2CTA" in text and "UTMALDG.2D.2CTA" in text, name
@@ -71,6 +71,6 @@ def test_attention_kernel_keeps_p_in_tmem_and_uses_packed_math(sass):
 def test_adaln_stream_kernel_uses_bulk_copies_and_pdl_pair_is_present(sass):
     ln = kernels(sass, "ln_mod_stream_kernel")
     assert ln and all("UBLKCP" in t for t in ln.values())
-    for needle in ("ln_mod_stream_kernel", "gemm_kernel", "attn_pair3_kernel"):
+    for needle in ("ln_mod_stream_kernel", "gemm_kernel", "attn_pair_kernel"):
         for name, text in kernels(sass, needle).items():
             assert "PREEXIT" in text and "ACQBULK" in text, name      # griddepcontrol.launch_dependents / .wait
