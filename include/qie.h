@@ -209,6 +209,8 @@ int qie_sp_tile_valid_host(int img_total, int txt_total, int size, int* out_host
 /* cudaMalloc'ed, zero-filled, IPC-exportable device buffer; handle_out receives the 64-byte cudaIpcMemHandle_t */
 int qie_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle_out64);
 int qie_peer_free(void* dev_ptr);
+/* stream-ordered device-to-device copy out of / into such a buffer (tests: the buffers have no torch tensor around them) */
+int qie_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
 /* maps a buffer exported by another process of this node (enables peer access to its device on first use) */
 int qie_peer_open(const unsigned char* handle64, void** dev_ptr);
 int qie_peer_close(void* dev_ptr);

@@ -467,3 +467,70 @@ def ref_fp8_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor
     xq = (x / s_x).to(torch.float8_e4m3fn).float()
     y = (xq @ wq.t()) * s_x * s_w.t()
     return y + bias if bias is not None else y
+
+
+def ref_llm_int8_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], threshold: float = 6.0) -> torch.Tensor:
+    """LLM.int8() as bitsandbytes' Linear8bitLt runs it with `llm_int8_threshold=6.0` — the only int8 configuration that is
+    actually present in the reference snapshot (benchmark_int8.py:72-76, test_quantized.py:40-43; the library itself is an
+    absent, un-pinned dependency, so this restates its published algorithm, Dettmers et al. 2022 / bitsandbytes
+    MatMul8bitLt): feature columns of the activation that hold any |x| > threshold are OUTLIER columns; they are taken out of
+    the int8 product (zeroed before the per-token absmax and the rounding) and multiplied in 16 bit against the dequantised
+    int8 weight columns; everything else is the vector-wise W8A8 product of ref_int8_linear."""
+    shp = x.shape
+    x2 = x.reshape(-1, shp[-1])
+    s_w = w.abs().amax(dim=1, keepdim=True).clamp_min(1e-12) / 127.0
+    wq = torch.round(w / s_w).clamp(-127, 127)
+    outlier = (x2.abs() > threshold).any(dim=0)                       # [K] feature columns
+    x_main = torch.where(outlier[None, :], torch.zeros_like(x2), x2)
+    s_x = x_main.abs().amax(dim=-1, keepdim=True).clamp_min(1e-12) / 127.0
+    xq = torch.round(x_main / s_x).clamp(-127, 127)
+    y = (xq.double() @ wq.double().t()).float() * s_x * s_w.t()
+    if outlier.any():
+        w_deq = (wq * s_w)[:, outlier]                                # the stored weights are int8: dequantised columns
+        xo = x2[:, outlier].to(torch.bfloat16).float()                # the outlier part runs in 16 bit
+        y = y + xo @ w_deq.to(torch.bfloat16).float().t()
+    y = y.reshape(*shp[:-1], w.shape[0])
+    return y + bias if bias is not None else y
+
+
+QUANT_LINEARS = {"int8": ref_int8_linear, "fp8": ref_fp8_linear, "llm_int8": ref_llm_int8_linear}
+# the four per-block linear groups the W8A8 path replaces (the matrices that hold 99.6 % of the weights and FLOPs): QKV of both
+# streams, the two attention output projections, FF up and FF down of both streams.  Embeddings, modulation and proj_out stay 16 bit.
+QUANT_TARGETS = ("attn.to_q", "attn.to_k", "attn.to_v", "attn.add_q_proj", "attn.add_k_proj", "attn.add_v_proj", "attn.to_out.0",
+                 "attn.to_add_out", "img_mlp.net.0.proj", "img_mlp.net.2", "txt_mlp.net.0.proj", "txt_mlp.net.2")
+
+
+class QuantLinearRef(nn.Module):
+    """an nn.Linear evaluated through one of the restated quantised products (same parameters, no copy)"""
+
+    def __init__(self, linear: nn.Linear, kind: str):
+        super().__init__()
+        self.linear, self.kind = linear, kind
+
+    def forward(self, x):
+        y = QUANT_LINEARS[self.kind](x.float(), self.linear.weight.float(), None if self.linear.bias is None else self.linear.bias.float())
+        return y.to(x.dtype)
+
+
+def quantized_view(model: "QwenImageTransformer2DModelRef", kind: str) -> "QwenImageTransformer2DModelRef":
+    """The int8 oracle MODEL of config 4: a shallow copy of `model` (parameters shared) whose four per-block linear groups run
+    through ref_int8_linear / ref_fp8_linear / ref_llm_int8_linear — 'the reference's own int8 path' restated at model level
+    (README.md:136-141 Int8Linear via quantize_transformer.py: replace nn.Linear of the transformer blocks)."""
+    import copy
+    assert kind in QUANT_LINEARS
+    memo = {id(p): p for p in model.parameters()}          # share every parameter tensor
+    q = copy.deepcopy(model, memo)
+    for blk in q.transformer_blocks:
+        for path in QUANT_TARGETS:
+            parent = blk
+            parts = path.split(".")
+            for name in parts[:-1]:
+                parent = parent[int(name)] if name.isdigit() else getattr(parent, name)
+            leaf = parts[-1]
+            lin = parent[int(leaf)] if leaf.isdigit() else getattr(parent, leaf)
+            wrapped = QuantLinearRef(lin, kind)
+            if leaf.isdigit():
+                parent[int(leaf)] = wrapped
+            else:
+                setattr(parent, leaf, wrapped)
+    return q.eval()

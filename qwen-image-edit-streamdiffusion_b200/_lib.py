@@ -106,6 +106,7 @@ SYMBOLS = {
     "qie_set_peers": (_i, [_vp, C.POINTER(Peers), _vp]),
     "qie_peer_alloc": (_i, [C.c_size_t, C.POINTER(_vp), C.c_char_p]),
     "qie_peer_free": (_i, [_vp]),
+    "qie_peer_copy": (_i, [_vp, _vp, C.c_size_t, _vp]),
     "qie_peer_open": (_i, [C.c_char_p, C.POINTER(_vp)]),
     "qie_peer_close": (_i, [_vp]),
     "qie_peer_barrier": (_i, [_vp, _vp]),

@@ -749,19 +749,21 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
                 orow = reinterpret_cast<__nv_bfloat16*>(__ldg(reinterpret_cast<const unsigned long long*>(p.peer_out) + srank)) +
                        ((long long)b * p.sp_rows_pad + local) * p.out_ld + (p.head_off + head) * ATT_TILE + wg * 64;
         }
-        if (store) {
+        if (q_valid) {      // warp-uniform: tcgen05.ld is a warp-collective; only the global stores are per-row predicated
 #pragma unroll 1
             for (int ch = 0; ch < 2; ++ch) {
                 uint32_t o[32];
                 tmem_ld32(tO + ch * 32, o);
                 tmem_ld_wait();
+                if (store) {
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    float v[8];
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        float v[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(o[q4 * 8 + i]) * inv;
-                    *reinterpret_cast<uint4*>(orow + ch * 32 + q4 * 8) =
-                        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(o[q4 * 8 + i]) * inv;
+                        *reinterpret_cast<uint4*>(orow + ch * 32 + q4 * 8) =
+                            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                    }
                 }
             }
         }

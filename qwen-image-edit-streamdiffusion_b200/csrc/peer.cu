@@ -140,6 +140,14 @@ extern "C" int qie_peer_free(void* dev_ptr) {
     return QIE_OK;
 }
 
+// stream-ordered device-to-device copy out of / into a qie_peer_alloc buffer (tests, debugging: the buffers are raw cudaMalloc
+// allocations without a torch tensor around them)
+extern "C" int qie_peer_copy(void* dst, const void* src, size_t bytes, void* stream) {
+    QIE_REQUIRE(dst && src, QIE_EINVAL, "qie_peer_copy: null pointer");
+    QIE_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return QIE_OK;
+}
+
 extern "C" int qie_peer_open(const unsigned char* handle64, void** dev_ptr) {
     QIE_REQUIRE(handle64 && dev_ptr, QIE_EINVAL, "qie_peer_open: null pointer");
     cudaIpcMemHandle_t h;

@@ -484,11 +484,8 @@ def emulate_fused_ulysses(transformer, size: int, hidden_states, encoder_hidden_
 
 
 def _memcpy_d2d(dst: torch.Tensor, src_ptr: int, nbytes: int) -> None:
-    """device-to-device copy from a raw libqie allocation into a torch tensor (cudart through torch's own binding)"""
-    rt = torch.cuda.cudart()
-    err = rt.cudaMemcpy(dst.data_ptr(), src_ptr, nbytes, 3)      # cudaMemcpyDeviceToDevice
-    if int(err) != 0:
-        raise L.QieError(f"cudaMemcpy failed with {err}")
+    """device-to-device copy from a raw libqie allocation into a torch tensor, ordered on the current stream"""
+    L.check(L.lib().qie_peer_copy(L.ptr(dst), C.c_void_p(src_ptr), nbytes, L.cur_stream()), "qie_peer_copy")
 
 
 # ------------------------------------------------------------------------------------------------

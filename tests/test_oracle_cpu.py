@@ -4,6 +4,7 @@ no compute call needs a GPU here)."""
 import ctypes as C
 import math
 import re
+import sys
 from pathlib import Path
 
 import numpy as np
@@ -344,3 +345,65 @@ def test_rope_table_library_vs_oracle_random_image_lists():
         assert torch.allclose(tab[seq.img_pad:seq.img_pad + T], torch.view_as_real(txt), atol=3e-6)
 
     check()
+
+
+# ------------------------------------------------------------------ the real upstream, whenever it is importable
+def _have_diffusers():
+    try:
+        import diffusers  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+_DIFF_FIXTURE = GOLD / "diffusers_tiny.npz"
+_needs_upstream = pytest.mark.skipif(not _have_diffusers() and not _DIFF_FIXTURE.exists(),
+                                     reason="diffusers is not installed and tests/golden/diffusers_tiny.npz has not been generated "
+                                            "(python tests/golden/make_golden_from_diffusers.py where diffusers exists): parity unpinned")
+
+
+def _upstream_case():
+    """(state_dict, hidden, enc, timestep, velocity, rope_img, rope_txt, tables) from a live diffusers run, else the fixture"""
+    sys.path.insert(0, str(GOLD))
+    import make_golden_from_diffusers as G
+    if _have_diffusers():
+        m = G.build_diffusers_tiny()
+        hidden, enc, ts, v, rope = G.diffusers_outputs(m)
+        sd = {k: t.clone() for k, t in m.state_dict().items()}
+        return (sd, hidden, enc, ts, v, torch.view_as_real(rope[0]), torch.view_as_real(rope[1]),
+                {k: torch.from_numpy(np.asarray(a)) for k, a in G.scheduler_tables().items()})
+    z = np.load(_DIFF_FIXTURE)
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    t = lambda k: torch.from_numpy(z[k])
+    tables = {k: t(k) for k in z.files if k.startswith(("sigmas_", "timesteps_", "step_"))}
+    return sd, t("hidden"), t("enc"), t("timestep"), t("velocity"), t("rope_img"), t("rope_txt"), tables
+
+
+@_needs_upstream
+def test_oracle_matches_diffusers_transformer_on_identical_weights():
+    """The oracle loads the diffusers state_dict unchanged (same parameter names) and must reproduce the upstream
+    velocity and RoPE tables in fp32 — the check that turns 'parity unpinned' into pinned."""
+    sd, hidden, enc, ts, v, rope_img, rope_txt, _ = _upstream_case()
+    m = R.QwenImageTransformer2DModelRef(R.TINY_CONFIG).eval()
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not [k for k in missing if "pos_embed" not in k] and not [k for k in unexpected if "pos_embed" not in k], (missing, unexpected)
+    shapes = [[(1, 16, 16), (1, 16, 16)]]
+    with torch.no_grad():
+        got = m(hidden, enc, None, ts, shapes, [enc.shape[1]])[0]
+        fi, ft = m.pos_embed(shapes, [enc.shape[1]])
+    assert torch.allclose(got, v, atol=2e-5, rtol=1e-4), float((got - v).abs().max())
+    assert torch.allclose(torch.view_as_real(fi), rope_img, atol=1e-6) and torch.allclose(torch.view_as_real(ft), rope_txt, atol=1e-6)
+
+
+@_needs_upstream
+def test_oracle_matches_diffusers_scheduler():
+    *_, tables = _upstream_case()
+    for n in (2, 4, 8):
+        for seq in (4096, 1024, 256):
+            ref = R.ref_flowmatch_sigmas(n, seq)
+            assert np.allclose(ref, tables[f"sigmas_n{n}_s{seq}"].numpy(), atol=2e-6), (n, seq)
+            assert np.allclose(ref[:-1] * 1000, tables[f"timesteps_n{n}_s{seq}"].numpy(), atol=2e-3), (n, seq)
+            assert np.allclose(qie_b200.flowmatch_sigmas(n, seq), tables[f"sigmas_n{n}_s{seq}"].numpy(), atol=2e-6)
+    sig = R.ref_flowmatch_sigmas(4, 4096)
+    out = R.ref_euler_step(tables["step_x"], tables["step_v"], float(sig[0]), float(sig[1]))
+    assert torch.allclose(out, tables["step_out"], atol=1e-6)
