@@ -196,7 +196,8 @@ typedef struct qie_peers {
     void* vel[8];            /* rank s's velocity buffer bf16 [batch][img_total][out_dim]: every rank receives all rows */
     void* flags[8];          /* rank s's barrier words: 16 zero-initialised uint32 ([0..7] arrivals, [8] its barrier count) */
 } qie_peers;
-/* installs (or with NULL removes) the peer tables of ONE geometry (batch, img_total, txt_total); call it again whenever the
+/* installs (or with NULL removes) the peer tables of ONE geometry (batch, img_total, txt_total), used by the sequence-parallel
+ * entry points (qie_forward_phase with `sp`, qie_forward_sp); a plain qie_forward on the same handle ignores them.  Call it again whenever the
  * geometry of the next forward differs (cheap: host-side, the tile list of each geometry is built once and kept).  A forward whose
  * seq / sp do not match the installed geometry returns QIE_ESTATE.  qie_set_peers(h, NULL, ...) returns QIE_ECUDA (once) if a
  * barrier of the dissolved group had timed out. */

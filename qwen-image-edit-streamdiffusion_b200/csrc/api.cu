@@ -453,7 +453,7 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
     if (int rc_sticky = peer_sticky_error()) return rc_sticky;   // a peer barrier of an earlier launch timed out
     if (phases & QIE_PHASE_BEGIN)
         QIE_REQUIRE(hidden && enc && timestep && img_shapes_host, QIE_EINVAL, "qie_forward: null input pointer");
-    if (phases & QIE_PHASE_END) QIE_REQUIRE(out || h->has_peers, QIE_EINVAL, "qie_forward: null output pointer");
+    if (phases & QIE_PHASE_END) QIE_REQUIRE(out || (h->has_peers && sp), QIE_EINVAL, "qie_forward: null output pointer");
     QIE_REQUIRE(h->has_weights, QIE_ESTATE, "qie_forward: weights not set");
     QIE_REQUIRE(seq->batch >= 1 && seq->batch <= 8, QIE_ESHAPE, "qie_forward: batch must be 1..8");
     qie_seq chk;
@@ -466,6 +466,9 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
                 ws.total);
     QIE_REQUIRE(((uintptr_t)workspace & 1023) == 0, QIE_EINVAL, "qie_forward: workspace must be 1 KB aligned");
     cudaStream_t st = (cudaStream_t)stream;
+    // the installed peer tables apply to sequence-parallel calls only (sp given); a plain qie_forward on the same handle runs
+    // the single-GPU path untouched
+    const bool use_peers = h->has_peers && sp != nullptr;
     const int B = seq->batch, D = h->D, L = h->cfg.num_layers;
     const int nb = n_blocks < 0 || n_blocks > L ? L : n_blocks;
     const int rpb = seq->img_pad + seq->txt_pad;
@@ -492,7 +495,7 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
         return qie_gemm(&g, seq, st);
     };
     auto run_attn = [&]() -> int {
-        if (h->has_peers) {
+        if (use_peers) {
             // my head group over the gathered sequence of every rank; the epilogue stores each token's output into the
             // attention buffer of the rank that owns the token
             const qie_peers& pr = h->peers;
@@ -505,9 +508,9 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
         ProfScope ps(h, st, 1, 4.0 * S * S * 128.0 * h->cfg.num_heads * B);
         return qie_attn_fwd(qkv, attn, seq, h->cfg.num_heads, h->attn_variant, st);
     };
-    if (h->has_peers && (phases & (QIE_PHASE_QKV | QIE_PHASE_ATTN | QIE_PHASE_END)))
+    if (use_peers && (phases & (QIE_PHASE_QKV | QIE_PHASE_ATTN | QIE_PHASE_END)))
         QIE_REQUIRE(B == h->peers.batch && h->peers.img_pad == seq->img_pad && h->peers.txt_pad == seq->txt_pad && h->fuse_qk &&
-                        sp && sp->size == h->peers.size && sp->rank == h->peers.rank && sp->img_total == h->peers.img_total &&
+                        sp->size == h->peers.size && sp->rank == h->peers.rank && sp->img_total == h->peers.img_total &&
                         sp->txt_total == h->peers.txt_total,
                     QIE_ESTATE, "qie_forward_phase: the installed peers describe another geometry (batch %d, shard %d+%d rows, "
                     "%d+%d tokens): call qie_set_peers for this one", h->peers.batch, h->peers.img_pad, h->peers.txt_pad,
@@ -643,7 +646,7 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
                 g.w_scale[s] = bw.qkv_ws[s];
             }
             g.a = fp8 ? xm8 : xm; g.fp8 = fp8; g.a_scale = xscale;
-            if (h->has_peers) {   // epilogue scatters q|k|v of head group g into rank g's gathered buffer (peer stores)
+            if (use_peers) {   // epilogue scatters q|k|v of head group g into rank g's gathered buffer (peer stores)
                 const qie_peers& pr = h->peers;
                 g.peer_out = h->d_peer_tab; g.sp_rank = pr.rank; g.sp_size = pr.size;
                 g.sp_gathered_rows = pr.size * pr.img_pad + (pr.txt_total + 127) / 128 * 128;
@@ -716,7 +719,7 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
         g.epilogue = QIE_EPI_BF16;
         if ((rc = run_gemm(g))) return rc;
     }
-    if (h->has_peers) {
+    if (use_peers) {
         // sequence parallel: every rank of the group needs the whole velocity for the (replicated) Euler update — my rows go
         // straight into every rank's velocity buffer (NVLink peer stores); the caller's barrier makes them visible
         if ((rc = peer_bcast_rows(outp, h->d_peer_tab + 16, &h->peers, seq->img_rows, sp->img_offset, h->cfg.out_dim, st)))
