@@ -4,7 +4,8 @@
 //
 // Two kernels: attn_pair_kernel (default: a CTA pair per 256 query rows, cta_group::2 MMAs, 256-wide KV tiles, P in TMEM) and
 // attn_kernel (single-CTA fallback, variant bit 0x8; also the A/B yard-stick).  The kernels that lost the round-1 A/B runs
-// (first pair kernels, persistent / speculative / traced builds) live in the git history (commit 550b982 and before).
+// (first pair kernels, persistent / speculative / traced builds; the round-2 ping-pong kernel with two Q super-tiles per pair)
+// live in the git history (commits 550b982 and before; "Ping-pong CTA-pair attention kernel"), measurements in profiles/.
 //
 // attn_kernel: one CTA = one (batch, head) x 256 query rows = two 128-row Q tiles that ping-pong on the tensor pipe:
 //   warp 0 / lane 0 : TMA producer (Q tiles once; K_j, V_j tiles through a ring, 128 rows x 128 dims each)
@@ -795,374 +796,6 @@ static int launch_attn_pair(const CUtensorMap& tm128, const AttnDev& p, dim3 gri
 }
 
 
-// =====================================================================================================================
-// Ping-pong CTA-pair attention ("pp", round 2).  The round-1 trace of attn_pair_kernel showed its period (2950 cycles per 256 KV
-// rows) set by the SUM of a serial hand-off: one Q tile per CTA means S(j+1) -> softmax -> P -> PV is one chain, the two
-// softmax warpgroups work on the same tile in lock-step (both on TMEM loads, both on the max exchange, both on the MUFU) and the
-// tensor pipe idles while they do.  This kernel gives every CTA pair TWO independent Q super-tiles (A and B, 256 rows each: 128
-// per CTA) that share the K/V stream:
-//   S_c = Q_c K_j^T : 256 x 128 x 128 SS MMA (each CTA stages half of K_j: 64 kv rows)          96 B/clk of operands per SM
-//   O_c += P_c V_j  : 256 x 128 x 128 TS MMA, P_c (bf16) written by the softmax warps over the first 64 columns of S_c in TMEM,
-//                     each CTA stages its 64 head dims of V_j (MN-major)                         32 B/clk
-// TMEM: S_A [0,128) | S_B [128,256) | O_A [256,384) | O_B [384,512).  Softmax warpgroup c owns chain c outright: a thread holds the
-// whole 128-score row of its query for this KV tile, so there is no cross-warpgroup max exchange, no shared-memory traffic and no
-// named barrier in the loop; the row sum is thread-local.  The tensor pipe executes in issue order
-//   S_A(0) S_B(0) | PV_A(0) S_A(1) PV_B(0) S_B(1) | PV_A(1) S_A(2) PV_B(1) S_B(2) | ...
-// so while warpgroup A is in its exponentials the pipe runs chain B's MMAs and vice versa (the chains settle half a period
-// apart), P_c(j) is consumed by PV_c(j) before S_c(j+1) overwrites the columns (in-order pipe), and S_c(j) complete implies
-// PV_c(j-1) complete, so warpgroup c may rescale O_c (lazily, threshold 8 in log2 units) without another barrier.
-// Work unit = 512 query rows of one (batch, head) per CTA pair.
-// =====================================================================================================================
-constexpr int PP_KSTAGES = 4, PP_VSTAGES = 4;
-constexpr int PP_THREADS = 384;               // warps 0-3 softmax A, 4-7 softmax B, warp 8 TMA, warp 9 MMA issuer, 10-11 idle
-constexpr int PP_STAGE_BYTES = 16 * 1024;     // K: my 64 kv rows x 128 dims (two 64-dim halves of 8 KB); V: 128 kv rows x my 64 dims
-constexpr int PP_SMEM = 2 * ATT_TILE_BYTES + (PP_KSTAGES + PP_VSTAGES) * PP_STAGE_BYTES + 512 + 1024;
-
-template <int POLY>
-__global__ void __launch_bounds__(PP_THREADS, 1)
-attn_pp_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm64, const AttnDev p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                                       // [2 chains][2 d-halves][128 rows x 128 B]
-    uint8_t* sK = smem + 2 * ATT_TILE_BYTES;                  // [K stages][2 d-halves][64 kv rows x 128 B]
-    uint8_t* sV = sK + PP_KSTAGES * PP_STAGE_BYTES;           // [V stages][128 kv rows x 128 B (my 64 dims)]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + PP_VSTAGES * PP_STAGE_BYTES);
-    uint64_t* q_full = bars;                       // leader
-    uint64_t* k_full = bars + 1;                   // [K stages] leader
-    uint64_t* k_empty = k_full + PP_KSTAGES;       // both
-    uint64_t* v_full = k_empty + PP_KSTAGES;       // [V stages] leader
-    uint64_t* v_empty = v_full + PP_VSTAGES;       // both
-    uint64_t* s_full = v_empty + PP_VSTAGES;       // [2 chains] both
-    uint64_t* p_full = s_full + 2;                 // [2 chains] leader, 8 warp arrivals (4 warps x 2 CTAs)
-    uint64_t* o_done = p_full + 2;                 // [2 chains] both: the last PV of the chain has retired
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
-
-    const int warp = threadIdx.x >> 5, lane = lane_id();
-    const int cta_rank = (int)cluster_ctarank();
-    const int rpb = p.seq.img_pad + p.seq.txt_pad;
-    const int n_kv = rpb / ATT_TILE;               // 128-row KV tiles
-    const int head = blockIdx.y, b = blockIdx.z;
-    const int unit_row0 = (blockIdx.x >> 1) * 4 * ATT_TILE;          // 512 query rows per pair
-    const bool chainB = unit_row0 + 2 * ATT_TILE < rpb;              // pair-uniform: the second super-tile exists
-    const int D = p.H * ATT_TILE;
-    const int colQ = head * ATT_TILE, colK = D + head * ATT_TILE, colV = 2 * D + head * ATT_TILE;
-    const int row_base = b * rpb;
-    griddep_launch_dependents();
-
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tm128);
-        tma_prefetch_desc(&tm64);
-        mbar_init(q_full, 1);
-        for (int i = 0; i < PP_KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
-        for (int i = 0; i < PP_VSTAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-        for (int c = 0; c < 2; ++c) { mbar_init(&s_full[c], 1); mbar_init(&p_full[c], 8); mbar_init(&o_done[c], 1); }
-        fence_barrier_init();
-    }
-    if (warp == 9) tmem_alloc_cg2<512>(tmem_slot);
-    tc_fence_before();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t COL_S = 0, COL_O = 256;       // + 128 * chain
-    griddep_wait();      // the prologue above overlapped the QKV GEMM's last wave; q|k|v are visible from here on
-
-    if (warp >= 8) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-      if (warp == 8) {
-        if (lane == 0) {
-            // ================= TMA producer =================
-            const int nq = chainB ? 2 : 1;
-            if (cta_rank == 0) mbar_expect_tx(q_full, 2 * nq * ATT_TILE_BYTES);
-            for (int c = 0; c < nq; ++c) {
-                int qr = unit_row0 + c * 2 * ATT_TILE + cta_rank * ATT_TILE;
-                if (qr >= rpb) qr = 0;                       // odd 128-row tile count: the peer half of the last super-tile
-                for (int hf = 0; hf < 2; ++hf)
-                    tma_load_2d_cg2(sQ + c * ATT_TILE_BYTES + hf * ATT_HALF_BYTES, &tm128, colQ + hf * 64, row_base + qr,
-                                    leader_smem_u32(q_full));
-            }
-            int ks = 0, vs = 0;
-            uint32_t kph = 0, vph = 0;
-            auto load_k = [&](int j) {       // my 64 kv rows (half of the 128-row tile) x 128 head dims, two 64-dim halves
-                mbar_wait(&k_empty[ks], kph ^ 1);
-                if (cta_rank == 0) mbar_expect_tx(&k_full[ks], 2 * PP_STAGE_BYTES);
-                const uint32_t bar = leader_smem_u32(&k_full[ks]);
-                for (int hf = 0; hf < 2; ++hf)
-                    tma_load_2d_cg2(sK + ks * PP_STAGE_BYTES + hf * (PP_STAGE_BYTES / 2), &tm64, colK + hf * 64,
-                                    row_base + j * ATT_TILE + cta_rank * 64, bar);
-                if (++ks == PP_KSTAGES) { ks = 0; kph ^= 1; }
-            };
-            auto load_v = [&](int j) {       // 128 kv rows x my 64 head dims
-                mbar_wait(&v_empty[vs], vph ^ 1);
-                if (cta_rank == 0) mbar_expect_tx(&v_full[vs], 2 * PP_STAGE_BYTES);
-                tma_load_2d_cg2(sV + vs * PP_STAGE_BYTES, &tm128, colV + cta_rank * 64, row_base + j * ATT_TILE,
-                                leader_smem_u32(&v_full[vs]));
-                if (++vs == PP_VSTAGES) { vs = 0; vph ^= 1; }
-            };
-            load_k(0);
-            for (int j = 0; j < n_kv; ++j) {
-                if (j + 1 < n_kv) load_k(j + 1);
-                load_v(j);
-            }
-        }
-      } else if (warp == 9) {
-        // The issuer has the highest warp id of its scheduler: the arbiter serves it first.
-        if (lane == 0 && cta_rank == 0) {
-            // ================= MMA issuer (leader) =================
-            constexpr uint32_t IDESC_S = umma_idesc_bf16(256, 128, false);
-            constexpr uint32_t IDESC_O = umma_idesc_bf16(256, 128, true);   // B = V is MN-major
-            int ks = 0, vs = 0;
-            uint32_t kph = 0, vph = 0;
-            const uint64_t dqA = umma_desc_kmajor_sw128(smem_u32(sQ)), dqB = umma_desc_kmajor_sw128(smem_u32(sQ + ATT_TILE_BYTES));
-            auto issue_S = [&](int c, uint64_t dk) {
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {   // 8 x 16 head dims: + 32 B inside a swizzled row; second d-half 16 KB (Q) / 8 KB (K) on
-                    const uint64_t qoff = (uint64_t)(((s >> 2) * ATT_HALF_BYTES + (s & 3) * 32) >> 4);
-                    const uint64_t koff = (uint64_t)(((s >> 2) * (PP_STAGE_BYTES / 2) + (s & 3) * 32) >> 4);
-                    umma_ss_f16_cg2(tmem_base + COL_S + c * 128, (c ? dqB : dqA) + qoff, dk + koff, IDESC_S, s ? 1u : 0u);
-                }
-                umma_commit_cg2(&s_full[c], 3);
-            };
-            auto issue_PV = [&](int c, int j, uint64_t dv) {
-#pragma unroll
-                for (int s = 0; s < 8; ++s)     // 8 x 16 kv rows (2 KB of V each); A = P_c (8 packed columns per step)
-                    umma_ts_f16_cg2(tmem_base + COL_O + c * 128, tmem_base + COL_S + c * 128 + s * 8, dv + (uint64_t)(s * 128),
-                                    IDESC_O, (j == 0 && s == 0) ? 0u : 1u);
-                if (j == n_kv - 1) umma_commit_cg2(&o_done[c], 3);
-            };
-            mbar_wait(q_full, 0);
-            mbar_wait(&k_full[0], 0);
-            tc_fence_after();
-            {
-                const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(sK));
-                issue_S(0, dk);
-                if (chainB) issue_S(1, dk);
-                umma_commit_cg2(&k_empty[0], 3);
-                ks = 1;
-            }
-            for (int j = 0; j < n_kv; ++j) {
-                const bool more = j + 1 < n_kv;
-                uint64_t dk = 0;
-                mbar_wait(&v_full[vs], vph);
-                const uint64_t dv = umma_desc_mnmajor_sw128(smem_u32(sV + vs * PP_STAGE_BYTES), ATT_HALF_BYTES, 1024);
-                mbar_wait(&p_full[0], j & 1);                // P_A(j) is in TMEM in both CTAs, O_A rescaled
-                tc_fence_after();
-                issue_PV(0, j, dv);
-                if (more) {
-                    mbar_wait(&k_full[ks], kph);
-                    tc_fence_after();
-                    dk = umma_desc_kmajor_sw128(smem_u32(sK + ks * PP_STAGE_BYTES));
-                    issue_S(0, dk);
-                }
-                if (chainB) {
-                    mbar_wait(&p_full[1], j & 1);
-                    tc_fence_after();
-                    issue_PV(1, j, dv);
-                    if (more) issue_S(1, dk);
-                }
-                umma_commit_cg2(&v_empty[vs], 3);
-                if (++vs == PP_VSTAGES) { vs = 0; vph ^= 1; }
-                if (more) {
-                    umma_commit_cg2(&k_empty[ks], 3);
-                    if (++ks == PP_KSTAGES) { ks = 0; kph ^= 1; }
-                }
-            }
-        }
-      }
-    } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-        // ================= softmax: warpgroup c (warps 4c .. 4c+3) owns chain c; thread = one query row =================
-        const int c = warp >> 2;
-        const int quad = warp & 3;                   // TMEM lane quadrant a warp may touch = warp id % 4
-        const int r = quad * 32 + lane;
-        if (c == 0 || chainB) {
-            const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-            const uint32_t tS = tmem_base + lane_addr + COL_S + c * 128;      // scores in, P (bf16 pairs, 64 columns) out
-            const uint32_t tO = tmem_base + lane_addr + COL_O + c * 128;
-            const float sc = p.scale_log2;
-            const uint64_t c2 = pk2(sc, sc);
-            float m_ref = -INFINITY;
-            uint64_t l2 = pk2(0.f, 0.f);
-            auto valid_rows = [&](int t128) -> int {
-                return t128 < n_kv ? (p.tile_valid ? __ldg(p.tile_valid + t128) : kv_valid_rows(p.seq, t128)) : 0;
-            };
-            int nv_next = valid_rows(0);
-            for (int j = 0; j < n_kv; ++j) {
-                const int nv = nv_next;
-                mbar_wait(&s_full[c], j & 1);
-                tc_fence_after();
-                uint32_t s[128];
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t(&dst)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[ch * 32]);
-                    tmem_ld32(tS + ch * 32, dst);
-                }
-                nv_next = valid_rows(j + 1);                 // its latency hides under the TMEM load
-                tmem_ld_wait();
-                // ---- row max of the whole tile (thread-local) ----
-                float m0 = -INFINITY, m1 = -INFINITY;
-                if (nv == ATT_TILE) {
-                    float m2 = -INFINITY, m3 = -INFINITY;     // four chains of 16
-#pragma unroll
-                    for (int i = 0; i < 128; i += 8) {
-                        m0 = max3(m0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-                        m1 = max3(m1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-                        m2 = max3(m2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
-                        m3 = max3(m3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
-                    }
-                    m0 = fmaxf(m0, m2);
-                    m1 = fmaxf(m1, m3);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 128; ++i)
-                        if (i < nv) m0 = fmaxf(m0, __uint_as_float(s[i]));
-                }
-                const float mx = fmaxf(m0, m1) * sc;
-                // lazy rescale: the reference only moves when the row max grew by more than 8 (log2 units)
-                float alpha = 1.f;
-                const bool grow = mx > m_ref + 8.0f;
-                if (grow) {
-                    alpha = fast_exp2(m_ref - mx);
-                    m_ref = mx;
-                    l2 = fma2(l2, pk2(alpha, alpha), pk2(0.f, 0.f));
-                }
-                const uint64_t nm2 = pk2(-m_ref, -m_ref);
-                // ---- exponentials in place: s[i/2] <- bf16x2(p_i, p_i+1) ----
-                if (nv == ATT_TILE) {
-#pragma unroll
-                    for (int i = 0; i < 128; i += 2) {
-                        const uint64_t X = fma2(pk2u(s[i], s[i + 1]), c2, nm2);
-                        float x0, x1, e0, e1;
-                        upk2(X, x0, x1);
-                        if (((i >> 1) & 7) < POLY) {
-                            // FMA-pipe exp2: x = n + f, 2^f by a degree-3 polynomial, 2^n via the exponent bits
-                            const uint64_t Xc = pk2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
-                            const uint64_t T = add2(Xc, pk2(12582912.f, 12582912.f));
-                            const uint64_t N = add2(T, pk2(-12582912.f, -12582912.f));
-                            const uint64_t Fr = fma2(N, pk2(-1.f, -1.f), Xc);
-                            uint64_t P = fma2(Fr, pk2(0.0551716574f, 0.0551716574f), pk2(0.2426111400f, 0.2426111400f));
-                            P = fma2(P, Fr, pk2(0.6932609677f, 0.6932609677f));
-                            P = fma2(P, Fr, pk2(0.9999280572f, 0.9999280572f));
-                            float t0, t1, p0, p1;
-                            upk2(T, t0, t1);
-                            upk2(P, p0, p1);
-                            e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-                            e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
-                        } else {
-                            e0 = fast_exp2(x0);
-                            e1 = fast_exp2(x1);
-                        }
-                        l2 = add2(l2, pk2(e0, e1));
-                        s[i >> 1] = pack_bf16(e0, e1);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 128; i += 2) {
-                        float x0, x1;
-                        upk2(fma2(pk2u(s[i], s[i + 1]), c2, nm2), x0, x1);
-                        const float e0 = i < nv ? fast_exp2(x0) : 0.f, e1 = i + 1 < nv ? fast_exp2(x1) : 0.f;
-                        l2 = add2(l2, pk2(e0, e1));
-                        s[i >> 1] = pack_bf16(e0, e1);
-                    }
-                }
-                // S_c(j) complete implies PV_c(j-1) complete (in-order pipe), so O_c is mine until I raise p_full: rescale it now
-                // that the score row has shrunk to 64 packed registers
-                if (j > 0 && __any_sync(0xffffffffu, grow)) {
-#pragma unroll 1
-                    for (int ch = 0; ch < 4; ++ch) {
-                        uint32_t o[32];
-                        tmem_ld32(tO + ch * 32, o);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st32(tO + ch * 32, o);
-                    }
-                }
-                {
-                    uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
-                    uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
-                    tmem_st32(tS, lo);
-                    tmem_st32(tS + 32, hi);
-                    tmem_st_wait();
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(leader_smem_u32(&p_full[c]));
-            }
-            // ---- epilogue: O_c / l -> bf16 -> global (thread = one query row, 128 head dims) ----
-            float l_lo, l_hi;
-            upk2(l2, l_lo, l_hi);
-            const float inv = 1.f / (l_lo + l_hi);
-            mbar_wait(&o_done[c], 0);
-            tc_fence_after();
-            const int q_row0 = unit_row0 + c * 2 * ATT_TILE + cta_rank * ATT_TILE;
-            const bool q_valid = q_row0 < rpb;
-            bool store = q_valid;
-            __nv_bfloat16* orow = p.out + (long long)(row_base + q_row0 + r) * D + head * ATT_TILE;
-            if (p.peer_out && q_valid) {
-                // gathered sequence-parallel layout: this row's token is owned by rank `srank` (see AttnDev); NVLink peer store
-                const int qg = q_row0 + r;
-                int srank, local;
-                if (qg < p.sp_img_region) {
-                    srank = qg / p.sp_img_pad;
-                    local = qg - srank * p.sp_img_pad;
-                } else {
-                    const int t = qg - p.sp_img_region, cut = p.sp_txt_rem * (p.sp_txt_base + 1);
-                    store = t < p.sp_txt_total;               // pad rows of the text region belong to nobody
-                    int first;
-                    if (t < cut) { srank = t / (p.sp_txt_base + 1); first = srank * (p.sp_txt_base + 1); }
-                    else { srank = p.sp_txt_rem + (t - cut) / p.sp_txt_base; first = cut + (srank - p.sp_txt_rem) * p.sp_txt_base; }
-                    local = p.sp_img_pad + (t - first);
-                }
-                if (store)
-                    orow = reinterpret_cast<__nv_bfloat16*>(__ldg(reinterpret_cast<const unsigned long long*>(p.peer_out) + srank)) +
-                           ((long long)b * p.sp_rows_pad + local) * p.out_ld + (p.head_off + head) * ATT_TILE;
-            }
-            if (q_valid) {      // warp-uniform: tcgen05.ld is a warp-collective; only the global stores are per-row predicated
-#pragma unroll 1
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t o[32];
-                    tmem_ld32(tO + ch * 32, o);
-                    tmem_ld_wait();
-                    if (store) {
-#pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) {
-                            float v[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(o[q4 * 8 + i]) * inv;
-                            *reinterpret_cast<uint4*>(orow + ch * 32 + q4 * 8) =
-                                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                        }
-                    }
-                }
-            }
-        }
-    }
-
-    __syncwarp();
-    tc_fence_before();
-    cluster_sync_all();
-    if (warp == 9) {
-        tc_fence_after();
-        tmem_dealloc_cg2<512>(tmem_base);
-    }
-}
-
-template <int POLY>
-static int launch_attn_pp(const CUtensorMap& tm128, const CUtensorMap& tm64, const AttnDev& p, dim3 grid, cudaStream_t st) {
-    QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(attn_pp_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM));
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(PP_THREADS);
-    cfg.dynamicSmemBytes = PP_SMEM;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[2];
-    cfg.attrs = attr;
-    cfg.numAttrs = launch_attrs(attr, 2);
-    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_pp_kernel<POLY>, tm128, tm64, p));
-    QIE_LAUNCH_OK("attn_pp_kernel");
-    return QIE_OK;
-}
-
 }  // namespace qie
 
 using namespace qie;
@@ -1213,8 +846,8 @@ int attn_fwd_peers(const void* qkv_gathered, void* const* peer_out_dev, const qi
 static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int* tile_valid, int num_heads, int variant,
                        void* stream, const AttnScatter* sc) {
     if (variant == 0) variant = 0x20;
-    const int poly = (variant >> 4) & 15, single = (variant >> 3) & 1, pp = (variant >> 2) & 1;
-    QIE_REQUIRE((variant & ~0x1FC) == 0 && (poly == 0 || poly == 2 || poly == 3 || poly == 4) && !(pp && single), QIE_EINVAL,
+    const int poly = (variant >> 4) & 15, single = (variant >> 3) & 1;
+    QIE_REQUIRE((variant & ~0x1F8) == 0 && (poly == 0 || poly == 2 || poly == 3 || poly == 4), QIE_EINVAL,
                 "qie_attn_fwd: bad variant 0x%x", variant);
     const int rpb = seq->img_pad + seq->txt_pad;
     const int D = num_heads * 128;
@@ -1253,18 +886,6 @@ static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int
             case 2: return launch_attn<true, 2>(tm, p, grid, st);
             case 3: return launch_attn<true, 3>(tm, p, grid, st);
             case 4: return launch_attn<true, 4>(tm, p, grid, st);
-        }
-    }
-    if (pp) {        // ping-pong kernel: a cluster of two CTAs per 512 query rows
-        CUtensorMap tm64;
-        rc = make_tmap_2d(&tm64, qkv, (uint64_t)seq->batch * rpb, (uint64_t)3 * D, (uint64_t)3 * D * 2, 64, 64, 2);
-        if (rc) return rc;
-        grid.x = 2 * ((rpb + 511) / 512);
-        switch (poly) {
-            case 0: return launch_attn_pp<0>(tm, tm64, p, grid, st);
-            case 2: return launch_attn_pp<2>(tm, tm64, p, grid, st);
-            case 3: return launch_attn_pp<3>(tm, tm64, p, grid, st);
-            case 4: return launch_attn_pp<4>(tm, tm64, p, grid, st);
         }
     }
     grid.x *= 2;     // a cluster of two CTAs per 256 query rows
