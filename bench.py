@@ -281,11 +281,12 @@ def strong_leg(args, model, dev, world, rank, timed):
     cond = (torch.randn(1, T_TXT, cfg.joint_attention_dim, generator=g, device=dev) * 3).bfloat16()
     unc = (torch.randn(1, T_TXT, cfg.joint_attention_dim, generator=g, device=dev) * 3).bfloat16()
 
-    def single():
-        return qie_b200.run_denoise(model, lat, img_lat, cond, IMG_SHAPES, STEPS_PER_IMAGE, unc, 4.0)
+    def single(collect=None):
+        return qie_b200.run_denoise(model, lat, img_lat, cond, IMG_SHAPES, STEPS_PER_IMAGE, unc, 4.0, collect=collect)
 
-    for _ in range(2):
-        ref = single()
+    ref_v = []
+    ref = single(ref_v)
+    single()
     n1_ms = timed(single, max(2, args.steps // 2)) / max(2, args.steps // 2)      # max over ranks of the same single-GPU frame
     rec = {"mode": mode, "frame": f"true-CFG 4.0, {STEPS_PER_IMAGE} steps = {2 * STEPS_PER_IMAGE} forwards of {N_IMG_TOK}+{T_TXT} tokens",
            "n1_ms_per_frame": n1_ms, "n1_how": "the same frame on ONE GPU of this box (every rank runs it alone; max over ranks)"}
@@ -298,16 +299,22 @@ def strong_leg(args, model, dev, world, rank, timed):
     if layout.sp_size > 1:
         runner = qie_b200.UlyssesTransformer(model, layout.sp_group, fused=True)
 
-    def frame():
-        return qie_b200.run_denoise_parallel(runner, layout, lat, img_lat, cond, unc, IMG_SHAPES, STEPS_PER_IMAGE, 4.0)
+    def frame(collect=None):
+        return qie_b200.run_denoise_parallel(runner, layout, lat, img_lat, cond, unc, IMG_SHAPES, STEPS_PER_IMAGE, 4.0, collect=collect)
 
     for _ in range(3):                  # eager, graph capture, first replay
         got = frame()
     ms = timed(frame, args.steps) / args.steps
-    got = frame()
+    got_v = []
+    got = frame(got_v)
     torch.cuda.synchronize()
-    err = ((got.float() - ref.float()).abs().max() / ref.float().abs().max()).item()
-    errs = torch.tensor([err], device=dev)
+    rel = lambda a, b: ((a.float() - b.float()).abs().max() / b.float().abs().max()).item()
+    # the forwards of step 0 see identical inputs on both sides: velocity of the cond and of the uncond forward (max-rel, as the
+    # north star states the tolerance); then the frame's final latents (after the CFG combine, which amplifies differences ~4x)
+    err = max(rel(got_v[0][0], ref_v[0][0]), rel(got_v[0][1], ref_v[0][1]))
+    err_final = rel(got, ref)
+    cos = torch.nn.functional.cosine_similarity(got.float().flatten(), ref.float().flatten(), dim=0).item()
+    errs = torch.tensor([err, err_final, -cos], device=dev)
     dist.all_reduce(errs, op=dist.ReduceOp.MAX)
     timeouts = torch.tensor([qie_b200.lib().qie_peer_barrier_timeouts()], device=dev)
     dist.all_reduce(timeouts, op=dist.ReduceOp.MAX)
@@ -339,13 +346,16 @@ def strong_leg(args, model, dev, world, rank, timed):
     if branches == 2:
         xbytes += STEPS_PER_IMAGE * N_NOISE * 64 * 2         # the velocity all-gather of the CFG pair (NCCL, 512 KB per step)
     rec.update({"ms_per_frame": ms, "efficiency_vs_n1": n1_ms / (world * ms), "speedup_vs_n1": n1_ms / ms,
-                "parity_err": float(errs.item()), "parity_tolerance": 0.0 if sp == 1 else 1e-2,
+                "parity_err": float(errs[0].item()), "parity_tolerance": 0.0 if sp == 1 else 1e-2,
+                "parity_what": "max-rel-err of the step-0 velocities (cond and uncond forward) against the single-GPU forward on the same inputs",
+                "final_latent_max_rel_err": float(errs[1].item()), "final_latent_cosine": float(-errs[2].item()),
                 "barrier_timeouts": int(timeouts.item()), "exchange_bytes": int(xbytes),
                 "exchange_bytes_note": "bytes ONE rank stores into other GPUs' memory per frame (epilogue peer stores over NVLink "
                                        "+ the CFG-pair velocity all-gather)", "profile": prof})
     if hasattr(runner, "close"):
         runner.close()
-    bad = rec["parity_err"] > rec["parity_tolerance"] or rec["barrier_timeouts"] != 0 or not (rec["parity_err"] == rec["parity_err"])
+    bad = (rec["parity_err"] > rec["parity_tolerance"] or rec["barrier_timeouts"] != 0 or not (rec["parity_err"] == rec["parity_err"])
+           or rec["final_latent_cosine"] < 0.999 or (sp == 1 and rec["final_latent_max_rel_err"] != 0.0))
     if bad:
         rec["failed"] = "parity or barrier check failed"
     return rec

@@ -195,6 +195,9 @@ typedef struct qie_peers {
     void* attn_out[8];       /* rank s's attention-output buffer = its workspace + qie_workspace_offset(..., 1) */
     void* vel[8];            /* rank s's velocity buffer bf16 [batch][img_total][out_dim]: every rank receives all rows */
     void* flags[8];          /* rank s's barrier words: 16 zero-initialised uint32 ([0..7] arrivals, [8] its barrier count) */
+    void* mod[8];            /* rank s's modulation table fp32 [batch][num_layers*12*D]: in the BEGIN phase every rank computes 1/size
+                              * of the rows (the 13.6 GB modulation-weight stream does not shrink with the token shard) and stores them
+                              * into the other ranks' tables; a barrier must separate BEGIN from the first QKV phase */
 } qie_peers;
 /* installs (or with NULL removes) the peer tables of ONE geometry (batch, img_total, txt_total), used by the sequence-parallel
  * entry points (qie_forward_phase with `sp`, qie_forward_sp); a plain qie_forward on the same handle ignores them.  Call it again whenever the
@@ -222,7 +225,7 @@ int qie_peer_close(void* dev_ptr);
 int qie_peer_barrier(qie_handle* h, void* stream);
 /* 0, or 1 once a barrier has timed out (read from mapped host memory: no stream is synchronised) */
 int qie_peer_barrier_timeouts(void);
-/* The whole sequence-parallel forward of this rank as ONE call (peers installed): BEGIN, per block QKV -> barrier -> ATTN ->
+/* The whole sequence-parallel forward of this rank as ONE call (peers installed): BEGIN -> barrier, per block QKV -> barrier -> ATTN ->
  * barrier -> POST, END -> barrier; `out_full` bf16 [batch, img_total, out_dim] receives the velocity of ALL tokens (every rank's
  * END stores its rows into every rank's `vel` buffer).  No allocation, no host synchronisation: CUDA-graph capturable. */
 int qie_forward_sp(qie_handle* h, const void* hidden_local, const void* enc_local, const float* timestep,

@@ -72,7 +72,7 @@ class GemmArgs(C.Structure):
 class Peers(C.Structure):
     _fields_ = [("rank", C.c_int), ("size", C.c_int), ("batch", C.c_int), ("img_pad", C.c_int), ("txt_pad", C.c_int),
                 ("img_total", C.c_int), ("txt_total", C.c_int), ("qkv_gather", C.c_void_p * 8), ("attn_out", C.c_void_p * 8),
-                ("vel", C.c_void_p * 8), ("flags", C.c_void_p * 8)]
+                ("vel", C.c_void_p * 8), ("flags", C.c_void_p * 8), ("mod", C.c_void_p * 8)]
 
 
 PROFILE_CLASSES = 6

@@ -78,6 +78,8 @@ int attn_fwd_peers(const void* qkv_gathered, void* const* peer_out_dev, const qi
 int peer_bcast_rows(const void* src, void* const* peer_vel_dev, const qie_peers* pr, int img_rows, int img_offset, int C,
                     cudaStream_t st);
 int peer_barrier_launch(const qie_peers* pr, cudaStream_t st);
+int peer_bcast_span(const void* mine, void* const* peer_tab_dev, const qie_peers* pr, long long bstride_bytes, long long off_bytes,
+                    long long len_bytes, cudaStream_t st);
 
 // ---- per-(device, stream) kernel scratch (common.cuh) ----
 namespace {
@@ -162,11 +164,11 @@ struct qie_handle {
     int prompt_rows[4] = {0, 0, 0, 0};
     int sel_sched[8] = {-1, -1, -1, -1, -1, -1, -1, -1};         // per batch row, -1 = compute
     int sel_prompt = -1;
-    // fused Ulysses exchange (qie_set_peers): host copy + device table [0..7] qkv_gather, [8..15] attn_out, [16..23] vel
+    // fused Ulysses exchange (qie_set_peers): host copy + device table [0..7] qkv_gather, [8..15] attn_out, [16..23] vel, [24..31] mod
     bool has_peers = false;
     qie_peers peers{};
     void** d_peer_tab = nullptr;
-    void* peer_tab_host[24] = {};            // what d_peer_tab holds (re-uploaded only when an address changes)
+    void* peer_tab_host[32] = {};            // what d_peer_tab holds (re-uploaded only when an address changes); [24..31] mod tables
     const int* d_tile_valid = nullptr;       // valid rows per 128-row tile of the gathered sequence of the installed geometry
     struct TileEntry { int img_total, txt_total, size; int* d; };
     std::vector<TileEntry> tile_cache;       // one list per geometry, kept until qie_destroy (captured graphs point at them)
@@ -574,6 +576,9 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
     float* mod = temb + 8 * (size_t)D;                       // [B][L*2*6D]
     const long long modN = (long long)nb * 12 * D;   // batch stride of the modulation table
     float* fin = mod + 8 * (size_t)L * 12 * D;                     // [B][2D]
+    // sequence parallel: the modulation table lives in peer-visible memory; every rank computes 1/P of its rows (the 13.6 GB
+    // weight stream is the one part of the forward that does not shrink with the token shard) and stores them into the others
+    if (use_peers) mod = (float*)h->peers.mod[h->peers.rank];
     if (phases & QIE_PHASE_BEGIN) {
     bool sched_cached = h->n_sched > 0;
     for (int b = 0; b < B; ++b) sched_cached = sched_cached && h->sel_sched[b] >= 0 && h->sel_sched[b] < h->n_sched;
@@ -591,7 +596,16 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
     if ((rc = qie_timestep_proj(timestep, tproj, B, 0, st))) return rc;
     if ((rc = qie_gemv(tproj, h->w.t1_w, h->w.t1_b, t1, B, D, 256, 0, st))) return rc;
     if ((rc = qie_gemv(t1, h->w.t2_w, h->w.t2_b, temb, B, D, D, 1, st))) return rc;
-    if (nb > 0) {
+    if (nb > 0 && use_peers) {
+        const qie_peers& pr = h->peers;
+        const long long q = modN / 4, n0 = q * pr.rank / pr.size * 4, n1 = q * (pr.rank + 1) / pr.size * 4;   // 16-byte granules
+        {
+            ProfScope ps(h, st, 3, (double)(n1 - n0) * D * 2);
+            if ((rc = gemv_strided(temb, (const __nv_bfloat16*)h->w.mod_w + n0 * D, h->w.mod_b + n0, mod + n0, B, n1 - n0, D, 1, modN, st)))
+                return rc;
+        }
+        if ((rc = peer_bcast_span(mod, h->d_peer_tab + 24, &pr, modN * 4, n0 * 4, (n1 - n0) * 4, st))) return rc;
+    } else if (nb > 0) {
         ProfScope ps(h, st, 3, (double)modN * D * 2);
         if ((rc = qie_gemv(temb, h->w.mod_w, h->w.mod_b, mod, B, modN, D, 1, st))) return rc;
     }
@@ -814,13 +828,14 @@ extern "C" int qie_set_peers(qie_handle* h, const qie_peers* peers, void* stream
     QIE_REQUIRE(s.img_pad == peers->img_pad && s.txt_pad == peers->txt_pad, QIE_ESHAPE,
                 "qie_set_peers: shard padding %d+%d does not match qie_sp_shard (%d+%d)", peers->img_pad, peers->txt_pad,
                 s.img_pad, s.txt_pad);
-    void* tab[24] = {};
+    void* tab[32] = {};
     for (int i = 0; i < peers->size; ++i) {
-        QIE_REQUIRE(peers->qkv_gather[i] && peers->attn_out[i] && peers->vel[i] && peers->flags[i], QIE_EINVAL,
+        QIE_REQUIRE(peers->qkv_gather[i] && peers->attn_out[i] && peers->vel[i] && peers->flags[i] && peers->mod[i], QIE_EINVAL,
                     "qie_set_peers: a buffer of rank %d is null", i);
         tab[i] = peers->qkv_gather[i];
         tab[8 + i] = peers->attn_out[i];
         tab[16 + i] = peers->vel[i];
+        tab[24 + i] = peers->mod[i];
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (!h->d_peer_tab) {
@@ -870,6 +885,7 @@ extern "C" int qie_forward_sp(qie_handle* h, const void* hidden_local, const voi
     int rc = forward_impl(h, QIE_PHASE_BEGIN, -1, hidden_local, enc_local, timestep, img_shapes_host, n_img, seq, sp, nullptr,
                           workspace, workspace_bytes, -1, stream);
     if (rc) return rc;
+    if ((rc = qie_peer_barrier(h, stream))) return rc;          // every rank's share of the modulation table has landed in mine
     for (int l = 0; l < h->cfg.num_layers; ++l) {
         // adaLN1 + QKV GEMM: the epilogue stores q|k|v of head group g into rank g's gather buffer
         if ((rc = forward_impl(h, QIE_PHASE_QKV, l, nullptr, nullptr, nullptr, img_shapes_host, n_img, seq, sp, nullptr, workspace,

@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256, 1) ln_mod_stream_kernel(const float* __re
 template <int BATCH>
 __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                                    const float* __restrict__ bias, float* __restrict__ y,
-                                                   long long N, int K, int act, int rows_per_warp) {
+                                                   long long N, int K, int act, int rows_per_warp, long long y_bstride) {
     extern __shared__ float xs[];   // [BATCH][K]
     for (int i = threadIdx.x; i < BATCH * K; i += blockDim.x) {
         float v = x[i];
@@ -314,8 +314,8 @@ __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ x, 
         for (int b = 0; b < BATCH; ++b) {
             float s0 = warp_sum(acc0[b]), s1 = warp_sum(acc1[b]);
             if (lane == 0) {
-                y[(long long)b * N + n0] = s0 + (bias ? bias[n0] : 0.f);
-                if (has1) y[(long long)b * N + n1] = s1 + (bias ? bias[n1] : 0.f);
+                y[(long long)b * y_bstride + n0] = s0 + (bias ? bias[n0] : 0.f);
+                if (has1) y[(long long)b * y_bstride + n1] = s1 + (bias ? bias[n1] : 0.f);
             }
         }
     }
@@ -599,6 +599,12 @@ extern "C" int qie_ln_modulate(const float* x, const float* mod, long long mod_b
 
 extern "C" int qie_gemv(const float* x, const void* w, const float* bias, float* y, int batch, long long N, int K,
                         int act, void* stream) {
+    return qie::gemv_strided(x, w, bias, y, batch, N, K, act, N, stream);
+}
+
+// y[b * y_bstride + n]: a row range of a wider table (the sequence-parallel ranks each compute 1/P of the modulation table)
+int qie::gemv_strided(const float* x, const void* w, const float* bias, float* y, int batch, long long N, int K, int act,
+                      long long y_bstride, void* stream) {
     QIE_REQUIRE(x && w && y, QIE_EINVAL, "qie_gemv: null pointer");
     QIE_REQUIRE(batch >= 1 && batch <= 8 && K % 8 == 0 && N > 0, QIE_ESHAPE, "qie_gemv: bad shape B=%d N=%lld K=%d",
                 batch, N, K);
@@ -612,7 +618,7 @@ extern "C" int qie_gemv(const float* x, const void* w, const float* bias, float*
     case B:                                                                                                       \
         if (smem > 48 * 1024)                                                                                     \
             QIE_CUDA_OK(cudaFuncSetAttribute(gemv_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        gemv_kernel<B><<<blocks, 256, smem, st>>>(x, (const __nv_bfloat16*)w, bias, y, N, K, act, rows_per_warp);   \
+        gemv_kernel<B><<<blocks, 256, smem, st>>>(x, (const __nv_bfloat16*)w, bias, y, N, K, act, rows_per_warp, y_bstride);   \
         break;
     switch (batch) {
         QIE_GEMV_CASE(1)

@@ -48,6 +48,10 @@ struct PeerFlags {
 __global__ void peer_barrier_kernel(PeerFlags f, int rank, int size, int* sticky) {
     __shared__ unsigned epoch_s;
     const int t = threadIdx.x;
+    // programmatic dependent launch: this one-warp kernel is resident before its predecessor has drained and lets its successor
+    // run its prologue; the flag is only published once the predecessor has completed and flushed its (peer) stores
+    griddep_launch_dependents();
+    griddep_wait();
     if (t == 0) {
         unsigned* ctr = f.p[rank] + 8;
         epoch_s = *ctr + 1;
@@ -102,12 +106,43 @@ int peer_bcast_rows(const void* src, void* const* peer_vel_dev, const qie_peers*
     return QIE_OK;
 }
 
+// my span [off16, off16 + len16) (in 16-byte units) of every batch row of a table that all ranks hold at the same layout ->
+// the same span of every OTHER rank's copy (the modulation table: each rank computes 1/P of its rows)
+__global__ void peer_bcast_span_kernel(const uint4* __restrict__ src, void* const* __restrict__ tab, int size, int rank, int batch,
+                                       long long bstride16, long long off16, long long len16) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch * len16) return;
+    const long long idx = (i / len16) * bstride16 + off16 + i % len16;
+    const uint4 v = src[idx];
+    for (int g = 0; g < size; ++g)
+        if (g != rank) reinterpret_cast<uint4*>(__ldg(reinterpret_cast<const unsigned long long*>(tab) + g))[idx] = v;
+}
+
+int peer_bcast_span(const void* mine, void* const* peer_tab_dev, const qie_peers* pr, long long bstride_bytes, long long off_bytes,
+                    long long len_bytes, cudaStream_t st) {
+    QIE_REQUIRE(mine && peer_tab_dev && pr && bstride_bytes % 16 == 0 && off_bytes % 16 == 0 && len_bytes % 16 == 0, QIE_EINVAL,
+                "peer_bcast_span: bad argument");
+    const long long total = pr->batch * (len_bytes / 16);
+    if (total == 0) return QIE_OK;
+    peer_bcast_span_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint4*)mine, peer_tab_dev, pr->size, pr->rank,
+                                                                            pr->batch, bstride_bytes / 16, off_bytes / 16, len_bytes / 16);
+    QIE_LAUNCH_OK("peer_bcast_span_kernel");
+    return QIE_OK;
+}
+
 int peer_barrier_launch(const qie_peers* pr, cudaStream_t st) {
     int rc = sticky_init();
     if (rc) return rc;
     PeerFlags f{};
     for (int i = 0; i < pr->size; ++i) f.p[i] = (unsigned*)pr->flags[i];
-    peer_barrier_kernel<<<1, 32, 0, st>>>(f, pr->rank, pr->size, g_sticky_dev);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(32);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    cfg.attrs = attr;
+    cfg.numAttrs = launch_attrs(attr, 1);
+    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, peer_barrier_kernel, f, pr->rank, pr->size, g_sticky_dev));
     QIE_LAUNCH_OK("peer_barrier_kernel");
     return QIE_OK;
 }

@@ -114,7 +114,8 @@ def exchange_bytes_per_forward(plan: ShardPlan, batch: int, heads: int, layers: 
     D = heads * 128
     qkv = rows * 3 * D * 2 * (P - 1) // P
     att = (plan.img_total + plan.txt_total - rows) * (D // P) * 2
-    return batch * (layers * (qkv + att) + plan.img_rows * out_dim * 2 * (P - 1))
+    mod = layers * 12 * D * 4 // P * (P - 1)          # its share of the modulation table, to every other rank
+    return batch * (layers * (qkv + att) + plan.img_rows * out_dim * 2 * (P - 1) + mod)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -122,21 +123,21 @@ def exchange_bytes_per_forward(plan: ShardPlan, batch: int, heads: int, layers: 
 # ------------------------------------------------------------------------------------------------
 class PeerRankBuffers:
     """What ONE rank of a sequence-parallel group owns: its workspace (the attention-output buffer lives inside), the
-    gathered q|k|v buffer of its head group, its velocity buffer and its barrier words, all cudaMalloc'ed by libqie so that
+    gathered q|k|v buffer of its head group, its velocity buffer, its barrier words and its modulation table, all cudaMalloc'ed by libqie so that
     they can be exported over CUDA IPC and written by the other ranks' kernels through NVLink."""
 
-    def __init__(self, ws_bytes: int, gather_bytes: int, vel_bytes: int):
+    def __init__(self, ws_bytes: int, gather_bytes: int, vel_bytes: int, mod_bytes: int):
         lib = L.lib()
         self.ptrs, self.handles = [], []
-        for n in (ws_bytes, gather_bytes, vel_bytes, 256):
+        for n in (ws_bytes, gather_bytes, vel_bytes, 256, mod_bytes):
             p, h = C.c_void_p(), C.create_string_buffer(64)
             L.check(lib.qie_peer_alloc(n, C.byref(p), h), "qie_peer_alloc")
             if n == ws_bytes and p.value % 1024:      # qie_forward wants a 1 KB aligned workspace; large cudaMallocs are
                 raise L.QieError("cudaMalloc returned a workspace that is not 1 KB aligned")
             self.ptrs.append(p.value)
             self.handles.append(h.raw)
-        self.ws, self.gather, self.vel, self.flags = self.ptrs
-        self.sizes = (ws_bytes, gather_bytes, vel_bytes)
+        self.ws, self.gather, self.vel, self.flags, self.mod = self.ptrs
+        self.sizes = (ws_bytes, gather_bytes, vel_bytes, mod_bytes)
 
     def free(self):
         for p in self.ptrs:
@@ -170,7 +171,7 @@ def scatter_attn_reference(o_gathered: torch.Tensor, attn_out: Sequence[torch.Te
 
 
 def make_peers(plan: ShardPlan, batch: int, gathers: Sequence[int], attn_outs: Sequence[int], vels: Sequence[int],
-               flags: Sequence[int]):
+               flags: Sequence[int], mods: Sequence[int]):
     pr = L.Peers()
     pr.rank, pr.size, pr.batch = plan.rank, plan.size, batch
     pr.img_pad, pr.txt_pad, pr.img_total, pr.txt_total = plan.img_pad, plan.txt_pad, plan.img_total, plan.txt_total
@@ -179,6 +180,7 @@ def make_peers(plan: ShardPlan, batch: int, gathers: Sequence[int], attn_outs: S
         pr.attn_out[i] = attn_outs[i]
         pr.vel[i] = vels[i]
         pr.flags[i] = flags[i]
+        pr.mod[i] = mods[i]
     return pr
 
 
@@ -205,6 +207,7 @@ class _Geometry:
         self.ws_bytes = L.lib().qie_workspace_bytes(t._handle, C.byref(self.seq))
         self.gather_bytes = B * p.gathered_rows * 3 * hl * 128 * 2
         self.vel_bytes = B * S_i * t.cfg.out_dim * 2
+        self.mod_bytes = B * t.cfg.num_layers * 12 * t.cfg.inner_dim * 4
         self.hs = torch.empty(B, p.img_rows, t.cfg.in_channels, dtype=torch.bfloat16, device=dev)
         self.enc = torch.empty(B, p.txt_rows, t.cfg.joint_attention_dim, dtype=torch.bfloat16, device=dev)
         self.ts = torch.empty(B, dtype=torch.float32, device=dev)
@@ -245,7 +248,7 @@ class UlyssesTransformer:
     def _ensure_buffers(self, geo: _Geometry):
         """(re)allocates the IPC-shared buffers when `geo` needs more room than any geometry before it (collective: every
         rank sees the same geometries in the same order) and exchanges the handles"""
-        need = (geo.ws_bytes, geo.gather_bytes, geo.vel_bytes)
+        need = (geo.ws_bytes, geo.gather_bytes, geo.vel_bytes, geo.mod_bytes)
         if self._bufs is not None and all(h >= n for h, n in zip(self._bufs[0].sizes, need)):
             return
         sizes = need if self._bufs is None else tuple(max(h, n) for h, n in zip(self._bufs[0].sizes, need))
@@ -256,14 +259,14 @@ class UlyssesTransformer:
         blob = torch.frombuffer(bytearray(b"".join(mine.handles)), dtype=torch.uint8).to(dev)
         allb = torch.empty(P * blob.numel(), dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(allb, blob, group=self.group)
-        allb = allb.cpu().view(P, 4, 64)
+        allb = allb.cpu().view(P, 5, 64)
         per_rank, opened = [], []
         for r in range(P):
             if r == self.rank:
                 ptrs = list(mine.ptrs)
             else:
                 ptrs = []
-                for i in range(4):
+                for i in range(5):
                     q = C.c_void_p()
                     L.check(lib.qie_peer_open(bytes(allb[r, i].tolist()), C.byref(q)), "qie_peer_open")
                     ptrs.append(q.value)
@@ -295,7 +298,7 @@ class UlyssesTransformer:
         per_rank = self._bufs[2]
         off = lib.qie_workspace_offset(t._handle, C.byref(geo.seq), 1)
         peers = make_peers(geo.plan, geo.B, [p[1] for p in per_rank], [p[0] + off for p in per_rank], [p[2] for p in per_rank],
-                           [p[3] for p in per_rank])
+                           [p[3] for p in per_rank], [p[4] for p in per_rank])
         L.check(lib.qie_set_peers(t._handle, C.byref(peers), L.cur_stream()), "qie_set_peers")
         self._installed = key
 
@@ -442,10 +445,11 @@ def emulate_fused_ulysses(transformer, size: int, hidden_states, encoder_hidden_
     sps = [L.Sp(p.rank, p.size, p.img_total, p.txt_total, p.img_offset, p.txt_offset) for p in plans]
     ws_bytes = max(lib.qie_workspace_bytes(t._handle, C.byref(s)) for s in seqs)
     vel_bytes = B * S_i * t.cfg.out_dim * 2
-    bufs = [PeerRankBuffers(ws_bytes, B * plans[0].gathered_rows * 3 * hl * 128 * 2, vel_bytes) for _ in range(size)]
+    mod_bytes = B * t.cfg.num_layers * 12 * t.cfg.inner_dim * 4
+    bufs = [PeerRankBuffers(ws_bytes, B * plans[0].gathered_rows * 3 * hl * 128 * 2, vel_bytes, mod_bytes) for _ in range(size)]
     off = lib.qie_workspace_offset(t._handle, C.byref(seqs[0]), 1)
     peers = [make_peers(plans[r], B, [b.gather for b in bufs], [b.ws + off for b in bufs], [b.vel for b in bufs],
-                        [b.flags for b in bufs]) for r in range(size)]
+                        [b.flags for b in bufs], [b.mod for b in bufs]) for r in range(size)]
     ts = timestep.to(device=dev, dtype=torch.float32).reshape(-1).expand(B).contiguous()
     flat = _flat_shapes(img_shapes)
     shp = (C.c_int * len(flat))(*flat)

@@ -211,7 +211,7 @@ def test_exchange_bytes_accounting():
     p = qie_b200.make_shard_plan(8192, 256, 4, 1)
     rows, D = p.img_rows + p.txt_rows, 3072
     per_block = rows * 3 * D * 2 * 3 // 4 + (8448 - rows) * (D // 4) * 2
-    assert qie_b200.exchange_bytes_per_forward(p, 1, 24, 60) == 60 * per_block + p.img_rows * 64 * 2 * 3
+    assert qie_b200.exchange_bytes_per_forward(p, 1, 24, 60) == 60 * per_block + p.img_rows * 64 * 2 * 3 + 60 * 12 * D * 4 // 4 * 3
 
 
 def test_pure_sequence_parallel_layout_runs_both_cfg_forwards():

@@ -88,8 +88,9 @@ def test_fused_peer_exchange_two_text_lengths_same_padding():
     # a forward phase against peers of another geometry is an error, not a silent mis-mask
     import ctypes as C
     plan = qie_b200.make_shard_plan(376, 37, 2, 0)
-    bufs = [qie_b200.PeerRankBuffers(1 << 20, 1 << 20, 1 << 16) for _ in range(2)]
-    peers = qie_b200.make_peers(plan, 1, [b.gather for b in bufs], [b.ws for b in bufs], [b.vel for b in bufs], [b.flags for b in bufs])
+    bufs = [qie_b200.PeerRankBuffers(1 << 20, 1 << 20, 1 << 16, 1 << 20) for _ in range(2)]
+    peers = qie_b200.make_peers(plan, 1, [b.gather for b in bufs], [b.ws for b in bufs], [b.vel for b in bufs], [b.flags for b in bufs],
+                                [b.mod for b in bufs])
     lib = L.lib()
     L.check(lib.qie_set_peers(model._handle, C.byref(peers), L.cur_stream()))
     other = qie_b200.make_shard_plan(376, 22, 2, 0)
