@@ -242,6 +242,7 @@ def workload_config(args, n):
     return {"workload": "Qwen-Image-Edit-2509 MMDiT denoise (60 blocks, D=3072, 24 heads, random-init), " + what +
                         ("true-CFG 4.0 (cond+uncond)" if args.cfg else "cond-only"),
             "img_tokens": N_IMG_TOK, "txt_tokens": T_TXT, "forwards_per_image": STEPS_PER_IMAGE * (2 if args.cfg else 1),
+            "frames_per_forward": getattr(args, "batch", 1),
             "layers": args.layers, "precision": args.precision, "caches": bool(getattr(args, "cache", False)),
             "parallelism": (f"dp{n}: one independent frame stream per GPU, weights replicated, no data-path collective"
                             if args.mode == "dp" else f"{args.mode}{' (fused peer-memory exchange)' if args.fused else ' (NCCL all-to-all)' if 'ulysses' in args.mode else ''} over {n} GPUs: ONE frame, weights replicated"),
@@ -388,10 +389,11 @@ def run_ours(args):
         if os.environ.get(env):
             qie_b200.lib().qie_tune(key, int(os.environ[env]))
     g = torch.Generator(device=dev).manual_seed(1 + rank)
-    lat = torch.randn(1, N_NOISE, 64, generator=g, device=dev).bfloat16()
-    img_lat = torch.randn(1, N_IMG_TOK - N_NOISE, 64, generator=g, device=dev).bfloat16()
-    cond = (torch.randn(1, T_TXT, cfg.joint_attention_dim, generator=g, device=dev) * 3).bfloat16()
-    unc = (torch.randn(1, T_TXT, cfg.joint_attention_dim, generator=g, device=dev) * 3).bfloat16() if args.cfg else None
+    NB = args.batch
+    lat = torch.randn(NB, N_NOISE, 64, generator=g, device=dev).bfloat16()
+    img_lat = torch.randn(NB, N_IMG_TOK - N_NOISE, 64, generator=g, device=dev).bfloat16()
+    cond = (torch.randn(NB, T_TXT, cfg.joint_attention_dim, generator=g, device=dev) * 3).bfloat16()
+    unc = (torch.randn(NB, T_TXT, cfg.joint_attention_dim, generator=g, device=dev) * 3).bfloat16() if args.cfg else None
     host = {k: v.cpu().pin_memory() for k, v in (("lat", lat), ("img", img_lat), ("cond", cond))}
     if unc is not None:
         host["unc"] = unc.cpu().pin_memory()
@@ -410,10 +412,10 @@ def run_ours(args):
         if layout.sp_size > 1:
             runner = qie_b200.UlyssesTransformer(model, layout.sp_group, fused=args.fused)
         g = torch.Generator(device=dev).manual_seed(1)      # one frame: identical inputs on every rank
-        lat = torch.randn(1, N_NOISE, 64, generator=g, device=dev).bfloat16()
-        img_lat = torch.randn(1, N_IMG_TOK - N_NOISE, 64, generator=g, device=dev).bfloat16()
-        cond = (torch.randn(1, T_TXT, cfg.joint_attention_dim, generator=g, device=dev) * 3).bfloat16()
-        unc = (torch.randn(1, T_TXT, cfg.joint_attention_dim, generator=g, device=dev) * 3).bfloat16() if args.cfg else None
+        lat = torch.randn(NB, N_NOISE, 64, generator=g, device=dev).bfloat16()
+        img_lat = torch.randn(NB, N_IMG_TOK - N_NOISE, 64, generator=g, device=dev).bfloat16()
+        cond = (torch.randn(NB, T_TXT, cfg.joint_attention_dim, generator=g, device=dev) * 3).bfloat16()
+        unc = (torch.randn(NB, T_TXT, cfg.joint_attention_dim, generator=g, device=dev) * 3).bfloat16() if args.cfg else None
         host = {k: v.cpu().pin_memory() for k, v in (("lat", lat), ("img", img_lat), ("cond", cond))}
         if unc is not None:
             host["unc"] = unc.cpu().pin_memory()
@@ -425,12 +427,14 @@ def run_ours(args):
         if unc is not None:
             model.cache_prompt("uncond", unc)
 
+    shapes_b = IMG_SHAPES * args.batch if args.batch > 1 else IMG_SHAPES
+
     def denoise(l, i, c, u):
         if args.cache and args.mode == "dp":
             return qie_b200.run_denoise(runner, l, i, c, IMG_SHAPES, STEPS_PER_IMAGE, u, 4.0, use_caches=True)
         if layout is not None and layout.cfg_branches == 2:
-            return qie_b200.run_denoise_parallel(runner, layout, l, i, c, u, IMG_SHAPES, STEPS_PER_IMAGE, 4.0)
-        return qie_b200.run_denoise(runner, l, i, c, IMG_SHAPES, STEPS_PER_IMAGE, u, 4.0)
+            return qie_b200.run_denoise_parallel(runner, layout, l, i, c, u, shapes_b, STEPS_PER_IMAGE, 4.0)
+        return qie_b200.run_denoise(runner, l, i, c, shapes_b, STEPS_PER_IMAGE, u, 4.0)
 
     def step_resident():
         return denoise(lat, img_lat, cond, unc)
@@ -470,7 +474,7 @@ def run_ours(args):
         launches = L.qie_launch_count() - n0
     clocks = clk.summary()
     ms_step = ms_total / args.steps
-    frames = world if args.mode == "dp" else 1     # frames finished per step by the whole job
+    frames = (world if args.mode == "dp" else 1) * args.batch     # frames finished per step by the whole job
     value = frames * 1e3 / ms_step
 
     for _ in range(2):
@@ -524,14 +528,16 @@ def run_ours(args):
                 "mod_gemv": {"achieved_gbs": prof["mod_gemv"]["work"] / (prof["mod_gemv"]["ms"] * 1e-3) / 1e9 if prof["mod_gemv"]["ms"] else 0,
                              "peak_gbs": hbm, "share_of_step": prof["mod_gemv"]["ms"] / tot_ms if tot_ms else None},
                 "event_sum_ms_per_step": tot_ms / args.steps,      # sum of the per-kernel event intervals; the rest of ms_per_step is inter-kernel gaps
-                "step_tflops": STEPS_PER_IMAGE * (2 if args.cfg else 1) * flops_per_forward(args.layers) / (ms_step * 1e-3) / 1e12}
+                "step_tflops": args.batch * STEPS_PER_IMAGE * (2 if args.cfg else 1) * flops_per_forward(args.layers) / (ms_step * 1e-3) / 1e12}
 
     strong = None
-    if args.mode == "dp" and not args.no_strong and args.precision == "bf16" and args.workload == "1024x1ref" and not args.cache:
+    if (args.mode == "dp" and not args.no_strong and args.precision == "bf16" and args.workload == "1024x1ref" and not args.cache
+            and args.batch == 1 and not args.cfg and args.sched_steps == 0):
         strong = strong_leg(args, model, dev, world, rank, timed)
 
     eager = None
-    if rank == 0 and world == 1 and not args.no_eager_baseline and args.workload == "1024x1ref":
+    if (rank == 0 and world == 1 and not args.no_eager_baseline and args.workload == "1024x1ref" and args.batch == 1
+            and args.precision == "bf16" and args.layers == 60):
         e = run_eager_gpu(args, emit=False, min_ms=2000.0)
         eager = {"ms_per_forward": e["dit_forward_ms"], "value": e["value"], "unit": UNIT, "sample": e["sample"],
                  "clocks": e["clocks"], "speedup_of_this_repo": e["ms_per_step"] / ms_step}
@@ -555,7 +561,7 @@ def run_ours(args):
                 "e2e": {"value": frames * 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "dit_forward_ms": ms_step / (STEPS_PER_IMAGE * (2 if args.cfg else 1)),
+                "dit_forward_ms": ms_step / (STEPS_PER_IMAGE * (2 if args.cfg else 1)), "latency_ms_per_batch": ms_step,
                 "strong": strong, "gpu_eager_baseline": eager}
         print(json.dumps(line), flush=True)
     failed = bool(strong and strong.get("failed"))
@@ -582,6 +588,8 @@ def main():
     ap.add_argument("--mode", default="dp", choices=["dp", "cfgpair", "ulysses", "cfg+ulysses"])
     ap.add_argument("--fused", action="store_true", help="ulysses modes: exchange q|k|v and the attention output through "
                     "epilogue stores into peer memory (NVLink) instead of NCCL all-to-alls")
+    ap.add_argument("--batch", type=int, default=1, help="frames per forward on every rank (dp) / inside the group (other modes); "
+                    "BASELINE configs[4] streams batches of 8")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (ONE true-CFG frame over all ranks)")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the bf16 PyTorch-eager GPU side baseline (N = 1)")

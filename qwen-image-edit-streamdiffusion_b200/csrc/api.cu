@@ -373,7 +373,7 @@ extern "C" int qie_set_option(qie_handle* h, int key, int value) {
 // workspace carve-up (all offsets 1 KB aligned)
 namespace {
 struct Ws {
-    size_t resid, xm, xm8, xscale, qkv, attn, attn8, ffh, ffh8, xin, xtxt, outp, total;
+    size_t resid, xm, xm8, xscale, qkv, attn, attn8, ffh, ffh8, xin, xtxt, outp, amax, total;
 };
 inline size_t al(size_t x) { return (x + 1023) & ~size_t(1023); }
 Ws carve(const qie_handle* h, const qie_seq* s) {
@@ -392,6 +392,7 @@ Ws carve(const qie_handle* h, const qie_seq* s) {
     w.attn8 = o; o += al(rows * D);
     w.ffh8 = o; o += al(rows * 4 * D);
     w.xscale = o; o += al(rows * 4 * 3);
+    w.amax = o; o += al(rows * 4);
     w.total = o;
     return w;
 }
@@ -487,6 +488,7 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
     void* attn8 = W + ws.attn8;
     void* ffh8 = W + ws.ffh8;
     float* xscale = (float*)(W + ws.xscale);   // [3][rows]: xm, attn, ffh scales
+    float* ffh_amax = (float*)(W + ws.amax);   // [rows]: max|ffh| per token, folded in by the FF-up epilogue (8-bit modes)
     const size_t rows = (size_t)B * rpb;
     const int fp8 = h->precision;   // 0 bf16, 1 e4m3 W8A8, 2 int8 W8A8
 
@@ -686,6 +688,7 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
             }
             g.a = attn;
             if (fp8) {
+                ProfScope ps(h, st, 4, (double)rows * D * 3);
                 if ((rc = qie_quant_rows(attn, attn8, xscale + rows, (long long)rows, D, h->precision, st))) return rc;
                 g.a = attn8; g.fp8 = fp8; g.a_scale = xscale + rows;
             }
@@ -702,6 +705,10 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
                 g.w_scale[s] = bw.ff1_ws[s];
             }
             g.a = fp8 ? xm8 : xm; g.fp8 = fp8; g.a_scale = xscale;
+            if (fp8) {      // the per-token quantiser of the FF hidden needs the row max: the GELU epilogue folds it in
+                QIE_CUDA_OK(cudaMemsetAsync(ffh_amax, 0, rows * sizeof(float), st));
+                g.q8_amax = ffh_amax;
+            }
             if ((rc = run_gemm(g))) return rc;
         }
         {   // FF down + gate2 * y + residual
@@ -715,7 +722,8 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
             }
             g.a = ffh;
             if (fp8) {
-                if ((rc = qie_quant_rows(ffh, ffh8, xscale + 2 * rows, (long long)rows, 4 * D, h->precision, st))) return rc;
+                ProfScope ps(h, st, 4, (double)rows * 4 * D * 3);      // one streaming pass: bf16 in, 8 bit out
+                if ((rc = quant_rows_amax(ffh, ffh_amax, ffh8, xscale + 2 * rows, (long long)rows, 4 * D, h->precision, st))) return rc;
                 g.a = ffh8; g.fp8 = fp8; g.a_scale = xscale + 2 * rows;
             }
             if ((rc = run_gemm(g))) return rc;

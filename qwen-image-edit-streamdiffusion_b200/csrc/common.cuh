@@ -45,6 +45,7 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
                  uint32_t box_rows, uint32_t box_cols, int elt_bytes);
 
 int sm_count();
+int quant_rows_amax(const void* x, const float* amax, void* q, float* scale, long long rows, int K, int qmode, void* stream);
 int gemv_strided(const float* x, const void* w, const float* bias, float* y, int batch, long long N, int K, int act,
                  long long y_bstride, void* stream);
 // QIE_ECUDA (with the message set) once a peer barrier of this process has timed out, else QIE_OK; `clear` re-arms the flag

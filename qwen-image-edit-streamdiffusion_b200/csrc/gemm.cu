@@ -411,6 +411,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             };
 
             [[maybe_unused]] float rinv_head = 1.f;
+            [[maybe_unused]] float rmax[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // q8_amax: max|out| of my 8 rows over this tile
             if (!dummy) {
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c) {
@@ -521,6 +522,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         }
                         if constexpr (EPI == QIE_EPI_GELU_BF16) {
                             v.x = gelu_tanh(v.x); v.y = gelu_tanh(v.y); v.z = gelu_tanh(v.z); v.w = gelu_tanh(v.w);
+                            if (p.q8_amax) rmax[it] = fmaxf(rmax[it], fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
                         }
                         if constexpr (EPI == QIE_EPI_GATE_RESID_F32) {
                             if (valid) {
@@ -542,6 +544,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         }
                     }
                     __syncwarp();   // staging tile is reused by the next chunk
+                }
+            }
+            if constexpr (EPI == QIE_EPI_GELU_BF16) {
+                // the 8-bit GEMM that consumes this output quantises per token: fold max|out| of every row (as the bf16 value
+                // the quantiser will see; rounding is monotonic) into q8_amax[row] so that the cast needs no max pass of its own
+                if (p.q8_amax && !dummy) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        float m = rmax[it];
+                        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                        const int rr = it * 4 + sub;
+                        if ((lane & 7) == 0 && local0 + rr < seg_rows)
+                            atomicMax(reinterpret_cast<int*>(p.q8_amax + orow0 + rr), __float_as_int(__bfloat162float(__float2bfloat16(m))));
+                    }
                 }
             }
             // release this accumulator stage back to the MMA warp (of the leader CTA)
@@ -661,6 +679,8 @@ extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream
         for (int k = 0; k < 2; ++k) p.qk_norm_w[s][k] = g->qk_norm_w[s][k];
     }
     p.model_dim = g->N / 3;
+    QIE_REQUIRE(!g->q8_amax || g->epilogue == QIE_EPI_GELU_BF16, QIE_EINVAL, "qie_gemm: q8_amax is produced by the GELU epilogue only");
+    p.q8_amax = g->q8_amax;
     p.l2_hints = g_gemm_l2_hints;
     // raster band height: wide outputs (QKV, FF-up: >= 24 n-blocks) re-read A less with 16 m-units per band (ncu DRAM reads
     // 339 -> 239 MB and 429 -> 290 MB per launch), the N = 3072 shapes are best at 8 (profiles/r01_gemm_traffic.json)

@@ -434,19 +434,23 @@ __global__ void unpack_rows_kernel(const uint4* __restrict__ x, uint4* __restric
 // per-row dynamic e4m3 quantisation (activation side of the W8A8 path; README.md:140 "quantize + matmul + dequantize")
 __global__ void __launch_bounds__(256) quant_rows_kernel(const __nv_bfloat16* __restrict__ x,
                                                          uint8_t* __restrict__ q, float* __restrict__ scale,
-                                                         long long rows, int K, int qmode) {
+                                                         long long rows, int K, int qmode, const float* __restrict__ amax_in) {
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = lane_id();
     const __nv_bfloat16* xr = x + row * K;
     float amax = 0.f;
-    for (int c = lane * 8; c < K; c += 256) {
-        uint4 u = *reinterpret_cast<const uint4*>(xr + c);
-        float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
-        amax = fmaxf(amax, fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(b.x), fabsf(b.y))),
-                                 fmaxf(fmaxf(fabsf(cc.x), fabsf(cc.y)), fmaxf(fabsf(d.x), fabsf(d.y)))));
+    if (amax_in) {      // the producing GEMM epilogue already folded max|x| of the row: one streaming pass, no max pass
+        amax = amax_in[row];
+    } else {
+        for (int c = lane * 8; c < K; c += 256) {
+            uint4 u = *reinterpret_cast<const uint4*>(xr + c);
+            float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+            amax = fmaxf(amax, fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(b.x), fabsf(b.y))),
+                                     fmaxf(fmaxf(fabsf(cc.x), fabsf(cc.y)), fmaxf(fabsf(d.x), fabsf(d.y)))));
+        }
+        amax = warp_max(amax);
     }
-    amax = warp_max(amax);
     const float s = amax > 0.f ? amax / (qmode == 2 ? 127.f : 448.f) : 1.f;   // true divisions: bit-equal to torch.round(x / s) of the restated W8A8 reference
     for (int c = lane * 8; c < K; c += 256) {
         uint4 u = *reinterpret_cast<const uint4*>(xr + c);
@@ -748,10 +752,15 @@ extern "C" int qie_unpack_latents(const void* tokens, const float* mean, const f
 }
 
 extern "C" int qie_quant_rows(const void* x, void* q, float* scale, long long rows, int K, int qmode, void* stream) {
+    return qie::quant_rows_amax(x, nullptr, q, scale, rows, K, qmode, stream);
+}
+
+// amax != NULL: max|x| of every row is already known (folded in by the producing GEMM epilogue, qie_gemm_args::q8_amax)
+int qie::quant_rows_amax(const void* x, const float* amax, void* q, float* scale, long long rows, int K, int qmode, void* stream) {
     QIE_REQUIRE(x && q && scale, QIE_EINVAL, "qie_quant_rows: null pointer");
     QIE_REQUIRE(K % 8 == 0 && (qmode == 1 || qmode == 2), QIE_ESHAPE, "qie_quant_rows: K %% 8 != 0 or bad mode");
     quant_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, (uint8_t*)q, scale, rows, K, qmode);
+        (const __nv_bfloat16*)x, (uint8_t*)q, scale, rows, K, qmode, amax);
     QIE_LAUNCH_OK("quant_rows_kernel");
     return QIE_OK;
 }
