@@ -127,7 +127,7 @@ int qie_set_option(qie_handle* h, int key, int value);
 unsigned long long qie_launch_count(void);
 /* process-wide experiment / launch knobs: 0 adaLN threads/block, 1 adaLN smem reservation, 2 GEMM L2 hints (bit 0 weights
  * evict-last, bit 1 activations evict-first), 3 adaLN kernel form, 4 GEMM split-K tail, 5 GEMM raster band,
- * 7 programmatic dependent launch of the GEMM / attention / adaLN kernels (0 off, 1 on).
+ * 7 programmatic dependent launch of the GEMM / attention / adaLN / barrier kernels (1 on = default, 0 off).
  * qie_tune_get returns the current value (>= 0) or QIE_EINVAL for an unknown key. */
 int qie_tune(int key, int value);
 int qie_tune_get(int key);

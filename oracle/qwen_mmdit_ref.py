@@ -423,14 +423,18 @@ def ref_stream_prepare_latent(prev_latent, noise, frame_count: int, keyframe_int
 
 
 def ref_run_denoise(model, latents, image_latents, cond_embeds, img_shapes, num_steps: int,
-                    uncond_embeds=None, true_cfg_scale: float = 4.0, collect=None, begin_index: int = 0):
-    """The upstream pipeline denoise loop (A.6) on cached embeddings; begin_index = scheduler.set_begin_index."""
+                    uncond_embeds=None, true_cfg_scale: float = 4.0, collect=None, begin_index: int = 0,
+                    timestep_dtype: Optional[torch.dtype] = None):
+    """The upstream pipeline denoise loop (A.6) on cached embeddings; begin_index = scheduler.set_begin_index.
+    `timestep_dtype`: the pipeline casts t = 1000 * sigma to the LATENTS' dtype before dividing by 1000 (A.6), so a bf16
+    pipeline feeds the transformer 0.768 where an fp32 one feeds 0.766709; give torch.bfloat16 to follow the bf16 pipeline's
+    rounding chain while everything else stays fp32 (default: the latents' own dtype)."""
     sig = ref_flowmatch_sigmas(num_steps, latents.shape[1])
     n = latents.shape[1]
     B = latents.shape[0]
     for i in range(begin_index, num_steps):
         x = torch.cat([latents, image_latents], dim=1)
-        ts = ref_timestep_for_model(float(sig[i]), latents.dtype).expand(B)
+        ts = ref_timestep_for_model(float(sig[i]), timestep_dtype or latents.dtype).to(latents.dtype).expand(B)
         v = model(hidden_states=x, timestep=ts, encoder_hidden_states=cond_embeds, img_shapes=img_shapes,
                   txt_seq_lens=[cond_embeds.shape[1]] * B, return_dict=False)[0][:, :n]
         if uncond_embeds is not None and true_cfg_scale > 1:

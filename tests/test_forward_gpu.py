@@ -135,10 +135,13 @@ def _config4_gate(oracle, ours, lat, img_lat, cond, shapes, steps, tag, dev_orac
     to_o = lambda t: t.float().to(dev_oracle)
     ref_v, out = [], {}
     with torch.no_grad():
-        ref_final = R.ref_run_denoise(oracle, to_o(lat), to_o(img_lat), to_o(cond), shapes, steps, collect=ref_v)
+        # the oracles follow the bf16 pipeline's timestep rounding (t = 1000 sigma cast to bf16), everything else in fp32
+        ref_final = R.ref_run_denoise(oracle, to_o(lat), to_o(img_lat), to_o(cond), shapes, steps, collect=ref_v,
+                                      timestep_dtype=torch.bfloat16)
         for kind in ("int8", "fp8"):
             qv = []
-            qf = R.ref_run_denoise(R.quantized_view(oracle, kind), to_o(lat), to_o(img_lat), to_o(cond), shapes, steps, collect=qv)
+            qf = R.ref_run_denoise(R.quantized_view(oracle, kind), to_o(lat), to_o(img_lat), to_o(cond), shapes, steps, collect=qv,
+                                   timestep_dtype=torch.bfloat16)
             out["oracle_" + kind] = (fro(qv[0], ref_v[0]), K.rel_err(qv[0].cpu(), ref_v[0].cpu()), fro(qf, ref_final), cosine(qf, ref_final))
     for mode in ("bf16", "int8", "fp8"):
         ours.set_precision(mode)

@@ -87,8 +87,8 @@ for name, N, Kd, epi in [("qkv", 3 * D, D, K.L.EPI_QKV_NORM_ROPE), ("out", D, D,
 qkv = torch.randn(M, 3 * H * 128, device=dev).bfloat16()
 S = 8192 + 256
 aflops = 4.0 * S * S * 128 * H
-for v in (0x1020, 0x1000, 0x1030):
-    probe(f"attn_pair3_kernel variant {v:#x}", lambda: K.attn(s, qkv, H, v), aflops, "flop")
+for v in (0x20, 0x100, 0x30):
+    probe(f"attn_pair_kernel variant {v:#x}", lambda: K.attn(s, qkv, H, v), aflops, "flop")
 x = qkv[:S].reshape(1, S, 3, H, 128)
 q, k, v_ = (x[:, :, i].transpose(1, 2).contiguous() for i in range(3))
 probe("torch SDPA (cuDNN / flash)", lambda: F.scaled_dot_product_attention(q, k, v_), aflops, "flop")

@@ -49,12 +49,11 @@ def option(key):
 
 # (name, setter, default, values)
 KNOBS = [
-    ("attention variant (set_option 1)", option(1), 0, [0x1000, 0x1030, 0x1040, 0x1024]),
-    ("programmatic dependent launch (tune 7)", tune(7), 0, [1]),
+    ("attention variant (set_option 1)", option(1), 0, [0x100, 0x30, 0x40, 0x28]),
+    ("programmatic dependent launch (tune 7)", tune(7), 1, [0]),
     ("GEMM raster band, m-units (tune 5)", tune(5), 0, [4, 8, 16, 32]),
     ("GEMM TMA L2 hints (tune 2)", tune(2), 0, [1, 2, 3]),
     ("GEMM split-K tail (tune 4)", tune(4), 1, [0, 9]),
-    ("adaLN in the GEMM tail (set_option 3)", option(3), 0, [1]),
     ("adaLN kernel form (tune 3)", tune(3), 1, [0]),
 ]
 
