@@ -107,6 +107,47 @@ def test_fused_peer_exchange_two_text_lengths_same_padding():
         b.free()
 
 
+def test_starved_barrier_surfaces_through_the_abi():
+    """VERDICT r1 / ADVICE: a peer barrier that times out must not let the forward continue silently.  One emulated rank of a
+    2-rank group never arrives: the barrier kernel gives up after ~2 s and raises the sticky flag (mapped host memory), the
+    next qie_forward returns QIE_ECUDA with a message, the Python wrapper's check raises, and dissolving the group
+    (qie_set_peers(NULL)) reports the failure once more and re-arms the flag."""
+    import ctypes as C
+    dev = torch.device("cuda", 0)
+    model = _tiny_model(dev, heads=4)
+    lib = L.lib()
+    assert lib.qie_peer_barrier_timeouts() == 0
+    plan = qie_b200.make_shard_plan(376, 37, 2, 0)
+    bufs = [qie_b200.PeerRankBuffers(1 << 20, 1 << 20, 1 << 16, 1 << 20) for _ in range(2)]
+    peers = qie_b200.make_peers(plan, 1, [b.gather for b in bufs], [b.ws for b in bufs], [b.vel for b in bufs], [b.flags for b in bufs],
+                                [b.mod for b in bufs])
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 376, 64, generator=g).bfloat16().to(dev)
+    cond = (torch.randn(1, 37, 128, generator=g) * 3).bfloat16().to(dev)
+    ts = torch.tensor([0.25], device=dev)
+    shapes = [[(1, 16, 16), (1, 12, 10)]]
+    good = model(x, cond, None, ts, shapes, [37], return_dict=False)[0]
+    try:
+        L.check(lib.qie_set_peers(model._handle, C.byref(peers), L.cur_stream()))
+        L.check(lib.qie_peer_barrier(model._handle, L.cur_stream()))      # rank 1 never arrives
+        torch.cuda.synchronize()                                           # ~2 s: the kernel gives up instead of hanging
+        assert lib.qie_peer_barrier_timeouts() == 1
+        with pytest.raises(qie_b200.QieError, match="timed out"):          # the plain forward refuses to run on this process now
+            model(x, cond, None, ts, shapes, [37], return_dict=False)
+        sp = qie_b200.UlyssesTransformer.__new__(qie_b200.UlyssesTransformer)
+        with pytest.raises(qie_b200.QieError, match="timed out"):
+            sp.check_barriers()
+    finally:
+        rc = lib.qie_set_peers(model._handle, None, None)
+    assert rc == -3 and b"timed out" in lib.qie_last_error()               # QIE_ECUDA, reported once ...
+    assert lib.qie_peer_barrier_timeouts() == 0 and lib.qie_set_peers(model._handle, None, None) == 0      # ... and re-armed
+    again = model(x, cond, None, ts, shapes, [37], return_dict=False)[0]
+    assert torch.equal(again, good)
+    torch.cuda.synchronize()
+    for b in bufs:
+        b.free()
+
+
 def _worker(rank, world, q):
     import sys
     from pathlib import Path
