@@ -452,7 +452,7 @@ static int launch_attn(const CUtensorMap& tm, const AttnDev& p, dim3 grid, cudaS
 // Issue order of the leader: S(0) | S(1) PV(0) | S(2) PV(1) | ...
 // =====================================================================================================================
 constexpr int AT5_KSTAGES = 3, AT5_VSTAGES = 2;
-constexpr int AT5_THREADS = 384;              // warps 0-7 softmax (two warpgroups), warp 8 TMA, warp 9 MMA issuer, 10-11 idle
+constexpr int AT5_THREADS = 384;              // warps 0-7 softmax (two warpgroups), warp 8 TMA, warp 9 S issuer, warp 10 PV issuer, 11 idle
 constexpr int AT5_STAGE_BYTES = 32 * 1024;     // K: my 128 kv rows x 128 dims; V: 256 kv rows x my 64 dims
 constexpr int AT5_SMEM = ATT_TILE_BYTES + (AT5_KSTAGES + AT5_VSTAGES) * AT5_STAGE_BYTES + 2048 + 1024 + 512 + 1024;
 
@@ -548,16 +548,21 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
             }
         }
       } else if (warp == 9) {
-        // The issuer has the highest warp id of its scheduler: the arbiter serves it first, so an MMA is issued as soon
-        // as its operands are ready even while two softmax warps keep that scheduler busy.
+        // Two issuer threads on two schedulers (warps 9 and 10, each the highest warp id of its scheduler, which the arbiter
+        // serves first): issuing a tcgen05.mma costs the thread ~75-100 cycles here (descriptor arithmetic + the instruction
+        // itself, competing for issue slots with two busy softmax warps), so ONE thread needs ~2000 cycles per KV tile for the 8 S
+        // and 16 PV instructions — as long as the whole softmax chain (round-2 timing experiments, profiles/r02_attention.md).
+        // S and PV touch disjoint TMEM columns and are ordered against the softmax by s_free / p_full / pv_done, not against
+        // each other, so the two streams may interleave freely on the (in-order) tensor pipe.
         if (lane == 0 && cta_rank == 0) {
-            // ================= MMA issuer (leader) =================
+            // ================= S issuer (leader) =================
             constexpr uint32_t IDESC_S = umma_idesc_bf16(256, 256, false);
-            constexpr uint32_t IDESC_O = umma_idesc_bf16(256, 128, true);   // B = V is MN-major
-            int ks = 0, vs = 0;
-            uint32_t kph = 0, vph = 0;
+            int ks = 0;
+            uint32_t kph = 0;
             const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(sQ));
-            auto issue_S = [&]() {
+            mbar_wait(q_full, 0);
+            for (int j = 0; j < n_kv; ++j) {
+                if (j > 0) mbar_wait(s_free, (j - 1) & 1);   // S(j-1) is in registers in both CTAs
                 mbar_wait(&k_full[ks], kph);
                 tc_fence_after();
                 const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(sK + ks * AT5_STAGE_BYTES));
@@ -569,16 +574,15 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
                 umma_commit_cg2(s_full, 3);
                 umma_commit_cg2(&k_empty[ks], 3);
                 if (++ks == AT5_KSTAGES) { ks = 0; kph ^= 1; }
-            };
-            mbar_wait(q_full, 0);
-            tc_fence_after();
-            issue_S();
+            }
+        }
+      } else if (warp == 10) {
+        if (lane == 0 && cta_rank == 0) {
+            // ================= PV issuer (leader) =================
+            constexpr uint32_t IDESC_O = umma_idesc_bf16(256, 128, true);   // B = V is MN-major
+            int vs = 0;
+            uint32_t vph = 0;
             for (int j = 0; j < n_kv; ++j) {
-                if (j + 1 < n_kv) {
-                    mbar_wait(s_free, j & 1);                // S(j) is in registers in both CTAs
-                    tc_fence_after();
-                    issue_S();
-                }
                 mbar_wait(&v_full[vs], vph);
                 mbar_wait(p_full, j & 1);                    // P(j) is in TMEM in both CTAs, O rescaled
                 tc_fence_after();
