@@ -454,9 +454,9 @@ static int launch_attn(const CUtensorMap& tm, const AttnDev& p, dim3 grid, cudaS
 constexpr int AT5_KSTAGES = 3, AT5_VSTAGES = 2;
 constexpr int AT5_THREADS = 384;              // warps 0-7 softmax (two warpgroups), warp 8 TMA, warp 9 S issuer, warp 10 PV issuer, 11 idle
 constexpr int AT5_STAGE_BYTES = 32 * 1024;     // K: my 128 kv rows x 128 dims; V: 256 kv rows x my 64 dims
-constexpr int AT5_SMEM = ATT_TILE_BYTES + (AT5_KSTAGES + AT5_VSTAGES) * AT5_STAGE_BYTES + 2048 + 1024 + 8192 + 512 + 1024;
+constexpr int AT5_SMEM = ATT_TILE_BYTES + (AT5_KSTAGES + AT5_VSTAGES) * AT5_STAGE_BYTES + 2048 + 1024 + 512 + 1024;
 
-template <int POLY, int XCH>
+template <int POLY>
 __global__ void __launch_bounds__(AT5_THREADS, 1)
 attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
     extern __shared__ uint8_t smem_raw[];
@@ -466,8 +466,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
     uint8_t* sV = sK + AT5_KSTAGES * AT5_STAGE_BYTES;         // [V stages][256 kv rows x 128 B (my 64 dims)]
     float* xm = reinterpret_cast<float*>(sV + AT5_VSTAGES * AT5_STAGE_BYTES);   // [2 parities][2 WGs][128 rows] tile max
     float* xl = xm + 512;                                                        // [2 WGs][128 rows] partial row sums
-    unsigned long long* xs = reinterpret_cast<unsigned long long*>(xl + 256);    // XCH: [2 WGs][4 slots][128 rows] {tile, max} words
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 1024);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xl + 256);
     uint64_t* q_full = bars;                       // leader
     uint64_t* k_full = bars + 1;                   // [K stages] leader
     uint64_t* k_empty = k_full + AT5_KSTAGES;      // both
@@ -616,19 +615,6 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
             return t128 < n128 ? (p.tile_valid ? __ldg(p.tile_valid + t128) : kv_valid_rows(p.seq, t128)) : 0;
         };
         int nv_next = valid_rows(wg);
-        // XCH = 1, delayed reference: from the second tile on the softmax reference of tile j is built from the maxima of the tiles
-        // BEFORE j (my own, kept in a register, and my partner's, read from its {tile, max} slot in shared memory — published a
-        // whole tile earlier, so the read never waits in practice and there is no barrier on the critical path).  Both partner
-        // threads see the same values and take the same lazy-rescale decision.  Scores of tile j may exceed the reference
-        // (P > 1 is fine in fp32 / bf16: O, l and the reference move together one tile later); only a jump of more than 2^64 over
-        // every earlier tile is clamped (never with RMS-normed q, k: |q.k| / sqrt(128) <= 16.3 in log2 units).
-        volatile unsigned long long* my_slots = xs + (wg * 4) * 128 + r;
-        volatile unsigned long long* peer_slots = xs + ((wg ^ 1) * 4) * 128 + r;
-        if (XCH) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) my_slots[i * 128] = 0xFFFFFFFF00000000ull;      // tile tag -1
-        }
-        float m_loc_prev = -INFINITY;
         for (int j = 0; j < n_kv; ++j) {
             const int nv = nv_next;
             mbar_wait(s_full, j & 1);
@@ -640,16 +626,6 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
                 tmem_ld32(tS + ch * 32, dst);
             }
             nv_next = valid_rows(2 * (j + 1) + wg);          // its constant-bank / global latency hides under the TMEM load
-            float m_par_prev = -INFINITY;
-            if (XCH && j > 0) {
-                // before s_free(j): my partner can only publish tile j+1 (same slot parity as j-3, not j-1: 4 slots) after S(j+1),
-                // which needs my s_free(j) — so this read can never see a newer tile in the slot it looks at
-                unsigned long long v;
-                int spins = 0;
-                do { v = peer_slots[((j - 1) & 3) * 128]; } while ((int)(v >> 32) != j - 1 && ++spins < (1 << 24));
-                if ((int)(v >> 32) != j - 1) __trap();           // my partner never published: fail loudly, never hang
-                m_par_prev = __uint_as_float((unsigned)v);
-            }
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
@@ -672,19 +648,10 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
                 for (int i = 0; i < 128; ++i)
                     if (i < nv) m0 = fmaxf(m0, __uint_as_float(s[i]));
             }
-            float mx;
-            bool guard = false;
-            const float m_loc = fmaxf(m0, m1) * c;
-            if (XCH) my_slots[(j & 3) * 128] = ((unsigned long long)(unsigned)j << 32) | __float_as_uint(m_loc);
-            if (!XCH || j == 0) {
-                float* xmj = xm + (j & 1) * 256;
-                xmj[wg * 128 + r] = m_loc;
-                named_bar_sync(1 + quad, 64);                 // only my partner warp (same rows, other warpgroup)
-                mx = fmaxf(m_loc, xmj[(wg ^ 1) * 128 + r]);
-            } else {
-                mx = fmaxf(m_loc_prev, m_par_prev);           // the whole tile j-1; tile j itself is not in the reference yet
-            }
-            m_loc_prev = m_loc;
+            float* xmj = xm + (j & 1) * 256;
+            xmj[wg * 128 + r] = fmaxf(m0, m1);
+            named_bar_sync(1 + quad, 64);                 // only my partner warp (same rows, other warpgroup)
+            const float mx = fmaxf(fmaxf(m0, m1), xmj[(wg ^ 1) * 128 + r]) * c;
             float alpha = 1.f;
             const bool grow = mx > m_ref + 8.0f;      // identical decision in both warpgroups (same row, same inputs)
             if (grow) {
@@ -693,9 +660,8 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
                 l2 = fma2(l2, pk2(alpha, alpha), pk2(0.f, 0.f));
             }
             const uint64_t nm2 = pk2(-m_ref, -m_ref);
-            if (XCH) guard = m_loc > m_ref + 64.f;
             // ---- exponentials in place: s[i/2] <- bf16x2(p_i, p_i+1) ----
-            if (nv == ATT_TILE && !guard) {
+            if (nv == ATT_TILE) {
 #pragma unroll
                 for (int i = 0; i < 128; i += 2) {
                     const uint64_t X = fma2(pk2u(s[i], s[i + 1]), c2, nm2);
@@ -727,7 +693,6 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
                 for (int i = 0; i < 128; i += 2) {
                     float x0, x1;
                     upk2(fma2(pk2u(s[i], s[i + 1]), c2, nm2), x0, x1);
-                    if (XCH) { x0 = fminf(x0, 64.f); x1 = fminf(x1, 64.f); }
                     const float e0 = i < nv ? fast_exp2(x0) : 0.f, e1 = i + 1 < nv ? fast_exp2(x1) : 0.f;
                     l2 = add2(l2, pk2(e0, e1));
                     s[i >> 1] = pack_bf16(e0, e1);
@@ -818,9 +783,9 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
     }
 }
 
-template <int POLY, int XCH = 0>
+template <int POLY>
 static int launch_attn_pair(const CUtensorMap& tm128, const AttnDev& p, dim3 grid, cudaStream_t st) {
-    QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(attn_pair_kernel<POLY, XCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT5_SMEM));
+    QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(attn_pair_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT5_SMEM));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(AT5_THREADS);
@@ -829,7 +794,7 @@ static int launch_attn_pair(const CUtensorMap& tm128, const AttnDev& p, dim3 gri
     cudaLaunchAttribute attr[2];
     cfg.attrs = attr;
     cfg.numAttrs = launch_attrs(attr, 2);
-    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_pair_kernel<POLY, XCH>, tm128, p));
+    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_pair_kernel<POLY>, tm128, p));
     QIE_LAUNCH_OK("attn_pair_kernel");
     return QIE_OK;
 }
@@ -885,8 +850,8 @@ int attn_fwd_peers(const void* qkv_gathered, void* const* peer_out_dev, const qi
 static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int* tile_valid, int num_heads, int variant,
                        void* stream, const AttnScatter* sc) {
     if (variant == 0) variant = 0x20;
-    const int poly = (variant >> 4) & 15, single = (variant >> 3) & 1, xch = (variant >> 9) & 1;
-    QIE_REQUIRE((variant & ~0x3F8) == 0 && (poly == 0 || poly == 2 || poly == 3 || poly == 4) && !(xch && single), QIE_EINVAL,
+    const int poly = (variant >> 4) & 15, single = (variant >> 3) & 1;
+    QIE_REQUIRE((variant & ~0x1F8) == 0 && (poly == 0 || poly == 2 || poly == 3 || poly == 4), QIE_EINVAL,
                 "qie_attn_fwd: bad variant 0x%x", variant);
     const int rpb = seq->img_pad + seq->txt_pad;
     const int D = num_heads * 128;
@@ -928,14 +893,6 @@ static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int
         }
     }
     grid.x *= 2;     // a cluster of two CTAs per 256 query rows
-    if (xch) {       // bit 9 (0x200): delayed softmax reference, no warpgroup barrier in the loop
-        switch (poly) {
-            case 0: return launch_attn_pair<0, 1>(tm, p, grid, st);
-            case 2: return launch_attn_pair<2, 1>(tm, p, grid, st);
-            case 3: return launch_attn_pair<3, 1>(tm, p, grid, st);
-            case 4: return launch_attn_pair<4, 1>(tm, p, grid, st);
-        }
-    }
     switch (poly) {
         case 0: return launch_attn_pair<0>(tm, p, grid, st);
         case 2: return launch_attn_pair<2>(tm, p, grid, st);

@@ -306,7 +306,7 @@ def test_gemm_fp8(cta_group):
 # ------------------------------------------------------------------ attention
 @pytest.mark.parametrize("B,img,txt,H", [(1, 256, 128, 2), (1, 384, 128, 1), (2, 200, 19, 2), (1, 1024, 219, 3),
                                          (2, 520, 130, 2), (1, 1500, 300, 2)])
-@pytest.mark.parametrize("variant", [0, 0x100, 0x20, 0x30, 0x40, 0x108, 0x28, 0x220, 0x300, 0x230])     # CTA-pair kernel / 0x8: single-CTA fallback / 0x200: delayed softmax reference
+@pytest.mark.parametrize("variant", [0, 0x100, 0x20, 0x30, 0x40, 0x108, 0x28])     # CTA-pair kernel (default) / 0x8: single-CTA fallback
 def test_attention(B, img, txt, H, variant):
     s = K.seq(B, img, txt)
     D = H * 128
@@ -337,11 +337,11 @@ def test_attention_large_scores_lazy_rescale():
     assert K.rel_err(got, ref) <= 2 ** -6
 
 
-@pytest.mark.parametrize("variant,jump", [(0, 3.0), (0, 40.0), (0, 400.0), (0x28, 3.0), (0x28, 40.0), (0x220, 3.0), (0x220, 8.0)])
+@pytest.mark.parametrize("variant", [0, 0x28])
+@pytest.mark.parametrize("jump", [3.0, 40.0, 400.0])
 def test_attention_score_jumps_between_tiles(variant, jump):
-    """Keys whose scale jumps from one KV tile to the next: the lazy rescale path of both kernels.  The delayed-reference
-    build (0x200) is exact as long as no score exceeds every EARLIER tile's maximum by more than 2^64 (the forward only selects
-    it when the QK-norm weights bound the scores, see qie_forward), so it is exercised with jumps inside that range."""
+    """Keys whose scale jumps from one KV tile to the next: the lazy rescale path of both kernels (a jump of 400 puts the scores
+    of the later tiles hundreds of log2 units above every earlier one)."""
     s = K.seq(1, 768, 128)
     H, D = 1, 128
     qkv = randn(K.rows(s), 3 * D, seed=92, dtype=torch.bfloat16)
