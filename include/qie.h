@@ -18,7 +18,7 @@
  *   - threading: a handle (its timestep / modulation buffers) and a workspace serve ONE forward at a time; concurrent
  *     forwards (cond / uncond on two streams, README.md:127-128) take one handle + workspace per stream.  Kernel-internal
  *     scratch (row counters, split-K partials) is kept per (device, stream), so launches on different streams never share
- *     mutable state; at most 8 distinct streams per device are served (QIE_ESTATE beyond).
+ *     mutable state; at most 16 distinct streams per device are served (QIE_ESTATE beyond).
  *   - sm_100a only: on any other device qie_create returns QIE_EARCH.  There is no CPU path.
  *
  * Joint sequence layout used by all per-token entry points ("qie_seq"):

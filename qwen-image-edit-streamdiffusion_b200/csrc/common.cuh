@@ -56,7 +56,7 @@ int peer_sticky_error(bool clear = false);
 // device come from a fixed pool allocated by the first qie_create on that device, so handing one to a new stream allocates
 // nothing (qie_forward stays CUDA-graph capturable); the pool is exhausted after QIE_SCRATCH_SETS distinct streams per device.
 constexpr int SPLIT_SCRATCH_TILES = 96;      // split-K parts of 256 x 256 fp32 per set (24 MB)
-constexpr int QIE_SCRATCH_SETS = 8;
+constexpr int QIE_SCRATCH_SETS = 16;
 struct StreamScratch {
     int* ln_counters;        // [2]  next row, warps that left
     float* split_scratch;    // [SPLIT_SCRATCH_TILES][256][256]

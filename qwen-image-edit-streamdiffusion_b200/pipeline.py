@@ -42,10 +42,23 @@ def cfg_euler_step(latents: torch.Tensor, v_cond: torch.Tensor, v_uncond: Option
     return latents
 
 
+_TS_CACHE: dict = {}
+
+
 def model_timestep(sigma: float, batch: int, device) -> torch.Tensor:
-    """Pipeline rounding chain: t = 1000*sigma is cast to the latents dtype (bf16) before /1000."""
-    t = torch.tensor([sigma * 1000.0], dtype=torch.float32).to(torch.bfloat16)
-    return (t / 1000).expand(batch).to(device)
+    """Pipeline rounding chain: t = 1000*sigma is cast to the latents dtype (bf16) before /1000.
+    The device copy of a (sigma, batch, device) triple is made once (a fixed schedule re-uses 2-8 values for every frame): the
+    per-step pageable host-to-device copy of one scalar would otherwise block the host once per denoise step."""
+    dev = torch.device(device)
+    key = (float(sigma), int(batch), dev.type, dev.index)
+    t = _TS_CACHE.get(key)
+    if t is None:
+        h = torch.tensor([sigma * 1000.0], dtype=torch.float32).to(torch.bfloat16)
+        t = (h / 1000).expand(batch).contiguous().to(dev)
+        if len(_TS_CACHE) > 256:
+            _TS_CACHE.clear()
+        _TS_CACHE[key] = t
+    return t
 
 
 def pack_latents(z: torch.Tensor, mean: Optional[torch.Tensor] = None, std: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -96,10 +109,9 @@ def run_denoise(transformer, latents: torch.Tensor, image_latents: torch.Tensor,
     image_latents = image_latents.to(torch.bfloat16)
     for i in range(begin_index, num_inference_steps):
         x = torch.cat([latents, image_latents], dim=1)
-        ts_host = model_timestep(float(sig[i]), B, "cpu")
-        ts = ts_host.to(latents.device)
+        ts = model_timestep(float(sig[i]), B, latents.device)
         # use_caches: the transformer holds cache_schedule()/cache_prompt("cond"/"uncond") entries (exact)
-        kw = dict(timestep_values=[float(ts_host[0])], cached_prompt="cond") if use_caches else {}
+        kw = dict(timestep_values=[float(model_timestep(float(sig[i]), 1, "cpu")[0])], cached_prompt="cond") if use_caches else {}
         v = transformer(hidden_states=x, timestep=ts, encoder_hidden_states=prompt_embeds, img_shapes=img_shapes,
                         txt_seq_lens=[prompt_embeds.shape[1]] * B, return_dict=False, **kw)[0]
         u = None

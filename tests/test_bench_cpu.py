@@ -82,3 +82,14 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = _run_bench(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                    {"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_strong_mode_partition_by_world_size():
+    """the strong-scaling leg of bench.py: which partition ONE true-CFG frame takes at each GPU count (north star: CFG pair at 2,
+    CFG pair x Ulysses at 4 / 8; the sequence-parallel degree must divide the 24 heads)"""
+    import bench
+    assert bench.strong_mode(1) == ("single", 1, 1)
+    assert bench.strong_mode(2) == ("cfgpair", 2, 1)
+    assert bench.strong_mode(4)[1:] == (2, 2) and bench.strong_mode(8)[1:] == (2, 4) and "fused-ulysses4" in bench.strong_mode(8)[0]
+    assert bench.strong_mode(6)[1:] == (2, 3) and bench.strong_mode(3)[1:] == (1, 3)
+    assert bench.strong_mode(10)[0] is None and bench.strong_mode(7)[0] is None      # 5 and 7 do not divide 24 heads
