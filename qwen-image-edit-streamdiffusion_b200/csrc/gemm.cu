@@ -51,6 +51,7 @@ struct GemmDev {
     // split-K tail: the last `tail_tiles` tiles (the partial wave of the persistent schedule) are cut into `tail_split` K
     // ranges, one work item each, so the tail wave costs 1/tail_split of a tile; partial accumulators meet in `scratch`
     int tail_tiles, tail_split, tail_dbg;
+    int tail_nsplit;         // 1: the tail tiles are cut along N instead (two BN/2-column halves, no reduction; tail_split == 2)
     int group_m;             // m-units per raster band (qie_tune key 5; 0 = GEMM_GROUP_M)
     float* scratch;          // [tail_tiles][tail_split][CG*128 rows][BN] fp32
     int* tickets;            // [tail_tiles][8 row slices]
@@ -112,13 +113,19 @@ __device__ __forceinline__ void tile_to_mn(int tile, int m_units, int n_blocks, 
 // is `tail_split` items, each covering one K range.
 struct WorkItem {
     int tile, part, kb0, kb1;
-    bool split;
+    bool split;      // K range of a tail tile: partial sums meet in scratch
+    bool nhalf;      // column half `part` of a tail tile: an independent BN/2-wide tile
 };
-__device__ __forceinline__ WorkItem decode_item(int item, int num_tiles, int tail_tiles, int tail_split, int k_blocks) {
+__device__ __forceinline__ WorkItem decode_item(int item, int num_tiles, int tail_tiles, int tail_split, int k_blocks,
+                                                int tail_nsplit) {
     WorkItem w;
     const int whole = num_tiles - tail_tiles;
+    w.nhalf = false;
     if (item < whole) {
         w.tile = item; w.part = 0; w.kb0 = 0; w.kb1 = k_blocks; w.split = false;
+    } else if (tail_nsplit) {
+        const int i = item - whole;
+        w.tile = whole + (i >> 1); w.part = i & 1; w.kb0 = 0; w.kb1 = k_blocks; w.split = false; w.nhalf = true;
     } else {
         const int i = item - whole;
         w.tile = whole + i / tail_split;
@@ -141,6 +148,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr int BK = FP8 ? 128 : 64;           // elements per k-block
     constexpr uint32_t IDESC = QT == 2 ? umma_idesc_s8(GEMM_BM * CG, BN)
                                : QT == 1 ? umma_idesc_e4m3(GEMM_BM * CG, BN) : umma_idesc_bf16(GEMM_BM * CG, BN);
+    constexpr int BNH = BN / 2;                  // column half of a tail tile (N-split tail)
+    constexpr uint32_t IDESC_H = QT == 2 ? umma_idesc_s8(GEMM_BM * CG, BNH)
+                                 : QT == 1 ? umma_idesc_e4m3(GEMM_BM * CG, BNH) : umma_idesc_bf16(GEMM_BM * CG, BNH);
     auto accf = [](uint32_t r) -> float { return QT == 2 ? (float)(int)r : __uint_as_float(r); };   // int32 accumulators for kind::i8
 
     extern __shared__ uint8_t smem_raw[];
@@ -200,7 +210,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint64_t pol_w = l2_policy_evict_last(), pol_a = l2_policy_evict_first();
             const int hints = p.l2_hints;
             for (int item = tile0; item < num_items; item += tile_step) {
-                const WorkItem wi = decode_item(item, num_tiles, p.tail_tiles, p.tail_split, k_blocks);
+                const WorkItem wi = decode_item(item, num_tiles, p.tail_tiles, p.tail_split, k_blocks, p.tail_nsplit);
                 int mu, nb;
                 tile_to_mn(wi.tile, m_units, p.n_blocks, mu, nb, p.group_m);
                 const MUnit m = decode_munit<CG>(p, mu);
@@ -210,7 +220,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int a_row = p.a_compact ? m.b * seg_pad + ti * GEMM_BM
                                               : m.b * rpb + (m.s ? p.seq.img_pad : 0) + ti * GEMM_BM;
                 const CUtensorMap* tmB = m.s ? &tmB1 : &tmB0;
-                const int b_row = nb * BN + cta_rank * (BN / CG);
+                // column half of a tail tile: the pair's BN/2-wide B operand is BN/2/CG rows per CTA; the box stays BN/CG rows (the
+                // rows behind the ones the MMA reads are loaded and ignored: tail items only)
+                const int b_row = wi.nhalf ? nb * BN + wi.part * BNH + cta_rank * (BNH / CG) : nb * BN + cta_rank * (BN / CG);
                 for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * S::STAGE_BYTES;
@@ -242,7 +254,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int item = tile0; item < num_items; item += tile_step) {
-                const WorkItem wi = decode_item(item, num_tiles, p.tail_tiles, p.tail_split, k_blocks);
+                const WorkItem wi = decode_item(item, num_tiles, p.tail_tiles, p.tail_split, k_blocks, p.tail_nsplit);
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -255,7 +267,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {   // 4 x 32 B along the swizzled 128 B row
                         const uint32_t accum = ((kb - wi.kb0) | k) ? 1u : 0u;
-                        umma_ss<QT, CG>(d_tmem, da + 2 * k, db + 2 * k, IDESC, accum);
+                        umma_ss<QT, CG>(d_tmem, da + 2 * k, db + 2 * k, wi.nhalf ? IDESC_H : IDESC, accum);
                     }
                     // frees the smem slot (in both CTAs of a pair) when these MMAs retire
                     if constexpr (CG == 2) umma_commit_cg2(&empty_bar[stage], 3);
@@ -286,7 +298,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int item = tile0; item < num_items; item += tile_step) {
-            const WorkItem wi = decode_item(item, num_tiles, p.tail_tiles, p.tail_split, k_blocks);
+            const WorkItem wi = decode_item(item, num_tiles, p.tail_tiles, p.tail_split, k_blocks, p.tail_nsplit);
             int mu, nb;
             tile_to_mn(wi.tile, m_units, p.n_blocks, mu, nb, p.group_m);
             const MUnit m = decode_munit<CG>(p, mu);
@@ -300,6 +312,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const long long orow0 = p.out_compact ? (long long)m.b * seg_pad + local0 : jrow0;
             const long long arow0 = p.a_compact ? (long long)m.b * seg_pad + local0 : jrow0;
             const float* bias = p.bias[m.s];
+            const int n_base = nb * BN + (wi.nhalf ? wi.part * BNH : 0);      // first output column of this item
+            const int n_chunks = wi.nhalf ? BNH / 32 : BN / 32;               // 32-column chunks of this item
 
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
@@ -317,9 +331,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 for (int i = 0; i < 32; i += 4) {
                     float4 f = make_float4(accf(r[i]), accf(r[i + 1]), accf(r[i + 2]), accf(r[i + 3]));
                     if (add_bias_first) {
-                        const float4 bv = *reinterpret_cast<const float4*>(bias + nb * BN + c * 32 + i);
+                        const float4 bv = *reinterpret_cast<const float4*>(bias + n_base + c * 32 + i);
                         if constexpr (FP8) {
-                            const float4 ws = *reinterpret_cast<const float4*>(p.w_scale[m.s] + nb * BN + c * 32 + i);
+                            const float4 ws = *reinterpret_cast<const float4*>(p.w_scale[m.s] + n_base + c * 32 + i);
                             f.x *= as_row * ws.x; f.y *= as_row * ws.y; f.z *= as_row * ws.z; f.w *= as_row * ws.w;
                         }
                         f.x = (f.x + bv.x) * row_scale; f.y = (f.y + bv.y) * row_scale;
@@ -414,11 +428,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             [[maybe_unused]] float rmax[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // q8_amax: max|out| of my 8 rows over this tile
             if (!dummy) {
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
-                    const int n0 = nb * BN + c * 32;
+                for (int c = 0; c < n_chunks; ++c) {
+                    const int n0 = n_base + c * 32;
                     int which = 2;
                     if constexpr (EPI == QIE_EPI_QKV_NORM_ROPE) {
-                        which = (nb * BN) / p.model_dim;                      // 0 q, 1 k, 2 v (D % BN == 0)
+                        which = n_base / p.model_dim;                         // 0 q, 1 k, 2 v (D % BN == 0)
                         if (which != 2 && (c & 3) == 0) {                     // first chunk of a head: row RMS over 128 cols
                             float ss = 0.f;
 #pragma unroll 1
@@ -428,10 +442,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                 tmem_ld_wait();
 #pragma unroll
                                 for (int i = 0; i < 32; i += 4) {
-                                    const float4 bv = *reinterpret_cast<const float4*>(bias + nb * BN + cc * 32 + i);
+                                    const float4 bv = *reinterpret_cast<const float4*>(bias + n_base + cc * 32 + i);
                                     float4 ws = make_float4(1.f, 1.f, 1.f, 1.f);
                                     if constexpr (FP8) {
-                                        ws = *reinterpret_cast<const float4*>(p.w_scale[m.s] + nb * BN + cc * 32 + i);
+                                        ws = *reinterpret_cast<const float4*>(p.w_scale[m.s] + n_base + cc * 32 + i);
                                         ws.x *= as_row; ws.y *= as_row; ws.z *= as_row; ws.w *= as_row;
                                     }
                                     const float a0 = accf(r[i]) * ws.x + bv.x;
@@ -632,7 +646,8 @@ int qie::g_pdl = 1;          // qie_tune(7, v): programmatic dependent launch of
                             // +0.5 % on one GPU at the power cap, more for the short kernels of the sequence-parallel shards)
 int g_gemm_l2_hints = 0;    // set through qie_tune(2, v)
 int g_gemm_group_m = 0;     // qie_tune(5, v): m-units per raster band, 0 = default
-int g_gemm_split_tail = 1;  // qie_tune(4, v): 0 off, 1 long-K tiles only / two ranges (default), 9 wherever a split fits
+int g_gemm_split_tail = 17; // qie_tune(4, v): bit 0 K split of the tail (long-K tiles, two ranges), bit 3 K split wherever it fits, bit 4 N split
+                            // of the tail where no K split applies (default 1 | 16), bit 5 N split takes precedence over the K split
 
 extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream) {
     QIE_REQUIRE(g && seq && g->a && g->out, QIE_EINVAL, "qie_gemm: null pointer");
@@ -743,7 +758,7 @@ extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream
     {
         const int units = sm_count() / cg;
         const int tail = tiles % units, kblocks = (g->K + bk - 1) / bk;
-        if (g_gemm_split_tail && cg == 2 && bn == 256 && tiles > units && tail > 0 && g->epilogue != QIE_EPI_QKV_NORM_ROPE &&
+        if ((g_gemm_split_tail & 9) && cg == 2 && bn == 256 && tiles > units && tail > 0 && g->epilogue != QIE_EPI_QKV_NORM_ROPE &&
             g->fp8 != 2) {
             // the gain is (1 - 1/split) of a tile, the reduction costs a fixed few microseconds: worth it for long-K tiles only
             // (mode 1), or everywhere (mode 8 | 1, experiments / tests)
@@ -768,6 +783,19 @@ extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream
                     p.tickets = tickets;
                 }
             }
+        }
+    }
+    // N-split tail (qie_tune key 4, bit 4): when the partial last wave holds at most half as many tiles as there are CTA pairs,
+    // every tail tile becomes two independent BN/2-column items — the tail wave then costs ~0.55 of a tile instead of 1 (the
+    // N = 128 MMA runs at ~90 % of the N = 256 rate) and needs no reduction, so it also serves the QKV epilogue (a half is
+    // exactly one 128-column head) and the short-K shapes the K split does not pay for
+    if ((g_gemm_split_tail & 16) && bn == 256 && (p.tail_tiles == 0 || (g_gemm_split_tail & 32))) {
+        const int units = sm_count() / cg, tail = tiles % units;
+        if (tail > 0 && 2 * tail <= units && g->N % 128 == 0) {
+            p.tail_tiles = tail;
+            p.tail_split = 2;
+            p.tail_nsplit = 1;
+            p.tail_dbg = 0;
         }
     }
 #define QIE_GEMM_DISPATCH(F8, CGV)                                                                         \

@@ -501,7 +501,7 @@ extern "C" int qie_tune(int key, int value) {
     if (key == 1 && value >= 0 && value <= 200 * 1024) { qie::g_ln_smem = value; return QIE_OK; }
     if (key == 2 && value >= 0 && value <= 3) { g_gemm_l2_hints = value; return QIE_OK; }
     if (key == 3 && (value == 0 || value == 1)) { qie::g_ln_variant = value; return QIE_OK; }
-    if (key == 4 && value >= 0 && value <= 15) { g_gemm_split_tail = value; return QIE_OK; }
+    if (key == 4 && value >= 0 && value <= 63) { g_gemm_split_tail = value; return QIE_OK; }
     if (key == 5 && value >= 0 && value <= 64) { g_gemm_group_m = value; return QIE_OK; }
     if (key == 7 && (value == 0 || value == 1)) { qie::g_pdl = value; return QIE_OK; }   // programmatic dependent launch
     ::qie::set_error("qie_tune: bad key/value %d/%d", key, value);

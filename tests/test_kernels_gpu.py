@@ -218,7 +218,7 @@ def test_gemm_split_k_tail(epi, img, txt, N, Kd):
                 K.gemm(s, a, w, b, out, K.L.EPI_BF16, cta_group=2)
             return out
         finally:
-            K.L.check(K.L.lib().qie_tune(4, 1))
+            K.L.check(K.L.lib().qie_tune(4, 17))                       # library default: K split of long-K tails, N split elsewhere
 
     split, again, whole = run(9), run(9), run(0)
     assert torch.equal(split, again)                                   # deterministic
@@ -234,6 +234,51 @@ def test_gemm_split_k_tail(epi, img, txt, N, Kd):
     assert K.rel_err(gi, ri) <= max(tol, 2e-6 * Kd ** 0.5) and K.rel_err(gt, rt) <= max(tol, 2e-6 * Kd ** 0.5)
     # same numbers as the un-split schedule up to the fp32 association of the K ranges
     assert K.rel_err(gi, wi_) <= (5e-6 if epi == "gate_resid" else 2 ** -7) and K.rel_err(gt, wt_) <= (5e-6 if epi == "gate_resid" else 2 ** -7)
+
+
+@pytest.mark.parametrize("epi", ["gate_resid", "gelu", "bf16", "qkv"])
+@pytest.mark.parametrize("img,txt,cta_group", [(8192, 256, 2), (2048, 64, 2), (512, 32, 1), (3000, 219, 2)])
+def test_gemm_n_split_tail_is_bit_identical(epi, img, txt, cta_group):
+    """N-split tail (csrc/gemm.cu, WorkItem::nhalf): when the partial last wave of the persistent schedule holds at most half as
+    many tiles as there are CTAs / CTA pairs, every tail tile is computed as two independent 128-column items (an N = 128 MMA
+    into the same accumulator stage, no reduction).  Every output element sees the same K order as in the whole-tile schedule,
+    so the result must be BIT-identical to it, for every epilogue incl. the per-head RMSNorm + RoPE one (a half = one head)."""
+    s = K.seq(1, img, txt)
+    N, Kd = 3072, 512
+    H = N // 3 // 128
+    a, w, b = _gemm_case(s, N, Kd, seed=77)
+    rows = K.rows(s)
+    gate = randn(1, 2, N, seed=78)
+    res0 = randn(rows, N, seed=79)
+    ang = randn(rows, 64, seed=80, scale=3)
+    rope = torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).contiguous()
+    nw = [[1 + randn(128, seed=81 + 2 * st + k, scale=0.1) for k in range(2)] for st in range(2)]
+    lib = K.L.lib()
+    prev = lib.qie_tune_get(4)
+
+    def run(mode):
+        K.L.check(lib.qie_tune(4, mode))
+        try:
+            if epi == "gate_resid":
+                out = res0.clone()
+                K.gemm(s, a, w, b, out, K.L.EPI_GATE_RESID_F32, gate=gate, gate_bstride=2 * N, gate_sstride=N, cta_group=cta_group)
+            elif epi == "qkv":
+                out = torch.empty(rows, N, dtype=torch.bfloat16, device=DEV)
+                K.gemm(s, a, w, b, out, K.L.EPI_QKV_NORM_ROPE, rope=rope, qk_norm_w=nw, cta_group=cta_group)
+            else:
+                out = torch.empty(rows, N, dtype=torch.bfloat16, device=DEV)
+                K.gemm(s, a, w, b, out, K.L.EPI_GELU_BF16 if epi == "gelu" else K.L.EPI_BF16, cta_group=cta_group)
+            return out
+        finally:
+            K.L.check(lib.qie_tune(4, prev))
+
+    whole, halves = run(0), run(48)          # 48 = N split of the tail, taking precedence over the K split
+    valid = torch.cat([torch.arange(s.img_pad, device=DEV) < s.img_rows, torch.arange(s.txt_pad, device=DEV) < s.txt_rows])
+    assert torch.equal(halves[valid], whole[valid])
+    if epi == "bf16":                        # and it is the right answer
+        ri, rt = _gemm_ref(s, a, w, b)
+        gi, gt = K.from_joint(s, halves.float())
+        assert K.rel_err(gi, ri) <= 2 ** -7 and K.rel_err(gt, rt) <= 2 ** -7
 
 
 def test_gemm_compact_single_stream():
