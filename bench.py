@@ -434,7 +434,7 @@ def run_ours(args):
             return qie_b200.run_denoise(runner, l, i, c, IMG_SHAPES, STEPS_PER_IMAGE, u, 4.0, use_caches=True)
         if layout is not None and layout.cfg_branches == 2:
             return qie_b200.run_denoise_parallel(runner, layout, l, i, c, u, shapes_b, STEPS_PER_IMAGE, 4.0)
-        return qie_b200.run_denoise(runner, l, i, c, shapes_b, STEPS_PER_IMAGE, u, 4.0)
+        return qie_b200.run_denoise(runner, l, i, c, shapes_b, STEPS_PER_IMAGE, u, 4.0, batched_cfg=args.batched_cfg)
 
     def step_resident():
         return denoise(lat, img_lat, cond, unc)
@@ -600,6 +600,8 @@ def main():
                     "epilogue stores into peer memory (NVLink) instead of NCCL all-to-alls")
     ap.add_argument("--batch", type=int, default=1, help="frames per forward on every rank (dp) / inside the group (other modes); "
                     "BASELINE configs[4] streams batches of 8")
+    ap.add_argument("--batched-cfg", action="store_true", help="with --cfg on one GPU: cond and uncond forward of a step as ONE forward "
+                    "of batch 2 (per-element text lengths), the reference's batched_cfg_pipeline.py (README.md:126)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (ONE true-CFG frame over all ranks)")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the bf16 PyTorch-eager GPU side baseline (N = 1)")

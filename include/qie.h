@@ -66,9 +66,13 @@ typedef struct qie_model_cfg {
 typedef struct qie_seq {
     int batch;
     int img_rows; /* valid image tokens per batch element */
-    int txt_rows; /* valid text tokens per batch element */
+    int txt_rows; /* valid text tokens per batch element: the MAXIMUM over the batch when the lengths differ */
     int img_pad;  /* img_rows rounded up to 128 */
     int txt_pad;  /* txt_rows rounded up to 128 */
+    int txt_rows_b[8]; /* valid text tokens of every batch element (1 .. txt_rows; qie_make_seq fills them with txt_rows).  Rows behind
+                        * them are padding for every kernel: masked keys in attention, zero rows elsewhere.  This is what lets the cond and
+                        * the uncond prompt of a true-CFG step (different lengths) share ONE forward — replaces the reference's
+                        * batched_cfg_pipeline.py (README.md:126) without letting pad tokens take part in attention */
 } qie_seq;
 
 /* weights of one QwenImageTransformerBlock; index [0] = image stream, [1] = text stream.
@@ -135,6 +139,9 @@ int qie_profile_read(qie_handle* h, double* ms, double* work, int* launches);
 int qie_profile_timeline(qie_handle* h, float* start_ms, float* dur_ms, int* cls, int max_n);
 /* host helper: pad a (img_rows, txt_rows) pair into the joint layout */
 int qie_make_seq(int batch, int img_rows, int txt_rows, qie_seq* out);
+/* ... with one text length per batch element (encoder_hidden_states is then [batch, max length, joint_dim], rows behind an
+ * element's length are ignored) */
+int qie_make_seq_ragged(int batch, int img_rows, const int* txt_rows_b_host, qie_seq* out);
 size_t qie_workspace_bytes(const qie_handle* h, const qie_seq* seq);
 
 /* replaces: QwenImageTransformer2DModel.forward(hidden_states, encoder_hidden_states, timestep,

@@ -25,7 +25,13 @@ class ModelCfg(C.Structure):
 
 class Seq(C.Structure):
     _fields_ = [("batch", C.c_int), ("img_rows", C.c_int), ("txt_rows", C.c_int),
-                ("img_pad", C.c_int), ("txt_pad", C.c_int)]
+                ("img_pad", C.c_int), ("txt_pad", C.c_int), ("txt_rows_b", C.c_int * 8)]
+
+    def __init__(self, batch=0, img_rows=0, txt_rows=0, img_pad=0, txt_pad=0, txt_rows_b=None):
+        """txt_rows_b: valid text rows of every batch element (default: txt_rows for all, as qie_make_seq fills them)"""
+        super().__init__(batch, img_rows, txt_rows, img_pad, txt_pad)
+        for b in range(min(batch, 8)):
+            self.txt_rows_b[b] = txt_rows if txt_rows_b is None else int(txt_rows_b[b])
 
     @property
     def rows_per_batch(self) -> int:
@@ -97,6 +103,7 @@ SYMBOLS = {
     "qie_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i)]),
     "qie_profile_timeline": (_i, [_vp, C.POINTER(_f), C.POINTER(_f), C.POINTER(_i), _i]),
     "qie_make_seq": (_i, [_i, _i, _i, C.POINTER(Seq)]),
+    "qie_make_seq_ragged": (_i, [_i, _i, C.POINTER(_i), C.POINTER(Seq)]),
     "qie_workspace_bytes": (C.c_size_t, [_vp, C.POINTER(Seq)]),
     "qie_forward": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_i), _i, C.POINTER(Seq), _vp, _vp, C.c_size_t, _i, _vp]),
     "qie_forward_phase": (_i, [_vp, _i, _i, _vp, _vp, _vp, C.POINTER(_i), _i, C.POINTER(Seq), C.POINTER(Sp), _vp, _vp,
@@ -174,6 +181,14 @@ def check(rc: int, what: str = "") -> None:
 def make_seq(batch: int, img_rows: int, txt_rows: int) -> Seq:
     s = Seq()
     check(lib().qie_make_seq(batch, img_rows, txt_rows, C.byref(s)), "qie_make_seq")
+    return s
+
+
+def make_seq_ragged(img_rows: int, txt_rows_b) -> Seq:
+    """one text length per batch element (the cond and the uncond prompt of a true-CFG step in ONE forward)"""
+    s = Seq()
+    arr = (C.c_int * len(txt_rows_b))(*[int(v) for v in txt_rows_b])
+    check(lib().qie_make_seq_ragged(len(txt_rows_b), img_rows, arr, C.byref(s)), "qie_make_seq_ragged")
     return s
 
 

@@ -199,6 +199,20 @@ extern "C" int qie_make_seq(int batch, int img_rows, int txt_rows, qie_seq* out)
     out->txt_rows = txt_rows;
     out->img_pad = (img_rows + 127) / 128 * 128;
     out->txt_pad = (txt_rows + 127) / 128 * 128;
+    for (int b = 0; b < 8; ++b) out->txt_rows_b[b] = b < batch ? txt_rows : 0;
+    return QIE_OK;
+}
+
+extern "C" int qie_make_seq_ragged(int batch, int img_rows, const int* txt_rows_b, qie_seq* out) {
+    QIE_REQUIRE(out && txt_rows_b && batch > 0 && batch <= 8, QIE_EINVAL, "qie_make_seq_ragged: bad argument");
+    int mx = 0;
+    for (int b = 0; b < batch; ++b) {
+        QIE_REQUIRE(txt_rows_b[b] > 0, QIE_ESHAPE, "qie_make_seq_ragged: batch element %d has %d text tokens", b, txt_rows_b[b]);
+        if (txt_rows_b[b] > mx) mx = txt_rows_b[b];
+    }
+    int rc = qie_make_seq(batch, img_rows, mx, out);
+    if (rc) return rc;
+    for (int b = 0; b < batch; ++b) out->txt_rows_b[b] = txt_rows_b[b];
     return QIE_OK;
 }
 
@@ -464,6 +478,16 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
     if (rc) return rc;
     QIE_REQUIRE(chk.img_pad == seq->img_pad && chk.txt_pad == seq->txt_pad, QIE_ESHAPE,
                 "qie_forward: seq padding must come from qie_make_seq");
+    bool ragged = false;
+    long long txt_valid_total = 0;
+    for (int b = 0; b < seq->batch; ++b) {
+        QIE_REQUIRE(seq->txt_rows_b[b] >= 1 && seq->txt_rows_b[b] <= seq->txt_rows, QIE_ESHAPE,
+                    "qie_forward: batch element %d has %d text tokens (1..%d; build the layout with qie_make_seq / qie_make_seq_ragged)",
+                    b, seq->txt_rows_b[b], seq->txt_rows);
+        ragged = ragged || seq->txt_rows_b[b] != seq->txt_rows;
+        txt_valid_total += seq->txt_rows_b[b];
+    }
+    QIE_REQUIRE(!ragged || !sp, QIE_ESHAPE, "qie_forward_phase: per-element text lengths are not supported in sequence-parallel shards");
     const Ws ws = carve(h, seq);
     QIE_REQUIRE(workspace_bytes >= ws.total, QIE_ENOMEM, "qie_forward: workspace %zu < required %zu", workspace_bytes,
                 ws.total);
@@ -492,9 +516,9 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
     const size_t rows = (size_t)B * rpb;
     const int fp8 = h->precision;   // 0 bf16, 1 e4m3 W8A8, 2 int8 W8A8
 
-    const double valid_rows = (double)B * (seq->img_rows + seq->txt_rows);
+    const double valid_rows = (double)B * seq->img_rows + (double)txt_valid_total;
     auto run_gemm = [&](qie_gemm_args& g) -> int {
-        const double mv = (double)B * (((g.streams & 1) ? seq->img_rows : 0) + ((g.streams & 2) ? seq->txt_rows : 0));
+        const double mv = ((g.streams & 1) ? (double)B * seq->img_rows : 0) + ((g.streams & 2) ? (double)txt_valid_total : 0);
         ProfScope ps(h, st, 0, 2.0 * mv * g.N * g.K);
         return qie_gemm(&g, seq, st);
     };
@@ -508,8 +532,9 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
             ProfScope ps(h, st, 1, 4.0 * S * S * 128.0 * hl * pr.batch);
             return attn_fwd_peers(pr.qkv_gather[pr.rank], h->d_peer_tab + 8, &pr, h->d_tile_valid, hl, D, st);
         }
-        const double S = seq->img_rows + seq->txt_rows;
-        ProfScope ps(h, st, 1, 4.0 * S * S * 128.0 * h->cfg.num_heads * B);
+        double ss = 0;
+        for (int b = 0; b < B; ++b) ss += ((double)seq->img_rows + seq->txt_rows_b[b]) * ((double)seq->img_rows + seq->txt_rows_b[b]);
+        ProfScope ps(h, st, 1, 4.0 * ss * 128.0 * h->cfg.num_heads);
         return qie_attn_fwd(qkv, attn, seq, h->cfg.num_heads, h->attn_variant, st);
     };
     if (use_peers && (phases & (QIE_PHASE_QKV | QIE_PHASE_ATTN | QIE_PHASE_END)))
@@ -617,10 +642,11 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
 
     // ---- stream embeddings -> fp32 residual in the joint layout ----
     if ((rc = qie_pack_rows(hidden, xin, B, seq->img_rows, seq->img_pad, h->cfg.in_channels, st))) return rc;
-    const bool prompt_cached = h->sel_prompt >= 0 && h->d_prompt[h->sel_prompt] && !sp &&
+    const bool prompt_cached = h->sel_prompt >= 0 && h->d_prompt[h->sel_prompt] && !sp && !ragged &&
                                h->prompt_rows[h->sel_prompt] == seq->txt_rows;
     if (!prompt_cached &&
-        (rc = qie_rmsnorm_pack(enc, h->w.txt_norm_w, xtxt, B, seq->txt_rows, seq->txt_pad, h->cfg.joint_dim, 1e-6f, st)))
+        (rc = rmsnorm_pack_ragged(enc, h->w.txt_norm_w, xtxt, B, seq->txt_rows_b, seq->txt_rows, seq->txt_pad, h->cfg.joint_dim, 1e-6f,
+                                  st)))
         return rc;
     {
         qie_gemm_args g{};

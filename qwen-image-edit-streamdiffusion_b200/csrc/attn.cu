@@ -54,10 +54,11 @@ struct AttnDev {
     int out_ld, head_off;
 };
 
-__device__ __forceinline__ int kv_valid_rows(const qie_seq& s, int j) {
+// valid rows of 128-row KV tile j of batch element b (0 for a text tile behind the element's own text length)
+__device__ __forceinline__ int kv_valid_rows(const qie_seq& s, int j, int b) {
     const int r0 = j * ATT_TILE;
     if (r0 < s.img_pad) return min(ATT_TILE, s.img_rows - r0);
-    return min(ATT_TILE, s.txt_rows - (r0 - s.img_pad));
+    return max(0, min(ATT_TILE, s.txt_rows_b[b] - (r0 - s.img_pad)));
 }
 
 // packed fp32x2 helpers (Blackwell FFMA2 / FADD2)
@@ -348,7 +349,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnDev p) {
             float m_ref = -INFINITY;
             uint64_t l2 = pk2(0.f, 0.f);
             for (int j = 0; j < n_kv; ++j) {
-                const int nv = p.tile_valid ? __ldg(p.tile_valid + j) : kv_valid_rows(p.seq, j);
+                const int nv = p.tile_valid ? __ldg(p.tile_valid + j) : kv_valid_rows(p.seq, j, b);
                 const bool full = nv == ATT_TILE;
                 mbar_wait(&s_full[t], j & 1);
                 tc_fence_after();
@@ -612,7 +613,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
         float m_ref = -INFINITY;
         uint64_t l2 = pk2(0.f, 0.f);
         auto valid_rows = [&](int t128) -> int {     // valid kv rows of my half of a 256-row tile
-            return t128 < n128 ? (p.tile_valid ? __ldg(p.tile_valid + t128) : kv_valid_rows(p.seq, t128)) : 0;
+            return t128 < n128 ? (p.tile_valid ? __ldg(p.tile_valid + t128) : kv_valid_rows(p.seq, t128, b)) : 0;
         };
         int nv_next = valid_rows(wg);
         for (int j = 0; j < n_kv; ++j) {

@@ -45,6 +45,8 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
                  uint32_t box_rows, uint32_t box_cols, int elt_bytes);
 
 int sm_count();
+int rmsnorm_pack_ragged(const void* x, const float* w, void* out, int batch, const int* n_b_host, int n_max, int n_pad, int D, float eps,
+                        void* stream);
 int quant_rows_amax(const void* x, const float* amax, void* q, float* scale, long long rows, int K, int qmode, void* stream);
 int gemv_strided(const float* x, const void* w, const float* bias, float* y, int batch, long long N, int K, int act,
                  long long y_bstride, void* stream);

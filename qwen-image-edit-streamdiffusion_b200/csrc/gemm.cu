@@ -303,7 +303,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tile_to_mn(wi.tile, m_units, p.n_blocks, mu, nb, p.group_m);
             const MUnit m = decode_munit<CG>(p, mu);
             const int seg_pad = m.s ? p.seq.txt_pad : p.seq.img_pad;
-            const int seg_rows = m.s ? p.seq.txt_rows : p.seq.img_rows;
+            const int seg_rows = m.s ? p.seq.txt_rows_b[m.b] : p.seq.img_rows;
             const int ti = m.ti + cta_rank;
             const bool dummy = ti * GEMM_BM >= seg_pad;                       // peer half of an odd last unit: nothing to store
             const int local0 = ti * GEMM_BM + quad * 32;                      // first row of this warp inside the stream

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ x
     const int b = (int)(row / rpb), r = (int)(row % rpb);
     const int stream = r >= seq.img_pad ? 1 : 0;
     const int local = stream ? r - seq.img_pad : r;
-    const bool valid = local < (stream ? seq.txt_rows : seq.img_rows);
+    const bool valid = local < (stream ? seq.txt_rows_b[b] : seq.img_rows);
     __nv_bfloat16* orow = out + row * D;
     if (!valid) {   // keep pad rows exactly zero so downstream GEMM rows stay finite
 #pragma unroll
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256, 1) ln_mod_stream_kernel(const float* __re
     };
     auto is_valid = [&](int row) -> bool {
         const int r = row % rpb, stream = r >= seq.img_pad ? 1 : 0;
-        return (stream ? r - seq.img_pad : r) < (stream ? seq.txt_rows : seq.img_rows);
+        return (stream ? r - seq.img_pad : r) < (stream ? seq.txt_rows_b[row / rpb] : seq.img_rows);
     };
     auto issue = [&](int st, int row) {       // bulk copy of one fp32 row into my landing buffer `st`
         if (row < rows && is_valid(row) && lane == 0) {
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(256) qk_norm_rope_kernel(__nv_bfloat16* __rest
     const int r = (int)(row % rpb);
     const int stream = r >= seq.img_pad ? 1 : 0;
     const int local = stream ? r - seq.img_pad : r;
-    if (local >= (stream ? seq.txt_rows : seq.img_rows)) return;
+    if (local >= (stream ? seq.txt_rows_b[(int)(row / rpb)] : seq.img_rows)) return;
     const int D = H * 128;
     const float4 cs = *reinterpret_cast<const float4*>(rope + ((long long)r * 64 + lane * 2) * 2);  // c0,s0,c1,s1
 #pragma unroll
@@ -378,16 +378,17 @@ __global__ void __launch_bounds__(256) qk_norm_rope_kernel(__nv_bfloat16* __rest
 }
 
 // RMSNorm(weight) over rows of D, bf16 [B, n, D] -> bf16 [B, n_pad, D] (pad rows zero).  (txt_norm)
+struct RowCounts { int n[8]; };      // valid rows of every batch element (n = row stride of the input)
 __global__ void __launch_bounds__(256) rmsnorm_pack_kernel(const __nv_bfloat16* __restrict__ x,
                                                            const float* __restrict__ w,
                                                            __nv_bfloat16* __restrict__ out, int batch, int n, int n_pad,
-                                                           int D, float eps) {
+                                                           int D, float eps, RowCounts valid) {
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= (long long)batch * n_pad) return;
     const int lane = lane_id();
     const int b = (int)(row / n_pad), r = (int)(row % n_pad);
     __nv_bfloat16* o = out + row * D;
-    if (r >= n) {
+    if (r >= valid.n[b]) {
         for (int c = lane * 8; c < D; c += 256) *reinterpret_cast<uint4*>(o + c) = make_uint4(0, 0, 0, 0);
         return;
     }
@@ -664,11 +665,25 @@ extern "C" int qie_qk_norm_rope(void* qkv, const float* rope, const float* const
 
 extern "C" int qie_rmsnorm_pack(const void* x, const float* w, void* out, int batch, int n, int n_pad, int D,
                                 float eps, void* stream) {
-    QIE_REQUIRE(x && w && out, QIE_EINVAL, "qie_rmsnorm_pack: null pointer");
-    QIE_REQUIRE(D % 8 == 0 && n_pad >= n && n > 0, QIE_ESHAPE, "qie_rmsnorm_pack: bad shape");
+    QIE_REQUIRE(batch >= 1 && batch <= 8, QIE_ESHAPE, "qie_rmsnorm_pack: batch must be 1..8");
+    int nb[8];
+    for (int b = 0; b < 8; ++b) nb[b] = n;
+    return qie::rmsnorm_pack_ragged(x, w, out, batch, nb, n, n_pad, D, eps, stream);
+}
+
+// x [batch, n_max, D]; rows >= n_b[b] of batch element b are padding (zero rows in the output)
+int qie::rmsnorm_pack_ragged(const void* x, const float* w, void* out, int batch, const int* n_b, int n_max, int n_pad, int D, float eps,
+                             void* stream) {
+    QIE_REQUIRE(x && w && out && n_b, QIE_EINVAL, "qie_rmsnorm_pack: null pointer");
+    QIE_REQUIRE(D % 8 == 0 && n_pad >= n_max && n_max > 0 && batch >= 1 && batch <= 8, QIE_ESHAPE, "qie_rmsnorm_pack: bad shape");
+    RowCounts rc{};
+    for (int b = 0; b < batch; ++b) {
+        QIE_REQUIRE(n_b[b] >= 0 && n_b[b] <= n_max, QIE_ESHAPE, "qie_rmsnorm_pack: bad row count");
+        rc.n[b] = n_b[b];
+    }
     const long long rows = (long long)batch * n_pad;
     rmsnorm_pack_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, w, (__nv_bfloat16*)out, batch, n, n_pad, D, eps);
+        (const __nv_bfloat16*)x, w, (__nv_bfloat16*)out, batch, n_max, n_pad, D, eps, rc);
     QIE_LAUNCH_OK("rmsnorm_pack_kernel");
     return QIE_OK;
 }

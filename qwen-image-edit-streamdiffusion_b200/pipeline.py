@@ -98,18 +98,36 @@ def unpack_latents(tokens: torch.Tensor, h: int, w: int, mean: Optional[torch.Te
 def run_denoise(transformer, latents: torch.Tensor, image_latents: torch.Tensor, prompt_embeds: torch.Tensor,
                 img_shapes: List, num_inference_steps: int, negative_prompt_embeds: Optional[torch.Tensor] = None,
                 true_cfg_scale: float = 4.0, sigmas: Optional[Sequence[float]] = None, collect: Optional[list] = None,
-                uncond_fn=None, use_caches: bool = False, begin_index: int = 0) -> torch.Tensor:
+                uncond_fn=None, use_caches: bool = False, begin_index: int = 0, batched_cfg: bool = False) -> torch.Tensor:
     """The hot loop.  `uncond_fn(x, ts)` lets the CFG-pair parallel path supply v_uncond from the peer GPU.
     `begin_index` > 0 enters the schedule part-way (scheduler.set_begin_index upstream): the streaming path starts from the
-    previous frame's re-noised latent instead of pure noise."""
+    previous frame's re-noised latent instead of pure noise.
+    `batched_cfg`: the cond and the uncond forward of a step run as ONE forward of batch 2B (the reference's
+    batched_cfg_pipeline.py, README.md:126), each half with its own text length — worth it when one frame does not fill the GPU
+    (512x512 frames); the shorter prompt's rows are padding, not attended tokens, so the velocities equal the separate forwards."""
     latents = latents.to(torch.bfloat16).contiguous().clone()
     B, n, _ = latents.shape
     sig = np.asarray(sigmas, dtype=np.float32) if sigmas is not None else flowmatch_sigmas(num_inference_steps, n)
     do_cfg = true_cfg_scale > 1 and (negative_prompt_embeds is not None or uncond_fn is not None)
     image_latents = image_latents.to(torch.bfloat16)
+    batched = bool(batched_cfg and do_cfg and uncond_fn is None and not use_caches and 2 * B <= 8)
+    if batched:
+        Tc, Tu = prompt_embeds.shape[1], negative_prompt_embeds.shape[1]
+        both = torch.zeros(2 * B, max(Tc, Tu), prompt_embeds.shape[2], dtype=torch.bfloat16, device=latents.device)
+        both[:B, :Tc] = prompt_embeds
+        both[B:, :Tu] = negative_prompt_embeds
+        shapes2 = (list(img_shapes) * 2 if isinstance(img_shapes[0][0], (list, tuple)) and len(img_shapes) == B else img_shapes)
     for i in range(begin_index, num_inference_steps):
         x = torch.cat([latents, image_latents], dim=1)
         ts = model_timestep(float(sig[i]), B, latents.device)
+        if batched:
+            vu = transformer(hidden_states=torch.cat([x, x], 0), timestep=torch.cat([ts, ts], 0), encoder_hidden_states=both,
+                             img_shapes=shapes2, txt_seq_lens=[Tc] * B + [Tu] * B, return_dict=False)[0]
+            v, u = vu[:B].contiguous(), vu[B:].contiguous()
+            if collect is not None:
+                collect.append((v[:, :n].clone(), u[:, :n].clone()))
+            cfg_euler_step(latents, v, u, true_cfg_scale, float(sig[i]), float(sig[i + 1]))
+            continue
         # use_caches: the transformer holds cache_schedule()/cache_prompt("cond"/"uncond") entries (exact, SURVEY A.9)
         kw = dict(timestep_values=[float(model_timestep(float(sig[i]), 1, "cpu")[0])], cached_prompt="cond") if use_caches else {}
         v = transformer(hidden_states=x, timestep=ts, encoder_hidden_states=prompt_embeds, img_shapes=img_shapes,

@@ -430,10 +430,14 @@ class B200QwenImageTransformer2DModel(nn.Module):
                 raise L.QieError("txt_seq_lens exceeds encoder_hidden_states length")
             encoder_hidden_states = encoder_hidden_states[:, :max(txt_seq_lens)]
             T = encoder_hidden_states.shape[1]
+        # one length per batch element (batched true-CFG: cond and uncond prompt in one forward; replaces the reference's
+        # batched_cfg_pipeline.py, README.md:126): rows behind an element's own length are padding for every kernel — masked keys in
+        # attention — so the result equals the separate forwards (upstream would let the pad tokens take part)
+        ragged = txt_seq_lens is not None and len(txt_seq_lens) == B and len(set(int(v) for v in txt_seq_lens)) > 1
         shapes = img_shapes[0] if (isinstance(img_shapes, (list, tuple)) and isinstance(img_shapes[0], (list, tuple))
                                    and isinstance(img_shapes[0][0], (list, tuple))) else img_shapes
         flat = [int(v) for fhw in shapes for v in fhw]
-        seq = L.make_seq(B, S_i, T)
+        seq = L.make_seq_ragged(S_i, txt_seq_lens) if ragged else L.make_seq(B, S_i, T)
         ws = self._workspace(seq)
         base = (ws.data_ptr() + 1023) // 1024 * 1024
         hs = hidden_states.to(torch.bfloat16).contiguous()

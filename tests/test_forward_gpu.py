@@ -120,6 +120,41 @@ def test_denoise_loop_parity(cfg_on):
     assert cos >= COS_TOL, cos
 
 
+def test_batched_cfg_forward_equals_separate_forwards():
+    """Batched true CFG (the reference's batched_cfg_pipeline.py, README.md:126): the cond and the uncond prompt — different
+    lengths, 37 and 20 tokens here, another pair that pads to different tile counts below — share ONE forward of batch 2, each
+    batch element with its own text length (qie_seq::txt_rows_b).  Rows behind an element's length are padding for every kernel
+    (masked keys in attention), so the velocities must equal the two separate batch-1 forwards, and the denoise loop built on it
+    must equal the unbatched loop and the fp32 oracle."""
+    ref_cfg, our_cfg = small_cfg(layers=3)
+    oracle, ours = build_pair(ref_cfg, our_cfg)
+    shapes = [[(1, 16, 16), (1, 12, 10)]]
+    g = torch.Generator().manual_seed(9)
+    x = bf16_round(torch.randn(1, 376, 64, generator=g)).to(DEV).bfloat16()
+    ts = torch.tensor([0.5], device=DEV)
+    for Tc, Tu in ((37, 20), (300, 40), (20, 129)):
+        cond = bf16_round(torch.randn(1, Tc, 128, generator=g) * 3).to(DEV).bfloat16()
+        unc = bf16_round(torch.randn(1, Tu, 128, generator=g) * 3).to(DEV).bfloat16()
+        vc = ours(x, cond, None, ts, shapes, [Tc], return_dict=False)[0]
+        vu = ours(x, unc, None, ts, shapes, [Tu], return_dict=False)[0]
+        both = torch.zeros(2, max(Tc, Tu), 128, dtype=torch.bfloat16, device=DEV)
+        both[0, :Tc], both[1, :Tu] = cond[0], unc[0]
+        both[0, Tc:], both[1, Tu:] = 7.0, -9.0          # whatever sits behind an element's length must not matter
+        v2 = ours(torch.cat([x, x], 0), both, None, torch.cat([ts, ts], 0), shapes * 2, [Tc, Tu], return_dict=False)[0]
+        assert K.rel_err(v2[0], vc[0]) <= 1e-3 and K.rel_err(v2[1], vu[0]) <= 1e-3, (Tc, Tu, K.rel_err(v2[0], vc[0]), K.rel_err(v2[1], vu[0]))
+    lat = bf16_round(torch.randn(1, 256, 64, generator=g))
+    img_lat = bf16_round(torch.randn(1, 120, 64, generator=g))
+    cond = bf16_round(torch.randn(1, 37, 128, generator=g) * 3)
+    unc = bf16_round(torch.randn(1, 20, 128, generator=g) * 3)
+    plain = qie_b200.run_denoise(ours, lat.to(DEV), img_lat.to(DEV), cond.to(DEV), shapes, 4, unc.to(DEV), 4.0)
+    batched = qie_b200.run_denoise(ours, lat.to(DEV), img_lat.to(DEV), cond.to(DEV), shapes, 4, unc.to(DEV), 4.0, batched_cfg=True)
+    assert K.rel_err(batched, plain) <= 2e-3
+    with torch.no_grad():
+        ref = R.ref_run_denoise(oracle, lat, img_lat, cond, shapes, 4, unc, 4.0)
+    cos = torch.nn.functional.cosine_similarity(batched.float().cpu().flatten(), ref.flatten(), dim=0)
+    assert cos >= COS_TOL, cos
+
+
 def _config4_gate(oracle, ours, lat, img_lat, cond, shapes, steps, tag, dev_oracle):
     """Config 4: the W8A8 CUDA paths against 'the reference's own int8 path' at MODEL level.  The fp32 oracle and
     the int8 oracle model (the same blocks with ref_int8_linear in the four per-block linear groups, R.quantized_view) denoise

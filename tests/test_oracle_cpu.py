@@ -200,7 +200,7 @@ def test_abi_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header_sizes():
     # ctypes mirrors of the C structs: sizes follow from the field lists in include/qie.h
-    assert C.sizeof(L.Seq) == 5 * 4
+    assert C.sizeof(L.Seq) == (5 + 8) * 4
     assert C.sizeof(L.ModelCfg) == 9 * 4
     assert C.sizeof(L.BlockWeights) == 18 * 2 * 8
     assert C.sizeof(L.Weights) == 16 * 8
