@@ -305,7 +305,8 @@ def strong_leg(args, model, dev, world, rank, timed):
 
     for _ in range(3):                  # eager, graph capture, first replay
         got = frame()
-    ms = timed(frame, args.steps) / args.steps
+    with ClockSampler(dev.index or 0) as sclk:
+        ms = timed(frame, max(args.steps, 8)) / max(args.steps, 8)
     got_v = []
     got = frame(got_v)
     torch.cuda.synchronize()
@@ -350,7 +351,7 @@ def strong_leg(args, model, dev, world, rank, timed):
                 "parity_err": float(errs[0].item()), "parity_tolerance": 0.0 if sp == 1 else 1e-2,
                 "parity_what": "max-rel-err of the step-0 velocities (cond and uncond forward) against the single-GPU forward on the same inputs",
                 "final_latent_max_rel_err": float(errs[1].item()), "final_latent_cosine": float(-errs[2].item()),
-                "barrier_timeouts": int(timeouts.item()), "exchange_bytes": int(xbytes),
+                "barrier_timeouts": int(timeouts.item()), "exchange_bytes": int(xbytes), "clocks": sclk.summary(),
                 "exchange_bytes_note": "bytes ONE rank stores into other GPUs' memory per frame (epilogue peer stores over NVLink "
                                        "+ the CFG-pair velocity all-gather)", "profile": prof})
     if hasattr(runner, "close"):
