@@ -120,6 +120,34 @@ def test_denoise_loop_parity(cfg_on):
     assert cos >= COS_TOL, cos
 
 
+def test_two_handles_on_two_streams_do_not_share_scratch():
+    """the split-K tail scratch / tickets and the adaLN row counters used to be one set per device and
+    process, so two forwards on two CUDA streams (cond / uncond on two streams, README.md:127-128) raced on them.  They are now
+    one set per (device, stream): two handles driven concurrently from two streams must reproduce their serial results bit for
+    bit, repeatedly.  The shapes are chosen so that both mutable paths are live (a K-split tail in FF-down: K = 4 D >= 6144 needs
+    D >= 1536 -> 12 heads; the streaming adaLN kernel always takes rows from its counter)."""
+    cfg = qie_b200.QwenImageDiTConfig(num_layers=2, num_attention_heads=12, joint_attention_dim=128)
+    models = [qie_b200.B200QwenImageTransformer2DModel.from_random(cfg, seed=s_, device=DEV) for s_ in (0, 1)]
+    shapes = [[(1, 64, 64)]]      # 16 + 1 m-units x 6 n-blocks = 102 pair-tiles on 74 TPCs: a 28-tile tail, split in two K ranges
+    g = torch.Generator(device=DEV).manual_seed(3)
+    xs = [torch.randn(1, 4096, 64, generator=g, device=DEV).bfloat16() for _ in range(2)]
+    encs = [(torch.randn(1, 256, 128, generator=g, device=DEV) * 3).bfloat16() for _ in range(2)]
+    ts = torch.tensor([0.5], device=DEV)
+    serial = [m(x, e, None, ts, shapes, [256], return_dict=False)[0].clone() for m, x, e in zip(models, xs, encs)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for _ in range(3):
+        outs = [None, None]
+        for i in (0, 1):
+            streams[i].wait_stream(torch.cuda.current_stream())
+        for rep in range(2):                      # interleave the enqueueing so that the two forwards really overlap on the device
+            for i in (0, 1):
+                with torch.cuda.stream(streams[i]):
+                    outs[i] = models[i](xs[i], encs[i], None, ts, shapes, [256], return_dict=False)[0]
+        torch.cuda.synchronize()
+        assert torch.equal(outs[0], serial[0]) and torch.equal(outs[1], serial[1])
+
+
 def test_batched_cfg_forward_equals_separate_forwards():
     """Batched true CFG (the reference's batched_cfg_pipeline.py, README.md:126): the cond and the uncond prompt — different
     lengths, 37 and 20 tokens here, another pair that pads to different tile counts below — share ONE forward of batch 2, each
