@@ -57,6 +57,46 @@ def test_single_step_velocity(B, shapes, T, fuse_qk):
     assert err <= VEL_TOL, err
 
 
+@pytest.mark.parametrize("shapes,lens", [
+    ([(1, 6, 10), (1, 4, 4)], [1]),                              # 76 image tokens (less than one tile), ONE text token
+    ([(1, 16, 16), (1, 16, 16)], [1100]),                        # long prompt: 9 text tiles, 2 image tiles... text outweighs the image
+    ([(1, 8, 16)], [1, 5, 128, 129, 200, 64, 33, 7]),            # maximum batch (8), every element its own text length
+    ([(1, 16, 8), (1, 16, 8), (1, 16, 8), (1, 16, 8)], [255, 257]),   # four reference images; lengths either side of a tile edge
+])
+def test_edge_shapes_against_oracle(shapes, lens):
+    """Edge cases of the operator surface: tiny and ragged inputs, the maximum batch, text longer than the image,
+    per-element prompt lengths straddling a 128-row tile boundary — each batch element against its own fp32 oracle forward."""
+    ref_cfg, our_cfg = small_cfg()
+    oracle, ours = build_pair(ref_cfg, our_cfg)
+    B, T = len(lens), max(lens)
+    img_shapes = [shapes] * B
+    hidden, enc = R.make_inputs(ref_cfg, img_shapes, T, batch=B, seed=4)
+    hidden, enc = bf16_round(hidden), bf16_round(enc)
+    ts = torch.tensor([0.5] * B)
+    got = ours(hidden_states=hidden.to(DEV), encoder_hidden_states=enc.to(DEV), timestep=ts.to(DEV), img_shapes=img_shapes,
+               txt_seq_lens=lens, return_dict=False)[0].cpu()
+    assert torch.isfinite(got.float()).all()
+    with torch.no_grad():
+        for b in range(B):
+            ref = oracle(hidden[b:b + 1], enc[b:b + 1, :lens[b]], None, ts[b:b + 1], [shapes], [lens[b]])[0]
+            err = K.rel_err(got[b:b + 1], ref)
+            assert err <= VEL_TOL, (b, lens[b], err)
+
+
+def test_batch_above_eight_and_bad_text_lengths_are_refused():
+    ref_cfg, our_cfg = small_cfg()
+    _, ours = build_pair(ref_cfg, our_cfg)
+    shapes = [(1, 8, 16)]
+    x = torch.zeros(9, 128, 64, dtype=torch.bfloat16, device=DEV)
+    e = torch.zeros(9, 8, 128, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(qie_b200.QieError):
+        ours(x, e, None, torch.zeros(9, device=DEV), [shapes] * 9, [8] * 9, return_dict=False)
+    with pytest.raises(qie_b200.QieError):          # a batch element without text
+        ours(x[:2], e[:2], None, torch.zeros(2, device=DEV), [shapes] * 2, [8, 0], return_dict=False)
+    with pytest.raises(qie_b200.QieError):          # lengths longer than the embeddings
+        ours(x[:2], e[:2], None, torch.zeros(2, device=DEV), [shapes] * 2, [8, 9], return_dict=False)
+
+
 def test_output_object_and_dtype_surface():
     ref_cfg, our_cfg = small_cfg(layers=1)
     _, ours = build_pair(ref_cfg, our_cfg)
