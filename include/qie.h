@@ -121,8 +121,14 @@ int qie_set_weights(qie_handle* h, const qie_weights* w);
  * cublaslt_int8.py / triton_int8_gemm.py named at README.md:136-141 */
 int qie_set_precision(qie_handle* h, int mode);
 /* tuning/debug knobs outside the reference surface: key 0 = fuse QK-norm+RoPE into the QKV GEMM epilogue (default 1),
- * key 1 = attention kernel variant, key 2 = record CUDA events around every kernel class inside qie_forward */
+ * key 1 = attention kernel variant, key 2 = record CUDA events around every kernel class inside qie_forward,
+ * key 3 = bounded-score attention where the norm weights allow it (see qie_attn_score_bound) */
 int qie_set_option(qie_handle* h, int key, int value);
+/* key 3 of qie_set_option: 1 (default) = blocks whose score bound (below) is <= QIE_ATTN_SCORE_BOUND run the bounded-score
+ * attention (q pre-scaled in the QKV epilogue, qie_attn_fwd variant 0x200), 0 = every block runs the online-softmax kernel.
+ * qie_attn_score_bound: the bound on |q.k| * softmax_scale * log2(e) of block `layer`, derived at qie_set_weights from the
+ * four QK-RMSNorm weight vectors of the block (read back once, 2 % margin for the bf16 rounding of q and k); < 0 on error */
+float qie_attn_score_bound(const qie_handle* h, int layer);
 /* measurement aids: kernels launched by the library so far; event-timed ms / algorithmic work / launches per kernel
  * class since the last read (class 0 GEMM [FLOP], 1 attention [FLOP], 2 adaLN [bytes], 3 modulation GEMV [bytes], 4 other,
  * 5 peer barrier); arrays of QIE_PROFILE_CLASSES entries.  qie_profile_timeline lists the launches recorded since the last
@@ -313,13 +319,21 @@ typedef struct qie_gemm_args {
      * max|out| of every output row into q8_amax[row] (fp32, atomicMax on the bit pattern; the caller zeroes it) so that the
      * per-token quantiser that follows needs no separate max pass */
     float* q8_amax;
+    /* QKV_NORM_ROPE only: factor applied to the q columns after RMSNorm and RoPE, before the bf16 rounding (0 = 1.0).
+     * qie_forward passes softmax_scale * log2(e) in the blocks whose attention runs in the bounded-score form (qie_attn_fwd 0x200) */
+    float q_scale;
 } qie_gemm_args;
 int qie_gemm(const qie_gemm_args* args, const qie_seq* seq, void* stream);
 
 /* joint attention over all valid rows of each batch element; qkv bf16 [rows, 3*H*128] (q|k|v), q and k already
  * normed + roped; out bf16 [rows, H*128].  replaces F.scaled_dot_product_attention in
  * QwenDoubleStreamAttnProcessor2_0. variant: 0 = tuned default (CTA-pair kernel); 0x8 selects the single-CTA
- * fallback kernel; bits 4..7 = how many of every 8 score pairs use the FMA-pipe polynomial exp2 (0x100 = none, 2, 3, 4). */
+ * fallback kernel; bits 4..7 = how many of every 8 score pairs use the FMA-pipe polynomial exp2 (0x100 = none, 2, 3, 4).
+ * 0x200 = bounded-score form of the CTA-pair kernel: the CALLER promises that q already carries softmax_scale * log2(e)
+ * (qie_gemm_args.q_scale) and that |q.k| <= QIE_ATTN_SCORE_BOUND for every (query, key) pair, so p = 2^(q.k) needs no running
+ * max, no exchange between the softmax warpgroups and no rescale of O; the result is the same softmax.  After QK-RMSNorm the
+ * bound follows from the norm weights: |q.k| <= 128 * max|w_q| * max|w_k| * softmax_scale * log2(e) (RoPE is a rotation). */
+#define QIE_ATTN_SCORE_BOUND 80.0f
 int qie_attn_fwd(const void* qkv, void* out, const qie_seq* seq, int num_heads, int variant, void* stream);
 /* LayerNorm(no affine, eps) + x*(1+scale)+shift; x fp32 [rows, D] -> out bf16 [rows, D].
  * shift/scale for (b, stream) at mod[b*mod_bstride + stream*mod_sstride + {shift_off,scale_off} + c].

@@ -72,7 +72,7 @@ class GemmArgs(C.Structure):
                 ("rope", C.c_void_p), ("qk_norm_w", (C.c_void_p * 2) * 2),
                 ("fp8", C.c_int), ("a_scale", C.c_void_p), ("w_scale", _P2), ("block_n", C.c_int), ("cta_group", C.c_int),
                 ("peer_out", C.c_void_p), ("sp_rank", C.c_int), ("sp_size", C.c_int), ("sp_gathered_rows", C.c_int),
-                ("sp_txt_row0", C.c_int), ("q8_amax", C.c_void_p)]
+                ("sp_txt_row0", C.c_int), ("q8_amax", C.c_void_p), ("q_scale", C.c_float)]
 
 
 class Peers(C.Structure):
@@ -97,6 +97,7 @@ SYMBOLS = {
     "qie_set_weights": (_i, [_vp, C.POINTER(Weights)]),
     "qie_set_precision": (_i, [_vp, _i]),
     "qie_set_option": (_i, [_vp, _i, _i]),
+    "qie_attn_score_bound": (_f, [_vp, _i]),
     "qie_launch_count": (C.c_ulonglong, []),
     "qie_tune": (_i, [_i, _i]),
     "qie_tune_get": (_i, [_i]),

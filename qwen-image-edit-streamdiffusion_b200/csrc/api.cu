@@ -74,7 +74,7 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 
 int unpack_rows(const void* x, void* out, int batch, int n, int n_pad, int C, cudaStream_t st);
 int attn_fwd_peers(const void* qkv_gathered, void* const* peer_out_dev, const qie_peers* pr, const int* tile_valid_dev,
-                   int heads_local, int out_ld, void* stream);
+                   int heads_local, int out_ld, int variant, void* stream);
 int peer_bcast_rows(const void* src, void* const* peer_vel_dev, const qie_peers* pr, int img_rows, int img_offset, int C,
                     cudaStream_t st);
 int peer_barrier_launch(const qie_peers* pr, cudaStream_t st);
@@ -148,6 +148,8 @@ struct qie_handle {
     int precision;   // 0 bf16, 1 fp8
     int fuse_qk;     // 1: RMSNorm+RoPE in the QKV GEMM epilogue, 0: standalone kernel
     int attn_variant;
+    int attn_bounded = 1;               // option 3: bounded-score attention in the blocks whose bound allows it
+    std::vector<float> score_bound;     // per block: bound on |q.k| * softmax_scale * log2(e), from the QK-RMSNorm weights
     qie_weights w;
     std::vector<qie_block_weights> blocks;
     // library-owned small device buffers
@@ -355,8 +357,26 @@ extern "C" int qie_set_weights(qie_handle* h, const qie_weights* w) {
         }
     h->w = *w;
     h->w.blocks = h->blocks.data();
+    // bound on the attention scores of every block: after RMSNorm |q|^2 = sum (q_i / rms)^2 w_i^2 <= 128 max w^2, RoPE rotates
+    // pairs, so |q.k| <= 128 max|w_q| max|w_k| (over both streams: image queries meet text keys); 2 % for the bf16 rounding
+    h->score_bound.assign(h->cfg.num_layers, INFINITY);
+    for (int l = 0; l < h->cfg.num_layers; ++l) {
+        float mx[2] = {0.f, 0.f};
+        for (int s = 0; s < 2; ++s)
+            for (int k = 0; k < 2; ++k) {
+                float wv[128];
+                QIE_CUDA_OK(cudaMemcpy(wv, k ? h->blocks[l].k_norm_w[s] : h->blocks[l].q_norm_w[s], sizeof(wv), cudaMemcpyDeviceToHost));
+                for (float v : wv) mx[k] = fmaxf(mx[k], isfinite(v) ? fabsf(v) : INFINITY);
+            }
+        h->score_bound[l] = 128.f * mx[0] * mx[1] * ATTN_SCALE_LOG2 * 1.02f;
+    }
     h->has_weights = true;
     return QIE_OK;
+}
+
+extern "C" float qie_attn_score_bound(const qie_handle* h, int layer) {
+    if (!h || !h->has_weights || layer < 0 || layer >= h->cfg.num_layers) return -1.f;
+    return h->score_bound[layer];
 }
 
 extern "C" int qie_set_precision(qie_handle* h, int mode) {
@@ -380,6 +400,7 @@ extern "C" int qie_set_option(qie_handle* h, int key, int value) {
     if (key == 0) h->fuse_qk = value;
     else if (key == 1) h->attn_variant = value;
     else if (key == 2) h->profile = value;
+    else if (key == 3) h->attn_bounded = value;
     else QIE_REQUIRE(false, QIE_EINVAL, "qie_set_option: unknown key %d", key);
     return QIE_OK;
 }
@@ -522,7 +543,13 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
         ProfScope ps(h, st, 0, 2.0 * mv * g.N * g.K);
         return qie_gemm(&g, seq, st);
     };
-    auto run_attn = [&]() -> int {
+    // bounded-score attention of block l: q carries softmax_scale * log2(e) out of the fused QKV epilogue and the kernel skips the
+    // running max (attn.cu); only where the norm weights bound the scores, never with the unfused debug path or a forced kernel
+    auto bounded = [&](int l) -> bool {
+        return h->attn_bounded && h->fuse_qk && (h->attn_variant & 0x208) == 0 && h->score_bound[l] <= QIE_ATTN_SCORE_BOUND;
+    };
+    auto run_attn = [&](int l) -> int {
+        const int variant = bounded(l) ? (h->attn_variant | 0x200) : h->attn_variant;
         if (use_peers) {
             // my head group over the gathered sequence of every rank; the epilogue stores each token's output into the
             // attention buffer of the rank that owns the token
@@ -530,12 +557,12 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
             const int hl = h->cfg.num_heads / pr.size;
             const double S = (double)pr.img_total + pr.txt_total;
             ProfScope ps(h, st, 1, 4.0 * S * S * 128.0 * hl * pr.batch);
-            return attn_fwd_peers(pr.qkv_gather[pr.rank], h->d_peer_tab + 8, &pr, h->d_tile_valid, hl, D, st);
+            return attn_fwd_peers(pr.qkv_gather[pr.rank], h->d_peer_tab + 8, &pr, h->d_tile_valid, hl, D, variant, st);
         }
         double ss = 0;
         for (int b = 0; b < B; ++b) ss += ((double)seq->img_rows + seq->txt_rows_b[b]) * ((double)seq->img_rows + seq->txt_rows_b[b]);
         ProfScope ps(h, st, 1, 4.0 * ss * 128.0 * h->cfg.num_heads);
-        return qie_attn_fwd(qkv, attn, seq, h->cfg.num_heads, h->attn_variant, st);
+        return qie_attn_fwd(qkv, attn, seq, h->cfg.num_heads, variant, st);
     };
     if (use_peers && (phases & (QIE_PHASE_QKV | QIE_PHASE_ATTN | QIE_PHASE_END)))
         QIE_REQUIRE(B == h->peers.batch && h->peers.img_pad == seq->img_pad && h->peers.txt_pad == seq->txt_pad && h->fuse_qk &&
@@ -680,6 +707,7 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
             g.N = 3 * D; g.K = D; g.streams = 3; g.out = qkv; g.ldo = 3 * D;
             g.epilogue = h->fuse_qk ? QIE_EPI_QKV_NORM_ROPE : QIE_EPI_BF16;
             g.rope = h->d_rope;
+            g.q_scale = bounded(l) ? ATTN_SCALE_LOG2 : 1.f;
             for (int s = 0; s < 2; ++s) {
                 g.bias[s] = bw.qkv_b[s];
                 g.qk_norm_w[s][0] = bw.q_norm_w[s];
@@ -701,7 +729,7 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
             }
         }
         }   // QIE_PHASE_QKV
-        if ((phases & QIE_PHASE_ATTN) && (rc = run_attn())) return rc;
+        if ((phases & QIE_PHASE_ATTN) && (rc = run_attn(l))) return rc;
         if (phases & QIE_PHASE_POST) {
         {   // out-proj + gate1 * y + residual
             qie_gemm_args g{};

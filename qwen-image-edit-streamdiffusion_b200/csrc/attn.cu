@@ -457,7 +457,7 @@ constexpr int AT5_THREADS = 384;              // warps 0-7 softmax (two warpgrou
 constexpr int AT5_STAGE_BYTES = 32 * 1024;     // K: my 128 kv rows x 128 dims; V: 256 kv rows x my 64 dims
 constexpr int AT5_SMEM = ATT_TILE_BYTES + (AT5_KSTAGES + AT5_VSTAGES) * AT5_STAGE_BYTES + 2048 + 1024 + 512 + 1024;
 
-template <int POLY>
+template <int POLY, bool FIXED>
 __global__ void __launch_bounds__(AT5_THREADS, 1)
 attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
     extern __shared__ uint8_t smem_raw[];
@@ -631,6 +631,48 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(leader_smem_u32(s_free));   // the tensor pipe may refill S now
+            [[maybe_unused]] bool grow = false;
+            [[maybe_unused]] float alpha = 1.f;
+            if constexpr (FIXED) {
+                // ---- bounded scores (QK-RMSNorm: |q.k| <= 128 max|w_q| max|w_k|), q pre-multiplied by scale*log2(e) in the QKV
+                // epilogue: p = 2^s needs no reference, hence no row max, no exchange between the warpgroups, no O rescale and no
+                // scale/subtract FFMA2; p in [2^-B, 2^B] with B <= 80 neither underflows nor overflows fp32 / bf16 / the fp32
+                // accumulators (8448 * 2^80 * |v|).  The clamp of the polynomial path is not needed either. ----
+                if (nv == ATT_TILE) {
+#pragma unroll
+                    for (int i = 0; i < 128; i += 2) {
+                        const float x0 = __uint_as_float(s[i]), x1 = __uint_as_float(s[i + 1]);
+                        float e0, e1;
+                        if (((i >> 1) & 7) < POLY) {
+                            const uint64_t X = pk2(x0, x1);
+                            const uint64_t T = add2(X, pk2(12582912.f, 12582912.f));
+                            const uint64_t N = add2(T, pk2(-12582912.f, -12582912.f));
+                            const uint64_t Fr = fma2(N, pk2(-1.f, -1.f), X);
+                            uint64_t P = fma2(Fr, pk2(0.0551716574f, 0.0551716574f), pk2(0.2426111400f, 0.2426111400f));
+                            P = fma2(P, Fr, pk2(0.6932609677f, 0.6932609677f));
+                            P = fma2(P, Fr, pk2(0.9999280572f, 0.9999280572f));
+                            float t0, t1, p0, p1;
+                            upk2(T, t0, t1);
+                            upk2(P, p0, p1);
+                            e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+                            e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+                        } else {
+                            e0 = fast_exp2(x0);
+                            e1 = fast_exp2(x1);
+                        }
+                        l2 = add2(l2, pk2(e0, e1));
+                        s[i >> 1] = pack_bf16(e0, e1);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 128; i += 2) {
+                        const float e0 = i < nv ? fast_exp2(__uint_as_float(s[i])) : 0.f;
+                        const float e1 = i + 1 < nv ? fast_exp2(__uint_as_float(s[i + 1])) : 0.f;
+                        l2 = add2(l2, pk2(e0, e1));
+                        s[i >> 1] = pack_bf16(e0, e1);
+                    }
+                }
+            } else {
             // ---- row max of my 128 columns, then the row max of the whole 256-wide tile through shared memory ----
             float m0 = -INFINITY, m1 = -INFINITY;
             if (nv == ATT_TILE) {
@@ -653,8 +695,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
             xmj[wg * 128 + r] = fmaxf(m0, m1);
             named_bar_sync(1 + quad, 64);                 // only my partner warp (same rows, other warpgroup)
             const float mx = fmaxf(fmaxf(m0, m1), xmj[(wg ^ 1) * 128 + r]) * c;
-            float alpha = 1.f;
-            const bool grow = mx > m_ref + 8.0f;      // identical decision in both warpgroups (same row, same inputs)
+            grow = mx > m_ref + 8.0f;                 // identical decision in both warpgroups (same row, same inputs)
             if (grow) {
                 alpha = fast_exp2(m_ref - mx);
                 m_ref = mx;
@@ -699,11 +740,12 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
                     s[i >> 1] = pack_bf16(e0, e1);
                 }
             }
+            }   // !FIXED
             if (j > 0) {
                 // PV(j-1) reads the P buffer and owns O: it must have retired before either is touched
                 mbar_wait(pv_done, (j - 1) & 1);
                 tc_fence_after();
-                if (__any_sync(0xffffffffu, grow)) {
+                if (!FIXED && __any_sync(0xffffffffu, grow)) {
 #pragma unroll 1
                     for (int ch = 0; ch < 2; ++ch) {
                         uint32_t o[32];
@@ -784,9 +826,9 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
     }
 }
 
-template <int POLY>
+template <int POLY, bool FIXED>
 static int launch_attn_pair(const CUtensorMap& tm128, const AttnDev& p, dim3 grid, cudaStream_t st) {
-    QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(attn_pair_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT5_SMEM));
+    QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(attn_pair_kernel<POLY, FIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT5_SMEM));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(AT5_THREADS);
@@ -795,7 +837,7 @@ static int launch_attn_pair(const CUtensorMap& tm128, const AttnDev& p, dim3 gri
     cudaLaunchAttribute attr[2];
     cfg.attrs = attr;
     cfg.numAttrs = launch_attrs(attr, 2);
-    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_pair_kernel<POLY>, tm128, p));
+    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_pair_kernel<POLY, FIXED>, tm128, p));
     QIE_LAUNCH_OK("attn_pair_kernel");
     return QIE_OK;
 }
@@ -824,7 +866,10 @@ extern "C" int qie_attn_fwd_tiles(const void* qkv, void* out, int n_tiles, const
 
 // variant 0 = the tuned default (CTA-pair kernel, 2 of every 8 score pairs on the FMA-pipe polynomial exp2).  Explicit choices:
 // bit 3 (0x8) = single-CTA fallback kernel; bits 4..7 = how many of every 8 score pairs take the polynomial (0 with bit 8
-// (0x100) set = all MUFU, 2, 3, 4).
+// (0x100) set = all MUFU, 2, 3, 4); bit 9 (0x200) = bounded-score form: the caller promises that q is already multiplied by
+// softmax_scale * log2(e) and that |q.k| <= 80 for every pair (true after QK-RMSNorm with bounded norm weights: qie_forward
+// derives the bound of every block from its norm weights and picks this form only where it holds), so p = 2^s needs no
+// running max, no exchange between the two softmax warpgroups and no O rescale.
 extern "C" int qie_attn_fwd(const void* qkv, void* out, const qie_seq* seq, int num_heads, int variant, void* stream) {
     QIE_REQUIRE(qkv && out && seq, QIE_EINVAL, "qie_attn_fwd: null pointer");
     QIE_REQUIRE(seq->img_pad % 128 == 0 && seq->txt_pad % 128 == 0 && seq->batch > 0 && num_heads > 0 &&
@@ -838,22 +883,24 @@ extern "C" int qie_attn_fwd(const void* qkv, void* out, const qie_seq* seq, int 
 // (called by the ATTN phase of qie_forward_phase when peers are installed)
 namespace qie {
 int attn_fwd_peers(const void* qkv_gathered, void* const* peer_out_dev, const qie_peers* pr, const int* tile_valid_dev,
-                   int heads_local, int out_ld, void* stream) {
+                   int heads_local, int out_ld, int variant, void* stream) {
     QIE_REQUIRE(qkv_gathered && peer_out_dev && pr && tile_valid_dev && heads_local > 0, QIE_EINVAL, "attn_fwd_peers: bad argument");
     qie_seq s{};
     s.batch = pr->batch;
     s.img_rows = s.img_pad = pr->size * pr->img_pad + (pr->txt_total + 127) / 128 * 128;
     AttnScatter sc{peer_out_dev, pr, out_ld, pr->rank * heads_local};
-    return attn_launch(qkv_gathered, const_cast<void*>(qkv_gathered) /* unused */, &s, tile_valid_dev, heads_local, 0, stream, &sc);
+    return attn_launch(qkv_gathered, const_cast<void*>(qkv_gathered) /* unused */, &s, tile_valid_dev, heads_local, variant, stream, &sc);
 }
 }  // namespace qie
 
 static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int* tile_valid, int num_heads, int variant,
                        void* stream, const AttnScatter* sc) {
     if (variant == 0) variant = 0x20;
-    const int poly = (variant >> 4) & 15, single = (variant >> 3) & 1;
-    QIE_REQUIRE((variant & ~0x1F8) == 0 && (poly == 0 || poly == 2 || poly == 3 || poly == 4), QIE_EINVAL,
+    if (variant == 0x200) variant = 0x220;
+    const int poly = (variant >> 4) & 15, single = (variant >> 3) & 1, fixed = (variant >> 9) & 1;
+    QIE_REQUIRE((variant & ~0x3F8) == 0 && (poly == 0 || poly == 2 || poly == 3 || poly == 4), QIE_EINVAL,
                 "qie_attn_fwd: bad variant 0x%x", variant);
+    QIE_REQUIRE(!(fixed && single), QIE_EINVAL, "qie_attn_fwd: the bounded-score form (0x200) is a CTA-pair kernel");
     const int rpb = seq->img_pad + seq->txt_pad;
     const int D = num_heads * 128;
     CUtensorMap tm;
@@ -877,7 +924,7 @@ static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int
         p.out_ld = sc->out_ld;
         p.head_off = sc->head_off;
     }
-    p.scale_log2 = 0.08838834764831845f * 1.4426950408889634f;   // 1/sqrt(128) * log2(e)
+    p.scale_log2 = ATTN_SCALE_LOG2;
     // V tile in smem: two halves (64 dims each, 16 KB apart) of 128 kv rows x 128 B, 128B-swizzled by TMA.
     // MN-major canonical layout: 8 kv rows x 128 B = one 1024 B atom (SBO), next 64 dims LBO away.
     p.v_lbo = ATT_HALF_BYTES;
@@ -894,11 +941,19 @@ static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int
         }
     }
     grid.x *= 2;     // a cluster of two CTAs per 256 query rows
+    if (fixed) {
+        switch (poly) {
+            case 0: return launch_attn_pair<0, true>(tm, p, grid, st);
+            case 2: return launch_attn_pair<2, true>(tm, p, grid, st);
+            case 3: return launch_attn_pair<3, true>(tm, p, grid, st);
+            case 4: return launch_attn_pair<4, true>(tm, p, grid, st);
+        }
+    }
     switch (poly) {
-        case 0: return launch_attn_pair<0>(tm, p, grid, st);
-        case 2: return launch_attn_pair<2>(tm, p, grid, st);
-        case 3: return launch_attn_pair<3>(tm, p, grid, st);
-        case 4: return launch_attn_pair<4>(tm, p, grid, st);
+        case 0: return launch_attn_pair<0, false>(tm, p, grid, st);
+        case 2: return launch_attn_pair<2, false>(tm, p, grid, st);
+        case 3: return launch_attn_pair<3, false>(tm, p, grid, st);
+        case 4: return launch_attn_pair<4, false>(tm, p, grid, st);
     }
     return QIE_EINVAL;
 }

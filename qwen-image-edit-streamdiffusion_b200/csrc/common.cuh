@@ -458,6 +458,9 @@ __device__ __forceinline__ uint32_t pack_s8x4(float a, float b, float c, float d
     const int ic = max(-127, min(127, __float2int_rn(c))), id = max(-127, min(127, __float2int_rn(d)));
     return (uint32_t)(ia & 0xFF) | ((uint32_t)(ib & 0xFF) << 8) | ((uint32_t)(ic & 0xFF) << 16) | ((uint32_t)(id & 0xFF) << 24);
 }
+// softmax scale of head_dim 128 in the log2 domain: 1/sqrt(128) * log2(e)
+constexpr float ATTN_SCALE_LOG2 = 0.08838834764831845f * 1.4426950408889634f;
+
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -44,6 +44,7 @@ struct GemmDev {
     long long gate_bstride, gate_sstride;
     const float* rope;
     const float* qk_norm_w[2][2];
+    float q_scale;            // QKV epilogue: factor on the q columns (softmax scale * log2 e for the bounded-score attention)
     const float* a_scale;
     const float* w_scale[2];
     int model_dim;           // D (QKV epilogue: column block -> q/k/v)
@@ -456,6 +457,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                 }
                             }
                             rinv_head = rsqrtf(ss * (1.0f / 128.0f) + 1e-6f);
+                            if (which == 0) rinv_head *= p.q_scale;   // RMSNorm, RoPE and this factor are all linear in the row
                         }
                         stage_chunk(c, which != 2 ? rinv_head : 1.f, which != 2);
                     } else {
@@ -688,6 +690,7 @@ extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream
     p.gate_bstride = g->gate_bstride;
     p.gate_sstride = g->gate_sstride;
     p.rope = g->rope;
+    p.q_scale = g->q_scale == 0.f ? 1.f : g->q_scale;
     p.a_scale = g->a_scale;
     for (int s = 0; s < 2; ++s) {
         p.bias[s] = g->bias[s];

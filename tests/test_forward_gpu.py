@@ -83,6 +83,57 @@ def test_edge_shapes_against_oracle(shapes, lens):
             assert err <= VEL_TOL, (b, lens[b], err)
 
 
+def _scaled_norm_weights(oracle, factor):
+    with torch.no_grad():
+        for name, p in oracle.named_parameters():
+            if p.dim() == 1 and name.endswith("weight") and any(k in name for k in ("norm_q", "norm_k", "norm_added_q", "norm_added_k")):
+                p.mul_(factor)
+                p.copy_(p.to(torch.bfloat16).float())
+
+
+@pytest.mark.parametrize("factor,expect_bounded", [(1.0, True), (2.0, True), (2.6, False), (6.0, False)])
+def test_bounded_score_attention_follows_the_norm_weights(factor, expect_bounded):
+    """qie_set_weights derives a bound on |q.k| from the QK-RMSNorm weights of every block; blocks under QIE_ATTN_SCORE_BOUND (80 in
+    the log2 domain) run the bounded-score attention (q pre-scaled in the QKV epilogue, no running max), the others the
+    online-softmax kernel.  Either way the velocity equals the fp32 oracle's, and switching the form off (option 3) agrees."""
+    ref_cfg, our_cfg = small_cfg()
+    oracle = R.init_weights_(R.QwenImageTransformer2DModelRef(ref_cfg), seed=0)
+    with torch.no_grad():
+        for p in oracle.parameters():
+            p.copy_(p.to(torch.bfloat16).float())
+    _scaled_norm_weights(oracle, factor)
+    oracle.eval()
+    ours = qie_b200.B200QwenImageTransformer2DModel.from_state_dict(oracle.state_dict(), our_cfg, DEV)
+    lib = qie_b200.lib()
+    sd = oracle.state_dict()
+    for l in range(ref_cfg.num_layers):
+        names = [k for k in sd if k.startswith(f"transformer_blocks.{l}.") and k.endswith("weight") and
+                 any(t in k for t in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"))]
+        qmax = max(sd[k].abs().max().item() for k in names if "_q" in k)
+        kmax = max(sd[k].abs().max().item() for k in names if "_k" in k)
+        want = 128 * qmax * kmax * 0.08838834764831845 * 1.4426950408889634 * 1.02
+        got_b = lib.qie_attn_score_bound(ours._handle, l)
+        assert abs(got_b - want) <= 1e-3 * want, (l, got_b, want)
+        assert (got_b <= 80.0) == expect_bounded
+    shapes = [[(1, 16, 16), (1, 16, 16)]]
+    T = 77
+    hidden, enc = R.make_inputs(ref_cfg, shapes, T, seed=5)
+    hidden, enc = bf16_round(hidden), bf16_round(enc)
+    ts = torch.tensor([0.625])
+    with torch.no_grad():
+        ref = oracle(hidden, enc, None, ts, shapes, [T])[0]
+    run = lambda: ours(hidden_states=hidden.to(DEV), encoder_hidden_states=enc.to(DEV), timestep=ts.to(DEV), img_shapes=shapes,
+                       txt_seq_lens=[T], return_dict=False)[0].cpu()
+    got = run()
+    assert K.rel_err(got, ref) <= VEL_TOL, K.rel_err(got, ref)
+    ours.set_option(3, 0)
+    off = run()
+    assert K.rel_err(off, ref) <= VEL_TOL
+    assert K.rel_err(got, off.float()) <= VEL_TOL
+    if not expect_bounded:
+        assert torch.equal(got, off)          # the same kernels ran both times
+
+
 def test_batch_above_eight_and_bad_text_lengths_are_refused():
     ref_cfg, our_cfg = small_cfg()
     _, ours = build_pair(ref_cfg, our_cfg)

@@ -402,6 +402,52 @@ def test_attention_score_jumps_between_tiles(variant, jump):
     assert K.rel_err(got, ref) <= 2 ** -6
 
 
+@pytest.mark.parametrize("B,img,txt,H", [(1, 256, 128, 2), (2, 200, 19, 2), (1, 1024, 219, 3), (1, 1500, 300, 2)])
+@pytest.mark.parametrize("variant", [0x200, 0x300, 0x230, 0x240])
+@pytest.mark.parametrize("wnorm", [1.0, 2.2])
+def test_attention_bounded_scores(B, img, txt, H, variant, wnorm):
+    """Bounded-score form (0x200): q and k are RMS-normed rows with norm weight `wnorm` (|q.k| * scale * log2e <= 16.3 wnorm^2,
+    79 at 2.2 = just under QIE_ATTN_SCORE_BOUND), q arrives pre-multiplied by scale * log2(e); some queries are copies / negated
+    copies of keys so that scores sit at both ends of the range.  Same softmax as SDPA on the unscaled q."""
+    s = K.seq(B, img, txt)
+    D = H * 128
+    x = randn(K.rows(s), 3, H, 128, seed=93)
+    x[:, :2] = x[:, :2] * torch.rsqrt(x[:, :2].pow(2).mean(-1, keepdim=True)) * wnorm        # |q| = |k| = sqrt(128) * wnorm
+    x[5:9, 0] = x[40:44, 1]                  # queries aligned with a key: score = +bound
+    x[9:13, 0] = -x[60:64, 1]                # and opposed to one: score = -bound
+    c = 0.08838834764831845 * 1.4426950408889634
+    xq = x.clone()
+    xq[:, 0] *= c
+    qkv = xq.reshape(K.rows(s), 3 * D).to(torch.bfloat16)
+    got = K.attn(s, qkv, H, variant)
+    ref_in = qkv.float().reshape(K.rows(s), 3, H, 128)
+    qi, qt = K.from_joint(s, ref_in.reshape(K.rows(s), 3 * D))
+    y = torch.cat([qi, qt], dim=1).reshape(B, img + txt, 3, H, 128)
+    q, k, v = (y[:, :, i].transpose(1, 2) for i in range(3))
+    ref = F.scaled_dot_product_attention(q, k, v, scale=0.6931471805599453).transpose(1, 2).reshape(B, img + txt, D)
+    gi, gt = K.from_joint(s, got)
+    g = torch.cat([gi, gt], dim=1)
+    assert torch.isfinite(g.float()).all()
+    assert K.rel_err(g, ref) <= 2 ** -6, K.rel_err(g, ref)
+    # row-wise too: the rows whose softmax is one spike at the top of the range must not lose to the tolerance of the max norm
+    rows = (g.float() - ref).abs().amax(-1) / ref.abs().amax(-1).clamp_min(1e-6)
+    assert rows.max() <= 2 ** -5, rows.max()
+
+
+def test_attention_bounded_equals_online_softmax():
+    """Same inputs through the online-softmax kernel (unscaled q) and the bounded-score kernel (pre-scaled q): the two outputs
+    agree to the rounding of q * c in bf16."""
+    s = K.seq(1, 640, 77)
+    H, D = 2, 256
+    x = randn(K.rows(s), 3, H, 128, seed=94)
+    x[:, :2] = x[:, :2] * torch.rsqrt(x[:, :2].pow(2).mean(-1, keepdim=True))
+    a = K.attn(s, x.reshape(-1, 3 * D).to(torch.bfloat16), H, 0)
+    xq = x.clone()
+    xq[:, 0] *= 0.08838834764831845 * 1.4426950408889634
+    b = K.attn(s, xq.reshape(-1, 3 * D).to(torch.bfloat16), H, 0x200)
+    assert K.rel_err(b, a.float()) <= 2 ** -6
+
+
 @pytest.mark.parametrize("cta_group", [1, 2])
 def test_gemm_int8_bit_exact_against_int8_oracle(cta_group):
     """INT8 W8A8 (tcgen05 kind::i8, int32 accumulate): the activation quantiser reproduces the restated Int8Linear oracle's

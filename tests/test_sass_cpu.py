@@ -64,7 +64,11 @@ def test_attention_kernel_keeps_p_in_tmem_and_uses_packed_math(sass):
     for name, text in att.items():
         assert "UTCHMMA.2CTA" in text and "UTMALDG.2D.2CTA" in text, name
         assert "LDTM" in text and "STTM" in text, name                # S out of TMEM, P back into TMEM
-        assert "MUFU.EX2" in text and "FFMA2" in text and "FMNMX3" in text, name
+        assert "MUFU.EX2" in text and "FADD2" in text, name
+        # the online-softmax form carries the running max (FMNMX3) and the scale/subtract FFMA2; the bounded-score form
+        # (template flag 1: q pre-scaled, p = 2^s) has no max instruction at all
+        bounded = "ELb1EE" in name
+        assert ("FMNMX3" in text) != bounded, name
         assert "HMMA" not in text.replace("UTCHMMA", ""), name
 
 
