@@ -516,30 +516,40 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
     if (warp >= 8) {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
       if (warp == 8) {
-        if (lane == 0) {
-            // ================= TMA producer =================
-            if (cta_rank == 0) mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+        {
+            // ================= TMA producer (whole warp in the loop, one elected lane issues) =================
+            const bool issuer = elect_one_sync();
             const int qr = q_valid ? q_row0 : 0;
-            for (int hf = 0; hf < 2; ++hf)
-                tma_load_2d_cg2(sQ + hf * ATT_HALF_BYTES, &tm128, colQ + hf * 64, row_base + qr, leader_smem_u32(q_full));
+            if (issuer) {
+                if (cta_rank == 0) mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+                for (int hf = 0; hf < 2; ++hf)
+                    tma_load_2d_cg2(sQ + hf * ATT_HALF_BYTES, &tm128, colQ + hf * 64, row_base + qr, leader_smem_u32(q_full));
+            }
+            __syncwarp();
             int ks = 0, vs = 0;
             uint32_t kph = 0, vph = 0;
             auto load_k = [&](int j) {       // my 128 kv rows (half of the 256-row tile) x 128 head dims, two 64-dim halves
                 mbar_wait(&k_empty[ks], kph ^ 1);
-                if (cta_rank == 0) mbar_expect_tx(&k_full[ks], 2 * AT5_STAGE_BYTES);
-                const uint32_t bar = leader_smem_u32(&k_full[ks]);
-                for (int hf = 0; hf < 2; ++hf)
-                    tma_load_2d_cg2(sK + ks * AT5_STAGE_BYTES + hf * ATT_HALF_BYTES, &tm128, colK + hf * 64,
-                                    row_base + j * 256 + cta_rank * ATT_TILE, bar);
+                if (issuer) {
+                    if (cta_rank == 0) mbar_expect_tx(&k_full[ks], 2 * AT5_STAGE_BYTES);
+                    const uint32_t bar = leader_smem_u32(&k_full[ks]);
+                    for (int hf = 0; hf < 2; ++hf)
+                        tma_load_2d_cg2(sK + ks * AT5_STAGE_BYTES + hf * ATT_HALF_BYTES, &tm128, colK + hf * 64,
+                                        row_base + j * 256 + cta_rank * ATT_TILE, bar);
+                }
+                __syncwarp();
                 if (++ks == AT5_KSTAGES) { ks = 0; kph ^= 1; }
             };
             auto load_v = [&](int j) {       // 256 kv rows x my 64 head dims
                 mbar_wait(&v_empty[vs], vph ^ 1);
-                if (cta_rank == 0) mbar_expect_tx(&v_full[vs], 2 * AT5_STAGE_BYTES);
-                const uint32_t bar = leader_smem_u32(&v_full[vs]);
-                for (int hf = 0; hf < 2; ++hf)
-                    tma_load_2d_cg2(sV + vs * AT5_STAGE_BYTES + hf * ATT_HALF_BYTES, &tm128, colV + cta_rank * 64,
-                                    row_base + j * 256 + hf * ATT_TILE, bar);
+                if (issuer) {
+                    if (cta_rank == 0) mbar_expect_tx(&v_full[vs], 2 * AT5_STAGE_BYTES);
+                    const uint32_t bar = leader_smem_u32(&v_full[vs]);
+                    for (int hf = 0; hf < 2; ++hf)
+                        tma_load_2d_cg2(sV + vs * AT5_STAGE_BYTES + hf * ATT_HALF_BYTES, &tm128, colV + cta_rank * 64,
+                                        row_base + j * 256 + hf * ATT_TILE, bar);
+                }
+                __syncwarp();
                 if (++vs == AT5_VSTAGES) { vs = 0; vph ^= 1; }
             };
             load_k(0);
@@ -555,9 +565,14 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
         // and 16 PV instructions — as long as the whole softmax chain (round-2 timing experiments, profiles/r02_attention.md).
         // S and PV touch disjoint TMEM columns and are ordered against the softmax by s_free / p_full / pv_done, not against
         // each other, so the two streams may interleave freely on the (in-order) tensor pipe.
-        if (lane == 0 && cta_rank == 0) {
-            // ================= S issuer (leader) =================
+        if (cta_rank == 0) {
+            // ================= S issuer (leader CTA) =================
+            // The whole warp runs the loop (barrier waits included) and one elected lane issues: loop state and operands stay
+            // provably warp-uniform, so ptxas feeds UTCHMMA from uniform registers directly.  With the loop inside an
+            // `if (lane == 0)` it wrapped EVERY tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (75-100 cycles per issue).
             constexpr uint32_t IDESC_S = umma_idesc_bf16(256, 256, false);
+            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const bool issuer = elect_one_sync();
             int ks = 0;
             uint32_t kph = 0;
             const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(sQ));
@@ -567,20 +582,25 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
                 mbar_wait(&k_full[ks], kph);
                 tc_fence_after();
                 const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(sK + ks * AT5_STAGE_BYTES));
+                if (issuer) {
 #pragma unroll
-                for (int s = 0; s < 8; ++s) {   // 8 x 16 head dims: + 32 B inside a swizzled row, + 16 KB for the second d-half
-                    const uint64_t off = (uint64_t)(((s >> 2) * ATT_HALF_BYTES + (s & 3) * 32) >> 4);
-                    umma_ss_f16_cg2(tmem_base + COL_S, dq + off, dk + off, IDESC_S, s ? 1u : 0u);
+                    for (int s = 0; s < 8; ++s) {   // 8 x 16 head dims: + 32 B inside a swizzled row, + 16 KB for the second d-half
+                        const uint64_t off = (uint64_t)(((s >> 2) * ATT_HALF_BYTES + (s & 3) * 32) >> 4);
+                        umma_ss_f16_cg2(tb + COL_S, dq + off, dk + off, IDESC_S, s ? 1u : 0u);
+                    }
+                    umma_commit_cg2(s_full, 3);
+                    umma_commit_cg2(&k_empty[ks], 3);
                 }
-                umma_commit_cg2(s_full, 3);
-                umma_commit_cg2(&k_empty[ks], 3);
+                __syncwarp();
                 if (++ks == AT5_KSTAGES) { ks = 0; kph ^= 1; }
             }
         }
       } else if (warp == 10) {
-        if (lane == 0 && cta_rank == 0) {
-            // ================= PV issuer (leader) =================
+        if (cta_rank == 0) {
+            // ================= PV issuer (leader CTA; whole warp in the loop, one elected lane issues) =================
             constexpr uint32_t IDESC_O = umma_idesc_bf16(256, 128, true);   // B = V is MN-major
+            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const bool issuer = elect_one_sync();
             int vs = 0;
             uint32_t vph = 0;
             for (int j = 0; j < n_kv; ++j) {
@@ -588,12 +608,14 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm128, const AttnDev p) {
                 mbar_wait(p_full, j & 1);                    // P(j) is in TMEM in both CTAs, O rescaled
                 tc_fence_after();
                 const uint64_t dv = umma_desc_mnmajor_sw128(smem_u32(sV + vs * AT5_STAGE_BYTES), ATT_HALF_BYTES, 1024);
+                if (issuer) {
 #pragma unroll
-                for (int s = 0; s < 16; ++s)    // 16 x 16 kv rows (2 KB of V each); A = P (8 packed columns per step)
-                    umma_ts_f16_cg2(tmem_base, tmem_base + COL_P + s * 8, dv + (uint64_t)(s * 128), IDESC_O,
-                                    (j == 0 && s == 0) ? 0u : 1u);
-                umma_commit_cg2(pv_done, 3);
-                umma_commit_cg2(&v_empty[vs], 3);
+                    for (int s = 0; s < 16; ++s)    // 16 x 16 kv rows (2 KB of V each); A = P (8 packed columns per step)
+                        umma_ts_f16_cg2(tb, tb + COL_P + s * 8, dv + (uint64_t)(s * 128), IDESC_O, (j == 0 && s == 0) ? 0u : 1u);
+                    umma_commit_cg2(pv_done, 3);
+                    umma_commit_cg2(&v_empty[vs], 3);
+                }
+                __syncwarp();
                 if (++vs == AT5_VSTAGES) { vs = 0; vph ^= 1; }
             }
         }

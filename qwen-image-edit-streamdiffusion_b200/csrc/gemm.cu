@@ -201,8 +201,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     griddep_wait();      // everything above overlapped the previous kernel's tail; its output is visible from here on
 
     if (warp == 4) {
-        if (lane == 0) {
+        {
             // ================= TMA producer (every CTA loads its own A rows and its share of W) =================
+            // whole warp in the loop, one elected lane issues (uniform operands: no R2UR waterfall around UTMALDG, see the MMA issuer)
+            const bool issuer = elect_one_sync();
             int stage = 0;
             uint32_t phase = 0;
             // L2 residency: the weight matrix is re-read by every m-unit (33 times at config 2) and fits the 126 MB L2, the
@@ -228,6 +230,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * S::STAGE_BYTES;
                     uint8_t* sb = sa + S::A_BYTES;
+                    if (issuer) {
                     if constexpr (CG == 2) {
                         if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
                         const uint32_t bar = leader_smem_u32(&full_bar[stage]);
@@ -240,6 +243,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         tma_load_2d(sa, &tmA, kb * BK, a_row, &full_bar[stage]);
                         tma_load_2d(sb, tmB, kb * BK, b_row, &full_bar[stage]);
                     }
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -248,8 +253,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         }
     } else if (warp == 5) {
-        if (lane == 0 && cta_rank == 0) {
+        if (cta_rank == 0) {
             // ================= MMA issuer (leader CTA only) =================
+            // The whole warp walks the schedule and waits on the barriers; one elected lane issues.  Loop state and operands are
+            // then provably warp-uniform and UTCHMMA takes them from uniform registers; inside an `if (lane == 0)` loop ptxas
+            // wrapped every tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (5 broadcasts, ~75-100 cycles per issue).
+            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const bool issuer = elect_one_sync();
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -258,29 +268,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const WorkItem wi = decode_item(item, num_tiles, p.tail_tiles, p.tail_split, k_blocks, p.tail_nsplit);
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t d_tmem = tb + acc * BN;
+                const uint32_t idesc = wi.nhalf ? IDESC_H : IDESC;
                 for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
                     const uint64_t da = umma_desc_kmajor_sw128(sa);
                     const uint64_t db = umma_desc_kmajor_sw128(sa + S::A_BYTES);
+                    if (issuer) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {   // 4 x 32 B along the swizzled 128 B row
-                        const uint32_t accum = ((kb - wi.kb0) | k) ? 1u : 0u;
-                        umma_ss<QT, CG>(d_tmem, da + 2 * k, db + 2 * k, wi.nhalf ? IDESC_H : IDESC, accum);
+                        for (int k = 0; k < 4; ++k) {   // 4 x 32 B along the swizzled 128 B row
+                            const uint32_t accum = ((kb - wi.kb0) | k) ? 1u : 0u;
+                            umma_ss<QT, CG>(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+                        }
+                        // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+                        if constexpr (CG == 2) umma_commit_cg2(&empty_bar[stage], 3);
+                        else umma_commit(&empty_bar[stage]);
                     }
-                    // frees the smem slot (in both CTAs of a pair) when these MMAs retire
-                    if constexpr (CG == 2) umma_commit_cg2(&empty_bar[stage], 3);
-                    else umma_commit(&empty_bar[stage]);
+                    __syncwarp();
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
                 // accumulator complete -> epilogue warps (of both CTAs)
-                if constexpr (CG == 2) umma_commit_cg2(&tfull_bar[acc], 3);
-                else umma_commit(&tfull_bar[acc]);
+                if (issuer) {
+                    if constexpr (CG == 2) umma_commit_cg2(&tfull_bar[acc], 3);
+                    else umma_commit(&tfull_bar[acc]);
+                }
+                __syncwarp();
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1;
