@@ -445,25 +445,75 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             [[maybe_unused]] float rinv_head = 1.f;
             [[maybe_unused]] float rmax[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // q8_amax: max|out| of my 8 rows over this tile
             if (!dummy) {
+                // `which` (0 q, 1 k, 2 v) is a property of the tile: D % BN == 0
+                const int which = EPI == QIE_EPI_QKV_NORM_ROPE ? n_base / p.model_dim : 2;
+                const bool normed = EPI == QIE_EPI_QKV_NORM_ROPE && which != 2;
+                // Global operands of a chunk (bias, gate, norm weight, rope rows / residual rows): the loads of chunk c + 1 are
+                // issued before the math and the stores of chunk c, so their L2 latency (~1 us under load, it was > 50 % of the
+                // epilogue warps' stall samples in the ncu source view) is covered by work instead of being exposed once per chunk.
+                struct ChunkOps { float4 bv, wsc, g4, nw4, aux[8]; };
+                auto fetch_ops = [&](int c, ChunkOps& o) {
+                    const int n0 = n_base + c * 32;
+                    o.bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (bias && !normed) o.bv = *reinterpret_cast<const float4*>(bias + n0 + c4);
+                    o.wsc = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if constexpr (FP8) o.wsc = *reinterpret_cast<const float4*>(p.w_scale[m.s] + n0 + c4);
+                    o.g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if constexpr (EPI == QIE_EPI_GATE_RESID_F32)
+                        o.g4 = *reinterpret_cast<const float4*>(p.gate + m.b * p.gate_bstride + m.s * p.gate_sstride + n0 + c4);
+                    o.nw4 = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if constexpr (EPI == QIE_EPI_QKV_NORM_ROPE) {
+                        if (normed) {
+                            o.nw4 = *reinterpret_cast<const float4*>(p.qk_norm_w[m.s][which] + (c & 3) * 32 + c4);
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) {
+                                const int rr = it * 4 + sub;
+                                o.aux[it] = local0 + rr < seg_rows
+                                                ? __ldg(reinterpret_cast<const float4*>(
+                                                      p.rope + (long long)(jrow0_in_batch + rr) * 128 + (c & 3) * 32 + c4))
+                                                : make_float4(1.f, 0.f, 1.f, 0.f);
+                            }
+                        }
+                    }
+                    if constexpr (EPI == QIE_EPI_GATE_RESID_F32) {
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int rr = it * 4 + sub;
+                            o.aux[it] = local0 + rr < seg_rows
+                                            ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) +
+                                                                               (orow0 + rr) * p.ldo + n0 + c4)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                };
+                [[maybe_unused]] float asc[8];     // per-row activation scale (8-bit operands): the same for every chunk of the tile
+                if constexpr (FP8) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) asc[it] = normed ? 1.f : p.a_scale[arow0 + it * 4 + sub];
+                }
+                ChunkOps nxt;
+                fetch_ops(0, nxt);
 #pragma unroll 1
                 for (int c = 0; c < n_chunks; ++c) {
                     const int n0 = n_base + c * 32;
-                    int which = 2;
                     if constexpr (EPI == QIE_EPI_QKV_NORM_ROPE) {
-                        which = n_base / p.model_dim;                         // 0 q, 1 k, 2 v (D % BN == 0)
                         if (which != 2 && (c & 3) == 0) {                     // first chunk of a head: row RMS over 128 cols
+                            // the four TMEM loads of the head are pipelined two deep (chunk cc + 1 in flight while cc is squared)
                             float ss = 0.f;
-#pragma unroll 1
-                            for (int cc = c; cc < c + 4; ++cc) {
-                                uint32_t r[32];
-                                tmem_ld32(t_addr + cc * 32, r);
+                            uint32_t ra[32], rb[32];
+                            tmem_ld32(t_addr + c * 32, ra);
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc) {
+                                uint32_t(&r)[32] = (cc & 1) ? rb : ra;
+                                uint32_t(&rn)[32] = (cc & 1) ? ra : rb;
                                 tmem_ld_wait();
+                                if (cc < 3) tmem_ld32(t_addr + (c + cc + 1) * 32, rn);
 #pragma unroll
                                 for (int i = 0; i < 32; i += 4) {
-                                    const float4 bv = *reinterpret_cast<const float4*>(bias + n_base + cc * 32 + i);
+                                    const float4 bv = *reinterpret_cast<const float4*>(bias + n_base + (c + cc) * 32 + i);
                                     float4 ws = make_float4(1.f, 1.f, 1.f, 1.f);
                                     if constexpr (FP8) {
-                                        ws = *reinterpret_cast<const float4*>(p.w_scale[m.s] + n_base + cc * 32 + i);
+                                        ws = *reinterpret_cast<const float4*>(p.w_scale[m.s] + n_base + (c + cc) * 32 + i);
                                         ws.x *= as_row; ws.y *= as_row; ws.z *= as_row; ws.w *= as_row;
                                     }
                                     const float a0 = accf(r[i]) * ws.x + bv.x;
@@ -481,7 +531,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         if (from_scratch) stage_from_scratch(c);
                         else stage_chunk(c, 1.f, false);
                     }
-                    const bool normed = EPI == QIE_EPI_QKV_NORM_ROPE && which != 2;
                     // sequence-parallel scatter: this 32-column chunk belongs to one head, i.e. to one destination rank;
                     // image rows go to row (my_rank * img_pad + local row) of that rank's gathered [q|k|v] buffer, text rows
                     // behind the image shards of all ranks at their index in the whole text sequence
@@ -497,44 +546,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         }
                     }
 
-                    // phase 2: issue every global load of this chunk first, then do the math and the stores
-                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (bias && !normed) bv = *reinterpret_cast<const float4*>(bias + n0 + c4);
-                    [[maybe_unused]] float4 wsc = make_float4(1.f, 1.f, 1.f, 1.f);
-                    if constexpr (FP8) wsc = *reinterpret_cast<const float4*>(p.w_scale[m.s] + n0 + c4);
-                    [[maybe_unused]] float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if constexpr (EPI == QIE_EPI_GATE_RESID_F32)
-                        g4 = *reinterpret_cast<const float4*>(p.gate + m.b * p.gate_bstride + m.s * p.gate_sstride + n0 + c4);
-                    [[maybe_unused]] float4 nw4 = make_float4(1.f, 1.f, 1.f, 1.f);
-                    [[maybe_unused]] float4 aux[8];      // residual rows (GATE_RESID) or rope rows (QKV)
-                    if constexpr (EPI == QIE_EPI_QKV_NORM_ROPE) {
-                        if (normed) {
-                            nw4 = *reinterpret_cast<const float4*>(p.qk_norm_w[m.s][which] + (c & 3) * 32 + c4);
-#pragma unroll
-                            for (int it = 0; it < 8; ++it) {
-                                const int rr = it * 4 + sub;
-                                aux[it] = local0 + rr < seg_rows
-                                              ? __ldg(reinterpret_cast<const float4*>(
-                                                    p.rope + (long long)(jrow0_in_batch + rr) * 128 + (c & 3) * 32 + c4))
-                                              : make_float4(1.f, 0.f, 1.f, 0.f);
-                            }
-                        }
-                    }
-                    if constexpr (EPI == QIE_EPI_GATE_RESID_F32) {
-#pragma unroll
-                        for (int it = 0; it < 8; ++it) {
-                            const int rr = it * 4 + sub;
-                            aux[it] = local0 + rr < seg_rows
-                                          ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) +
-                                                                             (orow0 + rr) * p.ldo + n0 + c4)
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                    }
-                    [[maybe_unused]] float asc[8];
-                    if constexpr (FP8) {
-#pragma unroll
-                        for (int it = 0; it < 8; ++it) asc[it] = normed ? 1.f : p.a_scale[arow0 + it * 4 + sub];
-                    }
+                    // phase 2: this chunk's operands were fetched one chunk ago; issue the next chunk's loads, then math and stores
+                    const ChunkOps cur = nxt;
+                    if (c + 1 < n_chunks) fetch_ops(c + 1, nxt);
+                    const float4 bv = cur.bv, g4 = cur.g4, nw4 = cur.nw4;
+                    [[maybe_unused]] const float4 wsc = cur.wsc;
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int rr = it * 4 + sub;
@@ -546,7 +562,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             }
                         }
                         if (normed) {
-                            const float4 cs = aux[it];
+                            const float4 cs = cur.aux[it];
                             const float x0 = v.x * nw4.x, x1 = v.y * nw4.y, x2 = v.z * nw4.z, x3 = v.w * nw4.w;
                             v.x = x0 * cs.x - x1 * cs.y; v.y = x0 * cs.y + x1 * cs.x;
                             v.z = x2 * cs.z - x3 * cs.w; v.w = x2 * cs.w + x3 * cs.z;
@@ -559,7 +575,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         }
                         if constexpr (EPI == QIE_EPI_GATE_RESID_F32) {
                             if (valid) {
-                                float4 r4 = aux[it];
+                                float4 r4 = cur.aux[it];
                                 r4.x += g4.x * v.x; r4.y += g4.y * v.y; r4.z += g4.z * v.z; r4.w += g4.w * v.w;
                                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (orow0 + rr) * p.ldo + n0 + c4) = r4;
                             }
