@@ -110,6 +110,16 @@ __device__ __forceinline__ void tile_to_mn(int tile, int m_units, int n_blocks, 
     nb = local / gm;
 }
 
+// QKV epilogue: the q and k tiles carry the long epilogue (RMS pre-pass, RoPE), the v tiles the short one.  A pair walks the
+// schedule in steps of ~4.6 n-blocks, i.e. through runs of ~5 long epilogues (which stall the tensor pipe: two accumulator
+// stages only) followed by short ones (which leave the epilogue warps idle).  Interleaving the three column groups in the
+// schedule (n-block i of the schedule = block i/3 of group i%3) alternates them, so the two stages absorb the difference.
+template <int EPI>
+__device__ __forceinline__ int schedule_nb(int nb, int n_blocks) {
+    if constexpr (EPI == QIE_EPI_QKV_NORM_ROPE) return (nb % 3) * (n_blocks / 3) + nb / 3;
+    return nb;
+}
+
 // Work items of the persistent schedule: the first (num_tiles - tail_tiles) items are whole tiles; every remaining tile
 // is `tail_split` items, each covering one K range.
 struct WorkItem {
@@ -216,6 +226,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const WorkItem wi = decode_item(item, num_tiles, p.tail_tiles, p.tail_split, k_blocks, p.tail_nsplit);
                 int mu, nb;
                 tile_to_mn(wi.tile, m_units, p.n_blocks, mu, nb, p.group_m);
+                nb = schedule_nb<EPI>(nb, p.n_blocks);
                 const MUnit m = decode_munit<CG>(p, mu);
                 const int seg_pad = m.s ? p.seq.txt_pad : p.seq.img_pad;
                 int ti = m.ti + cta_rank;
@@ -319,6 +330,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const WorkItem wi = decode_item(item, num_tiles, p.tail_tiles, p.tail_split, k_blocks, p.tail_nsplit);
             int mu, nb;
             tile_to_mn(wi.tile, m_units, p.n_blocks, mu, nb, p.group_m);
+            nb = schedule_nb<EPI>(nb, p.n_blocks);
             const MUnit m = decode_munit<CG>(p, mu);
             const int seg_pad = m.s ? p.seq.txt_pad : p.seq.img_pad;
             const int seg_rows = m.s ? p.seq.txt_rows_b[m.b] : p.seq.img_rows;
