@@ -4,8 +4,10 @@
 //
 // Two kernels: attn_pair_kernel (default: a CTA pair per 256 query rows, cta_group::2 MMAs, 256-wide KV tiles, P in TMEM) and
 // attn_kernel (single-CTA fallback, variant bit 0x8; also the A/B yard-stick).  The kernels that lost the round-1 A/B runs
-// (first pair kernels, persistent / speculative / traced builds; the round-2 ping-pong kernel with two Q super-tiles per pair)
-// live in the git history (commits 550b982 and before; "Ping-pong CTA-pair attention kernel"), measurements in profiles/.
+// (first pair kernels, persistent / speculative / traced builds; the round-2 ping-pong kernel with two Q super-tiles per pair; the
+// bounded-score kernel with S delivered in two staggered column halves, with and without a MUFU hand-over between partner warps)
+// live in the git history (commits 550b982 and before; "Ping-pong CTA-pair attention kernel"; "staggered bounded-score kernel"),
+// measurements in profiles/.
 //
 // attn_kernel: one CTA = one (batch, head) x 256 query rows = two 128-row Q tiles that ping-pong on the tensor pipe:
 //   warp 0 / lane 0 : TMA producer (Q tiles once; K_j, V_j tiles through a ring, 128 rows x 128 dims each)
@@ -873,286 +875,6 @@ static int launch_attn_pair(const CUtensorMap& tm128, const AttnDev& p, dim3 gri
 }
 
 
-// =====================================================================================================================
-// Bounded-score CTA-pair attention with the score tile delivered in two column halves ("staggered" form, variant 0x400).
-// Same data flow as attn_pair_kernel<POLY, true> (q pre-scaled, p = 2^s, no running max), but S(j) = Q K_j^T is issued as two
-// independent N = 128 MMA groups with their own barriers: S_lo (kv rows [0,128) of the tile, consumed by softmax warpgroup 0)
-// completes 512 tensor cycles before S_hi (kv rows [128,256), warpgroup 1), and O += P V is issued per half as soon as that half
-// of P is in TMEM.  The two softmax warps that share a scheduler (and its MUFU) therefore run half a tile apart: while one is in
-// its exponentials the other loads / stores TMEM, instead of both hitting the MUFU at once and both leaving it idle afterwards
-// (profiles/r02_attention.md: the lock-step cost ~970 of 2870 cycles per tile).  Without a running max nothing couples the halves.
-// K staging: each CTA holds rows [64 r, 64 r + 64) of BOTH 128-row halves (the pair's N = 128 B operand is 64 rows per CTA),
-// as [half][d-half][64 rows x 128 B] = 4 x 8 KB per stage.
-// =====================================================================================================================
-template <int POLY>
-__global__ void __launch_bounds__(AT5_THREADS, 1)
-attn_stagger_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm64, const AttnDev p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                                       // [2 d-halves][128 rows x 128 B]
-    uint8_t* sK = smem + ATT_TILE_BYTES;                      // [K stages][2 kv halves][2 d-halves][64 kv rows x 128 B]
-    uint8_t* sV = sK + AT5_KSTAGES * AT5_STAGE_BYTES;         // [V stages][256 kv rows x 128 B (my 64 dims)]
-    float* xl = reinterpret_cast<float*>(sV + AT5_VSTAGES * AT5_STAGE_BYTES);   // [2 WGs][128 rows] partial row sums
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xl + 256);
-    uint64_t* q_full = bars;                       // leader
-    uint64_t* k_full = bars + 1;                   // [K stages] leader
-    uint64_t* k_empty = k_full + AT5_KSTAGES;      // both
-    uint64_t* v_full = k_empty + AT5_KSTAGES;      // [V stages] leader
-    uint64_t* v_empty = v_full + AT5_VSTAGES;      // both
-    uint64_t* s_full = v_empty + AT5_VSTAGES;      // [2 halves] both
-    uint64_t* s_free = s_full + 2;                 // [2 halves] leader, 8 warp arrivals each (one warpgroup in each CTA)
-    uint64_t* p_full = s_free + 2;                 // [2 halves] leader, 8 warp arrivals each
-    uint64_t* pv_done = p_full + 2;                // [2 halves] both
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
-
-    const int warp = threadIdx.x >> 5, lane = lane_id();
-    const int cta_rank = (int)cluster_ctarank();
-    const int rpb = p.seq.img_pad + p.seq.txt_pad;
-    const int n128 = rpb / ATT_TILE;
-    const int n_kv = (n128 + 1) / 2;               // 256-row KV tiles (the last one may be half empty)
-    const int head = blockIdx.y, b = blockIdx.z;
-    const int q_row0 = (blockIdx.x >> 1) * 2 * ATT_TILE + cta_rank * ATT_TILE;
-    const bool q_valid = q_row0 < rpb;
-    const int D = p.H * ATT_TILE;
-    const int colQ = head * ATT_TILE, colK = D + head * ATT_TILE, colV = 2 * D + head * ATT_TILE;
-    const int row_base = b * rpb;
-    griddep_launch_dependents();
-
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tm128);
-        tma_prefetch_desc(&tm64);
-        mbar_init(q_full, 1);
-        for (int i = 0; i < AT5_KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
-        for (int i = 0; i < AT5_VSTAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-        for (int h = 0; h < 2; ++h) {
-            mbar_init(&s_full[h], 1);
-            mbar_init(&s_free[h], 8);
-            mbar_init(&p_full[h], 8);
-            mbar_init(&pv_done[h], 1);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 9) tmem_alloc_cg2<512>(tmem_slot);
-    tc_fence_before();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t COL_S = 128, COL_P = 384;
-    constexpr int KQ = 8 * 1024;                   // one [64 rows x 128 B] K block
-    griddep_wait();
-
-    if (warp >= 8) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-      if (warp == 8) {
-        // ================= TMA producer (whole warp in the loop, one elected lane issues) =================
-        const bool issuer = elect_one_sync();
-        const int qr = q_valid ? q_row0 : 0;
-        if (issuer) {
-            if (cta_rank == 0) mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
-            for (int hf = 0; hf < 2; ++hf)
-                tma_load_2d_cg2(sQ + hf * ATT_HALF_BYTES, &tm128, colQ + hf * 64, row_base + qr, leader_smem_u32(q_full));
-        }
-        __syncwarp();
-        int ks = 0, vs = 0;
-        uint32_t kph = 0, vph = 0;
-        auto load_k = [&](int j) {       // my 64 kv rows of each 128-row half x 128 head dims
-            mbar_wait(&k_empty[ks], kph ^ 1);
-            if (issuer) {
-                if (cta_rank == 0) mbar_expect_tx(&k_full[ks], 2 * AT5_STAGE_BYTES);
-                const uint32_t bar = leader_smem_u32(&k_full[ks]);
-                for (int h = 0; h < 2; ++h)
-                    for (int hf = 0; hf < 2; ++hf)
-                        tma_load_2d_cg2(sK + ks * AT5_STAGE_BYTES + (h * 2 + hf) * KQ, &tm64, colK + hf * 64,
-                                        row_base + j * 256 + h * ATT_TILE + cta_rank * 64, bar);
-            }
-            __syncwarp();
-            if (++ks == AT5_KSTAGES) { ks = 0; kph ^= 1; }
-        };
-        auto load_v = [&](int j) {       // 256 kv rows x my 64 head dims
-            mbar_wait(&v_empty[vs], vph ^ 1);
-            if (issuer) {
-                if (cta_rank == 0) mbar_expect_tx(&v_full[vs], 2 * AT5_STAGE_BYTES);
-                const uint32_t bar = leader_smem_u32(&v_full[vs]);
-                for (int hf = 0; hf < 2; ++hf)
-                    tma_load_2d_cg2(sV + vs * AT5_STAGE_BYTES + hf * ATT_HALF_BYTES, &tm128, colV + cta_rank * 64,
-                                    row_base + j * 256 + hf * ATT_TILE, bar);
-            }
-            __syncwarp();
-            if (++vs == AT5_VSTAGES) { vs = 0; vph ^= 1; }
-        };
-        load_k(0);
-        for (int j = 0; j < n_kv; ++j) {
-            if (j + 1 < n_kv) load_k(j + 1);
-            load_v(j);
-        }
-      } else if (warp == 9) {
-        if (cta_rank == 0) {
-            // ================= S issuer (leader CTA; whole warp in the loop, one elected lane issues) =================
-            constexpr uint32_t IDESC_S = umma_idesc_bf16(256, 128, false);
-            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-            const bool issuer = elect_one_sync();
-            int ks = 0;
-            uint32_t kph = 0;
-            const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(sQ));
-            mbar_wait(q_full, 0);
-            for (int j = 0; j < n_kv; ++j) {
-                mbar_wait(&k_full[ks], kph);
-                for (int h = 0; h < 2; ++h) {
-                    if (j > 0) mbar_wait(&s_free[h], (j - 1) & 1);   // this half of S(j-1) is in registers in both CTAs
-                    tc_fence_after();
-                    const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(sK + ks * AT5_STAGE_BYTES + h * 2 * KQ));
-                    if (issuer) {
-#pragma unroll
-                        for (int s = 0; s < 8; ++s) {   // 8 x 16 head dims: + 32 B inside a swizzled row; second d-half 16 KB (Q) / 8 KB (K) on
-                            const uint64_t offq = (uint64_t)(((s >> 2) * ATT_HALF_BYTES + (s & 3) * 32) >> 4);
-                            const uint64_t offk = (uint64_t)(((s >> 2) * KQ + (s & 3) * 32) >> 4);
-                            umma_ss_f16_cg2(tb + COL_S + h * 128, dq + offq, dk + offk, IDESC_S, s ? 1u : 0u);
-                        }
-                        umma_commit_cg2(&s_full[h], 3);
-                        if (h == 1) umma_commit_cg2(&k_empty[ks], 3);
-                    }
-                    __syncwarp();
-                }
-                if (++ks == AT5_KSTAGES) { ks = 0; kph ^= 1; }
-            }
-        }
-      } else if (warp == 10) {
-        if (cta_rank == 0) {
-            // ================= PV issuer (leader CTA): each half of P feeds its 8 k-steps as soon as it is in TMEM =================
-            constexpr uint32_t IDESC_O = umma_idesc_bf16(256, 128, true);   // B = V is MN-major
-            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-            const bool issuer = elect_one_sync();
-            int vs = 0;
-            uint32_t vph = 0;
-            for (int j = 0; j < n_kv; ++j) {
-                mbar_wait(&v_full[vs], vph);
-                const uint64_t dv = umma_desc_mnmajor_sw128(smem_u32(sV + vs * AT5_STAGE_BYTES), ATT_HALF_BYTES, 1024);
-                for (int h = 0; h < 2; ++h) {
-                    mbar_wait(&p_full[h], j & 1);
-                    tc_fence_after();
-                    if (issuer) {
-#pragma unroll
-                        for (int s = 0; s < 8; ++s)     // 8 x 16 kv rows of this half (2 KB of V each); A = P (8 packed columns per step)
-                            umma_ts_f16_cg2(tb, tb + COL_P + (h * 8 + s) * 8, dv + (uint64_t)((h * 8 + s) * 128), IDESC_O,
-                                            (j == 0 && h == 0 && s == 0) ? 0u : 1u);
-                        umma_commit_cg2(&pv_done[h], 3);
-                        if (h == 1) umma_commit_cg2(&v_empty[vs], 3);
-                    }
-                    __syncwarp();
-                }
-                if (++vs == AT5_VSTAGES) { vs = 0; vph ^= 1; }
-            }
-        }
-      }
-    } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-        // ================= softmax (warps 0-7): warpgroup wg owns kv half wg of every tile, on its own barriers =================
-        const int wg = warp >> 2;
-        const int quad = warp & 3;
-        const int r = quad * 32 + lane;
-        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        const uint32_t tS = tmem_base + lane_addr + COL_S + wg * 128;
-        const uint32_t tP = tmem_base + lane_addr + COL_P + wg * 64;
-        const uint32_t tO = tmem_base + lane_addr + wg * 64;
-        uint64_t l2 = pk2(0.f, 0.f);
-        auto valid_rows = [&](int t128) -> int {
-            return t128 < n128 ? (p.tile_valid ? __ldg(p.tile_valid + t128) : kv_valid_rows(p.seq, t128, b)) : 0;
-        };
-        int nv_next = valid_rows(wg);
-        for (int j = 0; j < n_kv; ++j) {
-            const int nv = nv_next;
-            mbar_wait(&s_full[wg], j & 1);
-            tc_fence_after();
-            uint32_t s[128];
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t(&dst)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[ch * 32]);
-                tmem_ld32(tS + ch * 32, dst);
-            }
-            nv_next = valid_rows(2 * (j + 1) + wg);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(leader_smem_u32(&s_free[wg]));   // the tensor pipe may refill my half of S
-            if (nv == ATT_TILE) {
-#pragma unroll
-                for (int i = 0; i < 128; i += 2) {
-                    const float x0 = __uint_as_float(s[i]), x1 = __uint_as_float(s[i + 1]);
-                    float e0, e1;
-                    if (((i >> 1) & 7) < POLY) {
-                        // FMA-pipe exp2: x = n + f, 2^f by a degree-3 polynomial, 2^n via the exponent (|x| <= 80: no clamp needed)
-                        const uint64_t X = pk2(x0, x1);
-                        const uint64_t T = add2(X, pk2(12582912.f, 12582912.f));
-                        const uint64_t N = add2(T, pk2(-12582912.f, -12582912.f));
-                        const uint64_t Fr = fma2(N, pk2(-1.f, -1.f), X);
-                        uint64_t P = fma2(Fr, pk2(0.0551716574f, 0.0551716574f), pk2(0.2426111400f, 0.2426111400f));
-                        P = fma2(P, Fr, pk2(0.6932609677f, 0.6932609677f));
-                        P = fma2(P, Fr, pk2(0.9999280572f, 0.9999280572f));
-                        float t0, t1, p0, p1;
-                        upk2(T, t0, t1);
-                        upk2(P, p0, p1);
-                        e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-                        e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
-                    } else {
-                        e0 = fast_exp2(x0);
-                        e1 = fast_exp2(x1);
-                    }
-                    l2 = add2(l2, pk2(e0, e1));
-                    s[i >> 1] = pack_bf16(e0, e1);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 128; i += 2) {
-                    const float e0 = i < nv ? fast_exp2(__uint_as_float(s[i])) : 0.f;
-                    const float e1 = i + 1 < nv ? fast_exp2(__uint_as_float(s[i + 1])) : 0.f;
-                    l2 = add2(l2, pk2(e0, e1));
-                    s[i >> 1] = pack_bf16(e0, e1);
-                }
-            }
-            if (j > 0) {
-                mbar_wait(&pv_done[wg], (j - 1) & 1);      // the PV MMAs that read my half of P(j-1) have retired
-                tc_fence_after();
-            }
-            {
-                uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
-                uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
-                tmem_st32(tP, lo);
-                tmem_st32(tP + 32, hi);
-                tmem_st_wait();
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(leader_smem_u32(&p_full[wg]));
-        }
-        // all PV MMAs retire in issue order: the second half's commit of the last tile covers the whole accumulator
-        pair_epilogue(p, l2, xl, &pv_done[1], (n_kv - 1) & 1, tO, wg, quad, r, q_valid, q_row0, row_base, D, head, b);
-    }
-
-    __syncwarp();
-    tc_fence_before();
-    cluster_sync_all();
-    if (warp == 9) {
-        tc_fence_after();
-        tmem_dealloc_cg2<512>(tmem_base);
-    }
-}
-
-template <int POLY>
-static int launch_attn_stagger(const CUtensorMap& tm128, const CUtensorMap& tm64, const AttnDev& p, dim3 grid, cudaStream_t st) {
-    QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(attn_stagger_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT5_SMEM));
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(AT5_THREADS);
-    cfg.dynamicSmemBytes = AT5_SMEM;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[2];
-    cfg.attrs = attr;
-    cfg.numAttrs = launch_attrs(attr, 2);
-    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_stagger_kernel<POLY>, tm128, tm64, p));
-    QIE_LAUNCH_OK("attn_stagger_kernel");
-    return QIE_OK;
-}
-
 
 }  // namespace qie
 
@@ -1207,12 +929,11 @@ int attn_fwd_peers(const void* qkv_gathered, void* const* peer_out_dev, const qi
 static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int* tile_valid, int num_heads, int variant,
                        void* stream, const AttnScatter* sc) {
     if (variant == 0) variant = 0x20;
-    if ((variant & ~0x600) == 0 && variant) variant |= 0x20;
-    const int poly = (variant >> 4) & 15, single = (variant >> 3) & 1, fixed = (variant >> 9) & 1, stagger = (variant >> 10) & 1;
-    QIE_REQUIRE((variant & ~0x7F8) == 0 && (poly == 0 || poly == 2 || poly == 3 || poly == 4), QIE_EINVAL,
+    if (variant == 0x200) variant = 0x230;    // bounded-score default: 3 of every 8 score pairs on the polynomial
+    const int poly = (variant >> 4) & 15, single = (variant >> 3) & 1, fixed = (variant >> 9) & 1;
+    QIE_REQUIRE((variant & ~0x3F8) == 0 && (poly == 0 || poly == 2 || poly == 3 || poly == 4), QIE_EINVAL,
                 "qie_attn_fwd: bad variant 0x%x", variant);
     QIE_REQUIRE(!(fixed && single), QIE_EINVAL, "qie_attn_fwd: the bounded-score form (0x200) is a CTA-pair kernel");
-    QIE_REQUIRE(!stagger || fixed, QIE_EINVAL, "qie_attn_fwd: the staggered form (0x400) needs bounded scores (0x200)");
     const int rpb = seq->img_pad + seq->txt_pad;
     const int D = num_heads * 128;
     CUtensorMap tm;
@@ -1253,17 +974,6 @@ static int attn_launch(const void* qkv, void* out, const qie_seq* seq, const int
         }
     }
     grid.x *= 2;     // a cluster of two CTAs per 256 query rows
-    if (stagger) {
-        CUtensorMap tm64;    // K blocks of 64 kv rows (each CTA's share of a 128-row half tile)
-        rc = make_tmap_2d(&tm64, qkv, (uint64_t)seq->batch * rpb, (uint64_t)3 * D, (uint64_t)3 * D * 2, 64, 64, 2);
-        if (rc) return rc;
-        switch (poly) {
-            case 0: return launch_attn_stagger<0>(tm, tm64, p, grid, st);
-            case 2: return launch_attn_stagger<2>(tm, tm64, p, grid, st);
-            case 3: return launch_attn_stagger<3>(tm, tm64, p, grid, st);
-            case 4: return launch_attn_stagger<4>(tm, tm64, p, grid, st);
-        }
-    }
     if (fixed) {
         switch (poly) {
             case 0: return launch_attn_pair<0, true>(tm, p, grid, st);

@@ -354,6 +354,9 @@ __device__ __forceinline__ void umma_ts_f16_cg2(uint32_t d_tmem, uint32_t a_tmem
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 // commit of the pair's MMAs, arriving on the mbarrier at this smem offset in every CTA of `cta_mask`
 __device__ __forceinline__ void umma_commit_cg2(uint64_t* bar, uint16_t cta_mask) {
     asm volatile(

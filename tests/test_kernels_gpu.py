@@ -403,7 +403,7 @@ def test_attention_score_jumps_between_tiles(variant, jump):
 
 
 @pytest.mark.parametrize("B,img,txt,H", [(1, 256, 128, 2), (2, 200, 19, 2), (1, 1024, 219, 3), (1, 1500, 300, 2), (1, 384, 128, 1)])
-@pytest.mark.parametrize("variant", [0x200, 0x300, 0x230, 0x240, 0x600, 0x700, 0x630, 0x640])   # 0x400: staggered halves
+@pytest.mark.parametrize("variant", [0x200, 0x300, 0x220, 0x240])
 @pytest.mark.parametrize("wnorm", [1.0, 2.2])
 def test_attention_bounded_scores(B, img, txt, H, variant, wnorm):
     """Bounded-score form (0x200): q and k are RMS-normed rows with norm weight `wnorm` (|q.k| * scale * log2e <= 16.3 wnorm^2,
@@ -444,9 +444,8 @@ def test_attention_bounded_equals_online_softmax():
     a = K.attn(s, x.reshape(-1, 3 * D).to(torch.bfloat16), H, 0)
     xq = x.clone()
     xq[:, 0] *= 0.08838834764831845 * 1.4426950408889634
-    for variant in (0x200, 0x600):
-        b = K.attn(s, xq.reshape(-1, 3 * D).to(torch.bfloat16), H, variant)
-        assert K.rel_err(b, a.float()) <= 2 ** -6, hex(variant)
+    b = K.attn(s, xq.reshape(-1, 3 * D).to(torch.bfloat16), H, 0x200)
+    assert K.rel_err(b, a.float()) <= 2 ** -6
 
 
 @pytest.mark.parametrize("cta_group", [1, 2])

@@ -22,7 +22,7 @@ for img, txt in ((8192, 256), (8192, 219), (2048, 256)):
     flops = 4.0 * S * S * 128 * H
     qkv_b = qkv.clone()                               # bounded-score variants (0x200) take q pre-multiplied by scale * log2(e)
     qkv_b[:, : H * 128] = (qkv_b[:, : H * 128].float() * (0.08838834764831845 * 1.4426950408889634)).bfloat16()
-    for v in ([int(x, 0) for x in sys.argv[1:]] or (0x20, 0x28, 0x220, 0x230, 0x240, 0x620, 0x630, 0x640, 0x700)):
+    for v in ([int(x, 0) for x in sys.argv[1:]] or (0x20, 0x100, 0x28, 0x220, 0x230, 0x240, 0x300)):
         ms = bench(lambda: K.attn(s, qkv_b if v & 0x200 else qkv, H, v))
         print(f"attn img={img} txt={txt} variant={v:#x}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s", flush=True)
     x = qkv[: S].reshape(1, S, 3, H, 128)
