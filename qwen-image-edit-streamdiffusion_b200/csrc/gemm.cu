@@ -72,7 +72,8 @@ struct GemmSmem {
     static constexpr int BAR_BYTES = 512;                                   // ring + TMEM barriers, tmem slot, 16 LN landing barriers
     static constexpr int EPI_ROW_BYTES = 144;                               // 32 fp32 + 16 B pad: conflict-free both ways
     static constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_BYTES;               // per-warp transpose staging
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 4 * EPI_WARP_BYTES + 1024;   // +1024: manual alignment
+    static constexpr int COLV_BYTES = 2 * BN * 4;                           // per-warp copy of the tile's bias | weight scales (QKV epilogue)
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 4 * EPI_WARP_BYTES + 4 * COLV_BYTES + 1024;   // +1024: manual alignment
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;             // two accumulator stages
 };
 
@@ -108,16 +109,6 @@ __device__ __forceinline__ void tile_to_mn(int tile, int m_units, int n_blocks, 
     const int local = tile - band * group_m * n_blocks;
     mu = first + local % gm;
     nb = local / gm;
-}
-
-// QKV epilogue: the q and k tiles carry the long epilogue (RMS pre-pass, RoPE), the v tiles the short one.  A pair walks the
-// schedule in steps of ~4.6 n-blocks, i.e. through runs of ~5 long epilogues (which stall the tensor pipe: two accumulator
-// stages only) followed by short ones (which leave the epilogue warps idle).  Interleaving the three column groups in the
-// schedule (n-block i of the schedule = block i/3 of group i%3) alternates them, so the two stages absorb the difference.
-template <int EPI>
-__device__ __forceinline__ int schedule_nb(int nb, int n_blocks) {
-    if constexpr (EPI == QIE_EPI_QKV_NORM_ROPE) return (nb % 3) * (n_blocks / 3) + nb / 3;
-    return nb;
 }
 
 // Work items of the persistent schedule: the first (num_tiles - tail_tiles) items are whole tiles; every remaining tile
@@ -226,7 +217,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const WorkItem wi = decode_item(item, num_tiles, p.tail_tiles, p.tail_split, k_blocks, p.tail_nsplit);
                 int mu, nb;
                 tile_to_mn(wi.tile, m_units, p.n_blocks, mu, nb, p.group_m);
-                nb = schedule_nb<EPI>(nb, p.n_blocks);
                 const MUnit m = decode_munit<CG>(p, mu);
                 const int seg_pad = m.s ? p.seq.txt_pad : p.seq.img_pad;
                 int ti = m.ti + cta_rank;
@@ -330,7 +320,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const WorkItem wi = decode_item(item, num_tiles, p.tail_tiles, p.tail_split, k_blocks, p.tail_nsplit);
             int mu, nb;
             tile_to_mn(wi.tile, m_units, p.n_blocks, mu, nb, p.group_m);
-            nb = schedule_nb<EPI>(nb, p.n_blocks);
             const MUnit m = decode_munit<CG>(p, mu);
             const int seg_pad = m.s ? p.seq.txt_pad : p.seq.img_pad;
             const int seg_rows = m.s ? p.seq.txt_rows_b[m.b] : p.seq.img_rows;
@@ -344,6 +333,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const float* bias = p.bias[m.s];
             const int n_base = nb * BN + (wi.nhalf ? wi.part * BNH : 0);      // first output column of this item
             const int n_chunks = wi.nhalf ? BNH / 32 : BN / 32;               // 32-column chunks of this item
+
+            // QKV epilogue, q / k tiles: every thread of the row layout needs the bias (and weight scale) of every column of the
+            // tile, twice (RMS pre-pass, staging).  As global loads their L2 latency was exposed once per 32-column chunk and pass
+            // (the top stall sites of the ncu source view); a per-warp copy in shared memory is fetched before the accumulator is
+            // waited for, so its latency hides behind the main loop.
+            [[maybe_unused]] float* cbias = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + S::BAR_BYTES + 4 * S::EPI_WARP_BYTES +
+                                                                      warp * S::COLV_BYTES);
+            if constexpr (EPI == QIE_EPI_QKV_NORM_ROPE) {
+                if (n_base / p.model_dim != 2 && !dummy) {
+                    for (int i = lane * 4; i < n_chunks * 32; i += 128) {
+                        *reinterpret_cast<float4*>(cbias + i) = *reinterpret_cast<const float4*>(bias + n_base + i);
+                        if constexpr (FP8)
+                            *reinterpret_cast<float4*>(cbias + BN + i) = *reinterpret_cast<const float4*>(p.w_scale[m.s] + n_base + i);
+                    }
+                    __syncwarp();
+                }
+            }
 
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
@@ -361,9 +367,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 for (int i = 0; i < 32; i += 4) {
                     float4 f = make_float4(accf(r[i]), accf(r[i + 1]), accf(r[i + 2]), accf(r[i + 3]));
                     if (add_bias_first) {
-                        const float4 bv = *reinterpret_cast<const float4*>(bias + n_base + c * 32 + i);
+                        const float4 bv = *reinterpret_cast<const float4*>(cbias + c * 32 + i);
                         if constexpr (FP8) {
-                            const float4 ws = *reinterpret_cast<const float4*>(p.w_scale[m.s] + n_base + c * 32 + i);
+                            const float4 ws = *reinterpret_cast<const float4*>(cbias + BN + c * 32 + i);
                             f.x *= as_row * ws.x; f.y *= as_row * ws.y; f.z *= as_row * ws.z; f.w *= as_row * ws.w;
                         }
                         f.x = (f.x + bv.x) * row_scale; f.y = (f.y + bv.y) * row_scale;
@@ -522,10 +528,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                 if (cc < 3) tmem_ld32(t_addr + (c + cc + 1) * 32, rn);
 #pragma unroll
                                 for (int i = 0; i < 32; i += 4) {
-                                    const float4 bv = *reinterpret_cast<const float4*>(bias + n_base + (c + cc) * 32 + i);
+                                    const float4 bv = *reinterpret_cast<const float4*>(cbias + (c + cc) * 32 + i);
                                     float4 ws = make_float4(1.f, 1.f, 1.f, 1.f);
                                     if constexpr (FP8) {
-                                        ws = *reinterpret_cast<const float4*>(p.w_scale[m.s] + n_base + (c + cc) * 32 + i);
+                                        ws = *reinterpret_cast<const float4*>(cbias + BN + (c + cc) * 32 + i);
                                         ws.x *= as_row; ws.y *= as_row; ws.z *= as_row; ws.w *= as_row;
                                     }
                                     const float a0 = accf(r[i]) * ws.x + bv.x;
