@@ -49,13 +49,15 @@ def option(key):
 
 # (name, setter, default, values)
 KNOBS = [
-    ("attention variant (set_option 1)", option(1), 0, [0x100, 0x30, 0x40, 0x28]),
+    ("bounded-score attention where the norm weights allow it (set_option 3)", option(3), 1, [0]),
+    ("polynomial share of the exponentials (set_option 1; the bounded form adds 0x200)", option(1), 0, [0x100, 0x20, 0x40]),
     ("programmatic dependent launch (tune 7)", tune(7), 1, [0]),
-    ("GEMM raster band, m-units (tune 5)", tune(5), 0, [4, 8, 16, 32]),
-    ("GEMM TMA L2 hints (tune 2)", tune(2), 0, [1, 2, 3]),
-    ("GEMM split-K tail (tune 4)", tune(4), 1, [0, 9]),
-    ("adaLN kernel form (tune 3)", tune(3), 1, [0]),
+    ("GEMM raster band, m-units (tune 5)", tune(5), 0, [8, 16, 32]),
+    ("GEMM TMA L2 hints (tune 2)", tune(2), 0, [1, 3]),
+    ("GEMM tail: K split / N split (tune 4; default 17)", tune(4), 17, [0, 1, 16]),
 ]
+if len(sys.argv) > 2:                     # python tools/instep_sweep.py 4 0,1 -> only these knobs
+    KNOBS = [KNOBS[int(i)] for i in sys.argv[2].split(",")]
 
 for _ in range(3):          # reach the power-capped steady state before the first number
     measure()
