@@ -129,6 +129,10 @@ int qie_set_option(qie_handle* h, int key, int value);
  * qie_attn_score_bound: the bound on |q.k| * softmax_scale * log2(e) of block `layer`, derived at qie_set_weights from the
  * four QK-RMSNorm weight vectors of the block (read back once, 2 % margin for the bf16 rounding of q and k); < 0 on error */
 float qie_attn_score_bound(const qie_handle* h, int layer);
+/* The attention variant that matches the q|k|v the QKV phase of block `layer` produces (>= 0; negative = status): callers of
+ * the phase API that run the attention themselves (qie_forward_phase QKV -> their own exchange -> qie_attn_fwd / _tiles)
+ * MUST pass this value, because q is pre-scaled in the blocks that run the bounded-score form. */
+int qie_attn_layer_variant(const qie_handle* h, int layer);
 /* measurement aids: kernels launched by the library so far; event-timed ms / algorithmic work / launches per kernel
  * class since the last read (class 0 GEMM [FLOP], 1 attention [FLOP], 2 adaLN [bytes], 3 modulation GEMV [bytes], 4 other,
  * 5 peer barrier); arrays of QIE_PROFILE_CLASSES entries.  qie_profile_timeline lists the launches recorded since the last

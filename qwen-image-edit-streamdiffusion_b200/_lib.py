@@ -98,6 +98,7 @@ SYMBOLS = {
     "qie_set_precision": (_i, [_vp, _i]),
     "qie_set_option": (_i, [_vp, _i, _i]),
     "qie_attn_score_bound": (_f, [_vp, _i]),
+    "qie_attn_layer_variant": (_i, [_vp, _i]),
     "qie_launch_count": (C.c_ulonglong, []),
     "qie_tune": (_i, [_i, _i]),
     "qie_tune_get": (_i, [_i]),

@@ -374,6 +374,16 @@ extern "C" int qie_set_weights(qie_handle* h, const qie_weights* w) {
     return QIE_OK;
 }
 
+// block `layer` runs the bounded-score attention: q leaves the fused QKV epilogue multiplied by softmax_scale * log2(e)
+static bool layer_bounded(const qie_handle* h, int l) {
+    return h->attn_bounded && h->fuse_qk && (h->attn_variant & 0x208) == 0 && h->score_bound[l] <= QIE_ATTN_SCORE_BOUND;
+}
+
+extern "C" int qie_attn_layer_variant(const qie_handle* h, int layer) {
+    QIE_REQUIRE(h && h->has_weights && layer >= 0 && layer < h->cfg.num_layers, QIE_EINVAL, "qie_attn_layer_variant: bad argument");
+    return layer_bounded(h, layer) ? (h->attn_variant | 0x200) : h->attn_variant;
+}
+
 extern "C" float qie_attn_score_bound(const qie_handle* h, int layer) {
     if (!h || !h->has_weights || layer < 0 || layer >= h->cfg.num_layers) return -1.f;
     return h->score_bound[layer];
@@ -545,9 +555,7 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
     };
     // bounded-score attention of block l: q carries softmax_scale * log2(e) out of the fused QKV epilogue and the kernel skips the
     // running max (attn.cu); only where the norm weights bound the scores, never with the unfused debug path or a forced kernel
-    auto bounded = [&](int l) -> bool {
-        return h->attn_bounded && h->fuse_qk && (h->attn_variant & 0x208) == 0 && h->score_bound[l] <= QIE_ATTN_SCORE_BOUND;
-    };
+    auto bounded = [&](int l) -> bool { return layer_bounded(h, l); };
     auto run_attn = [&](int l) -> int {
         const int variant = bounded(l) ? (h->attn_variant | 0x200) : h->attn_variant;
         if (use_peers) {

@@ -365,7 +365,10 @@ class UlyssesTransformer:
             for l in range(t.cfg.num_layers):
                 phase(2, l)                                                          # adaLN1 + QKV on local tokens
                 dist.all_to_all_single(q_recv, pack_heads(qkv_local, P, H), group=self.group)   # tokens -> heads
-                L.check(lib.qie_attn_fwd_tiles(L.ptr(q_recv), L.ptr(o_full), P * rows // 128, L.ptr(tiles), hl, 0,
+                variant = lib.qie_attn_layer_variant(t._handle, l)      # q is pre-scaled in the blocks with bounded scores
+                if variant < 0:
+                    L.check(variant, "qie_attn_layer_variant")
+                L.check(lib.qie_attn_fwd_tiles(L.ptr(q_recv), L.ptr(o_full), P * rows // 128, L.ptr(tiles), hl, variant,
                                                L.cur_stream()), "qie_attn_fwd_tiles")
                 dist.all_to_all_single(o_recv, o_full, group=self.group)             # heads -> tokens
                 attn_local.copy_(unpack_heads(o_recv, P))
