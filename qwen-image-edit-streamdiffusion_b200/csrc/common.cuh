@@ -469,10 +469,28 @@ __device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float
     const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
     return lo | (hi << 16);
 }
-__device__ __forceinline__ uint32_t pack_s8x4(float a, float b, float c, float d) {   // round-to-nearest-even, clamp +-127
-    const int ia = max(-127, min(127, __float2int_rn(a))), ib = max(-127, min(127, __float2int_rn(b)));
-    const int ic = max(-127, min(127, __float2int_rn(c))), id = max(-127, min(127, __float2int_rn(d)));
-    return (uint32_t)(ia & 0xFF) | ((uint32_t)(ib & 0xFF) << 8) | ((uint32_t)(ic & 0xFF) << 16) | ((uint32_t)(id & 0xFF) << 24);
+__device__ __forceinline__ uint32_t pack_s8x4(float a, float b, float c, float d) {   // round-to-nearest-even, saturating bytes
+    // the quantisers feed |x / s| <= 127 (s = amax / 127), so the saturation to [-128, 127] of the pack never yields -128
+    uint32_t hi, r;
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(__float2int_rn(d)), "r"(__float2int_rn(c)), "r"(0u));
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(__float2int_rn(b)), "r"(__float2int_rn(a)), "r"(hi));
+    return r;
+}
+// x / s as far as round-to-nearest-integer can tell (int8 activation quantiser; bit-equal to torch.round(x / s) of the restated
+// W8A8 reference).  An IEEE division is ~10 instructions, and the quantisers do one per element; the reciprocal product is
+// within 2 ulp of the quotient (|q| <= 127: < 2e-5), so the rounded integer can only differ when the product sits that close to
+// a tie — only then (about 1 element in 5000) is the true quotient taken.
+__device__ __forceinline__ float quot_for_rint(float x, float s, float inv_s) {
+    float q = x * inv_s;
+    if (fabsf(fabsf(q - rintf(q)) - 0.5f) < 1e-4f) q = x / s;
+    return q;
+}
+__device__ __forceinline__ uint32_t quant_s8x4(float a, float b, float c, float d, float s, float inv_s) {
+    return pack_s8x4(quot_for_rint(a, s, inv_s), quot_for_rint(b, s, inv_s), quot_for_rint(c, s, inv_s), quot_for_rint(d, s, inv_s));
+}
+// e4m3 is held to its own quantised operands (not to integers of a reference): reciprocal product
+__device__ __forceinline__ uint32_t quant_e4m3x4(float a, float b, float c, float d, float inv_s) {
+    return pack_e4m3x4(a * inv_s, b * inv_s, c * inv_s, d * inv_s);
 }
 // softmax scale of head_dim 128 in the log2 domain: 1/sqrt(128) * log2(e)
 constexpr float ATTN_SCALE_LOG2 = 0.08838834764831845f * 1.4426950408889634f;

@@ -126,14 +126,13 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ x
         amax = warp_max(amax);
         amax = __bfloat162float(__float2bfloat16(amax));
         const float qmax = qmode == 2 ? 127.f : 448.f;
-        const float scale = amax > 0.f ? amax / qmax : 1.f;
+        const float scale = amax > 0.f ? amax / qmax : 1.f, inv_scale = 1.0f / scale;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const float4 b = make_float4(__bfloat162float(__float2bfloat16(v[i].x)), __bfloat162float(__float2bfloat16(v[i].y)),
                                          __bfloat162float(__float2bfloat16(v[i].z)), __bfloat162float(__float2bfloat16(v[i].w)));
             *reinterpret_cast<uint32_t*>(out8 + row * D + (i * 32 + lane) * 4) =
-                qmode == 2 ? pack_s8x4(b.x / scale, b.y / scale, b.z / scale, b.w / scale)
-                           : pack_e4m3x4(b.x / scale, b.y / scale, b.z / scale, b.w / scale);
+                qmode == 2 ? quant_s8x4(b.x, b.y, b.z, b.w, scale, inv_scale) : quant_e4m3x4(b.x, b.y, b.z, b.w, inv_scale);
         }
         if (lane == 0) out_scale[row] = scale;
     }
@@ -241,14 +240,13 @@ __global__ void __launch_bounds__(256, 1) ln_mod_stream_kernel(const float* __re
                 amax = warp_max(amax);
                 amax = __bfloat162float(__float2bfloat16(amax));
                 const float qmax = qmode == 2 ? 127.f : 448.f;
-                const float scale = amax > 0.f ? amax / qmax : 1.f;
+                const float scale = amax > 0.f ? amax / qmax : 1.f, inv_scale = 1.0f / scale;
 #pragma unroll
                 for (int i = 0; i < NV; ++i) {
                     const float4 bq = make_float4(__bfloat162float(__float2bfloat16(v[i].x)), __bfloat162float(__float2bfloat16(v[i].y)),
                                                   __bfloat162float(__float2bfloat16(v[i].z)), __bfloat162float(__float2bfloat16(v[i].w)));
                     *reinterpret_cast<uint32_t*>(out8 + (size_t)row * D + (i * 32 + lane) * 4) =
-                        qmode == 2 ? pack_s8x4(bq.x / scale, bq.y / scale, bq.z / scale, bq.w / scale)
-                                   : pack_e4m3x4(bq.x / scale, bq.y / scale, bq.z / scale, bq.w / scale);
+                        qmode == 2 ? quant_s8x4(bq.x, bq.y, bq.z, bq.w, scale, inv_scale) : quant_e4m3x4(bq.x, bq.y, bq.z, bq.w, inv_scale);
                 }
                 if (lane == 0) out_scale[row] = scale;
             }
@@ -452,17 +450,17 @@ __global__ void __launch_bounds__(256) quant_rows_kernel(const __nv_bfloat16* __
         }
         amax = warp_max(amax);
     }
-    const float s = amax > 0.f ? amax / (qmode == 2 ? 127.f : 448.f) : 1.f;   // true divisions: bit-equal to torch.round(x / s) of the restated W8A8 reference
+    const float s = amax > 0.f ? amax / (qmode == 2 ? 127.f : 448.f) : 1.f, inv_s = 1.0f / s;   // int8: bit-equal to torch.round(x / s) (quot_for_rint)
     for (int c = lane * 8; c < K; c += 256) {
         uint4 u = *reinterpret_cast<const uint4*>(xr + c);
         float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
         uint2 o;
         if (qmode == 2) {
-            o.x = pack_s8x4(a.x / s, a.y / s, b.x / s, b.y / s);
-            o.y = pack_s8x4(cc.x / s, cc.y / s, d.x / s, d.y / s);
+            o.x = quant_s8x4(a.x, a.y, b.x, b.y, s, inv_s);
+            o.y = quant_s8x4(cc.x, cc.y, d.x, d.y, s, inv_s);
         } else {
-            o.x = pack_e4m3x4(a.x / s, a.y / s, b.x / s, b.y / s);
-            o.y = pack_e4m3x4(cc.x / s, cc.y / s, d.x / s, d.y / s);
+            o.x = quant_e4m3x4(a.x, a.y, b.x, b.y, inv_s);
+            o.y = quant_e4m3x4(cc.x, cc.y, d.x, d.y, inv_s);
         }
         *reinterpret_cast<uint2*>(q + row * K + c) = o;
     }

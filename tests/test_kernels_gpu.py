@@ -55,6 +55,34 @@ def test_ln_modulate(D):
     assert got.reshape(2, -1, D)[:, s.img_rows:s.img_pad].abs().max() == 0
 
 
+@pytest.mark.parametrize("qmode", [1, 2])
+def test_ln_modulate_fused_quantiser(qmode):
+    """The adaLN kernel's 8-bit shadow output (per-token dynamic quantisation of the bf16-rounded rows, fused into the same pass):
+    int8 = exactly torch.round(x / s) with s = amax / 127 (the restated Int8Linear activation quantiser, README.md:136-141; the kernel
+    takes the reciprocal product and falls back to the true quotient next to a tie), e4m3 within its 3 mantissa bits."""
+    D = 3072
+    s = K.seq(1, 300, 77)
+    x = randn(K.rows(s), D, seed=14) * 2 + 0.3
+    x[:, 11] *= 30                                             # an outlier channel
+    mod = randn(1, 2, 6 * D, seed=15, scale=0.5)
+    out, out8, sc = K.ln_modulate(s, x, mod, 2 * 6 * D, 6 * D, 0, D, D, fp8=True, qmode=qmode)
+    valid = torch.zeros(K.rows(s), dtype=torch.bool, device=DEV)
+    valid[:s.img_rows] = True
+    valid[s.img_pad:s.img_pad + s.txt_rows] = True
+    xf = out.float()[valid]
+    qmax = 127.0 if qmode == 2 else 448.0
+    amax = xf.abs().amax(dim=1, keepdim=True)
+    scale = amax / torch.full_like(amax, qmax)                 # tensor / tensor: a true division (tensor / python float multiplies by 1/x)
+    assert torch.equal(sc[valid], scale.squeeze(1))
+    if qmode == 2:
+        want = torch.round(xf / scale).clamp(-127, 127)
+        assert torch.equal(out8[valid].view(torch.int8).float(), want)
+    else:
+        dq = out8[valid].view(torch.float8_e4m3fn).float() * scale
+        assert ((dq - xf).abs().amax(dim=1) <= amax.squeeze(1) * 2 ** -4 + 1e-6).all()
+    assert out8[~valid].view(torch.int8).abs().max() == 0 and sc[~valid].abs().max() == 0
+
+
 @pytest.mark.parametrize("B,N,K_,act", [(1, 1000, 256, 0), (2, 6 * 3072, 3072, 1), (8, 514, 512, 1)])
 def test_gemv(B, N, K_, act):
     x = randn(B, K_, seed=6)

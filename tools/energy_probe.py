@@ -87,8 +87,10 @@ for name, N, Kd, epi in [("qkv", 3 * D, D, K.L.EPI_QKV_NORM_ROPE), ("out", D, D,
 qkv = torch.randn(M, 3 * H * 128, device=dev).bfloat16()
 S = 8192 + 256
 aflops = 4.0 * S * S * 128 * H
-for v in (0x20, 0x100, 0x30):
-    probe(f"attn_pair_kernel variant {v:#x}", lambda: K.attn(s, qkv, H, v), aflops, "flop")
+qkv_b = qkv.clone()             # the bounded-score form (0x200) takes q pre-multiplied by softmax_scale * log2(e)
+qkv_b[:, : H * 128] = (qkv_b[:, : H * 128].float() * (0.08838834764831845 * 1.4426950408889634)).bfloat16()
+for v in (0x20, 0x220, 0x230, 0x240):
+    probe(f"attn_pair_kernel variant {v:#x}", lambda: K.attn(s, qkv_b if v & 0x200 else qkv, H, v), aflops, "flop")
 x = qkv[:S].reshape(1, S, 3, H, 128)
 q, k, v_ = (x[:, :, i].transpose(1, 2).contiguous() for i in range(3))
 probe("torch SDPA (cuDNN / flash)", lambda: F.scaled_dot_product_attention(q, k, v_), aflops, "flop")
@@ -96,3 +98,6 @@ probe("torch SDPA (cuDNN / flash)", lambda: F.scaled_dot_product_attention(q, k,
 xr = torch.randn(M, D, device=dev)
 mod = torch.randn(1, 2, 6 * D, device=dev)
 probe("ln_mod_stream_kernel", lambda: K.ln_modulate(s, xr, mod, 12 * D, 6 * D, 0, D, D), (8192 + 256) * D * 6.0, "byte")
+for qm, nm in ((1, "e4m3"), (2, "int8")):
+    probe(f"ln_mod_stream_kernel + fused {nm} quantiser", lambda: K.ln_modulate(s, xr, mod, 12 * D, 6 * D, 0, D, D, fp8=True, qmode=qm),
+          (8192 + 256) * D * 7.0, "byte")
