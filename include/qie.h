@@ -116,6 +116,8 @@ int qie_device_sm_count(void);
 /* ---- model handle: replaces constructing/holding `pipeline.transformer` (server.py:66-69) ---- */
 int qie_create(const qie_model_cfg* cfg, int device, qie_handle** out);
 int qie_destroy(qie_handle* h);
+/* qie_set_weights keeps the pointers (the caller owns the memory) and reads the four QK-RMSNorm weight vectors of every block back
+ * once (synchronous 512 B copies) to bound the attention scores (qie_attn_score_bound): call it again after changing them in place */
 int qie_set_weights(qie_handle* h, const qie_weights* w);
 /* 0 = bf16 GEMMs, 1 = FP8 e4m3 W8A8, 2 = INT8 W8A8 (both need the *_w8 / *_ws pointers); replaces int8_linear.py /
  * cublaslt_int8.py / triton_int8_gemm.py named at README.md:136-141 */
