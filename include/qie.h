@@ -338,7 +338,8 @@ int qie_gemm(const qie_gemm_args* args, const qie_seq* seq, void* stream);
  * 0x200 = bounded-score form of the CTA-pair kernel: the CALLER promises that q already carries softmax_scale * log2(e)
  * (qie_gemm_args.q_scale) and that |q.k| <= QIE_ATTN_SCORE_BOUND for every (query, key) pair, so p = 2^(q.k) needs no running
  * max, no exchange between the softmax warpgroups and no rescale of O; the result is the same softmax.  After QK-RMSNorm the
- * bound follows from the norm weights: |q.k| <= 128 * max|w_q| * max|w_k| * softmax_scale * log2(e) (RoPE is a rotation). */
+ * bound follows from the norm weights: |q.k| * softmax_scale * log2(e) <= 128 * max_p(m_q,p * m_k,p) * softmax_scale * log2(e) with
+ * m_p the larger |weight| of RoPE pair p over both streams (RoPE rotates inside a pair; Cauchy-Schwarz over the pairs). */
 #define QIE_ATTN_SCORE_BOUND 80.0f
 int qie_attn_fwd(const void* qkv, void* out, const qie_seq* seq, int num_heads, int variant, void* stream);
 /* LayerNorm(no affine, eps) + x*(1+scale)+shift; x fp32 [rows, D] -> out bf16 [rows, D].

@@ -357,18 +357,24 @@ extern "C" int qie_set_weights(qie_handle* h, const qie_weights* w) {
         }
     h->w = *w;
     h->w.blocks = h->blocks.data();
-    // bound on the attention scores of every block: after RMSNorm |q|^2 = sum (q_i / rms)^2 w_i^2 <= 128 max w^2, RoPE rotates
-    // pairs, so |q.k| <= 128 max|w_q| max|w_k| (over both streams: image queries meet text keys); 2 % for the bf16 rounding
+    // bound on the attention scores of every block.  After RMSNorm the unit row q^ has |q^|^2 = 128 and q = q^ * w; RoPE rotates the
+    // channel pairs (2i, 2i+1), so with m_p = max(|w_2i|, |w_2i+1|):  q.k = sum_p rot(q_p).rot(k_p) <= sum_p |q_p| |k_p|
+    // <= sum_p m_q,p m_k,p |q^_p| |k^_p| <= max_p(m_q,p m_k,p) * |q^| |k^| = 128 max_p(m_q,p m_k,p)   (Cauchy-Schwarz); image queries
+    // meet text keys, so the maximum runs over both streams on either side.  2 % for the bf16 rounding of q and k.
     h->score_bound.assign(h->cfg.num_layers, INFINITY);
     for (int l = 0; l < h->cfg.num_layers; ++l) {
-        float mx[2] = {0.f, 0.f};
+        float m[2][64];                  // [q / k][pair]: larger |weight| of the pair over both streams
+        for (int k = 0; k < 2; ++k)
+            for (int pr = 0; pr < 64; ++pr) m[k][pr] = 0.f;
         for (int s = 0; s < 2; ++s)
             for (int k = 0; k < 2; ++k) {
                 float wv[128];
                 QIE_CUDA_OK(cudaMemcpy(wv, k ? h->blocks[l].k_norm_w[s] : h->blocks[l].q_norm_w[s], sizeof(wv), cudaMemcpyDeviceToHost));
-                for (float v : wv) mx[k] = fmaxf(mx[k], isfinite(v) ? fabsf(v) : INFINITY);
+                for (int i = 0; i < 128; ++i) m[k][i >> 1] = fmaxf(m[k][i >> 1], isfinite(wv[i]) ? fabsf(wv[i]) : INFINITY);
             }
-        h->score_bound[l] = 128.f * mx[0] * mx[1] * ATTN_SCALE_LOG2 * 1.02f;
+        float mx = 0.f;
+        for (int pr = 0; pr < 64; ++pr) mx = fmaxf(mx, m[0][pr] * m[1][pr]);
+        h->score_bound[l] = 128.f * mx * ATTN_SCALE_LOG2 * 1.02f;
     }
     h->has_weights = true;
     return QIE_OK;

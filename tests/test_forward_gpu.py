@@ -109,9 +109,9 @@ def test_bounded_score_attention_follows_the_norm_weights(factor, expect_bounded
     for l in range(ref_cfg.num_layers):
         names = [k for k in sd if k.startswith(f"transformer_blocks.{l}.") and k.endswith("weight") and
                  any(t in k for t in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"))]
-        qmax = max(sd[k].abs().max().item() for k in names if "_q" in k)
-        kmax = max(sd[k].abs().max().item() for k in names if "_k" in k)
-        want = 128 * qmax * kmax * 0.08838834764831845 * 1.4426950408889634 * 1.02
+        pair_max = lambda ks: torch.stack([sd[k].abs().view(64, 2).amax(dim=1) for k in ks]).amax(dim=0)      # per RoPE pair, both streams
+        mq, mk = pair_max([k for k in names if "_q" in k]), pair_max([k for k in names if "_k" in k])
+        want = 128 * (mq * mk).max().item() * 0.08838834764831845 * 1.4426950408889634 * 1.02
         got_b = lib.qie_attn_score_bound(ours._handle, l)
         assert abs(got_b - want) <= 1e-3 * want, (l, got_b, want)
         assert (got_b <= 80.0) == expect_bounded
@@ -132,6 +132,38 @@ def test_bounded_score_attention_follows_the_norm_weights(factor, expect_bounded
     assert K.rel_err(got, off.float()) <= VEL_TOL
     if not expect_bounded:
         assert torch.equal(got, off)          # the same kernels ran both times
+
+
+def test_score_bound_is_taken_per_rope_pair():
+    """An outlier norm weight on one channel of q and on ANOTHER channel of k: the product of the maxima (16) would rule the bounded
+    form out, the per-pair bound (RoPE only rotates inside a pair) keeps it — and the velocity still equals the oracle's."""
+    ref_cfg, our_cfg = small_cfg()
+    oracle = R.init_weights_(R.QwenImageTransformer2DModelRef(ref_cfg), seed=0)
+    with torch.no_grad():
+        for p in oracle.parameters():
+            p.copy_(p.to(torch.bfloat16).float())
+        for blk in oracle.transformer_blocks:
+            blk.attn.norm_q.weight[10] = 4.0
+            blk.attn.norm_added_q.weight[11] = 4.0          # same RoPE pair as channel 10
+            blk.attn.norm_k.weight[77] = 4.0
+            blk.attn.norm_added_k.weight[100] = 4.0
+    oracle.eval()
+    ours = qie_b200.B200QwenImageTransformer2DModel.from_state_dict(oracle.state_dict(), our_cfg, DEV)
+    lib = qie_b200.lib()
+    for l in range(ref_cfg.num_layers):
+        b = lib.qie_attn_score_bound(ours._handle, l)
+        assert 60.0 < b <= 80.0, b                          # 4 x ~1.06 x 16.32 x 1.02; the product of the maxima would give ~270
+        assert lib.qie_attn_layer_variant(ours._handle, l) & 0x200
+    shapes = [[(1, 16, 16), (1, 16, 16)]]
+    T = 40
+    hidden, enc = R.make_inputs(ref_cfg, shapes, T, seed=6)
+    hidden, enc = bf16_round(hidden), bf16_round(enc)
+    ts = torch.tensor([0.375])
+    with torch.no_grad():
+        ref = oracle(hidden, enc, None, ts, shapes, [T])[0]
+    got = ours(hidden_states=hidden.to(DEV), encoder_hidden_states=enc.to(DEV), timestep=ts.to(DEV), img_shapes=shapes,
+               txt_seq_lens=[T], return_dict=False)[0].cpu()
+    assert K.rel_err(got, ref) <= VEL_TOL, K.rel_err(got, ref)
 
 
 def test_batch_above_eight_and_bad_text_lengths_are_refused():
