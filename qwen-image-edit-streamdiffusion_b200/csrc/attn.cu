@@ -453,6 +453,9 @@ static int launch_attn(const CUtensorMap& tm, const AttnDev& p, dim3 grid, cudaS
 // both halves of P use one reference) and keep separate partial row sums.  S is pulled into registers at once and handed
 // back (s_free), so S(j+1) runs under the exponentials of tile j; PV(j) runs under the softmax of tile j+1.
 // Issue order of the leader: S(0) | S(1) PV(0) | S(2) PV(1) | ...
+// FIXED = bounded-score form (variant 0x200; the default wherever the QK-RMSNorm weights of the block bound the scores, see
+// qie_attn_score_bound): q arrives multiplied by softmax_scale * log2(e) and p = 2^s is taken without any reference — no row
+// max, no exchange between the warpgroups, no O rescale.  FIXED = false is the online softmax with lazy rescaling.
 // =====================================================================================================================
 constexpr int AT5_KSTAGES = 3, AT5_VSTAGES = 2;
 constexpr int AT5_THREADS = 384;              // warps 0-7 softmax (two warpgroups), warp 8 TMA, warp 9 S issuer, warp 10 PV issuer, 11 idle

@@ -10,10 +10,12 @@
 //
 // Structure (192 threads, 1 CTA / SM, persistent, static round-robin tile schedule):
 //   warps 0..3      : epilogue      — tcgen05.ld 32x32b -> registers -> per-warp smem transpose -> coalesced global
-//   warp 4 / lane 0 : TMA producer  — A tile [128 x 128 B] and W tile (128B-swizzled rows) per stage
-//   warp 5 / lane 0 : MMA issuer    — tcgen05.mma kind::f16 / kind::f8f6f4, fp32 accumulators in TMEM.  Highest warp id of
+//   warp 4          : TMA producer  — A tile [128 x 128 B] and W tile (128B-swizzled rows) per stage
+//   warp 5          : MMA issuer    — tcgen05.mma kind::f16 / kind::f8f6f4 / kind::i8, accumulators in TMEM.  Highest warp id of
 //                                     its scheduler on purpose: the arbiter serves the highest id first, so the issuer is
 //                                     never queued behind the epilogue warp it shares the scheduler with.
+//                     Both walk the schedule and wait on the barriers as whole warps; ONE lane (elect.sync) issues, so that the
+//                     operands stay provably warp-uniform (no R2UR waterfall around UTCHMMA / UTMALDG, see the issuer loop).
 // Three pipelines: smem full/empty ring (TMA <-> MMA), 2 TMEM accumulator stages (MMA <-> epilogue, so the
 // epilogue of tile i overlaps the main loop of tile i+1), and the tile loop.
 //
