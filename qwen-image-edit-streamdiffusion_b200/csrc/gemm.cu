@@ -8,10 +8,11 @@
 // to 3D), to_out.0/to_add_out (+ gate*y + residual epilogue), img_mlp/txt_mlp net.0.proj (+GELU-tanh)
 // and net.2 (+ gate*y + residual), plus img_in/txt_in/proj_out.
 //
-// Structure (192 threads, 1 CTA / SM, persistent, static round-robin tile schedule):
-//   warps 0..3      : epilogue      — tcgen05.ld 32x32b -> registers -> per-warp smem transpose -> coalesced global
-//   warp 4          : TMA producer  — A tile [128 x 128 B] and W tile (128B-swizzled rows) per stage
-//   warp 5          : MMA issuer    — tcgen05.mma kind::f16 / kind::f8f6f4 / kind::i8, accumulators in TMEM.  Highest warp id of
+// Structure (192 threads, 1 CTA / SM, persistent, static round-robin tile schedule; 320 threads = eight epilogue warps for the
+// short-K 8-bit shapes, see gemm_threads):
+//   warps 0..EW-1   : epilogue      — tcgen05.ld 32x32b -> registers -> per-warp smem transpose -> coalesced global
+//   warp EW         : TMA producer  — A tile [128 x 128 B] and W tile (128B-swizzled rows) per stage
+//   warp EW+1       : MMA issuer    — tcgen05.mma kind::f16 / kind::f8f6f4 / kind::i8, accumulators in TMEM.  Highest warp id of
 //                                     its scheduler on purpose: the arbiter serves the highest id first, so the issuer is
 //                                     never queued behind the epilogue warp it shares the scheduler with.
 //                     Both walk the schedule and wait on the barriers as whole warps; ONE lane (elect.sync) issues, so that the
@@ -31,7 +32,12 @@ namespace qie {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK_BYTES = 128;   // one 128B swizzle row: 64 bf16 or 128 e4m3
-constexpr int GEMM_THREADS = 192;
+// Epilogue warps (template parameter EW): four (one per TMEM lane quadrant) for bf16 operands, where a 256-wide tile's main loop
+// (~24.6 k cycles at K = 3072) covers the epilogue; EIGHT for the 8-bit operand types at BN = 256 and K < 8192, whose main loop is
+// half as long and was waiting for the latency-bound epilogue warps (QKV + RMSNorm + RoPE at 0.54 of cuBLASLt e4m3, out-proj at 0.69:
+// tools/q8_gemm_bench.py).  Two warps then share a lane quadrant and split the tile's columns (one 128-column head each in the
+// QKV epilogue).  The long-K shape (FF-down) keeps four: its main loop covers the epilogue and it prefers the sixth ring stage.
+__host__ __device__ constexpr int gemm_threads(int EW) { return (EW + 2) * 32; }
 
 struct GemmDev {
     qie_seq seq;
@@ -65,17 +71,19 @@ struct GemmDev {
     float* q8_amax;                // optional: per-row max|out| folded in by the bf16 epilogues (feeds the 8-bit quantiser)
 };
 
-template <int BN, int CG>
+template <int BN, int CG, int EW = 4>
 struct GemmSmem {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK_BYTES;
     static constexpr int B_BYTES = (BN / CG) * GEMM_BK_BYTES;               // each CTA of a pair holds half of the W tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (196 * 1024) / STAGE_BYTES > 8 ? 8 : (196 * 1024) / STAGE_BYTES;
-    static constexpr int BAR_BYTES = 512;                                   // ring + TMEM barriers, tmem slot, 16 LN landing barriers
     static constexpr int EPI_ROW_BYTES = 144;                               // 32 fp32 + 16 B pad: conflict-free both ways
     static constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_BYTES;               // per-warp transpose staging
     static constexpr int COLV_BYTES = 2 * BN * 4;                           // per-warp copy of the tile's bias | weight scales (QKV epilogue)
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 4 * EPI_WARP_BYTES + 4 * COLV_BYTES + 1024;   // +1024: manual alignment
+    // four epilogue warps: 196 KB of operand ring; eight: what 227 KB leave beside the doubled staging (5 stages at BN = 256, pairs)
+    static constexpr int RING_BYTES = EW == 4 ? 196 * 1024 : 227 * 1024 - 1536 - EW * (EPI_WARP_BYTES + COLV_BYTES);
+    static constexpr int STAGES = RING_BYTES / STAGE_BYTES > 8 ? 8 : RING_BYTES / STAGE_BYTES;
+    static constexpr int BAR_BYTES = 512;                                   // ring + TMEM barriers, tmem slot, 16 LN landing barriers
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + EW * EPI_WARP_BYTES + EW * COLV_BYTES + 1024;   // +1024: manual alignment
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;             // two accumulator stages
 };
 
@@ -142,11 +150,12 @@ __device__ __forceinline__ WorkItem decode_item(int item, int num_tiles, int tai
     return w;
 }
 
-template <int BN, int EPI, int QT, int CG>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int EPI, int QT, int CG, int EW = 4>
+__global__ void __launch_bounds__(gemm_threads(EW), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
             const __grid_constant__ CUtensorMap tmB1, const GemmDev p) {
-    using S = GemmSmem<BN, CG>;
+    // epilogue warps 0 .. EW-1, TMA producer = warp EW, MMA issuer = warp EW + 1
+    using S = GemmSmem<BN, CG, EW>;
     constexpr int STAGES = S::STAGES;
     constexpr bool FP8 = QT != 0;                // 8-bit operands (e4m3 or int8): 128-element k-blocks, dequant epilogue
     constexpr int BK = FP8 ? 128 : 64;           // elements per k-block
@@ -188,11 +197,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4 * CG);
+            mbar_init(&tempty_bar[i], EW * CG);
         }
         fence_barrier_init();
     }
-    if (warp == 5) {
+    if (warp == EW + 1) {
         if constexpr (CG == 2) tmem_alloc_cg2<S::TMEM_COLS>(tmem_slot);
         else tmem_alloc<S::TMEM_COLS>(tmem_slot);
     }
@@ -203,7 +212,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t tmem_base = *tmem_slot;
     griddep_wait();      // everything above overlapped the previous kernel's tail; its output is visible from here on
 
-    if (warp == 4) {
+    if (warp == EW) {
         {
             // ================= TMA producer (every CTA loads its own A rows and its share of W) =================
             // whole warp in the loop, one elected lane issues (uniform operands: no R2UR waterfall around UTMALDG, see the MMA issuer)
@@ -255,7 +264,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == EW + 1) {
         if (cta_rank == 0) {
             // ================= MMA issuer (leader CTA only) =================
             // The whole warp walks the schedule and waits on the barriers; one elected lane issues.  Loop state and operands are
@@ -308,12 +317,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         }
     } else {
-        // ================= epilogue (warps 0..3) =================
+        // ================= epilogue (warps 0 .. EW-1) =================
         // Each warp owns the 32 accumulator rows of its TMEM lane quadrant.  Per 32-column chunk:
         //   phase 1 (lane == row)   : tcgen05.ld -> registers -> padded per-warp smem tile
         //   phase 2 (lanes == cols) : 8 lanes x float4 cover one 128 B row segment, 4 rows per instruction, so every
         //                             global load/store of bias, gate, residual, rope and output is a coalesced line.
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
+        [[maybe_unused]] const int half = warp >> 2;  // EW = 8: which half of the tile's columns this warp takes
         uint8_t* stg = smem + STAGES * S::STAGE_BYTES + S::BAR_BYTES + warp * S::EPI_WARP_BYTES;
         const int sub = lane >> 3, c4 = (lane & 7) * 4;
         int acc = 0;
@@ -335,12 +345,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const float* bias = p.bias[m.s];
             const int n_base = nb * BN + (wi.nhalf ? wi.part * BNH : 0);      // first output column of this item
             const int n_chunks = wi.nhalf ? BNH / 32 : BN / 32;               // 32-column chunks of this item
+            // my chunks of the item.  EW = 8: the two warps of a lane quadrant split them — one 128-column head each in the QKV
+            // epilogue (row statistics run over a whole head; the single head of a column-half tail item goes to the first warp)
+            int c_begin = 0, c_end = n_chunks;
+            if constexpr (EW == 8) {
+                const int per = (EPI == QIE_EPI_QKV_NORM_ROPE && n_chunks == 4) ? 4 : n_chunks / 2;
+                c_begin = half * per < n_chunks ? half * per : n_chunks;
+                c_end = c_begin + per < n_chunks ? c_begin + per : n_chunks;
+            }
 
             // QKV epilogue, q / k tiles: every thread of the row layout needs the bias (and weight scale) of every column of the
             // tile, twice (RMS pre-pass, staging).  As global loads their L2 latency was exposed once per 32-column chunk and pass
             // (the top stall sites of the ncu source view); a per-warp copy in shared memory is fetched before the accumulator is
             // waited for, so its latency hides behind the main loop.
-            [[maybe_unused]] float* cbias = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + S::BAR_BYTES + 4 * S::EPI_WARP_BYTES +
+            [[maybe_unused]] float* cbias = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + S::BAR_BYTES + EW * S::EPI_WARP_BYTES +
                                                                       warp * S::COLV_BYTES);
             if constexpr (EPI == QIE_EPI_QKV_NORM_ROPE) {
                 if (n_base / p.model_dim != 2 && !dummy) {
@@ -394,7 +412,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                   (size_t)(cta_rank * GEMM_BM + quad * 32) * BN;
                     if (!dummy && !(p.tail_dbg & 1)) {
 #pragma unroll 1
-                        for (int c = 0; c < BN / 32; ++c) {
+                        for (int c = c_begin; c < c_end; ++c) {       // K ranges are whole BN-wide tiles: n_chunks == BN / 32
                             stage_chunk(c, 1.f, false);
 #pragma unroll
                             for (int it = 0; it < 8; ++it) {
@@ -421,8 +439,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         int* ticket = p.tickets + tail_idx * 8 + cta_rank * 4 + quad;
                         if (lane == 0) t = atomicAdd(ticket, 1);
                         t = __shfl_sync(0xffffffffu, t, 0);
-                        last = t == p.tail_split - 1;
+                        last = t == p.tail_split * (EW / 4) - 1;    // every warp of this lane quadrant, of every K range, has parked
                         if (last) {
+                            c_begin = 0;                            // the last one sums and finishes ALL columns of the quadrant's rows
+                            c_end = n_chunks;
                             if (lane == 0) *ticket = 0;          // re-armed for the next launch
                             __threadfence();
                             from_scratch = true;
@@ -511,23 +531,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                     for (int it = 0; it < 8; ++it) asc[it] = normed ? 1.f : p.a_scale[arow0 + it * 4 + sub];
                 }
+                // EW = 8: two epilogue warps per scheduler cover each other's load latency, and the register file is split ten
+                // ways (168 registers per thread: the second operand set spilled, and spill reloads miss the few KB of L1 that the
+                // operand ring leaves): the operands of chunk c are fetched at the top of chunk c, under its TMEM load and staging
                 ChunkOps nxt;
-                fetch_ops(0, nxt);
+                if constexpr (EW == 4)
+                    if (c_begin < c_end) fetch_ops(c_begin, nxt);
 #pragma unroll 1
-                for (int c = 0; c < n_chunks; ++c) {
+                for (int c = c_begin; c < c_end; ++c) {
                     const int n0 = n_base + c * 32;
                     if constexpr (EPI == QIE_EPI_QKV_NORM_ROPE) {
                         if (which != 2 && (c & 3) == 0) {                     // first chunk of a head: row RMS over 128 cols
                             // the four TMEM loads of the head are pipelined two deep (chunk cc + 1 in flight while cc is squared)
+                            // (EW = 8: one buffer — the other warp of the scheduler covers the load, 32 registers fewer)
                             float ss = 0.f;
-                            uint32_t ra[32], rb[32];
+                            uint32_t ra[32], rb[EW == 8 ? 1 : 32];
                             tmem_ld32(t_addr + c * 32, ra);
 #pragma unroll
                             for (int cc = 0; cc < 4; ++cc) {
-                                uint32_t(&r)[32] = (cc & 1) ? rb : ra;
-                                uint32_t(&rn)[32] = (cc & 1) ? ra : rb;
+                                uint32_t(&r)[32] = (EW == 4 && (cc & 1)) ? reinterpret_cast<uint32_t(&)[32]>(rb) : ra;
+                                if constexpr (EW == 8) {
+                                    if (cc > 0) tmem_ld32(t_addr + (c + cc) * 32, ra);
+                                }
                                 tmem_ld_wait();
-                                if (cc < 3) tmem_ld32(t_addr + (c + cc + 1) * 32, rn);
+                                if constexpr (EW == 4) {
+                                    uint32_t(&rn)[32] = (cc & 1) ? ra : reinterpret_cast<uint32_t(&)[32]>(rb);
+                                    if (cc < 3) tmem_ld32(t_addr + (c + cc + 1) * 32, rn);
+                                }
 #pragma unroll
                                 for (int i = 0; i < 32; i += 4) {
                                     const float4 bv = *reinterpret_cast<const float4*>(cbias + (c + cc) * 32 + i);
@@ -546,8 +576,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             rinv_head = rsqrtf(ss * (1.0f / 128.0f) + 1e-6f);
                             if (which == 0) rinv_head *= p.q_scale;   // RMSNorm, RoPE and this factor are all linear in the row
                         }
+                        if constexpr (EW == 8) fetch_ops(c, nxt);
                         stage_chunk(c, which != 2 ? rinv_head : 1.f, which != 2);
                     } else {
+                        if constexpr (EW == 8) fetch_ops(c, nxt);
                         if (from_scratch) stage_from_scratch(c);
                         else stage_chunk(c, 1.f, false);
                     }
@@ -568,7 +600,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
                     // phase 2: this chunk's operands were fetched one chunk ago; issue the next chunk's loads, then math and stores
                     const ChunkOps cur = nxt;
-                    if (c + 1 < n_chunks) fetch_ops(c + 1, nxt);
+                    if constexpr (EW == 4)
+                        if (c + 1 < c_end) fetch_ops(c + 1, nxt);
                     const float4 bv = cur.bv, g4 = cur.g4, nw4 = cur.nw4;
                     [[maybe_unused]] const float4 wsc = cur.wsc;
 #pragma unroll
@@ -649,30 +682,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tc_fence_before();
     if constexpr (CG == 2) cluster_sync_all();   // the peer's barriers / smem must outlive the leader's last commit
     else __syncthreads();
-    if (warp == 5) {
+    if (warp == EW + 1) {
         tc_fence_after();
         if constexpr (CG == 2) tmem_dealloc_cg2<S::TMEM_COLS>(tmem_base);
         else tmem_dealloc<S::TMEM_COLS>(tmem_base);
     }
 }
 
-template <int BN, int EPI, int QT, int CG>
+template <int BN, int EPI, int QT, int CG, int EW>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB0, const CUtensorMap& tmB1, const GemmDev& p,
                        int num_tiles, cudaStream_t st) {
-    using S = GemmSmem<BN, CG>;
-    QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(gemm_kernel<BN, EPI, QT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    using S = GemmSmem<BN, CG, EW>;
+    QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(gemm_kernel<BN, EPI, QT, CG, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          S::TOTAL));
     int units = sm_count() / CG;                 // CTAs (CG=1) or CTA pairs (CG=2) resident at once
     if (units > num_tiles) units = num_tiles;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(units * CG);
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(gemm_threads(EW));
     cfg.dynamicSmemBytes = S::TOTAL;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     cfg.attrs = attr;
     cfg.numAttrs = launch_attrs(attr, CG);
-    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, QT, CG>, tmA, tmB0, tmB1, p));
+    QIE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, QT, CG, EW>, tmA, tmB0, tmB1, p));
     QIE_LAUNCH_OK("gemm_kernel");
     return QIE_OK;
 }
@@ -680,13 +713,24 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB0, const CU
 template <int BN, int QT, int CG>
 static int dispatch_epi(int epi, const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap& b1, const GemmDev& p,
                         int tiles, cudaStream_t st) {
+    if constexpr (QT != 0 && BN == 256) {        // eight epilogue warps (see gemm_threads) for the short-K 8-bit shapes
+        if (p.K < 8192) {
+            switch (epi) {
+                case QIE_EPI_BF16: return launch_gemm<BN, QIE_EPI_BF16, QT, CG, 8>(a, b0, b1, p, tiles, st);
+                case QIE_EPI_GELU_BF16: return launch_gemm<BN, QIE_EPI_GELU_BF16, QT, CG, 8>(a, b0, b1, p, tiles, st);
+                case QIE_EPI_F32: return launch_gemm<BN, QIE_EPI_F32, QT, CG, 8>(a, b0, b1, p, tiles, st);
+                case QIE_EPI_GATE_RESID_F32: return launch_gemm<BN, QIE_EPI_GATE_RESID_F32, QT, CG, 8>(a, b0, b1, p, tiles, st);
+                case QIE_EPI_QKV_NORM_ROPE: return launch_gemm<BN, QIE_EPI_QKV_NORM_ROPE, QT, CG, 8>(a, b0, b1, p, tiles, st);
+            }
+        }
+    }
     switch (epi) {
-        case QIE_EPI_BF16: return launch_gemm<BN, QIE_EPI_BF16, QT, CG>(a, b0, b1, p, tiles, st);
-        case QIE_EPI_GELU_BF16: return launch_gemm<BN, QIE_EPI_GELU_BF16, QT, CG>(a, b0, b1, p, tiles, st);
-        case QIE_EPI_F32: return launch_gemm<BN, QIE_EPI_F32, QT, CG>(a, b0, b1, p, tiles, st);
-        case QIE_EPI_GATE_RESID_F32: return launch_gemm<BN, QIE_EPI_GATE_RESID_F32, QT, CG>(a, b0, b1, p, tiles, st);
+        case QIE_EPI_BF16: return launch_gemm<BN, QIE_EPI_BF16, QT, CG, 4>(a, b0, b1, p, tiles, st);
+        case QIE_EPI_GELU_BF16: return launch_gemm<BN, QIE_EPI_GELU_BF16, QT, CG, 4>(a, b0, b1, p, tiles, st);
+        case QIE_EPI_F32: return launch_gemm<BN, QIE_EPI_F32, QT, CG, 4>(a, b0, b1, p, tiles, st);
+        case QIE_EPI_GATE_RESID_F32: return launch_gemm<BN, QIE_EPI_GATE_RESID_F32, QT, CG, 4>(a, b0, b1, p, tiles, st);
         case QIE_EPI_QKV_NORM_ROPE:
-            if constexpr (BN >= 128) return launch_gemm<BN, QIE_EPI_QKV_NORM_ROPE, QT, CG>(a, b0, b1, p, tiles, st);
+            if constexpr (BN >= 128) return launch_gemm<BN, QIE_EPI_QKV_NORM_ROPE, QT, CG, 4>(a, b0, b1, p, tiles, st);
     }
     set_error("qie_gemm: unsupported epilogue %d for block_n %d", epi, BN);
     return QIE_EINVAL;

@@ -268,6 +268,230 @@ __global__ void __launch_bounds__(256, 1) ln_mod_stream_kernel(const float* __re
     }
 }
 
+// K-lnmod, CTA-row form (default where D is a multiple of 1024; qie_tune(3, 2)): persistent, OCC = 2 CTAs per SM, the 8 warps of
+// a CTA SHARE every row — warp w owns the columns [w*D/8, (w+1)*D/8) of all rows the CTA handles, so its slice of the shift | scale vectors
+// lives in 2*D/256 registers per lane for the whole launch.  (In the warp-per-row forms every row re-reads both vectors: 24 KB
+// from L2 per 12 KB row, because the landing rings leave no L1 — two thirds of the L2->SM traffic of the kernel.)
+// Rows arrive R at a time: one thread keeps a ring of STAGES groups of R rows in flight with 1-D bulk copies (cp.async.bulk ->
+// UBLKCP) on one mbarrier per stage; groups are handed out statically for the first ring fill, then by an atomic counter.
+// Row statistics: every warp reduces (mean_w, M2_w = sum (x - mean_w)^2) over its slice, the eight pairs meet in shared memory
+// behind ONE block barrier per group and are merged with the pairwise formula of Chan et al. (exactly the two-pass variance
+// up to fp32 rounding); the same barrier releases the landing stage for the refill.  The 8-bit shadow output needs the row
+// maximum of the modulated values: a second exchange + barrier, only in the W8A8 modes.
+// The 8 warps of a CTA move in lock-step (one barrier per group), so the second CTA of the SM is what overlaps one group's
+// shuffle / rsqrt chains with the other's loads and stores.  Measured (profiles/r02_adaln_cta_rows.md): 30.1 us = 5.2 TB/s on the
+// 8448 rows of config 2 (warp-per-row ring: 34.4 us; 4 rows x 1 CTA per SM: 38.0; 2 rows x 2 CTAs: 34.7), 6.5 TB/s = 0.99 of the
+// measured copy peak at 4 x the rows; with the e4m3 / int8 shadow output 42.4 / 59.1 us (ring: 52.3 / 74.0).
+template <int NV, int R, int OCC>     // OCC = CTAs per SM that share the shared memory
+struct LnCtaSmem {
+    static constexpr int D = NV * 128, ROW_BYTES = D * 4, STAGE_BYTES = R * ROW_BYTES;
+    static constexpr int STAGES = (200 * 1024 / OCC) / STAGE_BYTES > 4 ? 4 : (200 * 1024 / OCC) / STAGE_BYTES;
+    static constexpr int TAIL_BYTES = 64 /* full barriers */ + 64 /* group ids */ + 2 * R * 8 * 8 /* stats */ + 2 * R * 8 * 4 /* amax */;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + TAIL_BYTES + 128;
+};
+template <int NV, int R, int OCC>
+__global__ void __launch_bounds__(256, OCC) ln_mod_cta_kernel(const float* __restrict__ x, const float* __restrict__ mod,
+                                                            long long mod_bstride, long long mod_sstride, int shift_off,
+                                                            int scale_off, __nv_bfloat16* __restrict__ out,
+                                                            uint8_t* __restrict__ out8, float* __restrict__ out_scale,
+                                                            int qmode, float eps, qie_seq seq, int* __restrict__ counters) {
+    using S = LnCtaSmem<NV, R, OCC>;
+    constexpr int D = S::D, ROW_BYTES = S::ROW_BYTES, STAGES = S::STAGES;
+    constexpr int NW = NV / 8;              // float4 per lane and row
+    constexpr int WCOLS = D / 8;            // columns per warp
+    static_assert(NV % 8 == 0 && STAGES >= 2, "CTA-row adaLN: D must be a multiple of 1024 and two stages must fit");
+    extern __shared__ uint8_t ln_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ln_smem_raw) + 127) & ~uintptr_t(127));
+    uint8_t* tail = smem + (size_t)STAGES * S::STAGE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(tail);                     // [STAGES]
+    volatile int* gid = reinterpret_cast<volatile int*>(tail + 64);         // [STAGES] group in the stage, -1 = no more work
+    float2* red = reinterpret_cast<float2*>(tail + 128);                    // [2][R][8] (mean_w, M2_w)
+    float* red8 = reinterpret_cast<float*>(tail + 128 + 2 * R * 8 * 8);     // [2][R][8] max |y| of the slice
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int rpb = seq.img_pad + seq.txt_pad;
+    const int num_groups = seq.batch * rpb / R;                             // img_pad, txt_pad are multiples of 128
+    griddep_launch_dependents();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) mbar_init(&full[i], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    griddep_wait();      // the residual stream written by the previous GEMM is visible from here on
+
+    struct Group { int row0, b, stream, nvalid; };
+    auto decode = [&](int g) -> Group {
+        Group r;
+        r.row0 = g * R;
+        r.b = r.row0 / rpb;
+        const int in_b = r.row0 - r.b * rpb;
+        r.stream = in_b >= seq.img_pad ? 1 : 0;
+        const int local = r.stream ? in_b - seq.img_pad : in_b;
+        const int left = (r.stream ? seq.txt_rows_b[r.b] : seq.img_rows) - local;   // valid rows are a prefix of the stream
+        r.nvalid = left < 0 ? 0 : (left > R ? R : left);
+        return r;
+    };
+    auto produce = [&](int st, int g) {      // thread 0: fill landing stage `st` with group g (or tell the CTA there is none)
+        if (g >= num_groups) {
+            gid[st] = -1;
+            mbar_arrive(&full[st]);
+            return;
+        }
+        gid[st] = g;
+        const Group gr = decode(g);
+        if (gr.nvalid == 0) {
+            mbar_arrive(&full[st]);
+            return;
+        }
+        mbar_expect_tx(&full[st], gr.nvalid * ROW_BYTES);
+        for (int r = 0; r < gr.nvalid; ++r)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(smem + (size_t)st * S::STAGE_BYTES + (size_t)r * ROW_BYTES)),
+                         "l"(x + (size_t)(gr.row0 + r) * D), "r"(ROW_BYTES), "r"(smem_u32(&full[st]))
+                         : "memory");
+    };
+    if (threadIdx.x == 0)
+        for (int k = 0; k < STAGES; ++k) produce(k, blockIdx.x + k * gridDim.x);     // no atomics in the start-up phase
+
+    float4 sh[NW], sc[NW];
+    int mod_key = -1;
+    int st = 0, it = 0;
+    uint32_t phase = 0;
+    while (true) {
+        int next_g = 0;
+        if (threadIdx.x == 0) next_g = STAGES * gridDim.x + atomicAdd(&counters[0], 1);   // latency hides under the group below
+        mbar_wait(&full[st], phase);
+        const int g = gid[st];
+        if (g < 0) break;
+        const Group gr = decode(g);
+        const int key = gr.b * 2 + gr.stream;
+        if (key != mod_key) {                // CTA-uniform; changes at most a few times per launch
+            const float* mrow = mod + gr.b * mod_bstride + gr.stream * mod_sstride + warp * WCOLS;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                sh[i] = __ldg(reinterpret_cast<const float4*>(mrow + shift_off) + i * 32 + lane);
+                sc[i] = __ldg(reinterpret_cast<const float4*>(mrow + scale_off) + i * 32 + lane);
+            }
+            mod_key = key;
+        }
+        const float* stage = reinterpret_cast<const float*>(smem + (size_t)st * S::STAGE_BYTES) + warp * WCOLS;
+        float2* my_red = red + (it & 1) * R * 8;
+        // Branch-free over the R rows of the group, so that their load / shuffle / rsqrt chains interleave: rows behind the valid
+        // prefix are computed on whatever the landing stage holds and replaced by zeros at the stores.
+        float4 v[R][NW];
+        float mean_w[R], q[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                v[r][i] = reinterpret_cast<const float4*>(stage + (size_t)r * D)[i * 32 + lane];
+                s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+            }
+            mean_w[r] = s;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int r = 0; r < R; ++r) mean_w[r] += __shfl_xor_sync(0xffffffffu, mean_w[r], o);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            mean_w[r] *= (1.0f / WCOLS);
+            q[r] = 0.f;
+#pragma unroll
+            for (int i = 0; i < NW; ++i)
+                q[r] += ln_sq4(v[r][i].x - mean_w[r], v[r][i].y - mean_w[r], v[r][i].z - mean_w[r], v[r][i].w - mean_w[r]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int r = 0; r < R; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
+        if (lane < R) {
+            float2 mine = make_float2(mean_w[0], q[0]);
+#pragma unroll
+            for (int r = 1; r < R; ++r)
+                if (lane == r) mine = make_float2(mean_w[r], q[r]);
+            my_red[lane * 8 + warp] = mine;
+        }
+        fence_proxy_async_smem();   // my reads of this landing stage are ordered before the bulk copies that refill it
+        __syncthreads();            // statistics of all eight slices are in shared memory; the stage is free
+        if (threadIdx.x == 0) produce(st, next_g);
+        float amax[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            __nv_bfloat16* orow = out + (size_t)(gr.row0 + r) * D + warp * WCOLS;
+            const bool valid = r < gr.nvalid;
+            const float4* pr = reinterpret_cast<const float4*>(my_red + r * 8);      // 8 x (mean_w, M2_w), broadcast reads
+            const float4 p0 = pr[0], p1 = pr[1], p2 = pr[2], p3 = pr[3];
+            const float mean = (((p0.x + p0.z) + (p1.x + p1.z)) + ((p2.x + p2.z) + (p3.x + p3.z))) * 0.125f;
+            const float m2 = ((p0.y + p0.w) + (p1.y + p1.w)) + ((p2.y + p2.w) + (p3.y + p3.w));
+            const float dev = ln_sq4(p0.x - mean, p0.z - mean, p1.x - mean, p1.z - mean) +
+                              ln_sq4(p2.x - mean, p2.z - mean, p3.x - mean, p3.z - mean);
+            const float rstd = rsqrtf((m2 + (float)WCOLS * dev) * (1.0f / D) + eps);
+            amax[r] = 0.f;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                v[r][i].x = ln_apply(v[r][i].x, mean, rstd, sc[i].x, sh[i].x);
+                v[r][i].y = ln_apply(v[r][i].y, mean, rstd, sc[i].y, sh[i].y);
+                v[r][i].z = ln_apply(v[r][i].z, mean, rstd, sc[i].z, sh[i].z);
+                v[r][i].w = ln_apply(v[r][i].w, mean, rstd, sc[i].w, sh[i].w);
+                amax[r] = fmaxf(amax[r], fmaxf(fmaxf(fabsf(v[r][i].x), fabsf(v[r][i].y)), fmaxf(fabsf(v[r][i].z), fabsf(v[r][i].w))));
+                // pad rows stay exactly zero so downstream GEMM rows stay finite
+                *reinterpret_cast<uint2*>(orow + (i * 32 + lane) * 4) =
+                    valid ? make_uint2(pack_bf16(v[r][i].x, v[r][i].y), pack_bf16(v[r][i].z, v[r][i].w)) : make_uint2(0u, 0u);
+            }
+        }
+        if (out8) {   // per-token dynamic quantisation for the W8A8 GEMM paths (quantises the bf16-rounded values)
+            float* my_red8 = red8 + (it & 1) * R * 8;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int r = 0; r < R; ++r) amax[r] = fmaxf(amax[r], __shfl_xor_sync(0xffffffffu, amax[r], o));
+            if (lane < R) {
+                float mine = amax[0];
+#pragma unroll
+                for (int r = 1; r < R; ++r)
+                    if (lane == r) mine = amax[r];
+                my_red8[lane * 8 + warp] = mine;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const size_t row = (size_t)(gr.row0 + r);
+                uint8_t* qrow = out8 + row * D + warp * WCOLS;
+                const bool valid = r < gr.nvalid;
+                const float4 a0 = reinterpret_cast<const float4*>(my_red8 + r * 8)[0], a1 = reinterpret_cast<const float4*>(my_red8 + r * 8)[1];
+                float am = fmaxf(fmaxf(fmaxf(a0.x, a0.y), fmaxf(a0.z, a0.w)), fmaxf(fmaxf(a1.x, a1.y), fmaxf(a1.z, a1.w)));
+                am = __bfloat162float(__float2bfloat16(am));
+                const float qmax = qmode == 2 ? 127.f : 448.f;
+                const float scale = am > 0.f ? am / qmax : 1.f, inv_scale = 1.0f / scale;
+#pragma unroll
+                for (int i = 0; i < NW; ++i) {
+                    const float4 bq = make_float4(__bfloat162float(__float2bfloat16(v[r][i].x)), __bfloat162float(__float2bfloat16(v[r][i].y)),
+                                                  __bfloat162float(__float2bfloat16(v[r][i].z)), __bfloat162float(__float2bfloat16(v[r][i].w)));
+                    const uint32_t q4 = qmode == 2 ? quant_s8x4(bq.x, bq.y, bq.z, bq.w, scale, inv_scale)
+                                                   : quant_e4m3x4(bq.x, bq.y, bq.z, bq.w, inv_scale);
+                    *reinterpret_cast<uint32_t*>(qrow + (i * 32 + lane) * 4) = valid ? q4 : 0u;
+                }
+                if (threadIdx.x == 0) out_scale[row] = valid ? scale : 0.f;
+            }
+        }
+        ++it;
+        if (++st == STAGES) {
+            st = 0;
+            phase ^= 1;
+        }
+    }
+    // the last CTA to leave re-arms the group counter for the next launch (launches are serialised on one stream)
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&counters[1], 1) == (int)gridDim.x - 1) {
+            counters[0] = 0;
+            counters[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // K-mod / K-embed GEMV: y[b,n] = bias[n] + sum_k act(x[b,k]) W[n,k], W bf16 streamed once.
 // (img_mod/txt_mod = Sequential(SiLU, Linear) of all blocks in ONE launch, norm_out.linear,
@@ -491,7 +715,8 @@ extern "C" int qie_cfg_euler_step(const void* v_cond, const void* v_uncond, void
 
 namespace qie {
 int g_ln_threads = 128, g_ln_smem = 0;   // 128 threads (4 rows) per block measured best: 4350 GB/s vs 3700 at 256
-int g_ln_variant = 1;                    // 1 = streaming persistent kernel (default), 0 = one warp per row, grid over rows
+int g_ln_variant = 2;                    // 2 = CTA-row form where D is a multiple of 1024, else 1 (default); 1 = warp-per-row streaming
+                                         // ring; 0 = one warp per row, grid over rows
 }
 // experiment knobs (not part of the reference surface): 0 = adaLN threads per block, 1 = adaLN dynamic smem reservation
 extern int g_gemm_l2_hints, g_gemm_split_tail, g_gemm_group_m;   // gemm.cu
@@ -499,7 +724,7 @@ extern "C" int qie_tune(int key, int value) {
     if (key == 0 && (value == 64 || value == 128 || value == 256 || value == 512)) { qie::g_ln_threads = value; return QIE_OK; }
     if (key == 1 && value >= 0 && value <= 200 * 1024) { qie::g_ln_smem = value; return QIE_OK; }
     if (key == 2 && value >= 0 && value <= 3) { g_gemm_l2_hints = value; return QIE_OK; }
-    if (key == 3 && (value == 0 || value == 1)) { qie::g_ln_variant = value; return QIE_OK; }
+    if (key == 3 && value >= 0 && value <= 2) { qie::g_ln_variant = value; return QIE_OK; }
     if (key == 4 && value >= 0 && value <= 63) { g_gemm_split_tail = value; return QIE_OK; }
     if (key == 5 && value >= 0 && value <= 64) { g_gemm_group_m = value; return QIE_OK; }
     if (key == 7 && (value == 0 || value == 1)) { qie::g_pdl = value; return QIE_OK; }   // programmatic dependent launch
@@ -529,7 +754,43 @@ extern "C" int qie_ln_modulate(const float* x, const float* mod, long long mod_b
     const long long rows = (long long)seq->batch * (seq->img_pad + seq->txt_pad);
     // Several short waves instead of one: a dynamic-smem reservation caps the resident blocks per SM so that the stores of
     // one wave overlap the loads of the next (one warp per row, the whole row in registers).
-    if (g_ln_variant == 1 && D % 128 == 0 && (size_t)D * 4 * 16 + 256 <= 200 * 1024) {
+    if (g_ln_variant == 2 && D % 1024 == 0 && D <= 3072) {
+        // CTA-row form: the eight warps of a persistent CTA share every row, the modulation vectors stay in registers
+        qie::StreamScratch scr;
+        int rc0 = qie::stream_scratch((cudaStream_t)stream, &scr);
+        if (rc0) return rc0;
+        int* counters = scr.ln_counters;
+        cudaStream_t cst = (cudaStream_t)stream;
+#define QIE_LNC_CASE(NV)                                                                                             \
+    case NV: {                                                                                                       \
+        constexpr int R = 4, OCC = 2;      /* rows per group, CTAs per SM */                                         \
+        using CS = LnCtaSmem<NV, R, OCC>;                                                                            \
+        auto* kern = ln_mod_cta_kernel<NV, R, OCC>;                                                                  \
+        QIE_CONFIGURE_ONCE(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CS::TOTAL));      \
+        cudaLaunchConfig_t lcfg{};                                                                                   \
+        lcfg.gridDim = dim3((int)std::min<long long>((long long)sm_count() * OCC, rows / R));                        \
+        lcfg.blockDim = dim3(256);                                                                                   \
+        lcfg.dynamicSmemBytes = CS::TOTAL;                                                                           \
+        lcfg.stream = cst;                                                                                           \
+        cudaLaunchAttribute lattr[2];                                                                                \
+        lcfg.attrs = lattr;                                                                                          \
+        lcfg.numAttrs = launch_attrs(lattr, 1);                                                                      \
+        QIE_CUDA_OK(cudaLaunchKernelEx(&lcfg, kern, x, mod, mod_bstride, mod_sstride, shift_off, scale_off,          \
+                                       (__nv_bfloat16*)out, (uint8_t*)out8, out_scale, qmode, eps, *seq, counters)); \
+        break;                                                                                                       \
+    }
+        switch (D / 128) {
+            QIE_LNC_CASE(8)
+            QIE_LNC_CASE(16)
+            QIE_LNC_CASE(24)
+            default:
+                QIE_REQUIRE(false, QIE_ESHAPE, "qie_ln_modulate: unsupported D=%d", D);
+        }
+#undef QIE_LNC_CASE
+        QIE_LAUNCH_OK("ln_mod_cta_kernel");
+        return QIE_OK;
+    }
+    if (g_ln_variant >= 1 && D % 128 == 0 && (size_t)D * 4 * 16 + 256 <= 200 * 1024) {
         // streaming form: persistent CTAs, bulk-copy landing ring per warp, dynamic row hand-out
         qie::StreamScratch scr;
         int rc0 = qie::stream_scratch((cudaStream_t)stream, &scr);

@@ -39,24 +39,42 @@ def test_cfg_euler(with_uncond):
     assert K.rel_err(got, ref) <= 2 ** -8
 
 
-@pytest.mark.parametrize("D", [256, 3072])
-def test_ln_modulate(D):
-    s = K.seq(2, 200, 19)
+@pytest.fixture
+def ln_variant(request):
+    """qie_tune(3, v): 0 = one warp per row, 1 = warp-per-row streaming ring, 2 = CTA-row form (library default where D is a
+    multiple of 1024, else 1).  Restores the library default."""
+    lib = K.L.lib()
+    prev = lib.qie_tune_get(3)
+    K.L.check(lib.qie_tune(3, request.param))
+    yield request.param
+    K.L.check(lib.qie_tune(3, prev))
+
+
+@pytest.mark.parametrize("ln_variant", [0, 1, 2], indirect=True)
+@pytest.mark.parametrize("D,lens", [(256, [19, 19]), (3072, [19, 19]), (3072, [19, 7]), (1024, [130, 1])])
+def test_ln_modulate(D, lens, ln_variant):
+    """every adaLN kernel against torch's LayerNorm + modulate; 200 image rows (56 pad rows), text rows that end inside a group of
+    four rows of the CTA-row form, one text length per batch element"""
+    s = K.L.make_seq_ragged(200, lens) if lens[0] != lens[1] else K.seq(2, 200, lens[0])
     x = randn(K.rows(s), D, seed=4) * 3 + 0.5
     mod = randn(2, 2, 6 * D, seed=5, scale=0.5)
     got = K.ln_modulate(s, x, mod, 2 * 6 * D, 6 * D, 3 * D, 4 * D, D)
-    gi, gt = K.from_joint(s, got)
-    xi, xt = K.from_joint(s, x)
+    got3 = got.reshape(2, -1, D)
+    x3 = x.reshape(2, -1, D)
     for b in range(2):
-        for st, (g, xx) in enumerate(((gi, xi), (gt, xt))):
-            ref = F.layer_norm(xx[b], (D,), eps=1e-6) * (1 + mod[b, st, 4 * D:5 * D]) + mod[b, st, 3 * D:4 * D]
-            assert K.rel_err(g[b], ref) <= 2 ** -8
-    # pad rows are written as exact zeros
-    assert got.reshape(2, -1, D)[:, s.img_rows:s.img_pad].abs().max() == 0
+        for st, (r0, n) in enumerate(((0, s.img_rows), (s.img_pad, lens[b]))):
+            ref = F.layer_norm(x3[b, r0:r0 + n], (D,), eps=1e-6) * (1 + mod[b, st, 4 * D:5 * D]) + mod[b, st, 3 * D:4 * D]
+            assert K.rel_err(got3[b, r0:r0 + n], ref) <= 2 ** -8
+            # pad rows (behind the element's own length) are written as exact zeros
+            pad_end = s.img_pad if st == 0 else s.img_pad + s.txt_pad
+            assert got3[b, r0 + n:pad_end].abs().max() == 0
+    # a second launch on the same stream (row counters re-armed by the first) gives the same bits
+    assert torch.equal(K.ln_modulate(s, x, mod, 2 * 6 * D, 6 * D, 3 * D, 4 * D, D), got)
 
 
+@pytest.mark.parametrize("ln_variant", [1, 2], indirect=True)
 @pytest.mark.parametrize("qmode", [1, 2])
-def test_ln_modulate_fused_quantiser(qmode):
+def test_ln_modulate_fused_quantiser(qmode, ln_variant):
     """The adaLN kernel's 8-bit shadow output (per-token dynamic quantisation of the bf16-rounded rows, fused into the same pass):
     int8 = exactly torch.round(x / s) with s = amax / 127 (the restated Int8Linear activation quantiser, README.md:136-141; the kernel
     takes the reciprocal product and falls back to the true quotient next to a tie), e4m3 within its 3 mantissa bits."""

@@ -55,6 +55,7 @@ KNOBS = [
     ("GEMM raster band, m-units (tune 5)", tune(5), 0, [8, 16, 32]),
     ("GEMM TMA L2 hints (tune 2)", tune(2), 0, [1, 3]),
     ("GEMM tail: K split / N split (tune 4; default 17)", tune(4), 17, [0, 1, 16]),
+    ("adaLN kernel: 2 = CTA-row form (default), 1 = warp-per-row ring, 0 = one warp per row (tune 3)", tune(3), 2, [1, 0, 1]),
 ]
 if len(sys.argv) > 2:                     # python tools/instep_sweep.py 4 0,1 -> only these knobs
     KNOBS = [KNOBS[int(i)] for i in sys.argv[2].split(",")]
