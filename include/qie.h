@@ -344,7 +344,8 @@ int qie_gemm(const qie_gemm_args* args, const qie_seq* seq, void* stream);
 int qie_attn_fwd(const void* qkv, void* out, const qie_seq* seq, int num_heads, int variant, void* stream);
 /* LayerNorm(no affine, eps) + x*(1+scale)+shift; x fp32 [rows, D] -> out bf16 [rows, D].
  * shift/scale for (b, stream) at mod[b*mod_bstride + stream*mod_sstride + {shift_off,scale_off} + c].
- * if out8/out_scale non-NULL also emits e4m3 rows with per-row scale (for the FP8 GEMMs). */
+ * if out8/out_scale non-NULL also emits e4m3 / int8 rows with per-row scale (for the W8A8 GEMMs); `out` may then be NULL (the
+ * W8A8 forward reads the 8-bit rows only: a third of the kernel's bytes are not written). */
 int qie_ln_modulate(const float* x, const float* mod, long long mod_bstride, long long mod_sstride, int shift_off,
                     int scale_off, void* out, void* out8, float* out_scale, int qmode /* 1 e4m3, 2 int8 */, int D, float eps,
                     const qie_seq* seq, void* stream);

@@ -586,8 +586,9 @@ static int forward_impl(qie_handle* h, int phases, int layer, const void* hidden
                     "%d+%d tokens): call qie_set_peers for this one", h->peers.batch, h->peers.img_pad, h->peers.txt_pad,
                     h->peers.img_total, h->peers.txt_total);
     auto run_ln = [&](const float* mv, long long bs, long long ss, int sh, int sc, bool q8) -> int {
-        ProfScope ps(h, st, 2, valid_rows * D * 6.0);
-        return qie_ln_modulate(resid, mv, bs, ss, sh, sc, xm, q8 ? xm8 : nullptr, q8 ? xscale : nullptr, h->precision, D,
+        ProfScope ps(h, st, 2, valid_rows * D * (q8 ? 5.0 : 6.0));   // algorithmic bytes: fp32 row in, bf16 (or 8-bit) row out
+        // W8A8 modes: the GEMMs that follow read the 8-bit shadow only, the bf16 rows are not written
+        return qie_ln_modulate(resid, mv, bs, ss, sh, sc, q8 ? nullptr : xm, q8 ? xm8 : nullptr, q8 ? xscale : nullptr, h->precision, D,
                                1e-6f, seq, st);
     };
 

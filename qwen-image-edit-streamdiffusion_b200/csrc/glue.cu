@@ -82,8 +82,10 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ x
     const bool valid = local < (stream ? seq.txt_rows_b[b] : seq.img_rows);
     __nv_bfloat16* orow = out + row * D;
     if (!valid) {   // keep pad rows exactly zero so downstream GEMM rows stay finite
+        if (out) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) *reinterpret_cast<uint2*>(orow + (i * 32 + lane) * 4) = make_uint2(0u, 0u);
+            for (int i = 0; i < NV; ++i) *reinterpret_cast<uint2*>(orow + (i * 32 + lane) * 4) = make_uint2(0u, 0u);
+        }
         if (out8) {
 #pragma unroll
             for (int i = 0; i < NV; ++i) *reinterpret_cast<uint32_t*>(out8 + row * D + (i * 32 + lane) * 4) = 0u;
@@ -119,8 +121,9 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ x
         v[i].z = ln_apply(v[i].z, mean, rstd, c.z, h.z);
         v[i].w = ln_apply(v[i].w, mean, rstd, c.w, h.w);
         amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
-        *reinterpret_cast<uint2*>(orow + (i * 32 + lane) * 4) =
-            make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+        if (out)
+            *reinterpret_cast<uint2*>(orow + (i * 32 + lane) * 4) =
+                make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
     }
     if (out8) {   // per-token dynamic quantisation for the W8A8 GEMM paths (quantises the bf16-rounded values)
         amax = warp_max(amax);
@@ -195,8 +198,10 @@ __global__ void __launch_bounds__(256, 1) ln_mod_stream_kernel(const float* __re
         const int stream = r >= seq.img_pad ? 1 : 0;
         __nv_bfloat16* orow = out + (size_t)row * D;
         if (!is_valid(row)) {   // keep pad rows exactly zero so downstream GEMM rows stay finite
+            if (out) {
 #pragma unroll
-            for (int i = 0; i < NV; ++i) *reinterpret_cast<uint2*>(orow + (i * 32 + lane) * 4) = make_uint2(0u, 0u);
+                for (int i = 0; i < NV; ++i) *reinterpret_cast<uint2*>(orow + (i * 32 + lane) * 4) = make_uint2(0u, 0u);
+            }
             if (out8) {
 #pragma unroll
                 for (int i = 0; i < NV; ++i) *reinterpret_cast<uint32_t*>(out8 + (size_t)row * D + (i * 32 + lane) * 4) = 0u;
@@ -233,8 +238,9 @@ __global__ void __launch_bounds__(256, 1) ln_mod_stream_kernel(const float* __re
                 v[i].z = ln_apply(v[i].z, mean, rstd, c.z, h.z);
                 v[i].w = ln_apply(v[i].w, mean, rstd, c.w, h.w);
                 amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
-                *reinterpret_cast<uint2*>(orow + (i * 32 + lane) * 4) =
-                    make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+                if (out)
+                    *reinterpret_cast<uint2*>(orow + (i * 32 + lane) * 4) =
+                        make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
             }
             if (out8) {
                 amax = warp_max(amax);
@@ -435,9 +441,11 @@ __global__ void __launch_bounds__(256, OCC) ln_mod_cta_kernel(const float* __res
                 v[r][i].z = ln_apply(v[r][i].z, mean, rstd, sc[i].z, sh[i].z);
                 v[r][i].w = ln_apply(v[r][i].w, mean, rstd, sc[i].w, sh[i].w);
                 amax[r] = fmaxf(amax[r], fmaxf(fmaxf(fabsf(v[r][i].x), fabsf(v[r][i].y)), fmaxf(fabsf(v[r][i].z), fabsf(v[r][i].w))));
-                // pad rows stay exactly zero so downstream GEMM rows stay finite
-                *reinterpret_cast<uint2*>(orow + (i * 32 + lane) * 4) =
-                    valid ? make_uint2(pack_bf16(v[r][i].x, v[r][i].y), pack_bf16(v[r][i].z, v[r][i].w)) : make_uint2(0u, 0u);
+                // pad rows stay exactly zero so downstream GEMM rows stay finite; the W8A8 forward takes the 8-bit shadow only
+                // (out == nullptr: a third of the kernel's bytes are not written)
+                if (out)
+                    *reinterpret_cast<uint2*>(orow + (i * 32 + lane) * 4) =
+                        valid ? make_uint2(pack_bf16(v[r][i].x, v[r][i].y), pack_bf16(v[r][i].z, v[r][i].w)) : make_uint2(0u, 0u);
             }
         }
         if (out8) {   // per-token dynamic quantisation for the W8A8 GEMM paths (quantises the bf16-rounded values)
@@ -749,7 +757,7 @@ extern "C" int qie_tune_get(int key) {
 extern "C" int qie_ln_modulate(const float* x, const float* mod, long long mod_bstride, long long mod_sstride,
                                int shift_off, int scale_off, void* out, void* out8, float* out_scale, int qmode, int D,
                                float eps, const qie_seq* seq, void* stream) {
-    QIE_REQUIRE(x && mod && out && seq, QIE_EINVAL, "qie_ln_modulate: null pointer");
+    QIE_REQUIRE(x && mod && (out || out8) && seq, QIE_EINVAL, "qie_ln_modulate: null pointer");
     QIE_REQUIRE((out8 == nullptr) == (out_scale == nullptr), QIE_EINVAL, "qie_ln_modulate: out8/out_scale mismatch");
     const long long rows = (long long)seq->batch * (seq->img_pad + seq->txt_pad);
     // Several short waves instead of one: a dynamic-smem reservation caps the resident blocks per SM so that the stores of

@@ -65,8 +65,8 @@ def attn(s, qkv, heads, variant=0):
     return out
 
 
-def ln_modulate(s, x, mod, bstride, sstride, shift_off, scale_off, D, fp8=False, qmode=1):
-    out = torch.empty(x.shape[0], D, dtype=torch.bfloat16, device=x.device)
+def ln_modulate(s, x, mod, bstride, sstride, shift_off, scale_off, D, fp8=False, qmode=1, want_bf16=True):
+    out = torch.empty(x.shape[0], D, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
     out8 = torch.empty(x.shape[0], D, dtype=torch.uint8, device=x.device) if fp8 else None
     sc = torch.empty(x.shape[0], dtype=torch.float32, device=x.device) if fp8 else None
     L.check(L.lib().qie_ln_modulate(L.ptr(x), L.ptr(mod), bstride, sstride, shift_off, scale_off, L.ptr(out),

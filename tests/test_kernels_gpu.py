@@ -99,6 +99,9 @@ def test_ln_modulate_fused_quantiser(qmode, ln_variant):
         dq = out8[valid].view(torch.float8_e4m3fn).float() * scale
         assert ((dq - xf).abs().amax(dim=1) <= amax.squeeze(1) * 2 ** -4 + 1e-6).all()
     assert out8[~valid].view(torch.int8).abs().max() == 0 and sc[~valid].abs().max() == 0
+    # the W8A8 forward asks for the 8-bit shadow only (out == NULL): same bytes, same scales
+    _, only8, only_sc = K.ln_modulate(s, x, mod, 2 * 6 * D, 6 * D, 0, D, D, fp8=True, qmode=qmode, want_bf16=False)
+    assert torch.equal(only8, out8) and torch.equal(only_sc, sc)
 
 
 @pytest.mark.parametrize("B,N,K_,act", [(1, 1000, 256, 0), (2, 6 * 3072, 3072, 1), (8, 514, 512, 1)])

@@ -37,6 +37,8 @@ for B in (1, 4):
             for qm, name in ((1, "e4m3"), (2, "int8")):
                 ms = bench(lambda: K.ln_modulate(s, xs[0], mod, 12 * D, 6 * D, 0, D, D, fp8=True, qmode=qm))
                 print(f"B={B} ln variant {v} + {name} shadow: {ms*1e3:.1f} us", flush=True)
+                ms = bench(lambda: K.ln_modulate(s, xs[0], mod, 12 * D, 6 * D, 0, D, D, fp8=True, qmode=qm, want_bf16=False))
+                print(f"B={B} ln variant {v}, {name} rows only (the W8A8 forward): {ms*1e3:.1f} us", flush=True)
     print(f"B={B} variant 2 vs 1: max |diff| {(outs[2] - outs[1]).abs().max().item():.3e} "
           f"(bf16 ulp at max |y| = {outs[1].abs().max().item() * 2 ** -8:.3e}), rows differing "
           f"{((outs[2] != outs[1]).any(dim=1)).sum().item()} of {outs[1].shape[0]}", flush=True)
