@@ -142,7 +142,8 @@ int qie_attn_layer_variant(const qie_handle* h, int layer);
 #define QIE_PROFILE_CLASSES 6
 unsigned long long qie_launch_count(void);
 /* process-wide experiment / launch knobs: 0 adaLN threads/block, 1 adaLN smem reservation, 2 GEMM L2 hints (bit 0 weights
- * evict-last, bit 1 activations evict-first), 3 adaLN kernel form, 4 GEMM split-K tail, 5 GEMM raster band,
+ * evict-last, bit 1 activations evict-first), 3 adaLN kernel form (2 = CTA rows where D % 1024 == 0 [default], 1 = warp-per-row
+ * streaming ring, 0 = one warp per row), 4 GEMM split-K tail, 5 GEMM raster band,
  * 7 programmatic dependent launch of the GEMM / attention / adaLN / barrier kernels (1 on = default, 0 off).
  * qie_tune_get returns the current value (>= 0) or QIE_EINVAL for an unknown key. */
 int qie_tune(int key, int value);
