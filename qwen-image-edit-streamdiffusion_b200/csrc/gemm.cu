@@ -858,8 +858,10 @@ extern "C" int qie_gemm(const qie_gemm_args* g, const qie_seq* seq, void* stream
     {
         const int units = sm_count() / cg;
         const int tail = tiles % units, kblocks = (g->K + bk - 1) / bk;
+        // (the eight-epilogue-warp instantiations — 8-bit operands, K < 8192 — take the N split below: their K split is short-K
+        // by construction and has no GPU test)
         if ((g_gemm_split_tail & 9) && cg == 2 && bn == 256 && tiles > units && tail > 0 && g->epilogue != QIE_EPI_QKV_NORM_ROPE &&
-            g->fp8 != 2) {
+            g->fp8 != 2 && !(g->fp8 && g->K < 8192)) {
             // the gain is (1 - 1/split) of a tile, the reduction costs a fixed few microseconds: worth it for long-K tiles only
             // (mode 1), or everywhere (mode 8 | 1, experiments / tests)
             int split = units / tail;
