@@ -72,9 +72,26 @@ def test_attention_kernel_keeps_p_in_tmem_and_uses_packed_math(sass):
         assert "HMMA" not in text.replace("UTCHMMA", ""), name
 
 
-def test_adaln_stream_kernel_uses_bulk_copies_and_pdl_pair_is_present(sass):
-    ln = kernels(sass, "ln_mod_stream_kernel")
-    assert ln and all("UBLKCP" in t for t in ln.values())
-    for needle in ("ln_mod_stream_kernel", "gemm_kernel", "attn_pair_kernel"):
+def test_adaln_kernels_use_bulk_copies_and_pdl_pair_is_present(sass):
+    for needle in ("ln_mod_cta_kernel", "ln_mod_stream_kernel"):      # CTA-row form (default) and the warp-per-row ring
+        ln = kernels(sass, needle)
+        assert ln and all("UBLKCP" in t for t in ln.values()), needle
+    for needle in ("ln_mod_cta_kernel", "ln_mod_stream_kernel", "gemm_kernel", "attn_pair_kernel"):
         for name, text in kernels(sass, needle).items():
             assert "PREEXIT" in text and "ACQBULK" in text, name      # griddepcontrol.launch_dependents / .wait
+
+
+def test_eight_epilogue_warp_gemms_exist_and_do_not_spill_in_their_chunk_loop(sass):
+    """The short-K 8-bit GEMMs run eight epilogue warps (template parameter EW = 8: ...ILi256E<EPI><QT>ELi2ELi8E).  Ten warps cap
+    them at 168 registers, and spill reloads miss the few KB of L1 beside the operand ring (the ncu finding of
+    profiles/r02_q8_qkv_ncu_stalls.txt: eight dependent LDL per 32-column chunk), so the spill traffic of these kernels is held
+    to the handful of per-tile values ptxas parks today; the bf16 kernels keep four epilogue warps."""
+    gemm = kernels(sass, "gemm_kernel")
+    ew8 = {n: t for n, t in gemm.items() if n.endswith("ELi8EEEv14CUtensorMap_stS1_S1_NS_7GemmDevE")}
+    assert len(ew8) == 20                                                # BN 256 x 5 epilogues x {e4m3, int8} x {single CTA, pair}
+    for name, text in ew8.items():
+        assert re.search(r"UTC[QI]MMA", text) and "UTCHMMA" not in text, name       # 8-bit operand types only
+        assert len(re.findall(r"\bLDL", text)) <= 20, (name, len(re.findall(r"\bLDL", text)))
+    for name, text in gemm.items():
+        if "UTCHMMA" in text:                                           # bf16: four epilogue warps, at most the 3 reloads of today
+            assert "ELi4EEEv14CUtensorMap" in name and len(re.findall(r"\bLDL", text)) <= 4, name
