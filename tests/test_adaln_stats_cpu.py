@@ -52,7 +52,7 @@ def test_merged_statistics_equal_two_pass_variance(D, offset, spread):
         assert abs(float(one_pass) - var64) > 20 * merged_err
 
 
-@settings(max_examples=60, deadline=None, derandomize=True)
+@settings(max_examples=100, deadline=None, derandomize=True)
 @given(st.integers(0, 2 ** 31 - 1), st.floats(-50, 50), st.floats(0.01, 20), st.integers(0, 7), st.floats(0, 40))
 def test_merged_statistics_property(seed, offset, spread, hot_slice, slice_shift):
     """slices with different means (one warp's columns shifted): the between-slice term of the merge carries the variance"""
@@ -63,4 +63,6 @@ def test_merged_statistics_property(seed, offset, spread, hot_slice, slice_shift
     mean, rstd = merged_stats(x)
     m64, r64 = two_pass_f64(x)
     assert abs(float(mean) - m64) <= 1e-5 * (abs(m64) + spread + slice_shift)
-    assert abs(float(rstd) - r64) <= 2e-5 * r64
+    # fp32 slice means carry ~1e-7 relative error of the OFFSET; where the spread is 1e-3 of the offset that is a few 1e-5 of rstd
+    # (first-order in the between-slice term) — still 20x under half a bf16 ulp (2^-9) of the stored output
+    assert abs(float(rstd) - r64) <= 1e-4 * r64
