@@ -53,7 +53,7 @@ int gemv_strided(const float* x, const void* w, const float* bias, float* y, int
 // QIE_ECUDA (with the message set) once a peer barrier of this process has timed out, else QIE_OK; `clear` re-arms the flag
 int peer_sticky_error(bool clear = false);
 
-// Mutable kernel scratch (row counters of ln_mod_stream_kernel, split-K tail partials and tickets of gemm_kernel) is one set
+// Mutable kernel scratch (row / group counters of the persistent adaLN kernels, split-K tail partials and tickets of gemm_kernel) is one set
 // per (device, stream): launches on one stream are serialised, launches on different streams never share a set.  The sets of a
 // device come from a fixed pool allocated by the first qie_create on that device, so handing one to a new stream allocates
 // nothing (qie_forward stays CUDA-graph capturable); the pool is exhausted after QIE_SCRATCH_SETS distinct streams per device.

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ x
     }
 }
 
-// K-lnmod, streaming form (default): persistent, one CTA per SM, 8 warps.  Every warp owns a two-row landing ring in shared
+// K-lnmod, streaming form (qie_tune(3, 1); the default for D that is not a multiple of 1024): persistent, one CTA per SM, 8 warps.  Every warp owns a two-row landing ring in shared
 // memory that 1-D bulk copies (cp.async.bulk -> UBLKCP, completion on a warp-private mbarrier) keep filled one row ahead, so
 // HBM reads stay in flight while the warp normalises and stores the previous row; rows are handed out by an atomic counter
 // (8448 rows over 1184 warps would otherwise quantise to 8 vs 7 rows per warp).  Same arithmetic as ln_mod_kernel.
