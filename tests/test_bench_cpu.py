@@ -53,6 +53,16 @@ def test_cuda_arm_refuses_to_run_without_a_device(bench, monkeypatch):
     assert "no CPU fallback" in str(e.value)
 
 
+def test_eight_bit_peak_probe_reports_absence_instead_of_guessing(bench):
+    """The W8A8 lines hold their GEMMs against a cuBLASLt e4m3 / int8 peak measured in the same run; where that cannot be
+    measured (no CUDA device here) the probe returns None and the line says it falls back to 2 x the bf16 peak."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    assert bench.q8_library_peak("fp8", "cuda:0", seconds=0.01) is None
+    assert bench.q8_library_peak("int8", "cuda:0", seconds=0.01) is None
+
+
 def _run_bench(args, env_extra):
     import os
     import subprocess
