@@ -545,19 +545,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             // the four TMEM loads of the head are pipelined two deep (chunk cc + 1 in flight while cc is squared)
                             // (EW = 8: one buffer — the other warp of the scheduler covers the load, 32 registers fewer)
                             float ss = 0.f;
-                            uint32_t ra[32], rb[EW == 8 ? 1 : 32];
-                            tmem_ld32(t_addr + c * 32, ra);
-#pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) {
-                                uint32_t(&r)[32] = (EW == 4 && (cc & 1)) ? reinterpret_cast<uint32_t(&)[32]>(rb) : ra;
-                                if constexpr (EW == 8) {
-                                    if (cc > 0) tmem_ld32(t_addr + (c + cc) * 32, ra);
-                                }
-                                tmem_ld_wait();
-                                if constexpr (EW == 4) {
-                                    uint32_t(&rn)[32] = (cc & 1) ? ra : reinterpret_cast<uint32_t(&)[32]>(rb);
-                                    if (cc < 3) tmem_ld32(t_addr + (c + cc + 1) * 32, rn);
-                                }
+                            auto square_chunk = [&](const uint32_t(&r)[32], int cc) {      // ss += |acc * scales + bias|^2 of chunk c + cc
 #pragma unroll
                                 for (int i = 0; i < 32; i += 4) {
                                     const float4 bv = *reinterpret_cast<const float4*>(cbias + (c + cc) * 32 + i);
@@ -571,6 +559,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                     const float a2 = accf(r[i + 2]) * ws.z + bv.z;
                                     const float a3 = accf(r[i + 3]) * ws.w + bv.w;
                                     ss += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+                                }
+                            };
+                            if constexpr (EW == 8) {
+                                uint32_t ra[32];
+#pragma unroll
+                                for (int cc = 0; cc < 4; ++cc) {
+                                    tmem_ld32(t_addr + (c + cc) * 32, ra);
+                                    tmem_ld_wait();
+                                    square_chunk(ra, cc);
+                                }
+                            } else {
+                                uint32_t ra[32], rb[32];
+                                tmem_ld32(t_addr + c * 32, ra);
+#pragma unroll
+                                for (int cc = 0; cc < 4; ++cc) {
+                                    uint32_t(&r)[32] = (cc & 1) ? rb : ra;
+                                    uint32_t(&rn)[32] = (cc & 1) ? ra : rb;
+                                    tmem_ld_wait();
+                                    if (cc < 3) tmem_ld32(t_addr + (c + cc + 1) * 32, rn);
+                                    square_chunk(r, cc);
                                 }
                             }
                             rinv_head = rsqrtf(ss * (1.0f / 128.0f) + 1e-6f);
