@@ -306,6 +306,23 @@ def strong_mode(world):
     return None, 0, 0
 
 
+def strong_check(rec: dict, sp: int) -> dict:
+    """Verdict on a multi-GPU `strong` record (sp = 1: CFG pair only, > 1: sequence-parallel ranks per branch).
+    Two levels.  `parity_tolerance` (1e-2 for the sequence-parallel modes, bit-identical for the CFG pair) is what the partition
+    is held to and `parity_ok` says whether it was met.  The run FAILS (exit 1) on a wrong partition: a CFG pair that is not
+    bit-identical, a barrier time-out, NaN, a final-latent cosine under 0.999, or a step-0 velocity beyond the north star's own
+    bound for a bf16 forward against the reference (2e-2) — the sequence-parallel forward differs from the single-GPU one only by
+    the fp32 summation order of the GEMM tail tiles (a few bf16 ulps after 60 blocks: 7.0e-3 on every build measured so far),
+    so a value between the two is reported, not fatal."""
+    rec["parity_ok"] = bool(rec["parity_err"] <= rec["parity_tolerance"])
+    rec["parity_hard_limit"] = 0.0 if sp == 1 else 2e-2
+    bad = (rec["parity_err"] > rec["parity_hard_limit"] or rec["barrier_timeouts"] != 0 or not (rec["parity_err"] == rec["parity_err"])
+           or rec["final_latent_cosine"] < 0.999 or (sp == 1 and rec["final_latent_max_rel_err"] != 0.0))
+    if bad:
+        rec["failed"] = "parity or barrier check failed"
+    return rec
+
+
 def strong_leg(args, model, dev, world, rank, timed):
     """ONE edited frame with true CFG (2 steps x (cond + uncond) = 4 forwards) over all N GPUs: CFG pair at N = 2, CFG pair x
     fused (peer-memory) Ulysses at N = 4 / 8.  Every rank first runs the same frame alone (the N = 1 time measured on this box
@@ -398,19 +415,7 @@ def strong_leg(args, model, dev, world, rank, timed):
                                        "+ the CFG-pair velocity all-gather)", "profile": prof})
     if hasattr(runner, "close"):
         runner.close()
-    # Two levels.  `parity_tolerance` (1e-2 for the sequence-parallel modes, bit-identical for the CFG pair) is what the partition
-    # is held to and `parity_ok` says whether it was met.  The run FAILS (exit 1) on a wrong partition: a CFG pair that is not
-    # bit-identical, a barrier time-out, NaN, a final-latent cosine under 0.999, or a step-0 velocity beyond the north star's own
-    # bound for a bf16 forward against the reference (2e-2) — the sequence-parallel forward differs from the single-GPU one only by
-    # the fp32 summation order of the GEMM tail tiles (a few bf16 ulps after 60 blocks: 7.0e-3 on every build measured so far),
-    # so a value between the two is reported, not fatal.
-    rec["parity_ok"] = bool(rec["parity_err"] <= rec["parity_tolerance"])
-    rec["parity_hard_limit"] = 0.0 if sp == 1 else 2e-2
-    bad = (rec["parity_err"] > rec["parity_hard_limit"] or rec["barrier_timeouts"] != 0 or not (rec["parity_err"] == rec["parity_err"])
-           or rec["final_latent_cosine"] < 0.999 or (sp == 1 and rec["final_latent_max_rel_err"] != 0.0))
-    if bad:
-        rec["failed"] = "parity or barrier check failed"
-    return rec
+    return strong_check(rec, sp)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -63,6 +63,24 @@ def test_eight_bit_peak_probe_reports_absence_instead_of_guessing(bench):
     assert bench.q8_library_peak("int8", "cuda:0", seconds=0.01) is None
 
 
+def test_strong_record_verdict(bench):
+    """bench.strong_check: the sequence-parallel frame is held to 1e-2 (`parity_ok`) and fails the run beyond the north star's
+    2e-2, on a barrier time-out, a NaN or a cosine under 0.999; the CFG pair must be bit-identical."""
+    def rec(err, cos=0.9999, timeouts=0, final=0.0, tol=1e-2):
+        return {"parity_err": err, "parity_tolerance": tol, "barrier_timeouts": timeouts, "final_latent_cosine": cos,
+                "final_latent_max_rel_err": final}
+    ok = bench.strong_check(rec(7.0e-3, final=6e-3), sp=4)
+    assert ok["parity_ok"] and "failed" not in ok and ok["parity_hard_limit"] == 2e-2
+    soft = bench.strong_check(rec(1.3e-2, final=9e-3), sp=4)
+    assert not soft["parity_ok"] and "failed" not in soft
+    for bad in (rec(2.5e-2), rec(float("nan")), rec(5e-3, timeouts=1), rec(5e-3, cos=0.99)):
+        assert "failed" in bench.strong_check(bad, sp=2)
+    pair = bench.strong_check(rec(0.0, cos=1.0, final=0.0, tol=0.0), sp=1)
+    assert pair["parity_ok"] and "failed" not in pair
+    assert "failed" in bench.strong_check(rec(1e-6, cos=1.0, final=0.0, tol=0.0), sp=1)       # a CFG pair that is not bit-identical
+    assert "failed" in bench.strong_check(rec(0.0, cos=1.0, final=1e-6, tol=0.0), sp=1)
+
+
 def _run_bench(args, env_extra):
     import os
     import subprocess
